@@ -1,0 +1,127 @@
+/*
+ * rlvd_b200.h — C ABI of the B200-native candidate-hop scoring path of RLVacDiffSim.
+ *
+ * One shared library (librlvd_b200.so, sm_100a only) replaces the device work the reference reaches
+ * through the un-vendored `rgnn` package at
+ *     rlsim/drl/simulator.py:56     rl_q = self.model(batch, q_params=self.q_params)["rl_q"]
+ *     rlsim/drl/trainer.py:112,166  model(batch, q_params=self.q_params)["rl_q"]
+ *     rlsim/cli/scripts/estimate_time.py:58   model(batch, inference=True)["time"]
+ * All pointers are plain; `d_` arguments are device pointers on the engine's GPU, `h_` arguments are host
+ * pointers.  `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Every entry point
+ * returns 0 on success, non-zero on failure with the message available from rlvd_last_error().
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef RLVD_B200_H
+#define RLVD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLVD_ABI_VERSION 1
+#define RLVD_F 128          /* hidden channels of the bundled painn (hyper_parameters.hidden_channels) */
+#define RLVD_NRBF 20        /* n_rbf */
+#define RLVD_NLAYER 3       /* n_interactions */
+
+typedef struct rlvd_engine rlvd_engine;
+
+/* activation codes for the head MLPs (HeadSpec in oracle/painn_oracle.py) */
+enum { RLVD_ACT_SILU = 0, RLVD_ACT_RELU = 1, RLVD_ACT_TANH = 2, RLVD_ACT_LEAKY_RELU = 3 };
+/* the two extra Q_output inputs */
+enum { RLVD_QX_KT_X10 = 0, RLVD_QX_DELTA_E = 1 };
+
+/* q_params of `model(batch, q_params)` (simulator.py:46, configs/*.toml [model.params]) plus the
+ * swappable head assumptions of SURVEY.md Appendix C.7. */
+typedef struct rlvd_q_params {
+    float alpha;
+    float beta;
+    int32_t dqn;                 /* bool */
+    float temperature;           /* K; used when d_temperature == NULL */
+    int32_t delta_e_standardised;/* 0: 33rd head input is delta_e in eV; 1: (delta_e-mean)/std */
+    int32_t painn_head_act;      /* RLVD_ACT_* for energy_output / reaction_representation / reaction_output */
+    int32_t dqn_head_act;        /* RLVD_ACT_* for Q_emb / Q_output */
+    int32_t q_extra[2];          /* RLVD_QX_* */
+    float mean_barrier, std_barrier, mean_freq, std_freq, mean_delta_e, std_delta_e;
+} rlvd_q_params;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+int  rlvd_abi_version(void);
+const char* rlvd_last_error(void);
+/* Creates an engine bound to CUDA device `device`.  Fails if the device is not compute capability 10.x. */
+int  rlvd_engine_create(int device, rlvd_engine** out);
+void rlvd_engine_destroy(rlvd_engine* e);
+
+/* ---- weights: `registry.get_model_class("dqn_v2").load(path)` (rlsim/drl/deploy.py:18) ----------- */
+/* Uploads one fp32 tensor of the checkpoint's state_dict under its checkpoint name, e.g.
+ * "reaction_model.representation.filter_net.weight".  int64 `elem_lookup` is passed as int32. */
+int  rlvd_set_weight(rlvd_engine* e, const char* name, const void* h_data, int64_t numel, int32_t is_int32);
+/* Checks that every tensor of SURVEY.md Appendix A is present with the right size and builds the
+ * kernel-side layouts (transposed weights, per-layer filter slices). */
+int  rlvd_finalize_weights(rlvd_engine* e);
+
+/* ---- K1: periodic radius graph → receiver-sorted CSR (replaces torch_cluster.radius_graph + minimum
+ *      image inside rgnn) ------------------------------------------------------- */
+/* n_struct disjoint structures; d_node_ptr[n_struct+1]; d_pos[M,3]; d_cell/d_inv_cell[n_struct,3,3]
+ * (row-vector cells, inverse = fp32 image of the fp64 inverse); d_img_range[n_struct,3] extra periodic
+ * images to scan per axis (0 for cells with heights >= 2*cutoff).
+ * Phase 1 writes d_row_ptr[M+1] (global edge offsets), d_node_struct[M] and the total edge count to
+ * d_n_edges[0] (int64).  Phase 2 fills d_col[E] (global sender index, ascending within a row) and
+ * d_shift[E,3] (int8).  Edge order is (receiver, sender, Sx, Sy, Sz) ascending. */
+int  rlvd_radius_graph_count(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes,
+                             const int32_t* d_node_ptr, const float* d_pos, const float* d_cell,
+                             const float* d_inv_cell, const int32_t* d_img_range, float cutoff,
+                             int32_t* d_row_ptr, int32_t* d_node_struct, int64_t* d_n_edges);
+int  rlvd_radius_graph_fill(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes,
+                            const int32_t* d_node_ptr, const float* d_pos, const float* d_cell,
+                            const float* d_inv_cell, const int32_t* d_img_range, float cutoff,
+                            const int32_t* d_row_ptr, int64_t edge_capacity,
+                            int32_t* d_col, int8_t* d_shift);
+
+/* ---- K2..K4: PaiNN representation (R2..R6) on a disjoint-union batch ---------------------------- */
+/* d_Z[M] atomic numbers (int32).  Output d_q[M,128] fp32 scalar features after 3 interaction+mixing
+ * blocks.  d_mu (optional, may be NULL) receives the vector features [M,3,128]. */
+int  rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes,
+                               int64_t n_edges, const int32_t* d_Z, const float* d_pos,
+                               const float* d_cell, const int32_t* d_node_struct,
+                               const int32_t* d_row_ptr, const int32_t* d_col, const int8_t* d_shift,
+                               float* d_q, float* d_mu);
+
+/* ---- K5: per-action readout (H1..H4) ------------------------------------------------------------ */
+/* n_react reaction graphs; graph g pairs the structure d_react_struct[g] (reactant) with
+ * d_prod_struct[g] (product) of the batch the representation ran on (same atom count, same species).
+ * Outputs (each [n_react], any may be NULL): rl_q, q0, q1, delta_e, E_R, E_P. */
+int  rlvd_reaction_readout(rlvd_engine* e, void* stream, int32_t n_react, int32_t n_nodes,
+                           const int32_t* d_node_ptr, const int32_t* d_react_struct,
+                           const int32_t* d_prod_struct, const int32_t* d_Z, const float* d_q,
+                           const rlvd_q_params* qp, const float* d_temperature,
+                           float* d_rl_q, float* d_q0, float* d_q1, float* d_delta_e,
+                           float* d_E_R, float* d_E_P);
+
+/* ---- whole path from HOST buffers (the call `model(batch, q_params)` makes after `batch_to`) ---- */
+/* n_struct structures (h_node_ptr, h_Z, h_pos, h_cell, h_inv_cell, h_img_range), n_react reaction
+ * graphs pairing them; copies inputs H2D, runs K1..K5 on `stream`, copies rl_q/q0/q1/delta_e/E_R/E_P
+ * (each [n_react], NULL to skip) back and synchronises the stream.  Host buffers should be pinned. */
+int  rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes,
+                               const int32_t* h_node_ptr, const int32_t* h_Z, const float* h_pos,
+                               const float* h_cell, const float* h_inv_cell, const int32_t* h_img_range,
+                               float cutoff, int32_t n_react, const int32_t* h_react_struct,
+                               const int32_t* h_prod_struct, const rlvd_q_params* qp,
+                               const float* h_temperature,
+                               float* h_rl_q, float* h_q0, float* h_q1, float* h_delta_e,
+                               float* h_E_R, float* h_E_P, int64_t* h_n_edges);
+
+/* ---- introspection ------------------------------------------------------------------------------ */
+/* Number of kernels this library has launched on the engine since creation (bench.py "gpu_launches"). */
+int64_t rlvd_launch_count(const rlvd_engine* e);
+/* Event-timed milliseconds spent in the named kernel family since the last reset
+ * ("neighbor", "edge", "node", "readout"); timing is off unless enabled. */
+int  rlvd_profile_enable(rlvd_engine* e, int32_t on);
+int  rlvd_profile_read(rlvd_engine* e, const char* family, double* ms_total, int64_t* launches);
+int  rlvd_profile_reset(rlvd_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLVD_B200_H */

@@ -1,0 +1,160 @@
+// Shared declarations for librlvd_b200.so (sm_100a).  See include/rlvd_b200.h for the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rlvd_b200.h"
+
+namespace rlvd {
+
+constexpr int F = RLVD_F;          // 128 hidden channels
+constexpr int NRBF = RLVD_NRBF;    // 20 Bessel functions
+constexpr int NLAYER = RLVD_NLAYER;
+constexpr int GEOM = 24;           // per-edge geometry record: 20 x phi*fcut, fcut, dir.xyz
+
+void set_error(const char* fmt, ...);
+
+#define RLVD_CUDA(call)                                                                  \
+    do {                                                                                 \
+        cudaError_t err__ = (call);                                                      \
+        if (err__ != cudaSuccess) {                                                      \
+            rlvd::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                 \
+                            cudaGetErrorString(err__));                                  \
+            return 1;                                                                    \
+        }                                                                                \
+    } while (0)
+
+#define RLVD_CHECK(cond, ...)                                                            \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            rlvd::set_error(__VA_ARGS__);                                                \
+            return 1;                                                                    \
+        }                                                                                \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Tensor {
+    void* d = nullptr;
+    int64_t numel = 0;
+    bool is_int = false;
+};
+
+enum Family { FAM_NEIGHBOR = 0, FAM_EDGE = 1, FAM_NODE = 2, FAM_READOUT = 3, FAM_COUNT = 4 };
+
+struct ProfSpan {
+    int family;
+    cudaEvent_t a, b;
+};
+
+// Kernel-side view of the checkpoint (all device pointers, fp32 unless noted).
+struct Weights {
+    const float* emb = nullptr;                 // [100,128]
+    const float* freqs = nullptr;               // [20]
+    const float* filt_T = nullptr;              // [L][21][384]  (k<20: weight^T, k=20: bias)
+    const float* inter_w0T[NLAYER] = {};        // [128][128]   (in-major: Wt[k][n])
+    const float* inter_b0[NLAYER] = {};
+    const float* inter_w3T[NLAYER] = {};        // [128][384]
+    const float* inter_b3[NLAYER] = {};
+    const float* mix_wT[NLAYER] = {};           // [128][256]
+    const float* intra_w0T[NLAYER] = {};        // [256][128]
+    const float* intra_b0[NLAYER] = {};
+    const float* intra_w3T[NLAYER] = {};        // [128][384]
+    const float* intra_b3[NLAYER] = {};
+    const float* en_w0T = nullptr;              // [128][64]
+    const float* en_b0 = nullptr;
+    const float* en_w3 = nullptr;               // [64]
+    const float* en_b3 = nullptr;               // [1]
+    const float* sp_scales = nullptr;           // [3]
+    const float* sp_shifts = nullptr;           // [3]
+    const int32_t* elem_lookup = nullptr;       // [100]
+    const float* rr_w0T = nullptr;              // [128][128]
+    const float* rr_b0 = nullptr;
+    const float* rr_w3T = nullptr;              // [128][32]
+    const float* rr_b3 = nullptr;
+    const float* ro_w[3] = {};                  // reaction_output [32,33] [32,32] [2,32] (out-major as stored)
+    const float* ro_b[3] = {};
+    const float* qe_w[2] = {};                  // Q_emb [16,33] [16,16]
+    const float* qe_b[2] = {};
+    const float* qo_w[3] = {};                  // Q_output [32,18] [32,32] [1,32]
+    const float* qo_b[3] = {};
+    float cutoff = 5.0f;
+};
+
+}  // namespace rlvd
+
+struct rlvd_engine {
+    int device = 0;
+    int sm_count = 0;
+    std::map<std::string, rlvd::Tensor> tensors;   // as uploaded, checkpoint layout
+    std::vector<void*> derived;                    // transposed copies owned by the engine
+    rlvd::Weights w;
+    bool finalized = false;
+    // workspaces (grown on demand, never shrunk)
+    rlvd::DevBuf x, mu0, mu1, hid, mix, nrm, vw, ctx, struct_edges, struct_edge_ptr, scratch;
+    // host-path staging
+    rlvd::DevBuf in_node_ptr, in_Z, in_pos, in_cell, in_inv, in_img, in_rs, in_ps, in_temp, in_qp;
+    rlvd::DevBuf g_row_ptr, g_node_struct, g_col, g_shift, g_nedges, g_q, out_pack;
+    int64_t launches = 0;
+    bool profiling = false;
+    std::vector<rlvd::ProfSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double prof_ms[rlvd::FAM_COUNT] = {};
+    int64_t prof_n[rlvd::FAM_COUNT] = {};
+};
+
+namespace rlvd {
+
+// RAII-less span helpers: begin/end record events on `stream` when profiling is on.
+struct Span {
+    rlvd_engine* e;
+    cudaStream_t s;
+    int idx;
+    Span(rlvd_engine* e_, cudaStream_t s_, int family);
+    void end(int n_launches);
+};
+
+// ---- kernel launchers (each returns 0 / non-zero with set_error) ----
+int launch_neighbor_count(rlvd_engine* e, cudaStream_t s, int n_struct, int n_nodes, const int* node_ptr,
+                          const float* pos, const float* cell, const float* inv, const int* img, float cutoff,
+                          int* row_ptr, int* node_struct, int64_t* n_edges);
+int launch_neighbor_fill(rlvd_engine* e, cudaStream_t s, int n_struct, int n_nodes, const int* node_ptr,
+                         const float* pos, const float* cell, const float* inv, const int* img, float cutoff,
+                         const int* row_ptr, int64_t cap, int* col, int8_t* shift);
+
+struct LinearArgs {
+    const float* A = nullptr;     // [M, K1] rows of length lda
+    int lda = 0;
+    const float* A2 = nullptr;    // optional second source for k >= K1 (concatenation)
+    int lda2 = 0;
+    int K1 = 0;
+    int M = 0, K = 0, N = 0;
+    const float* Wt = nullptr;    // [K][N]
+    const float* bias = nullptr;  // [N] or null
+    float* Y = nullptr;
+    int ldy = 0;
+    int act = 0;                  // 0 none, 1 SiLU
+};
+int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a);
+
+int launch_embed(rlvd_engine* e, cudaStream_t s, int M, const int* Z, float* q);
+int launch_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* row_ptr, const int* col,
+                const int8_t* shift, const float* pos, const float* cell, const int* node_struct,
+                const float* x, const float* mu_in, float* q, float* mu_out);
+int launch_mix_reduce(rlvd_engine* e, cudaStream_t s, int M, const float* mix, float* nrm, float* vw);
+int launch_mix_update(rlvd_engine* e, cudaStream_t s, int M, const float* ctx, const float* mix,
+                      const float* vw, float* q, float* mu);
+int launch_readout(rlvd_engine* e, cudaStream_t s, int n_react, const int* node_ptr, const int* rs,
+                   const int* ps, const int* Z, const float* q, const rlvd_q_params& qp, const float* d_temp,
+                   float* rl_q, float* q0, float* q1, float* delta_e, float* E_R, float* E_P);
+
+}  // namespace rlvd

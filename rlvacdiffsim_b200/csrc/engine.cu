@@ -1,0 +1,465 @@
+// C ABI of librlvd_b200.so: engine lifetime, checkpoint upload, and the drivers that chain the kernels of
+// neighbor.cu / node.cu / edge.cu / readout.cu into the path the reference runs at
+// rlsim/drl/simulator.py:56 (`model(batch, q_params)["rl_q"]`).  See include/rlvd_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace rlvd {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p != nullptr) {
+        RLVD_CUDA(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;  // a little headroom so near-equal batches do not reallocate
+    RLVD_CUDA(cudaMalloc(&p, want));
+    cap = want;
+    return 0;
+}
+
+void DevBuf::release() {
+    if (p != nullptr) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+Span::Span(rlvd_engine* e_, cudaStream_t s_, int family) : e(e_), s(s_), idx(-1) {
+    if (!e->profiling) return;
+    ProfSpan sp;
+    sp.family = family;
+    for (cudaEvent_t* ev : {&sp.a, &sp.b}) {
+        if (!e->event_pool.empty()) {
+            *ev = e->event_pool.back();
+            e->event_pool.pop_back();
+        } else {
+            cudaEventCreate(ev);
+        }
+    }
+    cudaEventRecord(sp.a, s);
+    e->spans.push_back(sp);
+    idx = (int)e->spans.size() - 1;
+}
+
+void Span::end(int n_launches) {
+    e->launches += n_launches;
+    if (idx >= 0) cudaEventRecord(e->spans[idx].b, s);
+}
+
+namespace {
+
+struct HostTensor {
+    std::vector<float> f;
+    std::vector<int32_t> i;
+};
+
+std::map<const rlvd_engine*, std::map<std::string, HostTensor>>& host_store() {
+    static std::map<const rlvd_engine*, std::map<std::string, HostTensor>> s;
+    return s;
+}
+
+int upload(rlvd_engine* e, const void* src, size_t bytes, void** out) {
+    void* d = nullptr;
+    RLVD_CUDA(cudaMalloc(&d, bytes));
+    RLVD_CUDA(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+    e->derived.push_back(d);
+    *out = d;
+    return 0;
+}
+
+// Upload W[out][in] transposed to Wt[in][out].
+int upload_T(rlvd_engine* e, const std::vector<float>& W, int n_out, int n_in, const float** out) {
+    std::vector<float> t((size_t)n_out * n_in);
+    for (int o = 0; o < n_out; ++o)
+        for (int k = 0; k < n_in; ++k) t[(size_t)k * n_out + o] = W[(size_t)o * n_in + k];
+    void* d = nullptr;
+    if (upload(e, t.data(), t.size() * sizeof(float), &d)) return 1;
+    *out = reinterpret_cast<const float*>(d);
+    return 0;
+}
+
+int upload_raw(rlvd_engine* e, const std::vector<float>& W, const float** out) {
+    void* d = nullptr;
+    if (upload(e, W.data(), W.size() * sizeof(float), &d)) return 1;
+    *out = reinterpret_cast<const float*>(d);
+    return 0;
+}
+
+}  // namespace
+
+}  // namespace rlvd
+
+using namespace rlvd;
+
+extern "C" {
+
+int rlvd_abi_version(void) { return RLVD_ABI_VERSION; }
+
+const char* rlvd_last_error(void) { return g_error; }
+
+int rlvd_engine_create(int device, rlvd_engine** out) {
+    RLVD_CHECK(out != nullptr, "rlvd_engine_create: out is NULL");
+    int n_dev = 0;
+    RLVD_CUDA(cudaGetDeviceCount(&n_dev));
+    RLVD_CHECK(device >= 0 && device < n_dev, "rlvd_engine_create: device %d not in [0,%d)", device, n_dev);
+    cudaDeviceProp prop;
+    RLVD_CUDA(cudaGetDeviceProperties(&prop, device));
+    RLVD_CHECK(prop.major == 10, "rlvd_engine_create: device %d is sm_%d%d; this library is built for sm_100a only",
+               device, prop.major, prop.minor);
+    RLVD_CUDA(cudaSetDevice(device));
+    rlvd_engine* e = new rlvd_engine();
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    *out = e;
+    return 0;
+}
+
+void rlvd_engine_destroy(rlvd_engine* e) {
+    if (e == nullptr) return;
+    cudaSetDevice(e->device);
+    for (void* d : e->derived) cudaFree(d);
+    for (DevBuf* b : {&e->x, &e->mu0, &e->mu1, &e->hid, &e->mix, &e->nrm, &e->vw, &e->ctx, &e->struct_edges,
+                      &e->struct_edge_ptr, &e->scratch, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
+                      &e->in_inv, &e->in_img, &e->in_rs, &e->in_ps, &e->in_temp, &e->in_qp, &e->g_row_ptr,
+                      &e->g_node_struct, &e->g_col, &e->g_shift, &e->g_nedges, &e->g_q, &e->out_pack})
+        b->release();
+    for (auto& sp : e->spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
+    host_store().erase(e);
+    delete e;
+}
+
+int rlvd_set_weight(rlvd_engine* e, const char* name, const void* h_data, int64_t numel, int32_t is_int32) {
+    RLVD_CHECK(e != nullptr && name != nullptr && h_data != nullptr && numel > 0, "rlvd_set_weight: bad argument");
+    HostTensor& t = host_store()[e][name];
+    if (is_int32) {
+        t.i.assign(reinterpret_cast<const int32_t*>(h_data), reinterpret_cast<const int32_t*>(h_data) + numel);
+        t.f.clear();
+    } else {
+        t.f.assign(reinterpret_cast<const float*>(h_data), reinterpret_cast<const float*>(h_data) + numel);
+        t.i.clear();
+    }
+    e->finalized = false;
+    return 0;
+}
+
+int rlvd_finalize_weights(rlvd_engine* e) {
+    RLVD_CHECK(e != nullptr, "rlvd_finalize_weights: engine is NULL");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    auto& hs = host_store()[e];
+    auto need = [&](const std::string& name, size_t numel, const std::vector<float>** out) -> int {
+        auto it = hs.find(name);
+        RLVD_CHECK(it != hs.end(), "missing checkpoint tensor '%s'", name.c_str());
+        RLVD_CHECK(it->second.f.size() == numel, "checkpoint tensor '%s' has %zu elements, expected %zu",
+                   name.c_str(), it->second.f.size(), numel);
+        *out = &it->second.f;
+        return 0;
+    };
+    RLVD_CUDA(cudaDeviceSynchronize());
+    for (void* d : e->derived) cudaFree(d);
+    e->derived.clear();
+    Weights w;
+    const std::vector<float>* t = nullptr;
+    const std::string rep = "reaction_model.representation.";
+    if (need(rep + "cutoff_fn.cutoff", 1, &t)) return 1;
+    w.cutoff = (*t)[0];
+    if (need(rep + "radial_basis.freqs", NRBF, &t) || upload_raw(e, *t, &w.freqs)) return 1;
+    if (need(rep + "embedding.weight", 100 * F, &t) || upload_raw(e, *t, &w.emb)) return 1;
+    {
+        const std::vector<float>*fw = nullptr, *fb = nullptr;
+        if (need(rep + "filter_net.weight", (size_t)NLAYER * 3 * F * NRBF, &fw)) return 1;
+        if (need(rep + "filter_net.bias", (size_t)NLAYER * 3 * F, &fb)) return 1;
+        std::vector<float> ft((size_t)NLAYER * (NRBF + 1) * 3 * F);
+        for (int l = 0; l < NLAYER; ++l)
+            for (int o = 0; o < 3 * F; ++o) {
+                const int row = l * 3 * F + o;
+                for (int k = 0; k < NRBF; ++k)
+                    ft[((size_t)l * (NRBF + 1) + k) * 3 * F + o] = (*fw)[(size_t)row * NRBF + k];
+                ft[((size_t)l * (NRBF + 1) + NRBF) * 3 * F + o] = (*fb)[row];
+            }
+        if (upload_raw(e, ft, &w.filt_T)) return 1;
+    }
+    for (int l = 0; l < NLAYER; ++l) {
+        const std::string pi = rep + "interactions." + std::to_string(l) + ".interatomic_context_net.layers.";
+        const std::string pm = rep + "mixing." + std::to_string(l) + ".";
+        if (need(pi + "0.weight", F * F, &t) || upload_T(e, *t, F, F, &w.inter_w0T[l])) return 1;
+        if (need(pi + "0.bias", F, &t) || upload_raw(e, *t, &w.inter_b0[l])) return 1;
+        if (need(pi + "3.weight", 3 * F * F, &t) || upload_T(e, *t, 3 * F, F, &w.inter_w3T[l])) return 1;
+        if (need(pi + "3.bias", 3 * F, &t) || upload_raw(e, *t, &w.inter_b3[l])) return 1;
+        if (need(pm + "mu_channel_mix.weight", 2 * F * F, &t) || upload_T(e, *t, 2 * F, F, &w.mix_wT[l])) return 1;
+        if (need(pm + "intraatomic_context_net.layers.0.weight", F * 2 * F, &t) ||
+            upload_T(e, *t, F, 2 * F, &w.intra_w0T[l]))
+            return 1;
+        if (need(pm + "intraatomic_context_net.layers.0.bias", F, &t) || upload_raw(e, *t, &w.intra_b0[l])) return 1;
+        if (need(pm + "intraatomic_context_net.layers.3.weight", 3 * F * F, &t) ||
+            upload_T(e, *t, 3 * F, F, &w.intra_w3T[l]))
+            return 1;
+        if (need(pm + "intraatomic_context_net.layers.3.bias", 3 * F, &t) || upload_raw(e, *t, &w.intra_b3[l])) return 1;
+    }
+    const std::string rm = "reaction_model.";
+    if (need(rm + "energy_output.layers.0.weight", 64 * F, &t) || upload_T(e, *t, 64, F, &w.en_w0T)) return 1;
+    if (need(rm + "energy_output.layers.0.bias", 64, &t) || upload_raw(e, *t, &w.en_b0)) return 1;
+    if (need(rm + "energy_output.layers.3.weight", 64, &t) || upload_raw(e, *t, &w.en_w3)) return 1;
+    if (need(rm + "energy_output.layers.3.bias", 1, &t) || upload_raw(e, *t, &w.en_b3)) return 1;
+    if (need(rm + "species_energy_scale.scales", 3, &t) || upload_raw(e, *t, &w.sp_scales)) return 1;
+    if (need(rm + "species_energy_scale.shifts", 3, &t) || upload_raw(e, *t, &w.sp_shifts)) return 1;
+    {
+        auto it = hs.find(rm + "species_energy_scale.elem_lookup");
+        RLVD_CHECK(it != hs.end() && it->second.i.size() == 100,
+                   "missing int32 checkpoint tensor 'reaction_model.species_energy_scale.elem_lookup' [100]");
+        for (int32_t v : it->second.i) RLVD_CHECK(v >= 0 && v < 3, "elem_lookup entry %d out of range", v);
+        void* d = nullptr;
+        if (upload(e, it->second.i.data(), 100 * sizeof(int32_t), &d)) return 1;
+        w.elem_lookup = reinterpret_cast<const int32_t*>(d);
+    }
+    if (need(rm + "reaction_representation.layers.0.weight", F * F, &t) || upload_T(e, *t, F, F, &w.rr_w0T)) return 1;
+    if (need(rm + "reaction_representation.layers.0.bias", F, &t) || upload_raw(e, *t, &w.rr_b0)) return 1;
+    if (need(rm + "reaction_representation.layers.3.weight", 32 * F, &t) || upload_T(e, *t, 32, F, &w.rr_w3T)) return 1;
+    if (need(rm + "reaction_representation.layers.3.bias", 32, &t) || upload_raw(e, *t, &w.rr_b3)) return 1;
+    const int ro_out[3] = {32, 32, 2}, ro_in[3] = {33, 32, 32};
+    const int qo_out[3] = {32, 32, 1}, qo_in[3] = {18, 32, 32};
+    const int qe_out[2] = {16, 16}, qe_in[2] = {33, 16};
+    for (int i = 0; i < 3; ++i) {
+        const std::string li = std::to_string(3 * i);
+        if (need(rm + "reaction_output.layers." + li + ".weight", (size_t)ro_out[i] * ro_in[i], &t) ||
+            upload_raw(e, *t, &w.ro_w[i]))
+            return 1;
+        if (need(rm + "reaction_output.layers." + li + ".bias", ro_out[i], &t) || upload_raw(e, *t, &w.ro_b[i])) return 1;
+        if (need("Q_output.layers." + li + ".weight", (size_t)qo_out[i] * qo_in[i], &t) ||
+            upload_raw(e, *t, &w.qo_w[i]))
+            return 1;
+        if (need("Q_output.layers." + li + ".bias", qo_out[i], &t) || upload_raw(e, *t, &w.qo_b[i])) return 1;
+    }
+    for (int i = 0; i < 2; ++i) {
+        const std::string li = std::to_string(3 * i);
+        if (need("Q_emb.layers." + li + ".weight", (size_t)qe_out[i] * qe_in[i], &t) || upload_raw(e, *t, &w.qe_w[i]))
+            return 1;
+        if (need("Q_emb.layers." + li + ".bias", qe_out[i], &t) || upload_raw(e, *t, &w.qe_b[i])) return 1;
+    }
+    e->w = w;
+    e->finalized = true;
+    return 0;
+}
+
+int rlvd_radius_graph_count(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes,
+                            const int32_t* d_node_ptr, const float* d_pos, const float* d_cell,
+                            const float* d_inv_cell, const int32_t* d_img_range, float cutoff, int32_t* d_row_ptr,
+                            int32_t* d_node_struct, int64_t* d_n_edges) {
+    RLVD_CHECK(e != nullptr, "engine is NULL");
+    RLVD_CHECK(n_struct >= 0 && n_nodes >= 0 && cutoff > 0.f, "rlvd_radius_graph_count: bad sizes");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_neighbor_count(e, (cudaStream_t)stream, n_struct, n_nodes, d_node_ptr, d_pos, d_cell, d_inv_cell,
+                                 d_img_range, cutoff, d_row_ptr, d_node_struct, d_n_edges);
+}
+
+int rlvd_radius_graph_fill(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes,
+                           const int32_t* d_node_ptr, const float* d_pos, const float* d_cell,
+                           const float* d_inv_cell, const int32_t* d_img_range, float cutoff,
+                           const int32_t* d_row_ptr, int64_t edge_capacity, int32_t* d_col, int8_t* d_shift) {
+    RLVD_CHECK(e != nullptr, "engine is NULL");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_neighbor_fill(e, (cudaStream_t)stream, n_struct, n_nodes, d_node_ptr, d_pos, d_cell, d_inv_cell,
+                                d_img_range, cutoff, d_row_ptr, edge_capacity, d_col, d_shift);
+}
+
+int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes, int64_t n_edges,
+                              const int32_t* d_Z, const float* d_pos, const float* d_cell,
+                              const int32_t* d_node_struct, const int32_t* d_row_ptr, const int32_t* d_col,
+                              const int8_t* d_shift, float* d_q, float* d_mu) {
+    (void)n_struct;
+    (void)n_edges;
+    RLVD_CHECK(e != nullptr && e->finalized, "rlvd_painn_representation: weights are not finalized");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int M = n_nodes;
+    if (M == 0) return 0;
+    const size_t MF = (size_t)M * F * sizeof(float);
+    if (e->x.ensure(3 * MF) || e->mu0.ensure(3 * MF) || e->mu1.ensure(3 * MF) || e->hid.ensure(MF) ||
+        e->mix.ensure(6 * MF) || e->nrm.ensure(MF) || e->vw.ensure(MF) || e->ctx.ensure(3 * MF))
+        return 1;
+    float* x = e->x.as<float>();
+    float* mu_cur = e->mu0.as<float>();
+    float* mu_nxt = e->mu1.as<float>();
+    float* hid = e->hid.as<float>();
+    float* mix = e->mix.as<float>();
+    float* nrm = e->nrm.as<float>();
+    float* vw = e->vw.as<float>();
+    float* ctx = e->ctx.as<float>();
+    const Weights& w = e->w;
+
+    if (launch_embed(e, s, M, d_Z, d_q)) return 1;
+    for (int l = 0; l < NLAYER; ++l) {
+        // R5 node part: x = Lin3(SiLU(Lin0(q)))
+        LinearArgs a0;
+        a0.A = d_q; a0.lda = F; a0.M = M; a0.K = F; a0.N = F; a0.Wt = w.inter_w0T[l]; a0.bias = w.inter_b0[l];
+        a0.Y = hid; a0.ldy = F; a0.act = 1;
+        if (launch_linear(e, s, a0)) return 1;
+        LinearArgs a1;
+        a1.A = hid; a1.lda = F; a1.M = M; a1.K = F; a1.N = 3 * F; a1.Wt = w.inter_w3T[l]; a1.bias = w.inter_b3[l];
+        a1.Y = x; a1.ldy = 3 * F; a1.act = 0;
+        if (launch_linear(e, s, a1)) return 1;
+        // R2 + R3 + R5 edge part + K4
+        if (launch_edge(e, s, l, M, d_row_ptr, d_col, d_shift, d_pos, d_cell, d_node_struct, x,
+                        l == 0 ? nullptr : mu_cur, d_q, mu_nxt))
+            return 1;
+        float* tmp = mu_cur; mu_cur = mu_nxt; mu_nxt = tmp;
+        // R6: mixing
+        LinearArgs am;
+        am.A = mu_cur; am.lda = F; am.M = 3 * M; am.K = F; am.N = 2 * F; am.Wt = w.mix_wT[l]; am.bias = nullptr;
+        am.Y = mix; am.ldy = 2 * F; am.act = 0;
+        if (launch_linear(e, s, am)) return 1;
+        if (launch_mix_reduce(e, s, M, mix, nrm, vw)) return 1;
+        LinearArgs b0;
+        b0.A = d_q; b0.lda = F; b0.A2 = nrm; b0.lda2 = F; b0.K1 = F; b0.M = M; b0.K = 2 * F; b0.N = F;
+        b0.Wt = w.intra_w0T[l]; b0.bias = w.intra_b0[l]; b0.Y = hid; b0.ldy = F; b0.act = 1;
+        if (launch_linear(e, s, b0)) return 1;
+        LinearArgs b1;
+        b1.A = hid; b1.lda = F; b1.M = M; b1.K = F; b1.N = 3 * F; b1.Wt = w.intra_w3T[l]; b1.bias = w.intra_b3[l];
+        b1.Y = ctx; b1.ldy = 3 * F; b1.act = 0;
+        if (launch_linear(e, s, b1)) return 1;
+        if (launch_mix_update(e, s, M, ctx, mix, vw, d_q, mu_cur)) return 1;
+    }
+    if (d_mu != nullptr)
+        RLVD_CUDA(cudaMemcpyAsync(d_mu, mu_cur, 3 * MF, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+int rlvd_reaction_readout(rlvd_engine* e, void* stream, int32_t n_react, int32_t n_nodes, const int32_t* d_node_ptr,
+                          const int32_t* d_react_struct, const int32_t* d_prod_struct, const int32_t* d_Z,
+                          const float* d_q, const rlvd_q_params* qp, const float* d_temperature, float* d_rl_q,
+                          float* d_q0, float* d_q1, float* d_delta_e, float* d_E_R, float* d_E_P) {
+    (void)n_nodes;
+    RLVD_CHECK(e != nullptr && e->finalized, "rlvd_reaction_readout: weights are not finalized");
+    RLVD_CHECK(qp != nullptr, "rlvd_reaction_readout: q_params is NULL");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_readout(e, (cudaStream_t)stream, n_react, d_node_ptr, d_react_struct, d_prod_struct, d_Z, d_q, *qp,
+                          d_temperature, d_rl_q, d_q0, d_q1, d_delta_e, d_E_R, d_E_P);
+}
+
+int rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes,
+                              const int32_t* h_node_ptr, const int32_t* h_Z, const float* h_pos, const float* h_cell,
+                              const float* h_inv_cell, const int32_t* h_img_range, float cutoff, int32_t n_react,
+                              const int32_t* h_react_struct, const int32_t* h_prod_struct, const rlvd_q_params* qp,
+                              const float* h_temperature, float* h_rl_q, float* h_q0, float* h_q1, float* h_delta_e,
+                              float* h_E_R, float* h_E_P, int64_t* h_n_edges) {
+    RLVD_CHECK(e != nullptr && e->finalized, "rlvd_score_reactions_host: weights are not finalized");
+    RLVD_CHECK(qp != nullptr && n_struct > 0 && n_nodes > 0 && n_react > 0, "rlvd_score_reactions_host: bad sizes");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int M = n_nodes;
+    if (e->in_node_ptr.ensure(((size_t)n_struct + 1) * 4) || e->in_Z.ensure((size_t)M * 4) ||
+        e->in_pos.ensure((size_t)M * 12) || e->in_cell.ensure((size_t)n_struct * 36) ||
+        e->in_inv.ensure((size_t)n_struct * 36) || e->in_img.ensure((size_t)n_struct * 12) ||
+        e->in_rs.ensure((size_t)n_react * 4) || e->in_ps.ensure((size_t)n_react * 4) ||
+        e->in_temp.ensure((size_t)n_react * 4) || e->g_row_ptr.ensure(((size_t)M + 1) * 4) ||
+        e->g_node_struct.ensure((size_t)M * 4) || e->g_nedges.ensure(8) || e->g_q.ensure((size_t)M * F * 4) ||
+        e->out_pack.ensure((size_t)6 * n_react * 4))
+        return 1;
+    RLVD_CUDA(cudaMemcpyAsync(e->in_node_ptr.p, h_node_ptr, ((size_t)n_struct + 1) * 4, cudaMemcpyHostToDevice, s));
+    RLVD_CUDA(cudaMemcpyAsync(e->in_Z.p, h_Z, (size_t)M * 4, cudaMemcpyHostToDevice, s));
+    RLVD_CUDA(cudaMemcpyAsync(e->in_pos.p, h_pos, (size_t)M * 12, cudaMemcpyHostToDevice, s));
+    RLVD_CUDA(cudaMemcpyAsync(e->in_cell.p, h_cell, (size_t)n_struct * 36, cudaMemcpyHostToDevice, s));
+    RLVD_CUDA(cudaMemcpyAsync(e->in_inv.p, h_inv_cell, (size_t)n_struct * 36, cudaMemcpyHostToDevice, s));
+    RLVD_CUDA(cudaMemcpyAsync(e->in_img.p, h_img_range, (size_t)n_struct * 12, cudaMemcpyHostToDevice, s));
+    RLVD_CUDA(cudaMemcpyAsync(e->in_rs.p, h_react_struct, (size_t)n_react * 4, cudaMemcpyHostToDevice, s));
+    RLVD_CUDA(cudaMemcpyAsync(e->in_ps.p, h_prod_struct, (size_t)n_react * 4, cudaMemcpyHostToDevice, s));
+    if (h_temperature != nullptr)
+        RLVD_CUDA(cudaMemcpyAsync(e->in_temp.p, h_temperature, (size_t)n_react * 4, cudaMemcpyHostToDevice, s));
+    if (launch_neighbor_count(e, s, n_struct, M, e->in_node_ptr.as<int>(), e->in_pos.as<float>(),
+                              e->in_cell.as<float>(), e->in_inv.as<float>(), e->in_img.as<int>(), cutoff,
+                              e->g_row_ptr.as<int>(), e->g_node_struct.as<int>(), e->g_nedges.as<int64_t>()))
+        return 1;
+    int64_t E = 0;
+    RLVD_CUDA(cudaMemcpyAsync(&E, e->g_nedges.p, 8, cudaMemcpyDeviceToHost, s));
+    RLVD_CUDA(cudaStreamSynchronize(s));
+    RLVD_CHECK(E >= 0 && E < (int64_t)0x7fffffff, "edge count %lld overflows int32 offsets; split the batch",
+               (long long)E);
+    if (h_n_edges != nullptr) *h_n_edges = E;
+    if (e->g_col.ensure((size_t)(E + 1) * 4) || e->g_shift.ensure((size_t)(E + 1) * 3)) return 1;
+    if (launch_neighbor_fill(e, s, n_struct, M, e->in_node_ptr.as<int>(), e->in_pos.as<float>(),
+                             e->in_cell.as<float>(), e->in_inv.as<float>(), e->in_img.as<int>(), cutoff,
+                             e->g_row_ptr.as<int>(), E, e->g_col.as<int>(), e->g_shift.as<int8_t>()))
+        return 1;
+    if (rlvd_painn_representation(e, stream, n_struct, M, E, e->in_Z.as<int>(), e->in_pos.as<float>(),
+                                  e->in_cell.as<float>(), e->g_node_struct.as<int>(), e->g_row_ptr.as<int>(),
+                                  e->g_col.as<int>(), e->g_shift.as<int8_t>(), e->g_q.as<float>(), nullptr))
+        return 1;
+    float* op = e->out_pack.as<float>();
+    if (launch_readout(e, s, n_react, e->in_node_ptr.as<int>(), e->in_rs.as<int>(), e->in_ps.as<int>(),
+                       e->in_Z.as<int>(), e->g_q.as<float>(), *qp,
+                       h_temperature != nullptr ? e->in_temp.as<float>() : nullptr, op, op + n_react,
+                       op + 2 * (size_t)n_react, op + 3 * (size_t)n_react, op + 4 * (size_t)n_react,
+                       op + 5 * (size_t)n_react))
+        return 1;
+    float* hosts[6] = {h_rl_q, h_q0, h_q1, h_delta_e, h_E_R, h_E_P};
+    for (int k = 0; k < 6; ++k)
+        if (hosts[k] != nullptr)
+            RLVD_CUDA(cudaMemcpyAsync(hosts[k], op + (size_t)k * n_react, (size_t)n_react * 4, cudaMemcpyDeviceToHost, s));
+    RLVD_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int64_t rlvd_launch_count(const rlvd_engine* e) { return e != nullptr ? e->launches : 0; }
+
+int rlvd_profile_enable(rlvd_engine* e, int32_t on) {
+    RLVD_CHECK(e != nullptr, "engine is NULL");
+    e->profiling = on != 0;
+    return 0;
+}
+
+static int drain_spans(rlvd_engine* e) {
+    if (e->spans.empty()) return 0;
+    RLVD_CUDA(cudaSetDevice(e->device));
+    RLVD_CUDA(cudaDeviceSynchronize());
+    for (auto& sp : e->spans) {
+        float ms = 0.f;
+        RLVD_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        e->prof_ms[sp.family] += ms;
+        e->prof_n[sp.family] += 1;
+        e->event_pool.push_back(sp.a);
+        e->event_pool.push_back(sp.b);
+    }
+    e->spans.clear();
+    return 0;
+}
+
+int rlvd_profile_read(rlvd_engine* e, const char* family, double* ms_total, int64_t* launches) {
+    RLVD_CHECK(e != nullptr && family != nullptr, "bad argument");
+    if (drain_spans(e)) return 1;
+    static const char* names[FAM_COUNT] = {"neighbor", "edge", "node", "readout"};
+    for (int f = 0; f < FAM_COUNT; ++f)
+        if (strcmp(names[f], family) == 0) {
+            if (ms_total) *ms_total = e->prof_ms[f];
+            if (launches) *launches = e->prof_n[f];
+            return 0;
+        }
+    RLVD_CHECK(false, "unknown kernel family '%s'", family);
+}
+
+int rlvd_profile_reset(rlvd_engine* e) {
+    RLVD_CHECK(e != nullptr, "engine is NULL");
+    if (drain_spans(e)) return 1;
+    for (int f = 0; f < FAM_COUNT; ++f) {
+        e->prof_ms[f] = 0.0;
+        e->prof_n[f] = 0;
+    }
+    return 0;
+}
+
+}  // extern "C"

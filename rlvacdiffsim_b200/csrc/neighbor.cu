@@ -1,0 +1,280 @@
+// K1 — periodic radius graph → receiver-sorted CSR.
+//
+// Replaces the torch_cluster.radius_graph + minimum-image step inside rgnn that the reference reaches at
+// rlsim/drl/simulator.py:56.  The pair arithmetic is the CANONICAL one documented in
+// oracle/painn_oracle.py::radius_graph_pbc — every multiply and add individually rounded (no FMA
+// contraction), strict d^2 < rc^2 — so the edge set is bit-identical to the oracle's.
+//
+// Layout: one CTA per structure.  A warp owns a receiver i and sweeps senders j in ascending chunks of
+// 32 (lane = j), so hits come out already sorted by (i, j, S) and a warp exclusive scan of the per-lane
+// hit counts gives each lane its slot: deterministic, no atomics, no sort.
+//   count : per-receiver degrees → block scan → structure-local row offsets + edges per structure
+//   scan  : one block scans the per-structure edge counts (≤ a few 10^4 entries)
+//   final : row_ptr += structure base; row_ptr[M] = E
+//   fill  : same sweep, writes col[E] (global sender index) and shift[E,3] (int8)
+#include "common.cuh"
+
+namespace rlvd {
+
+namespace {
+
+constexpr int NB_THREADS = 256;
+constexpr int MAX_SMEM_ATOMS = 3072;  // 36 KB of positions in static-free dynamic smem
+
+struct CellC {
+    float c[9];    // row-vector cell: c[k*3+comp]
+    float inv[9];  // inverse: inv[r*3+k], f_k = sum_r d_r * inv[r][k]
+    int R[3];
+};
+
+__device__ __forceinline__ void load_cell(CellC& C, const float* cell, const float* inv, const int* img, int g) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        C.c[t] = __ldg(cell + 9 * g + t);
+        C.inv[t] = __ldg(inv + 9 * g + t);
+    }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) C.R[t] = __ldg(img + 3 * g + t);
+}
+
+// base image S = -rint(d . inv), every op rounded separately.
+__device__ __forceinline__ void base_image(const CellC& C, float dx, float dy, float dz, float& b0, float& b1,
+                                           float& b2) {
+    float f0 = __fadd_rn(__fadd_rn(__fmul_rn(dx, C.inv[0]), __fmul_rn(dy, C.inv[3])), __fmul_rn(dz, C.inv[6]));
+    float f1 = __fadd_rn(__fadd_rn(__fmul_rn(dx, C.inv[1]), __fmul_rn(dy, C.inv[4])), __fmul_rn(dz, C.inv[7]));
+    float f2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, C.inv[2]), __fmul_rn(dy, C.inv[5])), __fmul_rn(dz, C.inv[8]));
+    b0 = -rintf(f0);
+    b1 = -rintf(f1);
+    b2 = -rintf(f2);
+}
+
+__device__ __forceinline__ float image_d2(const CellC& C, float dx, float dy, float dz, float S0, float S1,
+                                          float S2) {
+    float rx = __fadd_rn(__fadd_rn(__fadd_rn(dx, __fmul_rn(S0, C.c[0])), __fmul_rn(S1, C.c[3])), __fmul_rn(S2, C.c[6]));
+    float ry = __fadd_rn(__fadd_rn(__fadd_rn(dy, __fmul_rn(S0, C.c[1])), __fmul_rn(S1, C.c[4])), __fmul_rn(S2, C.c[7]));
+    float rz = __fadd_rn(__fadd_rn(__fadd_rn(dz, __fmul_rn(S0, C.c[2])), __fmul_rn(S1, C.c[5])), __fmul_rn(S2, C.c[8]));
+    return __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+}
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+}
+
+// Sweep all senders of receiver i; FILL=false counts, FILL=true writes.
+template <bool FILL>
+__device__ __forceinline__ int sweep_receiver(const CellC& C, const float* P, int n, int i, int lane, float rc2,
+                                              int node0, int row_start, int* col, int8_t* shift,
+                                              long long cap) {
+    const float xi = P[3 * i], yi = P[3 * i + 1], zi = P[3 * i + 2];
+    int off = 0;
+    for (int jb = 0; jb < n; jb += 32) {
+        const int j = jb + lane;
+        int cnt = 0;
+        float dx = 0.f, dy = 0.f, dz = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        if (j < n) {
+            dx = __fsub_rn(P[3 * j], xi);
+            dy = __fsub_rn(P[3 * j + 1], yi);
+            dz = __fsub_rn(P[3 * j + 2], zi);
+            base_image(C, dx, dy, dz, b0, b1, b2);
+            for (int o0 = -C.R[0]; o0 <= C.R[0]; ++o0)
+                for (int o1 = -C.R[1]; o1 <= C.R[1]; ++o1)
+                    for (int o2 = -C.R[2]; o2 <= C.R[2]; ++o2) {
+                        const float S0 = b0 + (float)o0, S1 = b1 + (float)o1, S2 = b2 + (float)o2;
+                        const bool self = (j == i) && S0 == 0.f && S1 == 0.f && S2 == 0.f;
+                        if (!self && image_d2(C, dx, dy, dz, S0, S1, S2) < rc2) ++cnt;
+                    }
+        }
+        int total;
+        const int excl = warp_excl_scan(cnt, lane, total);
+        if (FILL && cnt > 0) {
+            int w = row_start + off + excl;
+            for (int o0 = -C.R[0]; o0 <= C.R[0]; ++o0)
+                for (int o1 = -C.R[1]; o1 <= C.R[1]; ++o1)
+                    for (int o2 = -C.R[2]; o2 <= C.R[2]; ++o2) {
+                        const float S0 = b0 + (float)o0, S1 = b1 + (float)o1, S2 = b2 + (float)o2;
+                        const bool self = (j == i) && S0 == 0.f && S1 == 0.f && S2 == 0.f;
+                        if (!self && image_d2(C, dx, dy, dz, S0, S1, S2) < rc2 && w < cap) {
+                            col[w] = node0 + j;
+                            shift[3 * (int64_t)w + 0] = (int8_t)(int)S0;
+                            shift[3 * (int64_t)w + 1] = (int8_t)(int)S1;
+                            shift[3 * (int64_t)w + 2] = (int8_t)(int)S2;
+                            ++w;
+                        }
+                    }
+        }
+        off += total;
+    }
+    return off;
+}
+
+// Block-wide exclusive scan of `vals[0..n)` in place (n arbitrary), returns the total in every thread.
+__device__ int block_excl_scan_inplace(int* vals, int n, int* warp_sums /* [>= blockDim/32 + 1] */) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    int carry = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int idx = base + tid;
+        const int v = idx < n ? vals[idx] : 0;
+        int wtotal;
+        const int excl = warp_excl_scan(v, lane, wtotal);
+        if (lane == 31) warp_sums[wid] = wtotal;
+        __syncthreads();
+        if (wid == 0) {
+            int ws = lane < nw ? warp_sums[lane] : 0;
+            int t;
+            const int wex = warp_excl_scan(ws, lane, t);
+            if (lane < nw) warp_sums[lane] = wex;
+            if (lane == 0) warp_sums[nw] = t;
+        }
+        __syncthreads();
+        if (idx < n) vals[idx] = carry + warp_sums[wid] + excl;
+        carry += warp_sums[nw];
+        __syncthreads();
+    }
+    return carry;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(NB_THREADS) neighbor_kernel(
+    int n_struct, const int* __restrict__ node_ptr, const float* __restrict__ pos, const float* __restrict__ cell,
+    const float* __restrict__ inv, const int* __restrict__ img, float rc2,
+    int* __restrict__ row_ptr,       // count: out structure-local offsets; fill: in global offsets
+    int* __restrict__ node_struct,   // count only
+    int* __restrict__ struct_edges,  // count only
+    int* __restrict__ col, int8_t* __restrict__ shift, long long cap) {
+    extern __shared__ float smem_f[];
+    __shared__ int warp_sums[NB_THREADS / 32 + 1];
+    const int g = blockIdx.x;
+    if (g >= n_struct) return;
+    const int node0 = node_ptr[g], n = node_ptr[g + 1] - node0;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = NB_THREADS / 32;
+    CellC C;
+    load_cell(C, cell, inv, img, g);
+
+    const bool staged = n <= MAX_SMEM_ATOMS;
+    const float* P = pos + 3 * (int64_t)node0;
+    int* deg = nullptr;
+    if (staged) {
+        for (int t = tid; t < 3 * n; t += NB_THREADS) smem_f[t] = P[t];
+        P = smem_f;
+        deg = reinterpret_cast<int*>(smem_f + 3 * MAX_SMEM_ATOMS);
+    }
+    __syncthreads();
+
+    for (int i = wid; i < n; i += nw) {
+        const int row_start = FILL ? row_ptr[node0 + i] : 0;
+        const int d = sweep_receiver<FILL>(C, P, n, i, lane, rc2, node0, row_start, col, shift, cap);
+        if (!FILL && lane == 0) {
+            if (staged) deg[i] = d; else row_ptr[node0 + i] = d;
+            node_struct[node0 + i] = g;
+        }
+    }
+    if (FILL) return;
+    __syncthreads();
+    int* vals = staged ? deg : (row_ptr + node0);
+    const int total = block_excl_scan_inplace(vals, n, warp_sums);
+    if (staged)
+        for (int t = tid; t < n; t += NB_THREADS) row_ptr[node0 + t] = deg[t];
+    if (tid == 0) struct_edges[g] = total;
+}
+
+// One block: exclusive scan of per-structure edge counts (int64 running sum guards overflow detection).
+__global__ void __launch_bounds__(1024) struct_scan_kernel(int n_struct, const int* __restrict__ struct_edges,
+                                                           int* __restrict__ struct_edge_ptr,
+                                                           int64_t* __restrict__ n_edges) {
+    __shared__ int warp_sums[33];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    int carry = 0;
+    long long wide = 0;
+    for (int base = 0; base < n_struct; base += blockDim.x) {
+        const int idx = base + tid;
+        const int v = idx < n_struct ? struct_edges[idx] : 0;
+        int wtotal;
+        const int excl = warp_excl_scan(v, lane, wtotal);
+        if (lane == 31) warp_sums[wid] = wtotal;
+        __syncthreads();
+        if (wid == 0) {
+            int ws = lane < nw ? warp_sums[lane] : 0;
+            int t;
+            const int wex = warp_excl_scan(ws, lane, t);
+            if (lane < nw) warp_sums[lane] = wex;
+            if (lane == 0) warp_sums[32] = t;
+        }
+        __syncthreads();
+        if (idx < n_struct) struct_edge_ptr[idx] = carry + warp_sums[wid] + excl;
+        carry += warp_sums[32];
+        wide += warp_sums[32];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        struct_edge_ptr[n_struct] = carry;
+        n_edges[0] = wide;   // differs from `carry` only if the int32 offsets overflowed
+    }
+}
+
+__global__ void row_ptr_final_kernel(int n_nodes, const int* __restrict__ node_struct,
+                                     const int* __restrict__ struct_edge_ptr, int n_struct,
+                                     int* __restrict__ row_ptr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes) row_ptr[i] += struct_edge_ptr[node_struct[i]];
+    if (i == n_nodes) row_ptr[n_nodes] = struct_edge_ptr[n_struct];
+}
+
+size_t neighbor_smem() { return (size_t)MAX_SMEM_ATOMS * 3 * sizeof(float) + (size_t)MAX_SMEM_ATOMS * sizeof(int); }
+
+}  // namespace
+
+int launch_neighbor_count(rlvd_engine* e, cudaStream_t s, int n_struct, int n_nodes, const int* node_ptr,
+                          const float* pos, const float* cell, const float* inv, const int* img, float cutoff,
+                          int* row_ptr, int* node_struct, int64_t* n_edges) {
+    if (n_struct <= 0 || n_nodes <= 0) {
+        RLVD_CUDA(cudaMemsetAsync(n_edges, 0, sizeof(int64_t), s));
+        if (n_nodes == 0) RLVD_CUDA(cudaMemsetAsync(row_ptr, 0, sizeof(int), s));
+        return 0;
+    }
+    if (e->struct_edges.ensure((size_t)n_struct * sizeof(int))) return 1;
+    if (e->struct_edge_ptr.ensure(((size_t)n_struct + 1) * sizeof(int))) return 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RLVD_CUDA(cudaFuncSetAttribute(neighbor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)neighbor_smem()));
+        RLVD_CUDA(cudaFuncSetAttribute(neighbor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)neighbor_smem()));
+        attr_set = true;
+    }
+    const float rc = cutoff;
+    const float rc2 = rc * rc;  // fp32 product, as in the oracle
+    Span sp(e, s, FAM_NEIGHBOR);
+    neighbor_kernel<false><<<n_struct, NB_THREADS, neighbor_smem(), s>>>(
+        n_struct, node_ptr, pos, cell, inv, img, rc2, row_ptr, node_struct, e->struct_edges.as<int>(), nullptr,
+        nullptr, 0);
+    struct_scan_kernel<<<1, 1024, 0, s>>>(n_struct, e->struct_edges.as<int>(), e->struct_edge_ptr.as<int>(),
+                                           n_edges);
+    row_ptr_final_kernel<<<(n_nodes + 1 + 255) / 256, 256, 0, s>>>(n_nodes, node_struct,
+                                                                   e->struct_edge_ptr.as<int>(), n_struct, row_ptr);
+    sp.end(3);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_neighbor_fill(rlvd_engine* e, cudaStream_t s, int n_struct, int n_nodes, const int* node_ptr,
+                         const float* pos, const float* cell, const float* inv, const int* img, float cutoff,
+                         const int* row_ptr, int64_t cap, int* col, int8_t* shift) {
+    if (n_struct <= 0 || n_nodes <= 0) return 0;
+    const float rc = cutoff;
+    const float rc2 = rc * rc;
+    Span sp(e, s, FAM_NEIGHBOR);
+    neighbor_kernel<true><<<n_struct, NB_THREADS, neighbor_smem(), s>>>(
+        n_struct, node_ptr, pos, cell, inv, img, rc2, const_cast<int*>(row_ptr), nullptr, nullptr, col, shift, (long long)cap);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rlvd

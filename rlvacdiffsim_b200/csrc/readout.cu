@@ -1,0 +1,276 @@
+// K5 — batched per-action readout.
+//
+// Replaces the heads of rgnn's `painn` reaction model and `dqn_v2` reached from
+// rlsim/drl/simulator.py:56 / rlsim/drl/trainer.py:112,166: per-atom energy MLP (128→64→1) with the
+// species scale/shift, per-atom reaction MLP (128→128→32) on q_P - q_R, sum pooling per reaction graph
+// (torch_scatter / global_add_pool in the reference stack), reaction_output (33→32→32→2), Q_emb
+// (33→16→16), Q_output (18→32→32→1) and the q_params combination into rl_q.
+//
+// One CTA per reaction graph.  Atoms are processed in tiles of 32 held in shared memory; all sums run in a
+// fixed order (tile order, then atom order), so the result is bitwise reproducible.  delta_e is pooled from
+// per-atom differences scale_s*(o_P - o_R): the species shifts cancel exactly instead of being subtracted
+// as two ~1.6 keV totals.
+#include "common.cuh"
+
+namespace rlvd {
+
+namespace {
+
+constexpr int RT = 256;  // threads
+constexpr int TA = 32;   // atoms per tile
+constexpr int QS = F + 4;  // padded row stride of the shared q tiles
+
+__device__ __forceinline__ float act_fn(float v, int code) {
+    switch (code) {
+        case RLVD_ACT_RELU: return v > 0.f ? v : 0.f;
+        case RLVD_ACT_TANH: return tanhf(v);
+        case RLVD_ACT_LEAKY_RELU: return v > 0.f ? v : 0.01f * v;
+        default: return v / (1.0f + expf(-v));
+    }
+}
+
+struct ReadoutOut {
+    float *rl_q, *q0, *q1, *delta_e, *E_R, *E_P;
+};
+
+// y[n] = b[n] + sum_k W[n][k] * z[k]   (W out-major as in the checkpoint); lane = n.
+__device__ __forceinline__ float head_layer(const float* __restrict__ W, const float* __restrict__ b, int n_out,
+                                            int n_in, const float* z, int lane) {
+    float acc = 0.f;
+    if (lane < n_out) {
+        acc = __ldg(b + lane);
+        for (int k = 0; k < n_in; ++k) acc = fmaf(__ldg(W + lane * n_in + k), z[k], acc);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(RT) readout_kernel(int n_react, const int* __restrict__ node_ptr,
+                                                     const int* __restrict__ rs, const int* __restrict__ ps,
+                                                     const int* __restrict__ Z, const float* __restrict__ q,
+                                                     const Weights w, const rlvd_q_params qp,
+                                                     const float* __restrict__ d_temp, ReadoutOut out) {
+    extern __shared__ __align__(16) float sm[];
+    float* sR = sm;                 // [TA][QS]
+    float* sP = sm + TA * QS;       // [TA][QS]
+    float* red = sP + TA * QS;      // [TA][8] partial sums / scratch
+    float* eo = red + TA * 8;       // [2][TA] energy-head outputs (R, P)
+    float* hpart = eo + 2 * TA;     // [8][32] per-group partial pooled features
+    float* pool = hpart + 8 * 32;   // [32] h, then E_R, E_P, dE
+    float* zbuf = pool + 36;        // [64] head scratch
+
+    const int g = blockIdx.x;
+    if (g >= n_react) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int sr = rs[g], sp_ = ps[g];
+    const int r0 = node_ptr[sr], p0 = node_ptr[sp_];
+    const int n = node_ptr[sr + 1] - r0;
+    if (tid < 36) pool[tid] = 0.f;
+    __syncthreads();
+
+    for (int t0 = 0; t0 < n; t0 += TA) {
+        const int na = min(TA, n - t0);
+        // ---- load tiles (rows beyond na are zero)
+        for (int f = tid; f < TA * (F / 4); f += RT) {
+            const int a = f / (F / 4), c4 = f % (F / 4);
+            float4 vr = make_float4(0.f, 0.f, 0.f, 0.f), vp = vr;
+            if (a < na) {
+                vr = __ldg(reinterpret_cast<const float4*>(q + (int64_t)(r0 + t0 + a) * F) + c4);
+                vp = __ldg(reinterpret_cast<const float4*>(q + (int64_t)(p0 + t0 + a) * F) + c4);
+            }
+            *reinterpret_cast<float4*>(sR + a * QS + 4 * c4) = vr;
+            *reinterpret_cast<float4*>(sP + a * QS + 4 * c4) = vp;
+        }
+        __syncthreads();
+
+        // ---- H1: energy head on R and P.  thread: hidden unit nh = tid%64, atom group ag = tid/64 (4), atoms ag+4r
+        {
+            const int nh = tid & 63, ag = tid >> 6;
+            const float b0 = __ldg(w.en_b0 + nh), w3 = __ldg(w.en_w3 + nh);
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const float* S = side == 0 ? sR : sP;
+                float acc[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r] = b0;
+                for (int k = 0; k < F; k += 4) {
+                    const float w0 = __ldg(w.en_w0T + (k + 0) * 64 + nh), w1 = __ldg(w.en_w0T + (k + 1) * 64 + nh),
+                                w2 = __ldg(w.en_w0T + (k + 2) * 64 + nh), w3k = __ldg(w.en_w0T + (k + 3) * 64 + nh);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const float4 av = *reinterpret_cast<const float4*>(S + (ag + 4 * r) * QS + k);
+                        acc[r] = fmaf(av.x, w0, acc[r]);
+                        acc[r] = fmaf(av.y, w1, acc[r]);
+                        acc[r] = fmaf(av.z, w2, acc[r]);
+                        acc[r] = fmaf(av.w, w3k, acc[r]);
+                    }
+                }
+                // second layer: dot over the 64 hidden units = 2 warps per atom group
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    float v = act_fn(acc[r], qp.painn_head_act) * w3;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) red[(ag + 4 * r) * 8 + (wid & 1)] = v;
+                }
+                __syncthreads();
+                if (tid < TA) eo[side * TA + tid] = red[tid * 8] + red[tid * 8 + 1] + __ldg(w.en_b3);
+                __syncthreads();
+            }
+        }
+        // ---- pooled energies (thread 0, atom order)
+        if (tid == 0) {
+            float eR = pool[32], eP = pool[33], dE = pool[34];
+            for (int a = 0; a < na; ++a) {
+                const int s = __ldg(w.elem_lookup + min(max(__ldg(Z + r0 + t0 + a), 0), 99));
+                const float sc = __ldg(w.sp_scales + s), sh = __ldg(w.sp_shifts + s);
+                eR += fmaf(eo[a], sc, sh);
+                eP += fmaf(eo[TA + a], sc, sh);
+                dE += sc * (eo[TA + a] - eo[a]);
+            }
+            pool[32] = eR; pool[33] = eP; pool[34] = dE;
+        }
+        // ---- D = q_P - q_R (in place in sP)
+        for (int f = tid; f < TA * F; f += RT) {
+            const int a = f / F, cc = f % F;
+            sP[a * QS + cc] -= sR[a * QS + cc];
+        }
+        __syncthreads();
+        // ---- H2 layer 0: Hd = act(D·Wr0T + b0) → sR.  thread: n = tid%128, ag = tid/128 (2), atoms ag+2r
+        {
+            const int nh = tid & 127, ag = tid >> 7;
+            float acc[16];
+            const float b0 = __ldg(w.rr_b0 + nh);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) acc[r] = b0;
+            for (int k = 0; k < F; k += 4) {
+                const float w0 = __ldg(w.rr_w0T + (k + 0) * F + nh), w1 = __ldg(w.rr_w0T + (k + 1) * F + nh),
+                            w2 = __ldg(w.rr_w0T + (k + 2) * F + nh), w3k = __ldg(w.rr_w0T + (k + 3) * F + nh);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const float4 av = *reinterpret_cast<const float4*>(sP + (ag + 2 * r) * QS + k);
+                    acc[r] = fmaf(av.x, w0, acc[r]);
+                    acc[r] = fmaf(av.y, w1, acc[r]);
+                    acc[r] = fmaf(av.z, w2, acc[r]);
+                    acc[r] = fmaf(av.w, w3k, acc[r]);
+                }
+            }
+            __syncthreads();  // everyone finished reading sR (energy head) long ago; sP reads done
+#pragma unroll
+            for (int r = 0; r < 16; ++r) sR[(ag + 2 * r) * QS + nh] = act_fn(acc[r], qp.painn_head_act);
+        }
+        __syncthreads();
+        // ---- H2 layer 3 + sum pool: thread: n = tid%32, ag = tid/32 (8), atoms ag+8r
+        {
+            const int no = tid & 31, ag = tid >> 5;
+            float acc[4];
+            const float b3 = __ldg(w.rr_b3 + no);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = b3;
+            for (int k = 0; k < F; k += 4) {
+                const float w0 = __ldg(w.rr_w3T + (k + 0) * 32 + no), w1 = __ldg(w.rr_w3T + (k + 1) * 32 + no),
+                            w2 = __ldg(w.rr_w3T + (k + 2) * 32 + no), w3k = __ldg(w.rr_w3T + (k + 3) * 32 + no);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float4 av = *reinterpret_cast<const float4*>(sR + (ag + 8 * r) * QS + k);
+                    acc[r] = fmaf(av.x, w0, acc[r]);
+                    acc[r] = fmaf(av.y, w1, acc[r]);
+                    acc[r] = fmaf(av.z, w2, acc[r]);
+                    acc[r] = fmaf(av.w, w3k, acc[r]);
+                }
+            }
+            float part = 0.f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (ag + 8 * r < na) part += acc[r];
+            hpart[ag * 32 + no] = part;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            float h = pool[tid];
+#pragma unroll
+            for (int ag = 0; ag < 8; ++ag) h += hpart[ag * 32 + tid];
+            pool[tid] = h;
+        }
+        __syncthreads();
+    }
+
+    // ---- H3 / H4 in warp 0
+    if (wid == 0) {
+        const float E_R = pool[32], E_P = pool[33], dE = pool[34];
+        const float de_in = qp.delta_e_standardised ? (dE - qp.mean_delta_e) / qp.std_delta_e : dE;
+        float* z = zbuf;        // [33]
+        float* t1 = zbuf + 40;  // scratch
+        z[lane] = pool[lane];
+        if (lane == 0) z[32] = de_in;
+        __syncwarp();
+        // reaction_output 33 → 32 → 32 → 2
+        float v = act_fn(head_layer(w.ro_w[0], w.ro_b[0], 32, 33, z, lane), qp.painn_head_act);
+        t1[lane] = v;
+        __syncwarp();
+        v = act_fn(head_layer(w.ro_w[1], w.ro_b[1], 32, 32, t1, lane), qp.painn_head_act);
+        __syncwarp();
+        t1[lane] = v;
+        __syncwarp();
+        v = head_layer(w.ro_w[2], w.ro_b[2], 2, 32, t1, lane);
+        const float bhat = __shfl_sync(0xffffffffu, v, 0), fhat = __shfl_sync(0xffffffffu, v, 1);
+        const float barrier = fmaf(bhat, qp.std_barrier, qp.mean_barrier);
+        const float freq = fmaf(fhat, qp.std_freq, qp.mean_freq);
+        const float q0 = -barrier, q1 = freq;
+        const float T = d_temp != nullptr ? __ldg(d_temp + g) : qp.temperature;
+        const float kT = T * 8.617e-5f;
+        float rl = qp.alpha * (q0 + kT * q1) + qp.beta * (-dE);
+        if (qp.dqn) {
+            __syncwarp();
+            // Q_emb 33 → 16 → 16
+            v = act_fn(head_layer(w.qe_w[0], w.qe_b[0], 16, 33, z, lane), qp.dqn_head_act);
+            t1[lane] = v;
+            __syncwarp();
+            v = head_layer(w.qe_w[1], w.qe_b[1], 16, 16, t1, lane);
+            __syncwarp();
+            if (lane < 16) t1[lane] = v;
+            if (lane == 0) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    t1[16 + u] = qp.q_extra[u] == RLVD_QX_KT_X10 ? kT * 10.0f : dE;
+            }
+            __syncwarp();
+            // Q_output 18 → 32 → 32 → 1
+            v = act_fn(head_layer(w.qo_w[0], w.qo_b[0], 32, 18, t1, lane), qp.dqn_head_act);
+            __syncwarp();
+            z[lane] = v;
+            __syncwarp();
+            v = act_fn(head_layer(w.qo_w[1], w.qo_b[1], 32, 32, z, lane), qp.dqn_head_act);
+            __syncwarp();
+            t1[lane] = v;
+            __syncwarp();
+            v = head_layer(w.qo_w[2], w.qo_b[2], 1, 32, t1, lane);
+            rl += __shfl_sync(0xffffffffu, v, 0);
+        }
+        if (lane == 0) {
+            if (out.rl_q) out.rl_q[g] = rl;
+            if (out.q0) out.q0[g] = q0;
+            if (out.q1) out.q1[g] = q1;
+            if (out.delta_e) out.delta_e[g] = dE;
+            if (out.E_R) out.E_R[g] = E_R;
+            if (out.E_P) out.E_P[g] = E_P;
+        }
+    }
+}
+
+size_t readout_smem() { return (size_t)(2 * TA * QS + TA * 8 + 2 * TA + 8 * 32 + 36 + 128) * sizeof(float); }
+
+}  // namespace
+
+int launch_readout(rlvd_engine* e, cudaStream_t s, int n_react, const int* node_ptr, const int* rs, const int* ps,
+                   const int* Z, const float* q, const rlvd_q_params& qp, const float* d_temp, float* rl_q,
+                   float* q0, float* q1, float* delta_e, float* E_R, float* E_P) {
+    if (n_react <= 0) return 0;
+    ReadoutOut out{rl_q, q0, q1, delta_e, E_R, E_P};
+    Span sp(e, s, FAM_READOUT);
+    readout_kernel<<<n_react, RT, readout_smem(), s>>>(n_react, node_ptr, rs, ps, Z, q, e->w, qp, d_temp, out);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rlvd

@@ -1,0 +1,229 @@
+"""Python handle on one ``rlvd_engine`` (one per GPU / process).
+
+PyTorch is used here only for device memory, streams and (elsewhere) ``torch.distributed``; every
+kernel is launched through the C ABI of ``include/rlvd_b200.h``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT_CODES, QX_CODES, QParams, check
+
+
+@dataclass(frozen=True)
+class HeadSpec:
+    """Swappable head assumptions — mirrors ``oracle.painn_oracle.HeadSpec``."""
+    delta_e_input: str = "raw"
+    painn_head_activation: str = "silu"
+    dqn_head_activation: str = "silu"
+    q_extra: Tuple[str, str] = ("kT_x10", "delta_e")
+    name: str = "HEAD_SPEC_V0"
+
+
+HEAD_SPEC_V0 = HeadSpec()
+
+
+def cell_geometry(cells: np.ndarray, cutoff: float):
+    """fp32 inverse cells (fp32 image of the fp64 inverse) and per-axis periodic image ranges.
+
+    Same definitions as ``oracle.painn_oracle.inverse_cell_f32`` / ``image_range``: the two sides must
+    receive identical matrices for the edge sets to be bit-identical."""
+    cells64 = np.asarray(cells, dtype=np.float64).reshape(-1, 3, 3)
+    inv = np.linalg.inv(cells64).astype(np.float32)
+    vol = np.abs(np.linalg.det(cells64))
+    cross = np.stack([np.cross(cells64[:, 1], cells64[:, 2]), np.cross(cells64[:, 2], cells64[:, 0]),
+                      np.cross(cells64[:, 0], cells64[:, 1])], axis=1)
+    h = vol[:, None] / np.linalg.norm(cross, axis=2)
+    img = np.floor(cutoff / h + 0.5 + 1e-9).astype(np.int32)
+    return inv, img
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """Owns the device-side weights and workspaces of one GPU."""
+
+    def __init__(self, device: int | str | torch.device = 0):
+        self.lib = _lib.load()
+        dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        if dev.type != "cuda":
+            raise RuntimeError("rlvacdiffsim_b200 runs on CUDA devices only (no CPU fallback)")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        handle = C.c_void_p()
+        check(self.lib.rlvd_engine_create(self.device.index, C.byref(handle)))
+        self._h = handle
+        self.cutoff = 5.0
+        self.means: Dict[str, float] = {}
+        self.stddevs: Dict[str, float] = {}
+        self._pinned: Dict[str, torch.Tensor] = {}
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self.lib.rlvd_engine_destroy(h)
+            self._h = None
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], hyper_parameters: dict) -> None:
+        for name, t in state_dict.items():
+            t = t.detach().cpu()
+            if t.is_floating_point():
+                a = np.ascontiguousarray(t.to(torch.float32).numpy().reshape(-1))
+                check(self.lib.rlvd_set_weight(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.size, 0))
+            else:
+                a = np.ascontiguousarray(t.to(torch.int32).numpy().reshape(-1))
+                check(self.lib.rlvd_set_weight(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.size, 1))
+        check(self.lib.rlvd_finalize_weights(self._h))
+        rm = hyper_parameters["reaction_model"]
+        self.cutoff = float(rm["cutoff"])
+        self.means = {k: float(v) for k, v in rm["means"].items()}
+        self.stddevs = {k: float(v) for k, v in rm["stddevs"].items()}
+
+    def q_params(self, q_params: dict, spec: HeadSpec = HEAD_SPEC_V0) -> QParams:
+        qp = QParams()
+        qp.alpha = float(q_params["alpha"])
+        qp.beta = float(q_params["beta"])
+        qp.dqn = int(bool(q_params.get("dqn", False)))
+        qp.temperature = float(q_params.get("temperature", 0.0))
+        qp.delta_e_standardised = int(spec.delta_e_input != "raw")
+        qp.painn_head_act = ACT_CODES[spec.painn_head_activation]
+        qp.dqn_head_act = ACT_CODES[spec.dqn_head_activation]
+        qp.q_extra[0] = QX_CODES[spec.q_extra[0]]
+        qp.q_extra[1] = QX_CODES[spec.q_extra[1]]
+        qp.mean_barrier, qp.std_barrier = self.means["barrier"], self.stddevs["barrier"]
+        qp.mean_freq, qp.std_freq = self.means["freq"], self.stddevs["freq"]
+        qp.mean_delta_e, qp.std_delta_e = self.means["delta_e"], self.stddevs["delta_e"]
+        return qp
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ K1
+    def radius_graph(self, pos: torch.Tensor, cell: torch.Tensor, inv_cell: torch.Tensor, img_range: torch.Tensor,
+                     node_ptr: torch.Tensor, cutoff: Optional[float] = None):
+        """→ (row_ptr i32[M+1], col i32[E], shift i8[E,3], node_struct i32[M]); receiver-sorted CSR."""
+        cutoff = self.cutoff if cutoff is None else cutoff
+        n_struct, M = node_ptr.numel() - 1, pos.shape[0]
+        dev = self.device
+        row_ptr = torch.empty(M + 1, dtype=torch.int32, device=dev)
+        node_struct = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+        n_edges = torch.zeros(1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            check(self.lib.rlvd_radius_graph_count(self._h, self._stream(), n_struct, M, _ptr(node_ptr), _ptr(pos),
+                                                   _ptr(cell), _ptr(inv_cell), _ptr(img_range), cutoff,
+                                                   _ptr(row_ptr), _ptr(node_struct), _ptr(n_edges)))
+            E = int(n_edges.item())
+            if E >= 2 ** 31 - 1:
+                raise RuntimeError(f"{E} edges overflow int32 CSR offsets; split the batch")
+            col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+            shift = torch.empty((max(E, 1), 3), dtype=torch.int8, device=dev)
+            check(self.lib.rlvd_radius_graph_fill(self._h, self._stream(), n_struct, M, _ptr(node_ptr), _ptr(pos),
+                                                  _ptr(cell), _ptr(inv_cell), _ptr(img_range), cutoff,
+                                                  _ptr(row_ptr), E, _ptr(col), _ptr(shift)))
+        return row_ptr, col[:E], shift[:E], node_struct[:M]
+
+    # ------------------------------------------------------------------ K2..K4
+    def representation(self, Z: torch.Tensor, pos: torch.Tensor, cell: torch.Tensor, node_struct: torch.Tensor,
+                       row_ptr: torch.Tensor, col: torch.Tensor, shift: torch.Tensor, n_struct: int,
+                       return_mu: bool = False):
+        M = pos.shape[0]
+        q = torch.empty((M, 128), dtype=torch.float32, device=self.device)
+        mu = torch.empty((M, 3, 128), dtype=torch.float32, device=self.device) if return_mu else None
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_painn_representation(self._h, self._stream(), n_struct, M, col.shape[0], _ptr(Z),
+                                                     _ptr(pos), _ptr(cell), _ptr(node_struct), _ptr(row_ptr),
+                                                     _ptr(col), _ptr(shift), _ptr(q), _ptr(mu)))
+        return (q, mu) if return_mu else q
+
+    # ------------------------------------------------------------------ K5
+    def readout(self, q: torch.Tensor, Z: torch.Tensor, node_ptr: torch.Tensor, react_struct: torch.Tensor,
+                prod_struct: torch.Tensor, qp: QParams, temperature: Optional[torch.Tensor] = None
+                ) -> Dict[str, torch.Tensor]:
+        G = react_struct.numel()
+        out = torch.empty((6, max(G, 1)), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_reaction_readout(self._h, self._stream(), G, q.shape[0], _ptr(node_ptr),
+                                                 _ptr(react_struct), _ptr(prod_struct), _ptr(Z), _ptr(q),
+                                                 C.byref(qp), _ptr(temperature), _ptr(out[0]), _ptr(out[1]),
+                                                 _ptr(out[2]), _ptr(out[3]), _ptr(out[4]), _ptr(out[5])))
+        names = ("rl_q", "q0", "q1", "delta_e", "E_R", "E_P")
+        return {k: out[i, :G] for i, k in enumerate(names)}
+
+    # ------------------------------------------------------------------ whole path, device-resident inputs
+    def score_device(self, Z, pos, cell, inv_cell, img_range, node_ptr, react_struct, prod_struct, qp: QParams,
+                     temperature=None) -> Dict[str, torch.Tensor]:
+        n_struct = node_ptr.numel() - 1
+        row_ptr, col, shift, node_struct = self.radius_graph(pos, cell, inv_cell, img_range, node_ptr)
+        q = self.representation(Z, pos, cell, node_struct, row_ptr, col, shift, n_struct)
+        out = self.readout(q, Z, node_ptr, react_struct, prod_struct, qp, temperature)
+        out["n_edges"] = col.shape[0]
+        return out
+
+    # ------------------------------------------------------------------ whole path, host buffers (e2e)
+    def _pin(self, key: str, arr: np.ndarray) -> torch.Tensor:
+        """Copy ``arr`` into a cached pinned staging tensor and return the (sliced) tensor."""
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        buf = self._pinned.get(key)
+        if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+            buf = torch.empty(max(t.numel(), 16), dtype=t.dtype).pin_memory()
+            self._pinned[key] = buf
+        view = buf[: t.numel()]
+        view.copy_(t.reshape(-1))
+        return view
+
+    def score_host(self, Z: np.ndarray, pos: np.ndarray, cells: np.ndarray, node_ptr: np.ndarray,
+                   react_struct: np.ndarray, prod_struct: np.ndarray, qp: QParams,
+                   temperature: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
+        """H2D + K1..K5 + D2H in one C call (``rlvd_score_reactions_host``); inputs are numpy arrays."""
+        n_struct, M, G = len(node_ptr) - 1, int(node_ptr[-1]), len(react_struct)
+        inv, img = cell_geometry(cells, self.cutoff)
+        h = {
+            "node_ptr": self._pin("node_ptr", np.asarray(node_ptr, dtype=np.int32)),
+            "Z": self._pin("Z", np.asarray(Z, dtype=np.int32)),
+            "pos": self._pin("pos", np.asarray(pos, dtype=np.float32)),
+            "cell": self._pin("cell", np.asarray(cells, dtype=np.float32)),
+            "inv": self._pin("inv", inv),
+            "img": self._pin("img", img),
+            "rs": self._pin("rs", np.asarray(react_struct, dtype=np.int32)),
+            "ps": self._pin("ps", np.asarray(prod_struct, dtype=np.int32)),
+        }
+        t = None if temperature is None else self._pin("temp", np.asarray(temperature, dtype=np.float32))
+        out = self._pinned.get("out")
+        if out is None or out.numel() < 6 * G:
+            out = torch.empty(max(6 * G, 16), dtype=torch.float32).pin_memory()
+            self._pinned["out"] = out
+        o = [out[i * G:(i + 1) * G] for i in range(6)]
+        n_edges = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_score_reactions_host(
+                self._h, self._stream(), n_struct, M, _ptr(h["node_ptr"]), _ptr(h["Z"]), _ptr(h["pos"]),
+                _ptr(h["cell"]), _ptr(h["inv"]), _ptr(h["img"]), self.cutoff, G, _ptr(h["rs"]), _ptr(h["ps"]),
+                C.byref(qp), _ptr(t), _ptr(o[0]), _ptr(o[1]), _ptr(o[2]), _ptr(o[3]), _ptr(o[4]), _ptr(o[5]),
+                C.byref(n_edges)))
+        names = ("rl_q", "q0", "q1", "delta_e", "E_R", "E_P")
+        res = {k: o[i].numpy().copy() for i, k in enumerate(names)}
+        res["n_edges"] = int(n_edges.value)
+        return res
+
+    # ------------------------------------------------------------------ introspection
+    def launch_count(self) -> int:
+        return int(self.lib.rlvd_launch_count(self._h))
+
+    def profile(self, on: bool) -> None:
+        check(self.lib.rlvd_profile_enable(self._h, int(on)))
+
+    def profile_reset(self) -> None:
+        check(self.lib.rlvd_profile_reset(self._h))
+
+    def profile_read(self, family: str) -> Tuple[float, int]:
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        check(self.lib.rlvd_profile_read(self._h, family.encode(), C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)

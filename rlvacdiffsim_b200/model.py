@@ -1,0 +1,277 @@
+"""Host-side mirror of rgnn's ``dqn_v2`` / ``painn`` / ``t_net`` model classes.
+
+The classes are ``nn.Module`` parameter holders whose ``state_dict`` keys are exactly those of the
+bundled checkpoint ``data/model_trained``, so ``.load(path)`` / ``.save(path)`` /
+``.to`` / ``.eval`` / ``.state_dict`` / ``.named_parameters`` behave as the reference's callers expect
+(``rlsim/drl/deploy.py:18``, ``train.py:48-58``, ``trainer.py:36-39,120``).  ``forward`` does no torch
+arithmetic: it hands device pointers to the CUDA engine (``include/rlvd_b200.h``).  There is no eager
+fallback — on a machine without the built library or without a CUDA device ``forward`` raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .engine import HEAD_SPEC_V0, Engine, HeadSpec, cell_geometry
+
+_ACTS = {"silu": nn.SiLU, "relu": nn.ReLU, "tanh": nn.Tanh, "leaky_relu": nn.LeakyReLU}
+
+
+class MLP(nn.Module):
+    """``layers = [Linear, act, Dropout] * n_hidden + [Linear]`` → checkpoint keys ``layers.{0,3,6}``."""
+
+    def __init__(self, n_input: int, n_output: int, hidden_layers, activation: str = "silu",
+                 dropout_rate: float = 0.0):
+        super().__init__()
+        mods: List[nn.Module] = []
+        d = n_input
+        for h in hidden_layers:
+            mods += [nn.Linear(d, h), _ACTS[activation](), nn.Dropout(dropout_rate)]
+            d = h
+        mods.append(nn.Linear(d, n_output))
+        self.layers = nn.Sequential(*mods)
+
+
+class _Buffer(nn.Module):
+    def __init__(self, name: str, value: torch.Tensor):
+        super().__init__()
+        self.register_buffer(name, value)
+
+
+class _Interaction(nn.Module):
+    def __init__(self, F: int):
+        super().__init__()
+        self.interatomic_context_net = MLP(F, 3 * F, (F,), "silu")
+
+
+class _Mixing(nn.Module):
+    def __init__(self, F: int):
+        super().__init__()
+        self.intraatomic_context_net = MLP(2 * F, 3 * F, (F,), "silu")
+        self.mu_channel_mix = nn.Linear(F, 2 * F, bias=False)
+
+
+class PaiNNRepresentation(nn.Module):
+    def __init__(self, hidden_channels=128, n_interactions=3, n_rbf=20, cutoff=5.0, max_z=100):
+        super().__init__()
+        F = hidden_channels
+        self.cutoff_fn = _Buffer("cutoff", torch.tensor(float(cutoff)))
+        self.radial_basis = _Buffer("freqs", torch.arange(1, n_rbf + 1, dtype=torch.float32) * (np.pi / cutoff))
+        self.embedding = nn.Embedding(max_z, F)
+        self.filter_net = nn.Linear(n_rbf, n_interactions * 3 * F)
+        self.interactions = nn.ModuleList([_Interaction(F) for _ in range(n_interactions)])
+        self.mixing = nn.ModuleList([_Mixing(F) for _ in range(n_interactions)])
+
+
+class SpeciesEnergyScale(nn.Module):
+    def __init__(self, species):
+        super().__init__()
+        from .structures import SYMBOL_TO_Z
+        self.scales = nn.Parameter(torch.ones(len(species)))
+        self.shifts = nn.Parameter(torch.zeros(len(species)))
+        look = torch.zeros(100, dtype=torch.int64)
+        for i, s in enumerate(species):
+            look[SYMBOL_TO_Z[s]] = i
+        self.register_buffer("elem_lookup", look)
+
+
+class PaiNN(nn.Module):
+    """``registry.get_reaction_model_class("painn")`` — the reaction model inside ``dqn_v2``."""
+
+    def __init__(self, species=("Cr", "Co", "Ni"), cutoff=5.0, hidden_channels=128, reaction_feat=32,
+                 n_interactions=3, rbf_type="bessel", n_rbf=20, trainable_rbf=False, activation="silu",
+                 shared_interactions=False, shared_filters=False, epsilon=1e-8, means=None, stddevs=None,
+                 pool_method="sum", **_ignored):
+        super().__init__()
+        if (hidden_channels, n_rbf, n_interactions) != (128, 20, 3) or rbf_type != "bessel" or pool_method != "sum":
+            raise NotImplementedError("the sm_100a kernels are specialised for painn F=128, n_rbf=20, L=3, bessel, sum")
+        self.hyper = dict(species=list(species), cutoff=cutoff, hidden_channels=hidden_channels,
+                          reaction_feat=reaction_feat, n_interactions=n_interactions, rbf_type=rbf_type, n_rbf=n_rbf,
+                          trainable_rbf=trainable_rbf, activation=activation, shared_interactions=shared_interactions,
+                          shared_filters=shared_filters, epsilon=epsilon,
+                          means=means or {"barrier": 0.0, "freq": 0.0, "delta_e": 0.0},
+                          stddevs=stddevs or {"barrier": 1.0, "freq": 1.0, "delta_e": 1.0}, pool_method=pool_method)
+        self.hyper["@name"] = "painn"
+        self.cutoff = float(cutoff)
+        self.reaction_feat = reaction_feat
+        F = hidden_channels
+        self.species_energy_scale = SpeciesEnergyScale(species)
+        self.representation = PaiNNRepresentation(F, n_interactions, n_rbf, cutoff)
+        self.energy_output = MLP(F, 1, (F // 2,), activation)
+        self.reaction_representation = MLP(F, reaction_feat, (F,), activation)
+        self.reaction_output = MLP(reaction_feat + 1, 2, (reaction_feat, reaction_feat), activation)
+
+    @classmethod
+    def load(cls, path: str) -> "PaiNN":
+        ck = torch.load(path, weights_only=True, map_location="cpu")
+        hp = dict(ck["hyper_parameters"])
+        hp.pop("@name", None)
+        model = cls(**hp)
+        model.load_state_dict(ck["state_dict"])
+        return model
+
+    def save(self, path: str) -> None:
+        torch.save({"state_dict": self.state_dict(), "hyper_parameters": _plain(self.hyper)}, path)
+
+
+def _plain(obj):
+    if isinstance(obj, dict):
+        return {k: _plain(v) for k, v in obj.items()}
+    if torch.is_tensor(obj):
+        return obj.detach().cpu()
+    return obj
+
+
+class _EngineMixin:
+    """Keeps one CUDA :class:`Engine` per device in sync with the module's parameters."""
+
+    head_spec: HeadSpec = HEAD_SPEC_V0
+
+    def _engine_for(self, device: torch.device) -> Engine:
+        engines = self.__dict__.setdefault("_engines", {})
+        key = (device.type, device.index)
+        eng = engines.get(key)
+        sig = tuple((p.data_ptr(), p._version) for p in self._engine_tensors())
+        if eng is None:
+            eng = Engine(device)
+            engines[key] = eng
+            eng._sig = None
+        if eng._sig != sig:
+            sd, hp = self._engine_state()
+            eng.load_state_dict(sd, hp)
+            eng._sig = sig
+        return eng
+
+
+class DQNv2(nn.Module, _EngineMixin):
+    """``registry.get_model_class("dqn_v2")`` — ``model(batch, q_params)["rl_q"]`` (``simulator.py:56``)."""
+
+    def __init__(self, reaction_model: PaiNN, N_emb: int = 16, N_feat: int = 32, dropout_rate: float = 0.15,
+                 canonical: bool = True, **_ignored):
+        super().__init__()
+        self.reaction_model = reaction_model
+        self.hyper = {"@name": "dqn_v2", "N_emb": N_emb, "N_feat": N_feat, "dropout_rate": dropout_rate,
+                      "canonical": canonical}
+        rf = reaction_model.reaction_feat
+        self.Q_emb = MLP(rf + 1, N_emb, (N_emb,), "silu", dropout_rate)
+        self.Q_output = MLP(N_emb + 2, 1, (N_feat, N_feat), "silu", dropout_rate)
+        if (N_emb, N_feat, rf) != (16, 32, 32):
+            raise NotImplementedError("the readout kernel is specialised for N_emb=16, N_feat=32, reaction_feat=32")
+        self.kb = 8.617 * 10 ** -5
+        self.dedup_reactants = False   # share one representation pass between candidates of the same state
+
+    # ---- checkpoint I/O: {"state_dict", "hyper_parameters"} (SURVEY.md §5 checkpoint/resume)
+    @classmethod
+    def load(cls, path: str) -> "DQNv2":
+        ck = torch.load(path, weights_only=True, map_location="cpu")
+        hp = dict(ck["hyper_parameters"])
+        hp.pop("@name", None)
+        rm_hp = dict(hp.pop("reaction_model"))
+        rm_hp.pop("@name", None)
+        model = cls(PaiNN(**rm_hp), **hp)
+        model.load_state_dict(ck["state_dict"])
+        return model
+
+    def save(self, path: str) -> None:
+        hp = dict(self.hyper)
+        hp["reaction_model"] = _plain(self.reaction_model.hyper)
+        torch.save({"state_dict": self.state_dict(), "hyper_parameters": hp}, path)
+
+    # ---- engine plumbing
+    def _engine_tensors(self):
+        return list(self.parameters()) + list(self.buffers())
+
+    def _engine_state(self):
+        hp = dict(self.hyper)
+        hp["reaction_model"] = self.reaction_model.hyper
+        return self.state_dict(), hp
+
+    @property
+    def cutoff(self) -> float:
+        return self.reaction_model.cutoff
+
+    def forward(self, batch, q_params: Dict[str, float | bool]) -> Dict[str, torch.Tensor]:
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "dqn_v2 backward (replay-minibatch training, SURVEY.md §8a row B1) has no sm_100a kernels yet; "
+                "call under torch.no_grad() / .eval() for scoring")
+        pos = batch["pos"]
+        if pos.device.type != "cuda":
+            raise RuntimeError("dqn_v2.forward needs the batch on a CUDA device (no CPU fallback); use batch_to")
+        dev = pos.device
+        eng = self._engine_for(dev)
+        G = batch.num_graphs
+        n_atoms_host = np.diff(batch["ptr"].cpu().numpy()) if batch["ptr"].device.type != "cpu" else \
+            np.diff(batch["ptr"].numpy())
+        cells64 = np.asarray(batch["cell64"], dtype=np.float64)
+        if self.dedup_reactants:
+            keys = batch["reactant_key"]
+            first: Dict[int, int] = {}
+            r_of_graph = []
+            uniq: List[int] = []
+            for g, k in enumerate(keys):
+                if k not in first:
+                    first[k] = len(uniq)
+                    uniq.append(g)
+                r_of_graph.append(first[k])
+        else:
+            uniq = list(range(G))
+            r_of_graph = list(range(G))
+        nR = len(uniq)
+        ptr = batch["ptr"].to(dev)
+        if nR == G:
+            pos_all = torch.cat([pos, batch["pos_product"]], dim=0)
+            Z_all = torch.cat([batch["elems"], batch["elems"]]).to(torch.int32)
+            cell_all = torch.cat([batch["cell"], batch["cell"]], dim=0)
+            counts = np.concatenate([n_atoms_host, n_atoms_host])
+            cells_host = np.concatenate([cells64, cells64])
+        else:
+            sel = torch.cat([torch.arange(int(ptr[g]), int(ptr[g + 1]), device=dev) for g in uniq])
+            pos_all = torch.cat([pos[sel], batch["pos_product"]], dim=0)
+            Z_all = torch.cat([batch["elems"][sel], batch["elems"]]).to(torch.int32)
+            cell_all = torch.cat([batch["cell"][uniq], batch["cell"]], dim=0)
+            counts = np.concatenate([n_atoms_host[uniq], n_atoms_host])
+            cells_host = np.concatenate([cells64[uniq], cells64])
+        node_ptr_host = np.zeros(len(counts) + 1, dtype=np.int32)
+        np.cumsum(counts, out=node_ptr_host[1:])
+        inv, img = cell_geometry(cells_host, eng.cutoff)
+        node_ptr = torch.from_numpy(node_ptr_host).to(dev)
+        inv_d = torch.from_numpy(inv).to(dev)
+        img_d = torch.from_numpy(img).to(dev)
+        rs = torch.tensor(r_of_graph, dtype=torch.int32, device=dev)
+        ps = torch.arange(nR, nR + G, dtype=torch.int32, device=dev)
+        qp = eng.q_params(q_params, self.head_spec)
+        out = eng.score_device(Z_all.contiguous(), pos_all.contiguous(), cell_all.contiguous(), inv_d, img_d,
+                               node_ptr, rs, ps, qp)
+        out["barrier"] = -out["q0"]
+        out["freq"] = out["q1"]
+        return out
+
+
+class TNet(nn.Module, _EngineMixin):
+    """``registry.get_model_class("t_net")`` placeholder surface (``rlsim/time/train.py:44-48``).
+
+    No t_net checkpoint ships with the reference and rgnn's head is not recoverable from the repo, so the
+    head kernel is not built in this round; constructing the class works (so drivers can be wired) and
+    ``forward`` raises until SURVEY.md §8a row T1 lands."""
+
+    def __init__(self, reaction_model: PaiNN, n_feat: int = 64, pooling: str = "mean", dropout_rate: float = 0.1,
+                 tau0: float = 1.0, D_scaler: float = 1 / 256, T_scaler_m: float = 7918.951990135471, **_ignored):
+        super().__init__()
+        self.representation = reaction_model.representation
+        self.cutoff = reaction_model.cutoff
+        self.tau0 = tau0
+        self.tau = tau0
+        self.hyper = {"@name": "t_net", "n_feat": n_feat, "pooling": pooling, "dropout_rate": dropout_rate,
+                      "tau0": tau0, "D_scaler": D_scaler, "T_scaler_m": T_scaler_m}
+        self.time_output = MLP(reaction_model.hyper["hidden_channels"] + 2, 1, (n_feat, n_feat), "silu", dropout_rate)
+
+    @classmethod
+    def load_representation(cls, reaction_model: PaiNN, **cfg) -> "TNet":
+        return cls(reaction_model, **cfg)
+
+    def forward(self, batch, inference: bool = False, training: bool = False):
+        raise NotImplementedError("t_net head kernel (SURVEY.md §8a row T1) is scheduled after the Q path")

@@ -1,0 +1,226 @@
+"""The callers of the hot path: ``RLSimulator.select_action`` and a replica-batched variant.
+
+:class:`RLSimulator` keeps the reference's signature and return values (``rlsim/drl/simulator.py:26-103``):
+candidates → ``convert_to_graph_list`` → ``ReactionDataset`` → ``DataLoader(batch_size=16)`` →
+``batch_to`` → ``model(batch, q_params)["rl_q"]`` → softmax(Q / kT) → ``np.random.choice``.
+
+:class:`ReplicaScorer` is the B200-first entry the reference lacks: the reference loops replicas
+serially (``rlsim/drl/deploy.py:75-94``); here all candidates of many independent replicas go through
+ONE call of the C ABI from pinned host buffers, and replicas shard across ranks with no data-path
+collective.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .actions import get_action_space, get_action_space_legacy
+from .engine import Engine
+from .graph import DataLoader, ReactionDataset, ReactionGraph, batch_to
+from .structures import Atoms, apply_action
+
+KB_EV = 8.617 * 10 ** -5   # simulator.py:40
+
+
+def convert_to_graph_list(atoms, actions: Sequence[Sequence[float]]) -> List[ReactionGraph]:
+    """``simulator.py:439-460`` / ``trainer.py:185-205``: one reaction graph per candidate hop."""
+    return [ReactionGraph.from_ase(atoms, apply_action(atoms, act)) for act in actions]
+
+
+class LatticeEnv:
+    """The slice of ``rlsim.environment.Environment`` the scoring path touches: ``atoms``,
+    ``calc_params["device"]``, ``step`` (``environment.py:220-241``) and ``normalize_positions``.
+    Relaxation / NEB (ASE + MACE) are outside this build's scope."""
+
+    def __init__(self, atoms, calc_params: Optional[dict] = None):
+        self.atoms = atoms
+        self.calc_params = dict(calc_params or {"device": "cuda"})
+        self.n_atom = len(atoms)
+
+    def get_calculator(self, **_kw):
+        return None
+
+    def step(self, action: Sequence[float]) -> None:
+        self.atoms = apply_action(self.atoms, action)
+
+    def normalize_positions(self) -> None:
+        if hasattr(self.atoms, "wrap"):
+            self.atoms.wrap()
+
+
+class RLSimulator:
+    def __init__(self, environment, model=None,
+                 q_params: Dict[str, float | bool] | None = {"alpha": 0.0, "beta": 0.5, "dqn": True},
+                 sro_pixel=None, save_sro: bool = False, **kwargs):
+        self.env = environment
+        self.calculator = self.env.get_calculator(**self.env.calc_params) if hasattr(self.env, "get_calculator") else None
+        self.q_params = dict(q_params)
+        self.model = model
+        self.device = self.env.calc_params["device"]
+        self.kb = KB_EV
+        if sro_pixel is not None:
+            raise NotImplementedError("the SRO-pixel action filter (simulator.py:60-92) is outside the hot path")
+        self.sro_pixel = None
+        self.save_sro = save_sro
+        self.kwargs = kwargs
+
+    def update_q_params(self, **new_q_params) -> None:
+        self.q_params.update(**new_q_params)
+
+    def select_action(self, action_space, temperature):
+        self.update_q_params(**{"temperature": temperature})
+        self.model.to(self.device)
+        self.model.eval()
+        dataset = ReactionDataset(convert_to_graph_list(self.env.atoms, action_space))
+        total_q_list = []
+        dataloader = DataLoader(dataset, batch_size=16)
+        with torch.no_grad():
+            for batch in dataloader:
+                batch = batch_to(batch, self.device)
+                rl_q = self.model(batch, q_params=self.q_params)["rl_q"]
+                total_q_list.append(rl_q.detach())
+        Q = torch.concat(total_q_list, dim=-1)
+        action_probs = nn.Softmax(dim=0)(Q / (temperature * self.kb))
+        p = action_probs.detach().cpu().numpy()
+        action = np.random.choice(len(p), p=p)
+        return action, action_probs, Q, None
+
+    def _action_space(self):
+        enumerator = self.kwargs.get("enumerator", "live")
+        a = self.kwargs.get("lattice_parameter", None)
+        if enumerator == "legacy":
+            return get_action_space_legacy(self.env, a if a is not None else 3.528)
+        return get_action_space(self.env, lattice_parameter=a) if a is not None else get_action_space(self.env)
+
+    def run_LSS(self, horizon: int, temperature_schedule) -> Tuple[list, list]:
+        """Scoring-only LSS loop (``simulator.py:187-236`` without the MACE relaxations / file writes)."""
+        Qlist, action_idx_list = [[]], [[]]
+        for tstep in range(horizon):
+            T = temperature_schedule(tstep) if callable(temperature_schedule) else temperature_schedule
+            action_space = self._action_space()
+            act_id, _, Q, _ = self.select_action(action_space, T)
+            self.env.step(action_space[act_id])
+            Qlist.append(Q.tolist())
+            action_idx_list.append(int(act_id))
+        return Qlist, action_idx_list
+
+    def run_TKS(self, horizon: int, temperature: float):
+        """``simulator.py:238-287``: residence-time clock ``dt = 1e-6 / sum(exp(Q/kT))``."""
+        assert not self.q_params["dqn"], "TKS is only available for dqn==False."
+        kT = temperature * 8.617 * 10 ** -5
+        tlist, Qlist, action_idx_list = [0], [[]], [None]
+        for _ in range(horizon):
+            action_space = self._action_space()
+            act_id, _, Q, _ = self.select_action(action_space, temperature)
+            self.env.step(action_space[act_id])
+            Gamma = float(torch.sum(torch.exp(Q / kT)))
+            tlist.append(tlist[-1] + 1 / Gamma * 10 ** -6)
+            Qlist.append(Q.tolist())
+            action_idx_list.append(int(act_id))
+        return Qlist, action_idx_list, tlist
+
+
+class ThermalAnnealing:
+    """``simulator.py:418-436``."""
+
+    def __init__(self, total_horizon, T_start, T_end, annealing_time=None, T_speed=None):
+        if T_speed is not None and annealing_time is None:
+            self.annealing_time = int((T_start - T_end) / T_speed)
+        elif annealing_time is not None and T_speed is None:
+            self.annealing_time = annealing_time
+        else:
+            raise ValueError("Annealing time is not given")
+        assert self.annealing_time <= total_horizon
+        self.T_start, self.T_end = T_start, T_end
+
+    def get_temperature(self, tstep):
+        if tstep <= self.annealing_time:
+            return self.T_start - (self.T_start - self.T_end) * tstep / self.annealing_time
+        return self.T_end
+
+
+# ----------------------------------------------------------------------------- replica-batched scoring
+
+def pack_replicas(replicas: Sequence[Atoms], action_spaces: Sequence[Sequence[Sequence[float]]],
+                  dedup_reactants: bool = False):
+    """Flatten many replicas × candidates into the structure/pair arrays of ``rlvd_score_reactions_host``.
+
+    Like-for-like with the reference (``dedup_reactants=False``) every candidate carries its own reactant
+    structure (2 passes per Q-eval); with ``dedup_reactants=True`` the candidates of a replica share one."""
+    Zs, poss, cells, counts, rs, ps, owner = [], [], [], [], [], [], []
+    n_struct = 0
+    for r, (atoms, acts) in enumerate(zip(replicas, action_spaces)):
+        Z = np.asarray(atoms.get_atomic_numbers(), dtype=np.int32)
+        P = np.asarray(atoms.get_positions(), dtype=np.float64)
+        cell = np.asarray(atoms.get_cell(), dtype=np.float64)
+        if dedup_reactants:
+            Zs.append(Z); poss.append(P.astype(np.float32)); cells.append(cell); counts.append(len(Z))
+            shared = n_struct
+            n_struct += 1
+        for act in acts:
+            if not dedup_reactants:
+                Zs.append(Z); poss.append(P.astype(np.float32)); cells.append(cell); counts.append(len(Z))
+                rs.append(n_struct)
+                n_struct += 1
+            else:
+                rs.append(shared)
+            Pp = P.copy()
+            Pp[int(act[0])] += np.asarray(act[1:4], dtype=np.float64)
+            Zs.append(Z); poss.append(Pp.astype(np.float32)); cells.append(cell); counts.append(len(Z))
+            ps.append(n_struct)
+            n_struct += 1
+            owner.append(r)
+    node_ptr = np.zeros(n_struct + 1, dtype=np.int32)
+    np.cumsum(np.asarray(counts, dtype=np.int64), out=node_ptr[1:])
+    return {"Z": np.concatenate(Zs), "pos": np.concatenate(poss), "cells": np.stack(cells), "node_ptr": node_ptr,
+            "react_struct": np.asarray(rs, dtype=np.int32), "prod_struct": np.asarray(ps, dtype=np.int32),
+            "owner": np.asarray(owner, dtype=np.int64)}
+
+
+class ReplicaScorer:
+    """Scores every candidate of many independent replicas in one device pass and selects actions."""
+
+    def __init__(self, model, device: int | str = 0, dedup_reactants: bool = False, max_structs_per_call: int = 4096):
+        self.model = model
+        self.device = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        self.dedup = dedup_reactants
+        self.max_structs = max_structs_per_call
+        self.engine: Engine = model._engine_for(self.device)
+
+    def score(self, replicas: Sequence[Atoms], action_spaces, q_params: dict,
+              temperatures: Optional[Sequence[float]] = None) -> List[np.ndarray]:
+        """→ per-replica arrays of rl_q (one entry per candidate)."""
+        qp = self.engine.q_params(q_params, self.model.head_spec)
+        out: List[np.ndarray] = []
+        per = 2 if not self.dedup else 1
+        start = 0
+        while start < len(replicas):
+            n_structs, stop = 0, start
+            while stop < len(replicas):
+                need = len(action_spaces[stop]) * per + (1 if self.dedup else 0)
+                if stop > start and n_structs + need > self.max_structs:
+                    break
+                n_structs += need
+                stop += 1
+            pk = pack_replicas(replicas[start:stop], action_spaces[start:stop], self.dedup)
+            temp = None
+            if temperatures is not None:
+                temp = np.asarray(temperatures, dtype=np.float32)[start:stop][pk["owner"]]
+            res = self.engine.score_host(pk["Z"], pk["pos"], pk["cells"], pk["node_ptr"], pk["react_struct"],
+                                         pk["prod_struct"], qp, temp)
+            q = res["rl_q"]
+            for r in range(stop - start):
+                out.append(q[pk["owner"] == r])
+            start = stop
+        return out
+
+    @staticmethod
+    def select(Q: np.ndarray, temperature: float, rng: Optional[np.random.Generator] = None) -> Tuple[int, np.ndarray]:
+        """softmax(Q / kT) in fp32 like ``simulator.py:94`` then a draw (global ``np.random`` if no rng)."""
+        z = torch.from_numpy(np.asarray(Q, dtype=np.float32)) / (temperature * KB_EV)
+        p = torch.softmax(z, dim=0).numpy()
+        idx = int(np.random.choice(len(p), p=p)) if rng is None else int(rng.choice(len(p), p=p / p.sum()))
+        return idx, p

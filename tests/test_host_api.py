@@ -1,0 +1,127 @@
+"""CPU: the host-side mirror of the reference interface — no GPU compute."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD, ROOT
+import rlvacdiffsim_b200 as rb
+from rlvacdiffsim_b200 import _lib
+from rlvacdiffsim_b200.engine import cell_geometry
+from rlvacdiffsim_b200.simulator import (LatticeEnv, RLSimulator, ThermalAnnealing, convert_to_graph_list,
+                                         pack_replicas)
+from rlvacdiffsim_b200.structures import append_xdatcar, apply_action, make_crconi_supercell, read_poscar, write_poscar
+from oracle.painn_oracle import image_range, inverse_cell_f32
+
+
+def test_registry_load_save_roundtrip(tmp_path, checkpoint_path):
+    model = rb.registry.get_model_class("dqn_v2").load(checkpoint_path)           # deploy.py:18
+    ck = torch.load(checkpoint_path, weights_only=True, map_location="cpu")
+    assert set(model.state_dict().keys()) == set(ck["state_dict"].keys())
+    assert all(torch.equal(model.state_dict()[k], v) for k, v in ck["state_dict"].items())
+    assert sum(p.numel() for p in model.parameters()) + 21 == 614447              # SURVEY §2 (incl. freqs+cutoff)
+    assert any("reaction_model" in n for n, _ in model.named_parameters())        # trainer.py:36-39
+    out = tmp_path / "m.pth.tar"
+    model.save(str(out))
+    again = rb.registry.get_model_class("dqn_v2").load(str(out))
+    assert all(torch.equal(again.state_dict()[k], v) for k, v in ck["state_dict"].items())
+    assert rb.registry.get_reaction_model_class("painn") is type(model.reaction_model)
+    with pytest.raises(KeyError):
+        rb.registry.get_model_class("nope")
+
+
+def test_forward_refuses_cpu(checkpoint_path):
+    model = rb.registry.get_model_class("dqn_v2").load(checkpoint_path).eval()
+    s = make_crconi_supercell(3, seed=0)
+    acts = rb.get_action_space(s, 3.528)
+    batch = next(iter(rb.DataLoader(rb.ReactionDataset(convert_to_graph_list(s, acts)), batch_size=16)))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(batch, q_params={"alpha": 0.0, "beta": 1.0, "dqn": True, "temperature": 700})
+
+
+def test_graph_containers_and_loader():
+    s = make_crconi_supercell(3, seed=1)
+    acts = rb.get_action_space(s, 3.528)
+    graphs = convert_to_graph_list(s, acts)
+    assert len(graphs) == 12 and graphs[0]["elems"].dtype == torch.int64
+    moved = int(acts[0][0])
+    diff = (graphs[0]["pos_product"] - graphs[0]["pos"]).abs().sum(1)
+    assert torch.nonzero(diff).flatten().tolist() == [moved]
+    graphs[0].rl_q = torch.tensor(0.5)                                           # trainer.py:157
+    for g in graphs[1:]:
+        g.rl_q = torch.tensor(0.0)
+    loader = rb.DataLoader(rb.ReactionDataset(graphs), batch_size=8)              # trainer.py:160
+    batches = list(loader)
+    assert [b.num_graphs for b in batches] == [8, 4] and len(loader) == 2
+    b = rb.batch_to(batches[0], "cpu")
+    assert b["pos"].shape == (8 * 107, 3) and b["batch"].max().item() == 7
+    assert b["ptr"].tolist() == [107 * i for i in range(9)]
+    assert b["rl_q"].shape == (8,) and b["rl_q"][0].item() == 0.5
+    ag = rb.AtomsGraph.from_ase(s, 5.0, read_properties=False, neighborlist_backend="ase", add_batch=True)
+    ag.T = torch.as_tensor(900.0)                                                 # estimate_time.py:47-52
+    ag.defect = torch.as_tensor(1 / 256)
+    tb = next(iter(rb.DataLoader(rb.AtomsDataset([ag, ag]), batch_size=2)))
+    assert tb["T"].tolist() == [900.0, 900.0]
+
+
+def test_cell_geometry_matches_oracle_definitions():
+    for atoms in (read_poscar(os.path.join(GOLD, "POSCAR_0")), make_crconi_supercell(2, seed=0)):
+        inv, img = cell_geometry(atoms.cell[None], 5.0)
+        assert np.array_equal(inv[0], inverse_cell_f32(atoms.cell))
+        assert np.array_equal(img[0], image_range(atoms.cell, 5.0))
+
+
+def test_pack_replicas_layouts():
+    reps = [make_crconi_supercell(3, seed=s) for s in (0, 1)]
+    spaces = [rb.get_action_space(r, 3.528) for r in reps]
+    full = pack_replicas(reps, spaces, dedup_reactants=False)
+    assert len(full["node_ptr"]) == 2 * 24 + 1 and len(full["react_struct"]) == 24
+    assert np.array_equal(full["prod_struct"], full["react_struct"] + 1)
+    dd = pack_replicas(reps, spaces, dedup_reactants=True)
+    assert len(dd["node_ptr"]) == 2 * 13 + 1
+    assert sorted(set(dd["react_struct"].tolist())) == [0, 13]
+    a = spaces[1][5]
+    p = dd["prod_struct"][12 + 5]
+    lo = dd["node_ptr"][p]
+    np.testing.assert_allclose(dd["pos"][lo + int(a[0])], (reps[1].positions[int(a[0])] + np.array(a[1:])).astype(np.float32))
+
+
+def test_poscar_and_xdatcar_roundtrip(tmp_path):
+    s = make_crconi_supercell(3, seed=4, jitter=0.02)
+    p = tmp_path / "POSCAR"
+    write_poscar(str(p), s)
+    back = read_poscar(str(p))
+    first = list(dict.fromkeys(s.numbers.tolist()))                    # species blocks in order of first appearance
+    order = np.concatenate([np.nonzero(s.numbers == z)[0] for z in first])
+    np.testing.assert_allclose(back.positions, s.positions[order], atol=1e-12)
+    assert np.array_equal(back.numbers, s.numbers[order])
+    x = tmp_path / "XDATCAR"
+    append_xdatcar(str(x), s, 0, append=False)
+    append_xdatcar(str(x), apply_action(s, [0, 0.1, 0.0, 0.0]), 1)
+    assert open(x).read().count("Direct configuration=") == 2
+
+
+def test_simulator_surface(checkpoint_path):
+    model = rb.registry.get_model_class("dqn_v2").load(checkpoint_path)
+    env = LatticeEnv(make_crconi_supercell(3, seed=0), {"device": "cuda"})
+    sim = RLSimulator(env, model, q_params={"alpha": 0.0, "beta": 1.0, "dqn": True}, lattice_parameter=3.528)
+    sim.update_q_params(temperature=700)
+    assert sim.q_params["temperature"] == 700 and sim.kb == pytest.approx(8.617e-5)
+    sched = ThermalAnnealing(total_horizon=20, annealing_time=10, T_start=1200, T_end=700)   # demo/config.toml
+    assert sched.get_temperature(0) == 1200 and sched.get_temperature(10) == 700 and sched.get_temperature(19) == 700
+    before = env.atoms.positions.copy()
+    act = sim._action_space()[0]
+    env.step(act)
+    assert np.abs(env.atoms.positions - before).sum() == pytest.approx(np.abs(np.array(act[1:])).sum())
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rlvd_b200.h")).read()
+    declared = set(re.findall(r"\b(rlvd_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()                      # raises if the .so is missing; no compute without a GPU
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.rlvd_abi_version() == 1
