@@ -54,10 +54,10 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.rows = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
@@ -65,10 +65,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in ln.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(2)
         sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
