@@ -112,6 +112,16 @@ int  rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, i
                                float* h_rl_q, float* h_q0, float* h_q1, float* h_delta_e,
                                float* h_E_R, float* h_E_P, int64_t* h_n_edges);
 
+/* ---- the channel-mixing linear as a standalone op: Y[M,N] = act([A | A2]·Wᵀ + b) -------------------- */
+/* d_A [M,K1 or K], optional d_A2 [M,K-K1] (concatenated along K), host weight h_W[N,K] in nn.Linear layout,
+ * optional host bias, act: 0 none / 1 SiLU.  Runs the tcgen05 split-fp16 kernel when the "tensor_cores"
+ * option is on (default) and the shape qualifies (N % 128 == 0, K in {64..256} multiple of 64), else the
+ * fp32 SIMT tile kernel.  Synchronises the stream.  (nn.Linear inside rgnn's PaiNN) */
+int  rlvd_linear(rlvd_engine* e, void* stream, int32_t M, int32_t K, int32_t N, const float* d_A,
+                 const float* d_A2, int32_t K1, const float* h_W, const float* h_bias, int32_t act, float* d_Y);
+/* Engine options: "tensor_cores" (1 = tcgen05 channel-mixing GEMMs, 0 = fp32 SIMT tiles; both fp32-accurate). */
+int  rlvd_set_option(rlvd_engine* e, const char* name, int32_t value);
+
 /* ---- introspection ------------------------------------------------------------------------------ */
 /* Number of kernels this library has launched on the engine since creation (bench.py "gpu_launches"). */
 int64_t rlvd_launch_count(const rlvd_engine* e);

@@ -41,6 +41,8 @@ SYMBOLS = {
                                         _P, _P, _P, _P, _P, _P]),
     "rlvd_score_reactions_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float,
                                             C.c_int32, _P, _P, C.POINTER(QParams), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rlvd_linear": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int32, _P]),
+    "rlvd_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
     "rlvd_launch_count": (C.c_int64, [_P]),
     "rlvd_profile_enable": (C.c_int, [_P, C.c_int32]),
     "rlvd_profile_read": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -70,6 +70,12 @@ struct Weights {
     const float* intra_b0[NLAYER] = {};
     const float* intra_w3T[NLAYER] = {};        // [128][384]
     const float* intra_b3[NLAYER] = {};
+    // the same five linears pre-split into fp16 hi/lo tensor-core stages (tc_linear.cu)
+    const void* inter_w0F[NLAYER] = {};
+    const void* inter_w3F[NLAYER] = {};
+    const void* mix_wF[NLAYER] = {};
+    const void* intra_w0F[NLAYER] = {};
+    const void* intra_w3F[NLAYER] = {};
     const float* en_w0T = nullptr;              // [128][64]
     const float* en_b0 = nullptr;
     const float* en_w3 = nullptr;               // [64]
@@ -105,6 +111,7 @@ struct rlvd_engine {
     rlvd::DevBuf in_node_ptr, in_Z, in_pos, in_cell, in_inv, in_img, in_rs, in_ps, in_temp, in_qp;
     rlvd::DevBuf g_row_ptr, g_node_struct, g_col, g_shift, g_nedges, g_q, out_pack;
     int64_t launches = 0;
+    bool use_tensor_cores = true;
     bool profiling = false;
     std::vector<rlvd::ProfSpan> spans;
     std::vector<cudaEvent_t> event_pool;
@@ -138,13 +145,17 @@ struct LinearArgs {
     int lda2 = 0;
     int K1 = 0;
     int M = 0, K = 0, N = 0;
-    const float* Wt = nullptr;    // [K][N]
+    const float* Wt = nullptr;    // [K][N]           (fp32 SIMT path)
+    const void* Wfmt = nullptr;   // tensor-core stages (tc_linear.cu); used when the engine option is on
     const float* bias = nullptr;  // [N] or null
     float* Y = nullptr;
     int ldy = 0;
     int act = 0;                  // 0 none, 1 SiLU
 };
 int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a);
+int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt);
+bool tc_linear_supported(const LinearArgs& a);
+void tc_format_weight(const float* W, int N, int K, std::vector<uint8_t>& out);
 
 int launch_embed(rlvd_engine* e, cudaStream_t s, int M, const int* Z, float* q);
 int launch_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* row_ptr, const int* col,

@@ -91,6 +91,15 @@ int upload_T(rlvd_engine* e, const std::vector<float>& W, int n_out, int n_in, c
     return 0;
 }
 
+int upload_fmt(rlvd_engine* e, const std::vector<float>& W, int n_out, int n_in, const void** out) {
+    std::vector<uint8_t> f;
+    tc_format_weight(W.data(), n_out, n_in, f);
+    void* d = nullptr;
+    if (upload(e, f.data(), f.size(), &d)) return 1;
+    *out = d;
+    return 0;
+}
+
 int upload_raw(rlvd_engine* e, const std::vector<float>& W, const float** out) {
     void* d = nullptr;
     if (upload(e, W.data(), W.size() * sizeof(float), &d)) return 1;
@@ -198,17 +207,23 @@ int rlvd_finalize_weights(rlvd_engine* e) {
     for (int l = 0; l < NLAYER; ++l) {
         const std::string pi = rep + "interactions." + std::to_string(l) + ".interatomic_context_net.layers.";
         const std::string pm = rep + "mixing." + std::to_string(l) + ".";
-        if (need(pi + "0.weight", F * F, &t) || upload_T(e, *t, F, F, &w.inter_w0T[l])) return 1;
+        if (need(pi + "0.weight", F * F, &t) || upload_T(e, *t, F, F, &w.inter_w0T[l]) ||
+            upload_fmt(e, *t, F, F, &w.inter_w0F[l]))
+            return 1;
         if (need(pi + "0.bias", F, &t) || upload_raw(e, *t, &w.inter_b0[l])) return 1;
-        if (need(pi + "3.weight", 3 * F * F, &t) || upload_T(e, *t, 3 * F, F, &w.inter_w3T[l])) return 1;
+        if (need(pi + "3.weight", 3 * F * F, &t) || upload_T(e, *t, 3 * F, F, &w.inter_w3T[l]) ||
+            upload_fmt(e, *t, 3 * F, F, &w.inter_w3F[l]))
+            return 1;
         if (need(pi + "3.bias", 3 * F, &t) || upload_raw(e, *t, &w.inter_b3[l])) return 1;
-        if (need(pm + "mu_channel_mix.weight", 2 * F * F, &t) || upload_T(e, *t, 2 * F, F, &w.mix_wT[l])) return 1;
+        if (need(pm + "mu_channel_mix.weight", 2 * F * F, &t) || upload_T(e, *t, 2 * F, F, &w.mix_wT[l]) ||
+            upload_fmt(e, *t, 2 * F, F, &w.mix_wF[l]))
+            return 1;
         if (need(pm + "intraatomic_context_net.layers.0.weight", F * 2 * F, &t) ||
-            upload_T(e, *t, F, 2 * F, &w.intra_w0T[l]))
+            upload_T(e, *t, F, 2 * F, &w.intra_w0T[l]) || upload_fmt(e, *t, F, 2 * F, &w.intra_w0F[l]))
             return 1;
         if (need(pm + "intraatomic_context_net.layers.0.bias", F, &t) || upload_raw(e, *t, &w.intra_b0[l])) return 1;
         if (need(pm + "intraatomic_context_net.layers.3.weight", 3 * F * F, &t) ||
-            upload_T(e, *t, 3 * F, F, &w.intra_w3T[l]))
+            upload_T(e, *t, 3 * F, F, &w.intra_w3T[l]) || upload_fmt(e, *t, 3 * F, F, &w.intra_w3F[l]))
             return 1;
         if (need(pm + "intraatomic_context_net.layers.3.bias", 3 * F, &t) || upload_raw(e, *t, &w.intra_b3[l])) return 1;
     }
@@ -307,11 +322,11 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
     for (int l = 0; l < NLAYER; ++l) {
         // R5 node part: x = Lin3(SiLU(Lin0(q)))
         LinearArgs a0;
-        a0.A = d_q; a0.lda = F; a0.M = M; a0.K = F; a0.N = F; a0.Wt = w.inter_w0T[l]; a0.bias = w.inter_b0[l];
+        a0.A = d_q; a0.lda = F; a0.M = M; a0.K = F; a0.N = F; a0.Wt = w.inter_w0T[l]; a0.Wfmt = w.inter_w0F[l]; a0.bias = w.inter_b0[l];
         a0.Y = hid; a0.ldy = F; a0.act = 1;
         if (launch_linear(e, s, a0)) return 1;
         LinearArgs a1;
-        a1.A = hid; a1.lda = F; a1.M = M; a1.K = F; a1.N = 3 * F; a1.Wt = w.inter_w3T[l]; a1.bias = w.inter_b3[l];
+        a1.A = hid; a1.lda = F; a1.M = M; a1.K = F; a1.N = 3 * F; a1.Wt = w.inter_w3T[l]; a1.Wfmt = w.inter_w3F[l]; a1.bias = w.inter_b3[l];
         a1.Y = x; a1.ldy = 3 * F; a1.act = 0;
         if (launch_linear(e, s, a1)) return 1;
         // R2 + R3 + R5 edge part + K4
@@ -321,16 +336,16 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
         float* tmp = mu_cur; mu_cur = mu_nxt; mu_nxt = tmp;
         // R6: mixing
         LinearArgs am;
-        am.A = mu_cur; am.lda = F; am.M = 3 * M; am.K = F; am.N = 2 * F; am.Wt = w.mix_wT[l]; am.bias = nullptr;
+        am.A = mu_cur; am.lda = F; am.M = 3 * M; am.K = F; am.N = 2 * F; am.Wt = w.mix_wT[l]; am.Wfmt = w.mix_wF[l]; am.bias = nullptr;
         am.Y = mix; am.ldy = 2 * F; am.act = 0;
         if (launch_linear(e, s, am)) return 1;
         if (launch_mix_reduce(e, s, M, mix, nrm, vw)) return 1;
         LinearArgs b0;
         b0.A = d_q; b0.lda = F; b0.A2 = nrm; b0.lda2 = F; b0.K1 = F; b0.M = M; b0.K = 2 * F; b0.N = F;
-        b0.Wt = w.intra_w0T[l]; b0.bias = w.intra_b0[l]; b0.Y = hid; b0.ldy = F; b0.act = 1;
+        b0.Wt = w.intra_w0T[l]; b0.Wfmt = w.intra_w0F[l]; b0.bias = w.intra_b0[l]; b0.Y = hid; b0.ldy = F; b0.act = 1;
         if (launch_linear(e, s, b0)) return 1;
         LinearArgs b1;
-        b1.A = hid; b1.lda = F; b1.M = M; b1.K = F; b1.N = 3 * F; b1.Wt = w.intra_w3T[l]; b1.bias = w.intra_b3[l];
+        b1.A = hid; b1.lda = F; b1.M = M; b1.K = F; b1.N = 3 * F; b1.Wt = w.intra_w3T[l]; b1.Wfmt = w.intra_w3F[l]; b1.bias = w.intra_b3[l];
         b1.Y = ctx; b1.ldy = 3 * F; b1.act = 0;
         if (launch_linear(e, s, b1)) return 1;
         if (launch_mix_update(e, s, M, ctx, mix, vw, d_q, mu_cur)) return 1;
@@ -412,6 +427,56 @@ int rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, in
         if (hosts[k] != nullptr)
             RLVD_CUDA(cudaMemcpyAsync(hosts[k], op + (size_t)k * n_react, (size_t)n_react * 4, cudaMemcpyDeviceToHost, s));
     RLVD_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int rlvd_set_option(rlvd_engine* e, const char* name, int32_t value) {
+    RLVD_CHECK(e != nullptr && name != nullptr, "bad argument");
+    if (strcmp(name, "tensor_cores") == 0) {
+        e->use_tensor_cores = value != 0;
+        return 0;
+    }
+    RLVD_CHECK(false, "unknown option '%s'", name);
+}
+
+int rlvd_linear(rlvd_engine* e, void* stream, int32_t M, int32_t K, int32_t N, const float* d_A, const float* d_A2,
+                int32_t K1, const float* h_W, const float* h_bias, int32_t act, float* d_Y) {
+    RLVD_CHECK(e != nullptr && d_A != nullptr && h_W != nullptr && d_Y != nullptr, "rlvd_linear: bad argument");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<float> W(h_W, h_W + (size_t)N * K);
+    LinearArgs a;
+    a.A = d_A; a.lda = d_A2 != nullptr ? K1 : K; a.A2 = d_A2; a.lda2 = K - K1; a.K1 = d_A2 != nullptr ? K1 : 0;
+    a.M = M; a.K = K; a.N = N; a.Y = d_Y; a.ldy = N; a.act = act;
+    void* d_bias = nullptr;
+    void* d_w = nullptr;
+    if (h_bias != nullptr) {
+        RLVD_CUDA(cudaMalloc(&d_bias, (size_t)N * 4));
+        RLVD_CUDA(cudaMemcpy(d_bias, h_bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+        a.bias = reinterpret_cast<const float*>(d_bias);
+    }
+    int rc = 0;
+    if (e->use_tensor_cores && tc_linear_supported(a)) {
+        std::vector<uint8_t> f;
+        tc_format_weight(W.data(), N, K, f);
+        RLVD_CUDA(cudaMalloc(&d_w, f.size()));
+        RLVD_CUDA(cudaMemcpy(d_w, f.data(), f.size(), cudaMemcpyHostToDevice));
+        a.Wfmt = d_w;
+        rc = launch_linear(e, s, a);
+    } else {
+        std::vector<float> t((size_t)N * K);
+        for (int o = 0; o < N; ++o)
+            for (int k = 0; k < K; ++k) t[(size_t)k * N + o] = W[(size_t)o * K + k];
+        RLVD_CUDA(cudaMalloc(&d_w, t.size() * 4));
+        RLVD_CUDA(cudaMemcpy(d_w, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+        a.Wt = reinterpret_cast<const float*>(d_w);
+        rc = launch_linear(e, s, a);
+    }
+    cudaError_t err = cudaStreamSynchronize(s);
+    cudaFree(d_w);
+    if (d_bias != nullptr) cudaFree(d_bias);
+    if (rc != 0) return rc;
+    RLVD_CHECK(err == cudaSuccess, "rlvd_linear: %s", cudaGetErrorString(err));
     return 0;
 }
 

@@ -1,0 +1,321 @@
+// K3b on the 5th-generation tensor cores — Y = act(A·Wᵀ + b) with tcgen05.mma, accumulators in TMEM.
+//
+// The channel-mixing linears of PaiNN (128→128, 128→384, 128→256 on the three vector
+// components, 256→128, 128→384) are true dense GEMMs with M = number of atoms in the batch.  The parity
+// bar is fp32 (1e-5 relative on Q), which a single fp16/bf16/tf32 pass cannot meet, so every operand is
+// split into two fp16 numbers
+//        a = a_hi + 2^-11 · a_lo        (a_hi = fp16(a), a_lo = fp16((a - a_hi)·2^11): 22 significant bits)
+// and the product is evaluated as three tensor-core passes into two fp32 TMEM accumulators
+//        D0 += A_hi·B_hiᵀ          D1 += A_hi·B_loᵀ + A_lo·B_hiᵀ          Y = D0 + 2^-11·D1
+// (the dropped A_lo·B_lo term is 2^-22 relative).  Scaling the low parts by 2^11 keeps them in fp16's normal
+// range.  Three kind::f16 passes cost 1.5 tf32-pass equivalents and 4 bytes of shared memory per element.
+//
+// Kernel shape (persistent, one CTA per SM, 192 threads):
+//   warps 0-3  load the 128-row A tile (fp32, optionally the concatenation [A | A2]), split it, write it to
+//              shared memory in the canonical no-swizzle K-major core-matrix layout, later drain TMEM
+//              (tcgen05.ld), apply bias/SiLU and store Y
+//   warp  4    producer: 1-D bulk-TMA copies (cp.async.bulk → mbarrier complete_tx) of pre-formatted
+//              32 KB weight stages [128 out-rows x 64 k, hi | lo] through a 3-deep ring
+//   warp  5    allocates TMEM (512 columns = 2 x (D0,D1) x 128), one elected lane issues tcgen05.mma and
+//              tcgen05.commit onto the mbarriers that free weight stages / publish accumulators
+// Weights are formatted once on the host (rlvd_finalize_weights).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace rlvd {
+
+namespace {
+
+constexpr int TC_M = 128;
+constexpr int TC_N = 128;
+constexpr int TC_KS = 64;                              // k elements per weight stage
+constexpr int TC_NSTAGE = 3;
+constexpr int TC_HALF_STAGE = TC_N * TC_KS * 2;        // 16384 B: one of hi / lo
+constexpr int TC_STAGE_BYTES = 2 * TC_HALF_STAGE;      // 32768 B
+constexpr int CORE_LBO = 2048;                         // bytes between K-adjacent core matrices
+constexpr int CORE_SBO = 128;                          // bytes between 8-row groups
+constexpr int TC_THREADS = 192;
+constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | (16u << 17) | (8u << 24);   // fp32 accum, fp16 A/B, K-major
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("rlvd tc_linear: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(CORE_LBO >> 4) << 16) | ((uint64_t)(CORE_SBO >> 4) << 32) |
+           (1ull << 46);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(IDESC_F16_M128_N128), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void split8(const float4 lo4, const float4 hi4, uint4& H, uint4& L) {
+    const float v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+    __half h[8], l[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        h[t] = __float2half_rn(v[t]);
+        l[t] = __float2half_rn((v[t] - __half2float(h[t])) * 2048.0f);
+    }
+    H = *reinterpret_cast<uint4*>(h);
+    L = *reinterpret_cast<uint4*>(l);
+}
+
+struct TcSmem {
+    uint64_t full[TC_NSTAGE], empty[TC_NSTAGE], acc_full[2], acc_empty[2], a_ready;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearArgs a, const uint8_t* __restrict__ Wfmt) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int K = a.K;
+    const int a_half = K * 256;                       // bytes of A_hi (= A_lo): (K/8) core columns x 2048
+    uint8_t* A_hi = smem;
+    uint8_t* A_lo = smem + a_half;
+    uint8_t* Bst = smem + 2 * a_half;
+    TcSmem* S = reinterpret_cast<TcSmem*>(Bst + TC_NSTAGE * TC_STAGE_BYTES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = (a.M + TC_M - 1) / TC_M;
+    const int NB = a.N / TC_N, KSN = K / TC_KS;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&S->acc_full[b], 1); mbar_init(&S->acc_empty[b], 128); }
+        mbar_init(&S->a_ready, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S->tmem_base)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S->tmem_base;
+
+    if (warp < 4) {
+        // ================= A converter + epilogue (thread = row = TMEM lane) =================
+        const int r = tid;
+        uint32_t acc_it = 0;
+        const uint32_t row_off = (r >> 3) * CORE_SBO + (r & 7) * 16;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m = tile * TC_M + r;
+            const bool live = m < a.M;
+            // ---- A tile → split fp16, canonical layout.  (All MMAs of the previous tile have completed:
+            //      this thread waited on the acc_full barrier of its last N-block.)
+#pragma unroll 4
+            for (int kc = 0; kc < K / 8; ++kc) {
+                const int k = kc * 8;
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (live) {
+                    const float* src = (a.A2 != nullptr && k >= a.K1) ? a.A2 + (int64_t)m * a.lda2 + (k - a.K1)
+                                                                      : a.A + (int64_t)m * a.lda + k;
+                    v0 = __ldg(reinterpret_cast<const float4*>(src));
+                    v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                }
+                uint4 H, L;
+                split8(v0, v1, H, L);
+                *reinterpret_cast<uint4*>(A_hi + kc * CORE_LBO + row_off) = H;
+                *reinterpret_cast<uint4*>(A_lo + kc * CORE_LBO + row_off) = L;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores → async proxy (UMMA)
+            mbar_arrive(&S->a_ready);
+            // ---- epilogue per N-block
+            for (int nb = 0; nb < NB; ++nb, ++acc_it) {
+                const uint32_t buf = acc_it & 1;
+                mbar_wait(&S->acc_full[buf], (acc_it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t t0 = tmem + ((uint32_t)(warp * 32) << 16) + buf * 256;
+#pragma unroll 1
+                for (int ch = 0; ch < TC_N / 32; ++ch) {
+                    uint32_t d0[32], d1[32];
+                    tmem_ld32(t0 + ch * 32, d0);
+                    tmem_ld32(t0 + 128 + ch * 32, d1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (live) {
+                        const int col0 = nb * TC_N + ch * 32;
+                        float* dst = a.Y + (int64_t)m * a.ldy + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float y[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                float t = fmaf(__uint_as_float(d1[j + u]), 1.0f / 2048.0f, __uint_as_float(d0[j + u]));
+                                if (a.bias != nullptr) t += __ldg(a.bias + col0 + j + u);
+                                if (a.act == 1) t = t / (1.0f + expf(-t));
+                                y[u] = t;
+                            }
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(y[0], y[1], y[2], y[3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&S->acc_empty[buf]);
+            }
+        }
+    } else if (warp == 4) {
+        // ================= weight-stage producer =================
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int nb = 0; nb < NB; ++nb)
+                    for (int ks = 0; ks < KSN; ++ks, ++cnt) {
+                        const uint32_t s = cnt % TC_NSTAGE, ph = (cnt / TC_NSTAGE) & 1;
+                        mbar_wait(&S->empty[s], ph ^ 1);
+                        mbar_expect_tx(&S->full[s], TC_STAGE_BYTES);
+                        bulk_g2s(Bst + s * TC_STAGE_BYTES, Wfmt + (size_t)(nb * KSN + ks) * TC_STAGE_BYTES,
+                                 TC_STAGE_BYTES, &S->full[s]);
+                    }
+        }
+    } else {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t cnt = 0, acc_it = 0, tile_it = 0;
+            const uint32_t a_hi0 = smem_u32(A_hi), a_lo0 = smem_u32(A_lo), b0 = smem_u32(Bst);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+                mbar_wait(&S->a_ready, tile_it & 1);
+                tc_fence_after();
+                for (int nb = 0; nb < NB; ++nb, ++acc_it) {
+                    const uint32_t buf = acc_it & 1;
+                    mbar_wait(&S->acc_empty[buf], ((acc_it >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d0 = tmem + buf * 256, d1 = d0 + 128;
+                    for (int ks = 0; ks < KSN; ++ks, ++cnt) {
+                        const uint32_t s = cnt % TC_NSTAGE, ph = (cnt / TC_NSTAGE) & 1;
+                        mbar_wait(&S->full[s], ph);
+                        tc_fence_after();
+                        const uint32_t bh = b0 + s * TC_STAGE_BYTES, bl = bh + TC_HALF_STAGE;
+#pragma unroll
+                        for (int j = 0; j < TC_KS / 16; ++j) {
+                            const uint32_t koff_a = (uint32_t)(ks * (TC_KS / 8) + 2 * j) * CORE_LBO;
+                            const uint32_t koff_b = (uint32_t)(2 * j) * CORE_LBO;
+                            const uint32_t first = (ks == 0 && j == 0) ? 0u : 1u;
+                            umma_f16(d0, make_desc(a_hi0 + koff_a), make_desc(bh + koff_b), first);
+                            umma_f16(d1, make_desc(a_hi0 + koff_a), make_desc(bl + koff_b), first);
+                            umma_f16(d1, make_desc(a_lo0 + koff_a), make_desc(bh + koff_b), 1u);
+                        }
+                        umma_commit(&S->empty[s]);      // frees the weight stage when these MMAs retire
+                    }
+                    umma_commit(&S->acc_full[buf]);      // publishes (D0, D1) of this N-block
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+size_t tc_smem_bytes(int K) { return (size_t)2 * K * 256 + TC_NSTAGE * TC_STAGE_BYTES + sizeof(TcSmem) + 64; }
+
+}  // namespace
+
+// Host: format W[N][K] (checkpoint layout, out-major) into 32 KB stages [(nb, ks)] = [hi 128x64 | lo 128x64],
+// each half in the canonical core-matrix layout the MMA descriptors describe.
+void tc_format_weight(const float* W, int N, int K, std::vector<uint8_t>& out) {
+    const int NB = N / TC_N, KSN = K / TC_KS;
+    out.assign((size_t)NB * KSN * TC_STAGE_BYTES, 0);
+    for (int nb = 0; nb < NB; ++nb)
+        for (int ks = 0; ks < KSN; ++ks) {
+            uint8_t* st = out.data() + (size_t)(nb * KSN + ks) * TC_STAGE_BYTES;
+            for (int r = 0; r < TC_N; ++r)
+                for (int k = 0; k < TC_KS; ++k) {
+                    const float w = W[(size_t)(nb * TC_N + r) * K + ks * TC_KS + k];
+                    const __half h = __float2half_rn(w);
+                    const __half l = __float2half_rn((w - __half2float(h)) * 2048.0f);
+                    const size_t off = (size_t)(k / 8) * CORE_LBO + (r / 8) * CORE_SBO + (r % 8) * 16 + (k % 8) * 2;
+                    *reinterpret_cast<__half*>(st + off) = h;
+                    *reinterpret_cast<__half*>(st + TC_HALF_STAGE + off) = l;
+                }
+        }
+}
+
+bool tc_linear_supported(const LinearArgs& a) {
+    return a.N % TC_N == 0 && a.K % TC_KS == 0 && a.K <= 256 && (a.A2 == nullptr || a.K1 % 8 == 0) &&
+           a.lda % 4 == 0 && a.ldy % 4 == 0;
+}
+
+int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt) {
+    RLVD_CHECK(tc_linear_supported(a), "tc_linear: unsupported shape M=%d K=%d N=%d", a.M, a.K, a.N);
+    if (a.M <= 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RLVD_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc_smem_bytes(256)));
+        attr_set = true;
+    }
+    const int n_tiles = (a.M + TC_M - 1) / TC_M;
+    const int grid = n_tiles < e->sm_count ? n_tiles : e->sm_count;
+    Span sp(e, s, FAM_NODE);
+    tc_linear_kernel<<<grid, TC_THREADS, tc_smem_bytes(a.K), s>>>(a, reinterpret_cast<const uint8_t*>(Wfmt));
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rlvd

@@ -213,6 +213,26 @@ class Engine:
         res["n_edges"] = int(n_edges.value)
         return res
 
+    # ------------------------------------------------------------------ standalone linear + options
+    def set_option(self, name: str, value: int) -> None:
+        check(self.lib.rlvd_set_option(self._h, name.encode(), int(value)))
+
+    def linear(self, A: torch.Tensor, W: np.ndarray, bias: Optional[np.ndarray] = None, act: int = 0,
+               A2: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Y = act([A | A2] @ W.T + bias) through ``rlvd_linear`` (W, bias: host fp32 arrays)."""
+        M, K1 = A.shape
+        K = K1 + (A2.shape[1] if A2 is not None else 0)
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        N = W.shape[0]
+        assert W.shape[1] == K
+        Y = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_linear(self._h, self._stream(), M, K, N, _ptr(A), _ptr(A2), K1,
+                                       W.ctypes.data_as(C.c_void_p),
+                                       None if b is None else b.ctypes.data_as(C.c_void_p), act, _ptr(Y)))
+        return Y
+
     # ------------------------------------------------------------------ introspection
     def launch_count(self) -> int:
         return int(self.lib.rlvd_launch_count(self._h))

@@ -201,3 +201,41 @@ def test_per_replica_temperatures(model, engine):
     lo = sc.score(reps, spaces, dict(qp, temperature=300.0))
     hi = sc.score(reps, spaces, dict(qp, temperature=900.0))
     assert np.array_equal(mixed[0], lo[0]) and np.array_equal(mixed[1], hi[1])
+
+
+# ----------------------------------------------------------------------------- tcgen05 channel-mixing linear
+
+@pytest.mark.parametrize("M,K,N,K1,act", [(128, 128, 128, 0, 0), (300, 128, 384, 0, 1), (1000, 256, 128, 128, 1),
+                                          (77, 128, 256, 0, 0), (20000, 128, 384, 0, 0)])
+def test_tc_linear_matches_fp64(engine, M, K, N, K1, act):
+    """rlvd_linear: tcgen05 split-fp16 GEMM vs float64 torch, and vs the fp32 SIMT tile kernel."""
+    rng = np.random.default_rng(M + K + N)
+    A = torch.from_numpy(rng.normal(0, 1.0, (M, K)).astype(np.float32)).cuda()
+    A[:, :7] *= 1e-3                                   # small magnitudes exercise the scaled low halves
+    W = (rng.normal(0, 0.1, (N, K))).astype(np.float32)
+    b = rng.normal(0, 0.1, N).astype(np.float32)
+    ref = A.double().cpu() @ torch.from_numpy(W).double().T + torch.from_numpy(b).double()
+    if act:
+        ref = ref * torch.sigmoid(ref)
+    parts = (A[:, :K1].contiguous(), A[:, K1:].contiguous()) if K1 else (A, None)
+    engine.set_option("tensor_cores", 1)
+    y_tc = engine.linear(parts[0], W, b, act, parts[1]).double().cpu()
+    engine.set_option("tensor_cores", 0)
+    y_simt = engine.linear(parts[0], W, b, act, parts[1]).double().cpu()
+    engine.set_option("tensor_cores", 1)
+    scale = ref.abs().max().item()
+    err_tc = (y_tc - ref).abs().max().item() / scale
+    err_simt = (y_simt - ref).abs().max().item() / scale
+    assert err_simt < 2e-6, err_simt
+    assert err_tc < 2e-6, (err_tc, err_simt)          # 22-bit operands, fp32 accumulate
+
+
+def test_tensor_core_and_simt_paths_agree_end_to_end(model, engine):
+    g = load_gold("syn255_s2_jitter")
+    engine.set_option("tensor_cores", 0)
+    simt = _score_batch(model, g, "lss700")
+    engine.set_option("tensor_cores", 1)
+    tc = _score_batch(model, g, "lss700")
+    for k in ("E_R", "E_P"):
+        assert np.max(np.abs(tc[k] - simt[k]) / np.abs(simt[k])) < 1e-6, k
+    assert int(np.argmax(tc["rl_q"])) == int(np.argmax(simt["rl_q"]))
