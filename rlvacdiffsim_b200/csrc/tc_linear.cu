@@ -10,14 +10,18 @@
 // (the dropped A_lo·B_lo term is 2^-22 relative).  Scaling the low parts by 2^11 keeps them in fp16's normal
 // range.  Three kind::f16 passes cost 1.5 tf32-pass equivalents and 4 bytes of shared memory per element.
 //
-// Kernel shape (persistent, one CTA per SM, 192 threads):
-//   warps 0-3  load the 128-row A tile (fp32, optionally the concatenation [A | A2]), split it, write it to
-//              shared memory in the canonical no-swizzle K-major core-matrix layout, later drain TMEM
-//              (tcgen05.ld), apply bias/SiLU and store Y
-//   warp  4    producer: 1-D bulk-TMA copies (cp.async.bulk → mbarrier complete_tx) of pre-formatted
-//              32 KB weight stages [128 out-rows x 64 k, hi | lo] through a 3-deep ring
-//   warp  5    allocates TMEM (512 columns = 2 x (D0,D1) x 128), one elected lane issues tcgen05.mma and
-//              tcgen05.commit onto the mbarriers that free weight stages / publish accumulators
+// Kernel shape (persistent, one CTA per SM, 320 threads, 224 KB of shared memory):
+//   warps 0-7  stage the next 128-row x 128-k fp32 A phase with fully coalesced cp.async (prefetched one phase
+//              ahead, overlapping the MMAs and the epilogue), split it into fp16 hi/lo and write it in the
+//              canonical no-swizzle K-major core-matrix layout; later drain TMEM (tcgen05.ld, thread = row),
+//              apply bias/SiLU, transpose through a swizzled staging tile and store Y with coalesced 16-byte
+//              stores
+//   warp  8    producer: 1-D bulk-TMA copies (cp.async.bulk → mbarrier complete_tx) of pre-formatted 32 KB
+//              weight stages [128 out-rows x 64 k, hi | lo] through a 2-deep ring
+//   warp  9    allocates TMEM (512 columns = 2 x (D0,D1) x 128); one elected lane issues tcgen05.mma and the
+//              tcgen05.commit arrivals that free weight stages / A buffers and publish accumulators
+// K = 256 (the [q | n] concatenation of the intra-atomic net) runs as two 128-k phases through the same A
+// buffers, accumulating in TMEM.  Every mbarrier wait is bounded (trap, never hang).
 // Weights are formatted once on the host (rlvd_finalize_weights).
 #include <cuda_fp16.h>
 
@@ -30,12 +34,12 @@ namespace {
 constexpr int TC_M = 128;
 constexpr int TC_N = 128;
 constexpr int TC_KS = 64;                              // k elements per weight stage
-constexpr int TC_NSTAGE = 3;
+constexpr int TC_NSTAGE = 2;
 constexpr int TC_HALF_STAGE = TC_N * TC_KS * 2;        // 16384 B: one of hi / lo
 constexpr int TC_STAGE_BYTES = 2 * TC_HALF_STAGE;      // 32768 B
 constexpr int CORE_LBO = 2048;                         // bytes between K-adjacent core matrices
 constexpr int CORE_SBO = 128;                          // bytes between 8-row groups
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;                       // 8 stager/epilogue warps + producer + MMA issuer
 constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | (16u << 17) | (8u << 24);   // fp32 accum, fp16 A/B, K-major
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,30 +125,53 @@ __device__ __forceinline__ void split8(const float4 lo4, const float4 hi4, uint4
 }
 
 struct TcSmem {
-    uint64_t full[TC_NSTAGE], empty[TC_NSTAGE], acc_full[2], acc_empty[2], a_ready;
+    uint64_t full[TC_NSTAGE], empty[TC_NSTAGE], acc_full[2], acc_empty[2], a_ready, a_free;
     uint32_t tmem_base;
 };
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Asynchronous, fully coalesced load of one 128-row x 128-k fp32 A phase into the swizzled staging buffer:
+// 16-byte chunk `lc` of row `row` lands at row*512 + ((lc ^ (row & 7)) * 16).
+__device__ __forceinline__ void stage_A_async(const LinearArgs& a, int tile, int phase, uint32_t stage_addr, int t) {
+    const float* base = a.A;
+    int ld = a.lda, k0 = phase * 128;
+    if (a.A2 != nullptr && k0 >= a.K1) { base = a.A2; ld = a.lda2; k0 -= a.K1; }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int id = i * 256 + t, row = id >> 5, lc = id & 31;
+        const int m = tile * TC_M + row;
+        const bool live = m < a.M;
+        const float* src = base + (live ? (int64_t)m * ld : 0) + k0 + lc * 4;
+        cp_async16(stage_addr + row * 512 + ((lc ^ (row & 7)) << 4), src, live ? 16u : 0u);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearArgs a, const uint8_t* __restrict__ Wfmt) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int K = a.K;
-    const int a_half = K * 256;                       // bytes of A_hi (= A_lo): (K/8) core columns x 2048
-    uint8_t* A_hi = smem;
-    uint8_t* A_lo = smem + a_half;
-    uint8_t* Bst = smem + 2 * a_half;
-    TcSmem* S = reinterpret_cast<TcSmem*>(Bst + TC_NSTAGE * TC_STAGE_BYTES);
+    uint8_t* A_hi = smem;                              // 32 KB  [16 core columns][16 row groups][8 rows][16 B]
+    uint8_t* A_lo = smem + 32768;                      // 32 KB
+    uint8_t* Ast = smem + 65536;                       // 64 KB  fp32 staging of the next A phase (swizzled rows)
+    uint8_t* Bst = smem + 131072;                      // TC_NSTAGE x 32 KB weight stages
+    uint8_t* Yst = Bst + TC_NSTAGE * TC_STAGE_BYTES;   // 32 KB  [128 rows][64 cols] fp32 output staging (swizzled)
+    TcSmem* S = reinterpret_cast<TcSmem*>(Yst + 32768);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = (a.M + TC_M - 1) / TC_M;
-    const int NB = a.N / TC_N, KSN = K / TC_KS;
+    const int NB = a.N / TC_N, NPH = a.K / 128;       // K-phases of 128 (the A buffers hold one phase)
 
     if (tid == 0) {
         for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&S->acc_full[b], 1); mbar_init(&S->acc_empty[b], 128); }
-        mbar_init(&S->a_ready, 128);
+        for (int b = 0; b < 2; ++b) { mbar_init(&S->acc_full[b], 1); mbar_init(&S->acc_empty[b], 256); }
+        mbar_init(&S->a_ready, 256);
+        mbar_init(&S->a_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S->tmem_base)),
                      "r"(512u)
                      : "memory");
@@ -155,123 +182,147 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
     tc_fence_after();
     const uint32_t tmem = S->tmem_base;
 
-    if (warp < 4) {
-        // ================= A converter + epilogue (thread = row = TMEM lane) =================
-        const int r = tid;
-        uint32_t acc_it = 0;
+    if (warp < 8) {
+        // ================= A stager/converter + epilogue (256 threads) =================
+        const int t = tid;
+        const int r = t & 127, khalf = t >> 7;               // converter role: row r, core columns khalf*8..+8
+        const int q = warp & 3, h = warp >> 2;               // epilogue role: TMEM lane quarter q, column half h
+        const int er = q * 32 + lane;                        // epilogue row = TMEM lane
+        const uint32_t ast = smem_u32(Ast);
         const uint32_t row_off = (r >> 3) * CORE_SBO + (r & 7) * 16;
+        uint32_t acc_it = 0, ph_it = 0;
+        if (blockIdx.x < n_tiles) stage_A_async(a, blockIdx.x, 0, ast, t);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int m = tile * TC_M + r;
-            const bool live = m < a.M;
-            // ---- A tile → split fp16, canonical layout.  (All MMAs of the previous tile have completed:
-            //      this thread waited on the acc_full barrier of its last N-block.)
-#pragma unroll 4
-            for (int kc = 0; kc < K / 8; ++kc) {
-                const int k = kc * 8;
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                if (live) {
-                    const float* src = (a.A2 != nullptr && k >= a.K1) ? a.A2 + (int64_t)m * a.lda2 + (k - a.K1)
-                                                                      : a.A + (int64_t)m * a.lda + k;
-                    v0 = __ldg(reinterpret_cast<const float4*>(src));
-                    v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            for (int phase = 0; phase < NPH; ++phase, ++ph_it) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                mbar_wait(&S->a_free, (ph_it & 1) ^ 1);      // MMAs that read the previous A phase have retired
+                epi_barrier();                               // everyone's cp.async data is visible
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int kc = khalf * 8 + c;
+                    const float4 v0 = *reinterpret_cast<const float4*>(Ast + r * 512 + (((2 * kc) ^ (r & 7)) << 4));
+                    const float4 v1 = *reinterpret_cast<const float4*>(Ast + r * 512 + (((2 * kc + 1) ^ (r & 7)) << 4));
+                    uint4 H, L;
+                    split8(v0, v1, H, L);
+                    *reinterpret_cast<uint4*>(A_hi + kc * CORE_LBO + row_off) = H;
+                    *reinterpret_cast<uint4*>(A_lo + kc * CORE_LBO + row_off) = L;
                 }
-                uint4 H, L;
-                split8(v0, v1, H, L);
-                *reinterpret_cast<uint4*>(A_hi + kc * CORE_LBO + row_off) = H;
-                *reinterpret_cast<uint4*>(A_lo + kc * CORE_LBO + row_off) = L;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores → UMMA
+                mbar_arrive(&S->a_ready);
+                epi_barrier();                               // staging fully consumed → prefetch the next phase
+                if (phase + 1 < NPH) stage_A_async(a, tile, phase + 1, ast, t);
+                else if (tile + (int)gridDim.x < n_tiles) stage_A_async(a, tile + gridDim.x, 0, ast, t);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores → async proxy (UMMA)
-            mbar_arrive(&S->a_ready);
-            // ---- epilogue per N-block
+            // ---- epilogue: TMEM → registers → bias/SiLU → swizzled staging → coalesced global stores
             for (int nb = 0; nb < NB; ++nb, ++acc_it) {
                 const uint32_t buf = acc_it & 1;
                 mbar_wait(&S->acc_full[buf], (acc_it >> 1) & 1);
                 tc_fence_after();
-                const uint32_t t0 = tmem + ((uint32_t)(warp * 32) << 16) + buf * 256;
 #pragma unroll 1
-                for (int ch = 0; ch < TC_N / 32; ++ch) {
+                for (int sgm = 0; sgm < 2; ++sgm) {
+                    const int c0 = 64 * sgm + 32 * h;        // first column (inside the N-block) of this thread
+                    const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + c0;
                     uint32_t d0[32], d1[32];
-                    tmem_ld32(t0 + ch * 32, d0);
-                    tmem_ld32(t0 + 128 + ch * 32, d1);
+                    tmem_ld32(t0, d0);
+                    tmem_ld32(t0 + 128, d1);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (live) {
-                        const int col0 = nb * TC_N + ch * 32;
-                        float* dst = a.Y + (int64_t)m * a.ldy + col0;
+                    if (sgm == 1) {                          // all TMEM reads of this accumulator are done
+                        tc_fence_before();
+                        mbar_arrive(&S->acc_empty[buf]);
+                    }
+                    const int col0 = nb * TC_N + c0;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float y[4];
+                    for (int j = 0; j < 32; j += 4) {
+                        float y[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                float t = fmaf(__uint_as_float(d1[j + u]), 1.0f / 2048.0f, __uint_as_float(d0[j + u]));
-                                if (a.bias != nullptr) t += __ldg(a.bias + col0 + j + u);
-                                if (a.act == 1) t = t / (1.0f + expf(-t));
-                                y[u] = t;
-                            }
-                            *reinterpret_cast<float4*>(dst + j) = make_float4(y[0], y[1], y[2], y[3]);
+                        for (int u = 0; u < 4; ++u) {
+                            float v = fmaf(__uint_as_float(d1[j + u]), 1.0f / 2048.0f, __uint_as_float(d0[j + u]));
+                            if (a.bias != nullptr) v += __ldg(a.bias + col0 + j + u);
+                            if (a.act == 1) v = v / (1.0f + expf(-v));
+                            y[u] = v;
+                        }
+                        const int lc = h * 8 + (j >> 2);
+                        *reinterpret_cast<float4*>(Yst + er * 256 + ((lc ^ (er & 7)) << 4)) = make_float4(y[0], y[1], y[2], y[3]);
+                    }
+                    epi_barrier();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int id = i * 256 + t, row = id >> 4, lc = id & 15;
+                        const int m = tile * TC_M + row;
+                        if (m < a.M) {
+                            const float4 v = *reinterpret_cast<const float4*>(Yst + row * 256 + ((lc ^ (row & 7)) << 4));
+                            *reinterpret_cast<float4*>(a.Y + (int64_t)m * a.ldy + nb * TC_N + 64 * sgm + lc * 4) = v;
                         }
                     }
+                    epi_barrier();
                 }
-                tc_fence_before();
-                mbar_arrive(&S->acc_empty[buf]);
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ================= weight-stage producer =================
         if (lane == 0) {
             uint32_t cnt = 0;
+            const int KSN = a.K / TC_KS;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-                for (int nb = 0; nb < NB; ++nb)
-                    for (int ks = 0; ks < KSN; ++ks, ++cnt) {
-                        const uint32_t s = cnt % TC_NSTAGE, ph = (cnt / TC_NSTAGE) & 1;
-                        mbar_wait(&S->empty[s], ph ^ 1);
-                        mbar_expect_tx(&S->full[s], TC_STAGE_BYTES);
-                        bulk_g2s(Bst + s * TC_STAGE_BYTES, Wfmt + (size_t)(nb * KSN + ks) * TC_STAGE_BYTES,
-                                 TC_STAGE_BYTES, &S->full[s]);
-                    }
+                for (int phase = 0; phase < NPH; ++phase)
+                    for (int nb = 0; nb < NB; ++nb)
+                        for (int ksl = 0; ksl < 128 / TC_KS; ++ksl, ++cnt) {
+                            const uint32_t s = cnt % TC_NSTAGE, ph = (cnt / TC_NSTAGE) & 1;
+                            mbar_wait(&S->empty[s], ph ^ 1);
+                            mbar_expect_tx(&S->full[s], TC_STAGE_BYTES);
+                            const int ks = phase * (128 / TC_KS) + ksl;
+                            bulk_g2s(Bst + s * TC_STAGE_BYTES, Wfmt + (size_t)(nb * KSN + ks) * TC_STAGE_BYTES,
+                                     TC_STAGE_BYTES, &S->full[s]);
+                        }
         }
     } else {
         // ================= MMA issuer =================
         if (lane == 0) {
-            uint32_t cnt = 0, acc_it = 0, tile_it = 0;
+            uint32_t cnt = 0, acc_base = 0, ph_it = 0;
             const uint32_t a_hi0 = smem_u32(A_hi), a_lo0 = smem_u32(A_lo), b0 = smem_u32(Bst);
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-                mbar_wait(&S->a_ready, tile_it & 1);
-                tc_fence_after();
-                for (int nb = 0; nb < NB; ++nb, ++acc_it) {
-                    const uint32_t buf = acc_it & 1;
-                    mbar_wait(&S->acc_empty[buf], ((acc_it >> 1) & 1) ^ 1);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, acc_base += NB) {
+                for (int phase = 0; phase < NPH; ++phase, ++ph_it) {
+                    mbar_wait(&S->a_ready, ph_it & 1);
                     tc_fence_after();
-                    const uint32_t d0 = tmem + buf * 256, d1 = d0 + 128;
-                    for (int ks = 0; ks < KSN; ++ks, ++cnt) {
-                        const uint32_t s = cnt % TC_NSTAGE, ph = (cnt / TC_NSTAGE) & 1;
-                        mbar_wait(&S->full[s], ph);
-                        tc_fence_after();
-                        const uint32_t bh = b0 + s * TC_STAGE_BYTES, bl = bh + TC_HALF_STAGE;
-#pragma unroll
-                        for (int j = 0; j < TC_KS / 16; ++j) {
-                            const uint32_t koff_a = (uint32_t)(ks * (TC_KS / 8) + 2 * j) * CORE_LBO;
-                            const uint32_t koff_b = (uint32_t)(2 * j) * CORE_LBO;
-                            const uint32_t first = (ks == 0 && j == 0) ? 0u : 1u;
-                            umma_f16(d0, make_desc(a_hi0 + koff_a), make_desc(bh + koff_b), first);
-                            umma_f16(d1, make_desc(a_hi0 + koff_a), make_desc(bl + koff_b), first);
-                            umma_f16(d1, make_desc(a_lo0 + koff_a), make_desc(bh + koff_b), 1u);
+                    for (int nb = 0; nb < NB; ++nb) {
+                        const uint32_t acc_it = acc_base + nb, buf = acc_it & 1;
+                        if (phase == 0) {
+                            mbar_wait(&S->acc_empty[buf], ((acc_it >> 1) & 1) ^ 1);
+                            tc_fence_after();
                         }
-                        umma_commit(&S->empty[s]);      // frees the weight stage when these MMAs retire
+                        const uint32_t d0 = tmem + buf * 256, d1 = d0 + 128;
+                        for (int ksl = 0; ksl < 128 / TC_KS; ++ksl, ++cnt) {
+                            const uint32_t s = cnt % TC_NSTAGE, ph = (cnt / TC_NSTAGE) & 1;
+                            mbar_wait(&S->full[s], ph);
+                            tc_fence_after();
+                            const uint32_t bh = b0 + s * TC_STAGE_BYTES, bl = bh + TC_HALF_STAGE;
+#pragma unroll
+                            for (int j = 0; j < TC_KS / 16; ++j) {
+                                const uint32_t koff_a = (uint32_t)(ksl * (TC_KS / 8) + 2 * j) * CORE_LBO;
+                                const uint32_t koff_b = (uint32_t)(2 * j) * CORE_LBO;
+                                const uint32_t acc = (phase == 0 && ksl == 0 && j == 0) ? 0u : 1u;
+                                umma_f16(d0, make_desc(a_hi0 + koff_a), make_desc(bh + koff_b), acc);
+                                umma_f16(d1, make_desc(a_hi0 + koff_a), make_desc(bl + koff_b), acc);
+                                umma_f16(d1, make_desc(a_lo0 + koff_a), make_desc(bh + koff_b), 1u);
+                            }
+                            umma_commit(&S->empty[s]);                       // frees the weight stage
+                        }
+                        if (phase == NPH - 1) umma_commit(&S->acc_full[buf]);  // publishes (D0, D1)
                     }
-                    umma_commit(&S->acc_full[buf]);      // publishes (D0, D1) of this N-block
+                    umma_commit(&S->a_free);                                 // A buffers may be overwritten
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 9) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
 
-size_t tc_smem_bytes(int K) { return (size_t)2 * K * 256 + TC_NSTAGE * TC_STAGE_BYTES + sizeof(TcSmem) + 64; }
+size_t tc_smem_bytes(int) { return (size_t)131072 + TC_NSTAGE * TC_STAGE_BYTES + 32768 + sizeof(TcSmem) + 64; }
 
 }  // namespace
 
@@ -296,8 +347,8 @@ void tc_format_weight(const float* W, int N, int K, std::vector<uint8_t>& out) {
 }
 
 bool tc_linear_supported(const LinearArgs& a) {
-    return a.N % TC_N == 0 && a.K % TC_KS == 0 && a.K <= 256 && (a.A2 == nullptr || a.K1 % 8 == 0) &&
-           a.lda % 4 == 0 && a.ldy % 4 == 0;
+    const bool k_ok = a.K == 128 || (a.K == 256 && a.N <= 2 * TC_N);   // K=256 keeps every N-block's accumulator live
+    return a.N % TC_N == 0 && k_ok && (a.A2 == nullptr || a.K1 == 128) && a.lda % 4 == 0 && a.ldy % 4 == 0;
 }
 
 int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt) {
