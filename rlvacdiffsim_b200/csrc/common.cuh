@@ -61,6 +61,7 @@ struct Weights {
     const float* emb = nullptr;                 // [100,128]
     const float* freqs = nullptr;               // [20]
     const float* filt_T = nullptr;              // [L][21][384]  (k<20: weight^T, k=20: bias)
+    const void* filt_F = nullptr;               // [L][3 parts][hi|lo] tf32 tensor-core operand (tc_edge.cu)
     const float* inter_w0T[NLAYER] = {};        // [128][128]   (in-major: Wt[k][n])
     const float* inter_b0[NLAYER] = {};
     const float* inter_w3T[NLAYER] = {};        // [128][384]
@@ -161,6 +162,10 @@ int launch_embed(rlvd_engine* e, cudaStream_t s, int M, const int* Z, float* q);
 int launch_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* row_ptr, const int* col,
                 const int8_t* shift, const float* pos, const float* cell, const int* node_struct,
                 const float* x, const float* mu_in, float* q, float* mu_out);
+int launch_tc_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* row_ptr, const int* col,
+                   const int8_t* shift, const float* pos, const float* cell, const int* node_struct,
+                   const float* x, const float* mu_in, float* q, float* mu_out);
+void tc_edge_format_filters(const float* W, const float* b, std::vector<uint8_t>& out);
 int launch_mix_reduce(rlvd_engine* e, cudaStream_t s, int M, const float* mix, float* nrm, float* vw);
 int launch_mix_update(rlvd_engine* e, cudaStream_t s, int M, const float* ctx, const float* mix,
                       const float* vw, float* q, float* mu);

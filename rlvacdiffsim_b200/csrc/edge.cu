@@ -142,6 +142,8 @@ int launch_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* row
                 const int8_t* shift, const float* pos, const float* cell, const int* node_struct, const float* x,
                 const float* mu_in, float* q, float* mu_out) {
     if (M <= 0) return 0;
+    if (e->use_tensor_cores)
+        return launch_tc_edge(e, s, layer, M, row_ptr, col, shift, pos, cell, node_struct, x, mu_in, q, mu_out);
     const float* filt = e->w.filt_T + (size_t)layer * (NRBF + 1) * 3 * F;
     const int grid = (M + RPC - 1) / RPC;
     Span sp(e, s, FAM_EDGE);

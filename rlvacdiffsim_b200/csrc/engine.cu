@@ -203,6 +203,11 @@ int rlvd_finalize_weights(rlvd_engine* e) {
                 ft[((size_t)l * (NRBF + 1) + NRBF) * 3 * F + o] = (*fb)[row];
             }
         if (upload_raw(e, ft, &w.filt_T)) return 1;
+        std::vector<uint8_t> ff;
+        tc_edge_format_filters(fw->data(), fb->data(), ff);
+        void* dff = nullptr;
+        if (upload(e, ff.data(), ff.size(), &dff)) return 1;
+        w.filt_F = dff;
     }
     for (int l = 0; l < NLAYER; ++l) {
         const std::string pi = rep + "interactions." + std::to_string(l) + ".interatomic_context_net.layers.";
