@@ -173,7 +173,8 @@ def main():
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 512 MB > 126 MB L2
 
     def step_device():
-        return eng.score_device(d["Z"], d["pos"], d["cell"], d["inv"], d["img"], d["ptr"], d["rs"], d["ps"], qp)
+        return eng.score_device(d["Z"], d["pos"], d["cell"], d["inv"], d["img"], d["ptr"], d["rs"], d["ps"], qp,
+                                max_struct_nodes=int(np.diff(pk["node_ptr"]).max()))
 
     def step_host():
         return eng.score_host(pk["Z"], pk["pos"], pk["cells"], pk["node_ptr"], pk["react_struct"], pk["prod_struct"], qp)

@@ -81,9 +81,12 @@ int  rlvd_radius_graph_fill(rlvd_engine* e, void* stream, int32_t n_struct, int3
 
 /* ---- K2..K4: PaiNN representation (R2..R6) on a disjoint-union batch ---------------------------- */
 /* d_Z[M] atomic numbers (int32).  Output d_q[M,128] fp32 scalar features after 3 interaction+mixing
- * blocks.  d_mu (optional, may be NULL) receives the vector features [M,3,128]. */
+ * blocks.  d_mu (optional, may be NULL) receives the vector features [M,3,128].  max_struct_nodes is the
+ * largest atom count of any structure (host-known from node_ptr); when it is <= 256 the edge stage runs the
+ * structure-resident sliced kernel, otherwise the general gather kernel. */
 int  rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes,
-                               int64_t n_edges, const int32_t* d_Z, const float* d_pos,
+                               int64_t n_edges, int32_t max_struct_nodes, const int32_t* d_node_ptr,
+                               const int32_t* d_Z, const float* d_pos,
                                const float* d_cell, const int32_t* d_node_struct,
                                const int32_t* d_row_ptr, const int32_t* d_col, const int8_t* d_shift,
                                float* d_q, float* d_mu);
@@ -119,7 +122,8 @@ int  rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, i
  * fp32 SIMT tile kernel.  Synchronises the stream.  (nn.Linear inside rgnn's PaiNN) */
 int  rlvd_linear(rlvd_engine* e, void* stream, int32_t M, int32_t K, int32_t N, const float* d_A,
                  const float* d_A2, int32_t K1, const float* h_W, const float* h_bias, int32_t act, float* d_Y);
-/* Engine options: "tensor_cores" (1 = tcgen05 channel-mixing GEMMs, 0 = fp32 SIMT tiles; both fp32-accurate). */
+/* Engine options: "tensor_cores" (1 = tcgen05 GEMMs and filters, 0 = fp32 SIMT kernels; both fp32-accurate),
+ * "sliced_edge" (1 = structure-resident sliced edge kernel for structures of <= 256 atoms, 0 = general). */
 int  rlvd_set_option(rlvd_engine* e, const char* name, int32_t value);
 
 /* ---- introspection ------------------------------------------------------------------------------ */

@@ -35,8 +35,8 @@ SYMBOLS = {
     "rlvd_radius_graph_count": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_float, _P, _P, _P]),
     "rlvd_radius_graph_fill": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_float, _P,
                                          C.c_int64, _P, _P]),
-    "rlvd_painn_representation": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, _P, _P,
-                                            _P, _P]),
+    "rlvd_painn_representation": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P, _P,
+                                            _P, _P, _P, _P, _P]),
     "rlvd_reaction_readout": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.POINTER(QParams), _P,
                                         _P, _P, _P, _P, _P, _P]),
     "rlvd_score_reactions_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float,

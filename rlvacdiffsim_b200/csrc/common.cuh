@@ -62,6 +62,8 @@ struct Weights {
     const float* freqs = nullptr;               // [20]
     const float* filt_T = nullptr;              // [L][21][384]  (k<20: weight^T, k=20: bias)
     const void* filt_F = nullptr;               // [L][3 parts][hi|lo] tf32 tensor-core operand (tc_edge.cu)
+    const void* filt_S = nullptr;               // [L][4 slices][hi|lo] tf32 operand of the sliced kernel (tc_edge_small.cu)
+    const float* feps = nullptr;                // [20] freqs[k] - (k+1)*freqs[0]
     const float* inter_w0T[NLAYER] = {};        // [128][128]   (in-major: Wt[k][n])
     const float* inter_b0[NLAYER] = {};
     const float* inter_w3T[NLAYER] = {};        // [128][384]
@@ -107,12 +109,13 @@ struct rlvd_engine {
     rlvd::Weights w;
     bool finalized = false;
     // workspaces (grown on demand, never shrunk)
-    rlvd::DevBuf x, mu0, mu1, hid, mix, nrm, vw, ctx, struct_edges, struct_edge_ptr, scratch;
+    rlvd::DevBuf x, mu0, mu1, hid, mix, nrm, vw, ctx, struct_edges, struct_edge_ptr, scratch, geom;
     // host-path staging
     rlvd::DevBuf in_node_ptr, in_Z, in_pos, in_cell, in_inv, in_img, in_rs, in_ps, in_temp, in_qp;
     rlvd::DevBuf g_row_ptr, g_node_struct, g_col, g_shift, g_nedges, g_q, out_pack;
     int64_t launches = 0;
     bool use_tensor_cores = true;
+    bool use_sliced_edge = true;    // structure-resident sliced edge kernel when every structure has <= 256 atoms
     bool profiling = false;
     std::vector<rlvd::ProfSpan> spans;
     std::vector<cudaEvent_t> event_pool;
@@ -159,9 +162,30 @@ bool tc_linear_supported(const LinearArgs& a);
 void tc_format_weight(const float* W, int N, int K, std::vector<uint8_t>& out);
 
 int launch_embed(rlvd_engine* e, cudaStream_t s, int M, const int* Z, float* q);
-int launch_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* row_ptr, const int* col,
-                const int8_t* shift, const float* pos, const float* cell, const int* node_struct,
-                const float* x, const float* mu_in, float* q, float* mu_out);
+struct EdgeArgs {
+    int layer = 0, M = 0, n_struct = 0, max_struct_nodes = 0;
+    bool sliced = false;            // geometry records are ready (launch_edge_geometry ran)
+    const int* node_ptr = nullptr;
+    const int* row_ptr = nullptr;
+    const int* col = nullptr;
+    const int8_t* shift = nullptr;
+    const float* pos = nullptr;
+    const float* cell = nullptr;
+    const int* node_struct = nullptr;
+    const float* x = nullptr;
+    const float* mu_in = nullptr;   // null in layer 0 (mu == 0)
+    float* q = nullptr;
+    float* mu_out = nullptr;
+};
+int launch_edge(rlvd_engine* e, cudaStream_t s, const EdgeArgs& a);
+bool tc_edge_small_supported(int max_struct_nodes);
+int launch_edge_geometry(rlvd_engine* e, cudaStream_t s, int M, int64_t n_edges, const int* node_ptr,
+                         const int* node_struct, const int* row_ptr, const int* col, const int8_t* shift, const float* pos,
+                         const float* cell);
+int launch_tc_edge_small(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, int max_struct_nodes,
+                         const int* node_ptr, const int* row_ptr, const float* x, const float* mu_in, float* q,
+                         float* mu_out);
+void tc_edge_small_format(const float* W, const float* b, std::vector<uint8_t>& out);
 int launch_tc_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* row_ptr, const int* col,
                    const int8_t* shift, const float* pos, const float* cell, const int* node_struct,
                    const float* x, const float* mu_in, float* q, float* mu_out);

@@ -138,21 +138,24 @@ __global__ void __launch_bounds__(EDGE_THREADS) edge_kernel(
 
 }  // namespace
 
-int launch_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* row_ptr, const int* col,
-                const int8_t* shift, const float* pos, const float* cell, const int* node_struct, const float* x,
-                const float* mu_in, float* q, float* mu_out) {
+int launch_edge(rlvd_engine* e, cudaStream_t s, const EdgeArgs& a) {
+    const int M = a.M;
     if (M <= 0) return 0;
+    if (a.sliced)
+        return launch_tc_edge_small(e, s, a.layer, a.n_struct, a.max_struct_nodes, a.node_ptr, a.row_ptr, a.x, a.mu_in,
+                                    a.q, a.mu_out);
     if (e->use_tensor_cores)
-        return launch_tc_edge(e, s, layer, M, row_ptr, col, shift, pos, cell, node_struct, x, mu_in, q, mu_out);
-    const float* filt = e->w.filt_T + (size_t)layer * (NRBF + 1) * 3 * F;
+        return launch_tc_edge(e, s, a.layer, M, a.row_ptr, a.col, a.shift, a.pos, a.cell, a.node_struct, a.x, a.mu_in, a.q,
+                              a.mu_out);
+    const float* filt = e->w.filt_T + (size_t)a.layer * (NRBF + 1) * 3 * F;
     const int grid = (M + RPC - 1) / RPC;
     Span sp(e, s, FAM_EDGE);
-    if (mu_in == nullptr) {
-        edge_kernel<false><<<grid, EDGE_THREADS, 0, s>>>(M, filt, e->w.freqs, row_ptr, col, shift, pos, cell,
-                                                         node_struct, x, nullptr, q, mu_out, e->w.cutoff);
+    if (a.mu_in == nullptr) {
+        edge_kernel<false><<<grid, EDGE_THREADS, 0, s>>>(M, filt, e->w.freqs, a.row_ptr, a.col, a.shift, a.pos, a.cell,
+                                                         a.node_struct, a.x, nullptr, a.q, a.mu_out, e->w.cutoff);
     } else {
-        edge_kernel<true><<<grid, EDGE_THREADS, 0, s>>>(M, filt, e->w.freqs, row_ptr, col, shift, pos, cell,
-                                                        node_struct, x, mu_in, q, mu_out, e->w.cutoff);
+        edge_kernel<true><<<grid, EDGE_THREADS, 0, s>>>(M, filt, e->w.freqs, a.row_ptr, a.col, a.shift, a.pos, a.cell,
+                                                        a.node_struct, a.x, a.mu_in, a.q, a.mu_out, e->w.cutoff);
     }
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());

@@ -3,6 +3,7 @@
 // rlsim/drl/simulator.py:56 (`model(batch, q_params)["rl_q"]`).  See include/rlvd_b200.h.
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 
 #include "common.cuh"
@@ -141,7 +142,7 @@ void rlvd_engine_destroy(rlvd_engine* e) {
     cudaSetDevice(e->device);
     for (void* d : e->derived) cudaFree(d);
     for (DevBuf* b : {&e->x, &e->mu0, &e->mu1, &e->hid, &e->mix, &e->nrm, &e->vw, &e->ctx, &e->struct_edges,
-                      &e->struct_edge_ptr, &e->scratch, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
+                      &e->struct_edge_ptr, &e->scratch, &e->geom, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
                       &e->in_inv, &e->in_img, &e->in_rs, &e->in_ps, &e->in_temp, &e->in_qp, &e->g_row_ptr,
                       &e->g_node_struct, &e->g_col, &e->g_shift, &e->g_nedges, &e->g_q, &e->out_pack})
         b->release();
@@ -189,6 +190,11 @@ int rlvd_finalize_weights(rlvd_engine* e) {
     if (need(rep + "cutoff_fn.cutoff", 1, &t)) return 1;
     w.cutoff = (*t)[0];
     if (need(rep + "radial_basis.freqs", NRBF, &t) || upload_raw(e, *t, &w.freqs)) return 1;
+    {
+        std::vector<float> eps(NRBF);
+        for (int k = 0; k < NRBF; ++k) eps[k] = (float)((double)(*t)[k] - (double)(k + 1) * (double)(*t)[0]);
+        if (upload_raw(e, eps, &w.feps)) return 1;
+    }
     if (need(rep + "embedding.weight", 100 * F, &t) || upload_raw(e, *t, &w.emb)) return 1;
     {
         const std::vector<float>*fw = nullptr, *fb = nullptr;
@@ -208,6 +214,11 @@ int rlvd_finalize_weights(rlvd_engine* e) {
         void* dff = nullptr;
         if (upload(e, ff.data(), ff.size(), &dff)) return 1;
         w.filt_F = dff;
+        std::vector<uint8_t> fs;
+        tc_edge_small_format(fw->data(), fb->data(), fs);
+        void* dfs = nullptr;
+        if (upload(e, fs.data(), fs.size(), &dfs)) return 1;
+        w.filt_S = dfs;
     }
     for (int l = 0; l < NLAYER; ++l) {
         const std::string pi = rep + "interactions." + std::to_string(l) + ".interatomic_context_net.layers.";
@@ -299,11 +310,10 @@ int rlvd_radius_graph_fill(rlvd_engine* e, void* stream, int32_t n_struct, int32
 }
 
 int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes, int64_t n_edges,
-                              const int32_t* d_Z, const float* d_pos, const float* d_cell,
-                              const int32_t* d_node_struct, const int32_t* d_row_ptr, const int32_t* d_col,
-                              const int8_t* d_shift, float* d_q, float* d_mu) {
-    (void)n_struct;
-    (void)n_edges;
+                              int32_t max_struct_nodes, const int32_t* d_node_ptr, const int32_t* d_Z,
+                              const float* d_pos, const float* d_cell, const int32_t* d_node_struct,
+                              const int32_t* d_row_ptr, const int32_t* d_col, const int8_t* d_shift, float* d_q,
+                              float* d_mu) {
     RLVD_CHECK(e != nullptr && e->finalized, "rlvd_painn_representation: weights are not finalized");
     RLVD_CUDA(cudaSetDevice(e->device));
     cudaStream_t s = (cudaStream_t)stream;
@@ -323,6 +333,10 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
     float* ctx = e->ctx.as<float>();
     const Weights& w = e->w;
 
+    const bool sliced = e->use_tensor_cores && e->use_sliced_edge && d_node_ptr != nullptr &&
+                        tc_edge_small_supported(max_struct_nodes) && n_edges > 0;
+    if (sliced && launch_edge_geometry(e, s, M, n_edges, d_node_ptr, d_node_struct, d_row_ptr, d_col, d_shift, d_pos, d_cell))
+        return 1;
     if (launch_embed(e, s, M, d_Z, d_q)) return 1;
     for (int l = 0; l < NLAYER; ++l) {
         // R5 node part: x = Lin3(SiLU(Lin0(q)))
@@ -335,9 +349,11 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
         a1.Y = x; a1.ldy = 3 * F; a1.act = 0;
         if (launch_linear(e, s, a1)) return 1;
         // R2 + R3 + R5 edge part + K4
-        if (launch_edge(e, s, l, M, d_row_ptr, d_col, d_shift, d_pos, d_cell, d_node_struct, x,
-                        l == 0 ? nullptr : mu_cur, d_q, mu_nxt))
-            return 1;
+        EdgeArgs ea;
+        ea.layer = l; ea.M = M; ea.sliced = sliced; ea.n_struct = n_struct; ea.max_struct_nodes = max_struct_nodes; ea.node_ptr = d_node_ptr;
+        ea.row_ptr = d_row_ptr; ea.col = d_col; ea.shift = d_shift; ea.pos = d_pos; ea.cell = d_cell;
+        ea.node_struct = d_node_struct; ea.x = x; ea.mu_in = l == 0 ? nullptr : mu_cur; ea.q = d_q; ea.mu_out = mu_nxt;
+        if (launch_edge(e, s, ea)) return 1;
         float* tmp = mu_cur; mu_cur = mu_nxt; mu_nxt = tmp;
         // R6: mixing
         LinearArgs am;
@@ -416,7 +432,10 @@ int rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, in
                              e->in_cell.as<float>(), e->in_inv.as<float>(), e->in_img.as<int>(), cutoff,
                              e->g_row_ptr.as<int>(), E, e->g_col.as<int>(), e->g_shift.as<int8_t>()))
         return 1;
-    if (rlvd_painn_representation(e, stream, n_struct, M, E, e->in_Z.as<int>(), e->in_pos.as<float>(),
+    int max_nodes = 0;
+    for (int g = 0; g < n_struct; ++g) max_nodes = std::max(max_nodes, h_node_ptr[g + 1] - h_node_ptr[g]);
+    if (rlvd_painn_representation(e, stream, n_struct, M, E, max_nodes, e->in_node_ptr.as<int>(), e->in_Z.as<int>(),
+                                  e->in_pos.as<float>(),
                                   e->in_cell.as<float>(), e->g_node_struct.as<int>(), e->g_row_ptr.as<int>(),
                                   e->g_col.as<int>(), e->g_shift.as<int8_t>(), e->g_q.as<float>(), nullptr))
         return 1;
@@ -439,6 +458,10 @@ int rlvd_set_option(rlvd_engine* e, const char* name, int32_t value) {
     RLVD_CHECK(e != nullptr && name != nullptr, "bad argument");
     if (strcmp(name, "tensor_cores") == 0) {
         e->use_tensor_cores = value != 0;
+        return 0;
+    }
+    if (strcmp(name, "sliced_edge") == 0) {
+        e->use_sliced_edge = value != 0;
         return 0;
     }
     RLVD_CHECK(false, "unknown option '%s'", name);

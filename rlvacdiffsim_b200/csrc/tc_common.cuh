@@ -29,13 +29,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must trap, never hang the GPU.
+// Bounded wait: a protocol bug must trap, never hang the GPU.  A few fast polls, then back off with nanosleep so
+// that waiting warps do not steal issue slots from the warps they are waiting for.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+#pragma unroll 1
+    for (int fast = 0; fast < 8; ++fast)
+        if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+#pragma unroll 1
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("rlvd tc_linear: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __nanosleep(32);
+        if (++spins > 40000000u) {   // > 1 s: protocol bug
+            printf("rlvd: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();
         }
     }

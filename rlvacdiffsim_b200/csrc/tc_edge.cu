@@ -12,7 +12,7 @@
 // (hi = rna_tf32(v), lo = v - hi) and accumulated as hi·hi + hi·lo + lo·hi into one fp32 TMEM accumulator:
 // 22-bit operands, no scaling games, fp32-level filters.
 //
-// CTA = 256 consecutive receivers (their CSR rows are one contiguous edge range, cut into 32-edge tiles).
+// CTA = 64 consecutive receivers (their CSR rows are one contiguous edge range, cut into 32-edge tiles).
 //   warps 0-3  consumers: thread = channel = TMEM lane.  tcgen05.ld the three filter values of 8 edges at a
 //              time, gather x[j], mu[j] (coalesced 512 B rows), accumulate the row in CSR order, flush q / mu on
 //              every receiver change — no atomics, bitwise reproducible
@@ -33,7 +33,7 @@ namespace {
 
 constexpr int NE = 32;                 // edges per tile = MMA N
 constexpr int KP = 24;                 // padded K: 20 rbf + bias + 3 zeros (3 k-steps of 8 tf32)
-constexpr int RC = 256;                // receivers per CTA
+constexpr int RC = 64;                 // receivers per CTA (small enough that the in-flight node tables stay in L2)
 constexpr int TE_THREADS = 288;
 constexpr int A_HALF = 6 * 2048;       // one of hi/lo of one part: 6 core columns x (16 row groups x 128 B)
 constexpr int A_BYTES = 3 * 2 * A_HALF;   // 73728

@@ -1,0 +1,431 @@
+// K2 + K3a + K3c + K4 fused for structures of at most 256 atoms — the BASELINE workload (255/256-atom replicas).
+//
+// Same contract as edge.cu / tc_edge.cu.  What bounds those two is the gather: every edge pulls x[j] and mu[j]
+// (3 KB) from L2, 126 GB per layer at 128 replicas — more than the L2→SM fabric moves in the time the math
+// needs.  Here the gather never leaves the SM: a CTA owns ONE structure and ONE 32-channel slice, and keeps that
+// slice of the structure's whole node table (x: n x 96, mu: n x 96 fp32 = 192 KB) in shared memory, read from
+// HBM/L2 exactly once.  Four CTAs (slices) cover a structure; nothing is exchanged between them.
+//
+// Filters run on the tensor cores as in tc_edge.cu, transposed so they land in TMEM as lane = filter row,
+// column = edge:   D[128, 16 edges] = Wslice[96(+32 aliased) rows, 24] · Phi[16, 24]ᵀ,  tf32 hi/lo x3.
+// Rows 0-31 are the dq filters of the slice, 32-63 dmuR, 64-95 dmumu, so TMEM lane quarter = message part and
+// the three consumer warps of a pipeline each own one part:
+//      q-warp :  dq    += W · x_q[j]
+//      R-warp :  dmu_k += (W · x_R[j]) · dir_k
+//      m-warp :  dmu_k += (W · x_m[j]) · mu_k[j]        (partials of R and m are summed at the receiver flush)
+// A CTA runs three such pipelines on disjoint receiver ranges.  The per-edge embedding (20 x phi_k·fcut, fcut, dir)
+// is computed ONCE per representation call by edge_geom_kernel (one accurate sincos + an angle-addition tree) into
+// a 128-byte record per edge, shared by the 3 layers x 4 slices; warp 4p+3 of pipeline p streams the next 16-edge
+// tile of records (prefetched one tile ahead), splits it into the tf32 hi/lo operand tile and issues the 9 MMAs.
+// Consumers issue all shared-memory gathers of a half-tile before the first dependent FMA.  Sums run in CSR
+// order: no atomics, bitwise reproducible.
+#include <cstring>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace rlvd {
+
+namespace {
+
+constexpr int SL = 32;                  // channels per slice
+constexpr int NSLICE = F / SL;          // 4
+constexpr int NE = 16;                  // edges per tile = MMA N
+constexpr int KP = 24;
+constexpr int NPIPE = 3;
+constexpr int ES_THREADS = NPIPE * 128;
+constexpr int MAXN = 256;
+constexpr int A_COL = 12 * 128;         // bytes per core column: 12 stored row groups (rows 96..127 alias the next column)
+constexpr int A_HALF = 6 * A_COL + 512; // + overrun pad of the last column
+constexpr int A_SLICE = 2 * A_HALF;     // hi | lo   = 19456
+constexpr int B_HALF = 6 * 256;         // 6 core columns x 2 row groups x 128 B
+constexpr int B_TILE = 2 * B_HALF;      // 3072
+constexpr int META = NE * 24;           // j[16] | recv[16] | dir[16] float4 = 64 + 64 + 256
+constexpr float PI_F = 3.14159265358979323846f;
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NE >> 3) << 17) | (8u << 24);
+
+struct EsBars {
+    uint64_t mma_done[NPIPE][2], acc_free[NPIPE][2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void umma_tf32_n16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ float tf32_hi(float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void pair_barrier(int pipe) { asm volatile("bar.sync %0, 64;" ::"r"(pipe + 1) : "memory"); }
+
+// smem carve-up (dynamic): Xt | Mt | A | B[NPIPE] | meta[NPIPE][2] | exch[NPIPE][2][3][32] | rowp[MAXN+1] | bars
+struct Layout {
+    uint32_t xt, mt, a, b, meta, exch, rowp, bars, total;
+};
+__host__ __device__ inline Layout make_layout(int n_max) {
+    Layout L;
+    uint32_t o = 0;
+    L.xt = o; o += (uint32_t)n_max * 3 * SL * 4;
+    L.mt = o; o += (uint32_t)n_max * 3 * SL * 4;
+    L.a = o; o += A_SLICE;
+    L.b = o; o += NPIPE * B_TILE;
+    L.meta = o; o += NPIPE * 2 * META;
+    L.exch = o; o += NPIPE * 2 * 3 * SL * 4;
+    L.rowp = o; o += (MAXN + 1 + 3) / 4 * 16;
+    L.bars = o; o += 128;
+    L.total = o;
+    return L;
+}
+
+// Per-edge embedding record (8 x float4 = 128 B), computed once per representation call:
+//   c0..c4 = phi_k * fcut (k = 0..19)     c5 = { fcut, dir.x, dir.y, dir.z }     c6 = { j - node0, i - node0, 0, 0 } (ints)
+// sin(freqs[k] d): one accurate sincos of theta = freqs[0]*d (fp32 product error folded in), an angle-addition tree
+// of depth <= 5 for k*theta, and the deviation freqs[k] - (k+1)*freqs[0] folded in to first order (max abs error
+// 1.4e-6, below the 1.9e-6 argument-rounding error of evaluating sin(fl(freqs[k]*d)) directly in fp32).
+// One warp per receiver row, lanes over its edges.
+__global__ void __launch_bounds__(256) edge_geom_kernel(int M, const int* __restrict__ node_ptr,
+                                                        const int* __restrict__ node_struct,
+                                                        const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                                        const int8_t* __restrict__ shift, const float* __restrict__ pos,
+                                                        const float* __restrict__ cell, const float* __restrict__ freqs,
+                                                        const float* __restrict__ feps, float cutoff,
+                                                        float4* __restrict__ rec) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= M) return;
+    const int gs = __ldg(node_struct + i), node0 = __ldg(node_ptr + gs);
+    const float xi = __ldg(pos + 3 * (int64_t)i), yi = __ldg(pos + 3 * (int64_t)i + 1), zi = __ldg(pos + 3 * (int64_t)i + 2);
+    float C[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) C[t] = __ldg(cell + 9 * gs + t);
+    const float f1 = __ldg(freqs), pi_over_rc = PI_F / cutoff;
+    const int e_hi = __ldg(row_ptr + i + 1);
+    for (int e = __ldg(row_ptr + i) + lane; e < e_hi; e += 32) {
+        const int jg = __ldg(col + e);
+        const float S0 = (float)shift[3 * (int64_t)e], S1 = (float)shift[3 * (int64_t)e + 1], S2 = (float)shift[3 * (int64_t)e + 2];
+        float rx = __ldg(pos + 3 * (int64_t)jg) - xi, ry = __ldg(pos + 3 * (int64_t)jg + 1) - yi,
+              rz = __ldg(pos + 3 * (int64_t)jg + 2) - zi;
+        rx += S0 * C[0] + S1 * C[3] + S2 * C[6];
+        ry += S0 * C[1] + S1 * C[4] + S2 * C[7];
+        rz += S0 * C[2] + S1 * C[5] + S2 * C[8];
+        const float d = sqrtf(rx * rx + ry * ry + rz * rz);
+        const float inv_d = 1.0f / d;
+        const float fc = d < cutoff ? 0.5f * (cosf(d * pi_over_rc) + 1.0f) : 0.f;
+        const float scale = inv_d * fc;
+        const float pr = f1 * d, perr = fmaf(f1, d, -pr);
+        float sn, cs;
+        sincosf(pr, &sn, &cs);
+        float s[NRBF + 1], c[NRBF + 1], v[NRBF];
+        s[1] = fmaf(perr, cs, sn);
+        c[1] = fmaf(-perr, sn, cs);
+#define RLVD_ADD(a, b) { s[(a) + (b)] = fmaf(s[a], c[b], c[a] * s[b]); c[(a) + (b)] = fmaf(c[a], c[b], -(s[a] * s[b])); }
+        RLVD_ADD(1, 1) RLVD_ADD(2, 1) RLVD_ADD(2, 2) RLVD_ADD(4, 1) RLVD_ADD(4, 2) RLVD_ADD(4, 3) RLVD_ADD(4, 4)
+        RLVD_ADD(8, 1) RLVD_ADD(8, 2) RLVD_ADD(8, 3) RLVD_ADD(8, 4) RLVD_ADD(8, 5) RLVD_ADD(8, 6) RLVD_ADD(8, 7)
+        RLVD_ADD(8, 8) RLVD_ADD(16, 1) RLVD_ADD(16, 2) RLVD_ADD(16, 3) RLVD_ADD(16, 4)
+#undef RLVD_ADD
+#pragma unroll
+        for (int k = 0; k < NRBF; ++k) v[k] = fmaf(__ldg(feps + k) * d, c[k + 1], s[k + 1]) * scale;
+        float4* o = rec + 8 * (int64_t)e;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) o[t] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+        o[5] = make_float4(fc, rx * inv_d, ry * inv_d, rz * inv_d);
+        o[6] = make_float4(__int_as_float(jg - node0), __int_as_float(i - node0), 0.f, 0.f);
+    }
+}
+
+template <bool HAS_MU>
+__global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
+    int n_struct, int n_max, const int* __restrict__ node_ptr, const uint8_t* __restrict__ Wsl /* [4 slices][A_SLICE] */,
+    const int* __restrict__ row_ptr, const float4* __restrict__ rec, const float* __restrict__ x, const float* __restrict__ mu_in, float* __restrict__ q, float* __restrict__ mu_out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const Layout L = make_layout(n_max);
+    float* Xt = reinterpret_cast<float*>(smem + L.xt);
+    float* Mt = reinterpret_cast<float*>(smem + L.mt);
+    uint8_t* Aw = smem + L.a;
+    int* rowp = reinterpret_cast<int*>(smem + L.rowp);
+    EsBars* S = reinterpret_cast<EsBars*>(smem + L.bars);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x / NSLICE, slice = blockIdx.x % NSLICE;
+    const int node0 = __ldg(node_ptr + g), n = __ldg(node_ptr + g + 1) - node0;
+    const int e_base = __ldg(row_ptr + node0);
+
+    if (tid == 0) {
+        for (int p = 0; p < NPIPE; ++p)
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&S->mma_done[p][b], 1);
+                mbar_init(&S->acc_free[p][b], HAS_MU ? 96 : 64);
+            }
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(&S->tmem_base, 128);
+
+    // ---- stage this slice of the structure's node table, the slice's filter weights and the CSR row offsets
+    {
+        const uint32_t xt_s = smem_u32(Xt), mt_s = smem_u32(Mt), a_s = smem_u32(Aw);
+        const int chunks = n * 24;                                  // 3 parts x 8 x 16 B per node
+        for (int id = tid; id < chunks; id += ES_THREADS) {
+            const int node = id / 24, r = id - node * 24, part = r >> 3, c16 = r & 7;
+            const size_t goff = ((size_t)(node0 + node) * 3 * F + part * F + slice * SL) * 4 + c16 * 16;
+            const uint32_t soff = (uint32_t)(node * 3 * SL + part * SL) * 4 + c16 * 16;
+            cp16(xt_s + soff, reinterpret_cast<const uint8_t*>(x) + goff);
+            if (HAS_MU) cp16(mt_s + soff, reinterpret_cast<const uint8_t*>(mu_in) + goff);
+        }
+        for (int id = tid; id < A_SLICE / 16; id += ES_THREADS)
+            cp16(a_s + id * 16, Wsl + (size_t)slice * A_SLICE + (size_t)id * 16);
+        for (int id = tid; id <= n; id += ES_THREADS) rowp[id] = __ldg(row_ptr + node0 + id);
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        fence_async_smem();                                         // cp.async-written weights → UMMA (async proxy)
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S->tmem_base;
+
+    const int pipe = warp >> 2, role = warp & 3;                    // role 0 q, 1 R, 2 m, 3 producer (= TMEM lane quarter)
+    const int ra = (pipe * n) / NPIPE, rb = ((pipe + 1) * n) / NPIPE;   // local receiver range of this pipeline
+    const int e_begin = rowp[ra], e_end = rowp[rb];
+    const int n_tiles = (e_end - e_begin + NE - 1) / NE;
+    uint8_t* Bt = smem + L.b + pipe * B_TILE;
+    uint8_t* MetaP = smem + L.meta + pipe * 2 * META;
+    float* Ex = reinterpret_cast<float*>(smem + L.exch) + pipe * 2 * 3 * SL;
+
+    if (role == 3) {
+        // ======================= producer + MMA issuer =======================
+        // lane = (edge e = lane/2, half = lane%2): half 0 carries record chunks c0,c1,c2,c6, half 1 carries c3,c4,c5.
+        const uint32_t a_hi = smem_u32(Aw), a_lo = a_hi + A_HALF, b_hi = smem_u32(Bt), b_lo = b_hi + B_HALF;
+        const int pe = lane >> 1, half = lane & 1;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 n0 = zero4, n1 = zero4, n2 = zero4, n3 = zero4;
+        bool nvalid = false;
+        auto fetch = [&](int t) {
+            const int eid = e_begin + t * NE + pe;
+            nvalid = t < n_tiles && eid < e_end;
+            if (nvalid) {
+                const float4* r = rec + 8 * (int64_t)eid + 3 * half;
+                n0 = __ldg(r); n1 = __ldg(r + 1); n2 = __ldg(r + 2);
+                if (half == 0) n3 = __ldg(r + 6);
+            }
+        };
+        fetch(0);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int buf = t & 1;
+            float4 v0 = n0, v1 = n1, v2 = n2, m3 = n3;
+            if (!nvalid) {                                               // padding edge: zero filters, harmless receiver
+                v0 = v1 = v2 = zero4;
+                m3 = make_float4(__int_as_float(0), __int_as_float(rb - 1), 0.f, 0.f);
+            }
+            fetch(t + 1);                                                // prefetch: hidden behind this tile's work
+            float4 dir4 = zero4;
+            if (half == 1) {                                             // c5 = { fcut, dir } → k = 20..23 = { fcut, 0, 0, 0 }
+                dir4 = make_float4(v2.y, v2.z, v2.w, 0.f);
+                v2 = make_float4(v2.x, 0.f, 0.f, 0.f);
+            }
+            mbar_wait(&S->acc_free[pipe][buf], ((t >> 1) & 1) ^ 1);     // consumers released this buffer's meta + TMEM
+            if (t > 0) mbar_wait(&S->mma_done[pipe][buf ^ 1], ((t - 1) >> 1) & 1);   // previous tile's MMAs read B
+            {
+                uint8_t* meta = MetaP + buf * META;
+                if (half == 0) {
+                    reinterpret_cast<int*>(meta)[pe] = __float_as_int(m3.x);
+                    reinterpret_cast<int*>(meta + 64)[pe] = __float_as_int(m3.y);
+                } else {
+                    reinterpret_cast<float4*>(meta + 128)[pe] = dir4;
+                }
+                const uint32_t roff = (pe >> 3) * 128 + (pe & 7) * 16;
+                const float4 vv[3] = {v0, v1, v2};
+#pragma unroll
+                for (int i3 = 0; i3 < 3; ++i3) {
+                    const int kc = 3 * half + i3;
+                    float4 h, l;
+                    h.x = tf32_hi(vv[i3].x); h.y = tf32_hi(vv[i3].y); h.z = tf32_hi(vv[i3].z); h.w = tf32_hi(vv[i3].w);
+                    l.x = vv[i3].x - h.x; l.y = vv[i3].y - h.y; l.z = vv[i3].z - h.z; l.w = vv[i3].w - h.w;
+                    *reinterpret_cast<float4*>(Bt + kc * 256 + roff) = h;
+                    *reinterpret_cast<float4*>(Bt + B_HALF + kc * 256 + roff) = l;
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tc_fence_after();
+                const uint32_t d = tmem + (uint32_t)(pipe * 2 + buf) * NE;
+#pragma unroll
+                for (int ks = 0; ks < KP / 8; ++ks) {
+                    const uint64_t dah = umma_desc(a_hi + ks * 2 * A_COL, A_COL, 128), dal = umma_desc(a_lo + ks * 2 * A_COL, A_COL, 128);
+                    const uint64_t dbh = umma_desc(b_hi + ks * 512, 256, 128), dbl = umma_desc(b_lo + ks * 512, 256, 128);
+                    umma_tf32_n16(d, dah, dbh, ks == 0 ? 0u : 1u);
+                    umma_tf32_n16(d, dah, dbl, 1u);
+                    umma_tf32_n16(d, dal, dbh, 1u);
+                }
+                umma_commit(&S->mma_done[pipe][buf]);
+            }
+            __syncwarp();
+        }
+    } else if (role < (HAS_MU ? 3 : 2)) {
+        // ======================= consumers: lane = channel of the slice, role = message part =======================
+        const uint32_t taddr0 = tmem + ((uint32_t)(role * 32) << 16) + (uint32_t)(pipe * 2) * NE;
+        const int ch = slice * SL + lane;
+        int i_cur = ra, n_flush = 0;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;                            // q-warp: a0 = dq;  R/m-warp: a0..a2 = dmu partials
+        auto flush_to = [&](int next) {
+            for (int i = i_cur; i < next; ++i, ++n_flush) {
+                const int64_t gi = node0 + i;
+                if (role == 0) {
+                    q[gi * F + ch] += a0;
+                } else if (!HAS_MU) {
+                    mu_out[gi * 3 * F + ch] = a0;
+                    mu_out[gi * 3 * F + F + ch] = a1;
+                    mu_out[gi * 3 * F + 2 * F + ch] = a2;
+                } else {
+                    float* ex = Ex + (n_flush & 1) * 3 * SL;
+                    if (role == 2) {
+                        ex[lane] = a0; ex[SL + lane] = a1; ex[2 * SL + lane] = a2;
+                    }
+                    pair_barrier(pipe);
+                    if (role == 1) {
+                        const float* mi = Mt + i * 3 * SL;
+                        mu_out[gi * 3 * F + ch] = mi[lane] + a0 + ex[lane];
+                        mu_out[gi * 3 * F + F + ch] = mi[SL + lane] + a1 + ex[SL + lane];
+                        mu_out[gi * 3 * F + 2 * F + ch] = mi[2 * SL + lane] + a2 + ex[2 * SL + lane];
+                    }
+                }
+                a0 = a1 = a2 = 0.f;
+            }
+            i_cur = next;
+        };
+        for (int t = 0; t < n_tiles; ++t) {
+            const int buf = t & 1;
+            mbar_wait(&S->mma_done[pipe][buf], (t >> 1) & 1);
+            tc_fence_after();
+            uint32_t w[NE];
+            tmem_ld16(taddr0 + buf * NE, w);
+            tmem_wait_ld();
+            const uint8_t* meta = MetaP + buf * META;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {                             // half tiles of 8 edges: all gathers first
+                int jj[8], rr[8];
+#pragma unroll
+                for (int v4 = 0; v4 < 2; ++v4) {
+                    const int4 j4 = *reinterpret_cast<const int4*>(meta + (hh * 8 + v4 * 4) * 4);
+                    const int4 r4 = *reinterpret_cast<const int4*>(meta + 64 + (hh * 8 + v4 * 4) * 4);
+                    jj[4 * v4] = j4.x; jj[4 * v4 + 1] = j4.y; jj[4 * v4 + 2] = j4.z; jj[4 * v4 + 3] = j4.w;
+                    rr[4 * v4] = r4.x; rr[4 * v4 + 1] = r4.y; rr[4 * v4 + 2] = r4.z; rr[4 * v4 + 3] = r4.w;
+                }
+                float xv[8], g0[8], g1[8], g2[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    xv[u] = Xt[jj[u] * 3 * SL + role * SL + lane];
+                    if (role == 1) {
+                        const float4 dir = *reinterpret_cast<const float4*>(meta + 128 + (hh * 8 + u) * 16);
+                        g0[u] = dir.x; g1[u] = dir.y; g2[u] = dir.z;
+                    } else if (role == 2) {
+                        const float* mj = Mt + jj[u] * 3 * SL + lane;
+                        g0[u] = mj[0]; g1[u] = mj[SL]; g2[u] = mj[2 * SL];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (rr[u] != i_cur) flush_to(rr[u]);
+                    const float sx = __uint_as_float(w[hh * 8 + u]) * xv[u];
+                    if (role == 0) {
+                        a0 += sx;
+                    } else {
+                        a0 = fmaf(sx, g0[u], a0);
+                        a1 = fmaf(sx, g1[u], a1);
+                        a2 = fmaf(sx, g2[u], a2);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&S->acc_free[pipe][buf]);
+        }
+        flush_to(rb);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 128);
+    }
+}
+
+uint32_t tf32_round_host2(float w) {
+    uint32_t u;
+    memcpy(&u, &w, 4);
+    u += 0xFFFu + ((u >> 13) & 1u);
+    u &= 0xFFFFE000u;
+    return u;
+}
+
+}  // namespace
+
+// Host: per layer, per 32-channel slice: rows r = part*32 + ch (96 rows), k < 20 weights, k = 20 bias, tf32 hi | lo.
+void tc_edge_small_format(const float* W, const float* b, std::vector<uint8_t>& out) {
+    out.assign((size_t)NLAYER * NSLICE * A_SLICE, 0);
+    for (int l = 0; l < NLAYER; ++l)
+        for (int sl = 0; sl < NSLICE; ++sl)
+            for (int part = 0; part < 3; ++part)
+                for (int chn = 0; chn < SL; ++chn)
+                    for (int k = 0; k <= NRBF; ++k) {
+                        const int row = l * 3 * F + part * F + sl * SL + chn;
+                        const float w = k < NRBF ? W[(size_t)row * NRBF + k] : b[row];
+                        const uint32_t hu = tf32_round_host2(w);
+                        float hf;
+                        memcpy(&hf, &hu, 4);
+                        const float lf = w - hf;
+                        const int r = part * SL + chn;
+                        const size_t off = ((size_t)l * NSLICE + sl) * A_SLICE + (size_t)(k >> 2) * A_COL + (r >> 3) * 128 +
+                                           (r & 7) * 16 + (k & 3) * 4;
+                        memcpy(out.data() + off, &hf, 4);
+                        memcpy(out.data() + off + A_HALF, &lf, 4);
+                    }
+}
+
+bool tc_edge_small_supported(int max_struct_nodes) { return max_struct_nodes > 0 && max_struct_nodes <= MAXN; }
+
+int launch_edge_geometry(rlvd_engine* e, cudaStream_t s, int M, int64_t n_edges, const int* node_ptr,
+                         const int* node_struct, const int* row_ptr, const int* col, const int8_t* shift, const float* pos,
+                         const float* cell) {
+    if (M <= 0 || n_edges <= 0) return 0;
+    if (e->geom.ensure((size_t)n_edges * 128)) return 1;
+    Span sp(e, s, FAM_EDGE);
+    edge_geom_kernel<<<(M + 7) / 8, 256, 0, s>>>(M, node_ptr, node_struct, row_ptr, col, shift, pos, cell, e->w.freqs,
+                                                 e->w.feps, e->w.cutoff, e->geom.as<float4>());
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_tc_edge_small(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, int max_struct_nodes,
+                         const int* node_ptr, const int* row_ptr, const float* x, const float* mu_in, float* q,
+                         float* mu_out) {
+    if (n_struct <= 0) return 0;
+    const Layout L = make_layout(max_struct_nodes);
+    static bool attr_set = false;
+    if (!attr_set) {
+        const int cap = (int)make_layout(MAXN).total;
+        RLVD_CUDA(cudaFuncSetAttribute(tc_edge_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        RLVD_CUDA(cudaFuncSetAttribute(tc_edge_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        attr_set = true;
+    }
+    const uint8_t* wf = reinterpret_cast<const uint8_t*>(e->w.filt_S) + (size_t)layer * NSLICE * A_SLICE;
+    Span sp(e, s, FAM_EDGE);
+    if (mu_in == nullptr)
+        tc_edge_small_kernel<false><<<n_struct * NSLICE, ES_THREADS, L.total, s>>>(
+            n_struct, max_struct_nodes, node_ptr, wf, row_ptr, e->geom.as<float4>(), x, nullptr, q, mu_out);
+    else
+        tc_edge_small_kernel<true><<<n_struct * NSLICE, ES_THREADS, L.total, s>>>(
+            n_struct, max_struct_nodes, node_ptr, wf, row_ptr, e->geom.as<float4>(), x, mu_in, q, mu_out);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rlvd

@@ -133,12 +133,15 @@ class Engine:
     # ------------------------------------------------------------------ K2..K4
     def representation(self, Z: torch.Tensor, pos: torch.Tensor, cell: torch.Tensor, node_struct: torch.Tensor,
                        row_ptr: torch.Tensor, col: torch.Tensor, shift: torch.Tensor, n_struct: int,
-                       return_mu: bool = False):
+                       return_mu: bool = False, node_ptr: Optional[torch.Tensor] = None, max_struct_nodes: int = 0):
         M = pos.shape[0]
+        if node_ptr is None:
+            max_struct_nodes = 0
         q = torch.empty((M, 128), dtype=torch.float32, device=self.device)
         mu = torch.empty((M, 3, 128), dtype=torch.float32, device=self.device) if return_mu else None
         with torch.cuda.device(self.device):
-            check(self.lib.rlvd_painn_representation(self._h, self._stream(), n_struct, M, col.shape[0], _ptr(Z),
+            check(self.lib.rlvd_painn_representation(self._h, self._stream(), n_struct, M, col.shape[0],
+                                                     int(max_struct_nodes), _ptr(node_ptr), _ptr(Z),
                                                      _ptr(pos), _ptr(cell), _ptr(node_struct), _ptr(row_ptr),
                                                      _ptr(col), _ptr(shift), _ptr(q), _ptr(mu)))
         return (q, mu) if return_mu else q
@@ -159,10 +162,11 @@ class Engine:
 
     # ------------------------------------------------------------------ whole path, device-resident inputs
     def score_device(self, Z, pos, cell, inv_cell, img_range, node_ptr, react_struct, prod_struct, qp: QParams,
-                     temperature=None) -> Dict[str, torch.Tensor]:
+                     temperature=None, max_struct_nodes: int = 0) -> Dict[str, torch.Tensor]:
         n_struct = node_ptr.numel() - 1
         row_ptr, col, shift, node_struct = self.radius_graph(pos, cell, inv_cell, img_range, node_ptr)
-        q = self.representation(Z, pos, cell, node_struct, row_ptr, col, shift, n_struct)
+        q = self.representation(Z, pos, cell, node_struct, row_ptr, col, shift, n_struct, node_ptr=node_ptr,
+                                max_struct_nodes=max_struct_nodes)
         out = self.readout(q, Z, node_ptr, react_struct, prod_struct, qp, temperature)
         out["n_edges"] = col.shape[0]
         return out

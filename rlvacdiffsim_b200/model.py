@@ -245,7 +245,7 @@ class DQNv2(nn.Module, _EngineMixin):
         ps = torch.arange(nR, nR + G, dtype=torch.int32, device=dev)
         qp = eng.q_params(q_params, self.head_spec)
         out = eng.score_device(Z_all.contiguous(), pos_all.contiguous(), cell_all.contiguous(), inv_d, img_d,
-                               node_ptr, rs, ps, qp)
+                               node_ptr, rs, ps, qp, max_struct_nodes=int(counts.max()))
         out["barrier"] = -out["q0"]
         out["freq"] = out["q1"]
         return out

@@ -97,12 +97,19 @@ def test_representation_matches_fp64_oracle(engine):
     ptr = np.array([0, n], dtype=np.int32)
     row_ptr, col, shift, node_struct = _device_graph(engine, pos, cells, ptr)
     Z = torch.from_numpy(g["numbers"].astype(np.int32)).cuda()
-    q, mu = engine.representation(Z, torch.from_numpy(pos).cuda(), torch.from_numpy(cells).cuda(), node_struct,
-                                  row_ptr, col, shift, 1, return_mu=True)
     q_ref, mu_ref = g["f64.q_reactant"], g["f64.mu_reactant"]
-    err_q = np.abs(q.cpu().numpy() - q_ref).max() / np.abs(q_ref).max()
-    err_mu = np.abs(mu.cpu().numpy() - mu_ref).max() / np.abs(mu_ref).max()
-    assert err_q < TOL and err_mu < TOL, (err_q, err_mu)
+    ptr_d = torch.from_numpy(ptr).cuda()
+    # the three edge-stage implementations: sliced structure-resident (tcgen05), general gather (tcgen05), fp32 SIMT
+    for opts in ({"tensor_cores": 1, "sliced_edge": 1}, {"tensor_cores": 1, "sliced_edge": 0}, {"tensor_cores": 0}):
+        for k, v in opts.items():
+            engine.set_option(k, v)
+        q, mu = engine.representation(Z, torch.from_numpy(pos).cuda(), torch.from_numpy(cells).cuda(), node_struct,
+                                      row_ptr, col, shift, 1, return_mu=True, node_ptr=ptr_d, max_struct_nodes=n)
+        err_q = np.abs(q.cpu().numpy() - q_ref).max() / np.abs(q_ref).max()
+        err_mu = np.abs(mu.cpu().numpy() - mu_ref).max() / np.abs(mu_ref).max()
+        assert err_q < TOL and err_mu < TOL, (opts, err_q, err_mu)
+    engine.set_option("tensor_cores", 1)
+    engine.set_option("sliced_edge", 1)
 
 
 def _score_batch(model, g, tag, dedup=False):
