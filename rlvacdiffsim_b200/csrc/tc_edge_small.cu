@@ -30,17 +30,19 @@ namespace {
 
 constexpr int SL = 32;                  // channels per slice
 constexpr int NSLICE = F / SL;          // 4
-constexpr int NE = 16;                  // edges per tile = MMA N
+constexpr int NE = 32;                  // edges per tile = MMA N
 constexpr int KP = 24;
 constexpr int NPIPE = 3;
 constexpr int ES_THREADS = NPIPE * 128;
 constexpr int MAXN = 256;
-constexpr int A_COL = 12 * 128;         // bytes per core column: 12 stored row groups (rows 96..127 alias the next column)
-constexpr int A_HALF = 6 * A_COL + 512; // + overrun pad of the last column
-constexpr int A_SLICE = 2 * A_HALF;     // hi | lo   = 19456
-constexpr int B_HALF = 6 * 256;         // 6 core columns x 2 row groups x 128 B
-constexpr int B_TILE = 2 * B_HALF;      // 3072
-constexpr int META = NE * 24;           // j[16] | recv[16] | dir[16] float4 = 64 + 64 + 256
+constexpr int A_ROW = 2 * KP;           // floats per filter row in the host-formatted slice: hi[24] | lo[24]
+constexpr int A_SLICE = 96 * A_ROW * 4; // bytes per (layer, slice)
+constexpr int B_HALF = 6 * 512;         // 6 core columns x 4 row groups x 128 B
+constexpr int B_TILE = 2 * B_HALF;      // hi | lo = 6144
+constexpr int META = NE * 24;           // j[32] | recv[32] | dir[32] float4 = 128 + 128 + 512
+constexpr int TM_D = 0;                 // TMEM columns: accumulators [pipe][buf][32]
+constexpr int TM_A = NPIPE * 2 * NE;    // 192: filter operand A, hi[24] | lo[24]
+constexpr int TM_COLS = 256;
 constexpr float PI_F = 3.14159265358979323846f;
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NE >> 3) << 17) | (8u << 24);
 
@@ -49,13 +51,27 @@ struct EsBars {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void umma_tf32_n16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] · B[smem]ᵀ : the filter rows live in TMEM (lane = row), so the MMA only reads the small
+// per-tile operand from shared memory — with N = 32 an A operand in shared memory would cost 4 KB of smem reads per
+// instruction, three times the gather traffic this kernel exists to keep on-chip.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(IDESC), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8s(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 __device__ __forceinline__ float tf32_hi(float v) {
     uint32_t u;
@@ -67,16 +83,16 @@ __device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void pair_barrier(int pipe) { asm volatile("bar.sync %0, 64;" ::"r"(pipe + 1) : "memory"); }
 
-// smem carve-up (dynamic): Xt | Mt | A | B[NPIPE] | meta[NPIPE][2] | exch[NPIPE][2][3][32] | rowp[MAXN+1] | bars
+// smem carve-up (dynamic): Xt | Mt | B[NPIPE] | meta[NPIPE][2] | exch[NPIPE][2][3][32] | rowp[MAXN+1] | bars
 struct Layout {
-    uint32_t xt, mt, a, b, meta, exch, rowp, bars, total;
+    uint32_t xt, mt, b, meta, exch, rowp, bars, total;
 };
 __host__ __device__ inline Layout make_layout(int n_max) {
     Layout L;
     uint32_t o = 0;
     L.xt = o; o += (uint32_t)n_max * 3 * SL * 4;
     L.mt = o; o += (uint32_t)n_max * 3 * SL * 4;
-    L.a = o; o += A_SLICE;
+    o = (o + 127u) & ~127u;
     L.b = o; o += NPIPE * B_TILE;
     L.meta = o; o += NPIPE * 2 * META;
     L.exch = o; o += NPIPE * 2 * 3 * SL * 4;
@@ -143,20 +159,19 @@ __global__ void __launch_bounds__(256) edge_geom_kernel(int M, const int* __rest
 
 template <bool HAS_MU>
 __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
-    int n_struct, int n_max, const int* __restrict__ node_ptr, const uint8_t* __restrict__ Wsl /* [4 slices][A_SLICE] */,
-    const int* __restrict__ row_ptr, const float4* __restrict__ rec, const float* __restrict__ x, const float* __restrict__ mu_in, float* __restrict__ q, float* __restrict__ mu_out) {
+    int n_struct, int n_max, const int* __restrict__ node_ptr, const float* __restrict__ Wsl /* [4 slices][96][48] */,
+    const int* __restrict__ row_ptr, const float4* __restrict__ rec, const float* __restrict__ x,
+    const float* __restrict__ mu_in, float* __restrict__ q, float* __restrict__ mu_out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const Layout L = make_layout(n_max);
     float* Xt = reinterpret_cast<float*>(smem + L.xt);
     float* Mt = reinterpret_cast<float*>(smem + L.mt);
-    uint8_t* Aw = smem + L.a;
     int* rowp = reinterpret_cast<int*>(smem + L.rowp);
     EsBars* S = reinterpret_cast<EsBars*>(smem + L.bars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x / NSLICE, slice = blockIdx.x % NSLICE;
     const int node0 = __ldg(node_ptr + g), n = __ldg(node_ptr + g + 1) - node0;
-    const int e_base = __ldg(row_ptr + node0);
 
     if (tid == 0) {
         for (int p = 0; p < NPIPE; ++p)
@@ -166,11 +181,11 @@ __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
             }
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc(&S->tmem_base, 128);
+    if (warp == 0) tmem_alloc(&S->tmem_base, TM_COLS);
 
-    // ---- stage this slice of the structure's node table, the slice's filter weights and the CSR row offsets
+    // ---- stage this slice of the structure's node table and the CSR row offsets
     {
-        const uint32_t xt_s = smem_u32(Xt), mt_s = smem_u32(Mt), a_s = smem_u32(Aw);
+        const uint32_t xt_s = smem_u32(Xt), mt_s = smem_u32(Mt);
         const int chunks = n * 24;                                  // 3 parts x 8 x 16 B per node
         for (int id = tid; id < chunks; id += ES_THREADS) {
             const int node = id / 24, r = id - node * 24, part = r >> 3, c16 = r & 7;
@@ -179,16 +194,33 @@ __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
             cp16(xt_s + soff, reinterpret_cast<const uint8_t*>(x) + goff);
             if (HAS_MU) cp16(mt_s + soff, reinterpret_cast<const uint8_t*>(mu_in) + goff);
         }
-        for (int id = tid; id < A_SLICE / 16; id += ES_THREADS)
-            cp16(a_s + id * 16, Wsl + (size_t)slice * A_SLICE + (size_t)id * 16);
         for (int id = tid; id <= n; id += ES_THREADS) rowp[id] = __ldg(row_ptr + node0 + id);
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-        fence_async_smem();                                         // cp.async-written weights → UMMA (async proxy)
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S->tmem_base;
+
+    // ---- filter operand A → TMEM (lane = filter row: 0-31 dq, 32-63 dmuR, 64-95 dmumu of this slice, 96-127 zero)
+    if (warp < 4) {
+        const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + TM_A;
+        const float4* wrow = reinterpret_cast<const float4*>(Wsl + ((size_t)slice * 96 + warp * 32 + lane) * A_ROW);
+#pragma unroll
+        for (int c8 = 0; c8 < A_ROW / 8; ++c8) {
+            uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (warp < 3) {
+                const float4 f0 = __ldg(wrow + 2 * c8), f1 = __ldg(wrow + 2 * c8 + 1);
+                v[0] = __float_as_uint(f0.x); v[1] = __float_as_uint(f0.y); v[2] = __float_as_uint(f0.z); v[3] = __float_as_uint(f0.w);
+                v[4] = __float_as_uint(f1.x); v[5] = __float_as_uint(f1.y); v[6] = __float_as_uint(f1.z); v[7] = __float_as_uint(f1.w);
+            }
+            tmem_st8(ta + c8 * 8, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
     const int pipe = warp >> 2, role = warp & 3;                    // role 0 q, 1 R, 2 m, 3 producer (= TMEM lane quarter)
     const int ra = (pipe * n) / NPIPE, rb = ((pipe + 1) * n) / NPIPE;   // local receiver range of this pipeline
@@ -199,70 +231,66 @@ __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
     float* Ex = reinterpret_cast<float*>(smem + L.exch) + pipe * 2 * 3 * SL;
 
     if (role == 3) {
-        // ======================= producer + MMA issuer =======================
-        // lane = (edge e = lane/2, half = lane%2): half 0 carries record chunks c0,c1,c2,c6, half 1 carries c3,c4,c5.
-        const uint32_t a_hi = smem_u32(Aw), a_lo = a_hi + A_HALF, b_hi = smem_u32(Bt), b_lo = b_hi + B_HALF;
-        const int pe = lane >> 1, half = lane & 1;
+        // ======================= producer + MMA issuer: lane = edge of the tile =======================
+        const uint32_t b_hi = smem_u32(Bt), b_lo = b_hi + B_HALF;
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 n0 = zero4, n1 = zero4, n2 = zero4, n3 = zero4;
+        float4 nx[7];
         bool nvalid = false;
         auto fetch = [&](int t) {
-            const int eid = e_begin + t * NE + pe;
+            const int eid = e_begin + t * NE + lane;
             nvalid = t < n_tiles && eid < e_end;
             if (nvalid) {
-                const float4* r = rec + 8 * (int64_t)eid + 3 * half;
-                n0 = __ldg(r); n1 = __ldg(r + 1); n2 = __ldg(r + 2);
-                if (half == 0) n3 = __ldg(r + 6);
+                const float4* r = rec + 8 * (int64_t)eid;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) nx[c] = __ldg(r + c);
             }
         };
         fetch(0);
         for (int t = 0; t < n_tiles; ++t) {
             const int buf = t & 1;
-            float4 v0 = n0, v1 = n1, v2 = n2, m3 = n3;
-            if (!nvalid) {                                               // padding edge: zero filters, harmless receiver
-                v0 = v1 = v2 = zero4;
-                m3 = make_float4(__int_as_float(0), __int_as_float(rb - 1), 0.f, 0.f);
+            float4 v[6];
+            int j = 0, recv = rb - 1;                                    // padding edge: zero filters, harmless receiver
+            float4 dir4 = zero4;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) v[c] = zero4;
+            if (nvalid) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c) v[c] = nx[c];
+                v[5] = make_float4(nx[5].x, 0.f, 0.f, 0.f);              // k = 20: fcut (bias column); 21..23 zero
+                dir4 = make_float4(nx[5].y, nx[5].z, nx[5].w, 0.f);
+                j = __float_as_int(nx[6].x);
+                recv = __float_as_int(nx[6].y);
             }
             fetch(t + 1);                                                // prefetch: hidden behind this tile's work
-            float4 dir4 = zero4;
-            if (half == 1) {                                             // c5 = { fcut, dir } → k = 20..23 = { fcut, 0, 0, 0 }
-                dir4 = make_float4(v2.y, v2.z, v2.w, 0.f);
-                v2 = make_float4(v2.x, 0.f, 0.f, 0.f);
-            }
             mbar_wait(&S->acc_free[pipe][buf], ((t >> 1) & 1) ^ 1);     // consumers released this buffer's meta + TMEM
             if (t > 0) mbar_wait(&S->mma_done[pipe][buf ^ 1], ((t - 1) >> 1) & 1);   // previous tile's MMAs read B
             {
                 uint8_t* meta = MetaP + buf * META;
-                if (half == 0) {
-                    reinterpret_cast<int*>(meta)[pe] = __float_as_int(m3.x);
-                    reinterpret_cast<int*>(meta + 64)[pe] = __float_as_int(m3.y);
-                } else {
-                    reinterpret_cast<float4*>(meta + 128)[pe] = dir4;
-                }
-                const uint32_t roff = (pe >> 3) * 128 + (pe & 7) * 16;
-                const float4 vv[3] = {v0, v1, v2};
+                reinterpret_cast<int*>(meta)[lane] = j;
+                reinterpret_cast<int*>(meta + 128)[lane] = recv;
+                reinterpret_cast<float4*>(meta + 256)[lane] = dir4;
+                const uint32_t roff = (lane >> 3) * 128 + (lane & 7) * 16;
 #pragma unroll
-                for (int i3 = 0; i3 < 3; ++i3) {
-                    const int kc = 3 * half + i3;
+                for (int kc = 0; kc < 6; ++kc) {
                     float4 h, l;
-                    h.x = tf32_hi(vv[i3].x); h.y = tf32_hi(vv[i3].y); h.z = tf32_hi(vv[i3].z); h.w = tf32_hi(vv[i3].w);
-                    l.x = vv[i3].x - h.x; l.y = vv[i3].y - h.y; l.z = vv[i3].z - h.z; l.w = vv[i3].w - h.w;
-                    *reinterpret_cast<float4*>(Bt + kc * 256 + roff) = h;
-                    *reinterpret_cast<float4*>(Bt + B_HALF + kc * 256 + roff) = l;
+                    h.x = tf32_hi(v[kc].x); h.y = tf32_hi(v[kc].y); h.z = tf32_hi(v[kc].z); h.w = tf32_hi(v[kc].w);
+                    l.x = v[kc].x - h.x; l.y = v[kc].y - h.y; l.z = v[kc].z - h.z; l.w = v[kc].w - h.w;
+                    *reinterpret_cast<float4*>(Bt + kc * 512 + roff) = h;
+                    *reinterpret_cast<float4*>(Bt + B_HALF + kc * 512 + roff) = l;
                 }
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
                 tc_fence_after();
-                const uint32_t d = tmem + (uint32_t)(pipe * 2 + buf) * NE;
+                const uint32_t d = tmem + TM_D + (uint32_t)(pipe * 2 + buf) * NE;
+                const uint32_t a_hi = tmem + TM_A, a_lo = a_hi + KP;
 #pragma unroll
                 for (int ks = 0; ks < KP / 8; ++ks) {
-                    const uint64_t dah = umma_desc(a_hi + ks * 2 * A_COL, A_COL, 128), dal = umma_desc(a_lo + ks * 2 * A_COL, A_COL, 128);
-                    const uint64_t dbh = umma_desc(b_hi + ks * 512, 256, 128), dbl = umma_desc(b_lo + ks * 512, 256, 128);
-                    umma_tf32_n16(d, dah, dbh, ks == 0 ? 0u : 1u);
-                    umma_tf32_n16(d, dah, dbl, 1u);
-                    umma_tf32_n16(d, dal, dbh, 1u);
+                    const uint64_t dbh = umma_desc(b_hi + ks * 1024, 512, 128), dbl = umma_desc(b_lo + ks * 1024, 512, 128);
+                    umma_tf32_ts(d, a_hi + ks * 8, dbh, ks == 0 ? 0u : 1u);
+                    umma_tf32_ts(d, a_hi + ks * 8, dbl, 1u);
+                    umma_tf32_ts(d, a_lo + ks * 8, dbh, 1u);
                 }
                 umma_commit(&S->mma_done[pipe][buf]);
             }
@@ -270,7 +298,7 @@ __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
         }
     } else if (role < (HAS_MU ? 3 : 2)) {
         // ======================= consumers: lane = channel of the slice, role = message part =======================
-        const uint32_t taddr0 = tmem + ((uint32_t)(role * 32) << 16) + (uint32_t)(pipe * 2) * NE;
+        const uint32_t taddr0 = tmem + ((uint32_t)(role * 32) << 16) + TM_D + (uint32_t)(pipe * 2) * NE;
         const int ch = slice * SL + lane;
         int i_cur = ra, n_flush = 0;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;                            // q-warp: a0 = dq;  R/m-warp: a0..a2 = dmu partials
@@ -304,17 +332,16 @@ __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
             const int buf = t & 1;
             mbar_wait(&S->mma_done[pipe][buf], (t >> 1) & 1);
             tc_fence_after();
-            uint32_t w[NE];
-            tmem_ld16(taddr0 + buf * NE, w);
-            tmem_wait_ld();
             const uint8_t* meta = MetaP + buf * META;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {                             // half tiles of 8 edges: all gathers first
+#pragma unroll 1
+            for (int hh = 0; hh < NE / 8; ++hh) {                        // groups of 8 edges: all gathers before the FMAs
+                uint32_t w[8];
+                tmem_ld8s(taddr0 + buf * NE + hh * 8, w);
                 int jj[8], rr[8];
 #pragma unroll
                 for (int v4 = 0; v4 < 2; ++v4) {
                     const int4 j4 = *reinterpret_cast<const int4*>(meta + (hh * 8 + v4 * 4) * 4);
-                    const int4 r4 = *reinterpret_cast<const int4*>(meta + 64 + (hh * 8 + v4 * 4) * 4);
+                    const int4 r4 = *reinterpret_cast<const int4*>(meta + 128 + (hh * 8 + v4 * 4) * 4);
                     jj[4 * v4] = j4.x; jj[4 * v4 + 1] = j4.y; jj[4 * v4 + 2] = j4.z; jj[4 * v4 + 3] = j4.w;
                     rr[4 * v4] = r4.x; rr[4 * v4 + 1] = r4.y; rr[4 * v4 + 2] = r4.z; rr[4 * v4 + 3] = r4.w;
                 }
@@ -323,17 +350,18 @@ __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
                 for (int u = 0; u < 8; ++u) {
                     xv[u] = Xt[jj[u] * 3 * SL + role * SL + lane];
                     if (role == 1) {
-                        const float4 dir = *reinterpret_cast<const float4*>(meta + 128 + (hh * 8 + u) * 16);
+                        const float4 dir = *reinterpret_cast<const float4*>(meta + 256 + (hh * 8 + u) * 16);
                         g0[u] = dir.x; g1[u] = dir.y; g2[u] = dir.z;
                     } else if (role == 2) {
                         const float* mj = Mt + jj[u] * 3 * SL + lane;
                         g0[u] = mj[0]; g1[u] = mj[SL]; g2[u] = mj[2 * SL];
                     }
                 }
+                tmem_wait_ld();
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     if (rr[u] != i_cur) flush_to(rr[u]);
-                    const float sx = __uint_as_float(w[hh * 8 + u]) * xv[u];
+                    const float sx = __uint_as_float(w[u]) * xv[u];
                     if (role == 0) {
                         a0 += sx;
                     } else {
@@ -352,7 +380,7 @@ __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem, 128);
+        tmem_dealloc(tmem, TM_COLS);
     }
 }
 
@@ -366,9 +394,11 @@ uint32_t tf32_round_host2(float w) {
 
 }  // namespace
 
-// Host: per layer, per 32-channel slice: rows r = part*32 + ch (96 rows), k < 20 weights, k = 20 bias, tf32 hi | lo.
+// Host: per layer, per 32-channel slice: rows r = part*32 + ch (96 rows) of [hi[24] | lo[24]] tf32-split floats;
+// k < 20 filter_net weights, k = 20 bias (multiplied by the fcut column of the edge operand), 21..23 zero.
 void tc_edge_small_format(const float* W, const float* b, std::vector<uint8_t>& out) {
     out.assign((size_t)NLAYER * NSLICE * A_SLICE, 0);
+    float* o = reinterpret_cast<float*>(out.data());
     for (int l = 0; l < NLAYER; ++l)
         for (int sl = 0; sl < NSLICE; ++sl)
             for (int part = 0; part < 3; ++part)
@@ -379,12 +409,9 @@ void tc_edge_small_format(const float* W, const float* b, std::vector<uint8_t>& 
                         const uint32_t hu = tf32_round_host2(w);
                         float hf;
                         memcpy(&hf, &hu, 4);
-                        const float lf = w - hf;
-                        const int r = part * SL + chn;
-                        const size_t off = ((size_t)l * NSLICE + sl) * A_SLICE + (size_t)(k >> 2) * A_COL + (r >> 3) * 128 +
-                                           (r & 7) * 16 + (k & 3) * 4;
-                        memcpy(out.data() + off, &hf, 4);
-                        memcpy(out.data() + off + A_HALF, &lf, 4);
+                        const size_t base = (((size_t)l * NSLICE + sl) * 96 + part * SL + chn) * A_ROW;
+                        o[base + k] = hf;
+                        o[base + KP + k] = w - hf;
                     }
 }
 
@@ -415,7 +442,7 @@ int launch_tc_edge_small(rlvd_engine* e, cudaStream_t s, int layer, int n_struct
         RLVD_CUDA(cudaFuncSetAttribute(tc_edge_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         attr_set = true;
     }
-    const uint8_t* wf = reinterpret_cast<const uint8_t*>(e->w.filt_S) + (size_t)layer * NSLICE * A_SLICE;
+    const float* wf = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(e->w.filt_S) + (size_t)layer * NSLICE * A_SLICE);
     Span sp(e, s, FAM_EDGE);
     if (mu_in == nullptr)
         tc_edge_small_kernel<false><<<n_struct * NSLICE, ES_THREADS, L.total, s>>>(
