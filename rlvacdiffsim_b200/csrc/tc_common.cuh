@@ -18,28 +18,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the hint (ns) expires: it is a sleep with a
+// ~60-cycle wake-up, not a poll, so waiting warps cost no issue slots.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must trap, never hang the GPU.  A few fast polls, then back off with nanosleep so
-// that waiting warps do not steal issue slots from the warps they are waiting for.
+// Bounded wait: a protocol bug must trap, never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#pragma unroll 1
-    for (int fast = 0; fast < 8; ++fast)
-        if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
 #pragma unroll 1
     while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(32);
-        if (++spins > 40000000u) {   // > 1 s: protocol bug
+        if (++spins > 200000u) {   // >> 1 s of suspended waiting: protocol bug
             printf("rlvd: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();
         }

@@ -1,24 +1,27 @@
 // K2 + K3a + K3c + K4 fused for structures of at most 256 atoms — the BASELINE workload (255/256-atom replicas).
 //
 // Same contract as edge.cu / tc_edge.cu.  What bounds those two is the gather: every edge pulls x[j] and mu[j]
-// (3 KB) from L2, 126 GB per layer at 128 replicas — more than the L2→SM fabric moves in the time the math
-// needs.  Here the gather never leaves the SM: a CTA owns ONE structure and ONE 32-channel slice, and keeps that
-// slice of the structure's whole node table (x: n x 96, mu: n x 96 fp32 = 192 KB) in shared memory, read from
-// HBM/L2 exactly once.  Four CTAs (slices) cover a structure; nothing is exchanged between them.
+// (3 KB) from L2, 126 GB per layer at 128 replicas.  Here the gather never leaves the SM: a CTA owns ONE structure
+// and ONE 32-channel slice and keeps that slice of the structure's whole node table ([n][x_q, x_R, x_m, mu_x, mu_y,
+// mu_z][32] fp32 = 192 KB) in shared memory, read from HBM/L2 exactly once.  Four CTAs (slices) cover a
+// structure; nothing is exchanged between them.
 //
-// Filters run on the tensor cores as in tc_edge.cu, transposed so they land in TMEM as lane = filter row,
-// column = edge:   D[128, 16 edges] = Wslice[96(+32 aliased) rows, 24] · Phi[16, 24]ᵀ,  tf32 hi/lo x3.
-// Rows 0-31 are the dq filters of the slice, 32-63 dmuR, 64-95 dmumu, so TMEM lane quarter = message part and
-// the three consumer warps of a pipeline each own one part:
-//      q-warp :  dq    += W · x_q[j]
-//      R-warp :  dmu_k += (W · x_R[j]) · dir_k
-//      m-warp :  dmu_k += (W · x_m[j]) · mu_k[j]        (partials of R and m are summed at the receiver flush)
-// A CTA runs three such pipelines on disjoint receiver ranges.  The per-edge embedding (20 x phi_k·fcut, fcut, dir)
-// is computed ONCE per representation call by edge_geom_kernel (one accurate sincos + an angle-addition tree) into
-// a 128-byte record per edge, shared by the 3 layers x 4 slices; warp 4p+3 of pipeline p streams the next 16-edge
-// tile of records (prefetched one tile ahead), splits it into the tf32 hi/lo operand tile and issues the 9 MMAs.
-// Consumers issue all shared-memory gathers of a half-tile before the first dependent FMA.  Sums run in CSR
-// order: no atomics, bitwise reproducible.
+// Filters run on the tensor cores, transposed so they land in TMEM as lane = filter row, column = edge:
+//      D[128, 32 edges] = Wslice[128 rows, 24] · Phi[32, 24]ᵀ          tf32 hi/lo x3, A operand resident in TMEM
+// Rows 0-31 are the dq filters of the slice, 32-63 dmuR, 64-95 and 96-127 both dmumu, so the TMEM lane quarter a
+// warp may read selects its share of the message:
+//      warp 0 (q) :  dq          += W · x_q[j]
+//      warp 1 (R) :  dmu_k       += (W · x_R[j]) · dir_k
+//      warp 2 (m) :  dmu_{x,y}   += (W · x_m[j]) · mu_{x,y}[j]
+//      warp 3 (m') : dmu_z       += (W · x_m[j]) · mu_z[j]            (partials are summed at the receiver flush)
+// A CTA runs three such 4-warp pipelines on disjoint receiver ranges, fed by three producer warps.  The per-edge
+// embedding (20 x phi_k·fcut, fcut, dir) is computed ONCE per representation call by edge_geom_kernel into a
+// 128-byte record per edge, shared by the 3 layers x 4 slices; a producer streams the records of the next tile
+// (prefetched one tile ahead), splits them into the tf32 hi/lo operand tile and issues the 9 MMAs.  Tiles are built
+// from receiver-aligned groups of 8 edge slots (short rows padded with zero filters), so consumers test for a
+// receiver change once per group, issue all shared-memory gathers of a group before the first dependent FMA, and
+// address the table as [per-thread base + per-edge byte offset + immediate].  Sums run in CSR order: no atomics,
+// bitwise reproducible.
 #include <cstring>
 
 #include "common.cuh"
@@ -30,16 +33,18 @@ namespace {
 
 constexpr int SL = 32;                  // channels per slice
 constexpr int NSLICE = F / SL;          // 4
-constexpr int NE = 32;                  // edges per tile = MMA N
+constexpr int NE = 32;                  // edge slots per tile = MMA N
+constexpr int GS = 8;                   // slots per receiver-aligned group
 constexpr int KP = 24;
 constexpr int NPIPE = 3;
-constexpr int ES_THREADS = NPIPE * 128;
+constexpr int ES_THREADS = NPIPE * 128 + NPIPE * 32;   // 12 consumer warps + 3 producer warps
 constexpr int MAXN = 256;
+constexpr int NODE_BYTES = 6 * SL * 4;  // table row: x_q, x_R, x_m, mu_x, mu_y, mu_z of the slice
 constexpr int A_ROW = 2 * KP;           // floats per filter row in the host-formatted slice: hi[24] | lo[24]
-constexpr int A_SLICE = 96 * A_ROW * 4; // bytes per (layer, slice)
+constexpr int A_SLICE = 128 * A_ROW * 4;// bytes per (layer, slice)
 constexpr int B_HALF = 6 * 512;         // 6 core columns x 4 row groups x 128 B
 constexpr int B_TILE = 2 * B_HALF;      // hi | lo = 6144
-constexpr int META = NE * 24;           // j[32] | recv[32] | dir[32] float4 = 128 + 128 + 512
+constexpr int META = 768;               // joff[32] (128 B) | dir[32] float4 (512 B) | recv[4] (16 B) | pad
 constexpr int TM_D = 0;                 // TMEM columns: accumulators [pipe][buf][32]
 constexpr int TM_A = NPIPE * 2 * NE;    // 192: filter operand A, hi[24] | lo[24]
 constexpr int TM_COLS = 256;
@@ -81,17 +86,16 @@ __device__ __forceinline__ float tf32_hi(float v) {
 __device__ __forceinline__ void cp16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void pair_barrier(int pipe) { asm volatile("bar.sync %0, 64;" ::"r"(pipe + 1) : "memory"); }
+__device__ __forceinline__ void trio_barrier(int pipe) { asm volatile("bar.sync %0, 96;" ::"r"(pipe + 1) : "memory"); }
 
-// smem carve-up (dynamic): Xt | Mt | B[NPIPE] | meta[NPIPE][2] | exch[NPIPE][2][3][32] | rowp[MAXN+1] | bars
+// smem carve-up (dynamic): table | B[NPIPE] | meta[NPIPE][2] | exch[NPIPE][2][3][32] | rowp[MAXN+1] | bars
 struct Layout {
-    uint32_t xt, mt, b, meta, exch, rowp, bars, total;
+    uint32_t tab, b, meta, exch, rowp, bars, total;
 };
 __host__ __device__ inline Layout make_layout(int n_max) {
     Layout L;
     uint32_t o = 0;
-    L.xt = o; o += (uint32_t)n_max * 3 * SL * 4;
-    L.mt = o; o += (uint32_t)n_max * 3 * SL * 4;
+    L.tab = o; o += (uint32_t)n_max * NODE_BYTES;
     o = (o + 127u) & ~127u;
     L.b = o; o += NPIPE * B_TILE;
     L.meta = o; o += NPIPE * 2 * META;
@@ -157,27 +161,140 @@ __global__ void __launch_bounds__(256) edge_geom_kernel(int M, const int* __rest
     }
 }
 
+struct ConsState {
+    int i_cur, n_flush;
+    float a0, a1, a2, q_cur;
+};
+
+// Receiver change: write the finished receiver (and any edgeless receivers before `next`).  Rare (once per ~7
+// groups), kept out of line so the hot loop stays small enough for the instruction cache.
+template <bool HAS_MU, int ROLE>
+__device__ __noinline__ void flush_rows(ConsState& st, int next, int pipe, const uint8_t* tb, float* Ex, int rb, int node0,
+                                        int ch, int lane, float* __restrict__ q, float* __restrict__ mu_out) {
+    for (int i = st.i_cur; i < next; ++i, ++st.n_flush) {
+        const int64_t gi = node0 + i;
+        if (ROLE == 0) {
+            q[gi * F + ch] = st.q_cur + st.a0;
+            if (i + 1 < rb) st.q_cur = q[(gi + 1) * F + ch];      // next receiver's q: loaded now, needed one row later
+        } else if (!HAS_MU) {
+            mu_out[gi * 3 * F + ch] = st.a0;
+            mu_out[gi * 3 * F + F + ch] = st.a1;
+            mu_out[gi * 3 * F + 2 * F + ch] = st.a2;
+        } else {
+            float* ex = Ex + (st.n_flush & 1) * 3 * SL;
+            if (ROLE == 2) { ex[lane] = st.a0; ex[SL + lane] = st.a1; }
+            if (ROLE == 3) ex[2 * SL + lane] = st.a0;
+            trio_barrier(pipe);
+            if (ROLE == 1) {
+                const float* mi = reinterpret_cast<const float*>(tb + i * NODE_BYTES + 384);
+                mu_out[gi * 3 * F + ch] = mi[0] + st.a0 + ex[lane];
+                mu_out[gi * 3 * F + F + ch] = mi[SL] + st.a1 + ex[SL + lane];
+                mu_out[gi * 3 * F + 2 * F + ch] = mi[2 * SL] + st.a2 + ex[2 * SL + lane];
+            }
+        }
+        st.a0 = st.a1 = st.a2 = 0.f;
+    }
+    st.i_cur = next;
+}
+
+// One consumer warp: ROLE is its TMEM lane quarter = its share of the message (see the file header).
+template <bool HAS_MU, int ROLE>
+__device__ __forceinline__ void consume_tiles(const EsBars* S, int pipe, int n_tiles, uint32_t tmem, const uint8_t* MetaP,
+                                              const uint8_t* tb, float* Ex, int ra, int rb, int node0, int ch, int lane,
+                                              float* __restrict__ q, float* __restrict__ mu_out, long long* dbg) {
+    const uint32_t taddr0 = tmem + ((uint32_t)(ROLE * 32) << 16) + TM_D + (uint32_t)(pipe * 2) * NE;
+    ConsState st;                          // ROLE 0: a0 = dq; 1: dmu_xyz (dir part); 2: dmu_xy (mu part); 3: a0 = dmu_z (mu part)
+    st.i_cur = ra; st.n_flush = 0; st.a0 = st.a1 = st.a2 = 0.f; st.q_cur = 0.f;
+    if (ROLE == 0 && ra < rb) st.q_cur = q[(int64_t)(node0 + ra) * F + ch];
+    for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+#ifdef RLVD_TIMELINE
+        const bool DBG = dbg != nullptr && blockIdx.x == 0 && pipe == 0 && lane == 0 && t < 48;
+        if (DBG) dbg[(t * 5 + ROLE + 1) * 4 + 0] = clock64();
+#endif
+        mbar_wait(const_cast<uint64_t*>(&S->mma_done[pipe][buf]), (t >> 1) & 1);
+#ifdef RLVD_TIMELINE
+        if (DBG) dbg[(t * 5 + ROLE + 1) * 4 + 1] = clock64();
+#endif
+        tc_fence_after();
+        const uint8_t* meta = MetaP + buf * META;
+#pragma unroll 1
+        for (int gg = 0; gg < NE / GS; ++gg) {
+            uint32_t w[8];
+            tmem_ld8s(taddr0 + buf * NE + gg * GS, w);
+            const int recv = *reinterpret_cast<const int*>(meta + 640 + gg * 4);
+            const int4 ja = *reinterpret_cast<const int4*>(meta + gg * 32), jb = *reinterpret_cast<const int4*>(meta + gg * 32 + 16);
+            const int jo[8] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
+            float xv[8], g0[8], g1[8], g2[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint8_t* row = tb + jo[u];
+                if (ROLE == 0) {
+                    xv[u] = *reinterpret_cast<const float*>(row);
+                } else if (ROLE == 1) {
+                    xv[u] = *reinterpret_cast<const float*>(row + 128);
+                    const float4 dir = *reinterpret_cast<const float4*>(meta + 128 + (gg * GS + u) * 16);
+                    g0[u] = dir.x; g1[u] = dir.y; g2[u] = dir.z;
+                } else if (ROLE == 2) {
+                    xv[u] = *reinterpret_cast<const float*>(row + 256);
+                    g0[u] = *reinterpret_cast<const float*>(row + 384);
+                    g1[u] = *reinterpret_cast<const float*>(row + 512);
+                } else {
+                    xv[u] = *reinterpret_cast<const float*>(row + 256);
+                    g0[u] = *reinterpret_cast<const float*>(row + 640);
+                }
+            }
+            if (recv != st.i_cur) flush_rows<HAS_MU, ROLE>(st, recv, pipe, tb, Ex, rb, node0, ch, lane, q, mu_out);
+            tmem_wait_ld();
+            float a0 = st.a0, a1 = st.a1, a2 = st.a2;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float sx = __uint_as_float(w[u]) * xv[u];
+                if (ROLE == 0) {
+                    a0 += sx;
+                } else if (ROLE == 1) {
+                    a0 = fmaf(sx, g0[u], a0);
+                    a1 = fmaf(sx, g1[u], a1);
+                    a2 = fmaf(sx, g2[u], a2);
+                } else if (ROLE == 2) {
+                    a0 = fmaf(sx, g0[u], a0);
+                    a1 = fmaf(sx, g1[u], a1);
+                } else {
+                    a0 = fmaf(sx, g0[u], a0);
+                }
+            }
+            st.a0 = a0; st.a1 = a1; st.a2 = a2;
+        }
+        tc_fence_before();
+        mbar_arrive(const_cast<uint64_t*>(&S->acc_free[pipe][buf]));
+#ifdef RLVD_TIMELINE
+        if (DBG) dbg[(t * 5 + ROLE + 1) * 4 + 2] = clock64();
+#endif
+    }
+    flush_rows<HAS_MU, ROLE>(st, rb, pipe, tb, Ex, rb, node0, ch, lane, q, mu_out);
+}
+
 template <bool HAS_MU>
 __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
-    int n_struct, int n_max, const int* __restrict__ node_ptr, const float* __restrict__ Wsl /* [4 slices][96][48] */,
+    int n_struct, int n_max, const int* __restrict__ node_ptr, const float* __restrict__ Wsl /* [4 slices][128][48] */,
     const int* __restrict__ row_ptr, const float4* __restrict__ rec, const float* __restrict__ x,
-    const float* __restrict__ mu_in, float* __restrict__ q, float* __restrict__ mu_out) {
+    const float* __restrict__ mu_in, float* __restrict__ q, float* __restrict__ mu_out, long long* dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const Layout L = make_layout(n_max);
-    float* Xt = reinterpret_cast<float*>(smem + L.xt);
-    float* Mt = reinterpret_cast<float*>(smem + L.mt);
+    uint8_t* Tab = smem + L.tab;
     int* rowp = reinterpret_cast<int*>(smem + L.rowp);
     EsBars* S = reinterpret_cast<EsBars*>(smem + L.bars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x / NSLICE, slice = blockIdx.x % NSLICE;
     const int node0 = __ldg(node_ptr + g), n = __ldg(node_ptr + g + 1) - node0;
+    constexpr int NCONS = HAS_MU ? 4 : 2;                           // consumer warps per pipeline
 
     if (tid == 0) {
         for (int p = 0; p < NPIPE; ++p)
             for (int b = 0; b < 2; ++b) {
                 mbar_init(&S->mma_done[p][b], 1);
-                mbar_init(&S->acc_free[p][b], HAS_MU ? 96 : 64);
+                mbar_init(&S->acc_free[p][b], NCONS * 32);
             }
         fence_mbar_init();
     }
@@ -185,14 +302,13 @@ __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
 
     // ---- stage this slice of the structure's node table and the CSR row offsets
     {
-        const uint32_t xt_s = smem_u32(Xt), mt_s = smem_u32(Mt);
-        const int chunks = n * 24;                                  // 3 parts x 8 x 16 B per node
-        for (int id = tid; id < chunks; id += ES_THREADS) {
-            const int node = id / 24, r = id - node * 24, part = r >> 3, c16 = r & 7;
-            const size_t goff = ((size_t)(node0 + node) * 3 * F + part * F + slice * SL) * 4 + c16 * 16;
-            const uint32_t soff = (uint32_t)(node * 3 * SL + part * SL) * 4 + c16 * 16;
-            cp16(xt_s + soff, reinterpret_cast<const uint8_t*>(x) + goff);
-            if (HAS_MU) cp16(mt_s + soff, reinterpret_cast<const uint8_t*>(mu_in) + goff);
+        const uint32_t tab_s = smem_u32(Tab);
+        const int per_node = HAS_MU ? 48 : 24;                      // 16-byte chunks: 3 (or 6) rows of 128 B
+        for (int id = tid; id < n * per_node; id += ES_THREADS) {
+            const int node = id / per_node, r = id - node * per_node, row = r >> 3, c16 = r & 7;
+            const float* src = row < 3 ? x : mu_in;
+            const size_t goff = ((size_t)(node0 + node) * 3 * F + (row % 3) * F + slice * SL) * 4 + c16 * 16;
+            cp16(tab_s + node * NODE_BYTES + row * 128 + c16 * 16, reinterpret_cast<const uint8_t*>(src) + goff);
         }
         for (int id = tid; id <= n; id += ES_THREADS) rowp[id] = __ldg(row_ptr + node0 + id);
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
@@ -202,18 +318,15 @@ __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
     tc_fence_after();
     const uint32_t tmem = S->tmem_base;
 
-    // ---- filter operand A → TMEM (lane = filter row: 0-31 dq, 32-63 dmuR, 64-95 dmumu of this slice, 96-127 zero)
+    // ---- filter operand A → TMEM (lane = filter row: 0-31 dq, 32-63 dmuR, 64-95 dmumu, 96-127 dmumu again)
     if (warp < 4) {
         const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + TM_A;
-        const float4* wrow = reinterpret_cast<const float4*>(Wsl + ((size_t)slice * 96 + warp * 32 + lane) * A_ROW);
+        const float4* wrow = reinterpret_cast<const float4*>(Wsl + ((size_t)slice * 128 + warp * 32 + lane) * A_ROW);
 #pragma unroll
         for (int c8 = 0; c8 < A_ROW / 8; ++c8) {
-            uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (warp < 3) {
-                const float4 f0 = __ldg(wrow + 2 * c8), f1 = __ldg(wrow + 2 * c8 + 1);
-                v[0] = __float_as_uint(f0.x); v[1] = __float_as_uint(f0.y); v[2] = __float_as_uint(f0.z); v[3] = __float_as_uint(f0.w);
-                v[4] = __float_as_uint(f1.x); v[5] = __float_as_uint(f1.y); v[6] = __float_as_uint(f1.z); v[7] = __float_as_uint(f1.w);
-            }
+            const float4 f0 = __ldg(wrow + 2 * c8), f1 = __ldg(wrow + 2 * c8 + 1);
+            const uint32_t v[8] = {__float_as_uint(f0.x), __float_as_uint(f0.y), __float_as_uint(f0.z), __float_as_uint(f0.w),
+                                   __float_as_uint(f1.x), __float_as_uint(f1.y), __float_as_uint(f1.z), __float_as_uint(f1.w)};
             tmem_st8(ta + c8 * 8, v);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -222,34 +335,60 @@ __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
     __syncthreads();
     tc_fence_after();
 
-    const int pipe = warp >> 2, role = warp & 3;                    // role 0 q, 1 R, 2 m, 3 producer (= TMEM lane quarter)
+    const bool is_prod = warp >= NPIPE * 4;
+    const int pipe = is_prod ? warp - NPIPE * 4 : warp >> 2;
+    const int role = warp & 3;                                      // consumers: TMEM lane quarter
     const int ra = (pipe * n) / NPIPE, rb = ((pipe + 1) * n) / NPIPE;   // local receiver range of this pipeline
-    const int e_begin = rowp[ra], e_end = rowp[rb];
-    const int n_tiles = (e_end - e_begin + NE - 1) / NE;
+    int n_groups = 0;
+    for (int i = ra; i < rb; ++i) n_groups += (rowp[i + 1] - rowp[i] + GS - 1) / GS;
+    const int n_tiles = (n_groups + 3) / 4;
     uint8_t* Bt = smem + L.b + pipe * B_TILE;
     uint8_t* MetaP = smem + L.meta + pipe * 2 * META;
     float* Ex = reinterpret_cast<float*>(smem + L.exch) + pipe * 2 * 3 * SL;
 
-    if (role == 3) {
-        // ======================= producer + MMA issuer: lane = edge of the tile =======================
+    if (is_prod) {
+        // ======================= producer + MMA issuer: lane = slot (group lane/8, position lane%8) =======================
         const uint32_t b_hi = smem_u32(Bt), b_lo = b_hi + B_HALF;
+        uint64_t dbh[KP / 8], dbl[KP / 8];                              // B is single-buffered: descriptors are loop-invariant
+#pragma unroll
+        for (int ks = 0; ks < KP / 8; ++ks) {
+            dbh[ks] = umma_desc(b_hi + ks * 1024, 512, 128);
+            dbl[ks] = umma_desc(b_lo + ks * 1024, 512, 128);
+        }
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int my_g = lane >> 3, my_u = lane & 7;
+        int cur_i = ra, cur_e = rowp[ra];                               // group scheduler state (warp-uniform)
         float4 nx[7];
         bool nvalid = false;
-        auto fetch = [&](int t) {
-            const int eid = e_begin + t * NE + lane;
-            nvalid = t < n_tiles && eid < e_end;
+        int nrecv = rb - 1;
+        auto fetch = [&]() {                                            // schedule the next tile's 4 groups, load my record
+            int eid = -1;
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg) {
+                while (cur_i < rb && cur_e >= rowp[cur_i + 1]) { ++cur_i; if (cur_i < rb) cur_e = rowp[cur_i]; }
+                if (gg == my_g) {
+                    if (cur_i < rb) {
+                        nrecv = cur_i;
+                        eid = cur_e + my_u < rowp[cur_i + 1] ? cur_e + my_u : -1;
+                    } else {
+                        nrecv = rb - 1;                                 // padding group: zero filters, harmless receiver
+                    }
+                }
+                if (cur_i < rb) cur_e += GS;
+            }
+            nvalid = eid >= 0;
             if (nvalid) {
                 const float4* r = rec + 8 * (int64_t)eid;
 #pragma unroll
                 for (int c = 0; c < 7; ++c) nx[c] = __ldg(r + c);
             }
         };
-        fetch(0);
+        fetch();
         for (int t = 0; t < n_tiles; ++t) {
             const int buf = t & 1;
             float4 v[6];
-            int j = 0, recv = rb - 1;                                    // padding edge: zero filters, harmless receiver
+            int joff = 0;
+            const int recv = nrecv;
             float4 dir4 = zero4;
 #pragma unroll
             for (int c = 0; c < 6; ++c) v[c] = zero4;
@@ -258,17 +397,23 @@ __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
                 for (int c = 0; c < 5; ++c) v[c] = nx[c];
                 v[5] = make_float4(nx[5].x, 0.f, 0.f, 0.f);              // k = 20: fcut (bias column); 21..23 zero
                 dir4 = make_float4(nx[5].y, nx[5].z, nx[5].w, 0.f);
-                j = __float_as_int(nx[6].x);
-                recv = __float_as_int(nx[6].y);
+                joff = __float_as_int(nx[6].x) * NODE_BYTES;
             }
-            fetch(t + 1);                                                // prefetch: hidden behind this tile's work
+            if (t + 1 < n_tiles) fetch();                                // prefetch: hidden behind this tile's work
+#ifdef RLVD_TIMELINE
+            const bool DBG = dbg != nullptr && blockIdx.x == 0 && pipe == 0 && lane == 0 && t < 48;
+            if (DBG) dbg[(t * 5) * 4 + 0] = clock64();
+#endif
             mbar_wait(&S->acc_free[pipe][buf], ((t >> 1) & 1) ^ 1);     // consumers released this buffer's meta + TMEM
             if (t > 0) mbar_wait(&S->mma_done[pipe][buf ^ 1], ((t - 1) >> 1) & 1);   // previous tile's MMAs read B
+#ifdef RLVD_TIMELINE
+            if (DBG) dbg[(t * 5) * 4 + 1] = clock64();
+#endif
             {
                 uint8_t* meta = MetaP + buf * META;
-                reinterpret_cast<int*>(meta)[lane] = j;
-                reinterpret_cast<int*>(meta + 128)[lane] = recv;
-                reinterpret_cast<float4*>(meta + 256)[lane] = dir4;
+                reinterpret_cast<int*>(meta)[lane] = joff;
+                reinterpret_cast<float4*>(meta + 128)[lane] = dir4;
+                if (my_u == 0) reinterpret_cast<int*>(meta + 640)[my_g] = recv;
                 const uint32_t roff = (lane >> 3) * 128 + (lane & 7) * 16;
 #pragma unroll
                 for (int kc = 0; kc < 6; ++kc) {
@@ -287,94 +432,30 @@ __global__ void __launch_bounds__(ES_THREADS, 1) tc_edge_small_kernel(
                 const uint32_t a_hi = tmem + TM_A, a_lo = a_hi + KP;
 #pragma unroll
                 for (int ks = 0; ks < KP / 8; ++ks) {
-                    const uint64_t dbh = umma_desc(b_hi + ks * 1024, 512, 128), dbl = umma_desc(b_lo + ks * 1024, 512, 128);
-                    umma_tf32_ts(d, a_hi + ks * 8, dbh, ks == 0 ? 0u : 1u);
-                    umma_tf32_ts(d, a_hi + ks * 8, dbl, 1u);
-                    umma_tf32_ts(d, a_lo + ks * 8, dbh, 1u);
+                    umma_tf32_ts(d, a_hi + ks * 8, dbh[ks], ks == 0 ? 0u : 1u);
+                    umma_tf32_ts(d, a_hi + ks * 8, dbl[ks], 1u);
+                    umma_tf32_ts(d, a_lo + ks * 8, dbh[ks], 1u);
                 }
                 umma_commit(&S->mma_done[pipe][buf]);
+#ifdef RLVD_TIMELINE
+                if (DBG) dbg[(t * 5) * 4 + 2] = clock64();
+#endif
             }
             __syncwarp();
         }
-    } else if (role < (HAS_MU ? 3 : 2)) {
-        // ======================= consumers: lane = channel of the slice, role = message part =======================
-        const uint32_t taddr0 = tmem + ((uint32_t)(role * 32) << 16) + TM_D + (uint32_t)(pipe * 2) * NE;
+    } else if (role < NCONS) {
+        // ======================= consumers: lane = channel of the slice, role = share of the message =======================
+        // table row of sender j at Tab + j*768: x_q +0, x_R +128, x_m +256, mu_x +384, mu_y +512, mu_z +640
+        const uint8_t* tb = Tab + lane * 4;
         const int ch = slice * SL + lane;
-        int i_cur = ra, n_flush = 0;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;                            // q-warp: a0 = dq;  R/m-warp: a0..a2 = dmu partials
-        auto flush_to = [&](int next) {
-            for (int i = i_cur; i < next; ++i, ++n_flush) {
-                const int64_t gi = node0 + i;
-                if (role == 0) {
-                    q[gi * F + ch] += a0;
-                } else if (!HAS_MU) {
-                    mu_out[gi * 3 * F + ch] = a0;
-                    mu_out[gi * 3 * F + F + ch] = a1;
-                    mu_out[gi * 3 * F + 2 * F + ch] = a2;
-                } else {
-                    float* ex = Ex + (n_flush & 1) * 3 * SL;
-                    if (role == 2) {
-                        ex[lane] = a0; ex[SL + lane] = a1; ex[2 * SL + lane] = a2;
-                    }
-                    pair_barrier(pipe);
-                    if (role == 1) {
-                        const float* mi = Mt + i * 3 * SL;
-                        mu_out[gi * 3 * F + ch] = mi[lane] + a0 + ex[lane];
-                        mu_out[gi * 3 * F + F + ch] = mi[SL + lane] + a1 + ex[SL + lane];
-                        mu_out[gi * 3 * F + 2 * F + ch] = mi[2 * SL + lane] + a2 + ex[2 * SL + lane];
-                    }
-                }
-                a0 = a1 = a2 = 0.f;
-            }
-            i_cur = next;
-        };
-        for (int t = 0; t < n_tiles; ++t) {
-            const int buf = t & 1;
-            mbar_wait(&S->mma_done[pipe][buf], (t >> 1) & 1);
-            tc_fence_after();
-            const uint8_t* meta = MetaP + buf * META;
-#pragma unroll 1
-            for (int hh = 0; hh < NE / 8; ++hh) {                        // groups of 8 edges: all gathers before the FMAs
-                uint32_t w[8];
-                tmem_ld8s(taddr0 + buf * NE + hh * 8, w);
-                int jj[8], rr[8];
-#pragma unroll
-                for (int v4 = 0; v4 < 2; ++v4) {
-                    const int4 j4 = *reinterpret_cast<const int4*>(meta + (hh * 8 + v4 * 4) * 4);
-                    const int4 r4 = *reinterpret_cast<const int4*>(meta + 128 + (hh * 8 + v4 * 4) * 4);
-                    jj[4 * v4] = j4.x; jj[4 * v4 + 1] = j4.y; jj[4 * v4 + 2] = j4.z; jj[4 * v4 + 3] = j4.w;
-                    rr[4 * v4] = r4.x; rr[4 * v4 + 1] = r4.y; rr[4 * v4 + 2] = r4.z; rr[4 * v4 + 3] = r4.w;
-                }
-                float xv[8], g0[8], g1[8], g2[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    xv[u] = Xt[jj[u] * 3 * SL + role * SL + lane];
-                    if (role == 1) {
-                        const float4 dir = *reinterpret_cast<const float4*>(meta + 256 + (hh * 8 + u) * 16);
-                        g0[u] = dir.x; g1[u] = dir.y; g2[u] = dir.z;
-                    } else if (role == 2) {
-                        const float* mj = Mt + jj[u] * 3 * SL + lane;
-                        g0[u] = mj[0]; g1[u] = mj[SL]; g2[u] = mj[2 * SL];
-                    }
-                }
-                tmem_wait_ld();
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (rr[u] != i_cur) flush_to(rr[u]);
-                    const float sx = __uint_as_float(w[u]) * xv[u];
-                    if (role == 0) {
-                        a0 += sx;
-                    } else {
-                        a0 = fmaf(sx, g0[u], a0);
-                        a1 = fmaf(sx, g1[u], a1);
-                        a2 = fmaf(sx, g2[u], a2);
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&S->acc_free[pipe][buf]);
-        }
-        flush_to(rb);
+        if (role == 0)
+            consume_tiles<HAS_MU, 0>(S, pipe, n_tiles, tmem, MetaP, tb, Ex, ra, rb, node0, ch, lane, q, mu_out, dbg);
+        else if (role == 1)
+            consume_tiles<HAS_MU, 1>(S, pipe, n_tiles, tmem, MetaP, tb, Ex, ra, rb, node0, ch, lane, q, mu_out, dbg);
+        else if (role == 2)
+            consume_tiles<HAS_MU, 2>(S, pipe, n_tiles, tmem, MetaP, tb, Ex, ra, rb, node0, ch, lane, q, mu_out, dbg);
+        else
+            consume_tiles<HAS_MU, 3>(S, pipe, n_tiles, tmem, MetaP, tb, Ex, ra, rb, node0, ch, lane, q, mu_out, dbg);
     }
     tc_fence_before();
     __syncthreads();
@@ -394,22 +475,23 @@ uint32_t tf32_round_host2(float w) {
 
 }  // namespace
 
-// Host: per layer, per 32-channel slice: rows r = part*32 + ch (96 rows) of [hi[24] | lo[24]] tf32-split floats;
-// k < 20 filter_net weights, k = 20 bias (multiplied by the fcut column of the edge operand), 21..23 zero.
+// Host: per layer, per 32-channel slice: 128 rows (quarters: dq, dmuR, dmumu, dmumu again) of [hi[24] | lo[24]]
+// tf32-split floats; k < 20 filter_net weights, k = 20 bias (meets the fcut column of the edge operand), 21..23 zero.
 void tc_edge_small_format(const float* W, const float* b, std::vector<uint8_t>& out) {
     out.assign((size_t)NLAYER * NSLICE * A_SLICE, 0);
     float* o = reinterpret_cast<float*>(out.data());
     for (int l = 0; l < NLAYER; ++l)
         for (int sl = 0; sl < NSLICE; ++sl)
-            for (int part = 0; part < 3; ++part)
+            for (int quarter = 0; quarter < 4; ++quarter)
                 for (int chn = 0; chn < SL; ++chn)
                     for (int k = 0; k <= NRBF; ++k) {
+                        const int part = quarter < 3 ? quarter : 2;
                         const int row = l * 3 * F + part * F + sl * SL + chn;
                         const float w = k < NRBF ? W[(size_t)row * NRBF + k] : b[row];
                         const uint32_t hu = tf32_round_host2(w);
                         float hf;
                         memcpy(&hf, &hu, 4);
-                        const size_t base = (((size_t)l * NSLICE + sl) * 96 + part * SL + chn) * A_ROW;
+                        const size_t base = (((size_t)l * NSLICE + sl) * 128 + quarter * SL + chn) * A_ROW;
                         o[base + k] = hf;
                         o[base + KP + k] = w - hf;
                     }
@@ -443,13 +525,35 @@ int launch_tc_edge_small(rlvd_engine* e, cudaStream_t s, int layer, int n_struct
         attr_set = true;
     }
     const float* wf = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(e->w.filt_S) + (size_t)layer * NSLICE * A_SLICE);
+    long long* dbg = nullptr;
+#ifdef RLVD_TIMELINE   // in-kernel timeline of block 0 / pipeline 0 (build with RLVD_EXTRA_NVCC_FLAGS=-DRLVD_TIMELINE)
+    static long long* dbg_buf = nullptr;
+    static int dbg_calls = 0;
+    if (dbg_buf == nullptr) { cudaMalloc(&dbg_buf, 48 * 5 * 4 * 8); cudaMemset(dbg_buf, 0, 48 * 5 * 4 * 8); }
+    dbg = dbg_buf;
+#endif
     Span sp(e, s, FAM_EDGE);
     if (mu_in == nullptr)
         tc_edge_small_kernel<false><<<n_struct * NSLICE, ES_THREADS, L.total, s>>>(
-            n_struct, max_struct_nodes, node_ptr, wf, row_ptr, e->geom.as<float4>(), x, nullptr, q, mu_out);
+            n_struct, max_struct_nodes, node_ptr, wf, row_ptr, e->geom.as<float4>(), x, nullptr, q, mu_out, nullptr);
     else
         tc_edge_small_kernel<true><<<n_struct * NSLICE, ES_THREADS, L.total, s>>>(
-            n_struct, max_struct_nodes, node_ptr, wf, row_ptr, e->geom.as<float4>(), x, mu_in, q, mu_out);
+            n_struct, max_struct_nodes, node_ptr, wf, row_ptr, e->geom.as<float4>(), x, mu_in, q, mu_out, dbg);
+#ifdef RLVD_TIMELINE
+    if (++dbg_calls == 20) {
+        cudaStreamSynchronize(s);
+        static long long h[48 * 5 * 4];
+        cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        const long long t0 = h[0];
+        for (int t = 0; t < 40; ++t) {
+            printf("tile %2d  P: ready %7lld waited %5lld issue %5lld |", t, h[t * 20] - t0, h[t * 20 + 1] - h[t * 20], h[t * 20 + 2] - h[t * 20 + 1]);
+            for (int r = 0; r < 4; ++r)
+                printf(" C%d: at %7lld wait %5lld work %5lld |", r, h[t * 20 + (r + 1) * 4] - t0, h[t * 20 + (r + 1) * 4 + 1] - h[t * 20 + (r + 1) * 4],
+                       h[t * 20 + (r + 1) * 4 + 2] - h[t * 20 + (r + 1) * 4 + 1]);
+            printf("\n");
+        }
+    }
+#endif
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;
