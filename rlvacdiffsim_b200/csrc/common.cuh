@@ -63,6 +63,8 @@ struct Weights {
     const float* filt_T = nullptr;              // [L][21][384]  (k<20: weight^T, k=20: bias)
     const void* filt_F = nullptr;               // [L][3 parts][hi|lo] tf32 tensor-core operand (tc_edge.cu)
     const void* filt_S = nullptr;               // [L][4 slices][hi|lo] tf32 operand of the sliced kernel (tc_edge_small.cu)
+    const void* filt_E = nullptr;               // [L][4 slices][2 sets][128][32] fp16-split TMEM image (edge_stream.cu)
+    float filt_kappa[NLAYER] = {};              // 2^-(sA+10): undoes the fp16 range scaling of filt_E and the edge tiles
     const float* feps = nullptr;                // [20] freqs[k] - (k+1)*freqs[0]
     const float* inter_w0T[NLAYER] = {};        // [128][128]   (in-major: Wt[k][n])
     const float* inter_b0[NLAYER] = {};
@@ -110,12 +112,14 @@ struct rlvd_engine {
     bool finalized = false;
     // workspaces (grown on demand, never shrunk)
     rlvd::DevBuf x, mu0, mu1, hid, mix, nrm, vw, ctx, struct_edges, struct_edge_ptr, scratch, geom;
+    rlvd::DevBuf tiles, pipe_info, tile_ctr;       // edge stream (edge_stream.cu)
     // host-path staging
     rlvd::DevBuf in_node_ptr, in_Z, in_pos, in_cell, in_inv, in_img, in_rs, in_ps, in_temp, in_qp;
     rlvd::DevBuf g_row_ptr, g_node_struct, g_col, g_shift, g_nedges, g_q, out_pack;
     int64_t launches = 0;
     bool use_tensor_cores = true;
-    bool use_sliced_edge = true;    // structure-resident sliced edge kernel when every structure has <= 256 atoms
+    bool use_sliced_edge = true;    // structure-resident edge kernels when every structure has <= 256 atoms
+    int sliced_impl = 1;            // 1 = edge stream (edge_stream.cu), 0 = first sliced kernel (tc_edge_small.cu)
     bool profiling = false;
     std::vector<rlvd::ProfSpan> spans;
     std::vector<cudaEvent_t> event_pool;
@@ -164,7 +168,7 @@ void tc_format_weight(const float* W, int N, int K, std::vector<uint8_t>& out);
 int launch_embed(rlvd_engine* e, cudaStream_t s, int M, const int* Z, float* q);
 struct EdgeArgs {
     int layer = 0, M = 0, n_struct = 0, max_struct_nodes = 0;
-    bool sliced = false;            // geometry records are ready (launch_edge_geometry ran)
+    int sliced = 0;                 // 0 general; 1 geometry records ready (tc_edge_small); 2 edge tiles ready (edge_stream)
     const int* node_ptr = nullptr;
     const int* row_ptr = nullptr;
     const int* col = nullptr;
@@ -186,6 +190,12 @@ int launch_tc_edge_small(rlvd_engine* e, cudaStream_t s, int layer, int n_struct
                          const int* node_ptr, const int* row_ptr, const float* x, const float* mu_in, float* q,
                          float* mu_out);
 void tc_edge_small_format(const float* W, const float* b, std::vector<uint8_t>& out);
+bool edge_stream_supported(int max_struct_nodes);
+void edge_stream_format(const float* W, const float* b, std::vector<uint8_t>& out, float* kappa);
+int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_t n_edges, const int* node_ptr,
+                     const int* row_ptr, const int* col, const int8_t* shift, const float* pos, const float* cell);
+int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, int max_struct_nodes, const int* node_ptr,
+                       const float* x, const float* mu_in, float* q, float* mu_out);
 int launch_tc_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* row_ptr, const int* col,
                    const int8_t* shift, const float* pos, const float* cell, const int* node_struct,
                    const float* x, const float* mu_in, float* q, float* mu_out);

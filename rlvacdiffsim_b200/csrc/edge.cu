@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(EDGE_THREADS) edge_kernel(
 int launch_edge(rlvd_engine* e, cudaStream_t s, const EdgeArgs& a) {
     const int M = a.M;
     if (M <= 0) return 0;
-    if (a.sliced)
+    if (a.sliced == 2)
+        return launch_edge_stream(e, s, a.layer, a.n_struct, a.max_struct_nodes, a.node_ptr, a.x, a.mu_in, a.q, a.mu_out);
+    if (a.sliced == 1)
         return launch_tc_edge_small(e, s, a.layer, a.n_struct, a.max_struct_nodes, a.node_ptr, a.row_ptr, a.x, a.mu_in,
                                     a.q, a.mu_out);
     if (e->use_tensor_cores)

@@ -1,0 +1,626 @@
+// K2 + K3a + K3c + K4 fused for structures of at most 256 atoms — the BASELINE workload (255/256-atom replicas).
+// "Edge stream" design: the per-edge embedding is packed ONCE per representation call into tensor-core-ready tiles
+// that the three layers x four channel slices then only stream.
+//
+// Replaces, inside rgnn's PaiNN (reached from rlsim/drl/simulator.py:56): the Bessel / cosine-cutoff / unit-vector
+// embedding, `filter_net` (nn.Linear 20 -> 1152, materialised as [E,1152] by the eager path), the index_select
+// gathers of x[j] / mu[j] and torch_scatter.scatter_add (SURVEY.md §8a R2, R3, R5 edge part, K4).
+//
+// edge_pack_kernel (once per call, one CTA per structure)
+//   Splits the structure's receivers into NPIPE contiguous ranges of equal edge-group count and writes, per range,
+//   a stream of 32-slot tiles.  Slots come in receiver-aligned groups of 8 (short rows padded with zero filters).
+//   A tile is 4096 B of MMA operand + 576 B of meta:
+//     operand  [32 slots][64 fp16], K-major core-matrix layout:  b_hi[21] | b_lo[21] | b_hi[21] | 0
+//              b = 2^10 * {phi_k(d) * fcut(d) (k < 20), fcut(d)}, split b = b_hi + b_lo in fp16 (22 significant bits)
+//     meta     j[32] (local sender index) | dir_x[32] | dir_y[32] | dir_z[32] | receiver[4] (one per group)
+//
+// edge_stream_kernel (per layer; CTA = one structure x one 32-channel slice; 1 CTA per SM)
+//   The slice of the structure's node table lives in shared memory (gathers never leave the SM):
+//     row(j) = kappa*x_q | kappa*x_R | kappa*x_m*mu_x | kappa*x_m*mu_y | kappa*x_m*mu_z        (5 x 32 fp32)
+//   Filters run on tcgen05 with the weight operand resident in TMEM (A1 rows = dq | dmuR | dmuR | dmuR filters of the
+//   slice, A2 rows = 0 | dmumu | dmumu | dmumu), pre-split on the host as a_hi[21] | a_hi[21] | a_lo[21] | 0 so that
+//   ONE K=64 fp16 MMA chain evaluates  a_hi.b_hi + a_hi.b_lo + a_lo.b_hi  (fp32-accurate, 4 dispatches):
+//        D1[128, 32 slots] = A1 . Bt      D2[128, 32 slots] = A2 . Bt
+//   A TMEM lane quarter can only be read by the warps with warp%4 == quarter, which fixes the roles:
+//        warp 0 (q)   : dq    += D1 * x_q[j]                         (+ issues the tile's bulk copies and MMAs)
+//        warp a=1..3  : dmu_a += D1 * x_R[j] * dir_a + D2 * (x_m mu_a)[j]
+//   so every warp owns its output rows outright: no exchange between warps, no atomics, sums in CSR order
+//   (bitwise reproducible).  NPIPE such 4-warp pipelines run on disjoint receiver ranges; while one waits for its
+//   next tile's MMAs the others fill the issue slots.  kappa = 2^-(sA+10) undoes the fp16 range scaling exactly.
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace rlvd {
+
+namespace {
+
+constexpr int SL = 32;                    // channels per slice
+constexpr int NSLICE = F / SL;            // 4
+constexpr int NPIPE = 6;                  // 4-warp pipelines per CTA
+constexpr int TE = 32;                    // slots per tile = MMA N
+constexpr int GS = 8;                     // slots per receiver-aligned group
+constexpr int KH = 64;                    // fp16 k-extent of the split operands
+constexpr int NK = NRBF + 1;              // 21: 20 Bessel functions + the bias column (fcut)
+constexpr int TILE_B = TE * KH * 2;       // 4096
+constexpr int META = 576;                 // j[32] | dir[3][32] | recv[4] | pad
+constexpr int TILE_BYTES = TILE_B + META; // 4672
+constexpr int MAXN = 256;
+constexpr int ST_THREADS = NPIPE * 128;
+constexpr int B_SCALE_LOG2 = 10;
+constexpr int TM_D = 0;                   // TMEM columns: D1/D2 of pipe p at p*64 / p*64+32
+constexpr int TM_A = NPIPE * 64;          // A1 at TM_A, A2 at TM_A+32 (64 fp16 = 32 columns each)
+constexpr int TM_COLS = 512;
+constexpr int A_SET_WORDS = 128 * 32;     // u32 per (slice, set)
+constexpr float PI_F = 3.14159265358979323846f;
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TE >> 3) << 17) | (8u << 24);   // f16 x f16 -> f32, M=128, N=32
+
+static_assert(TM_A + 64 <= TM_COLS, "TMEM budget");
+
+struct StBars {
+    uint64_t b_full[NPIPE], mma_done[NPIPE], acc_free[NPIPE];
+    uint32_t tmem_base;
+};
+
+__device__ __noinline__ void st_timeout() {
+    printf("rlvd: edge_stream mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    __trap();
+}
+__device__ __forceinline__ void st_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+#pragma unroll 1
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > 400000u) st_timeout();
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// edge_pack_kernel
+// ------------------------------------------------------------------------------------------------------------------
+
+// 21 embedding values of one edge: phi_k(d)*fcut(d) (k < 20) and fcut(d).  sin(freqs[k] d): one accurate sincos of
+// theta = freqs[0]*d (fp32 product error folded in), an angle-addition tree of depth <= 5 for k*theta, and the deviation
+// freqs[k] - (k+1)*freqs[0] folded in to first order (max abs error 1.4e-6, below the 1.9e-6 argument-rounding error of
+// evaluating sin(fl(freqs[k]*d)) directly in fp32).
+__device__ __forceinline__ void edge_embedding(float d, float f1, const float* __restrict__ feps, float cutoff, float* v /*21*/) {
+    const float inv_d = 1.0f / d;
+    const float fc = d < cutoff ? 0.5f * (cosf(d * (PI_F / cutoff)) + 1.0f) : 0.f;
+    const float scale = inv_d * fc;
+    const float pr = f1 * d, perr = fmaf(f1, d, -pr);
+    float sn, cs;
+    sincosf(pr, &sn, &cs);
+    float s[NRBF + 1], c[NRBF + 1];
+    s[1] = fmaf(perr, cs, sn);
+    c[1] = fmaf(-perr, sn, cs);
+#define RLVD_ADD(a, b) { s[(a) + (b)] = fmaf(s[a], c[b], c[a] * s[b]); c[(a) + (b)] = fmaf(c[a], c[b], -(s[a] * s[b])); }
+    RLVD_ADD(1, 1) RLVD_ADD(2, 1) RLVD_ADD(2, 2) RLVD_ADD(4, 1) RLVD_ADD(4, 2) RLVD_ADD(4, 3) RLVD_ADD(4, 4)
+    RLVD_ADD(8, 1) RLVD_ADD(8, 2) RLVD_ADD(8, 3) RLVD_ADD(8, 4) RLVD_ADD(8, 5) RLVD_ADD(8, 6) RLVD_ADD(8, 7)
+    RLVD_ADD(8, 8) RLVD_ADD(16, 1) RLVD_ADD(16, 2) RLVD_ADD(16, 3) RLVD_ADD(16, 4)
+#undef RLVD_ADD
+#pragma unroll
+    for (int k = 0; k < NRBF; ++k) v[k] = fmaf(__ldg(feps + k) * d, c[k + 1], s[k + 1]) * scale;
+    v[NRBF] = fc;
+}
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+// Writes slot `r` of the tile at `tile`: operand row (8 x 16 B, one per core column) and meta.
+__device__ __forceinline__ void write_slot(uint8_t* tile, int r, const uint4* row8, int j, float dx, float dy, float dz) {
+    uint8_t* b = tile + (r >> 3) * 128 + (r & 7) * 16;
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(b + kc * 512) = row8[kc];
+    uint8_t* m = tile + TILE_B;
+    reinterpret_cast<int*>(m)[r] = j;
+    reinterpret_cast<float*>(m + 128)[r] = dx;
+    reinterpret_cast<float*>(m + 256)[r] = dy;
+    reinterpret_cast<float*>(m + 384)[r] = dz;
+}
+
+__global__ void __launch_bounds__(256) edge_pack_kernel(int n_struct, const int* __restrict__ node_ptr,
+                                                        const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                                        const int8_t* __restrict__ shift, const float* __restrict__ pos,
+                                                        const float* __restrict__ cell, const float* __restrict__ freqs,
+                                                        const float* __restrict__ feps, float cutoff,
+                                                        int* __restrict__ tile_counter, int tile_capacity,
+                                                        uint8_t* __restrict__ tiles, int4* __restrict__ pipe_info,
+                                                        int* __restrict__ err_flag) {
+    __shared__ int goff[MAXN + 1];        // exclusive prefix of per-receiver group counts
+    __shared__ int wsum[8];
+    __shared__ int bnd[NPIPE + 1];        // receiver range boundaries of the pipelines
+    __shared__ int tbeg[NPIPE + 1];       // first tile of each pipeline (absolute)
+    const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int node0 = __ldg(node_ptr + g), n = __ldg(node_ptr + g + 1) - node0;
+    if (n <= 0) {
+        if (tid < NPIPE) pipe_info[g * NPIPE + tid] = make_int4(0, 0, 0, 0);
+        return;
+    }
+    // ---- group counts and their block-wide exclusive scan
+    int e0 = 0, deg = 0;
+    if (tid < n) {
+        e0 = __ldg(row_ptr + node0 + tid);
+        deg = __ldg(row_ptr + node0 + tid + 1) - e0;
+    }
+    const int gc = (deg + GS - 1) / GS;
+    int incl = gc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += wsum[w];
+    goff[tid] = wbase + incl - gc;
+    if (tid == 255) goff[256] = wbase + incl;
+    __syncthreads();
+    const int G = goff[256];   // threads >= n contributed 0, so goff[i] == G for i >= n
+    // ---- receiver ranges with (nearly) equal group counts; tile allocation
+    if (tid <= NPIPE) {
+        int b;
+        if (tid == 0) b = 0;
+        else if (tid == NPIPE) b = n;
+        else {
+            const int target = (int)(((long long)tid * G) / NPIPE);
+            int lo = 0, hi = n;                       // smallest i in [0, n] with goff[i] >= target
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (goff[mid] >= target) hi = mid; else lo = mid + 1;
+            }
+            b = lo;
+        }
+        bnd[tid] = b;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int total = 0;
+        int tl[NPIPE];
+        for (int p = 0; p < NPIPE; ++p) {
+            tl[p] = (goff[bnd[p + 1]] - goff[bnd[p]] + 3) >> 2;
+            total += tl[p];
+        }
+        int base = atomicAdd(tile_counter, total);
+        bool ok = base + total <= tile_capacity;
+        if (!ok) atomicExch(err_flag, 1);
+        for (int p = 0; p < NPIPE; ++p) {
+            tbeg[p] = base;
+            pipe_info[g * NPIPE + p] = make_int4(base, ok ? tl[p] : 0, bnd[p], bnd[p + 1]);
+            base += tl[p];
+        }
+        tbeg[NPIPE] = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (tbeg[NPIPE] == 0) return;
+
+    float C[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) C[t] = __ldg(cell + 9 * g + t);
+    const float f1 = __ldg(freqs);
+    const float bscale = (float)(1 << B_SCALE_LOG2);
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+
+    // ---- one warp per receiver row, lanes over its slots
+    for (int i = warp; i < n; i += 8) {
+        int p = 0;
+        while (i >= bnd[p + 1]) ++p;
+        const int gi = node0 + i;
+        const int re0 = __ldg(row_ptr + gi), rdeg = __ldg(row_ptr + gi + 1) - re0;
+        const int nslots = ((rdeg + GS - 1) / GS) * GS;
+        const int slot0 = (goff[i] - goff[bnd[p]]) * GS;
+        const float xi = __ldg(pos + 3 * (int64_t)gi), yi = __ldg(pos + 3 * (int64_t)gi + 1), zi = __ldg(pos + 3 * (int64_t)gi + 2);
+        for (int s = lane; s < nslots; s += 32) {
+            const int slot = slot0 + s;
+            uint8_t* tile = tiles + (size_t)(tbeg[p] + (slot >> 5)) * TILE_BYTES;
+            const int r = slot & 31;
+            if ((s & (GS - 1)) == 0) reinterpret_cast<int*>(tile + TILE_B + 512)[r >> 3] = i;
+            if (s < rdeg) {
+                const int e = re0 + s;
+                const int jg = __ldg(col + e);
+                const float S0 = (float)shift[3 * (int64_t)e], S1 = (float)shift[3 * (int64_t)e + 1], S2 = (float)shift[3 * (int64_t)e + 2];
+                float rx = __ldg(pos + 3 * (int64_t)jg) - xi, ry = __ldg(pos + 3 * (int64_t)jg + 1) - yi,
+                      rz = __ldg(pos + 3 * (int64_t)jg + 2) - zi;
+                rx += S0 * C[0] + S1 * C[3] + S2 * C[6];
+                ry += S0 * C[1] + S1 * C[4] + S2 * C[7];
+                rz += S0 * C[2] + S1 * C[5] + S2 * C[8];
+                const float d = sqrtf(rx * rx + ry * ry + rz * rz);
+                const float inv_d = 1.0f / d;
+                float v[NK];
+                edge_embedding(d, f1, feps, cutoff, v);
+                __half hi[NK + 1], lo[NK + 1];
+#pragma unroll
+                for (int k = 0; k < NK; ++k) {
+                    const float sv = v[k] * bscale;
+                    hi[k] = __float2half_rn(sv);
+                    lo[k] = __float2half_rn(sv - __half2float(hi[k]));
+                }
+                // k' = 0..20 hi | 21..41 lo | 42..62 hi | 63 zero
+                __half kk[KH];
+#pragma unroll
+                for (int k = 0; k < NK; ++k) { kk[k] = hi[k]; kk[NK + k] = lo[k]; kk[2 * NK + k] = hi[k]; }
+                kk[KH - 1] = __float2half_rn(0.f);
+                uint4 row8[8];
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc)
+                    row8[kc] = make_uint4(pack_h2(kk[8 * kc], kk[8 * kc + 1]), pack_h2(kk[8 * kc + 2], kk[8 * kc + 3]),
+                                          pack_h2(kk[8 * kc + 4], kk[8 * kc + 5]), pack_h2(kk[8 * kc + 6], kk[8 * kc + 7]));
+                write_slot(tile, r, row8, jg - node0, rx * inv_d, ry * inv_d, rz * inv_d);
+            } else {
+                uint4 row8[8];
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc) row8[kc] = z4;
+                write_slot(tile, r, row8, 0, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    // ---- padding groups that complete each pipeline's last tile (zero filters, harmless receiver)
+    if (tid < NPIPE * 24) {
+        const int p = tid / 24, k = tid - p * 24;
+        const int groups = goff[bnd[p + 1]] - goff[bnd[p]];
+        const int ntile = (groups + 3) >> 2;
+        const int slot = groups * GS + k;
+        if (slot < ntile * TE) {
+            uint8_t* tile = tiles + (size_t)(tbeg[p] + (slot >> 5)) * TILE_BYTES;
+            const int r = slot & 31;
+            uint4 row8[8];
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) row8[kc] = z4;
+            write_slot(tile, r, row8, 0, 0.f, 0.f, 0.f);
+            if ((r & (GS - 1)) == 0) reinterpret_cast<int*>(tile + TILE_B + 512)[r >> 3] = bnd[p + 1] - 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// edge_stream_kernel
+// ------------------------------------------------------------------------------------------------------------------
+
+template <bool HAS_MU>
+struct Tab {
+    static constexpr int NODE_BYTES = HAS_MU ? 5 * SL * 4 : 2 * SL * 4;   // 640 / 256
+};
+
+// One warp of one pipeline.  ROLE = TMEM lane quarter: 0 -> q, a = 1..3 -> mu component a-1.
+template <bool HAS_MU, int ROLE>
+__device__ __forceinline__ void run_role(StBars* S, int pipe, int lane, uint32_t tmem, const uint8_t* tab, uint8_t* Bp,
+                                         uint8_t* MetaP, const uint8_t* __restrict__ tile_src, int n_tiles, int ra, int rb,
+                                         int node0, int ch, const float* __restrict__ base_src, float* __restrict__ out) {
+    constexpr int NB = Tab<HAS_MU>::NODE_BYTES;
+    constexpr int T1_OFF = ROLE == 0 ? 0 : SL * 4;
+    constexpr int T2_OFF = 2 * SL * 4 + (ROLE > 0 ? ROLE - 1 : 0) * SL * 4;
+    constexpr bool USE2 = HAS_MU && ROLE > 0;
+    constexpr int OUT_LD = ROLE == 0 ? F : 3 * F;
+    constexpr int OUT_OFF = ROLE == 0 ? 0 : (ROLE - 1) * F;
+    constexpr bool HAS_BASE = ROLE == 0 || HAS_MU;
+
+    const uint32_t d1 = tmem + ((uint32_t)(ROLE * 32) << 16) + TM_D + (uint32_t)pipe * 64;
+    const uint32_t d2 = d1 + 32;
+    const uint8_t* tb = tab + lane * 4;
+    const int64_t obase = (int64_t)node0 * OUT_LD + OUT_OFF + ch;
+    auto load_base = [&](int i) -> float { return HAS_BASE ? base_src[obase + (int64_t)i * OUT_LD] : 0.f; };
+
+    int cur = ra;
+    float acc0 = 0.f, acc1 = 0.f;
+    float base = ra < rb ? load_base(ra) : 0.f;
+
+    uint64_t bdesc[4];
+    if (ROLE == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bdesc[c] = umma_desc(smem_u32(Bp) + c * 1024, 512, 128);
+        if (lane == 0 && n_tiles > 0) {
+            mbar_expect_tx(&S->b_full[pipe], TILE_BYTES);
+            bulk_g2s(Bp, tile_src, TILE_B, &S->b_full[pipe]);
+            bulk_g2s(MetaP, tile_src + TILE_B, META, &S->b_full[pipe]);
+        }
+    }
+
+#pragma unroll 1
+    for (int t = 0; t < n_tiles; ++t) {
+        const uint32_t par = (uint32_t)t & 1u;
+        if (ROLE == 0) {
+            if (lane == 0) {
+                st_wait(&S->b_full[pipe], par);                     // operand + meta of tile t landed
+                if (t > 0) st_wait(&S->acc_free[pipe], par ^ 1u);   // all four roles are done with tile t-1
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) umma_f16_ts(tmem + TM_D + (uint32_t)pipe * 64, tmem + TM_A + c * 8, bdesc[c], c);
+                if (HAS_MU) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        umma_f16_ts(tmem + TM_D + (uint32_t)pipe * 64 + 32, tmem + TM_A + 32 + c * 8, bdesc[c], c);
+                }
+                umma_commit(&S->mma_done[pipe]);
+            }
+            __syncwarp();
+        }
+        st_wait(&S->mma_done[pipe], par);
+        tc_fence_after();
+        if (ROLE == 0 && lane == 0 && t + 1 < n_tiles) {            // operand buffer is free again: fetch tile t+1
+            const uint8_t* src = tile_src + (size_t)(t + 1) * TILE_BYTES;
+            mbar_expect_tx(&S->b_full[pipe], TILE_BYTES);
+            bulk_g2s(Bp, src, TILE_B, &S->b_full[pipe]);
+            bulk_g2s(MetaP + (par ^ 1u) * META, src + TILE_B, META, &S->b_full[pipe]);
+        }
+        const uint8_t* meta = MetaP + par * META;
+#pragma unroll 1
+        for (int gg = 0; gg < TE / GS; ++gg) {
+            uint32_t f1[8], f2[8];
+            tmem_ld8(d1 + gg * GS, f1);
+            if (USE2) tmem_ld8(d2 + gg * GS, f2);
+            const int4 ja = *reinterpret_cast<const int4*>(meta + gg * 32), jb = *reinterpret_cast<const int4*>(meta + gg * 32 + 16);
+            const int recv = *reinterpret_cast<const int*>(meta + 512 + gg * 4);
+            float dr[8];
+            if (ROLE > 0) {
+                const float4 da = *reinterpret_cast<const float4*>(meta + 128 + (ROLE - 1) * 128 + gg * 32);
+                const float4 db = *reinterpret_cast<const float4*>(meta + 128 + (ROLE - 1) * 128 + gg * 32 + 16);
+                dr[0] = da.x; dr[1] = da.y; dr[2] = da.z; dr[3] = da.w; dr[4] = db.x; dr[5] = db.y; dr[6] = db.z; dr[7] = db.w;
+            }
+            const int jo[8] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
+            float t1[8], t2[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint8_t* row = tb + jo[u] * NB;
+                t1[u] = *reinterpret_cast<const float*>(row + T1_OFF);
+                if (USE2) t2[u] = *reinterpret_cast<const float*>(row + T2_OFF);
+            }
+            if (recv != cur) {                                     // receiver change (groups are receiver-aligned)
+                out[obase + (int64_t)cur * OUT_LD] = base + (acc0 + acc1);
+#pragma unroll 1
+                for (int i = cur + 1; i < recv; ++i) out[obase + (int64_t)i * OUT_LD] = load_base(i);   // edgeless rows
+                cur = recv;
+                acc0 = acc1 = 0.f;
+                base = load_base(cur);
+            }
+            tmem_wait_ld();
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                if (ROLE == 0) {
+                    acc0 = fmaf(__uint_as_float(f1[u]), t1[u], acc0);
+                    acc1 = fmaf(__uint_as_float(f1[u + 1]), t1[u + 1], acc1);
+                } else {
+                    acc0 = fmaf(__uint_as_float(f1[u]) * t1[u], dr[u], acc0);
+                    acc1 = fmaf(__uint_as_float(f1[u + 1]) * t1[u + 1], dr[u + 1], acc1);
+                    if (USE2) {
+                        acc0 = fmaf(__uint_as_float(f2[u]), t2[u], acc0);
+                        acc1 = fmaf(__uint_as_float(f2[u + 1]), t2[u + 1], acc1);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S->acc_free[pipe]);
+    }
+    if (ra < rb) {
+        out[obase + (int64_t)cur * OUT_LD] = base + (acc0 + acc1);
+#pragma unroll 1
+        for (int i = cur + 1; i < rb; ++i) out[obase + (int64_t)i * OUT_LD] = load_base(i);
+    }
+}
+
+template <bool HAS_MU>
+__global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
+    int n_max, const int* __restrict__ node_ptr, const uint32_t* __restrict__ Afmt /* [4 slices][2 sets][128][32] */,
+    float kappa, const int4* __restrict__ pipe_info, const uint8_t* __restrict__ tiles, const float* __restrict__ x,
+    const float* __restrict__ mu_in, float* __restrict__ q, float* __restrict__ mu_out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int NB = Tab<HAS_MU>::NODE_BYTES;
+    uint8_t* TabS = smem;
+    const uint32_t tab_bytes = ((uint32_t)n_max * NB + 127u) & ~127u;
+    uint8_t* Bs = smem + tab_bytes;
+    uint8_t* MetaS = Bs + NPIPE * TILE_B;
+    StBars* S = reinterpret_cast<StBars*>(MetaS + NPIPE * 2 * META);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x / NSLICE, slice = blockIdx.x % NSLICE;
+    const int node0 = __ldg(node_ptr + g), n = __ldg(node_ptr + g + 1) - node0;
+
+    if (tid == 0) {
+        for (int p = 0; p < NPIPE; ++p) {
+            mbar_init(&S->b_full[p], 1);
+            mbar_init(&S->mma_done[p], 1);
+            mbar_init(&S->acc_free[p], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(&S->tmem_base, TM_COLS);
+
+    // ---- stage this slice of the structure's node table
+    for (int id = tid; id < n * 8; id += ST_THREADS) {
+        const int node = id >> 3, c4 = id & 7;
+        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(node0 + node) * 3 * F + slice * SL) + c4;
+        float4 xq = __ldg(xr), xR = __ldg(xr + F / 4);
+        uint8_t* row = TabS + node * NB + c4 * 16;
+        xq.x *= kappa; xq.y *= kappa; xq.z *= kappa; xq.w *= kappa;
+        xR.x *= kappa; xR.y *= kappa; xR.z *= kappa; xR.w *= kappa;
+        *reinterpret_cast<float4*>(row) = xq;
+        *reinterpret_cast<float4*>(row + SL * 4) = xR;
+        if (HAS_MU) {
+            float4 xm = __ldg(xr + 2 * F / 4);
+            xm.x *= kappa; xm.y *= kappa; xm.z *= kappa; xm.w *= kappa;
+            const float4* mr = reinterpret_cast<const float4*>(mu_in + (size_t)(node0 + node) * 3 * F + slice * SL) + c4;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float4 m = __ldg(mr + a * (F / 4));
+                *reinterpret_cast<float4*>(row + (2 + a) * SL * 4) = make_float4(xm.x * m.x, xm.y * m.y, xm.z * m.z, xm.w * m.w);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S->tmem_base;
+
+    // ---- weight operands -> TMEM (lane = filter row; 64 fp16 = 32 columns per set)
+    if (warp < 4) {
+#pragma unroll
+        for (int set = 0; set < (HAS_MU ? 2 : 1); ++set) {
+            const uint4* wrow = reinterpret_cast<const uint4*>(Afmt + ((size_t)(slice * 2 + set) * 128 + warp * 32 + lane) * 32);
+            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + TM_A + set * 32;
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                const uint4 w0 = __ldg(wrow + 2 * c8), w1 = __ldg(wrow + 2 * c8 + 1);
+                const uint32_t v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                tmem_st8(ta + c8 * 8, v);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const int pipe = warp >> 2, role = warp & 3;
+    const int4 pi = __ldg(pipe_info + (size_t)g * NPIPE + pipe);
+    const uint8_t* tile_src = tiles + (size_t)pi.x * TILE_BYTES;
+    const int n_tiles = pi.y, ra = pi.z, rb = pi.w;
+    uint8_t* Bp = Bs + pipe * TILE_B;
+    uint8_t* MetaP = MetaS + pipe * 2 * META;
+    const int ch = slice * SL + lane;
+    if (role == 0)
+        run_role<HAS_MU, 0>(S, pipe, lane, tmem, TabS, Bp, MetaP, tile_src, n_tiles, ra, rb, node0, ch, q, q);
+    else if (role == 1)
+        run_role<HAS_MU, 1>(S, pipe, lane, tmem, TabS, Bp, MetaP, tile_src, n_tiles, ra, rb, node0, ch, mu_in, mu_out);
+    else if (role == 2)
+        run_role<HAS_MU, 2>(S, pipe, lane, tmem, TabS, Bp, MetaP, tile_src, n_tiles, ra, rb, node0, ch, mu_in, mu_out);
+    else
+        run_role<HAS_MU, 3>(S, pipe, lane, tmem, TabS, Bp, MetaP, tile_src, n_tiles, ra, rb, node0, ch, mu_in, mu_out);
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, TM_COLS);
+    }
+}
+
+template <bool HAS_MU>
+size_t stream_smem_bytes(int n_max) {
+    const size_t tab = ((size_t)n_max * Tab<HAS_MU>::NODE_BYTES + 127) & ~(size_t)127;
+    return tab + (size_t)NPIPE * TILE_B + (size_t)NPIPE * 2 * META + sizeof(StBars) + 64;
+}
+
+}  // namespace
+
+// Host: per layer, per 32-channel slice, two 128-row weight operands in the TMEM image the kernel stores verbatim:
+// row = 32 u32 = 64 fp16 = a_hi[21] | a_hi[21] | a_lo[21] | 0 with a = 2^sA * {filter_net weight (k < 20), bias}.
+// Set 0 rows: dq | dmuR | dmuR | dmuR filters of the slice; set 1 rows: 0 | dmumu | dmumu | dmumu.
+// kappa[l] = 2^-(sA_l + 10) undoes the operand scaling (applied to the node table).
+void edge_stream_format(const float* W, const float* b, std::vector<uint8_t>& out, float* kappa /*[NLAYER]*/) {
+    out.assign((size_t)NLAYER * NSLICE * 2 * A_SET_WORDS * 4, 0);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out.data());
+    for (int l = 0; l < NLAYER; ++l) {
+        float mx = 0.f;
+        for (int r = l * 3 * F; r < (l + 1) * 3 * F; ++r) {
+            for (int k = 0; k < NRBF; ++k) mx = std::fmax(mx, std::fabs(W[(size_t)r * NRBF + k]));
+            mx = std::fmax(mx, std::fabs(b[r]));
+        }
+        int sA = 0;
+        if (mx > 0.f) sA = (int)std::floor(std::log2(16384.0 / (double)mx));
+        sA = sA < -20 ? -20 : (sA > 24 ? 24 : sA);
+        const float ascale = std::ldexp(1.0f, sA);
+        kappa[l] = std::ldexp(1.0f, -(sA + B_SCALE_LOG2));
+        for (int sl = 0; sl < NSLICE; ++sl)
+            for (int set = 0; set < 2; ++set)
+                for (int quarter = 0; quarter < 4; ++quarter) {
+                    if (set == 1 && quarter == 0) continue;    // unused rows stay zero
+                    const int part = set == 0 ? (quarter == 0 ? 0 : 1) : 2;
+                    for (int chn = 0; chn < SL; ++chn) {
+                        const int row = l * 3 * F + part * F + sl * SL + chn;
+                        __half kk[KH];
+                        for (int k = 0; k < KH; ++k) kk[k] = __float2half_rn(0.f);
+                        for (int k = 0; k < NK; ++k) {
+                            const float w = (k < NRBF ? W[(size_t)row * NRBF + k] : b[row]) * ascale;
+                            const __half h = __float2half_rn(w);
+                            const __half lo = __float2half_rn(w - __half2float(h));
+                            kk[k] = h;
+                            kk[NK + k] = h;
+                            kk[2 * NK + k] = lo;
+                        }
+                        uint32_t* dst = o + ((((size_t)l * NSLICE + sl) * 2 + set) * 128 + quarter * SL + chn) * 32;
+                        for (int c = 0; c < 32; ++c) {
+                            uint16_t h0, h1;
+                            memcpy(&h0, &kk[2 * c], 2);
+                            memcpy(&h1, &kk[2 * c + 1], 2);
+                            dst[c] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                        }
+                    }
+                }
+    }
+}
+
+bool edge_stream_supported(int max_struct_nodes) { return max_struct_nodes > 0 && max_struct_nodes <= MAXN; }
+
+size_t edge_stream_tile_capacity(int n_struct, int n_nodes, int64_t n_edges) {
+    return (size_t)((n_edges / GS + n_nodes) / 4 + (int64_t)NPIPE * n_struct + 16);
+}
+
+int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_t n_edges, const int* node_ptr,
+                     const int* row_ptr, const int* col, const int8_t* shift, const float* pos, const float* cell) {
+    if (n_struct <= 0 || M <= 0) return 0;
+    const size_t cap = edge_stream_tile_capacity(n_struct, M, n_edges);
+    RLVD_CHECK(cap < (size_t)0x7fffffff, "edge stream: %zu tiles overflow int32; split the batch", cap);
+    if (e->tiles.ensure(cap * TILE_BYTES) || e->pipe_info.ensure((size_t)n_struct * NPIPE * sizeof(int4)) ||
+        e->tile_ctr.ensure(8))
+        return 1;
+    RLVD_CUDA(cudaMemsetAsync(e->tile_ctr.p, 0, 8, s));
+    Span sp(e, s, FAM_EDGE);
+    edge_pack_kernel<<<n_struct, 256, 0, s>>>(n_struct, node_ptr, row_ptr, col, shift, pos, cell, e->w.freqs, e->w.feps,
+                                              e->w.cutoff, e->tile_ctr.as<int>(), (int)cap, e->tiles.as<uint8_t>(),
+                                              e->pipe_info.as<int4>(), e->tile_ctr.as<int>() + 1);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, int max_struct_nodes, const int* node_ptr,
+                       const float* x, const float* mu_in, float* q, float* mu_out) {
+    if (n_struct <= 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RLVD_CUDA(cudaFuncSetAttribute(edge_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)stream_smem_bytes<true>(MAXN)));
+        RLVD_CUDA(cudaFuncSetAttribute(edge_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)stream_smem_bytes<true>(MAXN)));
+        attr_set = true;
+    }
+    const uint32_t* af = reinterpret_cast<const uint32_t*>(e->w.filt_E) + (size_t)layer * NSLICE * 2 * A_SET_WORDS;
+    const float kappa = e->w.filt_kappa[layer];
+    // both variants request the HAS_MU footprint: one CTA per SM (each CTA owns all 512 TMEM columns)
+    const size_t smem = stream_smem_bytes<true>(max_struct_nodes) < 120 * 1024 ? 120 * 1024 : stream_smem_bytes<true>(max_struct_nodes);
+    Span sp(e, s, FAM_EDGE);
+    if (mu_in == nullptr)
+        edge_stream_kernel<false><<<n_struct * NSLICE, ST_THREADS, smem, s>>>(
+            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), x, nullptr, q, mu_out);
+    else
+        edge_stream_kernel<true><<<n_struct * NSLICE, ST_THREADS, smem, s>>>(
+            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), x, mu_in, q, mu_out);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rlvd
