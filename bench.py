@@ -156,6 +156,7 @@ def main():
 
     model = rb.registry.get_model_class("dqn_v2").load(CKPT).to(dev).eval()
     eng = model._engine_for(dev)
+    eng_sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     n_rep = args.replicas_per_gpu
     reps, spaces = make_shard(rank, n_rep, args.jitter)
     pk = pack_replicas(reps, spaces, dedup_reactants=args.dedup)
@@ -225,7 +226,7 @@ def main():
     for _ in range(prof_steps):
         flush.fill_(1.0)
         step_device()
-    fam = {k: eng.profile_read(k) for k in ("neighbor", "edge", "node", "readout")}
+    fam = {k: eng.profile_read(k) for k in ("neighbor", "edge_pack", "edge", "node", "readout")}
     eng.profile(False)
 
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
@@ -247,6 +248,18 @@ def main():
         n_nodes_total, edge_bytes = M, 40.0 * F * M + 7.0 * n_edges
         edge_avg_ms = edge_ms / max(edge_n, 1)
         achieved = edge_bytes / (edge_avg_ms * 1e-3) / 1e9 if edge_avg_ms > 0 else 0.0
+        # the same kernel against the resource that actually bounds it: every edge slot gathers five
+        # 128-byte table rows per 32-channel slice (two in layer 0) through the shared-memory crossbar, 128 B/clk/SM
+        sm_clock_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+        smem_peak = 128.0 * eng_sm_count * sm_clock_hz / 1e9
+        smem_bytes = n_edges * 4 * 128.0 * (5 + 5 + 2) / 3.0          # average over the three layer launches
+        smem_avg_ms = edge_avg_ms
+        smem_achieved = smem_bytes / (smem_avg_ms * 1e-3) / 1e9 if smem_avg_ms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("edge_stream_bytes_per_launch")
+        except Exception:
+            pass
         total_prof = sum(v[0] for v in fam.values())
         value = world * n_q * args.steps / (ms_dev * 1e-3)
         e2e = world * n_q * args.steps / (ms_e2e * 1e-3)
@@ -266,10 +279,15 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "edge_kernel (K2+K3a+K3c+K4 fused)", "achieved": achieved,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "edge_stream_kernel (K3a+K3c+K4 fused; one launch per layer)", "achieved": achieved,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": edge_bytes,
-                         "avg_launch_ms": edge_avg_ms, "launches_timed": edge_n},
+                         "avg_launch_ms": edge_avg_ms, "launches_timed": edge_n,
+                         "smem": {"bound": "shared-memory crossbar (what ncu shows this kernel saturating)",
+                                  "achieved": smem_achieved, "peak": smem_peak, "unit": "GB/s",
+                                  "frac": smem_achieved / smem_peak if smem_peak else None,
+                                  "gather_bytes_per_launch": smem_bytes,
+                                  "peak_source": "128 B/clk/SM x SMs x sampled SM clock"}},
             "kernel_share": {k: (v[0] / total_prof if total_prof > 0 else None) for k, v in fam.items()},
             "kernel_ms_per_step": {k: v[0] / prof_steps for k, v in fam.items()},
         }

@@ -131,7 +131,8 @@ int  rlvd_set_option(rlvd_engine* e, const char* name, int32_t value);
 /* Number of kernels this library has launched on the engine since creation (bench.py "gpu_launches"). */
 int64_t rlvd_launch_count(const rlvd_engine* e);
 /* Event-timed milliseconds spent in the named kernel family since the last reset
- * ("neighbor", "edge", "node", "readout"); timing is off unless enabled. */
+ * ("neighbor", "edge", "node", "readout", "edge_pack" = the once-per-call edge embedding pre-pass); timing is off
+ * unless enabled. */
 int  rlvd_profile_enable(rlvd_engine* e, int32_t on);
 int  rlvd_profile_read(rlvd_engine* e, const char* family, double* ms_total, int64_t* launches);
 int  rlvd_profile_reset(rlvd_engine* e);

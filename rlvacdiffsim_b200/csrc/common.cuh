@@ -49,7 +49,7 @@ struct Tensor {
     bool is_int = false;
 };
 
-enum Family { FAM_NEIGHBOR = 0, FAM_EDGE = 1, FAM_NODE = 2, FAM_READOUT = 3, FAM_COUNT = 4 };
+enum Family { FAM_NEIGHBOR = 0, FAM_EDGE = 1, FAM_NODE = 2, FAM_READOUT = 3, FAM_PACK = 4, FAM_COUNT = 5 };
 
 struct ProfSpan {
     int family;
@@ -63,7 +63,7 @@ struct Weights {
     const float* filt_T = nullptr;              // [L][21][384]  (k<20: weight^T, k=20: bias)
     const void* filt_F = nullptr;               // [L][3 parts][hi|lo] tf32 tensor-core operand (tc_edge.cu)
     const void* filt_S = nullptr;               // [L][4 slices][hi|lo] tf32 operand of the sliced kernel (tc_edge_small.cu)
-    const void* filt_E = nullptr;               // [L][4 slices][2 sets][128][32] fp16-split TMEM image (edge_stream.cu)
+    const void* filt_E = nullptr;               // [L][4 slices][128][32] fp16-split TMEM image (edge_stream.cu)
     float filt_kappa[NLAYER] = {};              // 2^-(sA+10): undoes the fp16 range scaling of filt_E and the edge tiles
     const float* feps = nullptr;                // [20] freqs[k] - (k+1)*freqs[0]
     const float* inter_w0T[NLAYER] = {};        // [128][128]   (in-major: Wt[k][n])

@@ -17,16 +17,21 @@
 // edge_stream_kernel (per layer; CTA = one structure x one 32-channel slice; 1 CTA per SM)
 //   The slice of the structure's node table lives in shared memory (gathers never leave the SM):
 //     row(j) = kappa*x_q | kappa*x_R | kappa*x_m*mu_x | kappa*x_m*mu_y | kappa*x_m*mu_z        (5 x 32 fp32)
-//   Filters run on tcgen05 with the weight operand resident in TMEM (A1 rows = dq | dmuR | dmuR | dmuR filters of the
-//   slice, A2 rows = 0 | dmumu | dmumu | dmumu), pre-split on the host as a_hi[21] | a_hi[21] | a_lo[21] | 0 so that
-//   ONE K=64 fp16 MMA chain evaluates  a_hi.b_hi + a_hi.b_lo + a_lo.b_hi  (fp32-accurate, 4 dispatches):
-//        D1[128, 32 slots] = A1 . Bt      D2[128, 32 slots] = A2 . Bt
+//   Filters run on tcgen05 with the weight operand resident in TMEM (A rows = dq | dmuR | dmumu | dmumu filters of
+//   the slice), pre-split on the host as a_hi[21] | a_hi[21] | a_lo[21] | 0 so that ONE K=64 fp16 MMA chain evaluates
+//   a_hi.b_hi + a_hi.b_lo + a_lo.b_hi (fp32-accurate, 4 dispatches):      D[128, 32 slots] = A . Bt
 //   A TMEM lane quarter can only be read by the warps with warp%4 == quarter, which fixes the roles:
-//        warp 0 (q)   : dq    += D1 * x_q[j]                         (+ issues the tile's bulk copies and MMAs)
-//        warp a=1..3  : dmu_a += D1 * x_R[j] * dir_a + D2 * (x_m mu_a)[j]
-//   so every warp owns its output rows outright: no exchange between warps, no atomics, sums in CSR order
-//   (bitwise reproducible).  NPIPE such 4-warp pipelines run on disjoint receiver ranges; while one waits for its
-//   next tile's MMAs the others fill the issue slots.  kappa = 2^-(sA+10) undoes the fp16 range scaling exactly.
+//        warp 0 (q)   : dq        += D * x_q[j]                  (+ bulk copies, MMA issue, and all global writes)
+//        warp 1 (R)   : dmuR_xyz  += D * x_R[j] * dir_xyz
+//        warp 2 (Mxy) : dmuM_xy   += D * (x_m mu_xy)[j]
+//        warp 3 (Mz)  : dmuM_z    += D * (x_m mu_z)[j]
+//   The kernel is shared-memory-bandwidth bound (gathers 5 x 128 B per slot), so every sender row is gathered exactly
+//   once.  When a receiver's row ends, warps 1-3 drop their partial sums into a small shared-memory slot; warp 0 adds
+//   them to mu_in and writes mu_out one tile later, inside the window in which it would otherwise wait for the next
+//   tile's MMAs — the tile barriers already order those accesses, so the combine needs no synchronisation of its own.
+//   No atomics; sums run in CSR order (bitwise reproducible).  NPIPE such 4-warp pipelines run on disjoint receiver
+//   ranges; while one waits for its next tile the others fill the issue slots.  kappa = 2^-(sA+10) undoes the fp16
+//   range scaling exactly.
 #include <cuda_fp16.h>
 
 #include <cmath>
@@ -47,22 +52,27 @@ constexpr int GS = 8;                     // slots per receiver-aligned group
 constexpr int KH = 64;                    // fp16 k-extent of the split operands
 constexpr int NK = NRBF + 1;              // 21: 20 Bessel functions + the bias column (fcut)
 constexpr int TILE_B = TE * KH * 2;       // 4096
-constexpr int META = 576;                 // j[32] | dir[3][32] | recv[4] | pad
-constexpr int TILE_BYTES = TILE_B + META; // 4672
+constexpr int META = 528;                 // j[32] | dir[3][32] | recv[4]
+constexpr int TILE_BYTES = TILE_B + META; // 4624
 constexpr int MAXN = 256;
 constexpr int ST_THREADS = NPIPE * 128;
 constexpr int B_SCALE_LOG2 = 10;
-constexpr int TM_D = 0;                   // TMEM columns: D1/D2 of pipe p at p*64 / p*64+32
-constexpr int TM_A = NPIPE * 64;          // A1 at TM_A, A2 at TM_A+32 (64 fp16 = 32 columns each)
-constexpr int TM_COLS = 512;
-constexpr int A_SET_WORDS = 128 * 32;     // u32 per (slice, set)
+constexpr int TM_D = 0;                   // TMEM columns: accumulator of pipe p at p*32
+constexpr int TM_A = NPIPE * TE;          // weight operand (64 fp16 = 32 columns)
+constexpr int TM_COLS = 256;
+constexpr int A_SLICE_WORDS = 128 * 32;   // u32 per (layer, slice)
+constexpr int NM_STAGE = 2;               // meta buffers per pipeline
+constexpr int PART_ROWS = 6;              // partial-sum rows per finished receiver: R x,y,z | M x,y | M z
+constexpr int PART_SLOT = PART_ROWS * SL * 4;          // 768 B
+constexpr int PART_BYTES = 2 * (TE / GS) * PART_SLOT;  // [tile parity][<= 4 finished receivers per tile]
 constexpr float PI_F = 3.14159265358979323846f;
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TE >> 3) << 17) | (8u << 24);   // f16 x f16 -> f32, M=128, N=32
 
-static_assert(TM_A + 64 <= TM_COLS, "TMEM budget");
+static_assert(TM_A + 32 <= TM_COLS, "TMEM budget");
 
 struct StBars {
     uint64_t b_full[NPIPE], mma_done[NPIPE], acc_free[NPIPE];
+    int chg[NPIPE][2][TE / GS];           // receivers finished in a tile, per tile parity
     uint32_t tmem_base;
 };
 
@@ -70,11 +80,24 @@ __device__ __noinline__ void st_timeout() {
     printf("rlvd: edge_stream mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
     __trap();
 }
+// try_wait without a suspend-time hint: the hardware's own (short) wait window, re-armed in a loop.  The hinted form
+// compiles to TRYWAIT + NANOSLEEP, whose wake-up granularity put ~1 us between a tile's barrier hand-offs.
+__device__ __forceinline__ bool st_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void st_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
 #pragma unroll 1
-    while (!mbar_try_wait(bar, parity))
-        if (++spins > 400000u) st_timeout();
+    while (!st_try_wait(bar, parity))
+        if (++spins > 50000000u) st_timeout();
 }
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(
@@ -164,7 +187,7 @@ __global__ void __launch_bounds__(256) edge_pack_kernel(int n_struct, const int*
         e0 = __ldg(row_ptr + node0 + tid);
         deg = __ldg(row_ptr + node0 + tid + 1) - e0;
     }
-    const int gc = (deg + GS - 1) / GS;
+    const int gc = tid < n ? max(1, (deg + GS - 1) / GS) : 0;   // edgeless receivers keep one (zero-filter) group
     int incl = gc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -229,7 +252,7 @@ __global__ void __launch_bounds__(256) edge_pack_kernel(int n_struct, const int*
         while (i >= bnd[p + 1]) ++p;
         const int gi = node0 + i;
         const int re0 = __ldg(row_ptr + gi), rdeg = __ldg(row_ptr + gi + 1) - re0;
-        const int nslots = ((rdeg + GS - 1) / GS) * GS;
+        const int nslots = max(1, (rdeg + GS - 1) / GS) * GS;
         const int slot0 = (goff[i] - goff[bnd[p]]) * GS;
         const float xi = __ldg(pos + 3 * (int64_t)gi), yi = __ldg(pos + 3 * (int64_t)gi + 1), zi = __ldg(pos + 3 * (int64_t)gi + 2);
         for (int s = lane; s < nslots; s += 32) {
@@ -303,37 +326,84 @@ struct Tab {
     static constexpr int NODE_BYTES = HAS_MU ? 5 * SL * 4 : 2 * SL * 4;   // 640 / 256
 };
 
-// One warp of one pipeline.  ROLE = TMEM lane quarter: 0 -> q, a = 1..3 -> mu component a-1.
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+struct PipeCtx {
+    StBars* S;
+    int pipe, lane;
+    uint32_t tmem;
+    const uint8_t* tab;      // node table of the slice
+    uint8_t* Bp;             // operand buffer
+    uint8_t* MetaP;          // NM_STAGE meta buffers
+    float* Part;             // [2][4][PART_ROWS][32] partial sums of finished receivers
+    const uint8_t* tile_src;
+    int n_tiles, ra, rb, node0, ch;
+};
+
+// warp 0: adds the partial sums of the receivers finished in a tile to mu_in and writes mu_out.
+template <bool HAS_MU>
+__device__ __forceinline__ void combine_mu(const PipeCtx& c, int buf, int count, const float* __restrict__ mu_in,
+                                           float* __restrict__ mu_out) {
+#pragma unroll 1
+    for (int k = 0; k < count; ++k) {
+        const int i = c.S->chg[c.pipe][buf][k];
+        const float* P = c.Part + ((buf * (TE / GS) + k) * PART_ROWS) * SL + c.lane;
+        const int64_t o = (int64_t)(c.node0 + i) * 3 * F + c.ch;
+        float v0 = P[0], v1 = P[SL], v2 = P[2 * SL];
+        if (HAS_MU) {
+            v0 += P[3 * SL] + __ldg(mu_in + o);
+            v1 += P[4 * SL] + __ldg(mu_in + o + F);
+            v2 += P[5 * SL] + __ldg(mu_in + o + 2 * F);
+        }
+        mu_out[o] = v0;
+        mu_out[o + F] = v1;
+        mu_out[o + 2 * F] = v2;
+    }
+}
+
+// One warp of one pipeline.  ROLE = TMEM lane quarter (see the file header).  Tile t uses the pipeline's operand
+// buffer, meta buffer t%2, TMEM accumulator and partial-sum buffer t%2:
+//   warp 0 / lane 0:  wait b_full (bulk copies of tile t landed) and acc_free (all roles done with tile t-1)
+//                     -> issue the tile's 4 MMAs -> commit to mma_done
+//   warp 0:           write mu_out for the receivers finished in tile t-1 (overlaps the MMAs)
+//   all warps:        wait mma_done -> [warp 0 / lane 0: operand buffer is free again, bulk-copy tile t+1]
+//                     -> consume the tile's 4 groups -> arrive on acc_free
+// Every receiver of the range owns at least one group (edge_pack_kernel), so a receiver change is a plain
+// "drop finished row, start next row".
 template <bool HAS_MU, int ROLE>
-__device__ __forceinline__ void run_role(StBars* S, int pipe, int lane, uint32_t tmem, const uint8_t* tab, uint8_t* Bp,
-                                         uint8_t* MetaP, const uint8_t* __restrict__ tile_src, int n_tiles, int ra, int rb,
-                                         int node0, int ch, const float* __restrict__ base_src, float* __restrict__ out) {
+__device__ __forceinline__ void run_role(const PipeCtx& c, const float* __restrict__ mu_in, float* __restrict__ q,
+                                         float* __restrict__ mu_out) {
     constexpr int NB = Tab<HAS_MU>::NODE_BYTES;
-    constexpr int T1_OFF = ROLE == 0 ? 0 : SL * 4;
-    constexpr int T2_OFF = 2 * SL * 4 + (ROLE > 0 ? ROLE - 1 : 0) * SL * 4;
-    constexpr bool USE2 = HAS_MU && ROLE > 0;
-    constexpr int OUT_LD = ROLE == 0 ? F : 3 * F;
-    constexpr int OUT_OFF = ROLE == 0 ? 0 : (ROLE - 1) * F;
-    constexpr bool HAS_BASE = ROLE == 0 || HAS_MU;
+    constexpr int NACC = ROLE == 0 ? 1 : ROLE == 1 ? 3 : ROLE == 2 ? 2 : 1;
+    constexpr int T_OFF = ROLE == 0 ? 0 : ROLE == 1 ? SL * 4 : ROLE == 2 ? 2 * SL * 4 : 4 * SL * 4;
+    constexpr int P_ROW = ROLE == 1 ? 0 : ROLE == 2 ? 3 : 5;
+    constexpr int NG = TE / GS;
+    StBars* S = c.S;
+    const int pipe = c.pipe, lane = c.lane, n_tiles = c.n_tiles;
+    if (n_tiles <= 0 || c.ra >= c.rb) return;     // (a non-empty receiver range always has tiles)
 
-    const uint32_t d1 = tmem + ((uint32_t)(ROLE * 32) << 16) + TM_D + (uint32_t)pipe * 64;
-    const uint32_t d2 = d1 + 32;
-    const uint8_t* tb = tab + lane * 4;
-    const int64_t obase = (int64_t)node0 * OUT_LD + OUT_OFF + ch;
-    auto load_base = [&](int i) -> float { return HAS_BASE ? base_src[obase + (int64_t)i * OUT_LD] : 0.f; };
+    const uint32_t dcol = c.tmem + ((uint32_t)(ROLE * 32) << 16) + TM_D + (uint32_t)pipe * TE;
+    const uint8_t* tb = c.tab + lane * 4 + T_OFF;
+    float* qp = q + ((int64_t)c.node0 * F + c.ch);
 
-    int cur = ra;
-    float acc0 = 0.f, acc1 = 0.f;
-    float base = ra < rb ? load_base(ra) : 0.f;
-
-    uint64_t bdesc[4];
-    if (ROLE == 0) {
+    int cur = c.ra;
+    float acc[NACC][2];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) bdesc[c] = umma_desc(smem_u32(Bp) + c * 1024, 512, 128);
-        if (lane == 0 && n_tiles > 0) {
+    for (int a = 0; a < NACC; ++a) acc[a][0] = acc[a][1] = 0.f;
+    float qbase = ROLE == 0 ? qp[(int64_t)cur * F] : 0.f;
+    int nprev = 0;                            // receivers finished in the previous tile (warp 0 combines them)
+
+    uint64_t bdesc0 = 0;
+    if (ROLE == 0) {
+        bdesc0 = umma_desc(smem_u32(c.Bp), 512, 128);
+        if (lane == 0) {
             mbar_expect_tx(&S->b_full[pipe], TILE_BYTES);
-            bulk_g2s(Bp, tile_src, TILE_B, &S->b_full[pipe]);
-            bulk_g2s(MetaP, tile_src + TILE_B, META, &S->b_full[pipe]);
+            bulk_g2s(c.Bp, c.tile_src, TILE_B, &S->b_full[pipe]);
+            bulk_g2s(c.MetaP, c.tile_src + TILE_B, META, &S->b_full[pipe]);
+            if (n_tiles > 1) prefetch_l2(c.tile_src + TILE_BYTES, TILE_BYTES);
+            if (n_tiles > 2) prefetch_l2(c.tile_src + 2 * TILE_BYTES, TILE_BYTES);
         }
     }
 
@@ -342,97 +412,126 @@ __device__ __forceinline__ void run_role(StBars* S, int pipe, int lane, uint32_t
         const uint32_t par = (uint32_t)t & 1u;
         if (ROLE == 0) {
             if (lane == 0) {
-                st_wait(&S->b_full[pipe], par);                     // operand + meta of tile t landed
-                if (t > 0) st_wait(&S->acc_free[pipe], par ^ 1u);   // all four roles are done with tile t-1
+                st_wait(&S->b_full[pipe], par);                       // operand + meta of tile t landed
+                if (t > 0) st_wait(&S->acc_free[pipe], par ^ 1u);     // all roles are done with tile t-1
                 tc_fence_after();
 #pragma unroll
-                for (int c = 0; c < 4; ++c) umma_f16_ts(tmem + TM_D + (uint32_t)pipe * 64, tmem + TM_A + c * 8, bdesc[c], c);
-                if (HAS_MU) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        umma_f16_ts(tmem + TM_D + (uint32_t)pipe * 64 + 32, tmem + TM_A + 32 + c * 8, bdesc[c], c);
-                }
+                for (int k = 0; k < 4; ++k)
+                    umma_f16_ts(c.tmem + TM_D + (uint32_t)pipe * TE, c.tmem + TM_A + k * 8, bdesc0 + (uint64_t)(k * 64), k);
                 umma_commit(&S->mma_done[pipe]);
             }
             __syncwarp();
+            combine_mu<HAS_MU>(c, par ^ 1, nprev, mu_in, mu_out);
         }
         st_wait(&S->mma_done[pipe], par);
         tc_fence_after();
-        if (ROLE == 0 && lane == 0 && t + 1 < n_tiles) {            // operand buffer is free again: fetch tile t+1
-            const uint8_t* src = tile_src + (size_t)(t + 1) * TILE_BYTES;
-            mbar_expect_tx(&S->b_full[pipe], TILE_BYTES);
-            bulk_g2s(Bp, src, TILE_B, &S->b_full[pipe]);
-            bulk_g2s(MetaP + (par ^ 1u) * META, src + TILE_B, META, &S->b_full[pipe]);
+        if (ROLE == 0 && lane == 0) {
+            if (t + 1 < n_tiles) {                                    // operand buffer is free again: fetch tile t+1
+                const uint8_t* src = c.tile_src + (size_t)(t + 1) * TILE_BYTES;
+                mbar_expect_tx(&S->b_full[pipe], TILE_BYTES);
+                bulk_g2s(c.Bp, src, TILE_B, &S->b_full[pipe]);
+                bulk_g2s(c.MetaP + (par ^ 1u) * META, src + TILE_B, META, &S->b_full[pipe]);
+            }
+            if (t + 3 < n_tiles) prefetch_l2(c.tile_src + (size_t)(t + 3) * TILE_BYTES, TILE_BYTES);
         }
-        const uint8_t* meta = MetaP + par * META;
-#pragma unroll 1
-        for (int gg = 0; gg < TE / GS; ++gg) {
-            uint32_t f1[8], f2[8];
-            tmem_ld8(d1 + gg * GS, f1);
-            if (USE2) tmem_ld8(d2 + gg * GS, f2);
+        const uint8_t* meta = c.MetaP + par * META;
+        float* part = c.Part + (par * NG * PART_ROWS + P_ROW) * SL + lane;
+        int nchg = 0;
+#pragma unroll
+        for (int gg = 0; gg < NG; ++gg) {
+            uint32_t f[8];
+            tmem_ld8(dcol + gg * GS, f);
             const int4 ja = *reinterpret_cast<const int4*>(meta + gg * 32), jb = *reinterpret_cast<const int4*>(meta + gg * 32 + 16);
             const int recv = *reinterpret_cast<const int*>(meta + 512 + gg * 4);
-            float dr[8];
-            if (ROLE > 0) {
-                const float4 da = *reinterpret_cast<const float4*>(meta + 128 + (ROLE - 1) * 128 + gg * 32);
-                const float4 db = *reinterpret_cast<const float4*>(meta + 128 + (ROLE - 1) * 128 + gg * 32 + 16);
-                dr[0] = da.x; dr[1] = da.y; dr[2] = da.z; dr[3] = da.w; dr[4] = db.x; dr[5] = db.y; dr[6] = db.z; dr[7] = db.w;
+            float dr[3][8];
+            if (ROLE == 1) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const float4 da = *reinterpret_cast<const float4*>(meta + 128 + a * 128 + gg * 32);
+                    const float4 db = *reinterpret_cast<const float4*>(meta + 128 + a * 128 + gg * 32 + 16);
+                    dr[a][0] = da.x; dr[a][1] = da.y; dr[a][2] = da.z; dr[a][3] = da.w;
+                    dr[a][4] = db.x; dr[a][5] = db.y; dr[a][6] = db.z; dr[a][7] = db.w;
+                }
             }
             const int jo[8] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
             float t1[8], t2[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const uint8_t* row = tb + jo[u] * NB;
-                t1[u] = *reinterpret_cast<const float*>(row + T1_OFF);
-                if (USE2) t2[u] = *reinterpret_cast<const float*>(row + T2_OFF);
+                t1[u] = *reinterpret_cast<const float*>(row);
+                if (ROLE == 2) t2[u] = *reinterpret_cast<const float*>(row + SL * 4);
             }
             if (recv != cur) {                                     // receiver change (groups are receiver-aligned)
-                out[obase + (int64_t)cur * OUT_LD] = base + (acc0 + acc1);
-#pragma unroll 1
-                for (int i = cur + 1; i < recv; ++i) out[obase + (int64_t)i * OUT_LD] = load_base(i);   // edgeless rows
+                if (ROLE == 0) {
+                    qp[(int64_t)cur * F] = qbase + (acc[0][0] + acc[0][1]);
+                    qbase = qp[(int64_t)recv * F];
+                    if (lane == 0) S->chg[pipe][par][nchg] = cur;
+                } else {
+#pragma unroll
+                    for (int a = 0; a < NACC; ++a) part[(nchg * PART_ROWS + a) * SL] = acc[a][0] + acc[a][1];
+                }
+                ++nchg;
                 cur = recv;
-                acc0 = acc1 = 0.f;
-                base = load_base(cur);
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) acc[a][0] = acc[a][1] = 0.f;
             }
             tmem_wait_ld();
 #pragma unroll
-            for (int u = 0; u < 8; u += 2) {
-                if (ROLE == 0) {
-                    acc0 = fmaf(__uint_as_float(f1[u]), t1[u], acc0);
-                    acc1 = fmaf(__uint_as_float(f1[u + 1]), t1[u + 1], acc1);
+            for (int u = 0; u < 8; ++u) {
+                const float w = __uint_as_float(f[u]);
+                if (ROLE == 0 || ROLE == 3) {
+                    acc[0][u & 1] = fmaf(w, t1[u], acc[0][u & 1]);
+                } else if (ROLE == 1) {
+                    const float sR = w * t1[u];
+                    acc[0][u & 1] = fmaf(sR, dr[0][u], acc[0][u & 1]);
+                    acc[1][u & 1] = fmaf(sR, dr[1][u], acc[1][u & 1]);
+                    acc[2][u & 1] = fmaf(sR, dr[2][u], acc[2][u & 1]);
                 } else {
-                    acc0 = fmaf(__uint_as_float(f1[u]) * t1[u], dr[u], acc0);
-                    acc1 = fmaf(__uint_as_float(f1[u + 1]) * t1[u + 1], dr[u + 1], acc1);
-                    if (USE2) {
-                        acc0 = fmaf(__uint_as_float(f2[u]), t2[u], acc0);
-                        acc1 = fmaf(__uint_as_float(f2[u + 1]), t2[u + 1], acc1);
-                    }
+                    acc[0][u & 1] = fmaf(w, t1[u], acc[0][u & 1]);
+                    acc[1][u & 1] = fmaf(w, t2[u], acc[1][u & 1]);
                 }
             }
         }
+        nprev = nchg;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&S->acc_free[pipe]);
     }
-    if (ra < rb) {
-        out[obase + (int64_t)cur * OUT_LD] = base + (acc0 + acc1);
-#pragma unroll 1
-        for (int i = cur + 1; i < rb; ++i) out[obase + (int64_t)i * OUT_LD] = load_base(i);
+    // ---- the receiver still in flight: drop its sums into the other parity's slot 0 once every role has left the
+    //      last tile (warp 0 has then finished reading that buffer), then let warp 0 write the remaining rows
+    const uint32_t lastpar = (uint32_t)(n_tiles - 1) & 1u;
+    st_wait(&S->acc_free[pipe], lastpar);
+    if (ROLE == 0) {
+        qp[(int64_t)cur * F] = qbase + (acc[0][0] + acc[0][1]);
+        if (lane == 0) S->chg[pipe][lastpar ^ 1u][0] = cur;
+    } else {
+        float* part = c.Part + ((lastpar ^ 1u) * NG * PART_ROWS + P_ROW) * SL + lane;
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) part[a * SL] = acc[a][0] + acc[a][1];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S->acc_free[pipe]);
+    if (ROLE == 0) {
+        st_wait(&S->acc_free[pipe], lastpar ^ 1u);
+        combine_mu<HAS_MU>(c, (int)lastpar, nprev, mu_in, mu_out);
+        combine_mu<HAS_MU>(c, (int)(lastpar ^ 1u), 1, mu_in, mu_out);
     }
 }
 
 template <bool HAS_MU>
 __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
-    int n_max, const int* __restrict__ node_ptr, const uint32_t* __restrict__ Afmt /* [4 slices][2 sets][128][32] */,
+    int n_max, const int* __restrict__ node_ptr, const uint32_t* __restrict__ Afmt /* [4 slices][128][32] */,
     float kappa, const int4* __restrict__ pipe_info, const uint8_t* __restrict__ tiles, const float* __restrict__ x,
     const float* __restrict__ mu_in, float* __restrict__ q, float* __restrict__ mu_out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int NB = Tab<HAS_MU>::NODE_BYTES;
+    constexpr int NROLE = HAS_MU ? 4 : 2;           // layer 0 (mu == 0) has no dmumu term: warps 2, 3 idle
     uint8_t* TabS = smem;
     const uint32_t tab_bytes = ((uint32_t)n_max * NB + 127u) & ~127u;
     uint8_t* Bs = smem + tab_bytes;
     uint8_t* MetaS = Bs + NPIPE * TILE_B;
-    StBars* S = reinterpret_cast<StBars*>(MetaS + NPIPE * 2 * META);
+    float* PartS = reinterpret_cast<float*>(MetaS + NPIPE * NM_STAGE * META);
+    StBars* S = reinterpret_cast<StBars*>(reinterpret_cast<uint8_t*>(PartS) + NPIPE * PART_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x / NSLICE, slice = blockIdx.x % NSLICE;
@@ -442,7 +541,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
         for (int p = 0; p < NPIPE; ++p) {
             mbar_init(&S->b_full[p], 1);
             mbar_init(&S->mma_done[p], 1);
-            mbar_init(&S->acc_free[p], 4);
+            mbar_init(&S->acc_free[p], NROLE);
         }
         fence_mbar_init();
     }
@@ -474,18 +573,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     tc_fence_after();
     const uint32_t tmem = S->tmem_base;
 
-    // ---- weight operands -> TMEM (lane = filter row; 64 fp16 = 32 columns per set)
+    // ---- weight operand -> TMEM (lane = filter row; 64 fp16 = 32 columns)
     if (warp < 4) {
+        const uint4* wrow = reinterpret_cast<const uint4*>(Afmt + ((size_t)slice * 128 + warp * 32 + lane) * 32);
+        const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + TM_A;
 #pragma unroll
-        for (int set = 0; set < (HAS_MU ? 2 : 1); ++set) {
-            const uint4* wrow = reinterpret_cast<const uint4*>(Afmt + ((size_t)(slice * 2 + set) * 128 + warp * 32 + lane) * 32);
-            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + TM_A + set * 32;
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-                const uint4 w0 = __ldg(wrow + 2 * c8), w1 = __ldg(wrow + 2 * c8 + 1);
-                const uint32_t v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                tmem_st8(ta + c8 * 8, v);
-            }
+        for (int c8 = 0; c8 < 4; ++c8) {
+            const uint4 w0 = __ldg(wrow + 2 * c8), w1 = __ldg(wrow + 2 * c8 + 1);
+            const uint32_t v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            tmem_st8(ta + c8 * 8, v);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
@@ -493,21 +589,27 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     __syncthreads();
     tc_fence_after();
 
-    const int pipe = warp >> 2, role = warp & 3;
-    const int4 pi = __ldg(pipe_info + (size_t)g * NPIPE + pipe);
-    const uint8_t* tile_src = tiles + (size_t)pi.x * TILE_BYTES;
-    const int n_tiles = pi.y, ra = pi.z, rb = pi.w;
-    uint8_t* Bp = Bs + pipe * TILE_B;
-    uint8_t* MetaP = MetaS + pipe * 2 * META;
-    const int ch = slice * SL + lane;
-    if (role == 0)
-        run_role<HAS_MU, 0>(S, pipe, lane, tmem, TabS, Bp, MetaP, tile_src, n_tiles, ra, rb, node0, ch, q, q);
-    else if (role == 1)
-        run_role<HAS_MU, 1>(S, pipe, lane, tmem, TabS, Bp, MetaP, tile_src, n_tiles, ra, rb, node0, ch, mu_in, mu_out);
-    else if (role == 2)
-        run_role<HAS_MU, 2>(S, pipe, lane, tmem, TabS, Bp, MetaP, tile_src, n_tiles, ra, rb, node0, ch, mu_in, mu_out);
-    else
-        run_role<HAS_MU, 3>(S, pipe, lane, tmem, TabS, Bp, MetaP, tile_src, n_tiles, ra, rb, node0, ch, mu_in, mu_out);
+    PipeCtx c;
+    c.S = S;
+    c.pipe = warp >> 2;
+    c.lane = lane;
+    c.tmem = tmem;
+    c.tab = TabS;
+    c.Bp = Bs + c.pipe * TILE_B;
+    c.MetaP = MetaS + c.pipe * NM_STAGE * META;
+    c.Part = PartS + c.pipe * (PART_BYTES / 4);
+    const int4 pi = __ldg(pipe_info + (size_t)g * NPIPE + c.pipe);
+    c.tile_src = tiles + (size_t)pi.x * TILE_BYTES;
+    c.n_tiles = pi.y;
+    c.ra = pi.z;
+    c.rb = pi.w;
+    c.node0 = node0;
+    c.ch = slice * SL + lane;
+    const int role = warp & 3;
+    if (role == 0) run_role<HAS_MU, 0>(c, mu_in, q, mu_out);
+    else if (role == 1) run_role<HAS_MU, 1>(c, mu_in, q, mu_out);
+    else if (HAS_MU && role == 2) run_role<HAS_MU, 2>(c, mu_in, q, mu_out);
+    else if (HAS_MU) run_role<HAS_MU, 3>(c, mu_in, q, mu_out);
 
     tc_fence_before();
     __syncthreads();
@@ -520,17 +622,17 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
 template <bool HAS_MU>
 size_t stream_smem_bytes(int n_max) {
     const size_t tab = ((size_t)n_max * Tab<HAS_MU>::NODE_BYTES + 127) & ~(size_t)127;
-    return tab + (size_t)NPIPE * TILE_B + (size_t)NPIPE * 2 * META + sizeof(StBars) + 64;
+    return tab + (size_t)NPIPE * TILE_B + (size_t)NPIPE * NM_STAGE * META + (size_t)NPIPE * PART_BYTES + sizeof(StBars);
 }
 
 }  // namespace
 
-// Host: per layer, per 32-channel slice, two 128-row weight operands in the TMEM image the kernel stores verbatim:
+// Host: per layer, per 32-channel slice, the 128-row weight operand in the TMEM image the kernel stores verbatim:
 // row = 32 u32 = 64 fp16 = a_hi[21] | a_hi[21] | a_lo[21] | 0 with a = 2^sA * {filter_net weight (k < 20), bias}.
-// Set 0 rows: dq | dmuR | dmuR | dmuR filters of the slice; set 1 rows: 0 | dmumu | dmumu | dmumu.
+// Row quarters: dq | dmuR | dmumu | dmumu filters of the slice.
 // kappa[l] = 2^-(sA_l + 10) undoes the operand scaling (applied to the node table).
 void edge_stream_format(const float* W, const float* b, std::vector<uint8_t>& out, float* kappa /*[NLAYER]*/) {
-    out.assign((size_t)NLAYER * NSLICE * 2 * A_SET_WORDS * 4, 0);
+    out.assign((size_t)NLAYER * NSLICE * A_SLICE_WORDS * 4, 0);
     uint32_t* o = reinterpret_cast<uint32_t*>(out.data());
     for (int l = 0; l < NLAYER; ++l) {
         float mx = 0.f;
@@ -544,31 +646,29 @@ void edge_stream_format(const float* W, const float* b, std::vector<uint8_t>& ou
         const float ascale = std::ldexp(1.0f, sA);
         kappa[l] = std::ldexp(1.0f, -(sA + B_SCALE_LOG2));
         for (int sl = 0; sl < NSLICE; ++sl)
-            for (int set = 0; set < 2; ++set)
-                for (int quarter = 0; quarter < 4; ++quarter) {
-                    if (set == 1 && quarter == 0) continue;    // unused rows stay zero
-                    const int part = set == 0 ? (quarter == 0 ? 0 : 1) : 2;
-                    for (int chn = 0; chn < SL; ++chn) {
-                        const int row = l * 3 * F + part * F + sl * SL + chn;
-                        __half kk[KH];
-                        for (int k = 0; k < KH; ++k) kk[k] = __float2half_rn(0.f);
-                        for (int k = 0; k < NK; ++k) {
-                            const float w = (k < NRBF ? W[(size_t)row * NRBF + k] : b[row]) * ascale;
-                            const __half h = __float2half_rn(w);
-                            const __half lo = __float2half_rn(w - __half2float(h));
-                            kk[k] = h;
-                            kk[NK + k] = h;
-                            kk[2 * NK + k] = lo;
-                        }
-                        uint32_t* dst = o + ((((size_t)l * NSLICE + sl) * 2 + set) * 128 + quarter * SL + chn) * 32;
-                        for (int c = 0; c < 32; ++c) {
-                            uint16_t h0, h1;
-                            memcpy(&h0, &kk[2 * c], 2);
-                            memcpy(&h1, &kk[2 * c + 1], 2);
-                            dst[c] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                        }
+            for (int quarter = 0; quarter < 4; ++quarter) {
+                const int part = quarter < 3 ? quarter : 2;
+                for (int chn = 0; chn < SL; ++chn) {
+                    const int row = l * 3 * F + part * F + sl * SL + chn;
+                    __half kk[KH];
+                    for (int k = 0; k < KH; ++k) kk[k] = __float2half_rn(0.f);
+                    for (int k = 0; k < NK; ++k) {
+                        const float w = (k < NRBF ? W[(size_t)row * NRBF + k] : b[row]) * ascale;
+                        const __half h = __float2half_rn(w);
+                        const __half lo = __float2half_rn(w - __half2float(h));
+                        kk[k] = h;
+                        kk[NK + k] = h;
+                        kk[2 * NK + k] = lo;
+                    }
+                    uint32_t* dst = o + (((size_t)l * NSLICE + sl) * 128 + quarter * SL + chn) * 32;
+                    for (int c = 0; c < 32; ++c) {
+                        uint16_t h0, h1;
+                        memcpy(&h0, &kk[2 * c], 2);
+                        memcpy(&h1, &kk[2 * c + 1], 2);
+                        dst[c] = (uint32_t)h0 | ((uint32_t)h1 << 16);
                     }
                 }
+            }
     }
 }
 
@@ -587,7 +687,7 @@ int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_
         e->tile_ctr.ensure(8))
         return 1;
     RLVD_CUDA(cudaMemsetAsync(e->tile_ctr.p, 0, 8, s));
-    Span sp(e, s, FAM_EDGE);
+    Span sp(e, s, FAM_PACK);
     edge_pack_kernel<<<n_struct, 256, 0, s>>>(n_struct, node_ptr, row_ptr, col, shift, pos, cell, e->w.freqs, e->w.feps,
                                               e->w.cutoff, e->tile_ctr.as<int>(), (int)cap, e->tiles.as<uint8_t>(),
                                               e->pipe_info.as<int4>(), e->tile_ctr.as<int>() + 1);
@@ -607,7 +707,7 @@ int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, 
                                        (int)stream_smem_bytes<true>(MAXN)));
         attr_set = true;
     }
-    const uint32_t* af = reinterpret_cast<const uint32_t*>(e->w.filt_E) + (size_t)layer * NSLICE * 2 * A_SET_WORDS;
+    const uint32_t* af = reinterpret_cast<const uint32_t*>(e->w.filt_E) + (size_t)layer * NSLICE * A_SLICE_WORDS;
     const float kappa = e->w.filt_kappa[layer];
     // both variants request the HAS_MU footprint: one CTA per SM (each CTA owns all 512 TMEM columns)
     const size_t smem = stream_smem_bytes<true>(max_struct_nodes) < 120 * 1024 ? 120 * 1024 : stream_smem_bytes<true>(max_struct_nodes);

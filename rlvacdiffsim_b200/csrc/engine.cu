@@ -549,7 +549,7 @@ static int drain_spans(rlvd_engine* e) {
 int rlvd_profile_read(rlvd_engine* e, const char* family, double* ms_total, int64_t* launches) {
     RLVD_CHECK(e != nullptr && family != nullptr, "bad argument");
     if (drain_spans(e)) return 1;
-    static const char* names[FAM_COUNT] = {"neighbor", "edge", "node", "readout"};
+    static const char* names[FAM_COUNT] = {"neighbor", "edge", "node", "readout", "edge_pack"};
     for (int f = 0; f < FAM_COUNT; ++f)
         if (strcmp(names[f], family) == 0) {
             if (ms_total) *ms_total = e->prof_ms[f];

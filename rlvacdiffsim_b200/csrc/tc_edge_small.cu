@@ -504,7 +504,7 @@ int launch_edge_geometry(rlvd_engine* e, cudaStream_t s, int M, int64_t n_edges,
                          const float* cell) {
     if (M <= 0 || n_edges <= 0) return 0;
     if (e->geom.ensure((size_t)n_edges * 128)) return 1;
-    Span sp(e, s, FAM_EDGE);
+    Span sp(e, s, FAM_PACK);
     edge_geom_kernel<<<(M + 7) / 8, 256, 0, s>>>(M, node_ptr, node_struct, row_ptr, col, shift, pos, cell, e->w.freqs,
                                                  e->w.feps, e->w.cutoff, e->geom.as<float4>());
     sp.end(1);
