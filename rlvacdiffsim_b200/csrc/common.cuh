@@ -112,7 +112,7 @@ struct rlvd_engine {
     bool finalized = false;
     // workspaces (grown on demand, never shrunk)
     rlvd::DevBuf x, mu0, mu1, hid, mix, nrm, vw, ctx, struct_edges, struct_edge_ptr, scratch, geom;
-    rlvd::DevBuf tiles, pipe_info, tile_ctr;       // edge stream (edge_stream.cu)
+    rlvd::DevBuf tiles, pipe_info, tile_ctr, stream_scratch;   // edge stream (edge_stream.cu)
     // host-path staging
     rlvd::DevBuf in_node_ptr, in_Z, in_pos, in_cell, in_inv, in_img, in_rs, in_ps, in_temp, in_qp;
     rlvd::DevBuf g_row_ptr, g_node_struct, g_col, g_shift, g_nedges, g_q, out_pack;

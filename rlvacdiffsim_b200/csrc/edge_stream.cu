@@ -9,10 +9,10 @@
 // edge_pack_kernel (once per call, one CTA per structure)
 //   Splits the structure's receivers into NPIPE contiguous ranges of equal edge-group count and writes, per range,
 //   a stream of 32-slot tiles.  Slots come in receiver-aligned groups of 8 (short rows padded with zero filters).
-//   A tile is 4096 B of MMA operand + 576 B of meta:
+//   A tile is 4096 B of MMA operand + 528 B of meta:
 //     operand  [32 slots][64 fp16], K-major core-matrix layout:  b_hi[21] | b_lo[21] | b_hi[21] | 0
 //              b = 2^10 * {phi_k(d) * fcut(d) (k < 20), fcut(d)}, split b = b_hi + b_lo in fp16 (22 significant bits)
-//     meta     j[32] (local sender index) | dir_x[32] | dir_y[32] | dir_z[32] | receiver[4] (one per group)
+//     meta     j[32] (local sender index) | dir_x[32] | dir_y[32] | dir_z[32] | new_receiver[4] u8 (one per group)
 //
 // edge_stream_kernel (per layer; CTA = one structure x one 32-channel slice; 1 CTA per SM)
 //   The slice of the structure's node table lives in shared memory (gathers never leave the SM):
@@ -20,15 +20,20 @@
 //   Filters run on tcgen05 with the weight operand resident in TMEM (A rows = dq | dmuR | dmumu | dmumu filters of
 //   the slice), pre-split on the host as a_hi[21] | a_hi[21] | a_lo[21] | 0 so that ONE K=64 fp16 MMA chain evaluates
 //   a_hi.b_hi + a_hi.b_lo + a_lo.b_hi (fp32-accurate, 4 dispatches):      D[128, 32 slots] = A . Bt
-//   A TMEM lane quarter can only be read by the warps with warp%4 == quarter, which fixes the roles:
-//        warp 0 (q)   : dq        += D * x_q[j]                  (+ bulk copies, MMA issue, and all global writes)
-//        warp 1 (R)   : dmuR_xyz  += D * x_R[j] * dir_xyz
-//        warp 2 (Mxy) : dmuM_xy   += D * (x_m mu_xy)[j]
-//        warp 3 (Mz)  : dmuM_z    += D * (x_m mu_z)[j]
+//   A TMEM lane quarter can only be read by the warps with warp%4 == quarter, so each of a pipeline's four warps
+//   takes the role whose filter rows sit in its quarter:
+//        role 0 (q)   : dq        += D * x_q[j]                  (+ bulk copies, MMA issue, and all global writes)
+//        role 1 (R)   : dmuR_xyz  += D * x_R[j] * dir_xyz
+//        role 2 (Mxy) : dmuM_xy   += D * (x_m mu_xy)[j]
+//        role 3 (Mz)  : dmuM_z    += D * (x_m mu_z)[j]
+//   warp%4 is also the SM sub-partition (issue scheduler) a warp runs on and the roles cost 45..85 issue slots per
+//   group, so the operand is kept in TMEM in four row rotations and pipeline p uses rotation p%4: every scheduler
+//   then hosts a mix of roles instead of one scheduler carrying all the R warps.
 //   The kernel is shared-memory-bandwidth bound (gathers 5 x 128 B per slot), so every sender row is gathered exactly
-//   once.  When a receiver's row ends, warps 1-3 drop their partial sums into a small shared-memory slot; warp 0 adds
-//   them to mu_in and writes mu_out one tile later, inside the window in which it would otherwise wait for the next
-//   tile's MMAs — the tile barriers already order those accesses, so the combine needs no synchronisation of its own.
+//   once.  When a receiver's row ends, warps 1-3 drop their partial sums into a per-SM scratch slot (55 KB per SM,
+//   L2-resident); warp 0 adds them to mu_in and writes mu_out one tile later — the tile barriers already order
+//   those accesses, so the combine needs no synchronisation of its own.  Accumulators (TMEM) and operand buffers
+//   are double-buffered: tile t+1's MMAs run while tile t is consumed.
 //   No atomics; sums run in CSR order (bitwise reproducible).  NPIPE such 4-warp pipelines run on disjoint receiver
 //   ranges; while one waits for its next tile the others fill the issue slots.  kappa = 2^-(sA+10) undoes the fp16
 //   range scaling exactly.
@@ -52,27 +57,41 @@ constexpr int GS = 8;                     // slots per receiver-aligned group
 constexpr int KH = 64;                    // fp16 k-extent of the split operands
 constexpr int NK = NRBF + 1;              // 21: 20 Bessel functions + the bias column (fcut)
 constexpr int TILE_B = TE * KH * 2;       // 4096
-constexpr int META = 528;                 // j[32] | dir[3][32] | recv[4]
+constexpr int META = 528;                 // j[32] i32 | dir[3][32] f32 | newrecv[4] u8 | pad[12]
+constexpr int META_DIR = 128;
+constexpr int META_FLAG = 512;
 constexpr int TILE_BYTES = TILE_B + META; // 4624
 constexpr int MAXN = 256;
 constexpr int ST_THREADS = NPIPE * 128;
 constexpr int B_SCALE_LOG2 = 10;
-constexpr int TM_D = 0;                   // TMEM columns: accumulator of pipe p at p*32
-constexpr int TM_A = NPIPE * TE;          // weight operand (64 fp16 = 32 columns)
-constexpr int TM_COLS = 256;
-constexpr int A_SLICE_WORDS = 128 * 32;   // u32 per (layer, slice)
-constexpr int NM_STAGE = 2;               // meta buffers per pipeline
+constexpr int TM_D = 0;                   // TMEM columns: accumulator buffer b of pipe p at (2p+b)*32
+constexpr int TM_A = NPIPE * 2 * TE;      // 4 row rotations of the weight operand (64 fp16 = 32 columns each)
+constexpr int NROT = 4;
+constexpr int TM_COLS = 512;
+constexpr int A_SLICE_WORDS = NROT * 128 * 32;   // u32 per (layer, slice): [rotation][row][32]
+constexpr int NB_STAGE = 2;               // operand buffers per pipeline
+constexpr int NM_STAGE = 3;               // meta buffers per pipeline
+constexpr int NP_STAGE = 4;               // partial-sum buffers per pipeline (tile t uses t % 4)
 constexpr int PART_ROWS = 6;              // partial-sum rows per finished receiver: R x,y,z | M x,y | M z
-constexpr int PART_SLOT = PART_ROWS * SL * 4;          // 768 B
-constexpr int PART_BYTES = 2 * (TE / GS) * PART_SLOT;  // [tile parity][<= 4 finished receivers per tile]
+constexpr int PART_SLOT = PART_ROWS * SL; // floats
+constexpr int PART_PIPE = NP_STAGE * (TE / GS) * PART_SLOT;   // floats per pipeline: [tile%4][<= 4 finished receivers]
+constexpr int PART_SM = NPIPE * PART_PIPE;                    // floats per SM (73,728 B)
+constexpr int MAX_SMID = 256;
+#ifndef RLVD_PF
+#define RLVD_PF 0
+#endif
+#ifndef RLVD_SPLIT
+#define RLVD_SPLIT 0
+#endif
+constexpr int PF_DIST = RLVD_PF;          // tiles between the L2 prefetch and the bulk copy of a tile (0 = off)
 constexpr float PI_F = 3.14159265358979323846f;
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TE >> 3) << 17) | (8u << 24);   // f16 x f16 -> f32, M=128, N=32
 
-static_assert(TM_A + 32 <= TM_COLS, "TMEM budget");
+static_assert(TM_A + NROT * 32 <= TM_COLS, "TMEM budget");
 
 struct StBars {
-    uint64_t b_full[NPIPE], mma_done[NPIPE], acc_free[NPIPE];
-    int chg[NPIPE][2][TE / GS];           // receivers finished in a tile, per tile parity
+    uint64_t b_full[NPIPE][NB_STAGE], mma_done[NPIPE][2], acc_free[NPIPE][2];
+    int chg[NPIPE][NP_STAGE][TE / GS];    // receivers finished in a tile (tile t uses slot t % 4)
     uint32_t tmem_base;
 };
 
@@ -158,9 +177,9 @@ __device__ __forceinline__ void write_slot(uint8_t* tile, int r, const uint4* ro
     for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(b + kc * 512) = row8[kc];
     uint8_t* m = tile + TILE_B;
     reinterpret_cast<int*>(m)[r] = j;
-    reinterpret_cast<float*>(m + 128)[r] = dx;
-    reinterpret_cast<float*>(m + 256)[r] = dy;
-    reinterpret_cast<float*>(m + 384)[r] = dz;
+    reinterpret_cast<float*>(m + META_DIR)[r] = dx;
+    reinterpret_cast<float*>(m + META_DIR + 128)[r] = dy;
+    reinterpret_cast<float*>(m + META_DIR + 256)[r] = dz;
 }
 
 __global__ void __launch_bounds__(256) edge_pack_kernel(int n_struct, const int* __restrict__ node_ptr,
@@ -259,7 +278,7 @@ __global__ void __launch_bounds__(256) edge_pack_kernel(int n_struct, const int*
             const int slot = slot0 + s;
             uint8_t* tile = tiles + (size_t)(tbeg[p] + (slot >> 5)) * TILE_BYTES;
             const int r = slot & 31;
-            if ((s & (GS - 1)) == 0) reinterpret_cast<int*>(tile + TILE_B + 512)[r >> 3] = i;
+            if ((s & (GS - 1)) == 0) tile[TILE_B + META_FLAG + (r >> 3)] = (uint8_t)(s == 0 && i > bnd[p] ? 1 : 0);   // new receiver starts
             if (s < rdeg) {
                 const int e = re0 + s;
                 const int jg = __ldg(col + e);
@@ -312,7 +331,7 @@ __global__ void __launch_bounds__(256) edge_pack_kernel(int n_struct, const int*
 #pragma unroll
             for (int kc = 0; kc < 8; ++kc) row8[kc] = z4;
             write_slot(tile, r, row8, 0, 0.f, 0.f, 0.f);
-            if ((r & (GS - 1)) == 0) reinterpret_cast<int*>(tile + TILE_B + 512)[r >> 3] = bnd[p + 1] - 1;
+            if ((r & (GS - 1)) == 0) tile[TILE_B + META_FLAG + (r >> 3)] = 0;
         }
     }
 }
@@ -332,30 +351,29 @@ __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
 
 struct PipeCtx {
     StBars* S;
-    int pipe, lane;
+    int pipe, lane, quarter;
     uint32_t tmem;
     const uint8_t* tab;      // node table of the slice
-    uint8_t* Bp;             // operand buffer
     uint8_t* MetaP;          // NM_STAGE meta buffers
-    float* Part;             // [2][4][PART_ROWS][32] partial sums of finished receivers
-    const uint8_t* tile_src;
+    float* Part;             // this SM's / pipeline's partial-sum scratch: [3][4][PART_ROWS][32] (global, L2-resident)
     int n_tiles, ra, rb, node0, ch;
+    long long* dbg;          // RLVD_TIMELINE: clock64 stamps of block 0 / pipeline 0
 };
 
 // warp 0: adds the partial sums of the receivers finished in a tile to mu_in and writes mu_out.
 template <bool HAS_MU>
 __device__ __forceinline__ void combine_mu(const PipeCtx& c, int buf, int count, const float* __restrict__ mu_in,
-                                           float* __restrict__ mu_out) {
+                                           float* __restrict__ mu_out, int first = 0) {
 #pragma unroll 1
-    for (int k = 0; k < count; ++k) {
+    for (int k = first; k < count; ++k) {
         const int i = c.S->chg[c.pipe][buf][k];
-        const float* P = c.Part + ((buf * (TE / GS) + k) * PART_ROWS) * SL + c.lane;
+        const float* P = c.Part + (buf * (TE / GS) + k) * PART_SLOT + c.lane;
         const int64_t o = (int64_t)(c.node0 + i) * 3 * F + c.ch;
-        float v0 = P[0], v1 = P[SL], v2 = P[2 * SL];
+        float v0 = __ldcg(P), v1 = __ldcg(P + SL), v2 = __ldcg(P + 2 * SL);
         if (HAS_MU) {
-            v0 += P[3 * SL] + __ldg(mu_in + o);
-            v1 += P[4 * SL] + __ldg(mu_in + o + F);
-            v2 += P[5 * SL] + __ldg(mu_in + o + 2 * F);
+            v0 += __ldcg(P + 3 * SL) + __ldg(mu_in + o);
+            v1 += __ldcg(P + 4 * SL) + __ldg(mu_in + o + F);
+            v2 += __ldcg(P + 5 * SL) + __ldg(mu_in + o + 2 * F);
         }
         mu_out[o] = v0;
         mu_out[o + F] = v1;
@@ -363,28 +381,68 @@ __device__ __forceinline__ void combine_mu(const PipeCtx& c, int buf, int count,
     }
 }
 
-// One warp of one pipeline.  ROLE = TMEM lane quarter (see the file header).  Tile t uses the pipeline's operand
-// buffer, meta buffer t%2, TMEM accumulator and partial-sum buffer t%2:
-//   warp 0 / lane 0:  wait b_full (bulk copies of tile t landed) and acc_free (all roles done with tile t-1)
-//                     -> issue the tile's 4 MMAs -> commit to mma_done
-//   warp 0:           write mu_out for the receivers finished in tile t-1 (overlaps the MMAs)
-//   all warps:        wait mma_done -> [warp 0 / lane 0: operand buffer is free again, bulk-copy tile t+1]
-//                     -> consume the tile's 4 groups -> arrive on acc_free
-// Every receiver of the range owns at least one group (edge_pack_kernel), so a receiver change is a plain
-// "drop finished row, start next row".
+__device__ __forceinline__ bool st_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+struct Feed {                // what the thread doing a pipeline's producer duty needs
+    const uint8_t* src;      // first tile of the pipeline
+    uint8_t* Bp;             // NB_STAGE operand buffers
+    uint64_t bdesc0;
+};
+
+__device__ __forceinline__ void feed_copy(const PipeCtx& c, const Feed& fd, int k) {
+    const uint8_t* sp = fd.src + (size_t)k * TILE_BYTES;
+    uint64_t* bar = &c.S->b_full[c.pipe][k & 1];
+    mbar_expect_tx(bar, TILE_BYTES);
+    bulk_g2s(fd.Bp + (k & 1) * TILE_B, sp, TILE_B, bar);
+    bulk_g2s(c.MetaP + (k % NM_STAGE) * META, sp + TILE_B, META, bar);
+    if (PF_DIST > 0 && k + PF_DIST < c.n_tiles) prefetch_l2(sp + (size_t)PF_DIST * TILE_BYTES, TILE_BYTES);   // HBM latency is paid here
+}
+__device__ __forceinline__ void feed_mma(const PipeCtx& c, const Feed& fd, int m) {
+    st_wait(&c.S->b_full[c.pipe][m & 1], ((uint32_t)m >> 1) & 1u);
+    tc_fence_after();
+    const uint32_t d = c.tmem + TM_D + (uint32_t)(c.pipe * 2 + (m & 1)) * TE;
+    const uint64_t bd = fd.bdesc0 + (uint64_t)((m & 1) * (TILE_B >> 4));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_f16_ts(d, c.tmem + TM_A + (c.pipe & 3) * 32 + k * 8, bd + (uint64_t)(k * 64), k);
+    umma_commit(&c.S->mma_done[c.pipe][m & 1]);
+}
+
+// One warp of one pipeline.  ROLE: see the file header; c.quarter = the warp's TMEM lane quarter.  Tile t uses operand
+// buffer t%2, TMEM accumulator t%2, meta buffer t%3, partial-sum buffer t%4; barriers / counters indexed t%2:
+//   wait mma_done(t) -> [role 0: write mu_out for the receivers finished in tile t-2] -> consume the tile's 4 groups
+//   -> arrive on acc_free(t); the pipeline's lightest warp without the mu_out duty (role 3, or role 0 in layer 0) then
+//   waits until every warp has left tile t and feeds the pipeline:
+//        issue the MMAs of tile t+2 (accumulator t%2 is free)         needs b_full(t+2): copy issued a tile earlier
+//        issue the bulk copies of tile t+3 into operand buffer (t+1)%2 needs mma_done(t+1): issued a tile earlier
+//                                                 and meta buffer t%3  free: everyone has left tile t
+//   Its own groups are the cheapest, so that wait falls into time it would spend idle anyway.
+// mma_done(t) implies every warp left tile t-2, so a warp runs at most one tile ahead of the slowest warp of its
+// pipeline and the partial sums of tile t-2 are complete when role 0 reads them.  Every receiver of the range owns at
+// least one group (edge_pack_kernel) and receivers are consecutive, so a receiver change is "drop row cur, start cur+1".
 template <bool HAS_MU, int ROLE>
-__device__ __forceinline__ void run_role(const PipeCtx& c, const float* __restrict__ mu_in, float* __restrict__ q,
-                                         float* __restrict__ mu_out) {
+__device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const float* __restrict__ mu_in,
+                                         float* __restrict__ q, float* __restrict__ mu_out) {
     constexpr int NB = Tab<HAS_MU>::NODE_BYTES;
     constexpr int NACC = ROLE == 0 ? 1 : ROLE == 1 ? 3 : ROLE == 2 ? 2 : 1;
     constexpr int T_OFF = ROLE == 0 ? 0 : ROLE == 1 ? SL * 4 : ROLE == 2 ? 2 * SL * 4 : 4 * SL * 4;
     constexpr int P_ROW = ROLE == 1 ? 0 : ROLE == 2 ? 3 : 5;
     constexpr int NG = TE / GS;
+    constexpr int PROD_ROLE = HAS_MU ? 3 : 0;   // the lightest role without the mu_out duty feeds the pipeline
     StBars* S = c.S;
     const int pipe = c.pipe, lane = c.lane, n_tiles = c.n_tiles;
     if (n_tiles <= 0 || c.ra >= c.rb) return;     // (a non-empty receiver range always has tiles)
 
-    const uint32_t dcol = c.tmem + ((uint32_t)(ROLE * 32) << 16) + TM_D + (uint32_t)pipe * TE;
+    const uint32_t dcol0 = c.tmem + ((uint32_t)(c.quarter * 32) << 16) + TM_D + (uint32_t)(pipe * 2) * TE;
     const uint8_t* tb = c.tab + lane * 4 + T_OFF;
     float* qp = q + ((int64_t)c.node0 * F + c.ch);
 
@@ -393,67 +451,78 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const float* __restri
 #pragma unroll
     for (int a = 0; a < NACC; ++a) acc[a][0] = acc[a][1] = 0.f;
     float qbase = ROLE == 0 ? qp[(int64_t)cur * F] : 0.f;
-    int nprev = 0;                            // receivers finished in the previous tile (warp 0 combines them)
+    int n1 = 0, n2 = 0;                       // receivers finished in tiles t-1 / t-2 (role 0 combines them)
 
-    uint64_t bdesc0 = 0;
-    if (ROLE == 0) {
-        bdesc0 = umma_desc(smem_u32(c.Bp), 512, 128);
-        if (lane == 0) {
-            mbar_expect_tx(&S->b_full[pipe], TILE_BYTES);
-            bulk_g2s(c.Bp, c.tile_src, TILE_B, &S->b_full[pipe]);
-            bulk_g2s(c.MetaP, c.tile_src + TILE_B, META, &S->b_full[pipe]);
-            if (n_tiles > 1) prefetch_l2(c.tile_src + TILE_BYTES, TILE_BYTES);
-            if (n_tiles > 2) prefetch_l2(c.tile_src + 2 * TILE_BYTES, TILE_BYTES);
+    if (ROLE == PROD_ROLE && lane == 0) {     // prologue: tiles 0, 1 in flight, tile 2 on its way
+        for (int k = 2; k < PF_DIST && k < n_tiles; ++k) prefetch_l2(fd.src + (size_t)k * TILE_BYTES, TILE_BYTES);
+        feed_copy(c, fd, 0);
+        if (n_tiles > 1) feed_copy(c, fd, 1);
+        feed_mma(c, fd, 0);
+        if (n_tiles > 1) feed_mma(c, fd, 1);
+        if (n_tiles > 2) {
+            st_wait(&S->mma_done[pipe][0], 0);
+            feed_copy(c, fd, 2);
         }
     }
-
+    int ms = 0, ps = 0;                       // t % 3, t % 4
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
-        const uint32_t par = (uint32_t)t & 1u;
-        if (ROLE == 0) {
-            if (lane == 0) {
-                st_wait(&S->b_full[pipe], par);                       // operand + meta of tile t landed
-                if (t > 0) st_wait(&S->acc_free[pipe], par ^ 1u);     // all roles are done with tile t-1
-                tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_f16_ts(c.tmem + TM_D + (uint32_t)pipe * TE, c.tmem + TM_A + k * 8, bdesc0 + (uint64_t)(k * 64), k);
-                umma_commit(&S->mma_done[pipe]);
-            }
-            __syncwarp();
-            combine_mu<HAS_MU>(c, par ^ 1, nprev, mu_in, mu_out);
-        }
-        st_wait(&S->mma_done[pipe], par);
+        const uint32_t bi = (uint32_t)t & 1u, ph = ((uint32_t)t >> 1) & 1u;
+#ifdef RLVD_TIMELINE
+#define RLVD_STAMP(k) if (c.dbg != nullptr && t < 64) c.dbg[(t * 4 + ROLE) * 6 + (k)] = clock64();
+#else
+#define RLVD_STAMP(k)
+#endif
+        RLVD_STAMP(0)
+        st_wait(&S->mma_done[pipe][bi], ph);
         tc_fence_after();
-        if (ROLE == 0 && lane == 0) {
-            if (t + 1 < n_tiles) {                                    // operand buffer is free again: fetch tile t+1
-                const uint8_t* src = c.tile_src + (size_t)(t + 1) * TILE_BYTES;
-                mbar_expect_tx(&S->b_full[pipe], TILE_BYTES);
-                bulk_g2s(c.Bp, src, TILE_B, &S->b_full[pipe]);
-                bulk_g2s(c.MetaP + (par ^ 1u) * META, src + TILE_B, META, &S->b_full[pipe]);
-            }
-            if (t + 3 < n_tiles) prefetch_l2(c.tile_src + (size_t)(t + 3) * TILE_BYTES, TILE_BYTES);
+        RLVD_STAMP(1)
+        // role 0: mu_out rows of the receivers finished in tile t-2.  The loads of the first one are issued here and
+        // consumed after this tile's groups (their L2 / HBM latency hides behind the tile); the rare further ones follow.
+        float cv[9];
+        int64_t co = 0;
+        const bool comb = RLVD_SPLIT && ROLE == 0 && t >= 2 && n2 > 0;
+        if (!RLVD_SPLIT && ROLE == 0 && t >= 2 && n2 > 0) {
+            if (lane == 0) st_wait(&S->acc_free[pipe][bi], ph ^ 1u);
+            __syncwarp();
+            combine_mu<HAS_MU>(c, (ps + 2) & 3, n2, mu_in, mu_out);
         }
-        const uint8_t* meta = c.MetaP + par * META;
-        float* part = c.Part + (par * NG * PART_ROWS + P_ROW) * SL + lane;
+        if (comb) {
+            if (lane == 0) st_wait(&S->acc_free[pipe][bi], ph ^ 1u);   // already complete: acquires the partial sums of tile t-2
+            __syncwarp();
+            const int cb = (ps + 2) & 3;
+            const int i = S->chg[pipe][cb][0];
+            const float* P = c.Part + (cb * NG) * PART_SLOT + lane;
+            co = (int64_t)(c.node0 + i) * 3 * F + c.ch;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                cv[r] = __ldcg(P + r * SL);
+                cv[3 + r] = HAS_MU ? __ldcg(P + (3 + r) * SL) : 0.f;
+                cv[6 + r] = HAS_MU ? __ldg(mu_in + co + r * F) : 0.f;
+            }
+        }
+        RLVD_STAMP(2)
+        const uint8_t* meta = c.MetaP + ms * META;
+        float* part = c.Part + (ps * NG * PART_ROWS + P_ROW) * SL + lane;
+        const uint32_t dcol = dcol0 + bi * TE;
+        const uint32_t flagw = *reinterpret_cast<const uint32_t*>(meta + META_FLAG);
         int nchg = 0;
 #pragma unroll
         for (int gg = 0; gg < NG; ++gg) {
             uint32_t f[8];
             tmem_ld8(dcol + gg * GS, f);
             const int4 ja = *reinterpret_cast<const int4*>(meta + gg * 32), jb = *reinterpret_cast<const int4*>(meta + gg * 32 + 16);
-            const int recv = *reinterpret_cast<const int*>(meta + 512 + gg * 4);
+            const int jo[8] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
             float dr[3][8];
             if (ROLE == 1) {
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
-                    const float4 da = *reinterpret_cast<const float4*>(meta + 128 + a * 128 + gg * 32);
-                    const float4 db = *reinterpret_cast<const float4*>(meta + 128 + a * 128 + gg * 32 + 16);
+                    const float4 da = *reinterpret_cast<const float4*>(meta + META_DIR + a * 128 + gg * 32);
+                    const float4 db = *reinterpret_cast<const float4*>(meta + META_DIR + a * 128 + gg * 32 + 16);
                     dr[a][0] = da.x; dr[a][1] = da.y; dr[a][2] = da.z; dr[a][3] = da.w;
                     dr[a][4] = db.x; dr[a][5] = db.y; dr[a][6] = db.z; dr[a][7] = db.w;
                 }
             }
-            const int jo[8] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
             float t1[8], t2[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -461,17 +530,17 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const float* __restri
                 t1[u] = *reinterpret_cast<const float*>(row);
                 if (ROLE == 2) t2[u] = *reinterpret_cast<const float*>(row + SL * 4);
             }
-            if (recv != cur) {                                     // receiver change (groups are receiver-aligned)
+            if ((flagw >> (8 * gg)) & 0xffu) {                       // this group starts the next receiver
                 if (ROLE == 0) {
                     qp[(int64_t)cur * F] = qbase + (acc[0][0] + acc[0][1]);
-                    qbase = qp[(int64_t)recv * F];
-                    if (lane == 0) S->chg[pipe][par][nchg] = cur;
+                    qbase = qp[(int64_t)(cur + 1) * F];
+                    if (lane == 0) S->chg[pipe][ps][nchg] = cur;
                 } else {
 #pragma unroll
                     for (int a = 0; a < NACC; ++a) part[(nchg * PART_ROWS + a) * SL] = acc[a][0] + acc[a][1];
                 }
                 ++nchg;
-                cur = recv;
+                ++cur;
 #pragma unroll
                 for (int a = 0; a < NACC; ++a) acc[a][0] = acc[a][1] = 0.f;
             }
@@ -492,57 +561,84 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const float* __restri
                 }
             }
         }
-        nprev = nchg;
+        if (comb) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) mu_out[co + r * F] = cv[r] + cv[3 + r] + cv[6 + r];
+            if (n2 > 1) combine_mu<HAS_MU>(c, (ps + 2) & 3, n2, mu_in, mu_out, 1);
+        }
+        RLVD_STAMP(3)
+        n2 = n1;
+        n1 = nchg;
+        ms = ms + 1 == NM_STAGE ? 0 : ms + 1;
+        ps = (ps + 1) & 3;
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&S->acc_free[pipe]);
+        if (lane == 0) {
+            mbar_arrive(&S->acc_free[pipe][bi]);
+            if (ROLE == PROD_ROLE && t + 2 < n_tiles) {                   // producer duty for tiles t+2 / t+3
+                st_wait(&S->acc_free[pipe][bi], ph);                      // every warp has left tile t
+                feed_mma(c, fd, t + 2);
+                if (t + 3 < n_tiles) {
+                    st_wait(&S->mma_done[pipe][bi ^ 1u], (((uint32_t)t + 1u) >> 1) & 1u);
+                    feed_copy(c, fd, t + 3);
+                }
+            }
+        }
     }
-    // ---- the receiver still in flight: drop its sums into the other parity's slot 0 once every role has left the
-    //      last tile (warp 0 has then finished reading that buffer), then let warp 0 write the remaining rows
-    const uint32_t lastpar = (uint32_t)(n_tiles - 1) & 1u;
-    st_wait(&S->acc_free[pipe], lastpar);
+    // ---- the receiver still in flight: once every role has left the last tile, drop its sums into slot 0 of the
+    //      next partial buffer; role 0 then writes the rows of the last two tiles and that one
+    const uint32_t lb = (uint32_t)(n_tiles - 1) & 1u, lph = ((uint32_t)(n_tiles - 1) >> 1) & 1u;
+    st_wait(&S->acc_free[pipe][lb], lph);
     if (ROLE == 0) {
         qp[(int64_t)cur * F] = qbase + (acc[0][0] + acc[0][1]);
-        if (lane == 0) S->chg[pipe][lastpar ^ 1u][0] = cur;
+        if (lane == 0) S->chg[pipe][ps][0] = cur;
     } else {
-        float* part = c.Part + ((lastpar ^ 1u) * NG * PART_ROWS + P_ROW) * SL + lane;
+        float* part = c.Part + (ps * NG * PART_ROWS + P_ROW) * SL + lane;
 #pragma unroll
         for (int a = 0; a < NACC; ++a) part[a * SL] = acc[a][0] + acc[a][1];
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&S->acc_free[pipe]);
+    if (lane == 0) mbar_arrive(&S->acc_free[pipe][lb ^ 1u]);
     if (ROLE == 0) {
-        st_wait(&S->acc_free[pipe], lastpar ^ 1u);
-        combine_mu<HAS_MU>(c, (int)lastpar, nprev, mu_in, mu_out);
-        combine_mu<HAS_MU>(c, (int)(lastpar ^ 1u), 1, mu_in, mu_out);
+        st_wait(&S->acc_free[pipe][lb ^ 1u], ((uint32_t)n_tiles >> 1) & 1u);
+        if (n_tiles >= 2) combine_mu<HAS_MU>(c, (ps + 2) & 3, n2, mu_in, mu_out);
+        combine_mu<HAS_MU>(c, (ps + 3) & 3, n1, mu_in, mu_out);
+        combine_mu<HAS_MU>(c, ps, 1, mu_in, mu_out);
     }
 }
 
 template <bool HAS_MU>
 __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
-    int n_max, const int* __restrict__ node_ptr, const uint32_t* __restrict__ Afmt /* [4 slices][128][32] */,
-    float kappa, const int4* __restrict__ pipe_info, const uint8_t* __restrict__ tiles, const float* __restrict__ x,
-    const float* __restrict__ mu_in, float* __restrict__ q, float* __restrict__ mu_out) {
+    int n_max, const int* __restrict__ node_ptr, const uint32_t* __restrict__ Afmt /* [4 slices][4 rotations][128][32] */,
+    float kappa, const int4* __restrict__ pipe_info, const uint8_t* __restrict__ tiles, float* __restrict__ scratch,
+    const float* __restrict__ x, const float* __restrict__ mu_in, float* __restrict__ q, float* __restrict__ mu_out,
+    long long* dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int NB = Tab<HAS_MU>::NODE_BYTES;
     constexpr int NROLE = HAS_MU ? 4 : 2;           // layer 0 (mu == 0) has no dmumu term: warps 2, 3 idle
     uint8_t* TabS = smem;
     const uint32_t tab_bytes = ((uint32_t)n_max * NB + 127u) & ~127u;
     uint8_t* Bs = smem + tab_bytes;
-    uint8_t* MetaS = Bs + NPIPE * TILE_B;
-    float* PartS = reinterpret_cast<float*>(MetaS + NPIPE * NM_STAGE * META);
-    StBars* S = reinterpret_cast<StBars*>(reinterpret_cast<uint8_t*>(PartS) + NPIPE * PART_BYTES);
+    uint8_t* MetaS = Bs + NPIPE * NB_STAGE * TILE_B;
+    StBars* S = reinterpret_cast<StBars*>(MetaS + NPIPE * NM_STAGE * META);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x / NSLICE, slice = blockIdx.x % NSLICE;
     const int node0 = __ldg(node_ptr + g), n = __ldg(node_ptr + g + 1) - node0;
+    uint32_t smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (smid >= MAX_SMID) {
+        if (tid == 0) printf("rlvd: edge_stream: smid %u exceeds the scratch table\n", smid);
+        __trap();
+    }
 
     if (tid == 0) {
-        for (int p = 0; p < NPIPE; ++p) {
-            mbar_init(&S->b_full[p], 1);
-            mbar_init(&S->mma_done[p], 1);
-            mbar_init(&S->acc_free[p], NROLE);
-        }
+        for (int p = 0; p < NPIPE; ++p)
+            for (int k = 0; k < 2; ++k) {
+                mbar_init(&S->b_full[p][k], 1);
+                mbar_init(&S->mma_done[p][k], 1);
+                mbar_init(&S->acc_free[p][k], NROLE);
+            }
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(&S->tmem_base, TM_COLS);
@@ -573,15 +669,18 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     tc_fence_after();
     const uint32_t tmem = S->tmem_base;
 
-    // ---- weight operand -> TMEM (lane = filter row; 64 fp16 = 32 columns)
+    // ---- weight operand -> TMEM in its four row rotations (lane = filter row; 64 fp16 = 32 columns each)
     if (warp < 4) {
-        const uint4* wrow = reinterpret_cast<const uint4*>(Afmt + ((size_t)slice * 128 + warp * 32 + lane) * 32);
-        const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + TM_A;
+#pragma unroll 1
+        for (int rot = 0; rot < NROT; ++rot) {
+            const uint4* wrow = reinterpret_cast<const uint4*>(Afmt + ((size_t)(slice * NROT + rot) * 128 + warp * 32 + lane) * 32);
+            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + TM_A + rot * 32;
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-            const uint4 w0 = __ldg(wrow + 2 * c8), w1 = __ldg(wrow + 2 * c8 + 1);
-            const uint32_t v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-            tmem_st8(ta + c8 * 8, v);
+            for (int c8 = 0; c8 < 4; ++c8) {
+                const uint4 w0 = __ldg(wrow + 2 * c8), w1 = __ldg(wrow + 2 * c8 + 1);
+                const uint32_t v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                tmem_st8(ta + c8 * 8, v);
+            }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
@@ -593,23 +692,27 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     c.S = S;
     c.pipe = warp >> 2;
     c.lane = lane;
+    c.quarter = warp & 3;
     c.tmem = tmem;
     c.tab = TabS;
-    c.Bp = Bs + c.pipe * TILE_B;
     c.MetaP = MetaS + c.pipe * NM_STAGE * META;
-    c.Part = PartS + c.pipe * (PART_BYTES / 4);
+    c.Part = scratch + (size_t)smid * PART_SM + (size_t)c.pipe * PART_PIPE;
     const int4 pi = __ldg(pipe_info + (size_t)g * NPIPE + c.pipe);
-    c.tile_src = tiles + (size_t)pi.x * TILE_BYTES;
     c.n_tiles = pi.y;
     c.ra = pi.z;
     c.rb = pi.w;
     c.node0 = node0;
     c.ch = slice * SL + lane;
-    const int role = warp & 3;
-    if (role == 0) run_role<HAS_MU, 0>(c, mu_in, q, mu_out);
-    else if (role == 1) run_role<HAS_MU, 1>(c, mu_in, q, mu_out);
-    else if (HAS_MU && role == 2) run_role<HAS_MU, 2>(c, mu_in, q, mu_out);
-    else if (HAS_MU) run_role<HAS_MU, 3>(c, mu_in, q, mu_out);
+    c.dbg = (blockIdx.x == 0 && c.pipe == 0 && lane == 0) ? dbg : nullptr;
+    const int role = ((warp & 3) + c.pipe) & 3;      // rotation pipe%4 puts this role's filter rows in this warp's quarter
+    Feed fd;
+    fd.src = tiles + (size_t)pi.x * TILE_BYTES;
+    fd.Bp = Bs + c.pipe * NB_STAGE * TILE_B;
+    fd.bdesc0 = umma_desc(smem_u32(fd.Bp), 512, 128);
+    if (role == 0) run_role<HAS_MU, 0>(c, fd, mu_in, q, mu_out);
+    else if (role == 1) run_role<HAS_MU, 1>(c, fd, mu_in, q, mu_out);
+    else if (HAS_MU && role == 2) run_role<HAS_MU, 2>(c, fd, mu_in, q, mu_out);
+    else if (HAS_MU) run_role<HAS_MU, 3>(c, fd, mu_in, q, mu_out);
 
     tc_fence_before();
     __syncthreads();
@@ -622,14 +725,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
 template <bool HAS_MU>
 size_t stream_smem_bytes(int n_max) {
     const size_t tab = ((size_t)n_max * Tab<HAS_MU>::NODE_BYTES + 127) & ~(size_t)127;
-    return tab + (size_t)NPIPE * TILE_B + (size_t)NPIPE * NM_STAGE * META + (size_t)NPIPE * PART_BYTES + sizeof(StBars);
+    return tab + (size_t)NPIPE * NB_STAGE * TILE_B + (size_t)NPIPE * NM_STAGE * META + sizeof(StBars);
 }
 
 }  // namespace
 
 // Host: per layer, per 32-channel slice, the 128-row weight operand in the TMEM image the kernel stores verbatim:
 // row = 32 u32 = 64 fp16 = a_hi[21] | a_hi[21] | a_lo[21] | 0 with a = 2^sA * {filter_net weight (k < 20), bias}.
-// Row quarters: dq | dmuR | dmumu | dmumu filters of the slice.
+// Row quarters of rotation r: the filters of role (quarter + r) % 4 (roles: dq | dmuR | dmumu | dmumu).
 // kappa[l] = 2^-(sA_l + 10) undoes the operand scaling (applied to the node table).
 void edge_stream_format(const float* W, const float* b, std::vector<uint8_t>& out, float* kappa /*[NLAYER]*/) {
     out.assign((size_t)NLAYER * NSLICE * A_SLICE_WORDS * 4, 0);
@@ -646,8 +749,10 @@ void edge_stream_format(const float* W, const float* b, std::vector<uint8_t>& ou
         const float ascale = std::ldexp(1.0f, sA);
         kappa[l] = std::ldexp(1.0f, -(sA + B_SCALE_LOG2));
         for (int sl = 0; sl < NSLICE; ++sl)
+          for (int rot = 0; rot < NROT; ++rot)
             for (int quarter = 0; quarter < 4; ++quarter) {
-                const int part = quarter < 3 ? quarter : 2;
+                const int role = (quarter + rot) & 3;          // pipeline p = rot (mod 4): warp quarter -> role
+                const int part = role < 3 ? role : 2;
                 for (int chn = 0; chn < SL; ++chn) {
                     const int row = l * 3 * F + part * F + sl * SL + chn;
                     __half kk[KH];
@@ -660,7 +765,7 @@ void edge_stream_format(const float* W, const float* b, std::vector<uint8_t>& ou
                         kk[NK + k] = h;
                         kk[2 * NK + k] = lo;
                     }
-                    uint32_t* dst = o + (((size_t)l * NSLICE + sl) * 128 + quarter * SL + chn) * 32;
+                    uint32_t* dst = o + ((((size_t)l * NSLICE + sl) * NROT + rot) * 128 + quarter * SL + chn) * 32;
                     for (int c = 0; c < 32; ++c) {
                         uint16_t h0, h1;
                         memcpy(&h0, &kk[2 * c], 2);
@@ -707,17 +812,42 @@ int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, 
                                        (int)stream_smem_bytes<true>(MAXN)));
         attr_set = true;
     }
+    if (e->stream_scratch.ensure((size_t)MAX_SMID * PART_SM * sizeof(float))) return 1;
+    float* scr = e->stream_scratch.as<float>();
     const uint32_t* af = reinterpret_cast<const uint32_t*>(e->w.filt_E) + (size_t)layer * NSLICE * A_SLICE_WORDS;
     const float kappa = e->w.filt_kappa[layer];
     // both variants request the HAS_MU footprint: one CTA per SM (each CTA owns all 512 TMEM columns)
     const size_t smem = stream_smem_bytes<true>(max_struct_nodes) < 120 * 1024 ? 120 * 1024 : stream_smem_bytes<true>(max_struct_nodes);
+    long long* dbg = nullptr;
+#ifdef RLVD_TIMELINE   // in-kernel timeline of block 0 / pipeline 0 (build with RLVD_EXTRA_NVCC_FLAGS=-DRLVD_TIMELINE)
+    static long long* dbg_buf = nullptr;
+    static int dbg_calls = 0;
+    if (dbg_buf == nullptr) { cudaMalloc(&dbg_buf, 64 * 4 * 6 * 8); cudaMemset(dbg_buf, 0, 64 * 4 * 6 * 8); }
+    dbg = dbg_buf;
+#endif
     Span sp(e, s, FAM_EDGE);
     if (mu_in == nullptr)
         edge_stream_kernel<false><<<n_struct * NSLICE, ST_THREADS, smem, s>>>(
-            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), x, nullptr, q, mu_out);
+            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, nullptr, q, mu_out, nullptr);
     else
         edge_stream_kernel<true><<<n_struct * NSLICE, ST_THREADS, smem, s>>>(
-            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), x, mu_in, q, mu_out);
+            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, mu_in, q, mu_out, dbg);
+#ifdef RLVD_TIMELINE
+    if (mu_in != nullptr && ++dbg_calls == 20) {
+        cudaStreamSynchronize(s);
+        static long long h[64 * 4 * 6];
+        cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        const long long t0 = h[0];
+        for (int t = 0; t < 40; ++t) {
+            printf("tile %2d |", t);
+            for (int r = 0; r < 4; ++r) {
+                const long long* w = h + (t * 4 + r) * 6;
+                printf(" R%d top %7lld wait +%5lld combine +%5lld consume +%5lld |", r, w[0] - t0, w[1] - w[0], w[2] - w[1], w[3] - w[2]);
+            }
+            printf("\n");
+        }
+    }
+#endif
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;
