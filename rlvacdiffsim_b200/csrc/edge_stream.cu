@@ -9,10 +9,10 @@
 // edge_pack_kernel (once per call, one CTA per structure)
 //   Splits the structure's receivers into NPIPE contiguous ranges of equal edge-group count and writes, per range,
 //   a stream of 32-slot tiles.  Slots come in receiver-aligned groups of 8 (short rows padded with zero filters).
-//   A tile is 4096 B of MMA operand + 528 B of meta:
+//   A tile is 4096 B of MMA operand + 432 B of meta:
 //     operand  [32 slots][64 fp16], K-major core-matrix layout:  b_hi[21] | b_lo[21] | b_hi[21] | 0
 //              b = 2^10 * {phi_k(d) * fcut(d) (k < 20), fcut(d)}, split b = b_hi + b_lo in fp16 (22 significant bits)
-//     meta     j[32] (local sender index) | dir_x[32] | dir_y[32] | dir_z[32] | new_receiver[4] u8 (one per group)
+//     meta     j[32] u8 (local sender index) | new_receiver[4] u8 (one per group) | pad | dir_x[32] | dir_y[32] | dir_z[32]
 //
 // edge_stream_kernel (per layer; CTA = one structure x one 32-channel slice; 1 CTA per SM)
 //   The slice of the structure's node table lives in shared memory (gathers never leave the SM):
@@ -22,11 +22,11 @@
 //   a_hi.b_hi + a_hi.b_lo + a_lo.b_hi (fp32-accurate, 4 dispatches):      D[128, 32 slots] = A . Bt
 //   A TMEM lane quarter can only be read by the warps with warp%4 == quarter, so each of a pipeline's four warps
 //   takes the role whose filter rows sit in its quarter:
-//        role 0 (q)   : dq        += D * x_q[j]                  (+ bulk copies, MMA issue, and all global writes)
+//        role 0 (q)   : dq        += D * x_q[j]                  (+ all global writes)
 //        role 1 (R)   : dmuR_xyz  += D * x_R[j] * dir_xyz
-//        role 2 (Mxy) : dmuM_xy   += D * (x_m mu_xy)[j]
-//        role 3 (Mz)  : dmuM_z    += D * (x_m mu_z)[j]
-//   warp%4 is also the SM sub-partition (issue scheduler) a warp runs on and the roles cost 45..85 issue slots per
+//        role 2 (M)   : dmuM_xyz  += D * (x_m mu_xyz)[j]
+//        role 3       : no rows; one thread feeds the pipeline (bulk copies, tcgen05.mma issue, commits)
+//   warp%4 is also the SM sub-partition (issue scheduler) a warp runs on and the roles cost 0..85 issue slots per
 //   group, so the operand is kept in TMEM in four row rotations and pipeline p uses rotation p%4: every scheduler
 //   then hosts a mix of roles instead of one scheduler carrying all the R warps.
 //   The kernel is shared-memory-bandwidth bound (gathers 5 x 128 B per slot), so every sender row is gathered exactly
@@ -57,10 +57,10 @@ constexpr int GS = 8;                     // slots per receiver-aligned group
 constexpr int KH = 64;                    // fp16 k-extent of the split operands
 constexpr int NK = NRBF + 1;              // 21: 20 Bessel functions + the bias column (fcut)
 constexpr int TILE_B = TE * KH * 2;       // 4096
-constexpr int META = 528;                 // j[32] i32 | dir[3][32] f32 | newrecv[4] u8 | pad[12]
-constexpr int META_DIR = 128;
-constexpr int META_FLAG = 512;
-constexpr int TILE_BYTES = TILE_B + META; // 4624
+constexpr int META = 432;                 // j[32] u8 | newrecv[4] u8 | pad[12] | dir[3][32] f32
+constexpr int META_DIR = 48;
+constexpr int META_FLAG = 32;
+constexpr int TILE_BYTES = TILE_B + META; // 4528
 constexpr int MAXN = 256;
 constexpr int ST_THREADS = NPIPE * 128;
 constexpr int B_SCALE_LOG2 = 10;
@@ -70,7 +70,7 @@ constexpr int NROT = 4;
 constexpr int TM_COLS = 512;
 constexpr int A_SLICE_WORDS = NROT * 128 * 32;   // u32 per (layer, slice): [rotation][row][32]
 constexpr int NB_STAGE = 2;               // operand buffers per pipeline
-constexpr int NM_STAGE = 3;               // meta buffers per pipeline
+constexpr int NM_STAGE = 5;               // meta buffers per pipeline (tiles t-? .. t+4 in flight)
 constexpr int NP_STAGE = 4;               // partial-sum buffers per pipeline (tile t uses t % 4)
 constexpr int PART_ROWS = 6;              // partial-sum rows per finished receiver: R x,y,z | M x,y | M z
 constexpr int PART_SLOT = PART_ROWS * SL; // floats
@@ -176,7 +176,7 @@ __device__ __forceinline__ void write_slot(uint8_t* tile, int r, const uint4* ro
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(b + kc * 512) = row8[kc];
     uint8_t* m = tile + TILE_B;
-    reinterpret_cast<int*>(m)[r] = j;
+    m[r] = (uint8_t)j;
     reinterpret_cast<float*>(m + META_DIR)[r] = dx;
     reinterpret_cast<float*>(m + META_DIR + 128)[r] = dy;
     reinterpret_cast<float*>(m + META_DIR + 256)[r] = dz;
@@ -381,18 +381,6 @@ __device__ __forceinline__ void combine_mu(const PipeCtx& c, int buf, int count,
     }
 }
 
-__device__ __forceinline__ bool st_test(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-
 struct Feed {                // what the thread doing a pipeline's producer duty needs
     const uint8_t* src;      // first tile of the pipeline
     uint8_t* Bp;             // NB_STAGE operand buffers
@@ -417,27 +405,57 @@ __device__ __forceinline__ void feed_mma(const PipeCtx& c, const Feed& fd, int m
     umma_commit(&c.S->mma_done[c.pipe][m & 1]);
 }
 
-// One warp of one pipeline.  ROLE: see the file header; c.quarter = the warp's TMEM lane quarter.  Tile t uses operand
-// buffer t%2, TMEM accumulator t%2, meta buffer t%3, partial-sum buffer t%4; barriers / counters indexed t%2:
+// The pipeline's fourth warp (one thread of it) only feeds the other three.  Tile t uses operand buffer t%2, TMEM
+// accumulator t%2, meta buffer t%5; barriers indexed t%2 complete their (t/2)-th phase with tile t.  Every step costs
+// this thread 100-450 cycles of issue latency (mbarrier try_wait ~120, four tcgen05.mma + commit ~420, bulk copies
+// ~450: measured, profiles/timeline_r01.txt), ~1300 per tile — which is why no consuming warp carries it:
+//   wait acc_free(t)  (every consumer has left tile t: accumulator t%2 is free)
+//   wait b_full(t+2), issue the MMAs of tile t+2, commit -> mma_done(t+2)
+//   wait mma_done(t+2) (operand buffer t%2 read), bulk-copy tile t+4 into it and into meta buffer (t+4)%5 (last used
+//   by tile t-1): a copy gets two tile periods to cover its HBM latency.
+__device__ __forceinline__ void run_feeder(const PipeCtx& c, const Feed& fd) {
+    StBars* S = c.S;
+    const int pipe = c.pipe, n_tiles = c.n_tiles;
+    if (n_tiles <= 0 || c.ra >= c.rb || c.lane != 0) return;
+    feed_copy(c, fd, 0);
+    if (n_tiles > 1) feed_copy(c, fd, 1);
+    feed_mma(c, fd, 0);
+    if (n_tiles > 1) feed_mma(c, fd, 1);
+    if (n_tiles > 2) {
+        st_wait(&S->mma_done[pipe][0], 0);
+        feed_copy(c, fd, 2);
+    }
+    if (n_tiles > 3) {
+        st_wait(&S->mma_done[pipe][1], 0);
+        feed_copy(c, fd, 3);
+    }
+#pragma unroll 1
+    for (int t = 0; t + 2 < n_tiles; ++t) {
+        const uint32_t bi = (uint32_t)t & 1u;
+        st_wait(&S->acc_free[pipe][bi], ((uint32_t)t >> 1) & 1u);
+        feed_mma(c, fd, t + 2);
+        if (t + 4 < n_tiles) {
+            st_wait(&S->mma_done[pipe][bi], (((uint32_t)t + 2u) >> 1) & 1u);
+            feed_copy(c, fd, t + 4);
+        }
+    }
+}
+
+// One consuming warp of one pipeline.  ROLE: see the file header; c.quarter = the warp's TMEM lane quarter.  Tile t
+// uses TMEM accumulator t%2, meta buffer t%5, partial-sum buffer t%4; barriers indexed t%2:
 //   wait mma_done(t) -> [role 0: write mu_out for the receivers finished in tile t-2] -> consume the tile's 4 groups
-//   -> arrive on acc_free(t); the pipeline's lightest warp without the mu_out duty (role 3, or role 0 in layer 0) then
-//   waits until every warp has left tile t and feeds the pipeline:
-//        issue the MMAs of tile t+2 (accumulator t%2 is free)         needs b_full(t+2): copy issued a tile earlier
-//        issue the bulk copies of tile t+3 into operand buffer (t+1)%2 needs mma_done(t+1): issued a tile earlier
-//                                                 and meta buffer t%3  free: everyone has left tile t
-//   Its own groups are the cheapest, so that wait falls into time it would spend idle anyway.
-// mma_done(t) implies every warp left tile t-2, so a warp runs at most one tile ahead of the slowest warp of its
+//   -> arrive on acc_free(t)
+// mma_done(t) implies every consumer left tile t-2, so a warp runs at most one tile ahead of the slowest warp of its
 // pipeline and the partial sums of tile t-2 are complete when role 0 reads them.  Every receiver of the range owns at
 // least one group (edge_pack_kernel) and receivers are consecutive, so a receiver change is "drop row cur, start cur+1".
 template <bool HAS_MU, int ROLE>
 __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const float* __restrict__ mu_in,
                                          float* __restrict__ q, float* __restrict__ mu_out) {
     constexpr int NB = Tab<HAS_MU>::NODE_BYTES;
-    constexpr int NACC = ROLE == 0 ? 1 : ROLE == 1 ? 3 : ROLE == 2 ? 2 : 1;
-    constexpr int T_OFF = ROLE == 0 ? 0 : ROLE == 1 ? SL * 4 : ROLE == 2 ? 2 * SL * 4 : 4 * SL * 4;
-    constexpr int P_ROW = ROLE == 1 ? 0 : ROLE == 2 ? 3 : 5;
+    constexpr int NACC = ROLE == 0 ? 1 : 3;
+    constexpr int T_OFF = ROLE == 0 ? 0 : ROLE == 1 ? SL * 4 : 2 * SL * 4;
+    constexpr int P_ROW = ROLE == 1 ? 0 : 3;
     constexpr int NG = TE / GS;
-    constexpr int PROD_ROLE = HAS_MU ? 3 : 0;   // the lightest role without the mu_out duty feeds the pipeline
     StBars* S = c.S;
     const int pipe = c.pipe, lane = c.lane, n_tiles = c.n_tiles;
     if (n_tiles <= 0 || c.ra >= c.rb) return;     // (a non-empty receiver range always has tiles)
@@ -453,23 +471,12 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
     float qbase = ROLE == 0 ? qp[(int64_t)cur * F] : 0.f;
     int n1 = 0, n2 = 0;                       // receivers finished in tiles t-1 / t-2 (role 0 combines them)
 
-    if (ROLE == PROD_ROLE && lane == 0) {     // prologue: tiles 0, 1 in flight, tile 2 on its way
-        for (int k = 2; k < PF_DIST && k < n_tiles; ++k) prefetch_l2(fd.src + (size_t)k * TILE_BYTES, TILE_BYTES);
-        feed_copy(c, fd, 0);
-        if (n_tiles > 1) feed_copy(c, fd, 1);
-        feed_mma(c, fd, 0);
-        if (n_tiles > 1) feed_mma(c, fd, 1);
-        if (n_tiles > 2) {
-            st_wait(&S->mma_done[pipe][0], 0);
-            feed_copy(c, fd, 2);
-        }
-    }
-    int ms = 0, ps = 0;                       // t % 3, t % 4
+    int ms = 0, ps = 0;                       // t % NM_STAGE, t % 4
 #pragma unroll 1
     for (int t = 0; t < n_tiles; ++t) {
         const uint32_t bi = (uint32_t)t & 1u, ph = ((uint32_t)t >> 1) & 1u;
 #ifdef RLVD_TIMELINE
-#define RLVD_STAMP(k) if (c.dbg != nullptr && t < 64) c.dbg[(t * 4 + ROLE) * 6 + (k)] = clock64();
+#define RLVD_STAMP(k) if (c.dbg != nullptr && t < 64) c.dbg[(t * 4 + ROLE) * 10 + (k)] = clock64();
 #else
 #define RLVD_STAMP(k)
 #endif
@@ -511,8 +518,7 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
         for (int gg = 0; gg < NG; ++gg) {
             uint32_t f[8];
             tmem_ld8(dcol + gg * GS, f);
-            const int4 ja = *reinterpret_cast<const int4*>(meta + gg * 32), jb = *reinterpret_cast<const int4*>(meta + gg * 32 + 16);
-            const int jo[8] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
+            const uint2 jw = *reinterpret_cast<const uint2*>(meta + gg * GS);
             float dr[3][8];
             if (ROLE == 1) {
 #pragma unroll
@@ -523,12 +529,15 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
                     dr[a][4] = db.x; dr[a][5] = db.y; dr[a][6] = db.z; dr[a][7] = db.w;
                 }
             }
-            float t1[8], t2[8];
+            float t1[8], t2[8], t3[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const uint8_t* row = tb + jo[u] * NB;
+                const uint8_t* row = tb + __byte_perm(u < 4 ? jw.x : jw.y, 0u, 0x4440u | (u & 3)) * NB;
                 t1[u] = *reinterpret_cast<const float*>(row);
-                if (ROLE == 2) t2[u] = *reinterpret_cast<const float*>(row + SL * 4);
+                if (ROLE == 2) {
+                    t2[u] = *reinterpret_cast<const float*>(row + SL * 4);
+                    t3[u] = *reinterpret_cast<const float*>(row + 2 * SL * 4);
+                }
             }
             if ((flagw >> (8 * gg)) & 0xffu) {                       // this group starts the next receiver
                 if (ROLE == 0) {
@@ -548,7 +557,7 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const float w = __uint_as_float(f[u]);
-                if (ROLE == 0 || ROLE == 3) {
+                if (ROLE == 0) {
                     acc[0][u & 1] = fmaf(w, t1[u], acc[0][u & 1]);
                 } else if (ROLE == 1) {
                     const float sR = w * t1[u];
@@ -558,6 +567,7 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
                 } else {
                     acc[0][u & 1] = fmaf(w, t1[u], acc[0][u & 1]);
                     acc[1][u & 1] = fmaf(w, t2[u], acc[1][u & 1]);
+                    acc[2][u & 1] = fmaf(w, t3[u], acc[2][u & 1]);
                 }
             }
         }
@@ -573,17 +583,7 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
         ps = (ps + 1) & 3;
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&S->acc_free[pipe][bi]);
-            if (ROLE == PROD_ROLE && t + 2 < n_tiles) {                   // producer duty for tiles t+2 / t+3
-                st_wait(&S->acc_free[pipe][bi], ph);                      // every warp has left tile t
-                feed_mma(c, fd, t + 2);
-                if (t + 3 < n_tiles) {
-                    st_wait(&S->mma_done[pipe][bi ^ 1u], (((uint32_t)t + 1u) >> 1) & 1u);
-                    feed_copy(c, fd, t + 3);
-                }
-            }
-        }
+        if (lane == 0) mbar_arrive(&S->acc_free[pipe][bi]);
     }
     // ---- the receiver still in flight: once every role has left the last tile, drop its sums into slot 0 of the
     //      next partial buffer; role 0 then writes the rows of the last two tiles and that one
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     long long* dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int NB = Tab<HAS_MU>::NODE_BYTES;
-    constexpr int NROLE = HAS_MU ? 4 : 2;           // layer 0 (mu == 0) has no dmumu term: warps 2, 3 idle
+    constexpr int NROLE = HAS_MU ? 3 : 2;           // consuming warps per pipeline (layer 0, mu == 0, has no dmumu term)
     uint8_t* TabS = smem;
     const uint32_t tab_bytes = ((uint32_t)n_max * NB + 127u) & ~127u;
     uint8_t* Bs = smem + tab_bytes;
@@ -711,8 +711,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     fd.bdesc0 = umma_desc(smem_u32(fd.Bp), 512, 128);
     if (role == 0) run_role<HAS_MU, 0>(c, fd, mu_in, q, mu_out);
     else if (role == 1) run_role<HAS_MU, 1>(c, fd, mu_in, q, mu_out);
-    else if (HAS_MU && role == 2) run_role<HAS_MU, 2>(c, fd, mu_in, q, mu_out);
-    else if (HAS_MU) run_role<HAS_MU, 3>(c, fd, mu_in, q, mu_out);
+    else if (role == 2) { if (HAS_MU) run_role<HAS_MU, 2>(c, fd, mu_in, q, mu_out); }
+    else run_feeder(c, fd);
 
     tc_fence_before();
     __syncthreads();
@@ -822,7 +822,7 @@ int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, 
 #ifdef RLVD_TIMELINE   // in-kernel timeline of block 0 / pipeline 0 (build with RLVD_EXTRA_NVCC_FLAGS=-DRLVD_TIMELINE)
     static long long* dbg_buf = nullptr;
     static int dbg_calls = 0;
-    if (dbg_buf == nullptr) { cudaMalloc(&dbg_buf, 64 * 4 * 6 * 8); cudaMemset(dbg_buf, 0, 64 * 4 * 6 * 8); }
+    if (dbg_buf == nullptr) { cudaMalloc(&dbg_buf, 64 * 4 * 10 * 8); cudaMemset(dbg_buf, 0, 64 * 4 * 10 * 8); }
     dbg = dbg_buf;
 #endif
     Span sp(e, s, FAM_EDGE);
@@ -835,15 +835,16 @@ int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, 
 #ifdef RLVD_TIMELINE
     if (mu_in != nullptr && ++dbg_calls == 20) {
         cudaStreamSynchronize(s);
-        static long long h[64 * 4 * 6];
+        static long long h[64 * 4 * 10];
         cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
         const long long t0 = h[0];
         for (int t = 0; t < 40; ++t) {
             printf("tile %2d |", t);
             for (int r = 0; r < 4; ++r) {
-                const long long* w = h + (t * 4 + r) * 6;
+                const long long* w = h + (t * 4 + r) * 10;
                 printf(" R%d top %7lld wait +%5lld combine +%5lld consume +%5lld |", r, w[0] - t0, w[1] - w[0], w[2] - w[1], w[3] - w[2]);
             }
+            { const long long* w = h + (t * 4 + 3) * 10; printf(" duty: accfree +%5lld bfull +%5lld mma +%5lld mmadone +%5lld copy +%5lld", w[4] - w[3], w[5] - w[4], w[6] - w[5], w[7] - w[6], w[8] - w[7]); }
             printf("\n");
         }
     }

@@ -251,3 +251,68 @@ def test_tensor_core_and_simt_paths_agree_end_to_end(model, engine):
     for k in ("E_R", "E_P"):
         assert np.max(np.abs(tc[k] - simt[k]) / np.abs(simt[k])) < 1e-6, k
     assert int(np.argmax(tc["rl_q"])) == int(np.argmax(simt["rl_q"]))
+
+
+# ----------------------------------------------------------------------------- edge stream kernel: ragged / degenerate batches
+
+def _ragged_batch():
+    """Structures of 1, 2, 31, 107, 255 and 256 atoms in one batch; the 107-atom one has two atoms pushed out of
+    everyone's cutoff sphere (edgeless receivers, also as the first and the last atom of the structure)."""
+    rng = np.random.default_rng(7)
+    structs = []
+    big = np.eye(3) * 40.0
+    structs.append((np.array([24]), np.array([[1.0, 2.0, 3.0]]), big))                                   # 1 atom, no edges
+    structs.append((np.array([27, 28]), np.array([[0.0, 0.0, 0.0], [2.4, 0.3, 0.1]]), big))              # one pair
+    s31 = make_crconi_supercell(2, seed=3, jitter=0.04)
+    structs.append((s31.numbers, s31.positions, s31.cell))                                                # multi-image cell
+    s107 = make_crconi_supercell(3, seed=5, jitter=0.04)
+    cell107 = np.array(s107.cell, dtype=np.float64).copy()
+    cell107[2, 2] += 30.0                                                                                 # open a vacuum gap
+    pos107 = np.array(s107.positions, dtype=np.float64).copy()
+    pos107[0] = [5.0, 5.0, 25.0]                                                                          # isolated: first atom
+    pos107[-1] = [1.0, 1.0, 33.0]                                                                         # isolated: last atom
+    structs.append((s107.numbers, pos107, cell107))
+    s255 = make_crconi_supercell(4, seed=9, jitter=0.05)
+    structs.append((s255.numbers, s255.positions, s255.cell))
+    a0 = 3.528
+    grid = np.array([[i, j, k] for i in range(4) for j in range(4) for k in range(4)], dtype=np.float64)
+    basis = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]])
+    pos256 = ((grid[:, None, :] + basis[None]).reshape(-1, 3) * a0) + rng.normal(0, 0.03, (256, 3))       # full 256-site cell
+    structs.append((rng.choice([24, 27, 28], 256), pos256, np.eye(3) * 4 * a0))
+    Z = np.concatenate([s[0] for s in structs]).astype(np.int32)
+    pos = np.concatenate([np.asarray(s[1], dtype=np.float64) for s in structs]).astype(np.float32)
+    cells = np.stack([np.asarray(s[2], dtype=np.float64) for s in structs])
+    ptr = np.concatenate([[0], np.cumsum([len(s[0]) for s in structs])]).astype(np.int32)
+    return structs, Z, pos, cells, ptr
+
+
+def test_edge_stream_ragged_batch_matches_simt_and_oracle(engine):
+    structs, Z, pos, cells, ptr = _ragged_batch()
+    row_ptr, col, shift, node_struct = _device_graph(engine, pos, cells.astype(np.float32), ptr)
+    deg = np.diff(row_ptr.cpu().numpy())
+    assert deg[0] == 0 and deg[ptr[3]] == 0 and deg[ptr[4] - 1] == 0        # the edgeless receivers are really edgeless
+    Zd, posd = torch.from_numpy(Z).cuda(), torch.from_numpy(pos).cuda()
+    celld, ptrd = torch.from_numpy(cells.astype(np.float32)).cuda(), torch.from_numpy(ptr).cuda()
+    out = {}
+    for name, opts in (("stream", {"tensor_cores": 1, "sliced_edge": 1, "sliced_impl": 1}), ("simt", {"tensor_cores": 0})):
+        for k, v in opts.items():
+            engine.set_option(k, v)
+        q, mu = engine.representation(Zd, posd, celld, node_struct, row_ptr, col, shift, len(structs), return_mu=True,
+                                      node_ptr=ptrd, max_struct_nodes=256)
+        out[name] = (q.cpu().numpy(), mu.cpu().numpy())
+    engine.set_option("tensor_cores", 1)
+    for a, b in zip(out["stream"], out["simt"]):
+        assert np.isfinite(a).all()
+        assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
+    # the isolated atoms keep their embedding-driven scalars and a zero vector state
+    assert np.abs(out["stream"][1][0]).max() == 0.0 and np.abs(out["stream"][1][ptr[3]]).max() == 0.0
+    # fp64 oracle on the two structures with degenerate rows
+    m64 = PaiNNOracle.load(os.path.join(GOLD, "model_trained"), dtype=torch.float64)
+    for s in (3, 5):
+        Zs, ps, cs = structs[s]
+        with torch.no_grad():
+            qr, mur = m64.representation(np.asarray(Zs), np.asarray(ps, dtype=np.float32), np.asarray(cs, dtype=np.float64)[None],
+                                         np.array([0, len(Zs)], dtype=np.int32), return_mu=True)
+        sl = slice(ptr[s], ptr[s + 1])
+        assert np.abs(out["stream"][0][sl] - qr.numpy()).max() <= TOL * np.abs(qr.numpy()).max()
+        assert np.abs(out["stream"][1][sl] - mur.numpy()).max() <= TOL * np.abs(mur.numpy()).max()
