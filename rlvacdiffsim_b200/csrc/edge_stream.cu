@@ -9,10 +9,10 @@
 // edge_pack_kernel (once per call, one CTA per structure)
 //   Splits the structure's receivers into NPIPE contiguous ranges of equal edge-group count and writes, per range,
 //   a stream of 32-slot tiles.  Slots come in receiver-aligned groups of 8 (short rows padded with zero filters).
-//   A tile is 4096 B of MMA operand + 432 B of meta:
+//   A tile is 4096 B of MMA operand + 528 B of meta:
 //     operand  [32 slots][64 fp16], K-major core-matrix layout:  b_hi[21] | b_lo[21] | b_hi[21] | 0
 //              b = 2^10 * {phi_k(d) * fcut(d) (k < 20), fcut(d)}, split b = b_hi + b_lo in fp16 (22 significant bits)
-//     meta     j[32] u8 (local sender index) | new_receiver[4] u8 (one per group) | pad | dir_x[32] | dir_y[32] | dir_z[32]
+//     meta     j[32] (local sender index) | dir_x[32] | dir_y[32] | dir_z[32] | new_receiver[4] u8 (one per group)
 //
 // edge_stream_kernel (per layer; CTA = one structure x one 32-channel slice; 1 CTA per SM)
 //   The slice of the structure's node table lives in shared memory (gathers never leave the SM):
@@ -27,7 +27,7 @@
 //        role 2 (M)   : dmuM_xyz  += D * (x_m mu_xyz)[j]
 //        role 3       : no rows; one thread feeds the pipeline (bulk copies, tcgen05.mma issue, commits)
 //   warp%4 is also the SM sub-partition (issue scheduler) a warp runs on and the roles cost 0..85 issue slots per
-//   group, so the operand is kept in TMEM in four row rotations and pipeline p uses rotation p%4: every scheduler
+//   group, so the operand is kept in TMEM in four row rotations and pipeline p uses rotation pipe_rot(p): every scheduler
 //   then hosts a mix of roles instead of one scheduler carrying all the R warps.
 //   The kernel is shared-memory-bandwidth bound (gathers 5 x 128 B per slot), so every sender row is gathered exactly
 //   once.  When a receiver's row ends, warps 1-3 drop their partial sums into a per-SM scratch slot (55 KB per SM,
@@ -57,16 +57,19 @@ constexpr int GS = 8;                     // slots per receiver-aligned group
 constexpr int KH = 64;                    // fp16 k-extent of the split operands
 constexpr int NK = NRBF + 1;              // 21: 20 Bessel functions + the bias column (fcut)
 constexpr int TILE_B = TE * KH * 2;       // 4096
-constexpr int META = 432;                 // j[32] u8 | newrecv[4] u8 | pad[12] | dir[3][32] f32
-constexpr int META_DIR = 48;
-constexpr int META_FLAG = 32;
-constexpr int TILE_BYTES = TILE_B + META; // 4528
+constexpr int META = 528;                 // j[32] i32 | dir[3][32] f32 | newrecv[4] u8 | pad[12]
+constexpr int META_DIR = 128;
+constexpr int META_FLAG = 512;
+constexpr int TILE_BYTES = TILE_B + META; // 4624
 constexpr int MAXN = 256;
 constexpr int ST_THREADS = NPIPE * 128;
 constexpr int B_SCALE_LOG2 = 10;
 constexpr int TM_D = 0;                   // TMEM columns: accumulator buffer b of pipe p at (2p+b)*32
 constexpr int TM_A = NPIPE * 2 * TE;      // 4 row rotations of the weight operand (64 fp16 = 32 columns each)
 constexpr int NROT = 4;
+// rotation of pipeline p: with role costs q 45 / R 75 / M 75 / feeder 0 issue slots per group this spreads the six
+// pipelines' warps over the four schedulers as 315 / 270 / 315 / 270
+__device__ __forceinline__ int pipe_rot(int p) { return p < 4 ? p : (p == 4 ? 0 : 2); }
 constexpr int TM_COLS = 512;
 constexpr int A_SLICE_WORDS = NROT * 128 * 32;   // u32 per (layer, slice): [rotation][row][32]
 constexpr int NB_STAGE = 2;               // operand buffers per pipeline
@@ -176,7 +179,7 @@ __device__ __forceinline__ void write_slot(uint8_t* tile, int r, const uint4* ro
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(b + kc * 512) = row8[kc];
     uint8_t* m = tile + TILE_B;
-    m[r] = (uint8_t)j;
+    reinterpret_cast<int*>(m)[r] = j;
     reinterpret_cast<float*>(m + META_DIR)[r] = dx;
     reinterpret_cast<float*>(m + META_DIR + 128)[r] = dy;
     reinterpret_cast<float*>(m + META_DIR + 256)[r] = dz;
@@ -401,7 +404,7 @@ __device__ __forceinline__ void feed_mma(const PipeCtx& c, const Feed& fd, int m
     const uint32_t d = c.tmem + TM_D + (uint32_t)(c.pipe * 2 + (m & 1)) * TE;
     const uint64_t bd = fd.bdesc0 + (uint64_t)((m & 1) * (TILE_B >> 4));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_f16_ts(d, c.tmem + TM_A + (c.pipe & 3) * 32 + k * 8, bd + (uint64_t)(k * 64), k);
+    for (int k = 0; k < 4; ++k) umma_f16_ts(d, c.tmem + TM_A + pipe_rot(c.pipe) * 32 + k * 8, bd + (uint64_t)(k * 64), k);
     umma_commit(&c.S->mma_done[c.pipe][m & 1]);
 }
 
@@ -518,7 +521,8 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
         for (int gg = 0; gg < NG; ++gg) {
             uint32_t f[8];
             tmem_ld8(dcol + gg * GS, f);
-            const uint2 jw = *reinterpret_cast<const uint2*>(meta + gg * GS);
+            const int4 ja = *reinterpret_cast<const int4*>(meta + gg * 32), jb = *reinterpret_cast<const int4*>(meta + gg * 32 + 16);
+            const int jo[8] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
             float dr[3][8];
             if (ROLE == 1) {
 #pragma unroll
@@ -532,7 +536,7 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
             float t1[8], t2[8], t3[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const uint8_t* row = tb + __byte_perm(u < 4 ? jw.x : jw.y, 0u, 0x4440u | (u & 3)) * NB;
+                const uint8_t* row = tb + jo[u] * NB;
                 t1[u] = *reinterpret_cast<const float*>(row);
                 if (ROLE == 2) {
                     t2[u] = *reinterpret_cast<const float*>(row + SL * 4);
@@ -704,7 +708,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     c.node0 = node0;
     c.ch = slice * SL + lane;
     c.dbg = (blockIdx.x == 0 && c.pipe == 0 && lane == 0) ? dbg : nullptr;
-    const int role = ((warp & 3) + c.pipe) & 3;      // rotation pipe%4 puts this role's filter rows in this warp's quarter
+    const int role = ((warp & 3) + pipe_rot(c.pipe)) & 3;   // the pipeline's rotation puts this role's filter rows in this warp's quarter
     Feed fd;
     fd.src = tiles + (size_t)pi.x * TILE_BYTES;
     fd.Bp = Bs + c.pipe * NB_STAGE * TILE_B;
@@ -751,7 +755,7 @@ void edge_stream_format(const float* W, const float* b, std::vector<uint8_t>& ou
         for (int sl = 0; sl < NSLICE; ++sl)
           for (int rot = 0; rot < NROT; ++rot)
             for (int quarter = 0; quarter < 4; ++quarter) {
-                const int role = (quarter + rot) & 3;          // pipeline p = rot (mod 4): warp quarter -> role
+                const int role = (quarter + rot) & 3;          // a pipeline with rotation rot: warp quarter -> role
                 const int part = role < 3 ? role : 2;
                 for (int chn = 0; chn < SL; ++chn) {
                     const int row = l * 3 * F + part * F + sl * SL + chn;
