@@ -9,10 +9,10 @@
 // edge_pack_kernel (once per call, one CTA per structure)
 //   Splits the structure's receivers into NPIPE contiguous ranges of equal edge-group count and writes, per range,
 //   a stream of 32-slot tiles.  Slots come in receiver-aligned groups of 8 (short rows padded with zero filters).
-//   A tile is 4096 B of MMA operand + 528 B of meta:
+//   A tile is 4096 B of MMA operand + 432 B of meta:
 //     operand  [32 slots][64 fp16], K-major core-matrix layout:  b_hi[21] | b_lo[21] | b_hi[21] | 0
 //              b = 2^10 * {phi_k(d) * fcut(d) (k < 20), fcut(d)}, split b = b_hi + b_lo in fp16 (22 significant bits)
-//     meta     j[32] (local sender index) | dir_x[32] | dir_y[32] | dir_z[32] | new_receiver[4] u8 (one per group)
+//     meta     j[32] u8 (local sender index) | new_receiver[4] u8 (one per group) | pad | dir_x[32] | dir_y[32] | dir_z[32]
 //
 // edge_stream_kernel (per layer; CTA = one structure x one 32-channel slice; 1 CTA per SM)
 //   The slice of the structure's node table lives in shared memory (gathers never leave the SM):
@@ -57,10 +57,10 @@ constexpr int GS = 8;                     // slots per receiver-aligned group
 constexpr int KH = 64;                    // fp16 k-extent of the split operands
 constexpr int NK = NRBF + 1;              // 21: 20 Bessel functions + the bias column (fcut)
 constexpr int TILE_B = TE * KH * 2;       // 4096
-constexpr int META = 528;                 // j[32] i32 | dir[3][32] f32 | newrecv[4] u8 | pad[12]
-constexpr int META_DIR = 128;
-constexpr int META_FLAG = 512;
-constexpr int TILE_BYTES = TILE_B + META; // 4624
+constexpr int META = 432;                 // j[32] u8 | newrecv[4] u8 | pad[12] | dir[3][32] f32
+constexpr int META_DIR = 48;
+constexpr int META_FLAG = 32;
+constexpr int TILE_BYTES = TILE_B + META; // 4528
 constexpr int MAXN = 256;
 constexpr int ST_THREADS = NPIPE * 128;
 constexpr int B_SCALE_LOG2 = 10;
@@ -102,24 +102,14 @@ __device__ __noinline__ void st_timeout() {
     printf("rlvd: edge_stream mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
     __trap();
 }
-// try_wait without a suspend-time hint: the hardware's own (short) wait window, re-armed in a loop.  The hinted form
-// compiles to TRYWAIT + NANOSLEEP, whose wake-up granularity put ~1 us between a tile's barrier hand-offs.
-__device__ __forceinline__ bool st_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
+// Waits use try_wait WITH a suspend-time hint (TRYWAIT + NANOSLEEP.SYNCS: the warp sleeps in hardware until the phase
+// completes).  The hint-less form spins; in this kernel a third of all issued instructions were such spins (ncu,
+// profiles/ncu_stream_r01d.txt) taken from the warps that had work.
 __device__ __forceinline__ void st_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
 #pragma unroll 1
-    while (!st_try_wait(bar, parity))
-        if (++spins > 50000000u) st_timeout();
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > 400000u) st_timeout();
 }
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(
@@ -179,7 +169,7 @@ __device__ __forceinline__ void write_slot(uint8_t* tile, int r, const uint4* ro
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(b + kc * 512) = row8[kc];
     uint8_t* m = tile + TILE_B;
-    reinterpret_cast<int*>(m)[r] = j;
+    m[r] = (uint8_t)j;
     reinterpret_cast<float*>(m + META_DIR)[r] = dx;
     reinterpret_cast<float*>(m + META_DIR + 128)[r] = dy;
     reinterpret_cast<float*>(m + META_DIR + 256)[r] = dz;
@@ -521,8 +511,7 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
         for (int gg = 0; gg < NG; ++gg) {
             uint32_t f[8];
             tmem_ld8(dcol + gg * GS, f);
-            const int4 ja = *reinterpret_cast<const int4*>(meta + gg * 32), jb = *reinterpret_cast<const int4*>(meta + gg * 32 + 16);
-            const int jo[8] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, jb.z, jb.w};
+            const uint2 jw = *reinterpret_cast<const uint2*>(meta + gg * GS);
             float dr[3][8];
             if (ROLE == 1) {
 #pragma unroll
@@ -536,7 +525,7 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
             float t1[8], t2[8], t3[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const uint8_t* row = tb + jo[u] * NB;
+                const uint8_t* row = tb + __byte_perm(u < 4 ? jw.x : jw.y, 0u, 0x4440u | (u & 3)) * NB;
                 t1[u] = *reinterpret_cast<const float*>(row);
                 if (ROLE == 2) {
                     t2[u] = *reinterpret_cast<const float*>(row + SL * 4);
