@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
     uint8_t* Bst = smem + 131072;                      // TC_NSTAGE x 32 KB weight stages
     uint8_t* Yst = Bst + TC_NSTAGE * TC_STAGE_BYTES;   // 32 KB  [128 rows][64 cols] fp32 output staging (swizzled)
     TcSmem* S = reinterpret_cast<TcSmem*>(Yst + 32768);
+    float* bias_s = reinterpret_cast<float*>(Yst + 32768 + 128);      // [N <= 384] bias staged once (zeros when absent)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = (a.M + TC_M - 1) / TC_M;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
         mbar_init(&S->a_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = tid; i < a.N; i += TC_THREADS) bias_s[i] = a.bias != nullptr ? __ldg(a.bias + i) : 0.f;
     if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S->tmem_base)),
                      "r"(512u)
@@ -177,11 +179,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float y[4];
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + j);
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            float v = fmaf(__uint_as_float(d1[j + u]), 1.0f / 2048.0f, __uint_as_float(d0[j + u]));
-                            if (a.bias != nullptr) v += __ldg(a.bias + col0 + j + u);
-                            if (a.act == 1) v = v / (1.0f + expf(-v));
+                            float v = fmaf(__uint_as_float(d1[j + u]), 1.0f / 2048.0f, __uint_as_float(d0[j + u])) + bb[u];
+                            if (a.act == 1) v = __fdividef(v, 1.0f + __expf(-v));   // SiLU; |error| < 2e-7 of max(|v|, 1)
                             y[u] = v;
                         }
                         const int lc = h * 8 + (j >> 2);
@@ -265,7 +268,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
     }
 }
 
-size_t tc_smem_bytes(int) { return (size_t)131072 + TC_NSTAGE * TC_STAGE_BYTES + 32768 + sizeof(TcSmem) + 64; }
+size_t tc_smem_bytes(int) { return (size_t)131072 + TC_NSTAGE * TC_STAGE_BYTES + 32768 + 128 + 384 * 4 + 64; }
+static_assert(sizeof(TcSmem) <= 128, "TcSmem must fit its 128-byte slot");
 
 }  // namespace
 
@@ -291,7 +295,7 @@ void tc_format_weight(const float* W, int N, int K, std::vector<uint8_t>& out) {
 
 bool tc_linear_supported(const LinearArgs& a) {
     const bool k_ok = a.K == 128 || (a.K == 256 && a.N <= 2 * TC_N);   // K=256 keeps every N-block's accumulator live
-    return a.N % TC_N == 0 && k_ok && (a.A2 == nullptr || a.K1 == 128) && a.lda % 4 == 0 && a.ldy % 4 == 0;
+    return a.N % TC_N == 0 && a.N <= 384 && k_ok && (a.A2 == nullptr || a.K1 == 128) && a.lda % 4 == 0 && a.ldy % 4 == 0;
 }
 
 int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt) {
