@@ -406,10 +406,30 @@ __device__ __forceinline__ void feed_mma(const PipeCtx& c, const Feed& fd, int m
 //   wait b_full(t+2), issue the MMAs of tile t+2, commit -> mma_done(t+2)
 //   wait mma_done(t+2) (operand buffer t%2 read), bulk-copy tile t+4 into it and into meta buffer (t+4)%5 (last used
 //   by tile t-1): a copy gets two tile periods to cover its HBM latency.
+// PART: 0 = both halves in one thread (layers with mu: all four warps of the pipeline are taken), 1 = MMA half only,
+// 2 = copy half only (layer 0 has an idle third warp, so the halves run as two threads and the ~1300-cycle duty, which
+// there exceeds what the two consumers need per tile, is cut in two).
+template <int PART>
 __device__ __forceinline__ void run_feeder(const PipeCtx& c, const Feed& fd) {
     StBars* S = c.S;
     const int pipe = c.pipe, n_tiles = c.n_tiles;
     if (n_tiles <= 0 || c.ra >= c.rb || c.lane != 0) return;
+    if (PART == 1) {
+#pragma unroll 1
+        for (int m = 0; m < n_tiles; ++m) {
+            if (m >= 2) st_wait(&S->acc_free[pipe][m & 1], (((uint32_t)m - 2u) >> 1) & 1u);
+            feed_mma(c, fd, m);
+        }
+        return;
+    }
+    if (PART == 2) {
+#pragma unroll 1
+        for (int k = 0; k < n_tiles; ++k) {     // mma_done(k-2) also implies every consumer has left tile k-4 >= k-5
+            if (k >= 2) st_wait(&S->mma_done[pipe][k & 1], (((uint32_t)k - 2u) >> 1) & 1u);
+            feed_copy(c, fd, k);
+        }
+        return;
+    }
     feed_copy(c, fd, 0);
     if (n_tiles > 1) feed_copy(c, fd, 1);
     feed_mma(c, fd, 0);
@@ -704,8 +724,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     fd.bdesc0 = umma_desc(smem_u32(fd.Bp), 512, 128);
     if (role == 0) run_role<HAS_MU, 0>(c, fd, mu_in, q, mu_out);
     else if (role == 1) run_role<HAS_MU, 1>(c, fd, mu_in, q, mu_out);
-    else if (role == 2) { if (HAS_MU) run_role<HAS_MU, 2>(c, fd, mu_in, q, mu_out); }
-    else run_feeder(c, fd);
+    else if (role == 2) { if (HAS_MU) run_role<HAS_MU, 2>(c, fd, mu_in, q, mu_out); else run_feeder<2>(c, fd); }
+    else run_feeder<HAS_MU ? 0 : 1>(c, fd);
 
     tc_fence_before();
     __syncthreads();
