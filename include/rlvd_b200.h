@@ -102,6 +102,24 @@ int  rlvd_reaction_readout(rlvd_engine* e, void* stream, int32_t n_react, int32_
                            float* d_rl_q, float* d_q0, float* d_q1, float* d_delta_e,
                            float* d_E_R, float* d_E_P);
 
+/* ---- T1: t_net head on top of rlvd_painn_representation (replaces rgnn `t_net` forward reached from
+ *      rlsim/cli/scripts/estimate_time.py:58 `model(batch, inference=True)["time"]` and rlsim/time/train.py:108,114) -- */
+/* Head weights live on the device (the caller's nn.Parameters); nn.Linear layout [out, in].  No t_net checkpoint is
+ * bundled with the reference, so the head wiring is a named assumption (oracle TimeHeadSpec): pooled node scalars,
+ * then T * T_scale and defect * D_scale, MLP (F+2 -> n_feat -> n_feat -> 1), time = tau * sigmoid(out). */
+typedef struct rlvd_time_head {
+    const float* d_w0; const float* d_b0;   /* [n_feat, 130], [n_feat] */
+    const float* d_w1; const float* d_b1;   /* [n_feat, n_feat], [n_feat] */
+    const float* d_w2; const float* d_b2;   /* [1, n_feat], [1] */
+    int32_t n_feat;                         /* <= 128 */
+    int32_t pooling;                        /* 0 mean, 1 sum */
+    int32_t act;                            /* RLVD_ACT_* */
+    float tau, T_scale, D_scale;
+} rlvd_time_head;
+/* d_q[M,128] from rlvd_painn_representation; d_T / d_defect / d_time are [n_struct]. */
+int  rlvd_time_readout(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const float* d_q,
+                       const float* d_T, const float* d_defect, const rlvd_time_head* head, float* d_time);
+
 /* ---- whole path from HOST buffers (the call `model(batch, q_params)` makes after `batch_to`) ---- */
 /* n_struct structures (h_node_ptr, h_Z, h_pos, h_cell, h_inv_cell, h_img_range), n_react reaction
  * graphs pairing them; copies inputs H2D, runs K1..K5 on `stream`, copies rl_q/q0/q1/delta_e/E_R/E_P

@@ -53,6 +53,23 @@ class HeadSpec:
 
 HEAD_SPEC_V0 = HeadSpec()
 
+
+@dataclass(frozen=True)
+class TimeHeadSpec:
+    """Named assumptions for rgnn's ``t_net`` head — nothing in the reference pins them: no
+    t_net checkpoint is bundled.  Call sites fix only the interface: ``model(batch, inference=True)["time"]`` with
+    per-frame ``T`` and ``defect`` (``rlsim/time/misc.py:115-141``), ``t_real = -tau * log(1 - t / tau)``
+    (``estimate_time.py:15-35``), constructor keywords ``n_feat, pooling, tau0, D_scaler, T_scaler_m``."""
+    pooling: str = "mean"                 # mean of the node scalars q over the frame's atoms
+    T_input: str = "T / T_scaler_m"
+    D_input: str = "defect / D_scaler"
+    activation: str = "silu"
+    squash: str = "tau * sigmoid"         # time in (0, tau)
+    name: str = "TIME_HEAD_SPEC_V0"
+
+
+TIME_HEAD_SPEC_V0 = TimeHeadSpec()
+
 _ACT = {"silu": F.silu, "relu": F.relu, "tanh": torch.tanh,
         "leaky_relu": lambda x: F.leaky_relu(x, 0.01)}
 
@@ -225,6 +242,24 @@ class PaiNNOracle:
             q = q + a + c * (mu_V * mu_W).sum(dim=1)
             mu = mu + b[:, None, :] * mu_W
         return (q, mu) if return_mu else q
+
+    # -- T1: t_net head (TimeHeadSpec)
+    def time_forward(self, Z, pos, cells, node_ptr, T, defect, head: Dict[str, np.ndarray], tau: float = 1.0,
+                     T_scaler_m: float = 7918.951990135471, D_scaler: float = 1 / 256, pooling: str = "mean"):
+        """→ time[G]; ``head`` = {"w0","b0","w1","b1","w2","b2"} in nn.Linear layout."""
+        dt = self.dtype
+        q = self.representation(Z, pos, cells, node_ptr)
+        out = []
+        W = {k: torch.from_numpy(np.asarray(v, dtype=np.float64)).to(dt) for k, v in head.items()}
+        for g in range(len(node_ptr) - 1):
+            qs = q[int(node_ptr[g]):int(node_ptr[g + 1])]
+            pooled = qs.mean(dim=0) if pooling == "mean" else qs.sum(dim=0)
+            z = torch.cat([pooled, torch.tensor([float(T[g]) / T_scaler_m, float(defect[g]) / D_scaler], dtype=dt)])
+            h = F.silu(W["w0"] @ z + W["b0"])
+            h = F.silu(W["w1"] @ h + W["b1"])
+            o = W["w2"] @ h + W["b2"]
+            out.append(tau * torch.sigmoid(o))
+        return torch.cat(out)
 
     # -- H1..H4
     def atom_energies(self, q, Z):

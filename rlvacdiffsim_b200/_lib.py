@@ -23,6 +23,13 @@ class QParams(C.Structure):
                 ("std_freq", C.c_float), ("mean_delta_e", C.c_float), ("std_delta_e", C.c_float)]
 
 
+class TimeHead(C.Structure):
+    """``rlvd_time_head`` (include/rlvd_b200.h)."""
+    _fields_ = [("d_w0", C.c_void_p), ("d_b0", C.c_void_p), ("d_w1", C.c_void_p), ("d_b1", C.c_void_p),
+                ("d_w2", C.c_void_p), ("d_b2", C.c_void_p), ("n_feat", C.c_int32), ("pooling", C.c_int32),
+                ("act", C.c_int32), ("tau", C.c_float), ("T_scale", C.c_float), ("D_scale", C.c_float)]
+
+
 # name -> (restype, argtypes); every symbol include/rlvd_b200.h declares
 _P = C.c_void_p
 SYMBOLS = {
@@ -41,6 +48,7 @@ SYMBOLS = {
                                         _P, _P, _P, _P, _P, _P]),
     "rlvd_score_reactions_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_float,
                                             C.c_int32, _P, _P, C.POINTER(QParams), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rlvd_time_readout": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, C.POINTER(TimeHead), _P]),
     "rlvd_linear": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int32, _P]),
     "rlvd_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
     "rlvd_launch_count": (C.c_int64, [_P]),

@@ -207,4 +207,7 @@ int launch_readout(rlvd_engine* e, cudaStream_t s, int n_react, const int* node_
                    const int* ps, const int* Z, const float* q, const rlvd_q_params& qp, const float* d_temp,
                    float* rl_q, float* q0, float* q1, float* delta_e, float* E_R, float* E_P);
 
+int launch_time_readout(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const float* q, const float* T,
+                        const float* defect, const rlvd_time_head& h, float* time_out);
+
 }  // namespace rlvd

@@ -398,6 +398,15 @@ int rlvd_reaction_readout(rlvd_engine* e, void* stream, int32_t n_react, int32_t
                           d_temperature, d_rl_q, d_q0, d_q1, d_delta_e, d_E_R, d_E_P);
 }
 
+int rlvd_time_readout(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const float* d_q,
+                      const float* d_T, const float* d_defect, const rlvd_time_head* head, float* d_time) {
+    RLVD_CHECK(e != nullptr && head != nullptr, "rlvd_time_readout: bad argument");
+    RLVD_CHECK(head->d_w0 && head->d_b0 && head->d_w1 && head->d_b1 && head->d_w2 && head->d_b2,
+               "rlvd_time_readout: head weights missing");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_time_readout(e, (cudaStream_t)stream, n_struct, d_node_ptr, d_q, d_T, d_defect, *head, d_time);
+}
+
 int rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes,
                               const int32_t* h_node_ptr, const int32_t* h_Z, const float* h_pos, const float* h_cell,
                               const float* h_inv_cell, const int32_t* h_img_range, float cutoff, int32_t n_react,

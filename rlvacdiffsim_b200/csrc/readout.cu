@@ -261,6 +261,64 @@ size_t readout_smem() { return (size_t)(2 * TA * QS + TA * 8 + 2 * TA + 8 * 32 +
 
 }  // namespace
 
+namespace {
+
+// T1 — t_net head (called at rlsim/cli/scripts/estimate_time.py:58 and rlsim/time/train.py:108):
+// pool the node scalars of ONE structure, append the two per-frame scalars, run the 3-layer MLP
+// (hidden_channels+2 -> n_feat -> n_feat -> 1) and squash to [0, tau).  One CTA per structure, thread = channel /
+// hidden unit; sums run in atom order (bitwise reproducible).
+constexpr int TT = 128;
+
+__global__ void __launch_bounds__(TT) time_readout_kernel(int n_struct, const int* __restrict__ node_ptr,
+                                                          const float* __restrict__ q, const float* __restrict__ T,
+                                                          const float* __restrict__ defect, const rlvd_time_head h,
+                                                          float* __restrict__ time_out) {
+    __shared__ float z[F + 2];
+    __shared__ float h0[TT], h1[TT];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (g >= n_struct) return;
+    const int n0 = node_ptr[g], n = node_ptr[g + 1] - n0;
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) acc += __ldg(q + (int64_t)(n0 + i) * F + tid);
+    z[tid] = h.pooling == 0 ? (n > 0 ? acc / (float)n : 0.f) : acc;
+    if (tid == 0) {
+        z[F] = __ldg(T + g) * h.T_scale;
+        z[F + 1] = __ldg(defect + g) * h.D_scale;
+    }
+    __syncthreads();
+    const int nf = h.n_feat, k0 = F + 2;
+    if (tid < nf) {
+        float v = __ldg(h.d_b0 + tid);
+        for (int k = 0; k < k0; ++k) v = fmaf(__ldg(h.d_w0 + tid * k0 + k), z[k], v);
+        h0[tid] = act_fn(v, h.act);
+    }
+    __syncthreads();
+    if (tid < nf) {
+        float v = __ldg(h.d_b1 + tid);
+        for (int k = 0; k < nf; ++k) v = fmaf(__ldg(h.d_w1 + tid * nf + k), h0[k], v);
+        h1[tid] = act_fn(v, h.act);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float v = __ldg(h.d_b2);
+        for (int k = 0; k < nf; ++k) v = fmaf(__ldg(h.d_w2 + k), h1[k], v);
+        time_out[g] = h.tau / (1.0f + expf(-v));
+    }
+}
+
+}  // namespace
+
+int launch_time_readout(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const float* q, const float* T,
+                        const float* defect, const rlvd_time_head& h, float* time_out) {
+    if (n_struct <= 0) return 0;
+    RLVD_CHECK(h.n_feat > 0 && h.n_feat <= TT, "rlvd_time_readout: n_feat %d not in [1,%d]", h.n_feat, TT);
+    Span sp(e, s, FAM_READOUT);
+    time_readout_kernel<<<n_struct, TT, 0, s>>>(n_struct, node_ptr, q, T, defect, h, time_out);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_readout(rlvd_engine* e, cudaStream_t s, int n_react, const int* node_ptr, const int* rs, const int* ps,
                    const int* Z, const float* q, const rlvd_q_params& qp, const float* d_temp, float* rl_q,
                    float* q0, float* q1, float* delta_e, float* E_R, float* E_P) {

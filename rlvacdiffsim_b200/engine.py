@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ACT_CODES, QX_CODES, QParams, check
+from ._lib import ACT_CODES, QX_CODES, QParams, TimeHead, check
 
 
 @dataclass(frozen=True)
@@ -159,6 +159,17 @@ class Engine:
                                                  _ptr(out[2]), _ptr(out[3]), _ptr(out[4]), _ptr(out[5])))
         names = ("rl_q", "q0", "q1", "delta_e", "E_R", "E_P")
         return {k: out[i, :G] for i, k in enumerate(names)}
+
+    # ------------------------------------------------------------------ T1: t_net head
+    def time_readout(self, q: torch.Tensor, node_ptr: torch.Tensor, T: torch.Tensor, defect: torch.Tensor,
+                     head: TimeHead) -> torch.Tensor:
+        """``rlvd_time_readout``: pooled node scalars + (T, defect) → MLP → tau * sigmoid, one value per structure."""
+        G = node_ptr.numel() - 1
+        out = torch.empty(max(G, 1), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_time_readout(self._h, self._stream(), G, _ptr(node_ptr), _ptr(q), _ptr(T), _ptr(defect),
+                                             C.byref(head), _ptr(out)))
+        return out[:G]
 
     # ------------------------------------------------------------------ whole path, device-resident inputs
     def score_device(self, Z, pos, cell, inv_cell, img_range, node_ptr, react_struct, prod_struct, qp: QParams,

@@ -252,16 +252,23 @@ class DQNv2(nn.Module, _EngineMixin):
 
 
 class TNet(nn.Module, _EngineMixin):
-    """``registry.get_model_class("t_net")`` placeholder surface (``rlsim/time/train.py:44-48``).
+    """``registry.get_model_class("t_net")`` — ``model(batch, inference=True)["time"]``
+    (``rlsim/cli/scripts/estimate_time.py:58``, ``rlsim/time/train.py:44-48,108,114``).
 
-    No t_net checkpoint ships with the reference and rgnn's head is not recoverable from the repo, so the
-    head kernel is not built in this round; constructing the class works (so drivers can be wired) and
-    ``forward`` raises until SURVEY.md §8a row T1 lands."""
+    The PaiNN representation is shared with the DQN's reaction model and runs on the same CUDA kernels
+    (one graph per frame); the head is ``rlvd_time_readout``.  No t_net checkpoint ships with the reference and
+    rgnn's head is not in the repo, so its wiring is a named assumption (``oracle.painn_oracle.TimeHeadSpec``):
+    mean-pooled node scalars ‖ T / T_scaler_m ‖ defect / D_scaler → MLP(130 → n_feat → n_feat → 1, SiLU) →
+    ``time = tau * sigmoid(.)`` ∈ (0, tau), matching ``timer_converter``'s ``-tau * log(1 - t / tau)``
+    (``estimate_time.py:15-35``).  ``t_net_binary``'s ``"goal"`` logit is not built."""
 
     def __init__(self, reaction_model: PaiNN, n_feat: int = 64, pooling: str = "mean", dropout_rate: float = 0.1,
                  tau0: float = 1.0, D_scaler: float = 1 / 256, T_scaler_m: float = 7918.951990135471, **_ignored):
         super().__init__()
+        if n_feat > 128 or pooling not in ("mean", "sum"):
+            raise NotImplementedError("t_net head kernel: n_feat <= 128, pooling in {mean, sum}")
         self.representation = reaction_model.representation
+        self.__dict__["_reaction_model"] = reaction_model          # not a registered submodule: no duplicate parameters
         self.cutoff = reaction_model.cutoff
         self.tau0 = tau0
         self.tau = tau0
@@ -273,5 +280,64 @@ class TNet(nn.Module, _EngineMixin):
     def load_representation(cls, reaction_model: PaiNN, **cfg) -> "TNet":
         return cls(reaction_model, **cfg)
 
+    # ---- engine plumbing: the engine wants the dqn_v2 checkpoint layout; the Q heads are irrelevant here (zeros)
+    def _engine_tensors(self):
+        return list(self._reaction_model.parameters()) + list(self._reaction_model.buffers())
+
+    def _engine_state(self):
+        sd = {"reaction_model." + k: v for k, v in self._reaction_model.state_dict().items()}
+        rf = self._reaction_model.reaction_feat
+        for name, shape in (("Q_emb.layers.0.weight", (16, rf + 1)), ("Q_emb.layers.0.bias", (16,)),
+                            ("Q_emb.layers.3.weight", (16, 16)), ("Q_emb.layers.3.bias", (16,)),
+                            ("Q_output.layers.0.weight", (32, 18)), ("Q_output.layers.0.bias", (32,)),
+                            ("Q_output.layers.3.weight", (32, 32)), ("Q_output.layers.3.bias", (32,)),
+                            ("Q_output.layers.6.weight", (1, 32)), ("Q_output.layers.6.bias", (1,))):
+            sd[name] = torch.zeros(shape)
+        return sd, {"@name": "dqn_v2", "reaction_model": self._reaction_model.hyper}
+
+    def _head(self, dev: torch.device):
+        from ._lib import ACT_CODES, TimeHead
+        L = self.time_output.layers
+        ws = [L[0].weight, L[0].bias, L[3].weight, L[3].bias, L[6].weight, L[6].bias]
+        keep = []
+        for w in ws:
+            t = w.detach()
+            if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(device=dev, dtype=torch.float32).contiguous()
+            keep.append(t)
+        h = TimeHead()
+        h.d_w0, h.d_b0, h.d_w1, h.d_b1, h.d_w2, h.d_b2 = [t.data_ptr() for t in keep]
+        h.n_feat = int(self.hyper["n_feat"])
+        h.pooling = 0 if self.hyper["pooling"] == "mean" else 1
+        h.act = ACT_CODES["silu"]
+        h.tau = float(self.tau)
+        h.T_scale = 1.0 / float(self.hyper["T_scaler_m"])
+        h.D_scale = 1.0 / float(self.hyper["D_scaler"])
+        return h, keep
+
     def forward(self, batch, inference: bool = False, training: bool = False):
-        raise NotImplementedError("t_net head kernel (SURVEY.md §8a row T1) is scheduled after the Q path")
+        if torch.is_grad_enabled() and (training or self.training) and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("t_net backward has no sm_100a kernels yet; call under torch.no_grad() / .eval()")
+        pos = batch["pos"]
+        if pos.device.type != "cuda":
+            raise RuntimeError("t_net.forward needs the batch on a CUDA device (no CPU fallback); use batch_to")
+        dev = pos.device
+        eng = self._engine_for(dev)
+        counts = np.diff(batch["ptr"].cpu().numpy())
+        node_ptr_host = np.zeros(len(counts) + 1, dtype=np.int32)
+        np.cumsum(counts, out=node_ptr_host[1:])
+        inv, img = cell_geometry(np.asarray(batch["cell64"], dtype=np.float64), eng.cutoff)
+        node_ptr = torch.from_numpy(node_ptr_host).to(dev)
+        cell = batch["cell"].to(torch.float32).contiguous()
+        posc = pos.to(torch.float32).contiguous()
+        row_ptr, col, shift, node_struct = eng.radius_graph(posc, cell, torch.from_numpy(inv).to(dev),
+                                                            torch.from_numpy(img).to(dev), node_ptr)
+        q = eng.representation(batch["elems"].to(torch.int32).contiguous(), posc, cell, node_struct, row_ptr, col, shift,
+                               len(counts), node_ptr=node_ptr, max_struct_nodes=int(counts.max()))
+        G = len(counts)
+        T = torch.as_tensor(batch["T"], dtype=torch.float32, device=dev).reshape(G).contiguous()
+        defect = torch.as_tensor(batch["defect"], dtype=torch.float32, device=dev).reshape(G).contiguous()
+        head, keep = self._head(dev)
+        time = eng.time_readout(q, node_ptr, T, defect, head)
+        del keep
+        return {"time": time}

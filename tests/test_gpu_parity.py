@@ -316,3 +316,38 @@ def test_edge_stream_ragged_batch_matches_simt_and_oracle(engine):
         sl = slice(ptr[s], ptr[s + 1])
         assert np.abs(out["stream"][0][sl] - qr.numpy()).max() <= TOL * np.abs(qr.numpy()).max()
         assert np.abs(out["stream"][1][sl] - mur.numpy()).max() <= TOL * np.abs(mur.numpy()).max()
+
+
+# ----------------------------------------------------------------------------- T1: t_net forward
+
+def test_t_net_time_matches_fp64_oracle(model):
+    """estimate_time.py:58 semantics: ``model(batch, inference=True)["time"]`` on AtomsGraph batches with per-frame T, defect."""
+    torch.manual_seed(11)
+    tnet = rb.registry.get_model_class("t_net").load_representation(model.reaction_model, n_feat=64, tau0=30.0,
+                                                                     dropout_rate=0.0).to("cuda").eval()
+    frames = [make_crconi_supercell(4, seed=21, jitter=0.04), make_crconi_supercell(3, seed=22, jitter=0.02),
+              make_crconi_supercell(4, seed=23, jitter=0.0)]
+    Ts, defects = [900.0, 700.0, 1200.0], [1 / 256, 1 / 108, 1 / 256]
+    graphs = []
+    for a, T, d in zip(frames, Ts, defects):
+        g = rb.AtomsGraph.from_ase(a, tnet.cutoff, read_properties=False, neighborlist_backend="ase", add_batch=True)
+        g.T = torch.tensor(T, dtype=torch.float32)
+        g.defect = torch.tensor(d, dtype=torch.float32)
+        graphs.append(g)
+    batch = rb.batch_to(next(iter(rb.DataLoader(rb.AtomsDataset(graphs), batch_size=8))), "cuda")
+    with torch.no_grad():
+        got = tnet(batch, inference=True)["time"].cpu().numpy()
+    assert got.shape == (3,) and np.all(got > 0) and np.all(got < tnet.tau)
+    L = tnet.time_output.layers
+    head = {"w0": L[0].weight, "b0": L[0].bias, "w1": L[3].weight, "b1": L[3].bias, "w2": L[6].weight, "b2": L[6].bias}
+    head = {k: v.detach().cpu().double().numpy() for k, v in head.items()}
+    m64 = PaiNNOracle.load(os.path.join(GOLD, "model_trained"), dtype=torch.float64)
+    Z = np.concatenate([f.numbers for f in frames])
+    pos = np.concatenate([f.positions for f in frames]).astype(np.float32)
+    cells = np.stack([np.asarray(f.cell, dtype=np.float64) for f in frames])
+    ptr = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(np.int32)
+    with torch.no_grad():
+        ref = m64.time_forward(Z, pos, cells, ptr, Ts, defects, head, tau=30.0).numpy()
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) < TOL
+    # t_real of estimate_time.py:15-35 stays finite
+    assert np.all(np.isfinite(-tnet.tau * np.log(1 - got / tnet.tau)))

@@ -125,3 +125,28 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert getattr(lib, name) is not None
     assert lib.rlvd_abi_version() == 1
+
+
+def test_t_net_surface_and_oracle_head(checkpoint_path):
+    """rlsim/time/train.py:44-48: registry.get_model_class("t_net").load_representation(dqn.reaction_model, **cfg)."""
+    import torch
+    from oracle.painn_oracle import PaiNNOracle, TIME_HEAD_SPEC_V0
+    dqn = rb.registry.get_model_class("dqn_v2").load(checkpoint_path)
+    tnet = rb.registry.get_model_class("t_net").load_representation(dqn.reaction_model, n_feat=32, tau0=12.0)
+    assert tnet.tau == 12.0 and tnet.tau0 == 12.0 and tnet.cutoff == 5.0
+    assert tnet.representation is dqn.reaction_model.representation          # shared weights, same kernels
+    assert {"time_output.layers.0.weight", "time_output.layers.6.bias"} <= set(tnet.state_dict())
+    g = rb.AtomsGraph.from_ase(make_crconi_supercell(2, seed=1), 5.0)
+    g.T, g.defect = torch.tensor(900.0), torch.tensor(1 / 32)
+    batch = next(iter(rb.DataLoader(rb.AtomsDataset([g, g]), batch_size=8)))
+    assert batch["T"].shape == (2,) and batch.num_graphs == 2
+    with pytest.raises(RuntimeError):
+        tnet.eval()(batch, inference=True)                                    # CPU batch: no fallback
+    # the oracle head is monotone in its logit and bounded by tau
+    s = make_crconi_supercell(2, seed=1)
+    m = PaiNNOracle.load(checkpoint_path, dtype=torch.float64)
+    head = {"w0": np.zeros((4, 130)), "b0": np.zeros(4), "w1": np.zeros((4, 4)), "b1": np.zeros(4),
+            "w2": np.zeros((1, 4)), "b2": np.array([0.0])}
+    t = m.time_forward(s.numbers, s.positions.astype(np.float32), np.asarray(s.cell)[None], np.array([0, len(s)]),
+                       [900.0], [1 / 32], head, tau=12.0)
+    assert TIME_HEAD_SPEC_V0.squash == "tau * sigmoid" and float(t[0]) == pytest.approx(6.0)
