@@ -124,11 +124,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
                  "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
 }
+// TMEM loads carry no "memory" clobber: they touch no memory the compiler knows about, and a clobber would pin every
+// shared-memory load of the next group behind this group's FMAs (no software pipelining across groups).  The wait
+// takes the loaded registers as in/out operands so that their uses stay behind it.
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr)
-                 : "memory");
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld8(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -476,6 +482,7 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
     const uint32_t dcol0 = c.tmem + ((uint32_t)(c.quarter * 32) << 16) + TM_D + (uint32_t)(pipe * 2) * TE;
     const uint8_t* tb = c.tab + lane * 4 + T_OFF;
     float* qp = q + ((int64_t)c.node0 * F + c.ch);
+    float* mup = mu_out + ((int64_t)c.node0 * 3 * F + c.ch);
 
     int cur = c.ra;
     float acc[NACC][2];
@@ -501,8 +508,8 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
         // consumed after this tile's groups (their L2 / HBM latency hides behind the tile); the rare further ones follow.
         float cv[9];
         int64_t co = 0;
-        const bool comb = RLVD_SPLIT && ROLE == 0 && t >= 2 && n2 > 0;
-        if (!RLVD_SPLIT && ROLE == 0 && t >= 2 && n2 > 0) {
+        const bool comb = RLVD_SPLIT && HAS_MU && ROLE == 0 && t >= 2 && n2 > 0;
+        if (!RLVD_SPLIT && HAS_MU && ROLE == 0 && t >= 2 && n2 > 0) {
             if (lane == 0) st_wait(&S->acc_free[pipe][bi], ph ^ 1u);
             __syncwarp();
             combine_mu<HAS_MU>(c, (ps + 2) & 3, n2, mu_in, mu_out);
@@ -556,7 +563,10 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
                 if (ROLE == 0) {
                     qp[(int64_t)cur * F] = qbase + (acc[0][0] + acc[0][1]);
                     qbase = qp[(int64_t)(cur + 1) * F];
-                    if (lane == 0) S->chg[pipe][ps][nchg] = cur;
+                    if (HAS_MU && lane == 0) S->chg[pipe][ps][nchg] = cur;
+                } else if (!HAS_MU) {                              // layer 0: mu = dmuR, role 1 owns the rows outright
+#pragma unroll
+                    for (int a = 0; a < NACC; ++a) mup[(int64_t)cur * 3 * F + a * F] = acc[a][0] + acc[a][1];
                 } else {
 #pragma unroll
                     for (int a = 0; a < NACC; ++a) part[(nchg * PART_ROWS + a) * SL] = acc[a][0] + acc[a][1];
@@ -566,7 +576,7 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
 #pragma unroll
                 for (int a = 0; a < NACC; ++a) acc[a][0] = acc[a][1] = 0.f;
             }
-            tmem_wait_ld();
+            tmem_wait_ld8(f);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const float w = __uint_as_float(f[u]);
@@ -598,8 +608,17 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
         __syncwarp();
         if (lane == 0) mbar_arrive(&S->acc_free[pipe][bi]);
     }
-    // ---- the receiver still in flight: once every role has left the last tile, drop its sums into slot 0 of the
-    //      next partial buffer; role 0 then writes the rows of the last two tiles and that one
+    // ---- the receiver still in flight
+    if (!HAS_MU) {                                                 // layer 0: every role owns its rows
+        if (ROLE == 0) qp[(int64_t)cur * F] = qbase + (acc[0][0] + acc[0][1]);
+        else {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) mup[(int64_t)cur * 3 * F + a * F] = acc[a][0] + acc[a][1];
+        }
+        return;
+    }
+    // once every role has left the last tile, drop its sums into slot 0 of the next partial buffer; role 0 then
+    // writes the rows of the last two tiles and that one
     const uint32_t lb = (uint32_t)(n_tiles - 1) & 1u, lph = ((uint32_t)(n_tiles - 1) >> 1) & 1u;
     st_wait(&S->acc_free[pipe][lb], lph);
     if (ROLE == 0) {
