@@ -119,6 +119,7 @@ struct rlvd_engine {
     int64_t launches = 0;
     bool use_tensor_cores = true;
     bool use_sliced_edge = true;    // structure-resident edge kernels when every structure has <= 256 atoms
+    bool fuse_mlp = true;           // Linear -> SiLU -> Linear pairs as one tcgen05 launch (tc_linear.cu two-layer mode)
     int sliced_impl = 1;            // 1 = edge stream (edge_stream.cu), 0 = first sliced kernel (tc_edge_small.cu)
     bool profiling = false;
     std::vector<rlvd::ProfSpan> spans;
@@ -159,6 +160,12 @@ struct LinearArgs {
     float* Y = nullptr;
     int ldy = 0;
     int act = 0;                  // 0 none, 1 SiLU
+    // optional second layer fused behind the first (tc_linear.cu, N == 128 only): Y = act2(act(A W^T + b) W2^T + b2);
+    // Y / ldy then describe the [M, N2] output and the hidden tile never leaves the SM
+    const void* W2fmt = nullptr;
+    const float* bias2 = nullptr;
+    int N2 = 0;
+    int act2 = 0;
 };
 int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a);
 int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt);

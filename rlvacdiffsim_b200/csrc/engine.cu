@@ -349,15 +349,21 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
         return 1;
     if (launch_embed(e, s, M, d_Z, d_q)) return 1;
     for (int l = 0; l < NLAYER; ++l) {
-        // R5 node part: x = Lin3(SiLU(Lin0(q)))
+        // R5 node part: x = Lin3(SiLU(Lin0(q)))   (one launch: the hidden tile stays on the SM)
         LinearArgs a0;
         a0.A = d_q; a0.lda = F; a0.M = M; a0.K = F; a0.N = F; a0.Wt = w.inter_w0T[l]; a0.Wfmt = w.inter_w0F[l]; a0.bias = w.inter_b0[l];
-        a0.Y = hid; a0.ldy = F; a0.act = 1;
-        if (launch_linear(e, s, a0)) return 1;
-        LinearArgs a1;
-        a1.A = hid; a1.lda = F; a1.M = M; a1.K = F; a1.N = 3 * F; a1.Wt = w.inter_w3T[l]; a1.Wfmt = w.inter_w3F[l]; a1.bias = w.inter_b3[l];
-        a1.Y = x; a1.ldy = 3 * F; a1.act = 0;
-        if (launch_linear(e, s, a1)) return 1;
+        a0.act = 1;
+        if (e->use_tensor_cores && e->fuse_mlp) {
+            a0.W2fmt = w.inter_w3F[l]; a0.bias2 = w.inter_b3[l]; a0.N2 = 3 * F; a0.act2 = 0; a0.Y = x; a0.ldy = 3 * F;
+            if (launch_linear(e, s, a0)) return 1;
+        } else {
+            a0.Y = hid; a0.ldy = F;
+            if (launch_linear(e, s, a0)) return 1;
+            LinearArgs a1;
+            a1.A = hid; a1.lda = F; a1.M = M; a1.K = F; a1.N = 3 * F; a1.Wt = w.inter_w3T[l]; a1.Wfmt = w.inter_w3F[l]; a1.bias = w.inter_b3[l];
+            a1.Y = x; a1.ldy = 3 * F; a1.act = 0;
+            if (launch_linear(e, s, a1)) return 1;
+        }
         // R2 + R3 + R5 edge part + K4
         EdgeArgs ea;
         ea.layer = l; ea.M = M; ea.sliced = sliced; ea.n_struct = n_struct; ea.max_struct_nodes = max_struct_nodes; ea.node_ptr = d_node_ptr;
@@ -373,12 +379,18 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
         if (launch_mix_reduce(e, s, M, mix, nrm, vw)) return 1;
         LinearArgs b0;
         b0.A = d_q; b0.lda = F; b0.A2 = nrm; b0.lda2 = F; b0.K1 = F; b0.M = M; b0.K = 2 * F; b0.N = F;
-        b0.Wt = w.intra_w0T[l]; b0.Wfmt = w.intra_w0F[l]; b0.bias = w.intra_b0[l]; b0.Y = hid; b0.ldy = F; b0.act = 1;
-        if (launch_linear(e, s, b0)) return 1;
-        LinearArgs b1;
-        b1.A = hid; b1.lda = F; b1.M = M; b1.K = F; b1.N = 3 * F; b1.Wt = w.intra_w3T[l]; b1.Wfmt = w.intra_w3F[l]; b1.bias = w.intra_b3[l];
-        b1.Y = ctx; b1.ldy = 3 * F; b1.act = 0;
-        if (launch_linear(e, s, b1)) return 1;
+        b0.Wt = w.intra_w0T[l]; b0.Wfmt = w.intra_w0F[l]; b0.bias = w.intra_b0[l]; b0.act = 1;
+        if (e->use_tensor_cores && e->fuse_mlp) {
+            b0.W2fmt = w.intra_w3F[l]; b0.bias2 = w.intra_b3[l]; b0.N2 = 3 * F; b0.act2 = 0; b0.Y = ctx; b0.ldy = 3 * F;
+            if (launch_linear(e, s, b0)) return 1;
+        } else {
+            b0.Y = hid; b0.ldy = F;
+            if (launch_linear(e, s, b0)) return 1;
+            LinearArgs b1;
+            b1.A = hid; b1.lda = F; b1.M = M; b1.K = F; b1.N = 3 * F; b1.Wt = w.intra_w3T[l]; b1.Wfmt = w.intra_w3F[l]; b1.bias = w.intra_b3[l];
+            b1.Y = ctx; b1.ldy = 3 * F; b1.act = 0;
+            if (launch_linear(e, s, b1)) return 1;
+        }
         if (launch_mix_update(e, s, M, ctx, mix, vw, d_q, mu_cur)) return 1;
     }
     if (d_mu != nullptr)
@@ -481,6 +493,10 @@ int rlvd_set_option(rlvd_engine* e, const char* name, int32_t value) {
     }
     if (strcmp(name, "sliced_edge") == 0) {
         e->use_sliced_edge = value != 0;
+        return 0;
+    }
+    if (strcmp(name, "fuse_mlp") == 0) {
+        e->fuse_mlp = value != 0;
         return 0;
     }
     if (strcmp(name, "sliced_impl") == 0) {

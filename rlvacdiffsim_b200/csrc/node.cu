@@ -195,6 +195,8 @@ __global__ void mix_update_kernel(int M, const float* __restrict__ ctx, const fl
 
 int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a) {
     if (e->use_tensor_cores && a.Wfmt != nullptr && tc_linear_supported(a)) return launch_tc_linear(e, s, a, a.Wfmt);
+    RLVD_CHECK(a.W2fmt == nullptr, "linear: the fused two-layer form exists on the tcgen05 path only (shape M=%d K=%d N=%d N2=%d)",
+               a.M, a.K, a.N, a.N2);
     RLVD_CHECK(a.Wt != nullptr, "linear: no fp32 weight for the SIMT path");
     RLVD_CHECK(a.K % KC == 0, "linear: K=%d is not a multiple of %d", a.K, KC);
     RLVD_CHECK(a.A2 == nullptr || a.K1 % KC == 0, "linear: K1=%d is not a multiple of %d", a.K1, KC);

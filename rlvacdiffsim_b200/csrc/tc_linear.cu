@@ -22,6 +22,10 @@
 //              tcgen05.commit arrivals that free weight stages / A buffers and publish accumulators
 // K = 256 (the [q | n] concatenation of the intra-atomic net) runs as two 128-k phases through the same A
 // buffers, accumulating in TMEM.  Every mbarrier wait is bounded (trap, never hang).
+// Two-layer mode (LinearArgs::W2fmt): the interatomic / intraatomic context nets are Linear -> SiLU -> Linear with a
+// 128-wide hidden layer.  The epilogue of the first GEMM writes SiLU(hidden) straight into the A operand buffers (fp16
+// hi/lo, core-matrix layout) and the second GEMM runs from there: the hidden activations never touch HBM and are never
+// staged or converted a second time.
 // Weights are formatted once on the host (rlvd_finalize_weights).
 #include <cuda_fp16.h>
 
@@ -94,7 +98,8 @@ __device__ __forceinline__ void stage_A_async(const LinearArgs& a, int tile, int
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearArgs a, const uint8_t* __restrict__ Wfmt) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearArgs a, const uint8_t* __restrict__ Wfmt,
+                                                                  const uint8_t* __restrict__ W2fmt) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* A_hi = smem;                              // 32 KB  [16 core columns][16 row groups][8 rows][16 B]
     uint8_t* A_lo = smem + 32768;                      // 32 KB
@@ -103,6 +108,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
     uint8_t* Yst = Bst + TC_NSTAGE * TC_STAGE_BYTES;   // 32 KB  [128 rows][64 cols] fp32 output staging (swizzled)
     TcSmem* S = reinterpret_cast<TcSmem*>(Yst + 32768);
     float* bias_s = reinterpret_cast<float*>(Yst + 32768 + 128);      // [N <= 384] bias staged once (zeros when absent)
+    const bool two = W2fmt != nullptr;
+    float* bias2_s = bias_s + 128;                                     // [N2 <= 384] second-layer bias (two-layer mode: N == 128)
+    const int NB2 = two ? a.N2 / TC_N : 0;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = (a.M + TC_M - 1) / TC_M;
@@ -116,6 +124,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < a.N; i += TC_THREADS) bias_s[i] = a.bias != nullptr ? __ldg(a.bias + i) : 0.f;
+    for (int i = tid; i < (two ? a.N2 : 0); i += TC_THREADS) bias2_s[i] = a.bias2 != nullptr ? __ldg(a.bias2 + i) : 0.f;
     if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S->tmem_base)),
                      "r"(512u)
@@ -158,8 +167,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                 if (phase + 1 < NPH) stage_A_async(a, tile, phase + 1, ast, t);
                 else if (tile + (int)gridDim.x < n_tiles) stage_A_async(a, tile + gridDim.x, 0, ast, t);
             }
+            if (two) {
+                // ---- hidden layer: TMEM -> registers -> bias/SiLU -> fp16 hi/lo -> A operand buffers (no HBM, no staging)
+                const uint32_t buf = acc_it & 1;
+                mbar_wait(&S->acc_full[buf], (acc_it >> 1) & 1);
+                mbar_wait(&S->a_free, (ph_it & 1) ^ 1);           // the first layer's MMAs have finished reading A
+                tc_fence_after();
+#pragma unroll 1
+                for (int sgm = 0; sgm < 2; ++sgm) {
+                    const int c0 = 64 * sgm + 32 * h;
+                    const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + c0;
+                    uint32_t d0[32], d1[32];
+                    tmem_ld32(t0, d0);
+                    tmem_ld32(t0 + 128, d1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (sgm == 1) {
+                        tc_fence_before();
+                        mbar_arrive(&S->acc_empty[buf]);
+                    }
+                    const uint32_t hrow = (er >> 3) * CORE_SBO + (er & 7) * 16;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float y[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            float v = fmaf(__uint_as_float(d1[j + u]), 1.0f / 2048.0f, __uint_as_float(d0[j + u])) + bias_s[c0 + j + u];
+                            if (a.act == 1) v = __fdividef(v, 1.0f + __expf(-v));
+                            y[u] = v;
+                        }
+                        uint4 H, L;
+                        split8(make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]), H, L);
+                        const int kc = (c0 + j) >> 3;
+                        *reinterpret_cast<uint4*>(A_hi + kc * CORE_LBO + hrow) = H;
+                        *reinterpret_cast<uint4*>(A_lo + kc * CORE_LBO + hrow) = L;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&S->a_ready);
+                ++acc_it;
+                ++ph_it;
+            }
             // ---- epilogue: TMEM → registers → bias/SiLU → swizzled staging → coalesced global stores
-            for (int nb = 0; nb < NB; ++nb, ++acc_it) {
+            const int NBo = two ? NB2 : NB;
+            const float* bias_o = two ? bias2_s : bias_s;
+            const int act_o = two ? a.act2 : a.act;
+            for (int nb = 0; nb < NBo; ++nb, ++acc_it) {
                 const uint32_t buf = acc_it & 1;
                 mbar_wait(&S->acc_full[buf], (acc_it >> 1) & 1);
                 tc_fence_after();
@@ -179,12 +231,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float y[4];
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col0 + j);
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_o + col0 + j);
                         const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             float v = fmaf(__uint_as_float(d1[j + u]), 1.0f / 2048.0f, __uint_as_float(d0[j + u])) + bb[u];
-                            if (a.act == 1) v = __fdividef(v, 1.0f + __expf(-v));   // SiLU; |error| < 2e-7 of max(|v|, 1)
+                            if (act_o == 1) v = __fdividef(v, 1.0f + __expf(-v));   // SiLU; |error| < 2e-7 of max(|v|, 1)
                             y[u] = v;
                         }
                         const int lc = h * 8 + (j >> 2);
@@ -209,7 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
         if (lane == 0) {
             uint32_t cnt = 0;
             const int KSN = a.K / TC_KS;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int phase = 0; phase < NPH; ++phase)
                     for (int nb = 0; nb < NB; ++nb)
                         for (int ksl = 0; ksl < 128 / TC_KS; ++ksl, ++cnt) {
@@ -220,13 +272,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                             bulk_g2s(Bst + s * TC_STAGE_BYTES, Wfmt + (size_t)(nb * KSN + ks) * TC_STAGE_BYTES,
                                      TC_STAGE_BYTES, &S->full[s]);
                         }
+                for (int nb = 0; nb < NB2; ++nb)                               // second layer: K = 128 hidden units
+                    for (int ksl = 0; ksl < 128 / TC_KS; ++ksl, ++cnt) {
+                        const uint32_t s = cnt % TC_NSTAGE, ph = (cnt / TC_NSTAGE) & 1;
+                        mbar_wait(&S->empty[s], ph ^ 1);
+                        mbar_expect_tx(&S->full[s], TC_STAGE_BYTES);
+                        bulk_g2s(Bst + s * TC_STAGE_BYTES, W2fmt + (size_t)(nb * (128 / TC_KS) + ksl) * TC_STAGE_BYTES,
+                                 TC_STAGE_BYTES, &S->full[s]);
+                    }
+            }
         }
     } else {
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t cnt = 0, acc_base = 0, ph_it = 0;
             const uint32_t a_hi0 = smem_u32(A_hi), a_lo0 = smem_u32(A_lo), b0 = smem_u32(Bst);
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, acc_base += NB) {
+            auto kstages = [&](uint32_t d0, uint32_t d1, int k_first_stage, bool first) {
+                for (int ksl = 0; ksl < 128 / TC_KS; ++ksl, ++cnt) {
+                    const uint32_t s = cnt % TC_NSTAGE, ph = (cnt / TC_NSTAGE) & 1;
+                    mbar_wait(&S->full[s], ph);
+                    tc_fence_after();
+                    const uint32_t bh = b0 + s * TC_STAGE_BYTES, bl = bh + TC_HALF_STAGE;
+#pragma unroll
+                    for (int j = 0; j < TC_KS / 16; ++j) {
+                        const uint32_t koff_a = (uint32_t)(ksl * (TC_KS / 8) + 2 * j) * CORE_LBO;
+                        const uint32_t koff_b = (uint32_t)(2 * j) * CORE_LBO;
+                        const uint32_t acc = (first && ksl == 0 && j == 0) ? 0u : 1u;
+                        umma_f16(d0, make_desc(a_hi0 + koff_a), make_desc(bh + koff_b), acc);
+                        umma_f16(d1, make_desc(a_hi0 + koff_a), make_desc(bl + koff_b), acc);
+                        umma_f16(d1, make_desc(a_lo0 + koff_a), make_desc(bh + koff_b), 1u);
+                    }
+                    umma_commit(&S->empty[s]);                               // frees the weight stage
+                }
+                (void)k_first_stage;
+            };
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, acc_base += NB + NB2) {
                 for (int phase = 0; phase < NPH; ++phase, ++ph_it) {
                     mbar_wait(&S->a_ready, ph_it & 1);
                     tc_fence_after();
@@ -237,25 +317,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                             tc_fence_after();
                         }
                         const uint32_t d0 = tmem + buf * 256, d1 = d0 + 128;
-                        for (int ksl = 0; ksl < 128 / TC_KS; ++ksl, ++cnt) {
-                            const uint32_t s = cnt % TC_NSTAGE, ph = (cnt / TC_NSTAGE) & 1;
-                            mbar_wait(&S->full[s], ph);
-                            tc_fence_after();
-                            const uint32_t bh = b0 + s * TC_STAGE_BYTES, bl = bh + TC_HALF_STAGE;
-#pragma unroll
-                            for (int j = 0; j < TC_KS / 16; ++j) {
-                                const uint32_t koff_a = (uint32_t)(ksl * (TC_KS / 8) + 2 * j) * CORE_LBO;
-                                const uint32_t koff_b = (uint32_t)(2 * j) * CORE_LBO;
-                                const uint32_t acc = (phase == 0 && ksl == 0 && j == 0) ? 0u : 1u;
-                                umma_f16(d0, make_desc(a_hi0 + koff_a), make_desc(bh + koff_b), acc);
-                                umma_f16(d1, make_desc(a_hi0 + koff_a), make_desc(bl + koff_b), acc);
-                                umma_f16(d1, make_desc(a_lo0 + koff_a), make_desc(bh + koff_b), 1u);
-                            }
-                            umma_commit(&S->empty[s]);                       // frees the weight stage
-                        }
+                        kstages(d0, d1, phase * (128 / TC_KS), phase == 0);
                         if (phase == NPH - 1) umma_commit(&S->acc_full[buf]);  // publishes (D0, D1)
                     }
                     umma_commit(&S->a_free);                                 // A buffers may be overwritten
+                }
+                if (two) {                                                   // second layer from the hidden tile in A
+                    mbar_wait(&S->a_ready, ph_it & 1);
+                    tc_fence_after();
+                    for (int nb = 0; nb < NB2; ++nb) {
+                        const uint32_t acc_it = acc_base + NB + nb, buf = acc_it & 1;
+                        mbar_wait(&S->acc_empty[buf], ((acc_it >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t d0 = tmem + buf * 256, d1 = d0 + 128;
+                        kstages(d0, d1, 0, true);
+                        umma_commit(&S->acc_full[buf]);
+                    }
+                    umma_commit(&S->a_free);
+                    ++ph_it;
                 }
             }
         }
@@ -268,7 +347,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
     }
 }
 
-size_t tc_smem_bytes(int) { return (size_t)131072 + TC_NSTAGE * TC_STAGE_BYTES + 32768 + 128 + 384 * 4 + 64; }
+size_t tc_smem_bytes(int) { return (size_t)131072 + TC_NSTAGE * TC_STAGE_BYTES + 32768 + 128 + 512 * 4 + 64; }
+static_assert(131072 + TC_NSTAGE * TC_STAGE_BYTES + 32768 + 128 + 512 * 4 + 64 <= 232448, "shared memory budget");
 static_assert(sizeof(TcSmem) <= 128, "TcSmem must fit its 128-byte slot");
 
 }  // namespace
@@ -295,6 +375,7 @@ void tc_format_weight(const float* W, int N, int K, std::vector<uint8_t>& out) {
 
 bool tc_linear_supported(const LinearArgs& a) {
     const bool k_ok = a.K == 128 || (a.K == 256 && a.N <= 2 * TC_N);   // K=256 keeps every N-block's accumulator live
+    if (a.W2fmt != nullptr && (a.N != TC_N || a.N2 % TC_N != 0 || a.N2 <= 0 || a.N2 > 384)) return false;
     return a.N % TC_N == 0 && a.N <= 384 && k_ok && (a.A2 == nullptr || a.K1 == 128) && a.lda % 4 == 0 && a.ldy % 4 == 0;
 }
 
@@ -310,7 +391,8 @@ int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const 
     const int n_tiles = (a.M + TC_M - 1) / TC_M;
     const int grid = n_tiles < e->sm_count ? n_tiles : e->sm_count;
     Span sp(e, s, FAM_NODE);
-    tc_linear_kernel<<<grid, TC_THREADS, tc_smem_bytes(a.K), s>>>(a, reinterpret_cast<const uint8_t*>(Wfmt));
+    tc_linear_kernel<<<grid, TC_THREADS, tc_smem_bytes(a.K), s>>>(a, reinterpret_cast<const uint8_t*>(Wfmt),
+                                                                  reinterpret_cast<const uint8_t*>(a.W2fmt));
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;

@@ -169,7 +169,7 @@ def test_host_path_equals_device_path(model, engine):
     assert np.array_equal(q[0], dev["rl_q"])
     before = engine.launch_count()
     scorer.score([atoms], [g["actions"].tolist()], {"alpha": 0.0, "beta": 1.0, "dqn": True, "temperature": 700.0})
-    assert engine.launch_count() - before >= 30       # our kernels ran, not a library fallback
+    assert engine.launch_count() - before >= 20       # our kernels ran, not a library fallback
 
 
 def test_replica_batch_matches_single_and_oracle(model):
