@@ -143,7 +143,8 @@ int  rlvd_linear(rlvd_engine* e, void* stream, int32_t M, int32_t K, int32_t N, 
 /* Engine options: "tensor_cores" (1 = tcgen05 GEMMs and filters, 0 = fp32 SIMT kernels; both fp32-accurate),
  * "sliced_edge" (1 = structure-resident edge kernels for structures of <= 256 atoms, 0 = general),
  * "sliced_impl" (1 = edge stream, edge_stream.cu; 0 = first sliced kernel, tc_edge_small.cu),
- * "fuse_mlp" (1 = each Linear-SiLU-Linear context net is one launch with the hidden tile kept on the SM). */
+ * "fuse_mlp" (1 = each Linear-SiLU-Linear context net is one launch with the hidden tile kept on the SM),
+ * "fuse_mix" (1 = the |mu_V| and <mu_V, mu_W> reductions run in the mu_channel_mix GEMM epilogue). */
 int  rlvd_set_option(rlvd_engine* e, const char* name, int32_t value);
 
 /* ---- introspection ------------------------------------------------------------------------------ */

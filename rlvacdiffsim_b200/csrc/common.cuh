@@ -119,6 +119,8 @@ struct rlvd_engine {
     int64_t launches = 0;
     bool use_tensor_cores = true;
     bool use_sliced_edge = true;    // structure-resident edge kernels when every structure has <= 256 atoms
+    bool fuse_mix = false;          // nrm / vw reductions inside the mu_channel_mix GEMM epilogue (tc_linear.cu mixred mode);
+                                    // measured 0.3 ms/step SLOWER than GEMM + reduction kernel (the epilogue is the GEMM's bottleneck)
     bool fuse_mlp = true;           // Linear -> SiLU -> Linear pairs as one tcgen05 launch (tc_linear.cu two-layer mode)
     int sliced_impl = 1;            // 1 = edge stream (edge_stream.cu), 0 = first sliced kernel (tc_edge_small.cu)
     bool profiling = false;
@@ -166,6 +168,14 @@ struct LinearArgs {
     const float* bias2 = nullptr;
     int N2 = 0;
     int act2 = 0;
+    // mu_channel_mix with the equivariant reductions fused into its epilogue (tc_linear.cu, K = 128, N = 256, no bias):
+    // A = mu as [3*n_nodes, 128] rows (node, component); the epilogue forms nrm = sqrt(sum_c V_c^2 + eps) and
+    // vw = sum_c V_c W_c per node and writes only W (Y, [3*n_nodes, 128]) — V never reaches HBM
+    int mixred = 0;
+    int n_nodes = 0;
+    float* nrm = nullptr;
+    float* vw = nullptr;
+    float eps = 1e-8f;
 };
 int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a);
 int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt);
@@ -208,7 +218,7 @@ int launch_tc_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* 
                    const float* x, const float* mu_in, float* q, float* mu_out);
 void tc_edge_format_filters(const float* W, const float* b, std::vector<uint8_t>& out);
 int launch_mix_reduce(rlvd_engine* e, cudaStream_t s, int M, const float* mix, float* nrm, float* vw);
-int launch_mix_update(rlvd_engine* e, cudaStream_t s, int M, const float* ctx, const float* mix,
+int launch_mix_update(rlvd_engine* e, cudaStream_t s, int M, const float* ctx, const float* W, int ldw,
                       const float* vw, float* q, float* mu);
 int launch_readout(rlvd_engine* e, cudaStream_t s, int n_react, const int* node_ptr, const int* rs,
                    const int* ps, const int* Z, const float* q, const rlvd_q_params& qp, const float* d_temp,

@@ -374,9 +374,16 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
         // R6: mixing
         LinearArgs am;
         am.A = mu_cur; am.lda = F; am.M = 3 * M; am.K = F; am.N = 2 * F; am.Wt = w.mix_wT[l]; am.Wfmt = w.mix_wF[l]; am.bias = nullptr;
-        am.Y = mix; am.ldy = 2 * F; am.act = 0;
-        if (launch_linear(e, s, am)) return 1;
-        if (launch_mix_reduce(e, s, M, mix, nrm, vw)) return 1;
+        am.act = 0;
+        const bool fused_mix = e->use_tensor_cores && e->fuse_mix;
+        if (fused_mix) {                                  // nrm, vw from the GEMM epilogue; `mix` holds W only, [3M, F]
+            am.mixred = 1; am.n_nodes = M; am.nrm = nrm; am.vw = vw; am.Y = mix; am.ldy = F;
+            if (launch_linear(e, s, am)) return 1;
+        } else {
+            am.Y = mix; am.ldy = 2 * F;
+            if (launch_linear(e, s, am)) return 1;
+            if (launch_mix_reduce(e, s, M, mix, nrm, vw)) return 1;
+        }
         LinearArgs b0;
         b0.A = d_q; b0.lda = F; b0.A2 = nrm; b0.lda2 = F; b0.K1 = F; b0.M = M; b0.K = 2 * F; b0.N = F;
         b0.Wt = w.intra_w0T[l]; b0.Wfmt = w.intra_w0F[l]; b0.bias = w.intra_b0[l]; b0.act = 1;
@@ -391,7 +398,7 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
             b1.Y = ctx; b1.ldy = 3 * F; b1.act = 0;
             if (launch_linear(e, s, b1)) return 1;
         }
-        if (launch_mix_update(e, s, M, ctx, mix, vw, d_q, mu_cur)) return 1;
+        if (launch_mix_update(e, s, M, ctx, fused_mix ? mix : mix + F, fused_mix ? F : 2 * F, vw, d_q, mu_cur)) return 1;
     }
     if (d_mu != nullptr)
         RLVD_CUDA(cudaMemcpyAsync(d_mu, mu_cur, 3 * MF, cudaMemcpyDeviceToDevice, s));
@@ -493,6 +500,10 @@ int rlvd_set_option(rlvd_engine* e, const char* name, int32_t value) {
     }
     if (strcmp(name, "sliced_edge") == 0) {
         e->use_sliced_edge = value != 0;
+        return 0;
+    }
+    if (strcmp(name, "fuse_mix") == 0) {
+        e->fuse_mix = value != 0;
         return 0;
     }
     if (strcmp(name, "fuse_mlp") == 0) {

@@ -168,8 +168,8 @@ __global__ void mix_reduce_kernel(int M, const float* __restrict__ mix, float* _
     reinterpret_cast<float4*>(vw)[idx] = dot;
 }
 
-// ctx[M][384] = [a | b | c];  q += a + c*vw;  mu[k] += b * W[k]
-__global__ void mix_update_kernel(int M, const float* __restrict__ ctx, const float* __restrict__ mix,
+// ctx[M][384] = [a | b | c];  q += a + c*vw;  mu[k] += b * W[k]   (W row (i, k) at W + (3 i + k) * ldw)
+__global__ void mix_update_kernel(int M, const float* __restrict__ ctx, const float* __restrict__ W, int ldw,
                                   const float* __restrict__ vw, float* __restrict__ q, float* __restrict__ mu) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)M * (F / 4)) return;
@@ -183,7 +183,7 @@ __global__ void mix_update_kernel(int M, const float* __restrict__ ctx, const fl
     reinterpret_cast<float4*>(q)[idx] = qv;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(mix + ((int64_t)i * 3 + k) * 2 * F + F) + c4);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(W + ((int64_t)i * 3 + k) * ldw) + c4);
         float4* mp = reinterpret_cast<float4*>(mu + ((int64_t)i * 3 + k) * F) + c4;
         float4 m = *mp;
         m.x = fmaf(b.x, w.x, m.x); m.y = fmaf(b.y, w.y, m.y); m.z = fmaf(b.z, w.z, m.z); m.w = fmaf(b.w, w.w, m.w);
@@ -195,6 +195,7 @@ __global__ void mix_update_kernel(int M, const float* __restrict__ ctx, const fl
 
 int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a) {
     if (e->use_tensor_cores && a.Wfmt != nullptr && tc_linear_supported(a)) return launch_tc_linear(e, s, a, a.Wfmt);
+    RLVD_CHECK(a.mixred == 0, "linear: the mix-reduce form exists on the tcgen05 path only (M=%d n_nodes=%d)", a.M, a.n_nodes);
     RLVD_CHECK(a.W2fmt == nullptr, "linear: the fused two-layer form exists on the tcgen05 path only (shape M=%d K=%d N=%d N2=%d)",
                a.M, a.K, a.N, a.N2);
     RLVD_CHECK(a.Wt != nullptr, "linear: no fp32 weight for the SIMT path");
@@ -239,12 +240,12 @@ int launch_mix_reduce(rlvd_engine* e, cudaStream_t s, int M, const float* mix, f
     return 0;
 }
 
-int launch_mix_update(rlvd_engine* e, cudaStream_t s, int M, const float* ctx, const float* mix, const float* vw,
+int launch_mix_update(rlvd_engine* e, cudaStream_t s, int M, const float* ctx, const float* W, int ldw, const float* vw,
                       float* q, float* mu) {
     if (M <= 0) return 0;
     Span sp(e, s, FAM_NODE);
     const int64_t n = (int64_t)M * (F / 4);
-    mix_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(M, ctx, mix, vw, q, mu);
+    mix_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(M, ctx, W, ldw, vw, q, mu);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;

@@ -26,6 +26,11 @@
 // 128-wide hidden layer.  The epilogue of the first GEMM writes SiLU(hidden) straight into the A operand buffers (fp16
 // hi/lo, core-matrix layout) and the second GEMM runs from there: the hidden activations never touch HBM and are never
 // staged or converted a second time.
+// Mix-reduce mode (LinearArgs::mixred): mu_channel_mix maps every (node, component) row of mu to [V | W].  A 128-row
+// tile is laid out as 4 warps x (10 nodes x 3 components) + 2 idle rows, so the three components of a node sit in
+// adjacent TMEM lanes of ONE warp; the epilogue reads V and W of a tile from the two accumulator buffers, forms
+// nrm = sqrt(sum_c V_c^2 + eps) and vw = sum_c V_c W_c with two warp shuffles per value and stores nrm, vw and W.
+// V never reaches HBM and the separate reduction kernel (and its 8 x [M,128] of traffic) is gone.
 // Weights are formatted once on the host (rlvd_finalize_weights).
 #include <cuda_fp16.h>
 
@@ -81,6 +86,20 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// Global row of tile row `row`: plain tiles are 128 consecutive rows; mix-reduce tiles hold 40 nodes as
+// 4 warps x 30 rows (+2 idle rows per warp), global row = 120*tile + 30*warp + lane.
+__device__ __forceinline__ int64_t tile_row(const LinearArgs& a, int tile, int row, bool& live) {
+    if (a.mixred) {
+        const int l = row & 31;
+        const int64_t m = (int64_t)tile * 120 + (row >> 5) * 30 + l;
+        live = l < 30 && m < a.M;
+        return m;
+    }
+    const int64_t m = (int64_t)tile * TC_M + row;
+    live = m < a.M;
+    return m;
+}
+
 // Asynchronous, fully coalesced load of one 128-row x 128-k fp32 A phase into the swizzled staging buffer:
 // 16-byte chunk `lc` of row `row` lands at row*512 + ((lc ^ (row & 7)) * 16).
 __device__ __forceinline__ void stage_A_async(const LinearArgs& a, int tile, int phase, uint32_t stage_addr, int t) {
@@ -90,9 +109,9 @@ __device__ __forceinline__ void stage_A_async(const LinearArgs& a, int tile, int
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int id = i * 256 + t, row = id >> 5, lc = id & 31;
-        const int m = tile * TC_M + row;
-        const bool live = m < a.M;
-        const float* src = base + (live ? (int64_t)m * ld : 0) + k0 + lc * 4;
+        bool live;
+        const int64_t m = tile_row(a, tile, row, live);
+        const float* src = base + (live ? m * ld : 0) + k0 + lc * 4;
         cp_async16(stage_addr + row * 512 + ((lc ^ (row & 7)) << 4), src, live ? 16u : 0u);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -113,7 +132,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
     const int NB2 = two ? a.N2 / TC_N : 0;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_tiles = (a.M + TC_M - 1) / TC_M;
+    const int n_tiles = a.mixred ? (a.n_nodes + 39) / 40 : (a.M + TC_M - 1) / TC_M;
     const int NB = a.N / TC_N, NPH = a.K / 128;       // K-phases of 128 (the A buffers hold one phase)
 
     if (tid == 0) {
@@ -166,6 +185,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                 epi_barrier();                               // staging fully consumed → prefetch the next phase
                 if (phase + 1 < NPH) stage_A_async(a, tile, phase + 1, ast, t);
                 else if (tile + (int)gridDim.x < n_tiles) stage_A_async(a, tile + gridDim.x, 0, ast, t);
+            }
+            if (a.mixred) {
+                // ---- V (block 0) and W (block 1) of this tile -> nrm, vw per node; only W is stored
+                const uint32_t bV = acc_it & 1, bW = bV ^ 1;
+                mbar_wait(&S->acc_full[bV], (acc_it >> 1) & 1);
+                mbar_wait(&S->acc_full[bW], ((acc_it + 1) >> 1) & 1);
+                tc_fence_after();
+                bool live_row;
+                const int64_t m_row = tile_row(a, tile, er, live_row);
+                const bool owner = live_row && (lane % 3) == 0;          // lane of component 0 writes the node's nrm / vw
+                const int64_t node = m_row / 3;
+#pragma unroll 1
+                for (int sgm = 0; sgm < 2; ++sgm) {
+#pragma unroll 1
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int c0 = 64 * sgm + 32 * h + 16 * hf;
+                        const uint32_t tV = tmem + ((uint32_t)(q * 32) << 16) + bV * 256 + c0;
+                        const uint32_t tW = tmem + ((uint32_t)(q * 32) << 16) + bW * 256 + c0;
+                        uint32_t v0[16], v1[16], w0[16], w1[16];
+                        tmem_ld16(tV, v0);
+                        tmem_ld16(tV + 128, v1);
+                        tmem_ld16(tW, w0);
+                        tmem_ld16(tW + 128, w1);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        float nr[16], dt[16], wv[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            const float v = fmaf(__uint_as_float(v1[u]), 1.0f / 2048.0f, __uint_as_float(v0[u]));
+                            const float w = fmaf(__uint_as_float(w1[u]), 1.0f / 2048.0f, __uint_as_float(w0[u]));
+                            const float vy = __shfl_down_sync(0xffffffffu, v, 1), vz = __shfl_down_sync(0xffffffffu, v, 2);
+                            const float wy = __shfl_down_sync(0xffffffffu, w, 1), wz = __shfl_down_sync(0xffffffffu, w, 2);
+                            nr[u] = sqrtf(fmaf(vz, vz, fmaf(vy, vy, v * v)) + a.eps);
+                            dt[u] = fmaf(vz, wz, fmaf(vy, wy, v * w));
+                            wv[u] = w;
+                        }
+                        if (owner) {
+                            float4* pn = reinterpret_cast<float4*>(a.nrm + node * TC_N + c0);
+                            float4* pv = reinterpret_cast<float4*>(a.vw + node * TC_N + c0);
+#pragma unroll
+                            for (int u = 0; u < 16; u += 4) {
+                                pn[u >> 2] = make_float4(nr[u], nr[u + 1], nr[u + 2], nr[u + 3]);
+                                pv[u >> 2] = make_float4(dt[u], dt[u + 1], dt[u + 2], dt[u + 3]);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; u += 4) {
+                            const int lc = h * 8 + hf * 4 + (u >> 2);
+                            *reinterpret_cast<float4*>(Yst + er * 256 + ((lc ^ (er & 7)) << 4)) = make_float4(wv[u], wv[u + 1], wv[u + 2], wv[u + 3]);
+                        }
+                    }
+                    if (sgm == 1) {                          // all TMEM reads of both accumulators are done
+                        tc_fence_before();
+                        mbar_arrive(&S->acc_empty[bV]);
+                        mbar_arrive(&S->acc_empty[bW]);
+                    }
+                    epi_barrier();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int id = i * 256 + t, row = id >> 4, lc = id & 15;
+                        bool live;
+                        const int64_t m = tile_row(a, tile, row, live);
+                        if (live) {
+                            const float4 v = *reinterpret_cast<const float4*>(Yst + row * 256 + ((lc ^ (row & 7)) << 4));
+                            *reinterpret_cast<float4*>(a.Y + m * a.ldy + 64 * sgm + lc * 4) = v;
+                        }
+                    }
+                    epi_barrier();
+                }
+                acc_it += 2;
+                continue;
             }
             if (two) {
                 // ---- hidden layer: TMEM -> registers -> bias/SiLU -> fp16 hi/lo -> A operand buffers (no HBM, no staging)
@@ -246,10 +335,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int id = i * 256 + t, row = id >> 4, lc = id & 15;
-                        const int m = tile * TC_M + row;
+                        const int64_t m = (int64_t)tile * TC_M + row;
                         if (m < a.M) {
                             const float4 v = *reinterpret_cast<const float4*>(Yst + row * 256 + ((lc ^ (row & 7)) << 4));
-                            *reinterpret_cast<float4*>(a.Y + (int64_t)m * a.ldy + nb * TC_N + 64 * sgm + lc * 4) = v;
+                            *reinterpret_cast<float4*>(a.Y + m * a.ldy + nb * TC_N + 64 * sgm + lc * 4) = v;
                         }
                     }
                     epi_barrier();
@@ -375,6 +464,9 @@ void tc_format_weight(const float* W, int N, int K, std::vector<uint8_t>& out) {
 
 bool tc_linear_supported(const LinearArgs& a) {
     const bool k_ok = a.K == 128 || (a.K == 256 && a.N <= 2 * TC_N);   // K=256 keeps every N-block's accumulator live
+    if (a.mixred && (a.K != 128 || a.N != 2 * TC_N || a.bias != nullptr || a.A2 != nullptr || a.W2fmt != nullptr ||
+                     a.nrm == nullptr || a.vw == nullptr || a.M != 3 * a.n_nodes))
+        return false;
     if (a.W2fmt != nullptr && (a.N != TC_N || a.N2 % TC_N != 0 || a.N2 <= 0 || a.N2 > 384)) return false;
     return a.N % TC_N == 0 && a.N <= 384 && k_ok && (a.A2 == nullptr || a.K1 == 128) && a.lda % 4 == 0 && a.ldy % 4 == 0;
 }
@@ -388,7 +480,7 @@ int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const 
                                        (int)tc_smem_bytes(256)));
         attr_set = true;
     }
-    const int n_tiles = (a.M + TC_M - 1) / TC_M;
+    const int n_tiles = a.mixred ? (a.n_nodes + 39) / 40 : (a.M + TC_M - 1) / TC_M;
     const int grid = n_tiles < e->sm_count ? n_tiles : e->sm_count;
     Span sp(e, s, FAM_NODE);
     tc_linear_kernel<<<grid, TC_THREADS, tc_smem_bytes(a.K), s>>>(a, reinterpret_cast<const uint8_t*>(Wfmt),

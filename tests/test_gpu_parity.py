@@ -104,7 +104,8 @@ def test_representation_matches_fp64_oracle(engine):
     # the edge-stage implementations: edge stream (tcgen05 fp16-split, default), first sliced kernel (tcgen05 tf32x3),
     # general gather (tcgen05), fp32 SIMT
     for opts in ({"tensor_cores": 1, "sliced_edge": 1, "sliced_impl": 1}, {"tensor_cores": 1, "sliced_edge": 1, "sliced_impl": 0},
-                 {"tensor_cores": 1, "sliced_edge": 0}, {"tensor_cores": 0}):
+                 {"tensor_cores": 1, "sliced_edge": 0}, {"tensor_cores": 0},
+                 {"tensor_cores": 1, "sliced_edge": 1, "sliced_impl": 1, "fuse_mix": 1, "fuse_mlp": 0}):
         for k, v in opts.items():
             engine.set_option(k, v)
         q, mu = engine.representation(Z, torch.from_numpy(pos).cuda(), torch.from_numpy(cells).cuda(), node_struct,
@@ -115,6 +116,8 @@ def test_representation_matches_fp64_oracle(engine):
     engine.set_option("tensor_cores", 1)
     engine.set_option("sliced_edge", 1)
     engine.set_option("sliced_impl", 1)
+    engine.set_option("fuse_mix", 0)
+    engine.set_option("fuse_mlp", 1)
 
 
 def _score_batch(model, g, tag, dedup=False):
