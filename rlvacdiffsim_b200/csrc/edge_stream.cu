@@ -137,6 +137,30 @@ __device__ __forceinline__ void tmem_wait_ld8(uint32_t* v) {
                  : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]));
 }
 
+// Packed fp32 pairs (FFMA2 / FMUL2, sm_100): the per-slot arithmetic runs on (even slot, odd slot) pairs, one issue slot
+// for two FMAs.  Same operations in the same order per lane as the scalar form.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float sum2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // edge_pack_kernel
 // ------------------------------------------------------------------------------------------------------------------
@@ -485,9 +509,9 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
     float* mup = mu_out + ((int64_t)c.node0 * 3 * F + c.ch);
 
     int cur = c.ra;
-    float acc[NACC][2];
+    f32x2 acc[NACC];                          // (even slots, odd slots) partial sums
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) acc[a][0] = acc[a][1] = 0.f;
+    for (int a = 0; a < NACC; ++a) acc[a] = pk2(0.f, 0.f);
     float qbase = ROLE == 0 ? qp[(int64_t)cur * F] : 0.f;
     int n1 = 0, n2 = 0;                       // receivers finished in tiles t-1 / t-2 (role 0 combines them)
 
@@ -561,36 +585,36 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
             }
             if ((flagw >> (8 * gg)) & 0xffu) {                       // this group starts the next receiver
                 if (ROLE == 0) {
-                    qp[(int64_t)cur * F] = qbase + (acc[0][0] + acc[0][1]);
+                    qp[(int64_t)cur * F] = qbase + sum2(acc[0]);
                     qbase = qp[(int64_t)(cur + 1) * F];
                     if (HAS_MU && lane == 0) S->chg[pipe][ps][nchg] = cur;
                 } else if (!HAS_MU) {                              // layer 0: mu = dmuR, role 1 owns the rows outright
 #pragma unroll
-                    for (int a = 0; a < NACC; ++a) mup[(int64_t)cur * 3 * F + a * F] = acc[a][0] + acc[a][1];
+                    for (int a = 0; a < NACC; ++a) mup[(int64_t)cur * 3 * F + a * F] = sum2(acc[a]);
                 } else {
 #pragma unroll
-                    for (int a = 0; a < NACC; ++a) part[(nchg * PART_ROWS + a) * SL] = acc[a][0] + acc[a][1];
+                    for (int a = 0; a < NACC; ++a) part[(nchg * PART_ROWS + a) * SL] = sum2(acc[a]);
                 }
                 ++nchg;
                 ++cur;
 #pragma unroll
-                for (int a = 0; a < NACC; ++a) acc[a][0] = acc[a][1] = 0.f;
+                for (int a = 0; a < NACC; ++a) acc[a] = pk2(0.f, 0.f);
             }
             tmem_wait_ld8(f);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const float w = __uint_as_float(f[u]);
+            for (int u = 0; u < 8; u += 2) {
+                const f32x2 w2 = pk2(__uint_as_float(f[u]), __uint_as_float(f[u + 1]));
+                const f32x2 x2 = pk2(t1[u], t1[u + 1]);
                 if (ROLE == 0) {
-                    acc[0][u & 1] = fmaf(w, t1[u], acc[0][u & 1]);
+                    acc[0] = fma2(w2, x2, acc[0]);
                 } else if (ROLE == 1) {
-                    const float sR = w * t1[u];
-                    acc[0][u & 1] = fmaf(sR, dr[0][u], acc[0][u & 1]);
-                    acc[1][u & 1] = fmaf(sR, dr[1][u], acc[1][u & 1]);
-                    acc[2][u & 1] = fmaf(sR, dr[2][u], acc[2][u & 1]);
+                    const f32x2 sR = mul2(w2, x2);
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) acc[a] = fma2(sR, pk2(dr[a][u], dr[a][u + 1]), acc[a]);
                 } else {
-                    acc[0][u & 1] = fmaf(w, t1[u], acc[0][u & 1]);
-                    acc[1][u & 1] = fmaf(w, t2[u], acc[1][u & 1]);
-                    acc[2][u & 1] = fmaf(w, t3[u], acc[2][u & 1]);
+                    acc[0] = fma2(w2, x2, acc[0]);
+                    acc[1] = fma2(w2, pk2(t2[u], t2[u + 1]), acc[1]);
+                    acc[2] = fma2(w2, pk2(t3[u], t3[u + 1]), acc[2]);
                 }
             }
         }
@@ -610,10 +634,10 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
     }
     // ---- the receiver still in flight
     if (!HAS_MU) {                                                 // layer 0: every role owns its rows
-        if (ROLE == 0) qp[(int64_t)cur * F] = qbase + (acc[0][0] + acc[0][1]);
+        if (ROLE == 0) qp[(int64_t)cur * F] = qbase + sum2(acc[0]);
         else {
 #pragma unroll
-            for (int a = 0; a < NACC; ++a) mup[(int64_t)cur * 3 * F + a * F] = acc[a][0] + acc[a][1];
+            for (int a = 0; a < NACC; ++a) mup[(int64_t)cur * 3 * F + a * F] = sum2(acc[a]);
         }
         return;
     }
@@ -622,12 +646,12 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
     const uint32_t lb = (uint32_t)(n_tiles - 1) & 1u, lph = ((uint32_t)(n_tiles - 1) >> 1) & 1u;
     st_wait(&S->acc_free[pipe][lb], lph);
     if (ROLE == 0) {
-        qp[(int64_t)cur * F] = qbase + (acc[0][0] + acc[0][1]);
+        qp[(int64_t)cur * F] = qbase + sum2(acc[0]);
         if (lane == 0) S->chg[pipe][ps][0] = cur;
     } else {
         float* part = c.Part + (ps * NG * PART_ROWS + P_ROW) * SL + lane;
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) part[a * SL] = acc[a][0] + acc[a][1];
+        for (int a = 0; a < NACC; ++a) part[a * SL] = sum2(acc[a]);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&S->acc_free[pipe][lb ^ 1u]);
