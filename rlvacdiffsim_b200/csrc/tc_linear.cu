@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
         const int r = t & 127, khalf = t >> 7;               // converter role: row r, core columns khalf*8..+8
         const int q = warp & 3, h = warp >> 2;               // epilogue role: TMEM lane quarter q, column half h
         const int er = q * 32 + lane;                        // epilogue row = TMEM lane
+        uint8_t* Yw = Yst + warp * 4096;                     // this warp's 32 x 32 fp32 output staging tile
         const uint32_t ast = smem_u32(Ast);
         const uint32_t row_off = (r >> 3) * CORE_SBO + (r & 7) * 16;
         uint32_t acc_it = 0, ph_it = 0;
@@ -328,20 +329,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                             if (act_o == 1) v = __fdividef(v, 1.0f + __expf(-v));   // SiLU; |error| < 2e-7 of max(|v|, 1)
                             y[u] = v;
                         }
-                        const int lc = h * 8 + (j >> 2);
-                        *reinterpret_cast<float4*>(Yst + er * 256 + ((lc ^ (er & 7)) << 4)) = make_float4(y[0], y[1], y[2], y[3]);
+                        // warp-private staging tile [32 rows][32 cols] (4 KB, 16-byte chunks swizzled by row): no CTA barrier
+                        *reinterpret_cast<float4*>(Yw + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = make_float4(y[0], y[1], y[2], y[3]);
                     }
-                    epi_barrier();
+                    __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int id = i * 256 + t, row = id >> 4, lc = id & 15;
-                        const int64_t m = (int64_t)tile * TC_M + row;
+                    for (int i = 0; i < 8; ++i) {            // 4 rows x 128 contiguous bytes per store instruction
+                        const int row = i * 4 + (lane >> 3), lc = lane & 7;
+                        const int64_t m = (int64_t)tile * TC_M + q * 32 + row;
                         if (m < a.M) {
-                            const float4 v = *reinterpret_cast<const float4*>(Yst + row * 256 + ((lc ^ (row & 7)) << 4));
-                            *reinterpret_cast<float4*>(a.Y + m * a.ldy + nb * TC_N + 64 * sgm + lc * 4) = v;
+                            const float4 v = *reinterpret_cast<const float4*>(Yw + row * 128 + ((lc ^ (row & 7)) << 4));
+                            *reinterpret_cast<float4*>(a.Y + m * a.ldy + col0 + lc * 4) = v;
                         }
                     }
-                    epi_barrier();
+                    __syncwarp();
                 }
             }
         }
