@@ -116,8 +116,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "action Q-evals/sec", "value": value, "unit": "Q-evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: 256-site CrCoNi replicas (255 atoms), 12 candidate hops each",
-                       "sample": f"{n_rep} replicas x 12 candidates per step"},
+            "config": {"workload": "BASELINE config 2 (1024 independent 256-site CrCoNi replicas, 255 atoms, 12 "
+                                   "candidate hops each, LSS scoring) sharded 128 replicas per GPU",
+                       "sample": f"{n_rep} replicas x 12 candidates per step (bounded CPU sample of the same workload)",
+                       "q_params": Q_PARAMS},
             "cpu_baseline": {"value": value, "unit": "Q-evals/s", "cores": threads, "kind": "port",
                              "sample": f"{n_rep} replicas x 12 candidates x {args.steps} steps, eager PyTorch fp32 oracle"},
             "e2e": {"value": value, "unit": "Q-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -293,9 +295,9 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            rate, dt = cpu_oracle_rate(4, threads)
+            rate, dt = cpu_oracle_rate(12, threads)
             line["cpu_baseline"] = {"value": rate, "unit": "Q-evals/s", "cores": threads, "kind": "port",
-                                    "sample": f"4 replicas x 12 candidates ({dt:.1f} s), eager PyTorch fp32 oracle, "
+                                    "sample": f"12 replicas x 12 candidates ({dt:.1f} s), eager PyTorch fp32 oracle, "
                                               "DataLoader batches of 16 as simulator.py:52"}
         print(json.dumps(line))
     if world > 1:
