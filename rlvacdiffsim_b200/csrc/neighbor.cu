@@ -74,6 +74,34 @@ __device__ __forceinline__ int sweep_receiver(const CellC& C, const float* P, in
                                               long long cap) {
     const float xi = P[3 * i], yi = P[3 * i + 1], zi = P[3 * i + 2];
     int off = 0;
+    if ((C.R[0] | C.R[1] | C.R[2]) == 0) {
+        // Single minimum image (every cell height >= 2*cutoff — the BASELINE supercells): at most one hit per pair, so a
+        // ballot replaces the image loops and the warp scan.  Same arithmetic, same edge order.
+        const unsigned lt = (1u << lane) - 1u;
+        for (int jb = 0; jb < n; jb += 32) {
+            const int j = jb + lane;
+            bool hit = false;
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+            if (j < n) {
+                const float dx = __fsub_rn(P[3 * j], xi), dy = __fsub_rn(P[3 * j + 1], yi), dz = __fsub_rn(P[3 * j + 2], zi);
+                base_image(C, dx, dy, dz, b0, b1, b2);
+                const bool self = (j == i) && b0 == 0.f && b1 == 0.f && b2 == 0.f;
+                hit = !self && image_d2(C, dx, dy, dz, b0, b1, b2) < rc2;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (FILL && hit) {
+                const int w = row_start + off + __popc(mask & lt);
+                if (w < cap) {
+                    col[w] = node0 + j;
+                    shift[3 * (int64_t)w + 0] = (int8_t)(int)b0;
+                    shift[3 * (int64_t)w + 1] = (int8_t)(int)b1;
+                    shift[3 * (int64_t)w + 2] = (int8_t)(int)b2;
+                }
+            }
+            off += __popc(mask);
+        }
+        return off;
+    }
     for (int jb = 0; jb < n; jb += 32) {
         const int j = jb + lane;
         int cnt = 0;
