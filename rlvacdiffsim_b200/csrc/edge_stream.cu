@@ -698,32 +698,21 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(&S->tmem_base, TM_COLS);
-
-    // ---- stage this slice of the structure's node table
-    for (int id = tid; id < n * 8; id += ST_THREADS) {
-        const int node = id >> 3, c4 = id & 7;
-        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(node0 + node) * 3 * F + slice * SL) + c4;
-        float4 xq = __ldg(xr), xR = __ldg(xr + F / 4);
-        uint8_t* row = TabS + node * NB + c4 * 16;
-        xq.x *= kappa; xq.y *= kappa; xq.z *= kappa; xq.w *= kappa;
-        xR.x *= kappa; xR.y *= kappa; xR.z *= kappa; xR.w *= kappa;
-        *reinterpret_cast<float4*>(row) = xq;
-        *reinterpret_cast<float4*>(row + SL * 4) = xR;
-        if (HAS_MU) {
-            float4 xm = __ldg(xr + 2 * F / 4);
-            xm.x *= kappa; xm.y *= kappa; xm.z *= kappa; xm.w *= kappa;
-            const float4* mr = reinterpret_cast<const float4*>(mu_in + (size_t)(node0 + node) * 3 * F + slice * SL) + c4;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float4 m = __ldg(mr + a * (F / 4));
-                *reinterpret_cast<float4*>(row + (2 + a) * SL * 4) = make_float4(xm.x * m.x, xm.y * m.y, xm.z * m.z, xm.w * m.w);
-            }
-        }
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S->tmem_base;
+
+    // Prologue overlap: the feeder warps only need the weight operand in TMEM, the consuming warps only need the node
+    // table.  Warps 0-3 load the operand and release the feeders through named barrier 1; the consuming warps stage the
+    // table meanwhile and meet at named barrier 2, so the first tiles' copies and MMAs run under the table staging.
+    const int pipe_w = warp >> 2;
+    const int role_w = ((warp & 3) + pipe_rot(pipe_w)) & 3;
+    const bool feeds = role_w == 3 || (!HAS_MU && role_w == 2);
+    constexpr int NCW = HAS_MU ? 3 : 2;                             // consuming warps per pipeline
+    constexpr int N_FEED_WARPS = NPIPE * (4 - NCW);
+    constexpr int A_BAR_THREADS = (NCW + N_FEED_WARPS) * 32;        // warps 0..NCW-1 arrive, every feeder warp waits
+    constexpr int STAGE_THREADS = NPIPE * NCW * 32;
 
     // ---- weight operand -> TMEM in its four row rotations (lane = filter row; 64 fp16 = 32 columns each)
     if (warp < 4) {
@@ -739,14 +728,41 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
             }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    if (feeds) {
+        asm volatile("bar.sync 1, %0;" ::"n"(A_BAR_THREADS) : "memory");
+        tc_fence_after();
+    } else {
+        if (warp < 4) asm volatile("bar.arrive 1, %0;" ::"n"(A_BAR_THREADS) : "memory");
+        // ---- stage this slice of the structure's node table (consuming warps only)
+        const int sid = (pipe_w * NCW + role_w) * 32 + lane;
+        for (int id = sid; id < n * 8; id += STAGE_THREADS) {
+            const int node = id >> 3, c4 = id & 7;
+            const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(node0 + node) * 3 * F + slice * SL) + c4;
+            float4 xq = __ldg(xr), xR = __ldg(xr + F / 4);
+            uint8_t* row = TabS + node * NB + c4 * 16;
+            xq.x *= kappa; xq.y *= kappa; xq.z *= kappa; xq.w *= kappa;
+            xR.x *= kappa; xR.y *= kappa; xR.z *= kappa; xR.w *= kappa;
+            *reinterpret_cast<float4*>(row) = xq;
+            *reinterpret_cast<float4*>(row + SL * 4) = xR;
+            if (HAS_MU) {
+                float4 xm = __ldg(xr + 2 * F / 4);
+                xm.x *= kappa; xm.y *= kappa; xm.z *= kappa; xm.w *= kappa;
+                const float4* mr = reinterpret_cast<const float4*>(mu_in + (size_t)(node0 + node) * 3 * F + slice * SL) + c4;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const float4 m = __ldg(mr + a * (F / 4));
+                    *reinterpret_cast<float4*>(row + (2 + a) * SL * 4) = make_float4(xm.x * m.x, xm.y * m.y, xm.z * m.z, xm.w * m.w);
+                }
+            }
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(STAGE_THREADS) : "memory");
+    }
 
     PipeCtx c;
     c.S = S;
-    c.pipe = warp >> 2;
+    c.pipe = pipe_w;
     c.lane = lane;
     c.quarter = warp & 3;
     c.tmem = tmem;
@@ -760,7 +776,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     c.node0 = node0;
     c.ch = slice * SL + lane;
     c.dbg = (blockIdx.x == 0 && c.pipe == 0 && lane == 0) ? dbg : nullptr;
-    const int role = ((warp & 3) + pipe_rot(c.pipe)) & 3;   // the pipeline's rotation puts this role's filter rows in this warp's quarter
+    const int role = role_w;                          // the pipeline's rotation puts this role's filter rows in this warp's quarter
     Feed fd;
     fd.src = tiles + (size_t)pi.x * TILE_BYTES;
     fd.Bp = Bs + c.pipe * NB_STAGE * TILE_B;
