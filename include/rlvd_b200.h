@@ -141,8 +141,7 @@ int  rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, i
 int  rlvd_linear(rlvd_engine* e, void* stream, int32_t M, int32_t K, int32_t N, const float* d_A,
                  const float* d_A2, int32_t K1, const float* h_W, const float* h_bias, int32_t act, float* d_Y);
 /* Engine options: "tensor_cores" (1 = tcgen05 GEMMs and filters, 0 = fp32 SIMT kernels; both fp32-accurate),
- * "sliced_edge" (1 = structure-resident edge kernels for structures of <= 256 atoms, 0 = general),
- * "sliced_impl" (1 = edge stream, edge_stream.cu; 0 = first sliced kernel, tc_edge_small.cu),
+ * "sliced_edge" (1 = structure-resident edge stream kernel, edge_stream.cu, for structures of <= 256 atoms; 0 = general),
  * "fuse_mlp" (1 = each Linear-SiLU-Linear context net is one launch with the hidden tile kept on the SM),
  * "fuse_mix" (1 = the |mu_V| and <mu_V, mu_W> reductions run in the mu_channel_mix GEMM epilogue). */
 int  rlvd_set_option(rlvd_engine* e, const char* name, int32_t value);

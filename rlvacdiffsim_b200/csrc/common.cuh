@@ -13,7 +13,7 @@ namespace rlvd {
 constexpr int F = RLVD_F;          // 128 hidden channels
 constexpr int NRBF = RLVD_NRBF;    // 20 Bessel functions
 constexpr int NLAYER = RLVD_NLAYER;
-constexpr int GEOM = 24;           // per-edge geometry record: 20 x phi*fcut, fcut, dir.xyz
+constexpr int GEOM = 24;           // per-edge geometry record of the fp32 SIMT kernel: 20 x phi*fcut, fcut, dir.xyz
 
 void set_error(const char* fmt, ...);
 
@@ -62,7 +62,6 @@ struct Weights {
     const float* freqs = nullptr;               // [20]
     const float* filt_T = nullptr;              // [L][21][384]  (k<20: weight^T, k=20: bias)
     const void* filt_F = nullptr;               // [L][3 parts][hi|lo] tf32 tensor-core operand (tc_edge.cu)
-    const void* filt_S = nullptr;               // [L][4 slices][hi|lo] tf32 operand of the sliced kernel (tc_edge_small.cu)
     const void* filt_E = nullptr;               // [L][4 slices][128][32] fp16-split TMEM image (edge_stream.cu)
     float filt_kappa[NLAYER] = {};              // 2^-(sA+10): undoes the fp16 range scaling of filt_E and the edge tiles
     const float* feps = nullptr;                // [20] freqs[k] - (k+1)*freqs[0]
@@ -111,7 +110,7 @@ struct rlvd_engine {
     rlvd::Weights w;
     bool finalized = false;
     // workspaces (grown on demand, never shrunk)
-    rlvd::DevBuf x, mu0, mu1, hid, mix, nrm, vw, ctx, struct_edges, struct_edge_ptr, scratch, geom;
+    rlvd::DevBuf x, mu0, mu1, hid, mix, nrm, vw, ctx, struct_edges, struct_edge_ptr, scratch;
     rlvd::DevBuf tiles, pipe_info, tile_ctr, stream_scratch;   // edge stream (edge_stream.cu)
     // host-path staging
     rlvd::DevBuf in_node_ptr, in_Z, in_pos, in_cell, in_inv, in_img, in_rs, in_ps, in_temp, in_qp;
@@ -122,7 +121,6 @@ struct rlvd_engine {
     bool fuse_mix = false;          // nrm / vw reductions inside the mu_channel_mix GEMM epilogue (tc_linear.cu mixred mode);
                                     // measured 0.3 ms/step SLOWER than GEMM + reduction kernel (the epilogue is the GEMM's bottleneck)
     bool fuse_mlp = true;           // Linear -> SiLU -> Linear pairs as one tcgen05 launch (tc_linear.cu two-layer mode)
-    int sliced_impl = 1;            // 1 = edge stream (edge_stream.cu), 0 = first sliced kernel (tc_edge_small.cu)
     bool profiling = false;
     std::vector<rlvd::ProfSpan> spans;
     std::vector<cudaEvent_t> event_pool;
@@ -185,7 +183,7 @@ void tc_format_weight(const float* W, int N, int K, std::vector<uint8_t>& out);
 int launch_embed(rlvd_engine* e, cudaStream_t s, int M, const int* Z, float* q);
 struct EdgeArgs {
     int layer = 0, M = 0, n_struct = 0, max_struct_nodes = 0;
-    int sliced = 0;                 // 0 general; 1 geometry records ready (tc_edge_small); 2 edge tiles ready (edge_stream)
+    int sliced = 0;                 // 0 general kernels; 2 edge tiles ready (edge_stream.cu)
     const int* node_ptr = nullptr;
     const int* row_ptr = nullptr;
     const int* col = nullptr;
@@ -199,14 +197,6 @@ struct EdgeArgs {
     float* mu_out = nullptr;
 };
 int launch_edge(rlvd_engine* e, cudaStream_t s, const EdgeArgs& a);
-bool tc_edge_small_supported(int max_struct_nodes);
-int launch_edge_geometry(rlvd_engine* e, cudaStream_t s, int M, int64_t n_edges, const int* node_ptr,
-                         const int* node_struct, const int* row_ptr, const int* col, const int8_t* shift, const float* pos,
-                         const float* cell);
-int launch_tc_edge_small(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, int max_struct_nodes,
-                         const int* node_ptr, const int* row_ptr, const float* x, const float* mu_in, float* q,
-                         float* mu_out);
-void tc_edge_small_format(const float* W, const float* b, std::vector<uint8_t>& out);
 bool edge_stream_supported(int max_struct_nodes);
 void edge_stream_format(const float* W, const float* b, std::vector<uint8_t>& out, float* kappa);
 int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_t n_edges, const int* node_ptr,

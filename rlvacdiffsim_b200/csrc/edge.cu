@@ -143,9 +143,6 @@ int launch_edge(rlvd_engine* e, cudaStream_t s, const EdgeArgs& a) {
     if (M <= 0) return 0;
     if (a.sliced == 2)
         return launch_edge_stream(e, s, a.layer, a.n_struct, a.max_struct_nodes, a.node_ptr, a.x, a.mu_in, a.q, a.mu_out);
-    if (a.sliced == 1)
-        return launch_tc_edge_small(e, s, a.layer, a.n_struct, a.max_struct_nodes, a.node_ptr, a.row_ptr, a.x, a.mu_in,
-                                    a.q, a.mu_out);
     if (e->use_tensor_cores)
         return launch_tc_edge(e, s, a.layer, M, a.row_ptr, a.col, a.shift, a.pos, a.cell, a.node_struct, a.x, a.mu_in, a.q,
                               a.mu_out);

@@ -142,7 +142,7 @@ void rlvd_engine_destroy(rlvd_engine* e) {
     cudaSetDevice(e->device);
     for (void* d : e->derived) cudaFree(d);
     for (DevBuf* b : {&e->x, &e->mu0, &e->mu1, &e->hid, &e->mix, &e->nrm, &e->vw, &e->ctx, &e->struct_edges,
-                      &e->struct_edge_ptr, &e->scratch, &e->geom, &e->tiles, &e->pipe_info, &e->tile_ctr, &e->stream_scratch, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
+                      &e->struct_edge_ptr, &e->scratch, &e->tiles, &e->pipe_info, &e->tile_ctr, &e->stream_scratch, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
                       &e->in_inv, &e->in_img, &e->in_rs, &e->in_ps, &e->in_temp, &e->in_qp, &e->g_row_ptr,
                       &e->g_node_struct, &e->g_col, &e->g_shift, &e->g_nedges, &e->g_q, &e->out_pack})
         b->release();
@@ -214,11 +214,6 @@ int rlvd_finalize_weights(rlvd_engine* e) {
         void* dff = nullptr;
         if (upload(e, ff.data(), ff.size(), &dff)) return 1;
         w.filt_F = dff;
-        std::vector<uint8_t> fs;
-        tc_edge_small_format(fw->data(), fb->data(), fs);
-        void* dfs = nullptr;
-        if (upload(e, fs.data(), fs.size(), &dfs)) return 1;
-        w.filt_S = dfs;
         std::vector<uint8_t> fe;
         edge_stream_format(fw->data(), fb->data(), fe, w.filt_kappa);
         void* dfe = nullptr;
@@ -340,11 +335,8 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
 
     int sliced = 0;
     if (e->use_tensor_cores && e->use_sliced_edge && d_node_ptr != nullptr && n_edges > 0) {
-        if (e->sliced_impl == 1 && edge_stream_supported(max_struct_nodes)) sliced = 2;
-        else if (e->sliced_impl == 0 && tc_edge_small_supported(max_struct_nodes)) sliced = 1;
+        if (edge_stream_supported(max_struct_nodes)) sliced = 2;
     }
-    if (sliced == 1 && launch_edge_geometry(e, s, M, n_edges, d_node_ptr, d_node_struct, d_row_ptr, d_col, d_shift, d_pos, d_cell))
-        return 1;
     if (sliced == 2 && launch_edge_pack(e, s, n_struct, M, n_edges, d_node_ptr, d_row_ptr, d_col, d_shift, d_pos, d_cell))
         return 1;
     if (launch_embed(e, s, M, d_Z, d_q)) return 1;
@@ -508,10 +500,6 @@ int rlvd_set_option(rlvd_engine* e, const char* name, int32_t value) {
     }
     if (strcmp(name, "fuse_mlp") == 0) {
         e->fuse_mlp = value != 0;
-        return 0;
-    }
-    if (strcmp(name, "sliced_impl") == 0) {
-        e->sliced_impl = value;
         return 0;
     }
     RLVD_CHECK(false, "unknown option '%s'", name);

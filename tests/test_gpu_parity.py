@@ -101,11 +101,10 @@ def test_representation_matches_fp64_oracle(engine):
     Z = torch.from_numpy(g["numbers"].astype(np.int32)).cuda()
     q_ref, mu_ref = g["f64.q_reactant"], g["f64.mu_reactant"]
     ptr_d = torch.from_numpy(ptr).cuda()
-    # the edge-stage implementations: edge stream (tcgen05 fp16-split, default), first sliced kernel (tcgen05 tf32x3),
-    # general gather (tcgen05), fp32 SIMT
-    for opts in ({"tensor_cores": 1, "sliced_edge": 1, "sliced_impl": 1}, {"tensor_cores": 1, "sliced_edge": 1, "sliced_impl": 0},
-                 {"tensor_cores": 1, "sliced_edge": 0}, {"tensor_cores": 0},
-                 {"tensor_cores": 1, "sliced_edge": 1, "sliced_impl": 1, "fuse_mix": 1, "fuse_mlp": 0}):
+    # the edge-stage implementations: edge stream (tcgen05 fp16-split, default), general gather (tcgen05 tf32x3),
+    # fp32 SIMT; and the optional node-side forms (mix-reduce epilogue, unfused context nets)
+    for opts in ({"tensor_cores": 1, "sliced_edge": 1}, {"tensor_cores": 1, "sliced_edge": 0}, {"tensor_cores": 0},
+                 {"tensor_cores": 1, "sliced_edge": 1, "fuse_mix": 1, "fuse_mlp": 0}):
         for k, v in opts.items():
             engine.set_option(k, v)
         q, mu = engine.representation(Z, torch.from_numpy(pos).cuda(), torch.from_numpy(cells).cuda(), node_struct,
@@ -115,7 +114,6 @@ def test_representation_matches_fp64_oracle(engine):
         assert err_q < TOL and err_mu < TOL, (opts, err_q, err_mu)
     engine.set_option("tensor_cores", 1)
     engine.set_option("sliced_edge", 1)
-    engine.set_option("sliced_impl", 1)
     engine.set_option("fuse_mix", 0)
     engine.set_option("fuse_mlp", 1)
 
@@ -297,7 +295,7 @@ def test_edge_stream_ragged_batch_matches_simt_and_oracle(engine):
     Zd, posd = torch.from_numpy(Z).cuda(), torch.from_numpy(pos).cuda()
     celld, ptrd = torch.from_numpy(cells.astype(np.float32)).cuda(), torch.from_numpy(ptr).cuda()
     out = {}
-    for name, opts in (("stream", {"tensor_cores": 1, "sliced_edge": 1, "sliced_impl": 1}), ("simt", {"tensor_cores": 0})):
+    for name, opts in (("stream", {"tensor_cores": 1, "sliced_edge": 1}), ("simt", {"tensor_cores": 0})):
         for k, v in opts.items():
             engine.set_option(k, v)
         q, mu = engine.representation(Zd, posd, celld, node_struct, row_ptr, col, shift, len(structs), return_mu=True,
