@@ -102,6 +102,17 @@ int  rlvd_reaction_readout(rlvd_engine* e, void* stream, int32_t n_react, int32_
                            float* d_rl_q, float* d_q0, float* d_q1, float* d_delta_e,
                            float* d_E_R, float* d_E_P);
 
+/* ---- A1: candidate vacancy-hop enumeration (replaces rlsim/actions/action.py:12-61 `get_action_space`, which the
+ *      reference runs on the host with ASE + a dense atoms x sites distance matrix per step) --------------------- */
+/* n_struct replicas with orthorhombic cells (off-diagonal terms exactly zero); d_pos[M,3] and d_cell[n_struct,3,3] are
+ * fp64 like ASE's.  Row w of replica g: d_actions[(g*max_actions + w)*4 + {0..3}] = {atom index, dx, dy, dz}, rows in
+ * the reference's order (vacancies ascending, neighbour sites ascending); d_count[g] rows are valid.
+ * d_status[g]: 0 ok, 1 cell not orthorhombic or more than 8192 sites (use the host enumerator), 2 vacancy count not
+ * in 1..max_vacancies (the reference's `assert len(vacant) == 1`, action.py:35), 3 more than max_actions rows. */
+int  rlvd_action_space(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const double* d_pos,
+                       const double* d_cell, double lattice_parameter, int32_t max_vacancies, int32_t max_actions,
+                       int32_t* d_count, double* d_actions, int32_t* d_status);
+
 /* ---- T1: t_net head on top of rlvd_painn_representation (replaces rgnn `t_net` forward reached from
  *      rlsim/cli/scripts/estimate_time.py:58 `model(batch, inference=True)["time"]` and rlsim/time/train.py:108,114) -- */
 /* Head weights live on the device (the caller's nn.Parameters); nn.Linear layout [out, in].  No t_net checkpoint is

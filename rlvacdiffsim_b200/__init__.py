@@ -5,7 +5,7 @@ message passing → deterministic segmented scatter → per-action Q readout, be
 Python surface (``registry``, ``ReactionGraph``, ``DataLoader``, ``batch_to``, ``model(batch, q_params)``,
 ``RLSimulator.select_action``).  See DESIGN.md and INTEGRATION.md.
 """
-from .actions import get_action_space, get_action_space_legacy  # noqa: F401
+from .actions import get_action_space, get_action_space_device, get_action_space_legacy  # noqa: F401
 from .graph import (AtomsDataset, AtomsGraph, Batch, DataLoader, ReactionDataset, ReactionGraph,  # noqa: F401
                     batch_to)
 from .registry import registry  # noqa: F401

@@ -130,3 +130,35 @@ def get_action_space_legacy(config, lattice_parameter: float = 3.528) -> List[Li
             if np.sum(d < 0.8) == 1:                                           # action.py:176
                 actions.append([int(i)] + vec.tolist())
     return actions
+
+
+def get_action_space_device(engine, replicas, lattice_parameter: float = 3.615, max_vacancies: int = 1) -> List[List[List[float]]]:
+    """:func:`get_action_space` for many replicas in ONE device launch (``rlvd_action_space``).
+
+    Same rows in the same order as the host enumerator for orthorhombic cells; replicas whose cell the kernel does
+    not take (status 1) fall through to the host enumerator, and the reference's vacancy-count assert
+    (``action.py:35``) is raised for status 2.  ``engine`` is an :class:`rlvacdiffsim_b200.engine.Engine`."""
+    import torch
+
+    atoms_l = [_atoms_of(r) for r in replicas]
+    counts = np.array([len(a) for a in atoms_l], dtype=np.int64)
+    node_ptr = np.zeros(len(atoms_l) + 1, dtype=np.int32)
+    np.cumsum(counts, out=node_ptr[1:])
+    pos = np.concatenate([np.asarray(a.get_positions(), dtype=np.float64) for a in atoms_l])
+    cells = np.stack([np.array(a.get_cell(), dtype=np.float64).reshape(3, 3) for a in atoms_l])
+    dev = engine.device
+    cnt, act, status = engine.action_space(torch.from_numpy(pos).to(dev), torch.from_numpy(cells).to(dev),
+                                           torch.from_numpy(node_ptr).to(dev), lattice_parameter, max_vacancies,
+                                           max_actions=12 * max_vacancies)
+    cnt, act, status = cnt.cpu().numpy(), act.cpu().numpy(), status.cpu().numpy()
+    out: List[List[List[float]]] = []
+    for g, atoms in enumerate(atoms_l):
+        if status[g] == 1:
+            out.append(get_action_space(atoms, lattice_parameter, max_vacancies))
+            continue
+        if status[g] == 2:
+            raise AssertionError("Expected 1 vacancy" if max_vacancies == 1 else f"Expected 1..{max_vacancies} vacancies")
+        if status[g] != 0:
+            raise RuntimeError(f"rlvd_action_space: status {int(status[g])} for replica {g}")
+        out.append([[int(r[0])] + r[1:].tolist() for r in act[g, : cnt[g]]])
+    return out

@@ -217,4 +217,7 @@ int launch_readout(rlvd_engine* e, cudaStream_t s, int n_react, const int* node_
 int launch_time_readout(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const float* q, const float* T,
                         const float* defect, const rlvd_time_head& h, float* time_out);
 
+int launch_action_space(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const double* pos, const double* cell,
+                        double a, int max_vac, int max_actions, int* count, double* actions, int* status);
+
 }  // namespace rlvd

@@ -409,6 +409,15 @@ int rlvd_reaction_readout(rlvd_engine* e, void* stream, int32_t n_react, int32_t
                           d_temperature, d_rl_q, d_q0, d_q1, d_delta_e, d_E_R, d_E_P);
 }
 
+int rlvd_action_space(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const double* d_pos,
+                      const double* d_cell, double lattice_parameter, int32_t max_vacancies, int32_t max_actions,
+                      int32_t* d_count, double* d_actions, int32_t* d_status) {
+    RLVD_CHECK(e != nullptr && d_node_ptr && d_pos && d_cell && d_count && d_actions && d_status, "rlvd_action_space: bad argument");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_action_space(e, (cudaStream_t)stream, n_struct, d_node_ptr, d_pos, d_cell, lattice_parameter, max_vacancies,
+                               max_actions, d_count, d_actions, d_status);
+}
+
 int rlvd_time_readout(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const float* d_q,
                       const float* d_T, const float* d_defect, const rlvd_time_head* head, float* d_time) {
     RLVD_CHECK(e != nullptr && head != nullptr, "rlvd_time_readout: bad argument");

@@ -160,6 +160,21 @@ class Engine:
         names = ("rl_q", "q0", "q1", "delta_e", "E_R", "E_P")
         return {k: out[i, :G] for i, k in enumerate(names)}
 
+    # ------------------------------------------------------------------ A1: candidate hops on the device
+    def action_space(self, pos: torch.Tensor, cells: torch.Tensor, node_ptr: torch.Tensor, lattice_parameter: float,
+                     max_vacancies: int = 1, max_actions: int = 16):
+        """``rlvd_action_space``: fp64 ``pos[M,3]``, ``cells[G,3,3]`` → (count i32[G], actions f64[G,max_actions,4],
+        status i32[G]) with the reference's row order (``rlsim/actions/action.py:12-61``)."""
+        G = node_ptr.numel() - 1
+        count = torch.empty(max(G, 1), dtype=torch.int32, device=self.device)
+        status = torch.empty(max(G, 1), dtype=torch.int32, device=self.device)
+        actions = torch.zeros((max(G, 1), max_actions, 4), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_action_space(self._h, self._stream(), G, _ptr(node_ptr), _ptr(pos), _ptr(cells),
+                                             float(lattice_parameter), int(max_vacancies), int(max_actions),
+                                             _ptr(count), _ptr(actions), _ptr(status)))
+        return count[:G], actions[:G], status[:G]
+
     # ------------------------------------------------------------------ T1: t_net head
     def time_readout(self, q: torch.Tensor, node_ptr: torch.Tensor, T: torch.Tensor, defect: torch.Tensor,
                      head: TimeHead) -> torch.Tensor:

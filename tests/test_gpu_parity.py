@@ -352,3 +352,30 @@ def test_t_net_time_matches_fp64_oracle(model):
     assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) < TOL
     # t_real of estimate_time.py:15-35 stays finite
     assert np.all(np.isfinite(-tnet.tau * np.log(1 - got / tnet.tau)))
+
+
+# ----------------------------------------------------------------------------- A1 on the device
+
+def test_action_space_device_matches_host_enumerator(engine):
+    """rlsim/actions/action.py:12-61 for many replicas in one launch: same atoms, same order, same displacements."""
+    reps = [make_crconi_supercell(4, seed=s, jitter=j) for s, j in ((0, 0.0), (1, 0.05), (2, 0.08))]
+    reps += [make_crconi_supercell(3, seed=5, jitter=0.03), make_crconi_supercell(4, seed=7, n_vac=2, jitter=0.02)]
+    # one replica displaced by a lattice vector and wrapped: minimum-image mapping must still find the same hops
+    moved = make_crconi_supercell(4, seed=0, jitter=0.02)
+    moved.positions = (moved.positions + np.array([14.112, -14.112, 28.224]))
+    reps.append(moved)
+    dev = rb.get_action_space_device(engine, reps[:4] + reps[5:], 3.528)
+    for got, atoms in zip(dev, reps[:4] + reps[5:]):
+        ref = rb.get_action_space(atoms, 3.528)
+        assert len(got) == len(ref) == 12
+        assert [r[0] for r in got] == [r[0] for r in ref]                      # atom indices and row order: exact
+        np.testing.assert_allclose(np.asarray(got), np.asarray(ref), rtol=0, atol=1e-12)
+    two = rb.get_action_space_device(engine, [reps[4]], 3.528, max_vacancies=2)[0]
+    ref2 = rb.get_action_space(reps[4], 3.528, max_vacancies=2)
+    assert [r[0] for r in two] == [r[0] for r in ref2] and len(two) == 24
+    np.testing.assert_allclose(np.asarray(two), np.asarray(ref2), rtol=0, atol=1e-12)
+    with pytest.raises(AssertionError, match="Expected 1 vacancy"):            # action.py:35
+        rb.get_action_space_device(engine, [reps[4]], 3.528)
+    # a non-orthorhombic cell (the demo POSCAR) falls through to the host enumerator
+    demo = read_poscar(os.path.join(GOLD, "POSCAR_0"))
+    assert rb.get_action_space_device(engine, [demo], 3.528)[0] == rb.get_action_space(demo, 3.528)
