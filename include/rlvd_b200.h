@@ -113,6 +113,26 @@ int  rlvd_action_space(rlvd_engine* e, void* stream, int32_t n_struct, const int
                        const double* d_cell, double lattice_parameter, int32_t max_vacancies, int32_t max_actions,
                        int32_t* d_count, double* d_actions, int32_t* d_status);
 
+/* ---- A2/A3/A5 on the device: a whole LSS step without a host round trip -------------------- */
+/* Exclusive scan of rlvd_action_space's counts: d_first[n_rep+1], d_total[0] = number of candidates. */
+int  rlvd_candidate_offsets(rlvd_engine* e, void* stream, int32_t n_rep, const int32_t* d_count, int32_t* d_first,
+                            int32_t* d_total);
+/* convert_to_graph_list + collate (rlsim/drl/simulator.py:439-460, :50-55) for every candidate of every replica:
+ * reaction graph g = d_first[r] + c gets reactant structure 2g (the replica) and product structure 2g+1
+ * (pos[atom] += disp in fp64, then fp32).  Replicas have n_atoms_per atoms each and orthorhombic cells with heights
+ * >= 2*cutoff.  Outputs are the inputs of rlvd_radius_graph_* / rlvd_painn_representation / rlvd_reaction_readout. */
+int  rlvd_expand_candidates(rlvd_engine* e, void* stream, int32_t n_rep, int32_t n_cand, int32_t n_atoms_per,
+                            const int32_t* d_rep_ptr, const int32_t* d_first, const int32_t* d_Z, const double* d_pos,
+                            const double* d_cell, const double* d_actions, int32_t max_actions, int32_t* d_node_ptr,
+                            int32_t* d_Z_out, float* d_pos_out, float* d_cell_out, float* d_inv_out, int32_t* d_img_out,
+                            int32_t* d_react_struct, int32_t* d_prod_struct, int32_t* d_owner);
+/* simulator.py:94-98 for every replica: p = softmax(Q / (T * 8.617e-5)) in fp32, np.random.choice's inverse-cdf draw
+ * with the caller's uniforms d_uniform[n_rep], argmax, and (apply != 0) pos[atom] += disp of the chosen hop in place
+ * (environment.step's position update).  d_probs[n_rep, max_actions] may be NULL. */
+int  rlvd_select_apply(rlvd_engine* e, void* stream, int32_t n_rep, const int32_t* d_rep_ptr, const int32_t* d_first,
+                       const float* d_rl_q, const float* d_temperature, const double* d_uniform, const double* d_actions,
+                       int32_t max_actions, int32_t apply, double* d_pos, int32_t* d_chosen, int32_t* d_argmax, float* d_probs);
+
 /* ---- T1: t_net head on top of rlvd_painn_representation (replaces rgnn `t_net` forward reached from
  *      rlsim/cli/scripts/estimate_time.py:58 `model(batch, inference=True)["time"]` and rlsim/time/train.py:108,114) -- */
 /* Head weights live on the device (the caller's nn.Parameters); nn.Linear layout [out, in].  No t_net checkpoint is

@@ -154,3 +154,173 @@ int launch_action_space(rlvd_engine* e, cudaStream_t s, int n_struct, const int*
 }
 
 }  // namespace rlvd
+
+// ------------------------------------------------------------------------------------------------------------------
+// A2/A3 and A5 on the device: the scoring batch of every candidate of every replica is built from the
+// replicas' fp64 state without a host round trip, and the chosen hop is applied in place.
+// ------------------------------------------------------------------------------------------------------------------
+namespace rlvd {
+
+namespace {
+
+// exclusive scan of the candidate counts (single block; a few thousand replicas)
+__global__ void __launch_bounds__(1024) candidate_offsets_kernel(int n_rep, const int* __restrict__ count, int* __restrict__ first,
+                                                                 int* __restrict__ total) {
+    __shared__ int wsum[33];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int carry = 0;
+    for (int base = 0; base < n_rep; base += 1024) {
+        const int idx = base + tid;
+        const int v = idx < n_rep ? count[idx] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int w = wsum[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            wsum[lane] = winc - w;
+            if (lane == 31) wsum[32] = winc;
+        }
+        __syncthreads();
+        if (idx < n_rep) first[idx] = carry + wsum[wid] + inc - v;
+        carry += wsum[32];
+        __syncthreads();
+    }
+    if (tid == 0) { first[n_rep] = carry; total[0] = carry; }
+}
+
+// convert_to_graph_list (rlsim/drl/simulator.py:439-460) + collate (:50-55) for all replicas: candidate c of replica r
+// becomes reaction graph g = first[r] + c with reactant structure 2g (a copy of the replica) and product structure
+// 2g+1 (pos[atom] += disp, added in fp64 and then rounded to fp32 like ASE positions cast by the collate).
+// grid = (total candidates, 2), one CTA per structure.
+__global__ void __launch_bounds__(128) expand_candidates_kernel(int n_rep, const int* __restrict__ rep_ptr, const int* __restrict__ first,
+                                                                const int* __restrict__ Z64as32, const double* __restrict__ pos,
+                                                                const double* __restrict__ cell, const double* __restrict__ actions,
+                                                                int max_actions, int n_atoms_per /* uniform replica size */,
+                                                                int* __restrict__ node_ptr, int* __restrict__ Zo, float* __restrict__ poso,
+                                                                float* __restrict__ cello, float* __restrict__ invo, int* __restrict__ imgo,
+                                                                int* __restrict__ rs, int* __restrict__ ps, int* __restrict__ owner) {
+    const int g = blockIdx.x, side = blockIdx.y, tid = threadIdx.x;
+    // replica of graph g: binary search in first[]
+    int lo = 0, hi = n_rep;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (first[mid] <= g) lo = mid; else hi = mid;
+    }
+    const int r = lo, c = g - first[r];
+    const int a0 = rep_ptr[r], n = rep_ptr[r + 1] - a0;
+    const int st = 2 * g + side;
+    const int64_t o0 = (int64_t)st * n_atoms_per;
+    const double* act = actions + ((int64_t)r * max_actions + c) * 4;
+    const int moved = side == 1 ? (int)act[0] : -1;
+    for (int i = tid; i < n; i += 128) {
+        double x = pos[3 * (int64_t)(a0 + i)], y = pos[3 * (int64_t)(a0 + i) + 1], z = pos[3 * (int64_t)(a0 + i) + 2];
+        if (i == moved) { x = __dadd_rn(x, act[1]); y = __dadd_rn(y, act[2]); z = __dadd_rn(z, act[3]); }
+        poso[3 * (o0 + i)] = (float)x;
+        poso[3 * (o0 + i) + 1] = (float)y;
+        poso[3 * (o0 + i) + 2] = (float)z;
+        Zo[o0 + i] = Z64as32[a0 + i];
+    }
+    if (tid < 9) {
+        const double cv = cell[9 * (int64_t)r + tid];
+        cello[9 * (int64_t)st + tid] = (float)cv;
+        const int row = tid / 3, colm = tid % 3;
+        invo[9 * (int64_t)st + tid] = row == colm ? (float)(1.0 / cv) : 0.f;     // orthorhombic cells only (rlvd_action_space status 0)
+    }
+    if (tid < 3) imgo[3 * (int64_t)st + tid] = 0;                                  // cell heights >= 2 * cutoff are the caller's contract
+    if (tid == 0) {
+        node_ptr[st] = (int)o0;
+        if (side == 0) { rs[g] = st; owner[g] = r; } else ps[g] = st;
+        if (g == gridDim.x - 1 && side == 1) node_ptr[st + 1] = (int)(o0 + n_atoms_per);
+    }
+}
+
+// simulator.py:94-98 for all replicas, then environment.step's position update: p = softmax(Q / kT) in fp32,
+// np.random.choice semantics for the draw (cdf = cumsum(p) in fp64, cdf /= cdf[-1], first index with cdf > u), then
+// pos[atom] += disp in fp64.  u[r] comes from the caller (np.random.random_sample() for bit-compatible replays, or any
+// counter-based generator).
+__global__ void __launch_bounds__(128) select_apply_kernel(int n_rep, const int* __restrict__ rep_ptr, const int* __restrict__ first,
+                                                           const float* __restrict__ rl_q, const float* __restrict__ temperature,
+                                                           const double* __restrict__ u, const double* __restrict__ actions,
+                                                           int max_actions, int apply, double* __restrict__ pos,
+                                                           int* __restrict__ chosen, int* __restrict__ argmax_out, float* __restrict__ probs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rep) return;
+    const int g0 = first[r], nc = first[r + 1] - g0;
+    if (nc <= 0) { chosen[r] = -1; argmax_out[r] = -1; return; }
+    const float kT = temperature[r] * 8.617e-5f;
+    float m = -3.4e38f;
+    int am = 0;
+    for (int c = 0; c < nc; ++c) {
+        const float z = rl_q[g0 + c] / kT;
+        if (z > m) { m = z; am = c; }
+    }
+    float s = 0.f;
+    for (int c = 0; c < nc; ++c) s += expf(rl_q[g0 + c] / kT - m);
+    double tot = 0.0;
+    for (int c = 0; c < nc; ++c) {
+        const float p = expf(rl_q[g0 + c] / kT - m) / s;
+        if (probs != nullptr) probs[(int64_t)r * max_actions + c] = p;
+        tot += (double)p;
+    }
+    double run = 0.0;
+    int pick = nc - 1;
+    for (int c = 0; c < nc; ++c) {
+        run += (double)(expf(rl_q[g0 + c] / kT - m) / s);
+        if (run / tot > u[r]) { pick = c; break; }
+    }
+    chosen[r] = pick;
+    argmax_out[r] = am;
+    if (apply) {
+        const double* act = actions + ((int64_t)r * max_actions + pick) * 4;
+        const int64_t a = rep_ptr[r] + (int)act[0];
+        pos[3 * a] += act[1];
+        pos[3 * a + 1] += act[2];
+        pos[3 * a + 2] += act[3];
+    }
+}
+
+}  // namespace
+
+int launch_candidate_offsets(rlvd_engine* e, cudaStream_t s, int n_rep, const int* count, int* first, int* total) {
+    Span sp(e, s, FAM_NEIGHBOR);
+    candidate_offsets_kernel<<<1, 1024, 0, s>>>(n_rep, count, first, total);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_expand_candidates(rlvd_engine* e, cudaStream_t s, int n_rep, int n_cand, const int* rep_ptr, const int* first, const int* Z,
+                             const double* pos, const double* cell, const double* actions, int max_actions, int n_atoms_per,
+                             int* node_ptr, int* Zo, float* poso, float* cello, float* invo, int* imgo, int* rs, int* ps, int* owner) {
+    if (n_cand <= 0) return 0;
+    Span sp(e, s, FAM_NEIGHBOR);
+    expand_candidates_kernel<<<dim3(n_cand, 2), 128, 0, s>>>(n_rep, rep_ptr, first, Z, pos, cell, actions, max_actions, n_atoms_per,
+                                                            node_ptr, Zo, poso, cello, invo, imgo, rs, ps, owner);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_select_apply(rlvd_engine* e, cudaStream_t s, int n_rep, const int* rep_ptr, const int* first, const float* rl_q,
+                        const float* temperature, const double* u, const double* actions, int max_actions, int apply, double* pos,
+                        int* chosen, int* argmax_out, float* probs) {
+    if (n_rep <= 0) return 0;
+    Span sp(e, s, FAM_READOUT);
+    select_apply_kernel<<<(n_rep + 127) / 128, 128, 0, s>>>(n_rep, rep_ptr, first, rl_q, temperature, u, actions, max_actions, apply,
+                                                           pos, chosen, argmax_out, probs);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rlvd

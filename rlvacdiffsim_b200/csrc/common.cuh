@@ -220,4 +220,12 @@ int launch_time_readout(rlvd_engine* e, cudaStream_t s, int n_struct, const int*
 int launch_action_space(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const double* pos, const double* cell,
                         double a, int max_vac, int max_actions, int* count, double* actions, int* status);
 
+int launch_candidate_offsets(rlvd_engine* e, cudaStream_t s, int n_rep, const int* count, int* first, int* total);
+int launch_expand_candidates(rlvd_engine* e, cudaStream_t s, int n_rep, int n_cand, const int* rep_ptr, const int* first, const int* Z,
+                             const double* pos, const double* cell, const double* actions, int max_actions, int n_atoms_per,
+                             int* node_ptr, int* Zo, float* poso, float* cello, float* invo, int* imgo, int* rs, int* ps, int* owner);
+int launch_select_apply(rlvd_engine* e, cudaStream_t s, int n_rep, const int* rep_ptr, const int* first, const float* rl_q,
+                        const float* temperature, const double* u, const double* actions, int max_actions, int apply, double* pos,
+                        int* chosen, int* argmax_out, float* probs);
+
 }  // namespace rlvd

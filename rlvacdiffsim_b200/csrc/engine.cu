@@ -418,6 +418,35 @@ int rlvd_action_space(rlvd_engine* e, void* stream, int32_t n_struct, const int3
                                max_actions, d_count, d_actions, d_status);
 }
 
+int rlvd_candidate_offsets(rlvd_engine* e, void* stream, int32_t n_rep, const int32_t* d_count, int32_t* d_first,
+                           int32_t* d_total) {
+    RLVD_CHECK(e != nullptr && n_rep > 0 && d_count && d_first && d_total, "rlvd_candidate_offsets: bad argument");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_candidate_offsets(e, (cudaStream_t)stream, n_rep, d_count, d_first, d_total);
+}
+
+int rlvd_expand_candidates(rlvd_engine* e, void* stream, int32_t n_rep, int32_t n_cand, int32_t n_atoms_per,
+                           const int32_t* d_rep_ptr, const int32_t* d_first, const int32_t* d_Z, const double* d_pos,
+                           const double* d_cell, const double* d_actions, int32_t max_actions, int32_t* d_node_ptr,
+                           int32_t* d_Z_out, float* d_pos_out, float* d_cell_out, float* d_inv_out, int32_t* d_img_out,
+                           int32_t* d_react_struct, int32_t* d_prod_struct, int32_t* d_owner) {
+    RLVD_CHECK(e != nullptr && n_rep > 0 && n_cand >= 0 && n_atoms_per > 0, "rlvd_expand_candidates: bad sizes");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_expand_candidates(e, (cudaStream_t)stream, n_rep, n_cand, d_rep_ptr, d_first, d_Z, d_pos, d_cell, d_actions,
+                                    max_actions, n_atoms_per, d_node_ptr, d_Z_out, d_pos_out, d_cell_out, d_inv_out, d_img_out,
+                                    d_react_struct, d_prod_struct, d_owner);
+}
+
+int rlvd_select_apply(rlvd_engine* e, void* stream, int32_t n_rep, const int32_t* d_rep_ptr, const int32_t* d_first,
+                      const float* d_rl_q, const float* d_temperature, const double* d_uniform, const double* d_actions,
+                      int32_t max_actions, int32_t apply, double* d_pos, int32_t* d_chosen, int32_t* d_argmax, float* d_probs) {
+    RLVD_CHECK(e != nullptr && n_rep > 0 && d_first && d_rl_q && d_temperature && d_uniform && d_chosen && d_argmax,
+               "rlvd_select_apply: bad argument");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_select_apply(e, (cudaStream_t)stream, n_rep, d_rep_ptr, d_first, d_rl_q, d_temperature, d_uniform, d_actions,
+                               max_actions, apply, d_pos, d_chosen, d_argmax, d_probs);
+}
+
 int rlvd_time_readout(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const float* d_q,
                       const float* d_T, const float* d_defect, const rlvd_time_head* head, float* d_time) {
     RLVD_CHECK(e != nullptr && head != nullptr, "rlvd_time_readout: bad argument");

@@ -175,6 +175,47 @@ class Engine:
                                              _ptr(count), _ptr(actions), _ptr(status)))
         return count[:G], actions[:G], status[:G]
 
+    # ------------------------------------------------------------------ A2/A3/A5 on the device
+    def candidate_offsets(self, count: torch.Tensor):
+        R = count.numel()
+        first = torch.empty(R + 1, dtype=torch.int32, device=self.device)
+        total = torch.empty(1, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_candidate_offsets(self._h, self._stream(), R, _ptr(count), _ptr(first), _ptr(total)))
+        return first, total
+
+    def expand_candidates(self, rep_ptr, first, n_cand: int, n_atoms_per: int, Z, pos, cell, actions):
+        """→ dict of the scoring-batch tensors (Z, pos, cell, inv, img, ptr, rs, ps, owner) for ``score_device``."""
+        R, S = rep_ptr.numel() - 1, 2 * n_cand
+        dev = self.device
+        o = {"Z": torch.empty(S * n_atoms_per, dtype=torch.int32, device=dev),
+             "pos": torch.empty((S * n_atoms_per, 3), dtype=torch.float32, device=dev),
+             "cell": torch.empty((S, 3, 3), dtype=torch.float32, device=dev),
+             "inv": torch.empty((S, 3, 3), dtype=torch.float32, device=dev),
+             "img": torch.empty((S, 3), dtype=torch.int32, device=dev),
+             "ptr": torch.empty(S + 1, dtype=torch.int32, device=dev),
+             "rs": torch.empty(n_cand, dtype=torch.int32, device=dev),
+             "ps": torch.empty(n_cand, dtype=torch.int32, device=dev),
+             "owner": torch.empty(n_cand, dtype=torch.int32, device=dev)}
+        with torch.cuda.device(dev):
+            check(self.lib.rlvd_expand_candidates(self._h, self._stream(), R, n_cand, n_atoms_per, _ptr(rep_ptr), _ptr(first),
+                                                  _ptr(Z), _ptr(pos), _ptr(cell), _ptr(actions), actions.shape[1], _ptr(o["ptr"]),
+                                                  _ptr(o["Z"]), _ptr(o["pos"]), _ptr(o["cell"]), _ptr(o["inv"]), _ptr(o["img"]),
+                                                  _ptr(o["rs"]), _ptr(o["ps"]), _ptr(o["owner"])))
+        return o
+
+    def select_apply(self, rep_ptr, first, rl_q, temperature, uniform, actions, pos, apply: bool = True):
+        """→ (chosen i32[R], argmax i32[R], probs f32[R, max_actions]); ``pos`` (fp64) is updated in place when ``apply``."""
+        R = rep_ptr.numel() - 1
+        chosen = torch.empty(R, dtype=torch.int32, device=self.device)
+        amax = torch.empty(R, dtype=torch.int32, device=self.device)
+        probs = torch.zeros((R, actions.shape[1]), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_select_apply(self._h, self._stream(), R, _ptr(rep_ptr), _ptr(first), _ptr(rl_q),
+                                             _ptr(temperature), _ptr(uniform), _ptr(actions), actions.shape[1], int(apply),
+                                             _ptr(pos), _ptr(chosen), _ptr(amax), _ptr(probs)))
+        return chosen, amax, probs
+
     # ------------------------------------------------------------------ T1: t_net head
     def time_readout(self, q: torch.Tensor, node_ptr: torch.Tensor, T: torch.Tensor, defect: torch.Tensor,
                      head: TimeHead) -> torch.Tensor:

@@ -224,3 +224,64 @@ class ReplicaScorer:
         p = torch.softmax(z, dim=0).numpy()
         idx = int(np.random.choice(len(p), p=p)) if rng is None else int(rng.choice(len(p), p=p / p.sum()))
         return idx, p
+
+
+class DeviceLSS:
+    """Whole LSS steps for many replicas without a host round trip.
+
+    The reference's loop (``rlsim/drl/simulator.py:187-236`` per replica, ``deploy.py:75-94`` over replicas) does, per
+    step and per replica on the host: ``get_action_space`` (ASE + numpy), ``convert_to_graph_list``, collate, H2D, the
+    model call, softmax + ``np.random.choice``, ``env.step``.  Here every stage is a kernel over all replicas:
+    ``rlvd_action_space`` → ``rlvd_candidate_offsets`` → ``rlvd_expand_candidates`` → K1..K5 → ``rlvd_select_apply``;
+    the replicas' fp64 positions never leave the device.  One 4-byte D2H per step (the candidate count, to size the
+    batch).  Replicas must share one atom count and have orthorhombic cells with heights >= 2 x cutoff (the BASELINE
+    supercells); relaxation / NEB between steps is outside this build's scope."""
+
+    def __init__(self, model, replicas: Sequence[Atoms], device: int | str = 0, lattice_parameter: float = 3.528,
+                 max_vacancies: int = 1, q_params: Optional[dict] = None):
+        self.model = model
+        self.device = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        self.engine: Engine = model._engine_for(self.device)
+        self.a = float(lattice_parameter)
+        self.max_vac = int(max_vacancies)
+        self.q_params = dict(q_params or {"alpha": 0.0, "beta": 1.0, "dqn": True})
+        n = {len(r) for r in replicas}
+        if len(n) != 1:
+            raise ValueError("DeviceLSS needs replicas of one size")
+        self.n_atoms = n.pop()
+        self.R = len(replicas)
+        for r in replicas:
+            c = np.asarray(r.get_cell(), dtype=np.float64)
+            if np.abs(c - np.diag(np.diag(c))).max() != 0.0 or np.diag(c).min() < 2 * self.engine.cutoff:
+                raise ValueError("DeviceLSS needs orthorhombic cells with heights >= 2 x cutoff")
+        dev = self.device
+        self.pos = torch.from_numpy(np.concatenate([np.asarray(r.get_positions(), dtype=np.float64) for r in replicas])).to(dev)
+        self.Z = torch.from_numpy(np.concatenate([np.asarray(r.get_atomic_numbers(), dtype=np.int32) for r in replicas])).to(dev)
+        self.cell = torch.from_numpy(np.stack([np.asarray(r.get_cell(), dtype=np.float64) for r in replicas])).to(dev)
+        self.rep_ptr = torch.arange(0, (self.R + 1) * self.n_atoms, self.n_atoms, dtype=torch.int32, device=dev)
+
+    def positions(self) -> np.ndarray:
+        return self.pos.cpu().numpy().reshape(self.R, self.n_atoms, 3)
+
+    def step(self, temperature: float, uniforms: Optional[np.ndarray] = None, apply: bool = True) -> Dict[str, torch.Tensor]:
+        """One LSS step of every replica.  ``uniforms[R]`` are the inverse-cdf draws (``np.random.random_sample(R)``
+        reproduces the reference's ``np.random.choice`` stream); default: a fresh draw from the global numpy RNG."""
+        eng, dev = self.engine, self.device
+        count, actions, status = eng.action_space(self.pos, self.cell, self.rep_ptr, self.a, self.max_vac,
+                                                  max_actions=12 * self.max_vac)
+        first, total = eng.candidate_offsets(count)
+        head = torch.cat([total, status.max().reshape(1).to(torch.int32)]).cpu().numpy()     # the step's one D2H
+        if head[1] != 0:
+            raise AssertionError("Expected 1 vacancy" if head[1] == 2 and self.max_vac == 1 else
+                                 f"rlvd_action_space status {int(head[1])}")
+        G = int(head[0])
+        b = eng.expand_candidates(self.rep_ptr, first, G, self.n_atoms, self.Z, self.pos, self.cell, actions)
+        qp = eng.q_params(dict(self.q_params, temperature=float(temperature)), self.model.head_spec)
+        out = eng.score_device(b["Z"], b["pos"], b["cell"], b["inv"], b["img"], b["ptr"], b["rs"], b["ps"], qp,
+                               max_struct_nodes=self.n_atoms)
+        u = np.random.random_sample(self.R) if uniforms is None else np.asarray(uniforms, dtype=np.float64)
+        T = torch.full((self.R,), float(temperature), dtype=torch.float32, device=dev)
+        chosen, amax, probs = eng.select_apply(self.rep_ptr, first, out["rl_q"], T, torch.from_numpy(u).to(dev), actions,
+                                               self.pos, apply)
+        return {"chosen": chosen, "argmax": amax, "probs": probs, "rl_q": out["rl_q"], "first": first, "actions": actions,
+                "count": count}

@@ -379,3 +379,34 @@ def test_action_space_device_matches_host_enumerator(engine):
     # a non-orthorhombic cell (the demo POSCAR) falls through to the host enumerator
     demo = read_poscar(os.path.join(GOLD, "POSCAR_0"))
     assert rb.get_action_space_device(engine, [demo], 3.528)[0] == rb.get_action_space(demo, 3.528)
+
+
+def test_device_lss_steps_match_host_loop(model):
+    """Three LSS steps of four replicas: device-resident pipeline vs the reference-shaped host loop
+    (get_action_space -> pack -> score -> softmax -> np.random.choice -> apply)."""
+    from rlvacdiffsim_b200.simulator import DeviceLSS
+    from rlvacdiffsim_b200.structures import apply_action
+    qp = {"alpha": 0.0, "beta": 1.0, "dqn": True}
+    host = [make_crconi_supercell(4, seed=30 + s, jitter=0.03) for s in range(4)]
+    lss = DeviceLSS(model, host, 0, 3.528, 1, qp)
+    scorer = ReplicaScorer(model, 0)
+    T = 900.0
+    rng = np.random.RandomState(5)
+    for step in range(3):
+        u = rng.random_sample(4)
+        res = lss.step(T, uniforms=u)
+        first = res["first"].cpu().numpy()
+        q_dev = res["rl_q"].cpu().numpy()
+        spaces = [rb.get_action_space(h, 3.528) for h in host]
+        q_host = scorer.score(host, spaces, dict(qp, temperature=T))
+        for r in range(4):
+            assert np.array_equal(q_dev[first[r]:first[r + 1]], q_host[r])            # same batch, same kernels: bitwise
+            z = torch.from_numpy(q_host[r]) / (T * 8.617e-5)
+            p = torch.softmax(z, dim=0).numpy().astype(np.float64)
+            cdf = np.cumsum(p); cdf /= cdf[-1]
+            pick = int(np.searchsorted(cdf, u[r], side="right"))                       # np.random.choice's draw
+            assert int(res["chosen"][r]) == pick
+            assert int(res["argmax"][r]) == int(np.argmax(q_host[r]))
+            np.testing.assert_allclose(res["probs"][r, :12].cpu().numpy(), p, rtol=2e-5, atol=1e-7)
+            host[r] = apply_action(host[r], spaces[r][pick])
+        np.testing.assert_array_equal(lss.positions(), np.stack([h.positions for h in host]))   # fp64 state: bit-identical
