@@ -231,6 +231,26 @@ def main():
     fam = {k: eng.profile_read(k) for k in ("neighbor", "edge_pack", "edge", "node", "readout")}
     eng.profile(False)
 
+    # whole LSS step on the device (enumerate -> expand -> K1..K5 -> select -> apply), next to the reference-shaped host
+    # front end (get_action_space + pack per replica) it replaces; reported as an extra object, never as the headline
+    from rlvacdiffsim_b200.simulator import DeviceLSS
+    lss = DeviceLSS(model, reps, dev, 3.528, 1, {k: Q_PARAMS[k] for k in ("alpha", "beta", "dqn")})
+    lss_rng = np.random.RandomState(1234 + rank)
+    for _ in range(2):
+        lss.step(Q_PARAMS["temperature"], uniforms=lss_rng.random_sample(n_rep))
+    torch.cuda.synchronize(dev)
+    lss_steps = min(args.steps, 3)
+    t0 = time.perf_counter()
+    for _ in range(lss_steps):
+        lss.step(Q_PARAMS["temperature"], uniforms=lss_rng.random_sample(n_rep))
+    torch.cuda.synchronize(dev)
+    ms_lss = (time.perf_counter() - t0) * 1e3 / lss_steps
+    t0 = time.perf_counter()
+    n_front = min(n_rep, 8)
+    front = make_shard(rank, n_front, args.jitter)
+    pack_replicas(front[0], front[1])
+    ms_host_front = (time.perf_counter() - t0) * 1e3 / n_front * n_rep      # supercell build + enumeration + packing, scaled
+
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -290,6 +310,12 @@ def main():
                                   "frac": smem_achieved / smem_peak if smem_peak else None,
                                   "gather_bytes_per_launch": smem_bytes,
                                   "peak_source": "128 B/clk/SM x SMs x sampled SM clock"}},
+            "device_lss": {"what": "one full LSS step of every replica on the device: rlvd_action_space -> expand -> K1..K5 -> "
+                                   "softmax/draw -> apply, fp64 state resident in HBM, one 8-byte D2H per step",
+                           "ms_per_step": ms_lss, "value": world * n_q / (ms_lss * 1e-3), "unit": "Q-evals/s (rank 0 wall clock)",
+                           "host_front_end_ms_per_step": ms_host_front,
+                           "host_front_end": "reference-shaped per-replica numpy enumeration + packing for the same shard "
+                                             f"(measured on {n_front} replicas, scaled)"},
             "kernel_share": {k: (v[0] / total_prof if total_prof > 0 else None) for k, v in fam.items()},
             "kernel_ms_per_step": {k: v[0] / prof_steps for k, v in fam.items()},
         }
