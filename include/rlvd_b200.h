@@ -133,6 +133,15 @@ int  rlvd_select_apply(rlvd_engine* e, void* stream, int32_t n_rep, const int32_
                        const float* d_rl_q, const float* d_temperature, const double* d_uniform, const double* d_actions,
                        int32_t max_actions, int32_t apply, double* d_pos, int32_t* d_chosen, int32_t* d_argmax, float* d_probs);
 
+/* ---- Warren-Cowley pair counts (rlsim/utils/sro.py:49-83 `get_sro_from_atoms`, used per candidate by the sro_pixel
+ *      filter at rlsim/drl/simulator.py:60-92) ------------------------------------------------------------------ */
+/* d_species_index[M] in [0, n_species) (index into the sorted species list); d_counts[n_struct, n_species, n_species]
+ * = ordered first-shell pair counts (i of species a, j of species b) with r_cut = (1 + sqrt2)/2 * NN_dist;
+ * d_status[g] = 1 for non-orthorhombic cells (not computed).  SRO[a,b] = 1 - (n_ab / n_pairs) / c_a / c_b on the host. */
+int  rlvd_sro_counts(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const double* d_pos,
+                     const double* d_cell, const int32_t* d_species_index, int32_t n_species, int64_t* d_counts,
+                     int32_t* d_status);
+
 /* ---- T1: t_net head on top of rlvd_painn_representation (replaces rgnn `t_net` forward reached from
  *      rlsim/cli/scripts/estimate_time.py:58 `model(batch, inference=True)["time"]` and rlsim/time/train.py:108,114) -- */
 /* Head weights live on the device (the caller's nn.Parameters); nn.Linear layout [out, in].  No t_net checkpoint is

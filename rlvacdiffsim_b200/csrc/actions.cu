@@ -324,3 +324,84 @@ int launch_select_apply(rlvd_engine* e, cudaStream_t s, int n_rep, const int* re
 }
 
 }  // namespace rlvd
+
+// ------------------------------------------------------------------------------------------------------------------
+// Warren–Cowley pair counts (rlsim/utils/sro.py:49-83, called per candidate at simulator.py:60-92):
+// NN_dist = smallest minimum-image distance above 0.1, r_cut = (1 + sqrt2)/2 * NN_dist, ordered pair counts per
+// species pair inside (0.1, r_cut).  One CTA per structure (orthorhombic cells), fp64 distances in numpy's operation
+// order; integer counts, so the host formula gives the reference's matrix exactly.
+// ------------------------------------------------------------------------------------------------------------------
+namespace rlvd {
+
+namespace {
+
+constexpr int SRO_MAX_SPECIES = 8;
+
+__global__ void __launch_bounds__(256) sro_counts_kernel(int n_struct, const int* __restrict__ node_ptr, const double* __restrict__ pos,
+                                                         const double* __restrict__ cell, const int* __restrict__ sid, int n_species,
+                                                         long long* __restrict__ counts, int* __restrict__ status) {
+    __shared__ double red[256];
+    __shared__ unsigned long long cnt[SRO_MAX_SPECIES * SRO_MAX_SPECIES];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (g >= n_struct) return;
+    const int n0 = node_ptr[g], n = node_ptr[g + 1] - n0;
+    const double* C = cell + 9 * (int64_t)g;
+    const bool diag = C[1] == 0.0 && C[2] == 0.0 && C[3] == 0.0 && C[5] == 0.0 && C[6] == 0.0 && C[7] == 0.0;
+    if (!diag) {
+        if (tid == 0) status[g] = 1;
+        return;
+    }
+    const double Lx = C[0], Ly = C[4], Lz = C[8];
+    if (tid < SRO_MAX_SPECIES * SRO_MAX_SPECIES) cnt[tid] = 0ull;
+    // ---- pass 1: nearest-neighbour distance
+    double best = 1e300;
+    for (int64_t p = tid; p < (int64_t)n * n; p += 256) {
+        const int i = (int)(p / n), j = (int)(p % n);
+        const double* pi = pos + 3 * (int64_t)(n0 + i);
+        const double* pj = pos + 3 * (int64_t)(n0 + j);
+        const double d = norm3(mic1(__dsub_rn(pj[0], pi[0]), Lx), mic1(__dsub_rn(pj[1], pi[1]), Ly), mic1(__dsub_rn(pj[2], pi[2]), Lz));
+        if (d > 0.1 && d < best) best = d;
+    }
+    red[tid] = best;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red[tid] = fmin(red[tid], red[tid + o]);
+        __syncthreads();
+    }
+    const double r_cut = __dmul_rn(__ddiv_rn(__dadd_rn(1.0, sqrt(2.0)), 2.0), red[0]);
+    // ---- pass 2: ordered pair counts per species pair
+    unsigned int mine[SRO_MAX_SPECIES * SRO_MAX_SPECIES];
+#pragma unroll
+    for (int t = 0; t < SRO_MAX_SPECIES * SRO_MAX_SPECIES; ++t) mine[t] = 0u;
+    for (int64_t p = tid; p < (int64_t)n * n; p += 256) {
+        const int i = (int)(p / n), j = (int)(p % n);
+        const double* pi = pos + 3 * (int64_t)(n0 + i);
+        const double* pj = pos + 3 * (int64_t)(n0 + j);
+        const double d = norm3(mic1(__dsub_rn(pj[0], pi[0]), Lx), mic1(__dsub_rn(pj[1], pi[1]), Ly), mic1(__dsub_rn(pj[2], pi[2]), Lz));
+        if (d > 0.1 && d < r_cut) {
+            const int k = sid[n0 + i] * n_species + sid[n0 + j];
+#pragma unroll
+            for (int t = 0; t < SRO_MAX_SPECIES * SRO_MAX_SPECIES; ++t) mine[t] += (t == k) ? 1u : 0u;
+        }
+    }
+    for (int t = 0; t < n_species * n_species; ++t)
+        if (mine[t]) atomicAdd(&cnt[t], (unsigned long long)mine[t]);      // integer sums: order-independent
+    __syncthreads();
+    if (tid < n_species * n_species) counts[(int64_t)g * n_species * n_species + tid] = (long long)cnt[tid];
+    if (tid == 0) status[g] = 0;
+}
+
+}  // namespace
+
+int launch_sro_counts(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const double* pos, const double* cell,
+                      const int* sid, int n_species, long long* counts, int* status) {
+    if (n_struct <= 0) return 0;
+    RLVD_CHECK(n_species >= 1 && n_species <= SRO_MAX_SPECIES, "rlvd_sro_counts: n_species %d not in [1,%d]", n_species, SRO_MAX_SPECIES);
+    Span sp(e, s, FAM_NEIGHBOR);
+    sro_counts_kernel<<<n_struct, 256, 0, s>>>(n_struct, node_ptr, pos, cell, sid, n_species, counts, status);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rlvd

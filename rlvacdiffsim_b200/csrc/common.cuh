@@ -228,4 +228,7 @@ int launch_select_apply(rlvd_engine* e, cudaStream_t s, int n_rep, const int* re
                         const float* temperature, const double* u, const double* actions, int max_actions, int apply, double* pos,
                         int* chosen, int* argmax_out, float* probs);
 
+int launch_sro_counts(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const double* pos, const double* cell,
+                      const int* sid, int n_species, long long* counts, int* status);
+
 }  // namespace rlvd

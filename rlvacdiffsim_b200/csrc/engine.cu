@@ -447,6 +447,15 @@ int rlvd_select_apply(rlvd_engine* e, void* stream, int32_t n_rep, const int32_t
                                max_actions, apply, d_pos, d_chosen, d_argmax, d_probs);
 }
 
+int rlvd_sro_counts(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const double* d_pos,
+                    const double* d_cell, const int32_t* d_species_index, int32_t n_species, int64_t* d_counts,
+                    int32_t* d_status) {
+    RLVD_CHECK(e != nullptr && d_node_ptr && d_pos && d_cell && d_species_index && d_counts && d_status, "rlvd_sro_counts: bad argument");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_sro_counts(e, (cudaStream_t)stream, n_struct, d_node_ptr, d_pos, d_cell, d_species_index, n_species,
+                             reinterpret_cast<long long*>(d_counts), d_status);
+}
+
 int rlvd_time_readout(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const float* d_q,
                       const float* d_T, const float* d_defect, const rlvd_time_head* head, float* d_time) {
     RLVD_CHECK(e != nullptr && head != nullptr, "rlvd_time_readout: bad argument");

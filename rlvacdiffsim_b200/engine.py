@@ -216,6 +216,17 @@ class Engine:
                                              _ptr(pos), _ptr(chosen), _ptr(amax), _ptr(probs)))
         return chosen, amax, probs
 
+    # ------------------------------------------------------------------ Warren-Cowley pair counts
+    def sro_counts(self, pos: torch.Tensor, cells: torch.Tensor, node_ptr: torch.Tensor, species_index: torch.Tensor,
+                   n_species: int):
+        G = node_ptr.numel() - 1
+        counts = torch.zeros((max(G, 1), n_species, n_species), dtype=torch.int64, device=self.device)
+        status = torch.zeros(max(G, 1), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_sro_counts(self._h, self._stream(), G, _ptr(node_ptr), _ptr(pos), _ptr(cells),
+                                           _ptr(species_index), n_species, _ptr(counts), _ptr(status)))
+        return counts[:G], status[:G]
+
     # ------------------------------------------------------------------ T1: t_net head
     def time_readout(self, q: torch.Tensor, node_ptr: torch.Tensor, T: torch.Tensor, defect: torch.Tensor,
                      head: TimeHead) -> torch.Tensor:

@@ -61,9 +61,7 @@ class RLSimulator:
         self.model = model
         self.device = self.env.calc_params["device"]
         self.kb = KB_EV
-        if sro_pixel is not None:
-            raise NotImplementedError("the SRO-pixel action filter (simulator.py:60-92) is outside the hot path")
-        self.sro_pixel = None
+        self.sro_pixel = sro_pixel
         self.save_sro = save_sro
         self.kwargs = kwargs
 
@@ -83,10 +81,38 @@ class RLSimulator:
                 rl_q = self.model(batch, q_params=self.q_params)["rl_q"]
                 total_q_list.append(rl_q.detach())
         Q = torch.concat(total_q_list, dim=-1)
+        sro_list = None
+        valid = None
+        if self.sro_pixel is not None:                         # simulator.py:60-92: keep candidates whose product SRO is in the pixel
+            from .sro import get_sro_from_atoms
+            valid, sros = [], []
+            atoms = self.env.atoms.copy()
+            pos = atoms.get_positions()
+            for i, action in enumerate(action_space):
+                pos[int(action[0])] += np.array(action[1:]) * 1 / 0.8
+                atoms.set_positions(pos)
+                sro = get_sro_from_atoms(atoms)
+                sros.append(sro)
+                pos[int(action[0])] -= np.array(action[1:]) * 1 / 0.8
+                d = np.diag(sro)
+                if len(self.sro_pixel) == 4:
+                    x0, y0, z0, L = self.sro_pixel
+                    if x0 - L / 2 < d[0] < x0 + L / 2 and y0 - L / 2 < d[1] < y0 + L / 2 and z0 - L / 2 < d[2] < z0 + L / 2:
+                        valid.append(i)
+                elif len(self.sro_pixel) == 2:
+                    x0, L = self.sro_pixel
+                    scalar = np.sqrt(np.sum(sro[0, :] ** 2) + np.sum(sro[1, 1:] ** 2) + sro[2, 2] ** 2)
+                    if x0 - L / 2 < scalar < x0 + L / 2:
+                        valid.append(i)
+            vt = torch.tensor(valid, device=Q.device, dtype=torch.long)
+            Q = Q[vt]
+            sro_list = torch.tensor(np.asarray(sros), device=Q.device)[vt]
         action_probs = nn.Softmax(dim=0)(Q / (temperature * self.kb))
         p = action_probs.detach().cpu().numpy()
         action = np.random.choice(len(p), p=p)
-        return action, action_probs, Q, None
+        if valid is not None:
+            action = valid[action]                             # simulator.py:99-101
+        return action, action_probs, Q, sro_list
 
     def _action_space(self):
         enumerator = self.kwargs.get("enumerator", "live")

@@ -410,3 +410,30 @@ def test_device_lss_steps_match_host_loop(model):
             np.testing.assert_allclose(res["probs"][r, :12].cpu().numpy(), p, rtol=2e-5, atol=1e-7)
             host[r] = apply_action(host[r], spaces[r][pick])
         np.testing.assert_array_equal(lss.positions(), np.stack([h.positions for h in host]))   # fp64 state: bit-identical
+
+
+# ----------------------------------------------------------------------------- SRO (Warren-Cowley) pair counts
+
+def test_sro_device_matches_host_mirror(model, engine):
+    """rlsim/utils/sro.py:49-83: the device pair counts give the host mirror's matrix exactly; the sro_pixel filter of
+    select_action (simulator.py:60-92) runs on top of it."""
+    from rlvacdiffsim_b200.sro import get_sro_from_atoms, sro_device
+    structs = [make_crconi_supercell(4, seed=s, jitter=j) for s, j in ((0, 0.0), (1, 0.04), (2, 0.07))]
+    structs.append(make_crconi_supercell(3, seed=4, jitter=0.02))
+    demo = read_poscar(os.path.join(GOLD, "POSCAR_0"))                     # non-orthorhombic: host fallback inside sro_device
+    got = sro_device(engine, structs + [demo], [24, 27, 28])
+    for m, s in zip(got, structs + [demo]):
+        ref = get_sro_from_atoms(s)
+        assert m.shape == (3, 3) and np.array_equal(m, ref)
+    env = LatticeEnv(structs[1], {"device": "cuda"})
+    # the filter un-scales the hop by 1/0.8 (simulator.py:66,70): it expects the 0.8-scaled legacy actions
+    legacy = rb.get_action_space_legacy(structs[1], 3.528)
+    sim = RLSimulator(env, model, q_params={"alpha": 0.0, "beta": 1.0, "dqn": True}, sro_pixel=(0.0, 10.0),
+                      lattice_parameter=3.528, enumerator="legacy")
+    np.random.seed(3)
+    act, probs, Q, sro_list = sim.select_action(legacy, 900.0)
+    assert 0 <= act < 12 and Q.shape == (12,) and tuple(sro_list.shape) == (12, 3, 3)
+    sim2 = RLSimulator(env, model, q_params={"alpha": 0.0, "beta": 1.0, "dqn": True}, sro_pixel=(5.0, 0.1),
+                       lattice_parameter=3.528, enumerator="legacy")
+    with pytest.raises(Exception):                                           # empty pixel: no valid action, like the reference
+        sim2.select_action(legacy, 900.0)

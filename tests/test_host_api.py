@@ -150,3 +150,16 @@ def test_t_net_surface_and_oracle_head(checkpoint_path):
     t = m.time_forward(s.numbers, s.positions.astype(np.float32), np.asarray(s.cell)[None], np.array([0, len(s)]),
                        [900.0], [1 / 32], head, tau=12.0)
     assert TIME_HEAD_SPEC_V0.squash == "tau * sigmoid" and float(t[0]) == pytest.approx(6.0)
+
+
+def test_sro_host_mirror_properties():
+    """rlsim/utils/sro.py:49-83 restated in numpy: symmetric, near zero for a random equiatomic alloy, and the
+    pair bookkeeping sums to the 12-neighbour first shell."""
+    from rlvacdiffsim_b200.sro import _sro_from_counts, get_sro_from_atoms
+    s = make_crconi_supercell(4, seed=0, jitter=0.02)
+    m = get_sro_from_atoms(s)
+    assert m.shape == (3, 3) and np.allclose(m, m.T) and np.abs(m).max() < 0.1
+    # a perfectly ordered toy: only unlike first-shell pairs -> alpha_AA = 1, alpha_AB = 1 - 1/(2 * 0.5 * 0.5) = -1
+    counts = np.array([[0.0, 48.0], [48.0, 0.0]])
+    o = _sro_from_counts(counts, np.array([4.0, 4.0]))
+    assert o[0, 0] == 1.0 and o[1, 1] == 1.0 and o[0, 1] == pytest.approx(-1.0)
