@@ -271,10 +271,11 @@ def main():
         edge_avg_ms = edge_ms / max(edge_n, 1)
         achieved = edge_bytes / (edge_avg_ms * 1e-3) / 1e9 if edge_avg_ms > 0 else 0.0
         # the same kernel against the resource that actually bounds it: every edge slot gathers five
-        # 128-byte table rows per 32-channel slice (two in layer 0) through the shared-memory crossbar, 128 B/clk/SM
+        # 128-byte table rows per 32-channel slice through the shared-memory crossbar, 128 B/clk/SM (layer 0 does not
+        # run this kernel any more: it is per-node GEMMs over species-resolved radial sums)
         sm_clock_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
         smem_peak = 128.0 * eng_sm_count * sm_clock_hz / 1e9
-        smem_bytes = n_edges * 4 * 128.0 * (5 + 5 + 2) / 3.0          # average over the three layer launches
+        smem_bytes = n_edges * 4 * 128.0 * 5
         smem_avg_ms = edge_avg_ms
         smem_achieved = smem_bytes / (smem_avg_ms * 1e-3) / 1e9 if smem_avg_ms > 0 else 0.0
         traffic = None
@@ -301,7 +302,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "edge_stream_kernel (K3a+K3c+K4 fused; one launch per layer)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "edge_stream_kernel (K3a+K3c+K4 fused; one launch per interaction layer 1, 2)", "achieved": achieved,
                          "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": edge_bytes,
                          "avg_launch_ms": edge_avg_ms, "launches_timed": edge_n,

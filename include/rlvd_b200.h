@@ -180,10 +180,17 @@ int  rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, i
  * fp32 SIMT tile kernel.  Synchronises the stream.  (nn.Linear inside rgnn's PaiNN) */
 int  rlvd_linear(rlvd_engine* e, void* stream, int32_t M, int32_t K, int32_t N, const float* d_A,
                  const float* d_A2, int32_t K1, const float* h_W, const float* h_bias, int32_t act, float* d_Y);
+/* Atomic numbers of the model's species (hyper_parameters["reaction_model"]["species"], the list rgnn's
+ * SpeciesEnergyScale and embedding are built over; deploy.py:18 loads them with the checkpoint).  Optional; call BEFORE
+ * rlvd_finalize_weights.  With <= 3 species the first interaction layer (q = embedding[Z], mu = 0) is evaluated as per-node
+ * GEMMs over species-resolved radial sums instead of per-edge messages; batches containing any other atomic
+ * number fall back to the per-edge kernels on the device, with identical results. */
+int  rlvd_set_species(rlvd_engine* e, const int32_t* atomic_numbers, int32_t n);
 /* Engine options: "tensor_cores" (1 = tcgen05 GEMMs and filters, 0 = fp32 SIMT kernels; both fp32-accurate),
  * "sliced_edge" (1 = structure-resident edge stream kernel, edge_stream.cu, for structures of <= 256 atoms; 0 = general),
  * "fuse_mlp" (1 = each Linear-SiLU-Linear context net is one launch with the hidden tile kept on the SM),
- * "fuse_mix" (1 = the |mu_V| and <mu_V, mu_W> reductions run in the mu_channel_mix GEMM epilogue). */
+ * "fuse_mix" (1 = the |mu_V| and <mu_V, mu_W> reductions run in the mu_channel_mix GEMM epilogue),
+ * "layer0_sums" (1 = layer 0 from species-resolved radial sums, see rlvd_set_species; 0 = per-edge kernels). */
 int  rlvd_set_option(rlvd_engine* e, const char* name, int32_t value);
 
 /* ---- introspection ------------------------------------------------------------------------------ */

@@ -12,6 +12,8 @@ namespace rlvd {
 
 constexpr int F = RLVD_F;          // 128 hidden channels
 constexpr int NRBF = RLVD_NRBF;    // 20 Bessel functions
+constexpr int L0_COLS = 256;       // layer-0 species sums per node: 4 blocks [Hx|Hy|Hz|G] of 64 = 3 species x 21 + pad
+constexpr int L0_STRIDE = 25;      // slot record of the pack kernel's layer-0 staging: v[21], dir[3], 1
 constexpr int NLAYER = RLVD_NLAYER;
 constexpr int GEOM = 24;           // per-edge geometry record of the fp32 SIMT kernel: 20 x phi*fcut, fcut, dir.xyz
 
@@ -63,7 +65,11 @@ struct Weights {
     const float* filt_T = nullptr;              // [L][21][384]  (k<20: weight^T, k=20: bias)
     const void* filt_F = nullptr;               // [L][3 parts][hi|lo] tf32 tensor-core operand (tc_edge.cu)
     const void* filt_E = nullptr;               // [L][4 slices][128][32] fp16-split TMEM image (edge_stream.cu)
-    float filt_kappa[NLAYER] = {};              // 2^-(sA+10): undoes the fp16 range scaling of filt_E and the edge tiles
+    float filt_kappa[NLAYER] = {};
+    // layer-0 collapse (engine.cu build_layer0): species index per atomic number and the three per-node GEMMs
+    const int32_t* z2s = nullptr;               // [100], -1 = not a model species
+    const void* l0_wF[3] = {};                  // [Hx|Hy] -> (dmu_x, dmu_y);  [Hz|G] -> dmu_z;  [Hz|G] -> dq
+    bool l0_ready = false;              // 2^-(sA+10): undoes the fp16 range scaling of filt_E and the edge tiles
     const float* feps = nullptr;                // [20] freqs[k] - (k+1)*freqs[0]
     const float* inter_w0T[NLAYER] = {};        // [128][128]   (in-major: Wt[k][n])
     const float* inter_b0[NLAYER] = {};
@@ -112,6 +118,10 @@ struct rlvd_engine {
     // workspaces (grown on demand, never shrunk)
     rlvd::DevBuf x, mu0, mu1, hid, mix, nrm, vw, ctx, struct_edges, struct_edge_ptr, scratch;
     rlvd::DevBuf tiles, pipe_info, tile_ctr, stream_scratch;   // edge stream (edge_stream.cu)
+    rlvd::DevBuf l0A;                                          // [M, 256] species-resolved radial sums of layer 0
+    int n_species = 0;                                         // rlvd_set_species
+    int species_z[3] = {};
+    bool use_l0_sums = true;        // layer 0 as per-node GEMMs over species-resolved radial sums (needs rlvd_set_species)
     // host-path staging
     rlvd::DevBuf in_node_ptr, in_Z, in_pos, in_cell, in_inv, in_img, in_rs, in_ps, in_temp, in_qp;
     rlvd::DevBuf g_row_ptr, g_node_struct, g_col, g_shift, g_nedges, g_q, out_pack;
@@ -174,6 +184,9 @@ struct LinearArgs {
     float* nrm = nullptr;
     float* vw = nullptr;
     float eps = 1e-8f;
+    // device-side gate: when set, the kernel runs only if *gate == gate_value (layer-0 collapse vs its fallback)
+    const int* gate = nullptr;
+    int gate_value = 0;
 };
 int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a);
 int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt);
@@ -195,14 +208,18 @@ struct EdgeArgs {
     const float* mu_in = nullptr;   // null in layer 0 (mu == 0)
     float* q = nullptr;
     float* mu_out = nullptr;
+    const int* gate = nullptr;      // stream kernel only: run only if *gate == gate_value
+    int gate_value = 0;
 };
 int launch_edge(rlvd_engine* e, cudaStream_t s, const EdgeArgs& a);
 bool edge_stream_supported(int max_struct_nodes);
 void edge_stream_format(const float* W, const float* b, std::vector<uint8_t>& out, float* kappa);
 int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_t n_edges, const int* node_ptr,
-                     const int* row_ptr, const int* col, const int8_t* shift, const float* pos, const float* cell);
+                     const int* row_ptr, const int* col, const int8_t* shift, const float* pos, const float* cell,
+                     const int* Z, float* l0A);
+int launch_axpy(rlvd_engine* e, cudaStream_t s, int64_t n, const float* x, float* y, const int* gate, int gate_value);   // y += x
 int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, int max_struct_nodes, const int* node_ptr,
-                       const float* x, const float* mu_in, float* q, float* mu_out);
+                       const float* x, const float* mu_in, float* q, float* mu_out, const int* gate, int gate_value);
 int launch_tc_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* row_ptr, const int* col,
                    const int8_t* shift, const float* pos, const float* cell, const int* node_struct,
                    const float* x, const float* mu_in, float* q, float* mu_out);

@@ -142,7 +142,7 @@ int launch_edge(rlvd_engine* e, cudaStream_t s, const EdgeArgs& a) {
     const int M = a.M;
     if (M <= 0) return 0;
     if (a.sliced == 2)
-        return launch_edge_stream(e, s, a.layer, a.n_struct, a.max_struct_nodes, a.node_ptr, a.x, a.mu_in, a.q, a.mu_out);
+        return launch_edge_stream(e, s, a.layer, a.n_struct, a.max_struct_nodes, a.node_ptr, a.x, a.mu_in, a.q, a.mu_out, a.gate, a.gate_value);
     if (e->use_tensor_cores)
         return launch_tc_edge(e, s, a.layer, M, a.row_ptr, a.col, a.shift, a.pos, a.cell, a.node_struct, a.x, a.mu_in, a.q,
                               a.mu_out);

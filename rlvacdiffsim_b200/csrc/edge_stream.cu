@@ -205,15 +205,17 @@ __device__ __forceinline__ void write_slot(uint8_t* tile, int r, const uint4* ro
     reinterpret_cast<float*>(m + META_DIR + 256)[r] = dz;
 }
 
-__global__ void __launch_bounds__(256) edge_pack_kernel(int n_struct, const int* __restrict__ node_ptr,
+__global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const int* __restrict__ node_ptr,
                                                         const int* __restrict__ row_ptr, const int* __restrict__ col,
                                                         const int8_t* __restrict__ shift, const float* __restrict__ pos,
                                                         const float* __restrict__ cell, const float* __restrict__ freqs,
                                                         const float* __restrict__ feps, float cutoff,
                                                         int* __restrict__ tile_counter, int tile_capacity,
                                                         uint8_t* __restrict__ tiles, int4* __restrict__ pipe_info,
-                                                        int* __restrict__ err_flag) {
+                                                        int* __restrict__ err_flag, const int* __restrict__ Z,
+                                                        const int* __restrict__ z2s, float* __restrict__ l0A) {
     __shared__ int goff[MAXN + 1];        // exclusive prefix of per-receiver group counts
+    __shared__ float stg[8][32 * L0_STRIDE];   // per-warp species-sorted slot records for the layer-0 sums
     __shared__ int wsum[8];
     __shared__ int bnd[NPIPE + 1];        // receiver range boundaries of the pipelines
     __shared__ int tbeg[NPIPE + 1];       // first tile of each pipeline (absolute)
@@ -289,6 +291,15 @@ __global__ void __launch_bounds__(256) edge_pack_kernel(int n_struct, const int*
     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
 
     // ---- one warp per receiver row, lanes over its slots
+    // layer-0 species sums: this lane's (block t, radial index k) outputs, o = lane + 32 m < 84
+    int l0k[3], l0t[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const int o = min(lane + 32 * m, 4 * NK - 1);
+        l0t[m] = o / NK;
+        l0k[m] = o - l0t[m] * NK;
+    }
+    float* const wst = stg[warp];
     for (int i = warp; i < n; i += 8) {
         int p = 0;
         while (i >= bnd[p + 1]) ++p;
@@ -297,14 +308,36 @@ __global__ void __launch_bounds__(256) edge_pack_kernel(int n_struct, const int*
         const int nslots = max(1, (rdeg + GS - 1) / GS) * GS;
         const int slot0 = (goff[i] - goff[bnd[p]]) * GS;
         const float xi = __ldg(pos + 3 * (int64_t)gi), yi = __ldg(pos + 3 * (int64_t)gi + 1), zi = __ldg(pos + 3 * (int64_t)gi + 2);
-        for (int s = lane; s < nslots; s += 32) {
+        float l0acc[3][3];
+#pragma unroll
+        for (int sp = 0; sp < 3; ++sp)
+#pragma unroll
+            for (int m = 0; m < 3; ++m) l0acc[sp][m] = 0.f;
+        for (int s0 = 0; s0 < nslots; s0 += 32) {
+            const int s = s0 + lane;
+            const bool live = s < rdeg;
+            const int jg = live ? __ldg(col + re0 + s) : 0;
+            // layer-0 sums: slot records are staged sorted by sender species (CSR order within a species)
+            int at = 0, c0 = 0, c1 = 0, c2 = 0;
+            if (l0A != nullptr) {
+                int my_sp = -1;                 // -1 = padding slot
+                if (live) {
+                    my_sp = __ldg(z2s + min(max(__ldg(Z + jg), 0), 99));
+                    if (my_sp < 0) { atomicExch(err_flag + 1, 1); my_sp = 0; }    // not a model species: the gated fallback runs
+                }
+                const unsigned m0 = __ballot_sync(0xffffffffu, my_sp == 0), m1 = __ballot_sync(0xffffffffu, my_sp == 1),
+                               m2 = __ballot_sync(0xffffffffu, my_sp == 2);
+                const unsigned below = (1u << lane) - 1u;
+                c0 = __popc(m0); c1 = __popc(m1); c2 = __popc(m2);
+                at = my_sp == 0 ? __popc(m0 & below) : my_sp == 1 ? c0 + __popc(m1 & below) : c0 + c1 + __popc(m2 & below);
+            }
+            if (s < nslots) {
             const int slot = slot0 + s;
             uint8_t* tile = tiles + (size_t)(tbeg[p] + (slot >> 5)) * TILE_BYTES;
             const int r = slot & 31;
             if ((s & (GS - 1)) == 0) tile[TILE_B + META_FLAG + (r >> 3)] = (uint8_t)(s == 0 && i > bnd[p] ? 1 : 0);   // new receiver starts
-            if (s < rdeg) {
+            if (live) {
                 const int e = re0 + s;
-                const int jg = __ldg(col + e);
                 const float S0 = (float)shift[3 * (int64_t)e], S1 = (float)shift[3 * (int64_t)e + 1], S2 = (float)shift[3 * (int64_t)e + 2];
                 float rx = __ldg(pos + 3 * (int64_t)jg) - xi, ry = __ldg(pos + 3 * (int64_t)jg + 1) - yi,
                       rz = __ldg(pos + 3 * (int64_t)jg + 2) - zi;
@@ -315,6 +348,12 @@ __global__ void __launch_bounds__(256) edge_pack_kernel(int n_struct, const int*
                 const float inv_d = 1.0f / d;
                 float v[NK];
                 edge_embedding(d, f1, feps, cutoff, v);
+                if (l0A != nullptr) {
+                    float* rec = wst + at * L0_STRIDE;
+#pragma unroll
+                    for (int k = 0; k < NK; ++k) rec[k] = v[k];
+                    rec[NK] = rx * inv_d; rec[NK + 1] = ry * inv_d; rec[NK + 2] = rz * inv_d; rec[NK + 3] = 1.0f;
+                }
                 __half hi[NK + 1], lo[NK + 1];
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
@@ -339,6 +378,34 @@ __global__ void __launch_bounds__(256) edge_pack_kernel(int n_struct, const int*
                 for (int kc = 0; kc < 8; ++kc) row8[kc] = z4;
                 write_slot(tile, r, row8, 0, 0.f, 0.f, 0.f);
             }
+            }
+            if (l0A != nullptr) {
+                // species-resolved radial sums of this chunk of <= 32 edges:
+                //   G[sp][k] += v_k,  H_a[sp][k] += v_k dir_a      (DESIGN.md "layer 0 collapses to per-node GEMMs")
+                __syncwarp();
+                int u = 0;
+#pragma unroll
+                for (int sp = 0; sp < 3; ++sp) {
+                    const int uend = sp == 0 ? c0 : sp == 1 ? c0 + c1 : c0 + c1 + c2;
+#pragma unroll 4
+                    for (; u < uend; ++u) {
+                        const float* rec = wst + u * L0_STRIDE;
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) l0acc[sp][m] = fmaf(rec[l0k[m]], rec[NK + l0t[m]], l0acc[sp][m]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (l0A != nullptr) {
+            float* row = l0A + (size_t)gi * L0_COLS;
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+                if (lane + 32 * m < 4 * NK) {
+#pragma unroll
+                    for (int sp = 0; sp < 3; ++sp) row[l0t[m] * 64 + sp * NK + l0k[m]] = l0acc[sp][m];
+                }
+            if (lane < 4) row[lane * 64 + 63] = 0.f;    // pad column of each 64-wide block
         }
     }
     // ---- padding groups that complete each pipeline's last tile (zero filters, harmless receiver)
@@ -668,8 +735,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     int n_max, const int* __restrict__ node_ptr, const uint32_t* __restrict__ Afmt /* [4 slices][4 rotations][128][32] */,
     float kappa, const int4* __restrict__ pipe_info, const uint8_t* __restrict__ tiles, float* __restrict__ scratch,
     const float* __restrict__ x, const float* __restrict__ mu_in, float* __restrict__ q, float* __restrict__ mu_out,
-    long long* dbg) {
+    long long* dbg, const int* __restrict__ gate, int gate_value) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    if (gate != nullptr && *gate != gate_value) return;     // uniform over the grid: layer-0 fallback not needed
     constexpr int NB = Tab<HAS_MU>::NODE_BYTES;
     constexpr int NROLE = HAS_MU ? 3 : 2;           // consuming warps per pipeline (layer 0, mu == 0, has no dmumu term)
     uint8_t* TabS = smem;
@@ -856,25 +924,26 @@ size_t edge_stream_tile_capacity(int n_struct, int n_nodes, int64_t n_edges) {
 }
 
 int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_t n_edges, const int* node_ptr,
-                     const int* row_ptr, const int* col, const int8_t* shift, const float* pos, const float* cell) {
+                     const int* row_ptr, const int* col, const int8_t* shift, const float* pos, const float* cell,
+                     const int* Z, float* l0A) {
     if (n_struct <= 0 || M <= 0) return 0;
     const size_t cap = edge_stream_tile_capacity(n_struct, M, n_edges);
     RLVD_CHECK(cap < (size_t)0x7fffffff, "edge stream: %zu tiles overflow int32; split the batch", cap);
     if (e->tiles.ensure(cap * TILE_BYTES) || e->pipe_info.ensure((size_t)n_struct * NPIPE * sizeof(int4)) ||
-        e->tile_ctr.ensure(8))
+        e->tile_ctr.ensure(16))
         return 1;
-    RLVD_CUDA(cudaMemsetAsync(e->tile_ctr.p, 0, 8, s));
+    RLVD_CUDA(cudaMemsetAsync(e->tile_ctr.p, 0, 16, s));   // tile counter | capacity error | species outside the model's list
     Span sp(e, s, FAM_PACK);
     edge_pack_kernel<<<n_struct, 256, 0, s>>>(n_struct, node_ptr, row_ptr, col, shift, pos, cell, e->w.freqs, e->w.feps,
                                               e->w.cutoff, e->tile_ctr.as<int>(), (int)cap, e->tiles.as<uint8_t>(),
-                                              e->pipe_info.as<int4>(), e->tile_ctr.as<int>() + 1);
+                                              e->pipe_info.as<int4>(), e->tile_ctr.as<int>() + 1, Z, e->w.z2s, l0A);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, int max_struct_nodes, const int* node_ptr,
-                       const float* x, const float* mu_in, float* q, float* mu_out) {
+                       const float* x, const float* mu_in, float* q, float* mu_out, const int* gate, int gate_value) {
     if (n_struct <= 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -897,13 +966,13 @@ int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, 
     if (dbg_buf == nullptr) { cudaMalloc(&dbg_buf, 64 * 4 * 10 * 8); cudaMemset(dbg_buf, 0, 64 * 4 * 10 * 8); }
     dbg = dbg_buf;
 #endif
-    Span sp(e, s, FAM_EDGE);
+    Span sp(e, s, gate != nullptr ? -1 : FAM_EDGE);     // a gated launch is the (normally skipped) layer-0 fallback
     if (mu_in == nullptr)
         edge_stream_kernel<false><<<n_struct * NSLICE, ST_THREADS, smem, s>>>(
-            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, nullptr, q, mu_out, nullptr);
+            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, nullptr, q, mu_out, nullptr, gate, gate_value);
     else
         edge_stream_kernel<true><<<n_struct * NSLICE, ST_THREADS, smem, s>>>(
-            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, mu_in, q, mu_out, dbg);
+            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, mu_in, q, mu_out, dbg, gate, gate_value);
 #ifdef RLVD_TIMELINE
     if (mu_in != nullptr && ++dbg_calls == 20) {
         cudaStreamSynchronize(s);
@@ -921,7 +990,7 @@ int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, 
         }
     }
 #endif
-    sp.end(1);
+    sp.end(gate != nullptr ? 0 : 1);
     RLVD_CUDA(cudaGetLastError());
     return 0;
 }

@@ -39,7 +39,7 @@ void DevBuf::release() {
 }
 
 Span::Span(rlvd_engine* e_, cudaStream_t s_, int family) : e(e_), s(s_), idx(-1) {
-    if (!e->profiling) return;
+    if (!e->profiling || family < 0) return;      // family < 0: launch kept out of the per-family timings
     ProfSpan sp;
     sp.family = family;
     for (cudaEvent_t* ev : {&sp.a, &sp.b}) {
@@ -98,6 +98,71 @@ int upload_fmt(rlvd_engine* e, const std::vector<float>& W, int n_out, int n_in,
     void* d = nullptr;
     if (upload(e, f.data(), f.size(), &d)) return 1;
     *out = d;
+    return 0;
+}
+
+int upload_raw(rlvd_engine* e, const std::vector<float>& W, const float** out);
+
+// Layer 0 of the representation sees q = embedding[Z] and mu = 0, so its per-edge messages
+//   dq_i = sum_j Wq(d_ij) * x_q[Z_j],   dmu_i = sum_j W_R(d_ij) * x_R[Z_j] * dir_ij        (x = context_net(embedding[Z]))
+// depend on the sender only through its species.  With G[i][s][k] = sum_{j in N(i), species s} g_k(d_ij)  (g = phi*fcut, fcut)
+// and H_a likewise weighted by dir_a, they are per-NODE GEMMs  dq = G Mq,  dmu_a = H_a MR  with constant matrices
+//   Mq[(s,k)][c] = x_q[s][c] Wf_q[c][k],   MR[(s,k)][c] = x_R[s][c] Wf_R[c][k]             (k = 20: the filter bias).
+// The sums come out of the edge pack kernel (edge_stream.cu), the GEMMs run on tc_linear; this builds the matrices.
+template <class Store>
+int build_layer0(rlvd_engine* e, Store& hs, Weights& w) {
+    const std::string rep = "reaction_model.representation.";
+    auto get = [&](const std::string& name) -> const std::vector<float>* {
+        auto it = hs.find(name);
+        return it == hs.end() ? nullptr : &it->second.f;
+    };
+    const std::vector<float>*emb = get(rep + "embedding.weight"), *fw = get(rep + "filter_net.weight"), *fb = get(rep + "filter_net.bias");
+    const std::string pi = rep + "interactions.0.interatomic_context_net.layers.";
+    const std::vector<float>*w0 = get(pi + "0.weight"), *b0 = get(pi + "0.bias"), *w3 = get(pi + "3.weight"), *b3 = get(pi + "3.bias");
+    RLVD_CHECK(emb && fw && fb && w0 && b0 && w3 && b3, "layer-0 collapse: missing checkpoint tensors");
+    const int S = e->n_species;
+    std::vector<double> xs((size_t)S * 3 * F);
+    for (int sp = 0; sp < S; ++sp) {
+        const float* q = emb->data() + (size_t)e->species_z[sp] * F;
+        std::vector<double> h(F);
+        for (int o = 0; o < F; ++o) {
+            double a = (*b0)[o];
+            for (int k = 0; k < F; ++k) a += (double)(*w0)[(size_t)o * F + k] * (double)q[k];
+            h[o] = a / (1.0 + std::exp(-a));
+        }
+        for (int o = 0; o < 3 * F; ++o) {
+            double a = (*b3)[o];
+            for (int k = 0; k < F; ++k) a += (double)(*w3)[(size_t)o * F + k] * h[k];
+            xs[(size_t)sp * 3 * F + o] = a;
+        }
+    }
+    // part 0 = q rows [0,F), part 1 = R rows [F,2F) of layer 0's filter and of x
+    auto Mval = [&](int part, int sp, int k, int c) -> float {
+        const int row = part * F + c;
+        const double f = k < NRBF ? (double)(*fw)[(size_t)row * NRBF + k] : (double)(*fb)[row];
+        return (float)(xs[(size_t)sp * 3 * F + row] * f);
+    };
+    const int NKK = NRBF + 1;
+    // nn.Linear layout W[n_out][128]; the A operand is two 64-wide blocks, each (species, k) + one pad column
+    std::vector<float> W1((size_t)2 * F * F, 0.f), W2((size_t)F * F, 0.f), W3((size_t)F * F, 0.f);
+    for (int c = 0; c < F; ++c)
+        for (int sp = 0; sp < S; ++sp)
+            for (int k = 0; k < NKK; ++k) {
+                const int kk = sp * NKK + k;
+                const float mr = Mval(1, sp, k, c), mq = Mval(0, sp, k, c);
+                W1[(size_t)c * F + kk] = mr;               // [Hx|Hy] -> dmu_x from the Hx block
+                W1[(size_t)(F + c) * F + 64 + kk] = mr;    //            dmu_y from the Hy block
+                W2[(size_t)c * F + kk] = mr;               // [Hz|G]  -> dmu_z from the Hz block
+                W3[(size_t)c * F + 64 + kk] = mq;          // [Hz|G]  -> dq    from the G block
+            }
+    if (upload_fmt(e, W1, 2 * F, F, &w.l0_wF[0]) || upload_fmt(e, W2, F, F, &w.l0_wF[1]) || upload_fmt(e, W3, F, F, &w.l0_wF[2]))
+        return 1;
+    std::vector<int32_t> z2s(100, -1);
+    for (int sp = 0; sp < S; ++sp) z2s[e->species_z[sp]] = sp;
+    void* d = nullptr;
+    if (upload(e, z2s.data(), z2s.size() * sizeof(int32_t), &d)) return 1;
+    w.z2s = reinterpret_cast<const int32_t*>(d);
+    w.l0_ready = true;
     return 0;
 }
 
@@ -243,6 +308,7 @@ int rlvd_finalize_weights(rlvd_engine* e) {
             return 1;
         if (need(pm + "intraatomic_context_net.layers.3.bias", 3 * F, &t) || upload_raw(e, *t, &w.intra_b3[l])) return 1;
     }
+    if (e->n_species > 0 && build_layer0(e, hs, w)) return 1;
     const std::string rm = "reaction_model.";
     if (need(rm + "energy_output.layers.0.weight", 64 * F, &t) || upload_T(e, *t, 64, F, &w.en_w0T)) return 1;
     if (need(rm + "energy_output.layers.0.bias", 64, &t) || upload_raw(e, *t, &w.en_b0)) return 1;
@@ -337,10 +403,44 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
     if (e->use_tensor_cores && e->use_sliced_edge && d_node_ptr != nullptr && n_edges > 0) {
         if (edge_stream_supported(max_struct_nodes)) sliced = 2;
     }
-    if (sliced == 2 && launch_edge_pack(e, s, n_struct, M, n_edges, d_node_ptr, d_row_ptr, d_col, d_shift, d_pos, d_cell))
+    const bool l0 = sliced == 2 && e->use_l0_sums && w.l0_ready;
+    if (l0 && e->l0A.ensure((size_t)M * L0_COLS * sizeof(float))) return 1;
+    if (sliced == 2 && launch_edge_pack(e, s, n_struct, M, n_edges, d_node_ptr, d_row_ptr, d_col, d_shift, d_pos, d_cell, d_Z,
+                                        l0 ? e->l0A.as<float>() : nullptr))
         return 1;
     if (launch_embed(e, s, M, d_Z, d_q)) return 1;
     for (int l = 0; l < NLAYER; ++l) {
+        if (l == 0 && l0) {
+            // layer 0: messages from per-node GEMMs over the species-resolved radial sums (build_layer0)
+            //          gated on the pack kernel's species flag: 0 = every sender is a model species -> GEMMs run;
+            //          1 = the stock layer-0 kernels run instead (same results, no host round trip)
+            const int* flag = e->tile_ctr.as<int>() + 2;
+            LinearArgs f0;
+            f0.A = d_q; f0.lda = F; f0.M = M; f0.K = F; f0.N = F; f0.Wt = w.inter_w0T[0]; f0.Wfmt = w.inter_w0F[0]; f0.bias = w.inter_b0[0];
+            f0.act = 1; f0.W2fmt = w.inter_w3F[0]; f0.bias2 = w.inter_b3[0]; f0.N2 = 3 * F; f0.act2 = 0; f0.Y = x; f0.ldy = 3 * F;
+            f0.gate = flag; f0.gate_value = 1;
+            if (launch_linear(e, s, f0)) return 1;
+            EdgeArgs fe;
+            fe.layer = 0; fe.M = M; fe.sliced = sliced; fe.n_struct = n_struct; fe.max_struct_nodes = max_struct_nodes; fe.node_ptr = d_node_ptr;
+            fe.row_ptr = d_row_ptr; fe.col = d_col; fe.shift = d_shift; fe.pos = d_pos; fe.cell = d_cell;
+            fe.node_struct = d_node_struct; fe.x = x; fe.mu_in = nullptr; fe.q = d_q; fe.mu_out = mu_nxt;
+            fe.gate = flag; fe.gate_value = 1;
+            if (launch_edge(e, s, fe)) return 1;
+            const float* A = e->l0A.as<float>();
+            LinearArgs g1;
+            g1.gate = flag;
+            g1.A = A; g1.lda = L0_COLS; g1.M = M; g1.K = F; g1.N = 2 * F; g1.Wfmt = w.l0_wF[0]; g1.Y = mu_nxt; g1.ldy = 3 * F;
+            if (launch_linear(e, s, g1)) return 1;
+            LinearArgs g2;
+            g2.gate = flag;
+            g2.A = A + F; g2.lda = L0_COLS; g2.M = M; g2.K = F; g2.N = F; g2.Wfmt = w.l0_wF[1]; g2.Y = mu_nxt + 2 * F; g2.ldy = 3 * F;
+            if (launch_linear(e, s, g2)) return 1;
+            LinearArgs g3;
+            g3.gate = flag;
+            g3.A = A + F; g3.lda = L0_COLS; g3.M = M; g3.K = F; g3.N = F; g3.Wfmt = w.l0_wF[2]; g3.Y = hid; g3.ldy = F;
+            if (launch_linear(e, s, g3)) return 1;
+            if (launch_axpy(e, s, (int64_t)M * F, hid, d_q, flag, 0)) return 1;
+        } else {
         // R5 node part: x = Lin3(SiLU(Lin0(q)))   (one launch: the hidden tile stays on the SM)
         LinearArgs a0;
         a0.A = d_q; a0.lda = F; a0.M = M; a0.K = F; a0.N = F; a0.Wt = w.inter_w0T[l]; a0.Wfmt = w.inter_w0F[l]; a0.bias = w.inter_b0[l];
@@ -362,6 +462,7 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
         ea.row_ptr = d_row_ptr; ea.col = d_col; ea.shift = d_shift; ea.pos = d_pos; ea.cell = d_cell;
         ea.node_struct = d_node_struct; ea.x = x; ea.mu_in = l == 0 ? nullptr : mu_cur; ea.q = d_q; ea.mu_out = mu_nxt;
         if (launch_edge(e, s, ea)) return 1;
+        }
         float* tmp = mu_cur; mu_cur = mu_nxt; mu_nxt = tmp;
         // R6: mixing
         LinearArgs am;
@@ -531,8 +632,25 @@ int rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, in
     return 0;
 }
 
+int rlvd_set_species(rlvd_engine* e, const int32_t* atomic_numbers, int32_t n) {
+    RLVD_CHECK(e != nullptr && n >= 0 && (n == 0 || atomic_numbers != nullptr), "rlvd_set_species: bad argument");
+    RLVD_CHECK(!e->finalized, "rlvd_set_species: call before rlvd_finalize_weights");
+    e->n_species = 0;
+    if (n == 0 || n > 3) return 0;                    // the layer-0 collapse packs 3 species x 21 radial terms into K = 64
+    for (int i = 0; i < n; ++i) {
+        RLVD_CHECK(atomic_numbers[i] >= 0 && atomic_numbers[i] < 100, "rlvd_set_species: atomic number %d out of range", atomic_numbers[i]);
+        e->species_z[i] = atomic_numbers[i];
+    }
+    e->n_species = n;
+    return 0;
+}
+
 int rlvd_set_option(rlvd_engine* e, const char* name, int32_t value) {
     RLVD_CHECK(e != nullptr && name != nullptr, "bad argument");
+    if (strcmp(name, "layer0_sums") == 0) {
+        e->use_l0_sums = value != 0;
+        return 0;
+    }
     if (strcmp(name, "tensor_cores") == 0) {
         e->use_tensor_cores = value != 0;
         return 0;

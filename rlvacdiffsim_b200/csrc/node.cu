@@ -141,6 +141,18 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const LinearArgs a)
     }
 }
 
+// y += x: adds the layer-0 message sum (a per-node GEMM output, engine.cu) to q.
+__global__ void axpy_kernel(int64_t n4, const float4* __restrict__ x, float4* __restrict__ y, const int* __restrict__ gate,
+                            int gate_value) {
+    if (gate != nullptr && *gate != gate_value) return;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n4) return;
+    const float4 a = __ldg(x + t);
+    float4 b = y[t];
+    b.x += a.x; b.y += a.y; b.z += a.z; b.w += a.w;
+    y[t] = b;
+}
+
 __global__ void embed_kernel(int M, const int* __restrict__ Z, const float* __restrict__ emb, float* __restrict__ q) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread
     if (idx >= (int64_t)M * (F / 4)) return;
@@ -195,6 +207,7 @@ __global__ void mix_update_kernel(int M, const float* __restrict__ ctx, const fl
 
 int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a) {
     if (e->use_tensor_cores && a.Wfmt != nullptr && tc_linear_supported(a)) return launch_tc_linear(e, s, a, a.Wfmt);
+    RLVD_CHECK(a.gate == nullptr, "linear: gated launches exist on the tcgen05 path only");
     RLVD_CHECK(a.mixred == 0, "linear: the mix-reduce form exists on the tcgen05 path only (M=%d n_nodes=%d)", a.M, a.n_nodes);
     RLVD_CHECK(a.W2fmt == nullptr, "linear: the fused two-layer form exists on the tcgen05 path only (shape M=%d K=%d N=%d N2=%d)",
                a.M, a.K, a.N, a.N2);
@@ -235,6 +248,16 @@ int launch_mix_reduce(rlvd_engine* e, cudaStream_t s, int M, const float* mix, f
     Span sp(e, s, FAM_NODE);
     const int64_t n = (int64_t)M * (F / 4);
     mix_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(M, mix, nrm, vw, 1e-8f);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_axpy(rlvd_engine* e, cudaStream_t s, int64_t n, const float* x, float* y, const int* gate, int gate_value) {
+    if (n <= 0) return 0;
+    Span sp(e, s, FAM_NODE);
+    axpy_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(n / 4, reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y),
+                                                                gate, gate_value);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;

@@ -120,6 +120,7 @@ __device__ __forceinline__ void stage_A_async(const LinearArgs& a, int tile, int
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearArgs a, const uint8_t* __restrict__ Wfmt,
                                                                   const uint8_t* __restrict__ W2fmt) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    if (a.gate != nullptr && *a.gate != a.gate_value) return;   // uniform over the grid
     uint8_t* A_hi = smem;                              // 32 KB  [16 core columns][16 row groups][8 rows][16 B]
     uint8_t* A_lo = smem + 32768;                      // 32 KB
     uint8_t* Ast = smem + 65536;                       // 64 KB  fp32 staging of the next A phase (swizzled rows)

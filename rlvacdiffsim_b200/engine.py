@@ -81,8 +81,13 @@ class Engine:
             else:
                 a = np.ascontiguousarray(t.to(torch.int32).numpy().reshape(-1))
                 check(self.lib.rlvd_set_weight(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.size, 1))
-        check(self.lib.rlvd_finalize_weights(self._h))
         rm = hyper_parameters["reaction_model"]
+        species = rm.get("species")
+        if species:
+            from .structures import SYMBOL_TO_Z
+            zs = np.asarray([SYMBOL_TO_Z[s] if isinstance(s, str) else int(s) for s in species], dtype=np.int32)
+            check(self.lib.rlvd_set_species(self._h, zs.ctypes.data_as(C.c_void_p), int(zs.size)))
+        check(self.lib.rlvd_finalize_weights(self._h))
         self.cutoff = float(rm["cutoff"])
         self.means = {k: float(v) for k, v in rm["means"].items()}
         self.stddevs = {k: float(v) for k, v in rm["stddevs"].items()}

@@ -103,7 +103,8 @@ def test_representation_matches_fp64_oracle(engine):
     ptr_d = torch.from_numpy(ptr).cuda()
     # the edge-stage implementations: edge stream (tcgen05 fp16-split, default), general gather (tcgen05 tf32x3),
     # fp32 SIMT; and the optional node-side forms (mix-reduce epilogue, unfused context nets)
-    for opts in ({"tensor_cores": 1, "sliced_edge": 1}, {"tensor_cores": 1, "sliced_edge": 0}, {"tensor_cores": 0},
+    for opts in ({"tensor_cores": 1, "sliced_edge": 1}, {"tensor_cores": 1, "sliced_edge": 1, "layer0_sums": 0},
+                 {"tensor_cores": 1, "sliced_edge": 0}, {"tensor_cores": 0},
                  {"tensor_cores": 1, "sliced_edge": 1, "fuse_mix": 1, "fuse_mlp": 0}):
         for k, v in opts.items():
             engine.set_option(k, v)
@@ -116,6 +117,38 @@ def test_representation_matches_fp64_oracle(engine):
     engine.set_option("sliced_edge", 1)
     engine.set_option("fuse_mix", 0)
     engine.set_option("fuse_mlp", 1)
+    engine.set_option("layer0_sums", 1)
+
+
+def test_layer0_sums_fall_back_for_foreign_species(engine):
+    """The layer-0 collapse (species-resolved radial sums + per-node GEMMs) only knows the model's species; a batch
+    holding any other atomic number must take the per-edge kernels on the device and give the same numbers as the
+    stock path.  Also checks collapse == per-edge path to fp32 noise on a model-species batch."""
+    g = load_gold("demo")
+    pos = g["positions"].astype(np.float32)
+    n = len(pos)
+    cells = g["cell"][None].astype(np.float32)
+    ptr = np.array([0, n], dtype=np.int32)
+    row_ptr, col, shift, node_struct = _device_graph(engine, pos, cells, ptr)
+    ptr_d = torch.from_numpy(ptr).cuda()
+    numbers = g["numbers"].astype(np.int32)
+    foreign = numbers.copy()
+    foreign[5] = 29                                  # Cu: has an embedding row, is not one of Cr/Co/Ni
+    out = {}
+    for tag, Zh in (("model", numbers), ("foreign", foreign)):
+        for l0 in (1, 0):
+            engine.set_option("layer0_sums", l0)
+            q, mu = engine.representation(torch.from_numpy(Zh).cuda(), torch.from_numpy(pos).cuda(), torch.from_numpy(cells).cuda(),
+                                          node_struct, row_ptr, col, shift, 1, return_mu=True, node_ptr=ptr_d, max_struct_nodes=n)
+            out[tag, l0] = (q.cpu().numpy(), mu.cpu().numpy())
+    engine.set_option("layer0_sums", 1)
+    for k in (0, 1):                                 # gated fallback ran the very same kernels: bitwise equal
+        assert np.array_equal(out["foreign", 1][k], out["foreign", 0][k])
+    assert not np.array_equal(out["foreign", 0][0], out["model", 0][0])
+    for k in (0, 1):
+        ref = out["model", 0][k]
+        assert np.abs(out["model", 1][k] - ref).max() / np.abs(ref).max() < TOL
+    assert not np.array_equal(out["model", 1][0], out["model", 0][0])     # the collapse really is a different evaluation order
 
 
 def _score_batch(model, g, tag, dedup=False):
