@@ -35,6 +35,18 @@ def cell_geometry(cells: np.ndarray, cutoff: float):
     Same definitions as ``oracle.painn_oracle.inverse_cell_f32`` / ``image_range``: the two sides must
     receive identical matrices for the edge sets to be bit-identical."""
     cells64 = np.asarray(cells, dtype=np.float64).reshape(-1, 3, 3)
+    if len(cells64) > 8:
+        # consecutive structures usually share a cell (a replica's reactant and its candidate products): solve each
+        # run once — the batched LAPACK inverse is the largest host cost of an end-to-end scoring call otherwise
+        first = np.concatenate([[True], np.any(cells64[1:] != cells64[:-1], axis=(1, 2))])
+        if int(first.sum()) * 2 <= len(cells64):
+            inv_u, img_u = _cell_geometry_dense(cells64[first], cutoff)
+            run = np.cumsum(first) - 1
+            return inv_u[run], img_u[run]
+    return _cell_geometry_dense(cells64, cutoff)
+
+
+def _cell_geometry_dense(cells64: np.ndarray, cutoff: float):
     inv = np.linalg.inv(cells64).astype(np.float32)
     vol = np.abs(np.linalg.det(cells64))
     cross = np.stack([np.cross(cells64[:, 1], cells64[:, 2]), np.cross(cells64[:, 2], cells64[:, 0]),
