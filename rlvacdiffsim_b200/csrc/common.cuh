@@ -13,7 +13,6 @@ namespace rlvd {
 constexpr int F = RLVD_F;          // 128 hidden channels
 constexpr int NRBF = RLVD_NRBF;    // 20 Bessel functions
 constexpr int L0_COLS = 256;       // layer-0 species sums per node: 4 blocks [Hx|Hy|Hz|G] of 64 = 3 species x 21 + pad
-constexpr int L0_STRIDE = 25;      // slot record of the pack kernel's layer-0 staging: v[21], dir[3], 1
 constexpr int NLAYER = RLVD_NLAYER;
 constexpr int GEOM = 24;           // per-edge geometry record of the fp32 SIMT kernel: 20 x phi*fcut, fcut, dir.xyz
 

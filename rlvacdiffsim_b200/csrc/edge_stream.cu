@@ -155,6 +155,9 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 __device__ __forceinline__ float sum2(f32x2 v) {
     float lo, hi;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
@@ -215,7 +218,11 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
                                                         int* __restrict__ err_flag, const int* __restrict__ Z,
                                                         const int* __restrict__ z2s, float* __restrict__ l0A) {
     __shared__ int goff[MAXN + 1];        // exclusive prefix of per-receiver group counts
-    __shared__ float stg[8][32 * L0_STRIDE];   // per-warp species-sorted slot records for the layer-0 sums
+    // per-warp species-sorted slot records for the layer-0 sums: v[32][21] and (dir_x, dir_y, dir_z, 1)[32]
+    __shared__ __align__(16) float stg_v[8][32 * NK];
+    __shared__ __align__(16) float4 stg_d[8][32];
+    __shared__ float spos[3 * MAXN];      // the structure's positions and species: senders are gathered from here
+    __shared__ int8_t ssp[MAXN];
     __shared__ int wsum[8];
     __shared__ int bnd[NPIPE + 1];        // receiver range boundaries of the pipelines
     __shared__ int tbeg[NPIPE + 1];       // first tile of each pipeline (absolute)
@@ -225,7 +232,16 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
         if (tid < NPIPE) pipe_info[g * NPIPE + tid] = make_int4(0, 0, 0, 0);
         return;
     }
-    // ---- group counts and their block-wide exclusive scan
+    for (int t = tid; t < 3 * n; t += 256) spos[t] = __ldg(pos + 3 * (int64_t)node0 + t);
+    if (tid < n) {
+        int sp = 0;
+        if (l0A != nullptr) {
+            sp = __ldg(z2s + min(max(__ldg(Z + node0 + tid), 0), 99));
+            if (sp < 0) { atomicExch(err_flag + 1, 1); sp = 0; }    // not a model species: the gated fallback runs
+        }
+        ssp[tid] = (int8_t)sp;
+    }
+    // ---- group counts and their block-wide exclusive scan (its barriers also publish spos / ssp)
     int e0 = 0, deg = 0;
     if (tid < n) {
         e0 = __ldg(row_ptr + node0 + tid);
@@ -291,15 +307,10 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
 
     // ---- one warp per receiver row, lanes over its slots
-    // layer-0 species sums: this lane's (block t, radial index k) outputs, o = lane + 32 m < 84
-    int l0k[3], l0t[3];
-#pragma unroll
-    for (int m = 0; m < 3; ++m) {
-        const int o = min(lane + 32 * m, 4 * NK - 1);
-        l0t[m] = o / NK;
-        l0k[m] = o - l0t[m] * NK;
-    }
-    float* const wst = stg[warp];
+    // layer-0 species sums: lane k < 21 owns radial term k of all four blocks (H_x, H_y | H_z, G as two f32x2 pairs)
+    const int l0k = min(lane, NK - 1);
+    float* const wst = stg_v[warp];
+    float4* const wsd = stg_d[warp];
     for (int i = warp; i < n; i += 8) {
         int p = 0;
         while (i >= bnd[p + 1]) ++p;
@@ -307,12 +318,10 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
         const int re0 = __ldg(row_ptr + gi), rdeg = __ldg(row_ptr + gi + 1) - re0;
         const int nslots = max(1, (rdeg + GS - 1) / GS) * GS;
         const int slot0 = (goff[i] - goff[bnd[p]]) * GS;
-        const float xi = __ldg(pos + 3 * (int64_t)gi), yi = __ldg(pos + 3 * (int64_t)gi + 1), zi = __ldg(pos + 3 * (int64_t)gi + 2);
-        float l0acc[3][3];
+        const float xi = spos[3 * i], yi = spos[3 * i + 1], zi = spos[3 * i + 2];
+        f32x2 l0xy[3], l0zg[3];
 #pragma unroll
-        for (int sp = 0; sp < 3; ++sp)
-#pragma unroll
-            for (int m = 0; m < 3; ++m) l0acc[sp][m] = 0.f;
+        for (int sp = 0; sp < 3; ++sp) l0xy[sp] = l0zg[sp] = pk2(0.f, 0.f);
         for (int s0 = 0; s0 < nslots; s0 += 32) {
             const int s = s0 + lane;
             const bool live = s < rdeg;
@@ -320,11 +329,7 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
             // layer-0 sums: slot records are staged sorted by sender species (CSR order within a species)
             int at = 0, c0 = 0, c1 = 0, c2 = 0;
             if (l0A != nullptr) {
-                int my_sp = -1;                 // -1 = padding slot
-                if (live) {
-                    my_sp = __ldg(z2s + min(max(__ldg(Z + jg), 0), 99));
-                    if (my_sp < 0) { atomicExch(err_flag + 1, 1); my_sp = 0; }    // not a model species: the gated fallback runs
-                }
+                const int my_sp = live ? (int)ssp[jg - node0] : -1;     // -1 = padding slot
                 const unsigned m0 = __ballot_sync(0xffffffffu, my_sp == 0), m1 = __ballot_sync(0xffffffffu, my_sp == 1),
                                m2 = __ballot_sync(0xffffffffu, my_sp == 2);
                 const unsigned below = (1u << lane) - 1u;
@@ -339,8 +344,8 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
             if (live) {
                 const int e = re0 + s;
                 const float S0 = (float)shift[3 * (int64_t)e], S1 = (float)shift[3 * (int64_t)e + 1], S2 = (float)shift[3 * (int64_t)e + 2];
-                float rx = __ldg(pos + 3 * (int64_t)jg) - xi, ry = __ldg(pos + 3 * (int64_t)jg + 1) - yi,
-                      rz = __ldg(pos + 3 * (int64_t)jg + 2) - zi;
+                const int jl = jg - node0;
+                float rx = spos[3 * jl] - xi, ry = spos[3 * jl + 1] - yi, rz = spos[3 * jl + 2] - zi;
                 rx += S0 * C[0] + S1 * C[3] + S2 * C[6];
                 ry += S0 * C[1] + S1 * C[4] + S2 * C[7];
                 rz += S0 * C[2] + S1 * C[5] + S2 * C[8];
@@ -349,10 +354,10 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
                 float v[NK];
                 edge_embedding(d, f1, feps, cutoff, v);
                 if (l0A != nullptr) {
-                    float* rec = wst + at * L0_STRIDE;
+                    float* rec = wst + at * NK;
 #pragma unroll
                     for (int k = 0; k < NK; ++k) rec[k] = v[k];
-                    rec[NK] = rx * inv_d; rec[NK + 1] = ry * inv_d; rec[NK + 2] = rz * inv_d; rec[NK + 3] = 1.0f;
+                    wsd[at] = make_float4(rx * inv_d, ry * inv_d, rz * inv_d, 1.0f);
                 }
                 __half hi[NK + 1], lo[NK + 1];
 #pragma unroll
@@ -389,9 +394,11 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
                     const int uend = sp == 0 ? c0 : sp == 1 ? c0 + c1 : c0 + c1 + c2;
 #pragma unroll 4
                     for (; u < uend; ++u) {
-                        const float* rec = wst + u * L0_STRIDE;
-#pragma unroll
-                        for (int m = 0; m < 3; ++m) l0acc[sp][m] = fmaf(rec[l0k[m]], rec[NK + l0t[m]], l0acc[sp][m]);
+                        const float vk = wst[u * NK + l0k];
+                        const ulonglong2 d4 = *reinterpret_cast<const ulonglong2*>(wsd + u);   // (dx, dy) | (dz, 1)
+                        const f32x2 vv = pk2(vk, vk);
+                        l0xy[sp] = fma2(vv, d4.x, l0xy[sp]);
+                        l0zg[sp] = fma2(vv, d4.y, l0zg[sp]);
                     }
                 }
                 __syncwarp();
@@ -399,13 +406,20 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
         }
         if (l0A != nullptr) {
             float* row = l0A + (size_t)gi * L0_COLS;
+            if (lane < NK) {
 #pragma unroll
-            for (int m = 0; m < 3; ++m)
-                if (lane + 32 * m < 4 * NK) {
-#pragma unroll
-                    for (int sp = 0; sp < 3; ++sp) row[l0t[m] * 64 + sp * NK + l0k[m]] = l0acc[sp][m];
+                for (int sp = 0; sp < 3; ++sp) {
+                    float hx, hy, hz, gg;
+                    unpk2(l0xy[sp], hx, hy);
+                    unpk2(l0zg[sp], hz, gg);
+                    row[sp * NK + lane] = hx;
+                    row[64 + sp * NK + lane] = hy;
+                    row[128 + sp * NK + lane] = hz;
+                    row[192 + sp * NK + lane] = gg;
                 }
-            if (lane < 4) row[lane * 64 + 63] = 0.f;    // pad column of each 64-wide block
+            } else if (lane < NK + 4) {
+                row[(lane - NK) * 64 + 63] = 0.f;       // pad column of each 64-wide block
+            }
         }
     }
     // ---- padding groups that complete each pipeline's last tile (zero filters, harmless receiver)
