@@ -98,18 +98,27 @@ struct StBars {
     uint32_t tmem_base;
 };
 
-__device__ __noinline__ void st_timeout() {
-    printf("rlvd: edge_stream mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-    __trap();
-}
 // Waits use try_wait WITH a suspend-time hint (TRYWAIT + NANOSLEEP.SYNCS: the warp sleeps in hardware until the phase
 // completes).  The hint-less form spins; in this kernel a third of all issued instructions were such spins (ncu,
 // profiles/ncu_stream_r01d.txt) taken from the warps that had work.
 __device__ __forceinline__ void st_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-#pragma unroll 1
-    while (!mbar_try_wait(bar, parity))
-        if (++spins > 400000u) st_timeout();
+    // The whole loop is PTX: 7 SASS instructions per wake-up instead of the compiler's 11 (NANOSLEEP.SYNCS wakes on every
+    // mbarrier event of the CTA, so waiting warps issue a third of the kernel's instructions).  Measured: neither this nor
+    // dropping the bounded-wait counter changes the kernel time — the spins only take issue slots nobody else wanted.
+    // The counter stays: a protocol bug must trap, never hang the GPU.
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 n;\n\t"
+        "mov.b32 n, 0;\n"
+        "ST_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra ST_WAIT_DONE;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.gt.u32 q, n, 4000000;\n\t"
+        "@q trap;\n\t"
+        "bra ST_WAIT_LOOP;\n"
+        "ST_WAIT_DONE:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
 }
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(
