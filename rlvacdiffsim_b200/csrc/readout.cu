@@ -25,7 +25,7 @@ __device__ __forceinline__ float act_fn(float v, int code) {
         case RLVD_ACT_RELU: return v > 0.f ? v : 0.f;
         case RLVD_ACT_TANH: return tanhf(v);
         case RLVD_ACT_LEAKY_RELU: return v > 0.f ? v : 0.01f * v;
-        default: return v / (1.0f + expf(-v));
+        default: return __fdividef(v, 1.0f + __expf(-v));    // same fast SiLU as the tc_linear epilogue
     }
 }
 
@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(RT) readout_kernel(int n_react, const int* __r
     float* sP = sm + TA * QS;       // [TA][QS]
     float* red = sP + TA * QS;      // [TA][8] partial sums / scratch
     float* eo = red + TA * 8;       // [2][TA] energy-head outputs (R, P)
-    float* hpart = eo + 2 * TA;     // [8][32] per-group partial pooled features
-    float* pool = hpart + 8 * 32;   // [32] h, then E_R, E_P, dE
+    float* hpart = eo + 2 * TA;     // [TA][32] per-atom reaction features of the tile
+    float* pool = hpart + TA * 32;  // [32] h, then E_R, E_P, dE
     float* zbuf = pool + 36;        // [64] head scratch
 
     const int g = blockIdx.x;
@@ -82,40 +82,45 @@ __global__ void __launch_bounds__(RT) readout_kernel(int n_react, const int* __r
         }
         __syncthreads();
 
-        // ---- H1: energy head on R and P.  thread: hidden unit nh = tid%64, atom group ag = tid/64 (4), atoms ag+4r
+        // ---- H1: energy head on R and P.  Register tile 4 hidden units x (2 atoms x 2 sides): thread = (hidden group
+        //      hg = tid%16, atom group ag = tid/16), atoms ag and ag+16.  Per 4 k: 4 LDG.128 of weights + 4 LDS.128 of
+        //      activations feed 64 FMAs (the 1 x 8 tile this replaces was bound by the load/store pipe, not the FMA pipe).
         {
-            const int nh = tid & 63, ag = tid >> 6;
-            const float b0 = __ldg(w.en_b0 + nh), w3 = __ldg(w.en_w3 + nh);
+            const int hg = tid & 15, ag = tid >> 4;
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(w.en_b0) + hg);
+            const float4 w3 = __ldg(reinterpret_cast<const float4*>(w.en_w3) + hg);
+            float4 acc[4];      // [side * 2 + atom half]
 #pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                const float* S = side == 0 ? sR : sP;
-                float acc[8];
+            for (int r = 0; r < 4; ++r) acc[r] = b0;
+            const float* rows[4] = {sR + ag * QS, sR + (ag + 16) * QS, sP + ag * QS, sP + (ag + 16) * QS};
+#pragma unroll 2      // lets the next block's weight loads (L2 latency: the weights do not stay in L1) issue above this block's FMAs
+            for (int k = 0; k < F; k += 4) {
+                float4 wk[4];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) acc[r] = b0;
-                for (int k = 0; k < F; k += 4) {
-                    const float w0 = __ldg(w.en_w0T + (k + 0) * 64 + nh), w1 = __ldg(w.en_w0T + (k + 1) * 64 + nh),
-                                w2 = __ldg(w.en_w0T + (k + 2) * 64 + nh), w3k = __ldg(w.en_w0T + (k + 3) * 64 + nh);
+                for (int i = 0; i < 4; ++i) wk[i] = __ldg(reinterpret_cast<const float4*>(w.en_w0T + (k + i) * 64) + hg);
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const float4 av = *reinterpret_cast<const float4*>(S + (ag + 4 * r) * QS + k);
-                        acc[r] = fmaf(av.x, w0, acc[r]);
-                        acc[r] = fmaf(av.y, w1, acc[r]);
-                        acc[r] = fmaf(av.z, w2, acc[r]);
-                        acc[r] = fmaf(av.w, w3k, acc[r]);
+                for (int r = 0; r < 4; ++r) {
+                    const float4 av = *reinterpret_cast<const float4*>(rows[r] + k);
+                    const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[r].x = fmaf(a4[i], wk[i].x, acc[r].x);
+                        acc[r].y = fmaf(a4[i], wk[i].y, acc[r].y);
+                        acc[r].z = fmaf(a4[i], wk[i].z, acc[r].z);
+                        acc[r].w = fmaf(a4[i], wk[i].w, acc[r].w);
                     }
                 }
-                // second layer: dot over the 64 hidden units = 2 warps per atom group
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    float v = act_fn(acc[r], qp.painn_head_act) * w3;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (lane == 0) red[(ag + 4 * r) * 8 + (wid & 1)] = v;
-                }
-                __syncthreads();
-                if (tid < TA) eo[side * TA + tid] = red[tid * 8] + red[tid * 8 + 1] + __ldg(w.en_b3);
-                __syncthreads();
             }
+            // second layer: dot over the 64 hidden units = the 16 lanes of one atom group (fixed shuffle tree)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float v = act_fn(acc[r].x, qp.painn_head_act) * w3.x + act_fn(acc[r].y, qp.painn_head_act) * w3.y +
+                          act_fn(acc[r].z, qp.painn_head_act) * w3.z + act_fn(acc[r].w, qp.painn_head_act) * w3.w;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (hg == 0) eo[(r >> 1) * TA + ag + 16 * (r & 1)] = v + __ldg(w.en_b3);
+            }
+            __syncthreads();
         }
         // ---- pooled energies (thread 0, atom order)
         if (tid == 0) {
@@ -135,60 +140,63 @@ __global__ void __launch_bounds__(RT) readout_kernel(int n_react, const int* __r
             sP[a * QS + cc] -= sR[a * QS + cc];
         }
         __syncthreads();
-        // ---- H2 layer 0: Hd = act(D·Wr0T + b0) → sR.  thread: n = tid%128, ag = tid/128 (2), atoms ag+2r
+        // ---- H2 layer 0: Hd = act(D·Wr0T + b0) → sR.  Register tile 4 hidden units x 4 atoms: hg = tid%32, ag = tid/32,
+        //      atoms ag + 8r
         {
-            const int nh = tid & 127, ag = tid >> 7;
-            float acc[16];
-            const float b0 = __ldg(w.rr_b0 + nh);
+            const int hg = tid & 31, ag = tid >> 5;
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(w.rr_b0) + hg);
+            float4 acc[4];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) acc[r] = b0;
+            for (int r = 0; r < 4; ++r) acc[r] = b0;
+#pragma unroll 2
             for (int k = 0; k < F; k += 4) {
-                const float w0 = __ldg(w.rr_w0T + (k + 0) * F + nh), w1 = __ldg(w.rr_w0T + (k + 1) * F + nh),
-                            w2 = __ldg(w.rr_w0T + (k + 2) * F + nh), w3k = __ldg(w.rr_w0T + (k + 3) * F + nh);
+                float4 wk[4];
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const float4 av = *reinterpret_cast<const float4*>(sP + (ag + 2 * r) * QS + k);
-                    acc[r] = fmaf(av.x, w0, acc[r]);
-                    acc[r] = fmaf(av.y, w1, acc[r]);
-                    acc[r] = fmaf(av.z, w2, acc[r]);
-                    acc[r] = fmaf(av.w, w3k, acc[r]);
-                }
-            }
-            __syncthreads();  // everyone finished reading sR (energy head) long ago; sP reads done
-#pragma unroll
-            for (int r = 0; r < 16; ++r) sR[(ag + 2 * r) * QS + nh] = act_fn(acc[r], qp.painn_head_act);
-        }
-        __syncthreads();
-        // ---- H2 layer 3 + sum pool: thread: n = tid%32, ag = tid/32 (8), atoms ag+8r
-        {
-            const int no = tid & 31, ag = tid >> 5;
-            float acc[4];
-            const float b3 = __ldg(w.rr_b3 + no);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r] = b3;
-            for (int k = 0; k < F; k += 4) {
-                const float w0 = __ldg(w.rr_w3T + (k + 0) * 32 + no), w1 = __ldg(w.rr_w3T + (k + 1) * 32 + no),
-                            w2 = __ldg(w.rr_w3T + (k + 2) * 32 + no), w3k = __ldg(w.rr_w3T + (k + 3) * 32 + no);
+                for (int i = 0; i < 4; ++i) wk[i] = __ldg(reinterpret_cast<const float4*>(w.rr_w0T + (k + i) * F) + hg);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const float4 av = *reinterpret_cast<const float4*>(sR + (ag + 8 * r) * QS + k);
-                    acc[r] = fmaf(av.x, w0, acc[r]);
-                    acc[r] = fmaf(av.y, w1, acc[r]);
-                    acc[r] = fmaf(av.z, w2, acc[r]);
-                    acc[r] = fmaf(av.w, w3k, acc[r]);
+                    const float4 av = *reinterpret_cast<const float4*>(sP + (ag + 8 * r) * QS + k);
+                    const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[r].x = fmaf(a4[i], wk[i].x, acc[r].x);
+                        acc[r].y = fmaf(a4[i], wk[i].y, acc[r].y);
+                        acc[r].z = fmaf(a4[i], wk[i].z, acc[r].z);
+                        acc[r].w = fmaf(a4[i], wk[i].w, acc[r].w);
+                    }
                 }
             }
-            float part = 0.f;
+            // sR is free: its last readers (the energy head) are two barriers back
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-                if (ag + 8 * r < na) part += acc[r];
-            hpart[ag * 32 + no] = part;
+                *reinterpret_cast<float4*>(sR + (ag + 8 * r) * QS + 4 * hg) =
+                    make_float4(act_fn(acc[r].x, qp.painn_head_act), act_fn(acc[r].y, qp.painn_head_act),
+                                act_fn(acc[r].z, qp.painn_head_act), act_fn(acc[r].w, qp.painn_head_act));
+        }
+        __syncthreads();
+        // ---- H2 layer 3 + sum pool: 4 outputs x 1 atom per thread: og = tid%8, atom a = tid/8
+        {
+            const int og = tid & 7, a = tid >> 3;
+            float4 acc = __ldg(reinterpret_cast<const float4*>(w.rr_b3) + og);
+            for (int k = 0; k < F; k += 4) {
+                const float4 av = *reinterpret_cast<const float4*>(sR + a * QS + k);
+                const float a4[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 wk = __ldg(reinterpret_cast<const float4*>(w.rr_w3T + (k + i) * 32) + og);
+                    acc.x = fmaf(a4[i], wk.x, acc.x);
+                    acc.y = fmaf(a4[i], wk.y, acc.y);
+                    acc.z = fmaf(a4[i], wk.z, acc.z);
+                    acc.w = fmaf(a4[i], wk.w, acc.w);
+                }
+            }
+            if (a >= na) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(hpart + a * 32 + 4 * og) = acc;
         }
         __syncthreads();
         if (tid < 32) {
             float h = pool[tid];
-#pragma unroll
-            for (int ag = 0; ag < 8; ++ag) h += hpart[ag * 32 + tid];
+            for (int a = 0; a < TA; ++a) h += hpart[a * 32 + tid];     // atom order
             pool[tid] = h;
         }
         __syncthreads();
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(RT) readout_kernel(int n_react, const int* __r
     }
 }
 
-size_t readout_smem() { return (size_t)(2 * TA * QS + TA * 8 + 2 * TA + 8 * 32 + 36 + 128) * sizeof(float); }
+size_t readout_smem() { return (size_t)(2 * TA * QS + TA * 8 + 2 * TA + TA * 32 + 36 + 128) * sizeof(float); }
 
 }  // namespace
 
