@@ -163,3 +163,35 @@ def test_sro_host_mirror_properties():
     counts = np.array([[0.0, 48.0], [48.0, 0.0]])
     o = _sro_from_counts(counts, np.array([4.0, 4.0]))
     assert o[0, 0] == 1.0 and o[1, 1] == 1.0 and o[0, 1] == pytest.approx(-1.0)
+
+
+def test_trajectory_writer_matches_per_step_appends(tmp_path):
+    """Buffered, batched XDATCAR / JSON writers produce byte-for-byte what the reference-shaped per-step
+    appends do (simulator.py:175,215), across flush boundaries."""
+    import json
+
+    from rlvacdiffsim_b200.trajectory import TrajectoryWriter
+    rng = np.random.default_rng(3)
+    reps = [make_crconi_supercell(2, seed=s) for s in range(3)]
+    numbers = np.stack([r.get_atomic_numbers() for r in reps])
+    cells = np.stack([r.get_cell() for r in reps])
+    w = TrajectoryWriter(str(tmp_path / "buf"), numbers, cells, flush_every=4)
+    T = 10
+    qs, acts = [], []
+    for t in range(T):
+        for r in reps:
+            r.set_positions(r.get_positions() + rng.normal(0, 0.05, r.get_positions().shape))
+        pos = np.stack([r.get_positions() for r in reps])
+        q = [rng.normal(size=rng.integers(3, 9)) for _ in reps]
+        a = [int(rng.integers(0, len(x))) for x in q]
+        qs.append(q)
+        acts.append(a)
+        w.append(pos, q_values=q, chosen=a)
+        for i, r in enumerate(reps):
+            append_xdatcar(str(tmp_path / f"ref{i}"), r, t, append=t > 0)
+    w.close()
+    for i in range(3):
+        assert open(w.xdatcar_path(i)).read() == open(tmp_path / f"ref{i}").read()
+    ql = json.load(open(tmp_path / "buf" / "q_values.json"))
+    assert len(ql) == 3 and len(ql[0]) == T and ql[1][4] == qs[4][1].tolist()
+    assert json.load(open(tmp_path / "buf" / "actions.json"))[2] == [acts[t][2] for t in range(T)]
