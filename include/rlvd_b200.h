@@ -128,10 +128,12 @@ int  rlvd_expand_candidates(rlvd_engine* e, void* stream, int32_t n_rep, int32_t
                             int32_t* d_react_struct, int32_t* d_prod_struct, int32_t* d_owner);
 /* simulator.py:94-98 for every replica: p = softmax(Q / (T * 8.617e-5)) in fp32, np.random.choice's inverse-cdf draw
  * with the caller's uniforms d_uniform[n_rep], argmax, and (apply != 0) pos[atom] += disp of the chosen hop in place
- * (environment.step's position update).  d_probs[n_rep, max_actions] may be NULL. */
+ * (environment.step's position update).  d_probs[n_rep, max_actions] may be NULL.  d_gamma[n_rep] (may be NULL) receives
+ * the TKS total rate sum(exp(Q / kT)) of simulator.py:262 (fp32, as torch.sum(torch.exp(Q / kT))). */
 int  rlvd_select_apply(rlvd_engine* e, void* stream, int32_t n_rep, const int32_t* d_rep_ptr, const int32_t* d_first,
                        const float* d_rl_q, const float* d_temperature, const double* d_uniform, const double* d_actions,
-                       int32_t max_actions, int32_t apply, double* d_pos, int32_t* d_chosen, int32_t* d_argmax, float* d_probs);
+                       int32_t max_actions, int32_t apply, double* d_pos, int32_t* d_chosen, int32_t* d_argmax, float* d_probs,
+                       float* d_gamma);
 
 /* ---- Warren-Cowley pair counts (rlsim/utils/sro.py:49-83 `get_sro_from_atoms`, used per candidate by the sro_pixel
  *      filter at rlsim/drl/simulator.py:60-92) ------------------------------------------------------------------ */

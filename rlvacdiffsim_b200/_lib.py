@@ -52,7 +52,7 @@ SYMBOLS = {
     "rlvd_candidate_offsets": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
     "rlvd_expand_candidates": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32,
                                          _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "rlvd_select_apply": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "rlvd_select_apply": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "rlvd_sro_counts": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, _P]),
     "rlvd_time_readout": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, C.POINTER(TimeHead), _P]),
     "rlvd_linear": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int32, _P]),

@@ -252,12 +252,18 @@ __global__ void __launch_bounds__(128) select_apply_kernel(int n_rep, const int*
                                                            const float* __restrict__ rl_q, const float* __restrict__ temperature,
                                                            const double* __restrict__ u, const double* __restrict__ actions,
                                                            int max_actions, int apply, double* __restrict__ pos,
-                                                           int* __restrict__ chosen, int* __restrict__ argmax_out, float* __restrict__ probs) {
+                                                           int* __restrict__ chosen, int* __restrict__ argmax_out, float* __restrict__ probs,
+                                                           float* __restrict__ gamma) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rep) return;
     const int g0 = first[r], nc = first[r + 1] - g0;
-    if (nc <= 0) { chosen[r] = -1; argmax_out[r] = -1; return; }
+    if (nc <= 0) { chosen[r] = -1; argmax_out[r] = -1; if (gamma != nullptr) gamma[r] = 0.f; return; }
     const float kT = temperature[r] * 8.617e-5f;
+    if (gamma != nullptr) {                       // TKS total rate: sum(exp(Q / kT)), simulator.py:262
+        float gsum = 0.f;
+        for (int c = 0; c < nc; ++c) gsum += expf(rl_q[g0 + c] / kT);
+        gamma[r] = gsum;
+    }
     float m = -3.4e38f;
     int am = 0;
     for (int c = 0; c < nc; ++c) {
@@ -313,11 +319,11 @@ int launch_expand_candidates(rlvd_engine* e, cudaStream_t s, int n_rep, int n_ca
 
 int launch_select_apply(rlvd_engine* e, cudaStream_t s, int n_rep, const int* rep_ptr, const int* first, const float* rl_q,
                         const float* temperature, const double* u, const double* actions, int max_actions, int apply, double* pos,
-                        int* chosen, int* argmax_out, float* probs) {
+                        int* chosen, int* argmax_out, float* probs, float* gamma) {
     if (n_rep <= 0) return 0;
     Span sp(e, s, FAM_READOUT);
     select_apply_kernel<<<(n_rep + 127) / 128, 128, 0, s>>>(n_rep, rep_ptr, first, rl_q, temperature, u, actions, max_actions, apply,
-                                                           pos, chosen, argmax_out, probs);
+                                                           pos, chosen, argmax_out, probs, gamma);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;

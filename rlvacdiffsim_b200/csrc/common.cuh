@@ -242,7 +242,7 @@ int launch_expand_candidates(rlvd_engine* e, cudaStream_t s, int n_rep, int n_ca
                              int* node_ptr, int* Zo, float* poso, float* cello, float* invo, int* imgo, int* rs, int* ps, int* owner);
 int launch_select_apply(rlvd_engine* e, cudaStream_t s, int n_rep, const int* rep_ptr, const int* first, const float* rl_q,
                         const float* temperature, const double* u, const double* actions, int max_actions, int apply, double* pos,
-                        int* chosen, int* argmax_out, float* probs);
+                        int* chosen, int* argmax_out, float* probs, float* gamma);
 
 int launch_sro_counts(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const double* pos, const double* cell,
                       const int* sid, int n_species, long long* counts, int* status);

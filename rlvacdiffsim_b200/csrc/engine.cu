@@ -540,12 +540,13 @@ int rlvd_expand_candidates(rlvd_engine* e, void* stream, int32_t n_rep, int32_t 
 
 int rlvd_select_apply(rlvd_engine* e, void* stream, int32_t n_rep, const int32_t* d_rep_ptr, const int32_t* d_first,
                       const float* d_rl_q, const float* d_temperature, const double* d_uniform, const double* d_actions,
-                      int32_t max_actions, int32_t apply, double* d_pos, int32_t* d_chosen, int32_t* d_argmax, float* d_probs) {
+                      int32_t max_actions, int32_t apply, double* d_pos, int32_t* d_chosen, int32_t* d_argmax, float* d_probs,
+                      float* d_gamma) {
     RLVD_CHECK(e != nullptr && n_rep > 0 && d_first && d_rl_q && d_temperature && d_uniform && d_chosen && d_argmax,
                "rlvd_select_apply: bad argument");
     RLVD_CUDA(cudaSetDevice(e->device));
     return launch_select_apply(e, (cudaStream_t)stream, n_rep, d_rep_ptr, d_first, d_rl_q, d_temperature, d_uniform, d_actions,
-                               max_actions, apply, d_pos, d_chosen, d_argmax, d_probs);
+                               max_actions, apply, d_pos, d_chosen, d_argmax, d_probs, d_gamma);
 }
 
 int rlvd_sro_counts(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const double* d_pos,

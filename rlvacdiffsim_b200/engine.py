@@ -222,16 +222,18 @@ class Engine:
         return o
 
     def select_apply(self, rep_ptr, first, rl_q, temperature, uniform, actions, pos, apply: bool = True):
-        """→ (chosen i32[R], argmax i32[R], probs f32[R, max_actions]); ``pos`` (fp64) is updated in place when ``apply``."""
+        """→ (chosen i32[R], argmax i32[R], probs f32[R, max_actions], gamma f32[R]); ``pos`` (fp64) is updated in place
+        when ``apply``; gamma = sum(exp(Q / kT)) is the TKS total rate (simulator.py:262)."""
         R = rep_ptr.numel() - 1
         chosen = torch.empty(R, dtype=torch.int32, device=self.device)
         amax = torch.empty(R, dtype=torch.int32, device=self.device)
         probs = torch.zeros((R, actions.shape[1]), dtype=torch.float32, device=self.device)
+        gamma = torch.empty(R, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             check(self.lib.rlvd_select_apply(self._h, self._stream(), R, _ptr(rep_ptr), _ptr(first), _ptr(rl_q),
                                              _ptr(temperature), _ptr(uniform), _ptr(actions), actions.shape[1], int(apply),
-                                             _ptr(pos), _ptr(chosen), _ptr(amax), _ptr(probs)))
-        return chosen, amax, probs
+                                             _ptr(pos), _ptr(chosen), _ptr(amax), _ptr(probs), _ptr(gamma)))
+        return chosen, amax, probs, gamma
 
     # ------------------------------------------------------------------ Warren-Cowley pair counts
     def sro_counts(self, pos: torch.Tensor, cells: torch.Tensor, node_ptr: torch.Tensor, species_index: torch.Tensor,

@@ -307,7 +307,45 @@ class DeviceLSS:
                                max_struct_nodes=self.n_atoms)
         u = np.random.random_sample(self.R) if uniforms is None else np.asarray(uniforms, dtype=np.float64)
         T = torch.full((self.R,), float(temperature), dtype=torch.float32, device=dev)
-        chosen, amax, probs = eng.select_apply(self.rep_ptr, first, out["rl_q"], T, torch.from_numpy(u).to(dev), actions,
-                                               self.pos, apply)
+        chosen, amax, probs, gamma = eng.select_apply(self.rep_ptr, first, out["rl_q"], T, torch.from_numpy(u).to(dev),
+                                                      actions, self.pos, apply)
         return {"chosen": chosen, "argmax": amax, "probs": probs, "rl_q": out["rl_q"], "first": first, "actions": actions,
-                "count": count}
+                "count": count, "gamma": gamma}
+
+    def run(self, horizon: int, temperature: float, mode: str = "lss", writer=None,
+            uniforms: Optional[np.ndarray] = None) -> Dict[str, list]:
+        """``horizon`` steps of every replica: the loop of ``RLSimulator.run_LSS`` / ``run_TKS``
+        (``rlsim/drl/simulator.py:187-236, 239-283``) without relaxation or energy logging.  ``mode="tks"`` also keeps
+        the residence-time clock ``t += 1e-6 / sum(exp(Q / kT))`` (simulator.py:262-265) and the tracked atom's
+        coordinates (the LAST atom, simulator.py:241,271).  ``writer``: a ``TrajectoryWriter`` fed once per step.
+        ``uniforms[horizon, R]`` pins the draws.  Returns per-replica lists shaped like the reference's outputs."""
+        if mode not in ("lss", "tks"):
+            raise ValueError("DeviceLSS.run supports mode 'lss' and 'tks'")
+        R = self.R
+        q_lists = [[] for _ in range(R)]
+        act_lists = [[] for _ in range(R)]
+        t_lists = [[0.0] for _ in range(R)]
+        c_lists = [[self.positions()[r, -1].tolist()] for r in range(R)] if mode == "tks" else None
+        for t in range(horizon):
+            out = self.step(temperature, None if uniforms is None else uniforms[t])
+            first = out["first"].cpu().numpy()
+            q = out["rl_q"].cpu().numpy()
+            chosen = out["chosen"].cpu().numpy()
+            gamma = out["gamma"].cpu().numpy()
+            pos = None
+            if writer is not None or mode == "tks":
+                pos = self.positions()
+            for r in range(R):
+                q_lists[r].append(q[first[r]:first[r + 1]].tolist())
+                act_lists[r].append(int(chosen[r]))
+                if mode == "tks":
+                    t_lists[r].append(t_lists[r][-1] + 1.0 / float(gamma[r]) * 10 ** -6)
+                    c_lists[r].append(pos[r, -1].tolist())
+            if writer is not None:
+                writer.append(pos, q_values=[q[first[r]:first[r + 1]] for r in range(R)], chosen=chosen,
+                              times=[t_lists[r][-1] for r in range(R)] if mode == "tks" else None)
+        res = {"Q": q_lists, "actions": act_lists}
+        if mode == "tks":
+            res["time"] = t_lists
+            res["coords"] = c_lists
+        return res

@@ -445,6 +445,40 @@ def test_device_lss_steps_match_host_loop(model):
         np.testing.assert_array_equal(lss.positions(), np.stack([h.positions for h in host]))   # fp64 state: bit-identical
 
 
+def test_device_tks_run_clock_and_writer(model, tmp_path):
+    """DeviceLSS.run(mode="tks"): residence-time clock t += 1e-6 / sum(exp(Q/kT)) (simulator.py:262-265), tracked
+    coordinates of the last atom, and the buffered writer, against the host loop on the same draws."""
+    from rlvacdiffsim_b200.simulator import DeviceLSS
+    from rlvacdiffsim_b200.structures import append_xdatcar, apply_action
+    from rlvacdiffsim_b200.trajectory import TrajectoryWriter
+    qp = {"alpha": 1.0, "beta": 0.0, "dqn": False}          # TKS rates: Q = -barrier + kT * log-frequency (deploy "tks")
+    host = [make_crconi_supercell(4, seed=50 + s, jitter=0.02) for s in range(3)]
+    lss = DeviceLSS(model, host, 0, 3.528, 1, qp)
+    w = TrajectoryWriter(str(tmp_path / "traj"), np.stack([h.get_atomic_numbers() for h in host]),
+                         np.stack([h.get_cell() for h in host]), flush_every=2)
+    T, H = 900.0, 3
+    u = np.random.RandomState(9).random_sample((H, 3))
+    res = lss.run(H, T, mode="tks", writer=w, uniforms=u)
+    w.close()
+    scorer = ReplicaScorer(model, 0)
+    kT = T * 8.617 * 10 ** -5
+    clock = [[0.0] for _ in host]
+    for t in range(H):
+        spaces = [rb.get_action_space(h, 3.528) for h in host]
+        q_host = scorer.score(host, spaces, dict(qp, temperature=T))
+        for r in range(3):
+            assert np.array_equal(np.asarray(res["Q"][r][t], dtype=np.float32), q_host[r])
+            pick = res["actions"][r][t]
+            gamma = float(torch.sum(torch.exp(torch.from_numpy(q_host[r]) / kT)))
+            clock[r].append(clock[r][-1] + 1 / gamma * 10 ** -6)
+            host[r] = apply_action(host[r], spaces[r][pick])
+            append_xdatcar(str(tmp_path / f"ref{r}"), host[r], t, append=t > 0)
+            assert res["coords"][r][t + 1] == host[r].positions[-1].tolist()
+    np.testing.assert_allclose(np.asarray(res["time"]), np.asarray(clock), rtol=1e-5)
+    for r in range(3):
+        assert open(w.xdatcar_path(r)).read() == open(tmp_path / f"ref{r}").read()
+
+
 # ----------------------------------------------------------------------------- SRO (Warren-Cowley) pair counts
 
 def test_sro_device_matches_host_mirror(model, engine):
