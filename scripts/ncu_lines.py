@@ -5,6 +5,7 @@ import collections, csv, io, os, re, subprocess, sys, tempfile
 
 rep, stem, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+nth = int(sys.argv[5]) if len(sys.argv) > 5 else 0          # which matching launch of the report
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "rlvacdiffsim_b200", "librlvd_b200.so")], cwd=tmp, capture_output=True)
@@ -13,7 +14,7 @@ rows = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "
 raw = list(csv.reader(io.StringIO(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)))
 names = [r[raw[0].index("Kernel Name")] for r in raw[2:]]
 his = [i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r]
-which = [i for i, n in enumerate(names) if kern in n][0]
+which = [i for i, n in enumerate(names) if kern in n][nth]
 h = rows[his[which]]
 ix = {n: i for i, n in enumerate(h)}
 end = his[which + 1] if which + 1 < len(his) else len(rows)
@@ -43,6 +44,9 @@ for r in data:
     agg[ln][0] += int(r[ix["# Samples"]])
     agg[ln][1] += int(r[ix["Instructions Executed"]])
 ts, ti = sum(v[0] for v in agg.values()) or 1, sum(v[1] for v in agg.values()) or 1
+stalls = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
+sagg = {st: sum(int(r[ix[st]]) for r in data) for st in stalls}
+print("stalls: " + "  ".join(f"{k[6:]} {v / ts:.3f}" for k, v in sorted(sagg.items(), key=lambda kv: -kv[1])[:8]))
 srcs = {}
 print(f"# {names[which][:100]}: {len(data)} SASS instructions ({len(best)} in the line table), {ti} warp instructions, {ts} samples")
 for ln, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
