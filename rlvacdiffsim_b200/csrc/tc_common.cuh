@@ -73,6 +73,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         : "r"(taddr)
         : "memory");
 }
+// .16x256b.x4: 16 TMEM lanes x 32 columns.  Thread t receives, for column group g = 0..3 and row half rh = 0..1,
+//   v[4g + 2rh + b] = D[lane_base + 8 rh + t/4][col_base + 8g + 2(t%4) + b]          (scripts/probes/tmem_ld_shapes.cu)
+// i.e. the m16n8 accumulator fragment: four threads hold 32 contiguous bytes of a row, so a warp-wide 8-byte store
+// writes whole 32-byte sectors straight from registers.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)

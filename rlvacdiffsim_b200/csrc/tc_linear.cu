@@ -308,42 +308,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                 tc_fence_after();
 #pragma unroll 1
                 for (int sgm = 0; sgm < 2; ++sgm) {
-                    const int c0 = 64 * sgm + 32 * h;        // first column (inside the N-block) of this thread
-                    const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + c0;
-                    uint32_t d0[32], d1[32];
-                    tmem_ld32(t0, d0);
-                    tmem_ld32(t0 + 128, d1);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (sgm == 1) {                          // all TMEM reads of this accumulator are done
-                        tc_fence_before();
-                        mbar_arrive(&S->acc_empty[buf]);
-                    }
+                    const int c0 = 64 * sgm + 32 * h;        // first column (inside the N-block) of this warp's segment
                     const int col0 = nb * TC_N + c0;
+                    const int u = lane & 3, rq = lane >> 2;
+                    float2 bb[4];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float y[4];
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_o + col0 + j);
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                    for (int g = 0; g < 4; ++g) bb[g] = *reinterpret_cast<const float2*>(bias_o + col0 + 8 * g + 2 * u);
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            float v = fmaf(__uint_as_float(d1[j + u]), 1.0f / 2048.0f, __uint_as_float(d0[j + u])) + bb[u];
-                            if (act_o == 1) v = __fdividef(v, 1.0f + __expf(-v));   // SiLU; |error| < 2e-7 of max(|v|, 1)
-                            y[u] = v;
+                    for (int hl = 0; hl < 2; ++hl) {         // the two 16-lane halves of this warp's TMEM quarter
+                        const uint32_t t0 = tmem + ((uint32_t)(q * 32 + 16 * hl) << 16) + buf * 256 + c0;
+                        uint32_t d0[16], d1[16];
+                        tmem_ld_16x256b_x4(t0, d0);
+                        tmem_ld_16x256b_x4(t0 + 128, d1);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (sgm == 1 && hl == 1) {           // all TMEM reads of this accumulator are done
+                            tc_fence_before();
+                            mbar_arrive(&S->acc_empty[buf]);
                         }
-                        // warp-private staging tile [32 rows][32 cols] (4 KB, 16-byte chunks swizzled by row): no CTA barrier
-                        *reinterpret_cast<float4*>(Yw + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = make_float4(y[0], y[1], y[2], y[3]);
-                    }
-                    __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {            // 4 rows x 128 contiguous bytes per store instruction
-                        const int row = i * 4 + (lane >> 3), lc = lane & 7;
-                        const int64_t m = (int64_t)tile * TC_M + q * 32 + row;
-                        if (m < a.M) {
-                            const float4 v = *reinterpret_cast<const float4*>(Yw + row * 128 + ((lc ^ (row & 7)) << 4));
-                            *reinterpret_cast<float4*>(a.Y + m * a.ldy + col0 + lc * 4) = v;
+                        for (int rh = 0; rh < 2; ++rh) {
+                            const int64_t m = (int64_t)tile * TC_M + q * 32 + 16 * hl + 8 * rh + rq;
+                            float* yrow = a.Y + m * a.ldy + col0 + 2 * u;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                float v0 = fmaf(__uint_as_float(d1[4 * g + 2 * rh]), 1.0f / 2048.0f, __uint_as_float(d0[4 * g + 2 * rh])) + bb[g].x;
+                                float v1 = fmaf(__uint_as_float(d1[4 * g + 2 * rh + 1]), 1.0f / 2048.0f, __uint_as_float(d0[4 * g + 2 * rh + 1])) + bb[g].y;
+                                if (act_o == 1) {            // SiLU; |error| < 2e-7 of max(|v|, 1)
+                                    v0 = __fdividef(v0, 1.0f + __expf(-v0));
+                                    v1 = __fdividef(v1, 1.0f + __expf(-v1));
+                                }
+                                // the four threads of a row write 32 contiguous bytes: one full sector per row, no staging
+                                if (m < a.M) *reinterpret_cast<float2*>(yrow + 8 * g) = make_float2(v0, v1);
+                            }
                         }
                     }
-                    __syncwarp();
                 }
             }
         }
