@@ -135,6 +135,27 @@ int  rlvd_select_apply(rlvd_engine* e, void* stream, int32_t n_rep, const int32_
                        int32_t max_actions, int32_t apply, double* d_pos, int32_t* d_chosen, int32_t* d_argmax, float* d_probs,
                        float* d_gamma);
 
+/* ---- replay-minibatch update of the DQN heads (rlsim/drl/trainer.py:163-177 with train_all = False, trainer.py:36-39) ---
+ * rlvd_reaction_readout_ex = rlvd_reaction_readout that also writes d_head_in[n_react, 36]: what the trainable heads see
+ * per reaction graph (33 Q_emb inputs, the 2 extra Q_output inputs, the alpha/beta part of rl_q).  Needs q_params.dqn. */
+int  rlvd_reaction_readout_ex(rlvd_engine* e, void* stream, int32_t n_react, int32_t n_nodes, const int32_t* d_node_ptr,
+                              const int32_t* d_react_struct, const int32_t* d_prod_struct, const int32_t* d_Z,
+                              const float* d_q, const rlvd_q_params* qp, const float* d_temperature, float* d_rl_q,
+                              float* d_q0, float* d_q1, float* d_delta_e, float* d_E_R, float* d_E_P, float* d_head_in);
+/* q_pred = heads(head_in); loss = mean((target - q_pred)^2); backward; clip_grad_norm_(max_norm); Adam step (torch.optim.Adam
+ * defaults) on the engine's Q_emb / Q_output weights IN PLACE.  d_exp_avg / d_exp_avg_sq: Adam state [2513] (zero before
+ * step 1), packed Q_emb.layers.{0,3}.{weight,bias}, Q_output.layers.{0,3,6}.{weight,bias}; step is 1-based.
+ * d_dropout_uniform[n_graphs, 80] (may be NULL = no dropout) drives the heads' train-mode dropout (keep if u >= p).
+ * apply = 0 only evaluates (loss, predictions, clipped gradient).  Outputs d_loss[1], d_pred[n_graphs], d_grad_norm[1],
+ * d_grad[2513] may be NULL.  Bitwise reproducible. */
+int  rlvd_q_head_train_step(rlvd_engine* e, void* stream, int32_t n_graphs, const float* d_head_in, const float* d_target,
+                            const float* d_dropout_uniform, float dropout_p, int32_t head_act, float lr, float beta1,
+                            float beta2, float eps, float max_norm, int32_t step, int32_t apply, float* d_exp_avg,
+                            float* d_exp_avg_sq, float* d_loss, float* d_pred, float* d_grad_norm, float* d_grad);
+/* Copies the current device value of a trainable tensor (checkpoint name, Q_emb.* / Q_output.*) to the host:
+ * policy_value_net.state_dict() after an update (trainer.py:120, train.py:102-104). */
+int  rlvd_get_weight(rlvd_engine* e, const char* name, float* h_out, int64_t numel);
+
 /* ---- Warren-Cowley pair counts (rlsim/utils/sro.py:49-83 `get_sro_from_atoms`, used per candidate by the sro_pixel
  *      filter at rlsim/drl/simulator.py:60-92) ------------------------------------------------------------------ */
 /* d_species_index[M] in [0, n_species) (index into the sorted species list); d_counts[n_struct, n_species, n_species]

@@ -54,6 +54,10 @@ SYMBOLS = {
                                          _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rlvd_select_apply": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "rlvd_sro_counts": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, _P]),
+    "rlvd_reaction_readout_ex": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.POINTER(QParams), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rlvd_q_head_train_step": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float,
+                                          C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "rlvd_get_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     "rlvd_time_readout": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, C.POINTER(TimeHead), _P]),
     "rlvd_linear": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int32, _P]),
     "rlvd_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),

@@ -12,6 +12,8 @@ namespace rlvd {
 
 constexpr int F = RLVD_F;          // 128 hidden channels
 constexpr int NRBF = RLVD_NRBF;    // 20 Bessel functions
+constexpr int RLVD_HEAD_IN = 36;   // DQN-head inputs per reaction graph: z[33], extras[2], base (readout.cu -> train.cu)
+constexpr int RLVD_QHEAD_PARAMS = 2513;   // Q_emb [16,33]+16, [16,16]+16; Q_output [32,18]+32, [32,32]+32, [1,32]+1
 constexpr int L0_COLS = 256;       // layer-0 species sums per node: 4 blocks [Hx|Hy|Hz|G] of 64 = 3 species x 21 + pad
 constexpr int NLAYER = RLVD_NLAYER;
 constexpr int GEOM = 24;           // per-edge geometry record of the fp32 SIMT kernel: 20 x phi*fcut, fcut, dir.xyz
@@ -216,6 +218,10 @@ void edge_stream_format(const float* W, const float* b, std::vector<uint8_t>& ou
 int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_t n_edges, const int* node_ptr,
                      const int* row_ptr, const int* col, const int8_t* shift, const float* pos, const float* cell,
                      const int* Z, float* l0A);
+int launch_q_head_train(rlvd_engine* e, cudaStream_t s, int n_graphs, const float* head_in, const float* target,
+                        const float* drop_u, float p_drop, int act, float lr, float beta1, float beta2, float eps,
+                        float max_norm, int step, int apply, float* m, float* v, float* loss, float* pred, float* gnorm,
+                        float* grad_out);
 int launch_axpy(rlvd_engine* e, cudaStream_t s, int64_t n, const float* x, float* y, const int* gate, int gate_value);   // y += x
 int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, int max_struct_nodes, const int* node_ptr,
                        const float* x, const float* mu_in, float* q, float* mu_out, const int* gate, int gate_value);
@@ -228,7 +234,7 @@ int launch_mix_update(rlvd_engine* e, cudaStream_t s, int M, const float* ctx, c
                       const float* vw, float* q, float* mu);
 int launch_readout(rlvd_engine* e, cudaStream_t s, int n_react, const int* node_ptr, const int* rs,
                    const int* ps, const int* Z, const float* q, const rlvd_q_params& qp, const float* d_temp,
-                   float* rl_q, float* q0, float* q1, float* delta_e, float* E_R, float* E_P);
+                   float* rl_q, float* q0, float* q1, float* delta_e, float* E_R, float* E_P, float* head_in = nullptr);
 
 int launch_time_readout(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const float* q, const float* T,
                         const float* defect, const rlvd_time_head& h, float* time_out);

@@ -510,6 +510,53 @@ int rlvd_reaction_readout(rlvd_engine* e, void* stream, int32_t n_react, int32_t
                           d_temperature, d_rl_q, d_q0, d_q1, d_delta_e, d_E_R, d_E_P);
 }
 
+int rlvd_reaction_readout_ex(rlvd_engine* e, void* stream, int32_t n_react, int32_t n_nodes, const int32_t* d_node_ptr,
+                             const int32_t* d_react_struct, const int32_t* d_prod_struct, const int32_t* d_Z,
+                             const float* d_q, const rlvd_q_params* qp, const float* d_temperature, float* d_rl_q,
+                             float* d_q0, float* d_q1, float* d_delta_e, float* d_E_R, float* d_E_P, float* d_head_in) {
+    (void)n_nodes;
+    RLVD_CHECK(e != nullptr && e->finalized, "rlvd_reaction_readout_ex: weights are not finalized");
+    RLVD_CHECK(qp != nullptr, "rlvd_reaction_readout_ex: q_params is NULL");
+    RLVD_CHECK(d_head_in == nullptr || qp->dqn != 0, "rlvd_reaction_readout_ex: the DQN-head inputs exist only with q_params.dqn");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_readout(e, (cudaStream_t)stream, n_react, d_node_ptr, d_react_struct, d_prod_struct, d_Z, d_q, *qp,
+                          d_temperature, d_rl_q, d_q0, d_q1, d_delta_e, d_E_R, d_E_P, d_head_in);
+}
+
+int rlvd_q_head_train_step(rlvd_engine* e, void* stream, int32_t n_graphs, const float* d_head_in, const float* d_target,
+                           const float* d_dropout_uniform, float dropout_p, int32_t head_act, float lr, float beta1,
+                           float beta2, float eps, float max_norm, int32_t step, int32_t apply, float* d_exp_avg,
+                           float* d_exp_avg_sq, float* d_loss, float* d_pred, float* d_grad_norm, float* d_grad) {
+    RLVD_CHECK(e != nullptr && e->finalized, "rlvd_q_head_train_step: weights are not finalized");
+    RLVD_CHECK(n_graphs > 0 && d_head_in && d_target, "rlvd_q_head_train_step: bad argument");
+    RLVD_CHECK(!apply || (d_exp_avg && d_exp_avg_sq && step >= 1), "rlvd_q_head_train_step: Adam state / step missing");
+    RLVD_CHECK(dropout_p >= 0.f && dropout_p < 1.f, "rlvd_q_head_train_step: dropout_p out of range");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_q_head_train(e, (cudaStream_t)stream, n_graphs, d_head_in, d_target, d_dropout_uniform, dropout_p, head_act,
+                               lr, beta1, beta2, eps, max_norm, step, apply, d_exp_avg, d_exp_avg_sq, d_loss, d_pred,
+                               d_grad_norm, d_grad);
+}
+
+int rlvd_get_weight(rlvd_engine* e, const char* name, float* h_out, int64_t numel) {
+    RLVD_CHECK(e != nullptr && e->finalized && name && h_out, "rlvd_get_weight: bad argument");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    const Weights& w = e->w;
+    struct Ent { const char* name; const float* p; int64_t n; };
+    const Ent tab[] = {
+        {"Q_emb.layers.0.weight", w.qe_w[0], 16 * 33}, {"Q_emb.layers.0.bias", w.qe_b[0], 16},
+        {"Q_emb.layers.3.weight", w.qe_w[1], 16 * 16}, {"Q_emb.layers.3.bias", w.qe_b[1], 16},
+        {"Q_output.layers.0.weight", w.qo_w[0], 32 * 18}, {"Q_output.layers.0.bias", w.qo_b[0], 32},
+        {"Q_output.layers.3.weight", w.qo_w[1], 32 * 32}, {"Q_output.layers.3.bias", w.qo_b[1], 32},
+        {"Q_output.layers.6.weight", w.qo_w[2], 32}, {"Q_output.layers.6.bias", w.qo_b[2], 1}};
+    for (const Ent& t : tab)
+        if (strcmp(name, t.name) == 0) {
+            RLVD_CHECK(numel == t.n, "rlvd_get_weight: '%s' has %lld elements, caller asked for %lld", name, (long long)t.n, (long long)numel);
+            RLVD_CUDA(cudaMemcpy(h_out, t.p, (size_t)t.n * sizeof(float), cudaMemcpyDeviceToHost));
+            return 0;
+        }
+    RLVD_CHECK(false, "rlvd_get_weight: '%s' is not a trainable tensor of this build (Q_emb.* / Q_output.* only)", name);
+}
+
 int rlvd_action_space(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const double* d_pos,
                       const double* d_cell, double lattice_parameter, int32_t max_vacancies, int32_t max_actions,
                       int32_t* d_count, double* d_actions, int32_t* d_status) {

@@ -31,6 +31,7 @@ __device__ __forceinline__ float act_fn(float v, int code) {
 
 struct ReadoutOut {
     float *rl_q, *q0, *q1, *delta_e, *E_R, *E_P;
+    float* head_in;   // [n_react, 36] or null: the DQN heads' inputs (33 pooled features + delta_e, 2 extras, base), train.cu
 };
 
 // y[n] = b[n] + sum_k W[n][k] * z[k]   (W out-major as in the checkpoint); lane = n.
@@ -242,6 +243,11 @@ __global__ void __launch_bounds__(RT) readout_kernel(int n_react, const int* __r
                     t1[16 + u] = qp.q_extra[u] == RLVD_QX_KT_X10 ? kT * 10.0f : dE;
             }
             __syncwarp();
+            if (out.head_in != nullptr) {         // what the trainable DQN heads see (rlvd_q_head_train_step)
+                float* hi = out.head_in + (int64_t)g * RLVD_HEAD_IN;
+                hi[lane] = z[lane];
+                if (lane == 0) { hi[32] = z[32]; hi[33] = t1[16]; hi[34] = t1[17]; hi[35] = rl; }
+            }
             // Q_output 18 → 32 → 32 → 1
             v = act_fn(head_layer(w.qo_w[0], w.qo_b[0], 32, 18, t1, lane), qp.dqn_head_act);
             __syncwarp();
@@ -329,9 +335,9 @@ int launch_time_readout(rlvd_engine* e, cudaStream_t s, int n_struct, const int*
 
 int launch_readout(rlvd_engine* e, cudaStream_t s, int n_react, const int* node_ptr, const int* rs, const int* ps,
                    const int* Z, const float* q, const rlvd_q_params& qp, const float* d_temp, float* rl_q,
-                   float* q0, float* q1, float* delta_e, float* E_R, float* E_P) {
+                   float* q0, float* q1, float* delta_e, float* E_R, float* E_P, float* head_in) {
     if (n_react <= 0) return 0;
-    ReadoutOut out{rl_q, q0, q1, delta_e, E_R, E_P};
+    ReadoutOut out{rl_q, q0, q1, delta_e, E_R, E_P, head_in};
     Span sp(e, s, FAM_READOUT);
     readout_kernel<<<n_react, RT, readout_smem(), s>>>(n_react, node_ptr, rs, ps, Z, q, e->w, qp, d_temp, out);
     sp.end(1);

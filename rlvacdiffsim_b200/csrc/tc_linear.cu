@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
         const int r = t & 127, khalf = t >> 7;               // converter role: row r, core columns khalf*8..+8
         const int q = warp & 3, h = warp >> 2;               // epilogue role: TMEM lane quarter q, column half h
         const int er = q * 32 + lane;                        // epilogue row = TMEM lane
-        uint8_t* Yw = Yst + warp * 4096;                     // this warp's 32 x 32 fp32 output staging tile
+
         const uint32_t ast = smem_u32(Ast);
         const uint32_t row_off = (r >> 3) * CORE_SBO + (r & 7) * 16;
         uint32_t acc_it = 0, ph_it = 0;

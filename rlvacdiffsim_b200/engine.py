@@ -165,17 +165,63 @@ class Engine:
 
     # ------------------------------------------------------------------ K5
     def readout(self, q: torch.Tensor, Z: torch.Tensor, node_ptr: torch.Tensor, react_struct: torch.Tensor,
-                prod_struct: torch.Tensor, qp: QParams, temperature: Optional[torch.Tensor] = None
-                ) -> Dict[str, torch.Tensor]:
+                prod_struct: torch.Tensor, qp: QParams, temperature: Optional[torch.Tensor] = None,
+                head_inputs: bool = False) -> Dict[str, torch.Tensor]:
+        """``head_inputs``: also return ``head_in[G, 36]``, what the trainable DQN heads see (``q_head_train_step``)."""
         G = react_struct.numel()
         out = torch.empty((6, max(G, 1)), dtype=torch.float32, device=self.device)
+        head_in = torch.empty((max(G, 1), 36), dtype=torch.float32, device=self.device) if head_inputs else None
         with torch.cuda.device(self.device):
-            check(self.lib.rlvd_reaction_readout(self._h, self._stream(), G, q.shape[0], _ptr(node_ptr),
-                                                 _ptr(react_struct), _ptr(prod_struct), _ptr(Z), _ptr(q),
-                                                 C.byref(qp), _ptr(temperature), _ptr(out[0]), _ptr(out[1]),
-                                                 _ptr(out[2]), _ptr(out[3]), _ptr(out[4]), _ptr(out[5])))
+            check(self.lib.rlvd_reaction_readout_ex(self._h, self._stream(), G, q.shape[0], _ptr(node_ptr),
+                                                    _ptr(react_struct), _ptr(prod_struct), _ptr(Z), _ptr(q),
+                                                    C.byref(qp), _ptr(temperature), _ptr(out[0]), _ptr(out[1]),
+                                                    _ptr(out[2]), _ptr(out[3]), _ptr(out[4]), _ptr(out[5]), _ptr(head_in)))
         names = ("rl_q", "q0", "q1", "delta_e", "E_R", "E_P")
-        return {k: out[i, :G] for i, k in enumerate(names)}
+        res = {k: out[i, :G] for i, k in enumerate(names)}
+        if head_inputs:
+            res["head_in"] = head_in[:G]
+        return res
+
+    # ------------------------------------------------------------------ B1: replay-minibatch update of the DQN heads
+    Q_HEAD_TENSORS = (("Q_emb.layers.0.weight", 16 * 33), ("Q_emb.layers.0.bias", 16), ("Q_emb.layers.3.weight", 16 * 16),
+                      ("Q_emb.layers.3.bias", 16), ("Q_output.layers.0.weight", 32 * 18), ("Q_output.layers.0.bias", 32),
+                      ("Q_output.layers.3.weight", 32 * 32), ("Q_output.layers.3.bias", 32),
+                      ("Q_output.layers.6.weight", 32), ("Q_output.layers.6.bias", 1))
+    N_Q_HEAD_PARAMS = sum(n for _, n in Q_HEAD_TENSORS)
+
+    def q_head_train_step(self, head_in: torch.Tensor, target: torch.Tensor, state: Dict[str, torch.Tensor], lr: float,
+                          head_act: int, max_norm: float = 0.8, betas=(0.9, 0.999), eps: float = 1e-8,
+                          dropout_uniform: Optional[torch.Tensor] = None, dropout_p: float = 0.0, apply: bool = True
+                          ) -> Dict[str, torch.Tensor]:
+        """``rlvd_q_head_train_step`` (``trainer.py:166-175`` with the reaction model frozen): forward of the heads, MSE
+        against ``target``, backward, ``clip_grad_norm_(max_norm)``, Adam — in place on the engine's weights.  ``state``
+        holds ``exp_avg`` / ``exp_avg_sq`` (f32[2513]) and the integer ``step``; it is advanced when ``apply``."""
+        G = head_in.shape[0]
+        dev = self.device
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        gnorm = torch.empty(1, dtype=torch.float32, device=dev)
+        pred = torch.empty(G, dtype=torch.float32, device=dev)
+        grad = torch.empty(self.N_Q_HEAD_PARAMS, dtype=torch.float32, device=dev)
+        step = int(state["step"]) + 1
+        with torch.cuda.device(dev):
+            check(self.lib.rlvd_q_head_train_step(
+                self._h, self._stream(), G, _ptr(head_in.contiguous()), _ptr(target.contiguous()), _ptr(dropout_uniform),
+                float(dropout_p), int(head_act), float(lr), float(betas[0]), float(betas[1]), float(eps), float(max_norm),
+                step, int(apply), _ptr(state["exp_avg"]), _ptr(state["exp_avg_sq"]), _ptr(loss), _ptr(pred), _ptr(gnorm),
+                _ptr(grad)))
+        if apply:
+            state["step"] = step
+        return {"loss": loss, "pred": pred, "grad_norm": gnorm, "grad": grad}
+
+    def new_q_head_state(self) -> Dict[str, torch.Tensor]:
+        z = lambda: torch.zeros(self.N_Q_HEAD_PARAMS, dtype=torch.float32, device=self.device)
+        return {"exp_avg": z(), "exp_avg_sq": z(), "step": 0}
+
+    def get_weight(self, name: str, numel: int) -> np.ndarray:
+        out = np.empty(numel, dtype=np.float32)
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_get_weight(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), numel))
+        return out
 
     # ------------------------------------------------------------------ A1: candidate hops on the device
     def action_space(self, pos: torch.Tensor, cells: torch.Tensor, node_ptr: torch.Tensor, lattice_parameter: float,
@@ -259,12 +305,12 @@ class Engine:
 
     # ------------------------------------------------------------------ whole path, device-resident inputs
     def score_device(self, Z, pos, cell, inv_cell, img_range, node_ptr, react_struct, prod_struct, qp: QParams,
-                     temperature=None, max_struct_nodes: int = 0) -> Dict[str, torch.Tensor]:
+                     temperature=None, max_struct_nodes: int = 0, head_inputs: bool = False) -> Dict[str, torch.Tensor]:
         n_struct = node_ptr.numel() - 1
         row_ptr, col, shift, node_struct = self.radius_graph(pos, cell, inv_cell, img_range, node_ptr)
         q = self.representation(Z, pos, cell, node_struct, row_ptr, col, shift, n_struct, node_ptr=node_ptr,
                                 max_struct_nodes=max_struct_nodes)
-        out = self.readout(q, Z, node_ptr, react_struct, prod_struct, qp, temperature)
+        out = self.readout(q, Z, node_ptr, react_struct, prod_struct, qp, temperature, head_inputs=head_inputs)
         out["n_edges"] = col.shape[0]
         return out
 

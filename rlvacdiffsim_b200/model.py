@@ -196,8 +196,51 @@ class DQNv2(nn.Module, _EngineMixin):
     def forward(self, batch, q_params: Dict[str, float | bool]) -> Dict[str, torch.Tensor]:
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
-                "dqn_v2 backward (replay-minibatch training, SURVEY.md §8a row B1) has no sm_100a kernels yet; "
-                "call under torch.no_grad() / .eval() for scoring")
+                "dqn_v2.forward builds no autograd graph.  Replay-minibatch training (SURVEY.md §8a row B1) exists for the "
+                "train_all=False form of rlsim/drl/trainer.py (reaction model frozen): use rlvacdiffsim_b200.trainer.Trainer "
+                "or DQNv2.q_head_update; backward through the PaiNN representation has no sm_100a kernels yet.  Call under "
+                "torch.no_grad() / .eval() for scoring")
+        return self._score(batch, q_params)
+
+    # ---- B1, train_all = False: one minibatch update of Q_emb / Q_output on the device
+    Q_HEAD_PREFIXES = ("Q_emb.", "Q_output.")
+
+    def q_head_update(self, batch, q_params: Dict[str, float | bool], target: torch.Tensor, state: Optional[dict], lr: float,
+                      max_norm: float = 0.8, dropout_uniform: Optional[torch.Tensor] = None, apply: bool = True) -> dict:
+        """``q_pred = self(batch, q_params)["rl_q"]; loss = mean((target - q_pred)**2); loss.backward();
+        clip_grad_norm_(parameters, max_norm); Adam.step()`` of ``trainer.py:166-175`` for a model whose reaction model is
+        frozen (``trainer.py:36-39``).  ``state``: the Adam state from ``new_q_head_state()`` (kept on the batch's device).
+        ``dropout_uniform[G, 80]`` drives the heads' train-mode dropout (p = ``hyper['dropout_rate']``); None = identity.
+        Returns ``{"loss", "pred", "grad_norm", "grad", "state"}``; the module's Q-head parameters are refreshed from the
+        device when ``apply``."""
+        if not q_params.get("dqn", False):
+            raise ValueError("q_head_update needs q_params['dqn'] = True (the DQN heads do not enter rl_q otherwise)")
+        dev = batch["pos"].device
+        eng = self._engine_for(dev)
+        if state is None:
+            state = eng.new_q_head_state()
+        out = self._score(batch, q_params, head_inputs=True)
+        spec = self.head_spec
+        from .engine import ACT_CODES
+        p_drop = float(self.hyper.get("dropout_rate", 0.0)) if dropout_uniform is not None else 0.0
+        res = eng.q_head_train_step(out["head_in"], target.to(dev, torch.float32), state, lr, ACT_CODES[spec.dqn_head_activation],
+                                    max_norm=max_norm, dropout_uniform=dropout_uniform, dropout_p=p_drop, apply=apply)
+        if apply:
+            self._pull_q_heads(eng)
+        res["state"] = state
+        res["frozen_rl_q"] = out["rl_q"]          # eval-mode prediction with the pre-update weights
+        return res
+
+    def _pull_q_heads(self, eng: Engine) -> None:
+        """Copy the updated Q_emb / Q_output tensors from the engine into this module's parameters (state_dict, save)."""
+        sd = dict(self.named_parameters())
+        with torch.no_grad():
+            for name, n in eng.Q_HEAD_TENSORS:
+                p = sd[name]
+                p.copy_(torch.from_numpy(eng.get_weight(name, n)).reshape(p.shape))
+        eng._sig = tuple((p.data_ptr(), p._version) for p in self._engine_tensors())   # the engine already holds these values
+
+    def _score(self, batch, q_params: Dict[str, float | bool], head_inputs: bool = False) -> Dict[str, torch.Tensor]:
         pos = batch["pos"]
         if pos.device.type != "cuda":
             raise RuntimeError("dqn_v2.forward needs the batch on a CUDA device (no CPU fallback); use batch_to")
@@ -245,7 +288,7 @@ class DQNv2(nn.Module, _EngineMixin):
         ps = torch.arange(nR, nR + G, dtype=torch.int32, device=dev)
         qp = eng.q_params(q_params, self.head_spec)
         out = eng.score_device(Z_all.contiguous(), pos_all.contiguous(), cell_all.contiguous(), inv_d, img_d,
-                               node_ptr, rs, ps, qp, max_struct_nodes=int(counts.max()))
+                               node_ptr, rs, ps, qp, max_struct_nodes=int(counts.max()), head_inputs=head_inputs)
         out["barrier"] = -out["q0"]
         out["freq"] = out["q1"]
         return out

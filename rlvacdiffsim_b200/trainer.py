@@ -1,0 +1,194 @@
+"""Host mirror of ``rlsim/drl/trainer.py`` (``Trainer``) and ``rlsim/memory.py`` (``Memory``) for the replay-minibatch
+path, SURVEY.md §8a row B1.
+
+What runs on the device: ``get_max_Q`` (the target network's scoring of every next state, ``trainer.py:102-117`` — the
+same forward as ``RLSimulator.select_action``) and, for ``train_all=False`` (``trainer.py:36-39``: every parameter
+whose name contains ``reaction_model`` is frozen, only ``Q_emb`` / ``Q_output`` learn), the whole minibatch update of
+``dqn_update`` (``trainer.py:163-177``): forward, MSE against ``next_Q * gamma + reward``, backward, ``clip_grad_norm_``
+at 0.8 and the Adam step, in one kernel launch behind ``DQNv2.q_head_update`` (``csrc/train.cu``).
+
+NOT built: ``train_all=True`` (the reference configs' default) needs the backward of the PaiNN representation;
+``context_bandit_update`` (``trainer.py:55-100``) trains ``q0`` / ``q1``, which live entirely inside the frozen reaction
+model.  Both raise ``NotImplementedError`` instead of silently training something else.
+"""
+from __future__ import annotations
+
+import copy
+import json
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .graph import DataLoader, ReactionDataset, batch_to
+from .simulator import convert_to_graph_list
+from .structures import Atoms
+
+
+class Memory:
+    """One episode of experience (``rlsim/memory.py:16-62``): the lists ``Trainer`` reads plus ``add`` / ``save`` /
+    ``load`` in the reference's JSON layout (``memory.py:88-133``)."""
+
+    def __init__(self, alpha: float, beta: float, T: float = 0.0):
+        self.alpha, self.beta, self.T = alpha, beta, T
+        self.states: List[Atoms] = []
+        self.next_states: List[Atoms] = []
+        self.actions: List[int] = []
+        self.act_space: List[list] = []
+        self.action_probs: List[list] = []
+        self.rewards: List[float] = []
+        self.freq: List[float] = []
+        self.E_min: List[float] = []
+        self.barrier: List[float] = []
+        self.E_s: List[float] = []
+        self.E_next: List[float] = []
+        self.fail: List[bool] = []
+        self.fail_panelty = -0.5
+        self.kb = 1.380649 / 1.602 * 10 ** -4
+
+    def add(self, info: dict) -> None:
+        self.states.append(info["state"])
+        self.actions.append(info["act"])
+        self.act_space.append(info["act_space"])
+        self.action_probs.append(info["act_probs"])
+        self.fail.append(info["fail"])
+        self.next_states.append(info["next"])
+        self.freq.append(info["log_freq"])
+        self.E_s.append(info["E_s"])
+        self.E_min.append(info["E_min"])
+        self.E_next.append(info["E_next"])
+        if not info["fail"]:
+            self.barrier.append(info["E_s"] - info["E_min"])
+            self.rewards.append(self.alpha * (-self.barrier[-1] + self.kb * self.T * self.freq[-1])
+                                + self.beta * (self.E_min[-1] - self.E_next[-1]))
+        else:
+            self.barrier.append(0.0)
+            self.rewards.append(self.fail_panelty)
+
+    @staticmethod
+    def _atoms_dict(a: Atoms) -> dict:
+        return {"numbers": np.asarray(a.get_atomic_numbers()).tolist(), "positions": np.asarray(a.get_positions()).tolist(),
+                "cell": np.asarray(a.get_cell()).tolist(), "pbc": np.asarray(a.get_pbc()).tolist()}
+
+    def save(self, filename: str) -> None:
+        to_list = [self.alpha, self.beta, [self._atoms_dict(u) for u in self.states], self.E_min,
+                   [self._atoms_dict(u) for u in self.next_states], self.actions,
+                   [[[int(v[0])] + list(v[1:]) for v in u] for u in self.act_space], self.action_probs, self.rewards,
+                   self.E_min, self.barrier, self.E_s, self.E_next, self.fail, self.freq]
+        with open(filename + ".json", "w") as fh:
+            json.dump(to_list, fh)
+
+    def load(self, filename: str) -> None:
+        with open(filename) as fh:
+            data = json.load(fh)
+        (self.alpha, self.beta, states, self.E_min, next_states, self.actions, self.act_space, self.action_probs,
+         self.rewards, self.E_min, self.barrier, self.E_s, self.E_next, self.fail, self.freq) = data
+        for i in range(len(self.actions)):
+            self.states.append(Atoms(states[i]["numbers"], states[i]["positions"], states[i]["cell"]))
+            self.next_states.append(Atoms(next_states[i]["numbers"], next_states[i]["positions"], next_states[i]["cell"]))
+
+
+def convert(atoms, actions: Sequence[Sequence[float]]):
+    """``rlsim/drl/trainer.py:185-205`` — the twin of ``convert_to_graph_list``."""
+    return convert_to_graph_list(atoms, actions)
+
+
+class AverageMeter:
+    def __init__(self):
+        self.sum, self.count = 0.0, 0
+
+    def update(self, v: float, n: int = 1) -> None:
+        self.sum += v * n
+        self.count += n
+
+    @property
+    def avg(self) -> float:
+        return self.sum / max(self.count, 1)
+
+
+class Trainer:
+    """``Trainer(model, q_params, offline_model, lr, train_all)`` (``trainer.py:24-46``)."""
+
+    def __init__(self, model, q_params: Dict, offline_model=None, lr: float = 10 ** -3, train_all: bool = True):
+        self.policy_value_net = model
+        self.target_net = offline_model
+        self.train_all = bool(train_all)
+        if not train_all:
+            for name, param in self.policy_value_net.named_parameters():
+                if "reaction_model" in name:
+                    param.requires_grad = False
+        self.lr = float(lr)
+        self.q_params = q_params
+        self._adam: Dict[tuple, dict] = {}          # Adam state of the DQN heads, per device (optim.Adam, trainer.py:43)
+        self.dropout = False                        # set True to apply the heads' train-mode dropout (numpy RNG uniforms)
+
+    def update(self, memory_l, mode: str = "dqn", **kwargs) -> float:
+        if mode == "dqn":
+            return self.dqn_update(memory_l, **kwargs)
+        return self.context_bandit_update(memory_l, **kwargs)
+
+    def context_bandit_update(self, memory_l, episode_size, num_epoch, batch_size=8, device="cuda"):
+        raise NotImplementedError(
+            "context_bandit_update fits q0/q1 (rlsim/drl/trainer.py:55-100), i.e. the reaction model; its backward "
+            "(PaiNN representation + reaction heads) has no sm_100a kernels in this build")
+
+    def get_max_Q(self, model, state, action_space, device="cuda") -> torch.Tensor:
+        dataloader = DataLoader(ReactionDataset(convert(state, action_space)), batch_size=16, shuffle=False)
+        q_values = []
+        with torch.no_grad():
+            model.eval()
+            model.to(device)
+            for batch in dataloader:
+                batch = batch_to(batch, device)
+                q_values.append(model(batch, q_params=self.q_params)["rl_q"].detach())
+        return torch.max(torch.cat(q_values, dim=0))
+
+    def dqn_update(self, memory_l, gamma, episode_size, num_epoch, batch_size=8, device="cuda") -> float:
+        if self.train_all:
+            raise NotImplementedError(
+                "dqn_update with train_all=True back-propagates through the PaiNN representation (rlsim/drl/trainer.py:"
+                "163-177), which has no sm_100a kernels in this build; construct Trainer(..., train_all=False) to train "
+                "the DQN heads on the device")
+        if self.target_net is None:
+            self.target_net = copy.deepcopy(self.policy_value_net)
+        self.target_net.load_state_dict(self.policy_value_net.state_dict())
+        self.target_net.eval()
+        self.target_net.to(device)
+        self.policy_value_net.train()
+        self.policy_value_net.to(device)
+        losses = AverageMeter()
+        prob = [0.99 ** (len(memory_l) - i) for i in range(len(memory_l))]
+        randint = np.random.choice(range(len(memory_l)), size=episode_size, p=prob / np.sum(prob))
+        states, next_states, taken_actions, rewards, next_aspace = [], [], [], [], []
+        for u in randint:
+            memory = memory_l[u]
+            states += memory.states[:-1]
+            next_states += memory.next_states[:-1]
+            rewards += memory.rewards[:-1]
+            aspace, actions = memory.act_space, memory.actions
+            taken_actions += [[aspace[i][actions[i]]] for i in range(len(aspace) - 1)]
+            next_aspace += [aspace[i] for i in range(1, len(aspace))]
+        rewards = torch.tensor(rewards, dtype=torch.float)
+        next_Q = torch.zeros(len(next_aspace))
+        for i, state in enumerate(next_states):
+            next_Q[i] = self.get_max_Q(self.target_net, state, next_aspace[i], device=device)
+        dataset_list = []
+        for i, state in enumerate(states):
+            for data in convert(state, taken_actions[i]):
+                data.rl_q = next_Q[i] * gamma + rewards[i]
+                dataset_list.append(data)
+        q_dataloader = DataLoader(ReactionDataset(dataset_list), batch_size=batch_size, shuffle=False)
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        key = (dev.type, dev.index)
+        for _ in range(num_epoch):
+            for batch in q_dataloader:
+                batch = batch_to(batch, dev)
+                G = batch.num_graphs
+                u = torch.from_numpy(np.random.random_sample((G, 80)).astype(np.float32)).to(dev) if self.dropout else None
+                res = self.policy_value_net.q_head_update(batch, self.q_params, batch["rl_q"].reshape(-1), self._adam.get(key),
+                                                          self.lr, max_norm=0.8, dropout_uniform=u)
+                self._adam[key] = res["state"]
+                losses.update(float(res["loss"].item()))
+        return losses.avg

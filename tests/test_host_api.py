@@ -195,3 +195,30 @@ def test_trajectory_writer_matches_per_step_appends(tmp_path):
     ql = json.load(open(tmp_path / "buf" / "q_values.json"))
     assert len(ql) == 3 and len(ql[0]) == T and ql[1][4] == qs[4][1].tolist()
     assert json.load(open(tmp_path / "buf" / "actions.json"))[2] == [acts[t][2] for t in range(T)]
+
+
+def test_trainer_surface_and_memory_roundtrip(tmp_path, checkpoint_path):
+    """rlsim/drl/trainer.py / rlsim/memory.py mirror: constructor semantics (train_all freezes reaction_model), the JSON
+    layout of Memory.save / load, and loud failures for the forms that are not built."""
+    from rlvacdiffsim_b200.structures import apply_action
+    from rlvacdiffsim_b200.trainer import Memory, Trainer
+    model = rb.registry.get_model_class("dqn_v2").load(checkpoint_path)
+    tr = Trainer(model, {"alpha": 0.0, "beta": 1.0, "dqn": True}, train_all=False)
+    frozen = [n for n, p in model.named_parameters() if not p.requires_grad]
+    assert frozen and all("reaction_model" in n for n in frozen)
+    assert all(p.requires_grad for n, p in model.named_parameters() if "reaction_model" not in n)
+    s = make_crconi_supercell(2, seed=1)
+    space = rb.get_action_space(s, 3.528)
+    mem = Memory(alpha=1.0, beta=0.0, T=900.0)
+    mem.add({"state": s, "act": 1, "act_space": space, "act_probs": [0.1], "fail": False, "next": apply_action(s, space[1]),
+             "log_freq": 2.0, "E_s": 1.5, "E_min": 1.0, "E_next": 0.9})
+    assert abs(mem.rewards[0] - (-(0.5) + mem.kb * 900.0 * 2.0)) < 1e-12          # memory.py:58-62
+    mem.save(str(tmp_path / "traj0"))
+    back = Memory(alpha=0, beta=0)
+    back.load(str(tmp_path / "traj0.json"))
+    assert back.actions == [1] and back.rewards == mem.rewards and len(back.act_space[0]) == len(space)
+    np.testing.assert_array_equal(back.states[0].get_positions(), s.get_positions())
+    with pytest.raises(NotImplementedError):
+        Trainer(model, {"dqn": True}, train_all=True).dqn_update([mem], gamma=0.8, episode_size=1, num_epoch=1)
+    with pytest.raises(NotImplementedError):
+        tr.context_bandit_update([mem], episode_size=1, num_epoch=1)
