@@ -14,7 +14,8 @@ from conftest import GOLD, load_gold  # noqa: E402
 
 model = rb.registry.get_model_class("dqn_v2").load(os.path.join(GOLD, "model_trained")).to("cuda").eval()
 eng = model._engine_for(torch.device("cuda", 0))
-IMPLS = {"stream": {"tensor_cores": 1, "sliced_edge": 1},
+IMPLS = {"stream": {"tensor_cores": 1, "sliced_edge": 1, "layer0_sums": 1},
+         "stream_l0edge": {"tensor_cores": 1, "sliced_edge": 1, "layer0_sums": 0},
          "tc_general": {"tensor_cores": 1, "sliced_edge": 0},
          "simt": {"tensor_cores": 0}}
 only = sys.argv[1:] or list(IMPLS)
