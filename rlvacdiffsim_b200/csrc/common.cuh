@@ -119,6 +119,7 @@ struct rlvd_engine {
     // workspaces (grown on demand, never shrunk)
     rlvd::DevBuf x, mu0, mu1, hid, mix, nrm, vw, ctx, struct_edges, struct_edge_ptr, scratch;
     rlvd::DevBuf tiles, pipe_info, tile_ctr, stream_scratch;   // edge stream (edge_stream.cu)
+    rlvd::DevBuf readout_scratch;                              // split-readout partial pools + arrival counters
     rlvd::DevBuf l0A;                                          // [M, 256] species-resolved radial sums of layer 0
     int n_species = 0;                                         // rlvd_set_species
     int species_z[3] = {};

@@ -207,7 +207,7 @@ void rlvd_engine_destroy(rlvd_engine* e) {
     cudaSetDevice(e->device);
     for (void* d : e->derived) cudaFree(d);
     for (DevBuf* b : {&e->x, &e->mu0, &e->mu1, &e->hid, &e->mix, &e->nrm, &e->vw, &e->ctx, &e->struct_edges,
-                      &e->struct_edge_ptr, &e->scratch, &e->tiles, &e->pipe_info, &e->tile_ctr, &e->stream_scratch, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
+                      &e->struct_edge_ptr, &e->scratch, &e->tiles, &e->pipe_info, &e->tile_ctr, &e->stream_scratch, &e->l0A, &e->readout_scratch, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
                       &e->in_inv, &e->in_img, &e->in_rs, &e->in_ps, &e->in_temp, &e->in_qp, &e->g_row_ptr,
                       &e->g_node_struct, &e->g_col, &e->g_shift, &e->g_nedges, &e->g_q, &e->out_pack})
         b->release();

@@ -45,11 +45,13 @@ __device__ __forceinline__ float head_layer(const float* __restrict__ W, const f
     return acc;
 }
 
-__global__ void __launch_bounds__(RT) readout_kernel(int n_react, const int* __restrict__ node_ptr,
+__global__ void __launch_bounds__(RT, 4) readout_kernel(int n_react, const int* __restrict__ node_ptr,
                                                      const int* __restrict__ rs, const int* __restrict__ ps,
                                                      const int* __restrict__ Z, const float* __restrict__ q,
                                                      const Weights w, const rlvd_q_params qp,
-                                                     const float* __restrict__ d_temp, ReadoutOut out) {
+                                                     const float* __restrict__ d_temp, ReadoutOut out, int n_splits,
+                                                     float* __restrict__ part /* [n_react][n_splits][36] */,
+                                                     unsigned int* __restrict__ arrived /* [n_react], zero */) {
     extern __shared__ __align__(16) float sm[];
     float* sR = sm;                 // [TA][QS]
     float* sP = sm + TA * QS;       // [TA][QS]
@@ -68,7 +70,9 @@ __global__ void __launch_bounds__(RT) readout_kernel(int n_react, const int* __r
     if (tid < 36) pool[tid] = 0.f;
     __syncthreads();
 
-    for (int t0 = 0; t0 < n; t0 += TA) {
+    // small batches: blockIdx.y splits a reaction's atom tiles over n_splits CTAs (tile t goes to CTA t % n_splits); the
+    // last CTA to finish adds the partial pools in split order and runs the heads.  n_splits == 1 is the plain kernel.
+    for (int t0 = blockIdx.y * TA; t0 < n; t0 += TA * n_splits) {
         const int na = min(TA, n - t0);
         // ---- load tiles (rows beyond na are zero)
         for (int f = tid; f < TA * (F / 4); f += RT) {
@@ -203,6 +207,23 @@ __global__ void __launch_bounds__(RT) readout_kernel(int n_react, const int* __r
         __syncthreads();
     }
 
+    if (n_splits > 1) {
+        __shared__ unsigned int ticket;
+        if (tid < 36) part[((int64_t)g * n_splits + blockIdx.y) * 36 + tid] = pool[tid];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) ticket = atomicAdd(arrived + g, 1u);
+        __syncthreads();
+        if (ticket != (unsigned int)(n_splits - 1)) return;
+        __threadfence();
+        if (tid < 36) {
+            float v = 0.f;
+            for (int sidx = 0; sidx < n_splits; ++sidx) v += __ldcg(part + ((int64_t)g * n_splits + sidx) * 36 + tid);
+            pool[tid] = v;
+        }
+        if (tid == 0) arrived[g] = 0u;            // ready for the next launch
+        __syncthreads();
+    }
     // ---- H3 / H4 in warp 0
     if (wid == 0) {
         const float E_R = pool[32], E_P = pool[33], dE = pool[34];
@@ -339,7 +360,21 @@ int launch_readout(rlvd_engine* e, cudaStream_t s, int n_react, const int* node_
     if (n_react <= 0) return 0;
     ReadoutOut out{rl_q, q0, q1, delta_e, E_R, E_P, head_in};
     Span sp(e, s, FAM_READOUT);
-    readout_kernel<<<n_react, RT, readout_smem(), s>>>(n_react, node_ptr, rs, ps, Z, q, e->w, qp, d_temp, out);
+    // few reactions (single-replica stepping, get_max_Q batches): split each reaction's atom tiles over several CTAs
+    int n_splits = 1;
+    if (n_react < 296) n_splits = min(8, (592 + n_react - 1) / n_react);
+    float* part = nullptr;
+    unsigned int* arrived = nullptr;
+    if (n_splits > 1) {
+        const size_t part_bytes = (size_t)n_react * n_splits * 36 * sizeof(float);
+        const size_t cnt_off = (part_bytes + 255) & ~(size_t)255;
+        if (e->readout_scratch.ensure(cnt_off + 296 * sizeof(unsigned int))) return 1;
+        part = e->readout_scratch.as<float>();
+        arrived = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(e->readout_scratch.p) + cnt_off);
+        RLVD_CUDA(cudaMemsetAsync(arrived, 0, 296 * sizeof(unsigned int), s));   // the kernel also re-zeroes what it used
+    }
+    readout_kernel<<<dim3(n_react, n_splits), RT, readout_smem(), s>>>(n_react, node_ptr, rs, ps, Z, q, e->w, qp, d_temp, out,
+                                                                      n_splits, part, arrived);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;
