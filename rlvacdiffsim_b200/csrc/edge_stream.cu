@@ -225,7 +225,11 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
                                                         int* __restrict__ tile_counter, int tile_capacity,
                                                         uint8_t* __restrict__ tiles, int4* __restrict__ pipe_info,
                                                         int* __restrict__ err_flag, const int* __restrict__ Z,
-                                                        const int* __restrict__ z2s, float* __restrict__ l0A) {
+                                                        const int* __restrict__ z2s, float* __restrict__ l0A, int mode,
+                                                        int n_splits) {
+    // mode 0: allocate tiles and fill them (one CTA per structure).  Small batches run mode 1 (allocation only) and then
+    // mode 2 with grid (n_struct, n_splits): CTA (g, y) fills the receivers of warp-stride class y; every CTA repeats the
+    // (cheap, deterministic) scan and takes the tile bases mode 1 published in pipe_info.
     __shared__ int goff[MAXN + 1];        // exclusive prefix of per-receiver group counts
     // per-warp species-sorted slot records for the layer-0 sums: v[32][21] and (dir_x, dir_y, dir_z, 1)[32]
     __shared__ __align__(16) float stg_v[8][32 * NK];
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
     const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int node0 = __ldg(node_ptr + g), n = __ldg(node_ptr + g + 1) - node0;
     if (n <= 0) {
-        if (tid < NPIPE) pipe_info[g * NPIPE + tid] = make_int4(0, 0, 0, 0);
+        if (tid < NPIPE && mode != 2) pipe_info[g * NPIPE + tid] = make_int4(0, 0, 0, 0);
         return;
     }
     for (int t = tid; t < 3 * n; t += 256) spos[t] = __ldg(pos + 3 * (int64_t)node0 + t);
@@ -288,7 +292,16 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
         bnd[tid] = b;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && mode == 2) {
+        int ok = 0;
+        for (int p = 0; p < NPIPE; ++p) {
+            const int4 pi = pipe_info[g * NPIPE + p];
+            tbeg[p] = pi.x;
+            ok |= pi.y > 0 ? 1 : 0;
+        }
+        tbeg[NPIPE] = ok;
+    }
+    if (tid == 0 && mode != 2) {
         int total = 0;
         int tl[NPIPE];
         for (int p = 0; p < NPIPE; ++p) {
@@ -306,7 +319,7 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
         tbeg[NPIPE] = ok ? 1 : 0;
     }
     __syncthreads();
-    if (tbeg[NPIPE] == 0) return;
+    if (tbeg[NPIPE] == 0 || mode == 1) return;
 
     float C[9];
 #pragma unroll
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
     const int l0k = min(lane, NK - 1);
     float* const wst = stg_v[warp];
     float4* const wsd = stg_d[warp];
-    for (int i = warp; i < n; i += 8) {
+    for (int i = warp + 8 * (int)blockIdx.y; i < n; i += 8 * n_splits) {
         int p = 0;
         while (i >= bnd[p + 1]) ++p;
         const int gi = node0 + i;
@@ -432,7 +445,7 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
         }
     }
     // ---- padding groups that complete each pipeline's last tile (zero filters, harmless receiver)
-    if (tid < NPIPE * 24) {
+    if (tid < NPIPE * 24 && blockIdx.y == 0) {
         const int p = tid / 24, k = tid - p * 24;
         const int groups = goff[bnd[p + 1]] - goff[bnd[p]];
         const int ntile = (groups + 3) >> 2;
@@ -957,10 +970,13 @@ int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_
         return 1;
     RLVD_CUDA(cudaMemsetAsync(e->tile_ctr.p, 0, 16, s));   // tile counter | capacity error | species outside the model's list
     Span sp(e, s, FAM_PACK);
-    edge_pack_kernel<<<n_struct, 256, 0, s>>>(n_struct, node_ptr, row_ptr, col, shift, pos, cell, e->w.freqs, e->w.feps,
-                                              e->w.cutoff, e->tile_ctr.as<int>(), (int)cap, e->tiles.as<uint8_t>(),
-                                              e->pipe_info.as<int4>(), e->tile_ctr.as<int>() + 1, Z, e->w.z2s, l0A);
-    sp.end(1);
+    // few structures (single-replica stepping): split each structure's receivers over several CTAs
+    const int n_splits = n_struct >= 296 ? 1 : min(8, (592 + n_struct - 1) / n_struct);
+    for (int mode = n_splits > 1 ? 1 : 0; mode <= (n_splits > 1 ? 2 : 0); ++mode)
+        edge_pack_kernel<<<dim3(n_struct, mode == 2 ? n_splits : 1), 256, 0, s>>>(
+            n_struct, node_ptr, row_ptr, col, shift, pos, cell, e->w.freqs, e->w.feps, e->w.cutoff, e->tile_ctr.as<int>(), (int)cap,
+            e->tiles.as<uint8_t>(), e->pipe_info.as<int4>(), e->tile_ctr.as<int>() + 1, Z, e->w.z2s, l0A, mode, n_splits);
+    sp.end(n_splits > 1 ? 2 : 1);
     RLVD_CUDA(cudaGetLastError());
     return 0;
 }
