@@ -19,6 +19,7 @@ namespace {
 constexpr int RT = 256;  // threads
 constexpr int TA = 32;   // atoms per tile
 constexpr int QS = F + 4;  // padded row stride of the shared q tiles
+constexpr int RO_TILE_CAP = 64;   // tiles per reaction the split form keeps partials for (structures of <= 2048 atoms)
 
 __device__ __forceinline__ float act_fn(float v, int code) {
     switch (code) {
@@ -71,8 +72,13 @@ __global__ void __launch_bounds__(RT, 4) readout_kernel(int n_react, const int* 
     __syncthreads();
 
     // small batches: blockIdx.y splits a reaction's atom tiles over n_splits CTAs (tile t goes to CTA t % n_splits); the
-    // last CTA to finish adds the partial pools in split order and runs the heads.  n_splits == 1 is the plain kernel.
-    for (int t0 = blockIdx.y * TA; t0 < n; t0 += TA * n_splits) {
+    // last CTA to finish adds the per-tile sums in tile order and runs the heads.  n_splits == 1 is the plain kernel; so
+    // is a reaction with more tiles than the scratch keeps (CTA 0 walks all of them, the others only check in).
+    const int n_tiles = (n + TA - 1) / TA;
+    const bool split = n_splits > 1 && n_tiles <= RO_TILE_CAP;
+    const int t_first = split ? (int)blockIdx.y * TA : (blockIdx.y == 0 ? 0 : n);
+    const int t_step = split ? TA * n_splits : TA;
+    for (int t0 = t_first; t0 < n; t0 += t_step) {
         const int na = min(TA, n - t0);
         // ---- load tiles (rows beyond na are zero)
         for (int f = tid; f < TA * (F / 4); f += RT) {
@@ -128,8 +134,10 @@ __global__ void __launch_bounds__(RT, 4) readout_kernel(int n_react, const int* 
             __syncthreads();
         }
         // ---- pooled energies (thread 0, atom order)
+        //      Every pooled quantity is summed per TILE from zero and the tile sums are added in tile order: the result
+        //      does not depend on which CTA computed a tile, i.e. not on the batch size (split form below).
         if (tid == 0) {
-            float eR = pool[32], eP = pool[33], dE = pool[34];
+            float eR = 0.f, eP = 0.f, dE = 0.f;
             for (int a = 0; a < na; ++a) {
                 const int s = __ldg(w.elem_lookup + min(max(__ldg(Z + r0 + t0 + a), 0), 99));
                 const float sc = __ldg(w.sp_scales + s), sh = __ldg(w.sp_shifts + s);
@@ -137,7 +145,12 @@ __global__ void __launch_bounds__(RT, 4) readout_kernel(int n_react, const int* 
                 eP += fmaf(eo[TA + a], sc, sh);
                 dE += sc * (eo[TA + a] - eo[a]);
             }
-            pool[32] = eR; pool[33] = eP; pool[34] = dE;
+            if (split) {
+                float* pt = part + ((int64_t)g * RO_TILE_CAP + t0 / TA) * 36;
+                pt[32] = eR; pt[33] = eP; pt[34] = dE;
+            } else {
+                pool[32] += eR; pool[33] += eP; pool[34] += dE;
+            }
         }
         // ---- D = q_P - q_R (in place in sP)
         for (int f = tid; f < TA * F; f += RT) {
@@ -200,25 +213,27 @@ __global__ void __launch_bounds__(RT, 4) readout_kernel(int n_react, const int* 
         }
         __syncthreads();
         if (tid < 32) {
-            float h = pool[tid];
+            float h = 0.f;
             for (int a = 0; a < TA; ++a) h += hpart[a * 32 + tid];     // atom order
-            pool[tid] = h;
+            if (split) part[((int64_t)g * RO_TILE_CAP + t0 / TA) * 36 + tid] = h;
+            else pool[tid] += h;
         }
         __syncthreads();
     }
 
     if (n_splits > 1) {
         __shared__ unsigned int ticket;
-        if (tid < 36) part[((int64_t)g * n_splits + blockIdx.y) * 36 + tid] = pool[tid];
+        if (!split && blockIdx.y == 0 && tid < 35) part[(int64_t)g * RO_TILE_CAP * 36 + tid] = pool[tid];   // one "tile"
         __threadfence();
         __syncthreads();
         if (tid == 0) ticket = atomicAdd(arrived + g, 1u);
         __syncthreads();
         if (ticket != (unsigned int)(n_splits - 1)) return;
         __threadfence();
-        if (tid < 36) {
+        if (tid < 35) {
             float v = 0.f;
-            for (int sidx = 0; sidx < n_splits; ++sidx) v += __ldcg(part + ((int64_t)g * n_splits + sidx) * 36 + tid);
+            const int n_comb = split ? n_tiles : 1;
+            for (int t = 0; t < n_comb; ++t) v += __ldcg(part + ((int64_t)g * RO_TILE_CAP + t) * 36 + tid);   // tile order
             pool[tid] = v;
         }
         if (tid == 0) arrived[g] = 0u;            // ready for the next launch
@@ -366,7 +381,7 @@ int launch_readout(rlvd_engine* e, cudaStream_t s, int n_react, const int* node_
     float* part = nullptr;
     unsigned int* arrived = nullptr;
     if (n_splits > 1) {
-        const size_t part_bytes = (size_t)n_react * n_splits * 36 * sizeof(float);
+        const size_t part_bytes = (size_t)n_react * RO_TILE_CAP * 36 * sizeof(float);
         const size_t cnt_off = (part_bytes + 255) & ~(size_t)255;
         if (e->readout_scratch.ensure(cnt_off + 296 * sizeof(unsigned int))) return 1;
         part = e->readout_scratch.as<float>();

@@ -223,6 +223,46 @@ def test_replica_batch_matches_single_and_oracle(model):
     assert int(np.argmax(together[3])) == int(np.argmax(ref))
 
 
+def test_full_size_batch_properties(model):
+    """BASELINE config 2's per-GPU shard (128 x 255-atom replicas, 12 candidates: 3072 structures, 42 M edges) has no
+    oracle run in a test's time budget; check the size-independent properties instead: (1) the batch is a disjoint
+    union, so permuting the replicas permutes the Q-values BITWISE; (2) scoring in chunks equals scoring at once,
+    bitwise; (3) a rigid translation of every structure leaves Q unchanged up to fp32 position rounding; (4) every
+    replica's Q-values match the fp64 oracle where it is affordable (two replicas)."""
+    R = 128
+    reps = [make_crconi_supercell(4, seed=1000 + s) for s in range(R)]
+    spaces = [rb.get_action_space(r, 3.528) for r in reps]
+    assert all(len(r) == 255 and len(sp) == 12 for r, sp in zip(reps, spaces))
+    qp = {"alpha": 0.0, "beta": 1.0, "dqn": True, "temperature": 700.0}
+    scorer = ReplicaScorer(model, 0)
+    full = scorer.score(reps, spaces, qp)
+    perm = np.random.RandomState(0).permutation(R)
+    shuffled = scorer.score([reps[i] for i in perm], [spaces[i] for i in perm], qp)
+    chunked = ReplicaScorer(model, 0, max_structs_per_call=24 * 37).score(reps, spaces, qp)
+    for k, i in enumerate(perm):
+        assert np.array_equal(shuffled[k], full[i])
+    for r in range(R):
+        assert np.array_equal(chunked[r], full[r])
+    shift = np.array([0.731, -1.377, 2.053])
+    moved = []
+    for r in reps[:16]:
+        m = r.copy()
+        m.set_positions(r.get_positions() + shift)
+        moved.append(m)
+    tr = scorer.score(moved, spaces[:16], qp)
+    for r in range(16):
+        scale = np.maximum(np.abs(full[r]), 1.0)
+        assert np.max(np.abs(tr[r] - full[r]) / scale) < 2e-4      # positions re-round in fp32 after the shift
+        assert int(np.argmax(tr[r])) == int(np.argmax(full[r]))
+    m64 = PaiNNOracle.load(os.path.join(GOLD, "model_trained"), dtype=torch.float64)
+    for r in (0, R - 1):
+        Z, pR, pP, cells, ptr = build_reaction_batch(reps[r].numbers, reps[r].positions, reps[r].cell, spaces[r])
+        with torch.no_grad():
+            ref = m64.reaction_forward(Z, pR, pP, cells, ptr, qp)["rl_q"].numpy()
+        assert np.max(np.abs(full[r] - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-4
+        assert int(np.argmax(full[r])) == int(np.argmax(ref))
+
+
 def test_select_action_drop_in_seeded(model):
     """simulator.py:45-103 semantics: same Q as the golden, same seeded draw as the oracle's probabilities."""
     g = load_gold("demo")
