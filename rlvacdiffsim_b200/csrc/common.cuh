@@ -128,6 +128,7 @@ struct rlvd_engine {
     rlvd::DevBuf in_node_ptr, in_Z, in_pos, in_cell, in_inv, in_img, in_rs, in_ps, in_temp, in_qp;
     rlvd::DevBuf g_row_ptr, g_node_struct, g_col, g_shift, g_nedges, g_q, out_pack;
     int64_t launches = 0;
+    bool attr_stream = false, attr_neighbor = false, attr_tc_edge = false, attr_tc_linear = false, attr_train = false;   // dynamic-smem opt-ins done on this device
     bool use_tensor_cores = true;
     bool use_sliced_edge = true;    // structure-resident edge kernels when every structure has <= 256 atoms
     bool fuse_mix = false;          // nrm / vw reductions inside the mu_channel_mix GEMM epilogue (tc_linear.cu mixred mode);

@@ -984,13 +984,12 @@ int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_
 int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, int max_struct_nodes, const int* node_ptr,
                        const float* x, const float* mu_in, float* q, float* mu_out, const int* gate, int gate_value) {
     if (n_struct <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!e->attr_stream) {                 // per engine = per device: the attribute is a per-device property
         RLVD_CUDA(cudaFuncSetAttribute(edge_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)stream_smem_bytes<true>(MAXN)));
         RLVD_CUDA(cudaFuncSetAttribute(edge_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)stream_smem_bytes<true>(MAXN)));
-        attr_set = true;
+        e->attr_stream = true;
     }
     if (e->stream_scratch.ensure((size_t)MAX_SMID * PART_SM * sizeof(float))) return 1;
     float* scr = e->stream_scratch.as<float>();

@@ -268,13 +268,12 @@ int launch_neighbor_count(rlvd_engine* e, cudaStream_t s, int n_struct, int n_no
     }
     if (e->struct_edges.ensure((size_t)n_struct * sizeof(int))) return 1;
     if (e->struct_edge_ptr.ensure(((size_t)n_struct + 1) * sizeof(int))) return 1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!e->attr_neighbor) {                 // per engine = per device: the attribute is a per-device property
         RLVD_CUDA(cudaFuncSetAttribute(neighbor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)neighbor_smem()));
         RLVD_CUDA(cudaFuncSetAttribute(neighbor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)neighbor_smem()));
-        attr_set = true;
+        e->attr_neighbor = true;
     }
     const float rc = cutoff;
     const float rc2 = rc * rc;  // fp32 product, as in the oracle

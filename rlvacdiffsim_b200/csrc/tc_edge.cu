@@ -329,11 +329,10 @@ int launch_tc_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* 
                    const int8_t* shift, const float* pos, const float* cell, const int* node_struct, const float* x,
                    const float* mu_in, float* q, float* mu_out) {
     if (M <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!e->attr_tc_edge) {                 // per engine = per device: the attribute is a per-device property
         RLVD_CUDA(cudaFuncSetAttribute(tc_edge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)te_smem_bytes()));
         RLVD_CUDA(cudaFuncSetAttribute(tc_edge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)te_smem_bytes()));
-        attr_set = true;
+        e->attr_tc_edge = true;
     }
     const uint8_t* wf = reinterpret_cast<const uint8_t*>(e->w.filt_F) + (size_t)layer * A_BYTES;
     const int grid = (M + RC - 1) / RC;

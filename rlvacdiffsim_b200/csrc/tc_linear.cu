@@ -474,11 +474,10 @@ bool tc_linear_supported(const LinearArgs& a) {
 int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt) {
     RLVD_CHECK(tc_linear_supported(a), "tc_linear: unsupported shape M=%d K=%d N=%d", a.M, a.K, a.N);
     if (a.M <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!e->attr_tc_linear) {                 // per engine = per device: the attribute is a per-device property
         RLVD_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)tc_smem_bytes(256)));
-        attr_set = true;
+        e->attr_tc_linear = true;
     }
     const int n_tiles = a.mixred ? (a.n_nodes + 39) / 40 : (a.M + TC_M - 1) / TC_M;
     const int grid = n_tiles < e->sm_count ? n_tiles : e->sm_count;

@@ -226,10 +226,9 @@ int launch_q_head_train(rlvd_engine* e, cudaStream_t s, int n_graphs, const floa
     if (n_graphs <= 0) return 0;
     const size_t smem = (size_t)(2 * NP + TR_THREADS + 4 + (size_t)n_graphs * S_PER) * sizeof(float);
     RLVD_CHECK(smem <= 200 * 1024, "q_head_train: minibatch of %d reaction graphs does not fit one CTA (max ~120)", n_graphs);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!e->attr_train) {                 // per engine = per device: the attribute is a per-device property
         RLVD_CUDA(cudaFuncSetAttribute(q_head_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        e->attr_train = true;
     }
     const Weights& w = e->w;
     QHeadPtrs W;
