@@ -216,6 +216,12 @@ int  rlvd_set_species(rlvd_engine* e, const int32_t* atomic_numbers, int32_t n);
  * "layer0_sums" (1 = layer 0 from species-resolved radial sums, see rlvd_set_species; 0 = per-edge kernels). */
 int  rlvd_set_option(rlvd_engine* e, const char* name, int32_t value);
 
+/* Device status word since the last call (synchronises `stream`, then clears it).  bit 0: an operand of a tensor-core GEMM
+ * left the range of the fp16 hi/lo split (|x| >= 65504, inf or NaN) — the results of that call are not valid; set option
+ * "tensor_cores" to 0 and repeat it (rlvd_score_reactions_host and the Python wrappers do this by themselves).  Physical
+ * structures stay orders of magnitude below the limit; unphysically dense ones make the network diverge in any precision. */
+int  rlvd_check_status(rlvd_engine* e, void* stream, int32_t* flags);
+
 /* ---- introspection ------------------------------------------------------------------------------ */
 /* Number of kernels this library has launched on the engine since creation (bench.py "gpu_launches"). */
 int64_t rlvd_launch_count(const rlvd_engine* e);

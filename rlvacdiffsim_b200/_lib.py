@@ -61,6 +61,7 @@ SYMBOLS = {
     "rlvd_time_readout": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, C.POINTER(TimeHead), _P]),
     "rlvd_linear": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int32, _P]),
     "rlvd_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
+    "rlvd_check_status": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
     "rlvd_set_species": (C.c_int, [_P, _P, C.c_int32]),
     "rlvd_launch_count": (C.c_int64, [_P]),
     "rlvd_profile_enable": (C.c_int, [_P, C.c_int32]),

@@ -119,6 +119,7 @@ struct rlvd_engine {
     // workspaces (grown on demand, never shrunk)
     rlvd::DevBuf x, mu0, mu1, hid, mix, nrm, vw, ctx, struct_edges, struct_edge_ptr, scratch;
     rlvd::DevBuf tiles, pipe_info, tile_ctr, stream_scratch;   // edge stream (edge_stream.cu)
+    rlvd::DevBuf status;                                       // int[4] device status word (rlvd_check_status)
     rlvd::DevBuf readout_scratch;                              // split-readout partial pools + arrival counters
     rlvd::DevBuf l0A;                                          // [M, 256] species-resolved radial sums of layer 0
     int n_species = 0;                                         // rlvd_set_species
@@ -190,6 +191,7 @@ struct LinearArgs {
     // device-side gate: when set, the kernel runs only if *gate == gate_value (layer-0 collapse vs its fallback)
     const int* gate = nullptr;
     int gate_value = 0;
+    int* status = nullptr;        // engine status word: bit 0 = an operand left the fp16-split range (tc_linear.cu)
 };
 int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a);
 int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt);

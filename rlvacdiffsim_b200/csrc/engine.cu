@@ -198,6 +198,8 @@ int rlvd_engine_create(int device, rlvd_engine** out) {
     rlvd_engine* e = new rlvd_engine();
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
+    if (e->status.ensure(16)) { delete e; return 1; }
+    RLVD_CUDA(cudaMemset(e->status.p, 0, 16));
     *out = e;
     return 0;
 }
@@ -207,7 +209,7 @@ void rlvd_engine_destroy(rlvd_engine* e) {
     cudaSetDevice(e->device);
     for (void* d : e->derived) cudaFree(d);
     for (DevBuf* b : {&e->x, &e->mu0, &e->mu1, &e->hid, &e->mix, &e->nrm, &e->vw, &e->ctx, &e->struct_edges,
-                      &e->struct_edge_ptr, &e->scratch, &e->tiles, &e->pipe_info, &e->tile_ctr, &e->stream_scratch, &e->l0A, &e->readout_scratch, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
+                      &e->struct_edge_ptr, &e->scratch, &e->tiles, &e->pipe_info, &e->tile_ctr, &e->stream_scratch, &e->l0A, &e->readout_scratch, &e->status, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
                       &e->in_inv, &e->in_img, &e->in_rs, &e->in_ps, &e->in_temp, &e->in_qp, &e->g_row_ptr,
                       &e->g_node_struct, &e->g_col, &e->g_shift, &e->g_nedges, &e->g_q, &e->out_pack})
         b->release();
@@ -614,6 +616,18 @@ int rlvd_time_readout(rlvd_engine* e, void* stream, int32_t n_struct, const int3
     return launch_time_readout(e, (cudaStream_t)stream, n_struct, d_node_ptr, d_q, d_T, d_defect, *head, d_time);
 }
 
+int rlvd_check_status(rlvd_engine* e, void* stream, int32_t* flags) {
+    RLVD_CHECK(e != nullptr && flags != nullptr, "rlvd_check_status: bad argument");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int h = 0;
+    RLVD_CUDA(cudaMemcpyAsync(&h, e->status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    RLVD_CUDA(cudaStreamSynchronize(s));
+    if (h != 0) RLVD_CUDA(cudaMemsetAsync(e->status.p, 0, sizeof(int), s));
+    *flags = h;
+    return 0;
+}
+
 int rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes,
                               const int32_t* h_node_ptr, const int32_t* h_Z, const float* h_pos, const float* h_cell,
                               const float* h_inv_cell, const int32_t* h_img_range, float cutoff, int32_t n_react,
@@ -676,7 +690,20 @@ int rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, in
     for (int k = 0; k < 6; ++k)
         if (hosts[k] != nullptr)
             RLVD_CUDA(cudaMemcpyAsync(hosts[k], op + (size_t)k * n_react, (size_t)n_react * 4, cudaMemcpyDeviceToHost, s));
+    int status = 0;
+    RLVD_CUDA(cudaMemcpyAsync(&status, e->status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     RLVD_CUDA(cudaStreamSynchronize(s));
+    if ((status & 1) && e->use_tensor_cores) {
+        // an activation left the fp16-split range of the tensor-core GEMMs (|x| >= 65504: the network diverging on an
+        // unphysical structure): redo the call on the fp32 SIMT kernels, which carry any finite fp32 value
+        RLVD_CUDA(cudaMemsetAsync(e->status.p, 0, sizeof(int), s));
+        e->use_tensor_cores = false;
+        const int rc = rlvd_score_reactions_host(e, stream, n_struct, n_nodes, h_node_ptr, h_Z, h_pos, h_cell, h_inv_cell,
+                                                 h_img_range, cutoff, n_react, h_react_struct, h_prod_struct, qp,
+                                                 h_temperature, h_rl_q, h_q0, h_q1, h_delta_e, h_E_R, h_E_P, h_n_edges);
+        e->use_tensor_cores = true;
+        return rc;
+    }
     return 0;
 }
 

@@ -64,11 +64,14 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "l"(a_desc), "l"(b_desc), "r"(IDESC_F16_M128_N128), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void split8(const float4 lo4, const float4 hi4, uint4& H, uint4& L) {
+// `bad` collects values outside the fp16 range (|v| >= 65504, inf, NaN): the fp16 hi/lo split cannot represent them.
+// Physical inputs stay below ~1e2; unphysically dense structures make the network itself diverge to 1e20+ in fp32.
+__device__ __forceinline__ void split8(const float4 lo4, const float4 hi4, uint4& H, uint4& L, bool& bad) {
     const float v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
     __half h[8], l[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
+        bad |= !(fabsf(v[t]) < 65504.0f);
         h[t] = __float2half_rn(v[t]);
         l[t] = __float2half_rn((v[t] - __half2float(h[t])) * 2048.0f);
     }
@@ -166,6 +169,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
         const uint32_t ast = smem_u32(Ast);
         const uint32_t row_off = (r >> 3) * CORE_SBO + (r & 7) * 16;
         uint32_t acc_it = 0, ph_it = 0;
+        bool bad = false;                                    // an operand left the fp16-split range (engine status bit 0)
         if (blockIdx.x < n_tiles) stage_A_async(a, blockIdx.x, 0, ast, t);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int phase = 0; phase < NPH; ++phase, ++ph_it) {
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                     const float4 v0 = *reinterpret_cast<const float4*>(Ast + r * 512 + (((2 * kc) ^ (r & 7)) << 4));
                     const float4 v1 = *reinterpret_cast<const float4*>(Ast + r * 512 + (((2 * kc + 1) ^ (r & 7)) << 4));
                     uint4 H, L;
-                    split8(v0, v1, H, L);
+                    split8(v0, v1, H, L, bad);
                     *reinterpret_cast<uint4*>(A_hi + kc * CORE_LBO + row_off) = H;
                     *reinterpret_cast<uint4*>(A_lo + kc * CORE_LBO + row_off) = L;
                 }
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                             y[u] = v;
                         }
                         uint4 H, L;
-                        split8(make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]), H, L);
+                        split8(make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]), H, L, bad);
                         const int kc = (c0 + j) >> 3;
                         *reinterpret_cast<uint4*>(A_hi + kc * CORE_LBO + hrow) = H;
                         *reinterpret_cast<uint4*>(A_lo + kc * CORE_LBO + hrow) = L;
@@ -345,6 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                 }
             }
         }
+        if (bad && a.status != nullptr) atomicOr(a.status, 1);
     } else if (warp == 8) {
         // ================= weight-stage producer =================
         if (lane == 0) {
@@ -471,7 +476,9 @@ bool tc_linear_supported(const LinearArgs& a) {
     return a.N % TC_N == 0 && a.N <= 384 && k_ok && (a.A2 == nullptr || a.K1 == 128) && a.lda % 4 == 0 && a.ldy % 4 == 0;
 }
 
-int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt) {
+int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a_in, const void* Wfmt) {
+    LinearArgs a = a_in;
+    a.status = e->status.as<int>();
     RLVD_CHECK(tc_linear_supported(a), "tc_linear: unsupported shape M=%d K=%d N=%d", a.M, a.K, a.N);
     if (a.M <= 0) return 0;
     if (!e->attr_tc_linear) {                 // per engine = per device: the attribute is a per-device property

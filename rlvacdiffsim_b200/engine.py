@@ -308,11 +308,30 @@ class Engine:
                      temperature=None, max_struct_nodes: int = 0, head_inputs: bool = False) -> Dict[str, torch.Tensor]:
         n_struct = node_ptr.numel() - 1
         row_ptr, col, shift, node_struct = self.radius_graph(pos, cell, inv_cell, img_range, node_ptr)
-        q = self.representation(Z, pos, cell, node_struct, row_ptr, col, shift, n_struct, node_ptr=node_ptr,
-                                max_struct_nodes=max_struct_nodes)
-        out = self.readout(q, Z, node_ptr, react_struct, prod_struct, qp, temperature, head_inputs=head_inputs)
+
+        def run():
+            q = self.representation(Z, pos, cell, node_struct, row_ptr, col, shift, n_struct, node_ptr=node_ptr,
+                                    max_struct_nodes=max_struct_nodes)
+            return self.readout(q, Z, node_ptr, react_struct, prod_struct, qp, temperature, head_inputs=head_inputs)
+
+        out = run()
+        if self.check_status() & 1:
+            # an activation left the fp16-split range of the tensor-core GEMMs (the network diverging on an unphysical
+            # structure, |x| >= 65504): repeat on the fp32 SIMT kernels, which carry any finite fp32 value
+            self.set_option("tensor_cores", 0)
+            try:
+                out = run()
+            finally:
+                self.set_option("tensor_cores", 1)
         out["n_edges"] = col.shape[0]
         return out
+
+    def check_status(self) -> int:
+        """``rlvd_check_status``: synchronises the current stream, returns and clears the device status word."""
+        flags = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_check_status(self._h, self._stream(), C.byref(flags)))
+        return int(flags.value)
 
     # ------------------------------------------------------------------ whole path, host buffers (e2e)
     def _pin(self, key: str, arr: np.ndarray) -> torch.Tensor:

@@ -392,6 +392,78 @@ def test_edge_stream_ragged_batch_matches_simt_and_oracle(engine):
         assert np.abs(out["stream"][1][sl] - mur.numpy()).max() <= TOL * np.abs(mur.numpy()).max()
 
 
+def test_edge_stream_fuzz_against_simt(engine):
+    """Randomised batches (1..256 atoms per structure, cubic / orthorhombic / triclinic cells from sparse gas to dense
+    multi-image packings, 1..40 structures, the three species in random proportions): the tcgen05 edge stream path with
+    the layer-0 collapse against the fp32 SIMT kernels on the same graph.  Covers the pack kernel's pipeline partition
+    (receivers with 0..100+ edges, ranges that come out empty), the split-fill form for small batches and the tile
+    allocator under many shapes."""
+    rng = np.random.RandomState(2024)
+    for trial in range(24):
+        n_struct = int(rng.choice([1, 2, 3, 7, 19, 40]))
+        Zs, ps, cs, ptr = [], [], [], [0]
+        for _ in range(n_struct):
+            n = int(rng.choice([1, 2, 5, 8, 9, 31, 64, 100, 177, 255, 256]))
+            kind = rng.randint(3)
+            g = int(np.ceil(n ** (1 / 3)))
+            lo = max(4.0, 1.9 * g)                       # >= 1.9 A lattice spacing: up to ~2x the density of fcc CrCoNi
+            L = rng.uniform(lo, lo + 12.0, 3) if kind else np.full(3, rng.uniform(lo, lo + 12.0))
+            cell = np.diag(L)
+            if kind == 2:
+                cell = cell + rng.uniform(-0.15, 0.15, (3, 3)) * L.min()
+            # jittered lattice placement keeps atoms apart
+            grid = np.stack(np.meshgrid(*[np.arange(g)] * 3, indexing="ij"), -1).reshape(-1, 3)[rng.permutation(g ** 3)[:n]]
+            frac = (grid + 0.5 + rng.uniform(-0.2, 0.2, (n, 3))) / g
+            Zs.append(rng.choice([24, 27, 28], size=n).astype(np.int32))
+            ps.append((frac @ cell).astype(np.float32))
+            cs.append(cell)
+            ptr.append(ptr[-1] + n)
+        Z, pos, cells, ptr = np.concatenate(Zs), np.concatenate(ps), np.stack(cs), np.asarray(ptr, dtype=np.int32)
+        row_ptr, col, shift, node_struct = _device_graph(engine, pos, cells.astype(np.float32), ptr)
+        if col.shape[0] == 0:
+            continue
+        Zd, posd = torch.from_numpy(Z).cuda(), torch.from_numpy(pos).cuda()
+        celld, ptrd = torch.from_numpy(cells.astype(np.float32)).cuda(), torch.from_numpy(ptr).cuda()
+        out = {}
+        for name, opts in (("stream", {"tensor_cores": 1, "sliced_edge": 1}), ("simt", {"tensor_cores": 0})):
+            for k, v in opts.items():
+                engine.set_option(k, v)
+            q, mu = engine.representation(Zd, posd, celld, node_struct, row_ptr, col, shift, n_struct, return_mu=True,
+                                          node_ptr=ptrd, max_struct_nodes=int(np.diff(ptr).max()))
+            out[name] = (q.cpu().numpy(), mu.cpu().numpy())
+        engine.set_option("tensor_cores", 1)
+        for a, b in zip(out["stream"], out["simt"]):
+            assert np.isfinite(a).all(), trial
+            assert np.abs(a - b).max() <= 5e-5 * max(np.abs(b).max(), 1.0), (trial, np.abs(a - b).max(), np.abs(b).max())
+
+
+def test_unphysical_density_falls_back_to_fp32(model):
+    """A structure ten times denser than any crystal makes the network itself diverge (|q| ~ 1e20 in fp32).  The fp16
+    hi/lo split of the tensor-core GEMMs cannot carry operands >= 65504: the device raises its status bit and the call
+    is repeated on the fp32 SIMT kernels, so the caller still gets what an fp32 evaluation gives (finite numbers, equal
+    to the tensor_cores=0 run) instead of NaN."""
+    rng = np.random.RandomState(5)
+    n, g = 255, 7
+    cell = np.diag([11.5, 4.4, 6.2])
+    grid = np.stack(np.meshgrid(*[np.arange(g)] * 3, indexing="ij"), -1).reshape(-1, 3)[rng.permutation(g ** 3)[:n]]
+    pos = ((grid + 0.5 + rng.uniform(-0.2, 0.2, (n, 3))) / g) @ cell
+    dense = Atoms(rng.choice([24, 27, 28], size=n), pos, cell)
+    ok = make_crconi_supercell(4, seed=3)
+    act = [[0, 0.3, 0.1, 0.0], [5, -0.2, 0.2, 0.1]]
+    scorer = ReplicaScorer(model, 0)
+    qp = {"alpha": 0.0, "beta": 1.0, "dqn": True, "temperature": 700.0}
+    eng = model._engine_for(torch.device("cuda", 0))
+    got = scorer.score([dense, ok], [act, rb.get_action_space(ok, 3.528)], qp)
+    assert eng.check_status() == 0                                   # consumed by the automatic fallback
+    eng.set_option("tensor_cores", 0)
+    ref = scorer.score([dense, ok], [act, rb.get_action_space(ok, 3.528)], qp)
+    eng.set_option("tensor_cores", 1)
+    assert np.isfinite(got[0]).all() and np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    assert np.abs(got[0]).max() > 1e6                                # the dense structure really is off the rails
+    alone = scorer.score([ok], [rb.get_action_space(ok, 3.528)], qp)   # the healthy replica on the tensor-core path
+    assert np.max(np.abs(alone[0] - got[1]) / np.maximum(np.abs(got[1]), 1.0)) < 1e-4
+
+
 # ----------------------------------------------------------------------------- T1: t_net forward
 
 def test_t_net_time_matches_fp64_oracle(model):
