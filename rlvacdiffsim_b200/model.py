@@ -375,8 +375,16 @@ class TNet(nn.Module, _EngineMixin):
         posc = pos.to(torch.float32).contiguous()
         row_ptr, col, shift, node_struct = eng.radius_graph(posc, cell, torch.from_numpy(inv).to(dev),
                                                             torch.from_numpy(img).to(dev), node_ptr)
-        q = eng.representation(batch["elems"].to(torch.int32).contiguous(), posc, cell, node_struct, row_ptr, col, shift,
-                               len(counts), node_ptr=node_ptr, max_struct_nodes=int(counts.max()))
+        Zc = batch["elems"].to(torch.int32).contiguous()
+        q = eng.representation(Zc, posc, cell, node_struct, row_ptr, col, shift, len(counts), node_ptr=node_ptr,
+                               max_struct_nodes=int(counts.max()))
+        if eng.check_status() & 1:        # operand outside the tensor-core split's range: fp32 SIMT kernels
+            eng.set_option("tensor_cores", 0)
+            try:
+                q = eng.representation(Zc, posc, cell, node_struct, row_ptr, col, shift, len(counts), node_ptr=node_ptr,
+                                       max_struct_nodes=int(counts.max()))
+            finally:
+                eng.set_option("tensor_cores", 1)
         G = len(counts)
         T = torch.as_tensor(batch["T"], dtype=torch.float32, device=dev).reshape(G).contiguous()
         defect = torch.as_tensor(batch["defect"], dtype=torch.float32, device=dev).reshape(G).contiguous()
