@@ -79,6 +79,32 @@ def test_edges_bit_exact_batched_mixed_sizes(engine):
     assert np.array_equal(node_struct.cpu().numpy(), np.repeat(np.arange(4), np.diff(ptr)))
 
 
+def test_edges_fuzz_bit_exact(engine):
+    """Randomised cells (cubic, orthorhombic, triclinic; heights from below the cutoff — several periodic images per pair —
+    to 3x the cutoff; 1..256 atoms; 1..12 structures per batch): the device CSR equals the oracle's edge list bit for bit."""
+    rng = np.random.RandomState(77)
+    for trial in range(16):
+        n_struct = int(rng.choice([1, 2, 5, 12]))
+        ps, cs, ptr = [], [], [0]
+        for _ in range(n_struct):
+            n = int(rng.choice([1, 2, 3, 17, 60, 128, 255, 256]))
+            kind = rng.randint(3)
+            L = rng.uniform(3.0, 15.0, 3) if kind else np.full(3, rng.uniform(3.0, 15.0))
+            cell = np.diag(L)
+            if kind == 2:
+                cell = cell + rng.uniform(-0.25, 0.25, (3, 3)) * L.min()
+            if n > 60:                                     # keep the edge lists test-sized
+                cell = cell * max(1.0, (n / 80.0) ** (1 / 3) * 9.0 / np.cbrt(abs(np.linalg.det(cell))))
+            ps.append(((rng.rand(n, 3) * 1.4 - 0.2) @ cell).astype(np.float32))      # some atoms outside the home cell
+            cs.append(cell)
+            ptr.append(ptr[-1] + n)
+        pos, cells, ptr = np.concatenate(ps), np.stack(cs), np.asarray(ptr, dtype=np.int32)
+        row_ptr, col, shift, node_struct = _device_graph(engine, pos, cells.astype(np.float32), ptr)
+        o_ptr, o_col, o_shift = batched_radius_graph(pos, cells, ptr.astype(np.int64), 5.0)
+        assert np.array_equal(row_ptr.cpu().numpy(), o_ptr), trial
+        assert np.array_equal(col.cpu().numpy(), o_col) and np.array_equal(shift.cpu().numpy(), o_shift), trial
+
+
 def test_edges_config3_digest(engine):
     g = load_gold("syn2040_v8")
     pos = g["positions"].astype(np.float32)
