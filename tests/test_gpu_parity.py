@@ -210,6 +210,36 @@ def test_q_values_match_fp64_oracle(model, name, tag):
     assert int(np.argmax(out["rl_q"])) == int(g[f"{tag}.argmax"])
 
 
+def test_q_values_fuzz_against_oracles(model):
+    """Fresh random cases every one of which runs BOTH oracles here (fp64 as the reference, fp32 eager as the noise
+    yardstick): random supercell sizes / compositions / thermal jitter / q_params / temperatures / replica counts, live
+    enumerator.  Same bars as the golden cases."""
+    rng = np.random.RandomState(314)
+    m64 = PaiNNOracle.load(os.path.join(GOLD, "model_trained"), dtype=torch.float64)
+    m32 = PaiNNOracle.load(os.path.join(GOLD, "model_trained"), dtype=torch.float32)
+    scorer = ReplicaScorer(model, 0)
+    for trial in range(6):
+        n_rep = int(rng.choice([1, 2, 3]))
+        reps = [make_crconi_supercell(int(rng.choice([2, 3])), seed=int(rng.randint(10 ** 6)), jitter=float(rng.choice([0.0, 0.03, 0.08])))
+                for _ in range(n_rep)]
+        spaces = [rb.get_action_space(r, 3.528) for r in reps]
+        qp = [{"alpha": 0.0, "beta": 1.0, "dqn": True}, {"alpha": 1.0, "beta": 0.0, "dqn": False},
+              {"alpha": 0.5, "beta": 0.5, "dqn": True}][trial % 3]
+        qp = dict(qp, temperature=float(rng.choice([300.0, 700.0, 1200.0])))
+        got = scorer.score(reps, spaces, qp)
+        for r in range(n_rep):
+            Z, pR, pP, cells, ptr = build_reaction_batch(reps[r].numbers, reps[r].positions, reps[r].cell, spaces[r])
+            with torch.no_grad():
+                ref = m64.reaction_forward(Z, pR, pP, cells, ptr, qp)["rl_q"].numpy()
+                eag = m32.reaction_forward(Z, pR, pP, cells, ptr, qp)["rl_q"].numpy()
+            scale = np.maximum(np.abs(ref), 1.0)
+            err, eager = np.max(np.abs(got[r] - ref) / scale), np.max(np.abs(eag - ref) / scale)
+            assert err <= max(TOL, HEAD_SLACK * eager), (trial, r, err, eager)
+            gap = np.sort(ref)[-1] - np.sort(ref)[-2]
+            if gap > 1e-3 * max(1.0, abs(ref).max()):
+                assert int(np.argmax(got[r])) == int(np.argmax(ref))
+
+
 def test_bitwise_determinism_and_dedup_equivalence(model):
     g = load_gold("syn255_s2_jitter")
     a = _score_batch(model, g, "lss700")
