@@ -613,6 +613,36 @@ def test_device_lss_steps_match_host_loop(model):
         np.testing.assert_array_equal(lss.positions(), np.stack([h.positions for h in host]))   # fp64 state: bit-identical
 
 
+def test_device_lss_long_trajectory_matches_host_loop(model):
+    """60 consecutive hops of 3 replicas (the vacancy wanders, atoms leave the home cell and come back through the
+    periodic boundary): the device-resident loop and the reference-shaped host loop pick the same hop every step and
+    end in bit-identical fp64 states."""
+    from rlvacdiffsim_b200.simulator import DeviceLSS
+    from rlvacdiffsim_b200.structures import apply_action
+    qp = {"alpha": 0.0, "beta": 1.0, "dqn": True}
+    host = [make_crconi_supercell(3, seed=90 + s, jitter=0.0) for s in range(3)]
+    lss = DeviceLSS(model, host, 0, 3.528, 1, qp)
+    scorer = ReplicaScorer(model, 0)
+    T, H = 60000.0, 60                                       # kT = 5 eV: a nearly uniform policy, so the vacancy diffuses
+    u = np.random.RandomState(21).random_sample((H, 3))
+    res = lss.run(H, T, mode="lss", uniforms=u)
+    moved = set()
+    for t in range(H):
+        spaces = [rb.get_action_space(h, 3.528) for h in host]
+        q_host = scorer.score(host, spaces, dict(qp, temperature=T))
+        for r in range(3):
+            assert np.array_equal(np.asarray(res["Q"][r][t], dtype=np.float32), q_host[r]), (t, r)
+            z = torch.from_numpy(q_host[r]) / (T * 8.617e-5)
+            p = torch.softmax(z, dim=0).numpy().astype(np.float64)
+            cdf = np.cumsum(p); cdf /= cdf[-1]
+            pick = int(np.searchsorted(cdf, u[t, r], side="right"))
+            assert res["actions"][r][t] == pick, (t, r)
+            moved.add((r, int(spaces[r][pick][0])))
+            host[r] = apply_action(host[r], spaces[r][pick])
+    assert len(moved) > 20                                   # many different atoms hopped: the vacancy really travelled
+    np.testing.assert_array_equal(lss.positions(), np.stack([h.positions for h in host]))
+
+
 def test_device_tks_run_clock_and_writer(model, tmp_path):
     """DeviceLSS.run(mode="tks"): residence-time clock t += 1e-6 / sum(exp(Q/kT)) (simulator.py:262-265), tracked
     coordinates of the last atom, and the buffered writer, against the host loop on the same draws."""
