@@ -277,6 +277,27 @@ def main():
                      "structures_per_step_per_gpu": len(pk2["node_ptr"]) - 1, "max_rel_diff_vs_headline_rl_q": rel}
         del d2
 
+    # latency regime: ONE replica's 12 candidates per call — the reference's own deployment shape (deploy.py:75-94 steps
+    # a single replica serially); small batches take the split pack / readout kernels.  Extra object, never the headline.
+    one = pack_replicas(reps[:1], spaces[:1])
+    inv1, img1 = cell_geometry(one["cells"], eng.cutoff)
+    d1 = {"Z": torch.from_numpy(one["Z"].astype(np.int32)).to(dev), "pos": torch.from_numpy(one["pos"]).to(dev),
+          "cell": torch.from_numpy(one["cells"].astype(np.float32)).to(dev), "inv": torch.from_numpy(inv1).to(dev),
+          "img": torch.from_numpy(img1).to(dev), "ptr": torch.from_numpy(one["node_ptr"]).to(dev),
+          "rs": torch.from_numpy(one["react_struct"]).to(dev), "ps": torch.from_numpy(one["prod_struct"]).to(dev)}
+    mx1 = int(np.diff(one["node_ptr"]).max())
+
+    def step_one():
+        return eng.score_device(d1["Z"], d1["pos"], d1["cell"], d1["inv"], d1["img"], d1["ptr"], d1["rs"], d1["ps"], qp,
+                                max_struct_nodes=mx1)
+    for _ in range(5):
+        step_one()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        step_one()["rl_q"].cpu()
+    ms_one = (time.perf_counter() - t0) * 1e3 / 20
+
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -338,6 +359,9 @@ def main():
                                   "gather_bytes_per_launch": smem_bytes,
                                   "peak_source": "128 B/clk/SM x SMs x sampled SM clock"}},
             "dedup": dedup_obj,
+            "single_replica": {"what": "one 255-atom replica, 12 candidate hops per call (24 structures), device-resident inputs, "
+                                       "Q-values read back to the host every call (rank 0 wall clock)",
+                               "ms_per_call": ms_one, "value": len(one["react_struct"]) / (ms_one * 1e-3), "unit": "Q-evals/s"},
             "device_lss": {"what": "one full LSS step of every replica on the device: rlvd_action_space -> expand -> K1..K5 -> "
                                    "softmax/draw -> apply, fp64 state resident in HBM, one 8-byte D2H per step",
                            "ms_per_step": ms_lss, "value": world * n_q / (ms_lss * 1e-3), "unit": "Q-evals/s (rank 0 wall clock)",
