@@ -175,7 +175,9 @@ __global__ void __launch_bounds__(NB_THREADS) neighbor_kernel(
     int* __restrict__ row_ptr,       // count: out structure-local offsets; fill: in global offsets
     int* __restrict__ node_struct,   // count only
     int* __restrict__ struct_edges,  // count only
-    int* __restrict__ col, int8_t* __restrict__ shift, long long cap) {
+    int* __restrict__ col, int8_t* __restrict__ shift, long long cap,
+    int n_splits,                    // small batches: blockIdx.y takes every n_splits-th group of receivers
+    int mode) {                      // count: 0 = degrees + per-structure scan, 1 = degrees only, 2 = scan only
     extern __shared__ float smem_f[];
     __shared__ int warp_sums[NB_THREADS / 32 + 1];
     const int g = blockIdx.x;
@@ -185,6 +187,11 @@ __global__ void __launch_bounds__(NB_THREADS) neighbor_kernel(
     CellC C;
     load_cell(C, cell, inv, img, g);
 
+    if (!FILL && mode == 2) {          // degrees are in row_ptr (mode 1): structure-local exclusive scan in place
+        const int total = block_excl_scan_inplace(row_ptr + node0, n, warp_sums);
+        if (tid == 0) struct_edges[g] = total;
+        return;
+    }
     const bool staged = n <= MAX_SMEM_ATOMS;
     const float* P = pos + 3 * (int64_t)node0;
     int* deg = nullptr;
@@ -195,15 +202,16 @@ __global__ void __launch_bounds__(NB_THREADS) neighbor_kernel(
     }
     __syncthreads();
 
-    for (int i = wid; i < n; i += nw) {
+    const bool to_global = !staged || mode == 1;
+    for (int i = wid + nw * (int)blockIdx.y; i < n; i += nw * n_splits) {
         const int row_start = FILL ? row_ptr[node0 + i] : 0;
         const int d = sweep_receiver<FILL>(C, P, n, i, lane, rc2, node0, row_start, col, shift, cap);
         if (!FILL && lane == 0) {
-            if (staged) deg[i] = d; else row_ptr[node0 + i] = d;
+            if (to_global) row_ptr[node0 + i] = d; else deg[i] = d;
             node_struct[node0 + i] = g;
         }
     }
-    if (FILL) return;
+    if (FILL || mode == 1) return;
     __syncthreads();
     int* vals = staged ? deg : (row_ptr + node0);
     const int total = block_excl_scan_inplace(vals, n, warp_sums);
@@ -254,6 +262,8 @@ __global__ void row_ptr_final_kernel(int n_nodes, const int* __restrict__ node_s
     if (i == n_nodes) row_ptr[n_nodes] = struct_edge_ptr[n_struct];
 }
 
+int neighbor_splits(int n_struct) { return n_struct >= 296 ? 1 : std::min(8, (592 + n_struct - 1) / n_struct); }
+
 size_t neighbor_smem() { return (size_t)MAX_SMEM_ATOMS * 3 * sizeof(float) + (size_t)MAX_SMEM_ATOMS * sizeof(int); }
 
 }  // namespace
@@ -278,14 +288,24 @@ int launch_neighbor_count(rlvd_engine* e, cudaStream_t s, int n_struct, int n_no
     const float rc = cutoff;
     const float rc2 = rc * rc;  // fp32 product, as in the oracle
     Span sp(e, s, FAM_NEIGHBOR);
-    neighbor_kernel<false><<<n_struct, NB_THREADS, neighbor_smem(), s>>>(
-        n_struct, node_ptr, pos, cell, inv, img, rc2, row_ptr, node_struct, e->struct_edges.as<int>(), nullptr,
-        nullptr, 0);
+    const int n_splits = neighbor_splits(n_struct);
+    if (n_splits == 1) {
+        neighbor_kernel<false><<<n_struct, NB_THREADS, neighbor_smem(), s>>>(
+            n_struct, node_ptr, pos, cell, inv, img, rc2, row_ptr, node_struct, e->struct_edges.as<int>(), nullptr,
+            nullptr, 0, 1, 0);
+    } else {                           // few structures: spread each one's receivers over several CTAs, then scan
+        neighbor_kernel<false><<<dim3(n_struct, n_splits), NB_THREADS, neighbor_smem(), s>>>(
+            n_struct, node_ptr, pos, cell, inv, img, rc2, row_ptr, node_struct, e->struct_edges.as<int>(), nullptr,
+            nullptr, 0, n_splits, 1);
+        neighbor_kernel<false><<<n_struct, NB_THREADS, neighbor_smem(), s>>>(
+            n_struct, node_ptr, pos, cell, inv, img, rc2, row_ptr, node_struct, e->struct_edges.as<int>(), nullptr,
+            nullptr, 0, 1, 2);
+    }
     struct_scan_kernel<<<1, 1024, 0, s>>>(n_struct, e->struct_edges.as<int>(), e->struct_edge_ptr.as<int>(),
                                            n_edges);
     row_ptr_final_kernel<<<(n_nodes + 1 + 255) / 256, 256, 0, s>>>(n_nodes, node_struct,
                                                                    e->struct_edge_ptr.as<int>(), n_struct, row_ptr);
-    sp.end(3);
+    sp.end(n_splits == 1 ? 3 : 4);
     RLVD_CUDA(cudaGetLastError());
     return 0;
 }
@@ -297,8 +317,10 @@ int launch_neighbor_fill(rlvd_engine* e, cudaStream_t s, int n_struct, int n_nod
     const float rc = cutoff;
     const float rc2 = rc * rc;
     Span sp(e, s, FAM_NEIGHBOR);
-    neighbor_kernel<true><<<n_struct, NB_THREADS, neighbor_smem(), s>>>(
-        n_struct, node_ptr, pos, cell, inv, img, rc2, const_cast<int*>(row_ptr), nullptr, nullptr, col, shift, (long long)cap);
+    const int n_splits = neighbor_splits(n_struct);
+    neighbor_kernel<true><<<dim3(n_struct, n_splits), NB_THREADS, neighbor_smem(), s>>>(
+        n_struct, node_ptr, pos, cell, inv, img, rc2, const_cast<int*>(row_ptr), nullptr, nullptr, col, shift, (long long)cap,
+        n_splits, 0);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;
