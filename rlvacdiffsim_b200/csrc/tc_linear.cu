@@ -171,27 +171,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
         uint32_t acc_it = 0, ph_it = 0;
         bool bad = false;                                    // an operand left the fp16-split range (engine status bit 0)
         if (blockIdx.x < n_tiles) stage_A_async(a, blockIdx.x, 0, ast, t);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int phase = 0; phase < NPH; ++phase, ++ph_it) {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                mbar_wait(&S->a_free, (ph_it & 1) ^ 1);      // MMAs that read the previous A phase have retired
-                epi_barrier();                               // everyone's cp.async data is visible
+        // One A phase: fp32 staging (cp.async, issued one phase ahead) -> fp16 hi/lo operand buffers, then prefetch the next.
+        auto convert_phase = [&](int tl, int phase) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            mbar_wait(&S->a_free, (ph_it & 1) ^ 1);          // MMAs that read the previous A contents have retired
+            epi_barrier();                                   // everyone's cp.async data is visible
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int kc = khalf * 8 + c;
-                    const float4 v0 = *reinterpret_cast<const float4*>(Ast + r * 512 + (((2 * kc) ^ (r & 7)) << 4));
-                    const float4 v1 = *reinterpret_cast<const float4*>(Ast + r * 512 + (((2 * kc + 1) ^ (r & 7)) << 4));
-                    uint4 H, L;
-                    split8(v0, v1, H, L, bad);
-                    *reinterpret_cast<uint4*>(A_hi + kc * CORE_LBO + row_off) = H;
-                    *reinterpret_cast<uint4*>(A_lo + kc * CORE_LBO + row_off) = L;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores → UMMA
-                mbar_arrive(&S->a_ready);
-                epi_barrier();                               // staging fully consumed → prefetch the next phase
-                if (phase + 1 < NPH) stage_A_async(a, tile, phase + 1, ast, t);
-                else if (tile + (int)gridDim.x < n_tiles) stage_A_async(a, tile + gridDim.x, 0, ast, t);
+            for (int c = 0; c < 8; ++c) {
+                const int kc = khalf * 8 + c;
+                const float4 v0 = *reinterpret_cast<const float4*>(Ast + r * 512 + (((2 * kc) ^ (r & 7)) << 4));
+                const float4 v1 = *reinterpret_cast<const float4*>(Ast + r * 512 + (((2 * kc + 1) ^ (r & 7)) << 4));
+                uint4 H, L;
+                split8(v0, v1, H, L, bad);
+                *reinterpret_cast<uint4*>(A_hi + kc * CORE_LBO + row_off) = H;
+                *reinterpret_cast<uint4*>(A_lo + kc * CORE_LBO + row_off) = L;
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores → UMMA
+            mbar_arrive(&S->a_ready);
+            epi_barrier();                                   // staging fully consumed → prefetch the next phase
+            if (phase + 1 < NPH) stage_A_async(a, tl, phase + 1, ast, t);
+            else if (tl + (int)gridDim.x < n_tiles) stage_A_async(a, tl + gridDim.x, 0, ast, t);
+            ++ph_it;
+        };
+        // Schedule: the first A phase of tile t+1 is converted BEFORE the last N-block epilogue of tile t, so the MMAs of
+        // tile t+1 run underneath that epilogue instead of the epilogue warps idling on them afterwards (the MMA and
+        // producer warps keep their program order; every barrier still sees its events in the same sequence).
+        bool pre = false;                                    // phase 0 of the current tile is already in the operand buffers
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int phase = pre ? 1 : 0; phase < NPH; ++phase) convert_phase(tile, phase);
+            pre = false;
             if (a.mixred) {
                 // ---- V (block 0) and W (block 1) of this tile -> nrm, vw per node; only W is stored
                 const uint32_t bV = acc_it & 1, bW = bV ^ 1;
@@ -307,6 +315,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
             const float* bias_o = two ? bias2_s : bias_s;
             const int act_o = two ? a.act2 : a.act;
             for (int nb = 0; nb < NBo; ++nb, ++acc_it) {
+                if (nb == NBo - 1 && tile + (int)gridDim.x < n_tiles) {
+                    convert_phase(tile + gridDim.x, 0);
+                    pre = true;
+                }
                 const uint32_t buf = acc_it & 1;
                 mbar_wait(&S->acc_full[buf], (acc_it >> 1) & 1);
                 tc_fence_after();
