@@ -322,40 +322,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                 const uint32_t buf = acc_it & 1;
                 mbar_wait(&S->acc_full[buf], (acc_it >> 1) & 1);
                 tc_fence_after();
-#pragma unroll 1
-                for (int sgm = 0; sgm < 2; ++sgm) {
+                // four quarter-steps (column segment sgm, 16-lane half hl); the TMEM loads of step i+1 are in flight while
+                // step i is combined and stored (a load + wait costs 250-650 cycles, as much as the stores it feeds)
+                const int u = lane & 3, rq = lane >> 2;
+                uint32_t dd[2][32];                          // [ping-pong][d0 (16) | d1 (16)]
+                {
+                    const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + 32 * h;
+                    tmem_ld_16x256b_x4(t0, dd[0]);
+                    tmem_ld_16x256b_x4(t0 + 128, dd[0] + 16);
+                }
+#pragma unroll
+                for (int st = 0; st < 4; ++st) {
+                    const int sgm = st >> 1, hl = st & 1;
                     const int c0 = 64 * sgm + 32 * h;        // first column (inside the N-block) of this warp's segment
                     const int col0 = nb * TC_N + c0;
-                    const int u = lane & 3, rq = lane >> 2;
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (st < 3) {
+                        const int sg2 = (st + 1) >> 1, hl2 = (st + 1) & 1;
+                        const uint32_t t1 = tmem + ((uint32_t)(q * 32 + 16 * hl2) << 16) + buf * 256 + 64 * sg2 + 32 * h;
+                        tmem_ld_16x256b_x4(t1, dd[(st + 1) & 1]);
+                        tmem_ld_16x256b_x4(t1 + 128, dd[(st + 1) & 1] + 16);
+                    } else {                                 // all TMEM reads of this accumulator are done
+                        tc_fence_before();
+                        mbar_arrive(&S->acc_empty[buf]);
+                    }
+                    const uint32_t* d0 = dd[st & 1];
+                    const uint32_t* d1 = dd[st & 1] + 16;
                     float2 bb[4];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) bb[g] = *reinterpret_cast<const float2*>(bias_o + col0 + 8 * g + 2 * u);
 #pragma unroll
-                    for (int hl = 0; hl < 2; ++hl) {         // the two 16-lane halves of this warp's TMEM quarter
-                        const uint32_t t0 = tmem + ((uint32_t)(q * 32 + 16 * hl) << 16) + buf * 256 + c0;
-                        uint32_t d0[16], d1[16];
-                        tmem_ld_16x256b_x4(t0, d0);
-                        tmem_ld_16x256b_x4(t0 + 128, d1);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (sgm == 1 && hl == 1) {           // all TMEM reads of this accumulator are done
-                            tc_fence_before();
-                            mbar_arrive(&S->acc_empty[buf]);
-                        }
+                    for (int rh = 0; rh < 2; ++rh) {
+                        const int64_t m = (int64_t)tile * TC_M + q * 32 + 16 * hl + 8 * rh + rq;
+                        float* yrow = a.Y + m * a.ldy + col0 + 2 * u;
 #pragma unroll
-                        for (int rh = 0; rh < 2; ++rh) {
-                            const int64_t m = (int64_t)tile * TC_M + q * 32 + 16 * hl + 8 * rh + rq;
-                            float* yrow = a.Y + m * a.ldy + col0 + 2 * u;
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                float v0 = fmaf(__uint_as_float(d1[4 * g + 2 * rh]), 1.0f / 2048.0f, __uint_as_float(d0[4 * g + 2 * rh])) + bb[g].x;
-                                float v1 = fmaf(__uint_as_float(d1[4 * g + 2 * rh + 1]), 1.0f / 2048.0f, __uint_as_float(d0[4 * g + 2 * rh + 1])) + bb[g].y;
-                                if (act_o == 1) {            // SiLU; |error| < 2e-7 of max(|v|, 1)
-                                    v0 = __fdividef(v0, 1.0f + __expf(-v0));
-                                    v1 = __fdividef(v1, 1.0f + __expf(-v1));
-                                }
-                                // the four threads of a row write 32 contiguous bytes: one full sector per row, no staging
-                                if (m < a.M) *reinterpret_cast<float2*>(yrow + 8 * g) = make_float2(v0, v1);
+                        for (int g = 0; g < 4; ++g) {
+                            float v0 = fmaf(__uint_as_float(d1[4 * g + 2 * rh]), 1.0f / 2048.0f, __uint_as_float(d0[4 * g + 2 * rh])) + bb[g].x;
+                            float v1 = fmaf(__uint_as_float(d1[4 * g + 2 * rh + 1]), 1.0f / 2048.0f, __uint_as_float(d0[4 * g + 2 * rh + 1])) + bb[g].y;
+                            if (act_o == 1) {                // SiLU; |error| < 2e-7 of max(|v|, 1)
+                                v0 = __fdividef(v0, 1.0f + __expf(-v0));
+                                v1 = __fdividef(v1, 1.0f + __expf(-v1));
                             }
+                            // the four threads of a row write 32 contiguous bytes: one full sector per row, no staging
+                            if (m < a.M) *reinterpret_cast<float2*>(yrow + 8 * g) = make_float2(v0, v1);
                         }
                     }
                 }
