@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--replicas-per-gpu", type=int, default=REPLICAS_PER_GPU)
     ap.add_argument("--jitter", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (experiments), e.g. --opt fuse_update=1")
     ap.add_argument("--dedup", action="store_true", help="share the reactant pass between a replica's candidates")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -158,6 +159,9 @@ def main():
 
     model = rb.registry.get_model_class("dqn_v2").load(CKPT).to(dev).eval()
     eng = model._engine_for(dev)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     eng_sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     n_rep = args.replicas_per_gpu
     reps, spaces = make_shard(rank, n_rep, args.jitter)
