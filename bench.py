@@ -334,6 +334,19 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("edge_stream_bytes_per_launch")
         except Exception:
             pass
+        # measured DRAM traffic of each kernel family (ncu, committed under profiles/) over its live time this run: which
+        # families sit on the HBM roofline and which are bound elsewhere (edge: shared-memory crossbar; readout: FMA)
+        dram_by_family = None
+        try:
+            tb = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["dram_bytes_per_step_by_family"]
+            dram_by_family = {}
+            for k in ("neighbor", "edge_pack", "edge", "node", "readout"):
+                ms_k = fam[k][0] / max(prof_steps, 1)
+                if ms_k > 0 and n_rep == REPLICAS_PER_GPU:
+                    gbs = tb[k] / (ms_k * 1e-3) / 1e9
+                    dram_by_family[k] = {"GB_per_step": tb[k] / 1e9, "GB/s": gbs, "frac_of_peak": gbs / hbm_peak}
+        except Exception:
+            pass
         total_prof = sum(v[0] for v in fam.values())
         value = world * n_q * args.steps / (ms_dev * 1e-3)
         e2e = world * n_q * args.steps / (ms_e2e * 1e-3)
@@ -362,6 +375,7 @@ def main():
                                   "frac": smem_achieved / smem_peak if smem_peak else None,
                                   "gather_bytes_per_launch": smem_bytes,
                                   "peak_source": "128 B/clk/SM x SMs x sampled SM clock"}},
+            "dram_by_family": dram_by_family,
             "dedup": dedup_obj,
             "single_replica": {"what": "one 255-atom replica, 12 candidate hops per call (24 structures), device-resident inputs, "
                                        "Q-values read back to the host every call (rank 0 wall clock)",
