@@ -143,12 +143,9 @@ class Trainer:
                 q_values.append(model(batch, q_params=self.q_params)["rl_q"].detach())
         return torch.max(torch.cat(q_values, dim=0))
 
-    def dqn_update(self, memory_l, gamma, episode_size, num_epoch, batch_size=8, device="cuda") -> float:
-        if self.train_all:
-            raise NotImplementedError(
-                "dqn_update with train_all=True back-propagates through the PaiNN representation (rlsim/drl/trainer.py:"
-                "163-177), which has no sm_100a kernels in this build; construct Trainer(..., train_all=False) to train "
-                "the DQN heads on the device")
+    # ---- the three stages of trainer.py:119-160, split out: target-net sync, replay sampling, TD targets
+    def _sync_target(self, device) -> None:
+        """``target_net.load_state_dict(policy.state_dict())``; eval / train modes and device placement (trainer.py:120-124)."""
         if self.target_net is None:
             self.target_net = copy.deepcopy(self.policy_value_net)
         self.target_net.load_state_dict(self.policy_value_net.state_dict())
@@ -156,28 +153,46 @@ class Trainer:
         self.target_net.to(device)
         self.policy_value_net.train()
         self.policy_value_net.to(device)
+
+    @staticmethod
+    def _sample_transitions(memory_l, episode_size):
+        """Episodes drawn with p ∝ 0.99**age (with replacement, trainer.py:126-127); every step but an episode's last
+        becomes (state, taken action row, next_state, reward, next action space) (trainer.py:135-146)."""
+        age_w = np.asarray([0.99 ** (len(memory_l) - i) for i in range(len(memory_l))])
+        picks = np.random.choice(range(len(memory_l)), size=episode_size, p=age_w / np.sum(age_w))
+        out = []
+        for u in picks:
+            mem = memory_l[u]
+            n = len(mem.act_space)
+            for i in range(n - 1):
+                out.append((mem.states[i], mem.act_space[i][mem.actions[i]], mem.next_states[i], mem.rewards[i],
+                            mem.act_space[i + 1]))
+        return out
+
+    def _td_targets(self, transitions, gamma, device):
+        """``next_Q * gamma + reward`` with ``next_Q = max_a Q_target(next_state, a)`` (trainer.py:147-157), fp32 tensors."""
+        rewards = torch.tensor([tr[3] for tr in transitions], dtype=torch.float)
+        next_q = torch.zeros(len(transitions))
+        for i, (_, _, nxt, _, nxt_space) in enumerate(transitions):
+            next_q[i] = self.get_max_Q(self.target_net, nxt, nxt_space, device=device)
+        return [next_q[i] * gamma + rewards[i] for i in range(len(transitions))]
+
+    def dqn_update(self, memory_l, gamma, episode_size, num_epoch, batch_size=8, device="cuda") -> float:
+        if self.train_all:
+            raise NotImplementedError(
+                "dqn_update with train_all=True back-propagates through the PaiNN representation (rlsim/drl/trainer.py:"
+                "163-177), which has no sm_100a kernels in this build; construct Trainer(..., train_all=False) to train "
+                "the DQN heads on the device")
+        self._sync_target(device)
+        transitions = self._sample_transitions(memory_l, episode_size)
+        targets = self._td_targets(transitions, gamma, device)
+        graphs = []
+        for (state, taken, _, _, _), y in zip(transitions, targets):
+            for data in convert(state, [taken]):
+                data.rl_q = y
+                graphs.append(data)
+        q_dataloader = DataLoader(ReactionDataset(graphs), batch_size=batch_size, shuffle=False)
         losses = AverageMeter()
-        prob = [0.99 ** (len(memory_l) - i) for i in range(len(memory_l))]
-        randint = np.random.choice(range(len(memory_l)), size=episode_size, p=prob / np.sum(prob))
-        states, next_states, taken_actions, rewards, next_aspace = [], [], [], [], []
-        for u in randint:
-            memory = memory_l[u]
-            states += memory.states[:-1]
-            next_states += memory.next_states[:-1]
-            rewards += memory.rewards[:-1]
-            aspace, actions = memory.act_space, memory.actions
-            taken_actions += [[aspace[i][actions[i]]] for i in range(len(aspace) - 1)]
-            next_aspace += [aspace[i] for i in range(1, len(aspace))]
-        rewards = torch.tensor(rewards, dtype=torch.float)
-        next_Q = torch.zeros(len(next_aspace))
-        for i, state in enumerate(next_states):
-            next_Q[i] = self.get_max_Q(self.target_net, state, next_aspace[i], device=device)
-        dataset_list = []
-        for i, state in enumerate(states):
-            for data in convert(state, taken_actions[i]):
-                data.rl_q = next_Q[i] * gamma + rewards[i]
-                dataset_list.append(data)
-        q_dataloader = DataLoader(ReactionDataset(dataset_list), batch_size=batch_size, shuffle=False)
         dev = torch.device(device) if not isinstance(device, torch.device) else device
         if dev.type == "cuda" and dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
