@@ -76,6 +76,7 @@ class Engine:
         self.means: Dict[str, float] = {}
         self.stddevs: Dict[str, float] = {}
         self._pinned: Dict[str, torch.Tensor] = {}
+        self._geom_cache = None
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -350,7 +351,15 @@ class Engine:
                    temperature: Optional[np.ndarray] = None) -> Dict[str, np.ndarray]:
         """H2D + K1..K5 + D2H in one C call (``rlvd_score_reactions_host``); inputs are numpy arrays."""
         n_struct, M, G = len(node_ptr) - 1, int(node_ptr[-1]), len(react_struct)
-        inv, img = cell_geometry(cells, self.cutoff)
+        # cells rarely change between calls (LSS / TKS keep the box fixed): reuse the inverse cells / image ranges when the
+        # bytes are the same as last time
+        c64 = np.ascontiguousarray(cells, dtype=np.float64)
+        key = (c64.shape, c64.tobytes())
+        if self._geom_cache is not None and self._geom_cache[0] == key:
+            inv, img = self._geom_cache[1]
+        else:
+            inv, img = cell_geometry(c64, self.cutoff)
+            self._geom_cache = (key, (inv, img))
         h = {
             "node_ptr": self._pin("node_ptr", np.asarray(node_ptr, dtype=np.int32)),
             "Z": self._pin("Z", np.asarray(Z, dtype=np.int32)),
