@@ -201,9 +201,6 @@ __device__ __forceinline__ void edge_embedding(float d, float f1, const float* _
     v[NRBF] = fc;
 }
 
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
 
 // Writes slot `r` of the tile at `tile`: operand row (8 x 16 B, one per core column) and meta.
 __device__ __forceinline__ void write_slot(uint8_t* tile, int r, const uint4* row8, int j, float dx, float dy, float dz) {
@@ -381,23 +378,38 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
                     for (int k = 0; k < NK; ++k) rec[k] = v[k];
                     wsd[at] = make_float4(rx * inv_d, ry * inv_d, rz * inv_d, 1.0f);
                 }
-                __half hi[NK + 1], lo[NK + 1];
+                // k' = 0..20 hi | 21..41 lo | 42..62 hi | 63 zero, two fp16 per 32-bit word; converted pairwise (one
+                // cvt.rn.f16x2.f32 per word): words 0-9 (hi,hi), 10 (hi20, lo0), 11-20 (lo,lo), 21-30 = words 0-9, 31 (hi20, 0).
+                // Same values as hi = fp16(sv), lo = fp16(sv - float(hi)) computed one by one.
+                float sv[NK], lf[NK];
 #pragma unroll
-                for (int k = 0; k < NK; ++k) {
-                    const float sv = v[k] * bscale;
-                    hi[k] = __float2half_rn(sv);
-                    lo[k] = __float2half_rn(sv - __half2float(hi[k]));
+                for (int k = 0; k < NK; ++k) sv[k] = v[k] * bscale;
+                uint32_t wd[32];
+#pragma unroll
+                for (int w = 0; w < 10; ++w) {
+                    const __half2 h2 = __floats2half2_rn(sv[2 * w], sv[2 * w + 1]);
+                    const float2 f = __half22float2(h2);
+                    lf[2 * w] = sv[2 * w] - f.x;
+                    lf[2 * w + 1] = sv[2 * w + 1] - f.y;
+                    wd[w] = *reinterpret_cast<const uint32_t*>(&h2);
+                    wd[21 + w] = wd[w];
                 }
-                // k' = 0..20 hi | 21..41 lo | 42..62 hi | 63 zero
-                __half kk[KH];
+                const float h20 = __half2float(__float2half_rn(sv[NK - 1]));
+                lf[NK - 1] = sv[NK - 1] - h20;
+                {
+                    const __half2 m = __floats2half2_rn(sv[NK - 1], lf[0]);
+                    const __half2 z = __floats2half2_rn(sv[NK - 1], 0.f);
+                    wd[10] = *reinterpret_cast<const uint32_t*>(&m);
+                    wd[31] = *reinterpret_cast<const uint32_t*>(&z);
+                }
 #pragma unroll
-                for (int k = 0; k < NK; ++k) { kk[k] = hi[k]; kk[NK + k] = lo[k]; kk[2 * NK + k] = hi[k]; }
-                kk[KH - 1] = __float2half_rn(0.f);
+                for (int i = 0; i < 10; ++i) {
+                    const __half2 l2 = __floats2half2_rn(lf[2 * i + 1], lf[2 * i + 2]);
+                    wd[11 + i] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
                 uint4 row8[8];
 #pragma unroll
-                for (int kc = 0; kc < 8; ++kc)
-                    row8[kc] = make_uint4(pack_h2(kk[8 * kc], kk[8 * kc + 1]), pack_h2(kk[8 * kc + 2], kk[8 * kc + 3]),
-                                          pack_h2(kk[8 * kc + 4], kk[8 * kc + 5]), pack_h2(kk[8 * kc + 6], kk[8 * kc + 7]));
+                for (int kc = 0; kc < 8; ++kc) row8[kc] = make_uint4(wd[4 * kc], wd[4 * kc + 1], wd[4 * kc + 2], wd[4 * kc + 3]);
                 write_slot(tile, r, row8, jg - node0, rx * inv_d, ry * inv_d, rz * inv_d);
             } else {
                 uint4 row8[8];
