@@ -130,6 +130,13 @@ class _EngineMixin:
 
     head_spec: HeadSpec = HEAD_SPEC_V0
 
+    def __getstate__(self):
+        """``copy.deepcopy(model)`` / ``torch.save(model)`` after a forward: the per-device engines hold ctypes handles
+        (not picklable, and one ``rlvd_engine*`` must not get two owners), so they are dropped and rebuilt lazily."""
+        state = self.__dict__.copy()
+        state.pop("_engines", None)
+        return state
+
     def _engine_for(self, device: torch.device) -> Engine:
         engines = self.__dict__.setdefault("_engines", {})
         key = (device.type, device.index)

@@ -25,6 +25,14 @@ from .structures import Atoms, apply_action
 KB_EV = 8.617 * 10 ** -5   # simulator.py:40
 
 
+def sample_from_q(Q: torch.Tensor, temperature: float):
+    """``simulator.py:94-98``: fp32 ``softmax(Q / (T kb))`` then ``np.random.choice`` on the global numpy RNG.
+    Returns ``(index, action_probs)``; pinned against the reference's own lines by tests/test_ref_fixtures.py."""
+    action_probs = nn.Softmax(dim=0)(Q / (temperature * KB_EV))
+    p = action_probs.detach().cpu().numpy()
+    return np.random.choice(len(p), p=p), action_probs
+
+
 def convert_to_graph_list(atoms, actions: Sequence[Sequence[float]]) -> List[ReactionGraph]:
     """``simulator.py:439-460`` / ``trainer.py:185-205``: one reaction graph per candidate hop."""
     return [ReactionGraph.from_ase(atoms, apply_action(atoms, act)) for act in actions]
@@ -57,7 +65,7 @@ class RLSimulator:
                  sro_pixel=None, save_sro: bool = False, **kwargs):
         self.env = environment
         self.calculator = self.env.get_calculator(**self.env.calc_params) if hasattr(self.env, "get_calculator") else None
-        self.q_params = dict(q_params)
+        self.q_params = q_params        # the caller's dict itself, like simulator.py:33: a Trainer sharing it sees the temperature
         self.model = model
         self.device = self.env.calc_params["device"]
         self.kb = KB_EV
@@ -107,9 +115,7 @@ class RLSimulator:
             vt = torch.tensor(valid, device=Q.device, dtype=torch.long)
             Q = Q[vt]
             sro_list = torch.tensor(np.asarray(sros), device=Q.device)[vt]
-        action_probs = nn.Softmax(dim=0)(Q / (temperature * self.kb))
-        p = action_probs.detach().cpu().numpy()
-        action = np.random.choice(len(p), p=p)
+        action, action_probs = sample_from_q(Q, temperature)
         if valid is not None:
             action = valid[action]                             # simulator.py:99-101
         return action, action_probs, Q, sro_list
@@ -321,6 +327,8 @@ class DeviceLSS:
         ``uniforms[horizon, R]`` pins the draws.  Returns per-replica lists shaped like the reference's outputs."""
         if mode not in ("lss", "tks"):
             raise ValueError("DeviceLSS.run supports mode 'lss' and 'tks'")
+        if mode == "tks":
+            assert not self.q_params["dqn"], "TKS needs rates, not DQN Q-values (simulator.py:181)"
         R = self.R
         q_lists = [[] for _ in range(R)]
         act_lists = [[] for _ in range(R)]

@@ -120,7 +120,11 @@ class Trainer:
         self.lr = float(lr)
         self.q_params = q_params
         self._adam: Dict[tuple, dict] = {}          # Adam state of the DQN heads, per device (optim.Adam, trainer.py:43)
-        self.dropout = False                        # set True to apply the heads' train-mode dropout (numpy RNG uniforms)
+        # trainer.py:123 calls policy_value_net.train(): the DQN heads' Dropout(p = hyper['dropout_rate'], 0.15 in the
+        # bundled checkpoint) is ON during the update.  Same here by default (uniforms from the global numpy RNG — a
+        # different stream from torch's Philox, so masks differ from a torch run draw by draw, not in distribution);
+        # set ``trainer.dropout = False`` for deterministic runs / parity tests.
+        self.dropout = float(getattr(model, "hyper", {}).get("dropout_rate", 0.0)) > 0.0
 
     def update(self, memory_l, mode: str = "dqn", **kwargs) -> float:
         if mode == "dqn":

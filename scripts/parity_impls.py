@@ -19,7 +19,9 @@ IMPLS = {"stream": {"tensor_cores": 1, "sliced_edge": 1, "layer0_sums": 1},
          "tc_general": {"tensor_cores": 1, "sliced_edge": 0},
          "simt": {"tensor_cores": 0}}
 only = sys.argv[1:] or list(IMPLS)
-print(f"{'impl':12s} {'case':26s} " + " ".join(f"{k:>9s}" for k in ("delta_e", "q0", "q1", "rl_q")) + "   (eager32: same keys)")
+print("# per output: el = max |cuda - f64| / max(|f64|, 1) per element; b = max |cuda - f64| / max(1, max_batch |f64|)  "
+      "(delta_e's b is relative to max(|E_R|, |E_P|)); eager32 columns: the fp32 eager oracle under the same two norms")
+print(f"{'impl':12s} {'case':26s} " + " ".join(f"{k + ':el':>9s} {k + ':b':>9s}" for k in ("delta_e", "q0", "q1", "rl_q")) + "   | eager32: same keys")
 for impl in only:
     for k, v in IMPLS[impl].items():
         eng.set_option(k, v)
@@ -30,6 +32,7 @@ for impl in only:
         for k in ("delta_e", "q0", "q1", "rl_q"):
             ref = g[f"{tag}.f64.{k}"]
             scale = np.maximum(np.abs(ref), 1.0)
-            errs.append(np.max(np.abs(out[k] - ref) / scale))
-            eag.append(np.max(np.abs(g[f"{tag}.f32.{k}"] - ref) / scale))
+            sb = max(1.0, np.abs(ref).max()) if k != "delta_e" else max(1.0, np.abs(g[f"{tag}.f64.E_R"]).max(), np.abs(g[f"{tag}.f64.E_P"]).max())
+            errs += [np.max(np.abs(out[k] - ref) / scale), np.abs(out[k] - ref).max() / sb]
+            eag += [np.max(np.abs(g[f"{tag}.f32.{k}"] - ref) / scale), np.abs(g[f"{tag}.f32.{k}"] - ref).max() / sb]
         print(f"{impl:12s} {name + '/' + tag:26s} " + " ".join(f"{e:9.2e}" for e in errs) + "   " + " ".join(f"{e:9.2e}" for e in eag))

@@ -810,3 +810,73 @@ def test_trainer_dqn_update_heads_only(checkpoint_path):
         assert torch.equal(sd1[k], sd2[k]), k
         moved = not torch.equal(sd1[k], ref_sd[k].cpu())
         assert moved == k.startswith(("Q_emb.", "Q_output.")), k
+
+
+# ----------------------------------------------------------------------------- device kernels vs the REFERENCE's own outputs
+# tests/golden/ref_*.npz are minted by running rlsim/actions/action.py, rlsim/utils/sro.py and simulator.py:94-98
+# themselves (scripts/make_ref_fixtures.py): these tests compare the CUDA kernels with the reference, not a restatement.
+
+def _ref_cases():
+    ref = np.load(os.path.join(GOLD, "ref_actions_sro.npz"))
+    return ref, [str(n) for n in ref["names"]]
+
+
+def test_action_space_device_equals_reference_enumerator(engine):
+    """rlvd_action_space vs rlsim/actions/action.py:12-61 run unmodified: atom indices / order exact, displacements 1e-12."""
+    ref, names = _ref_cases()
+    live = [n for n in names if f"{n}.live" in ref.files]
+    reps = [Atoms(ref[f"{n}.numbers"], ref[f"{n}.positions"], ref[f"{n}.cell"]) for n in live]
+    for size in sorted({len(r) for r in reps}):                       # one launch per replica size (ragged batches too)
+        idx = [i for i, r in enumerate(reps) if len(r) == size]
+        got = rb.get_action_space_device(engine, [reps[i] for i in idx], 3.528)
+        for i, g in zip(idx, got):
+            want = ref[f"{live[i]}.live"]
+            g = np.asarray(g, dtype=np.float64)
+            assert g.shape == want.shape and np.array_equal(g[:, 0], want[:, 0]), live[i]
+            np.testing.assert_allclose(g[:, 1:], want[:, 1:], rtol=0, atol=1e-12)
+    got = rb.get_action_space_device(engine, reps, 3.528)             # all sizes in one ragged launch
+    for n, g in zip(live, got):
+        np.testing.assert_allclose(np.asarray(g), ref[f"{n}.live"], rtol=0, atol=1e-12)
+
+
+def test_sro_device_equals_reference(engine):
+    """rlvd_sro_counts + the fp64 formula vs rlsim/utils/sro.py:49-83 run unmodified: matrices exactly equal."""
+    from rlvacdiffsim_b200.sro import sro_device
+    from rlvacdiffsim_b200.structures import apply_action
+    ref, names = _ref_cases()
+    structs, want = [], []
+    for n in names:
+        at = Atoms(ref[f"{n}.numbers"], ref[f"{n}.positions"], ref[f"{n}.cell"])
+        structs.append(at); want.append(ref[f"{n}.sro"])
+        if f"{n}.sro_products" in ref.files:
+            acts = ref[f"{n}.live"] if f"{n}.live" in ref.files else ref[f"{n}.legacy"]
+            for act, m in zip(acts, ref[f"{n}.sro_products"]):
+                structs.append(apply_action(at, act)); want.append(m)
+    got = sro_device(engine, structs, [24, 27, 28])
+    assert len(got) == len(want) > 60
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
+def test_select_apply_equals_reference_selection(engine):
+    """rlvd_select_apply vs simulator.py:94-98 exec'd from the reference: with the uniform np.random.choice consumes
+    (the first random_sample() after np.random.seed(s)) the kernel picks the reference's index for every seed."""
+    sel = np.load(os.path.join(GOLD, "ref_selection.npz"))
+    for name in [str(n) for n in sel["names"]]:
+        Q, T, picks = sel[f"{name}.Q"], float(sel[f"{name}.T"]), sel[f"{name}.picks"]
+        n, S = len(Q), len(picks)
+        u = np.empty(S)
+        for s in range(S):
+            np.random.seed(s)
+            u[s] = np.random.random_sample()
+        dev = engine.device
+        first = torch.arange(0, (S + 1) * n, n, dtype=torch.int32, device=dev)
+        rep_ptr = torch.arange(0, S + 1, dtype=torch.int32, device=dev)            # one dummy atom per "replica"
+        actions = torch.zeros(S, n, 4, dtype=torch.float64, device=dev)
+        pos = torch.zeros(S, 3, dtype=torch.float64, device=dev)
+        chosen, amax, probs, gamma = engine.select_apply(
+            rep_ptr, first, torch.from_numpy(np.tile(Q, S)).to(dev), torch.full((S,), T, dtype=torch.float32, device=dev),
+            torch.from_numpy(u).to(dev), actions, pos, False)
+        assert np.array_equal(chosen.cpu().numpy().astype(np.int64), picks), name
+        assert int(amax[0]) == int(np.argmax(Q))
+        np.testing.assert_allclose(probs[0, :n].cpu().numpy(), sel[f"{name}.probs"], rtol=2e-5, atol=1e-7)
