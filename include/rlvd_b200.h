@@ -156,6 +156,35 @@ int  rlvd_q_head_train_step(rlvd_engine* e, void* stream, int32_t n_graphs, cons
  * policy_value_net.state_dict() after an update (trainer.py:120, train.py:102-104). */
 int  rlvd_get_weight(rlvd_engine* e, const char* name, float* h_out, int64_t numel);
 
+/* ---- replay-minibatch forward + backward of the WHOLE model (rlsim/drl/trainer.py:163-177 `dqn_update` with
+ *      train_all = True, configs/train_dqn.toml:27; rlsim/drl/trainer.py:87-98 `context_bandit_update`) ---------------------
+ * Parameters and gradients are flat fp32 vectors of rlvd_train_param_count() = 614,447 floats in the checkpoint's state_dict
+ * order (every floating-point tensor, buffers included); rlvd_train_layout(i, ...) describes entry i (returns non-zero past
+ * the end): checkpoint name, offset, element count and whether the reference optimises it (buffers `cutoff`, `freqs` do not).
+ * The gradient vector is the bucket rl-train all-reduces across ranks before rlvd_adam_step. */
+int64_t rlvd_train_param_count(void);
+int  rlvd_train_layout(int32_t index, const char** name, int64_t* offset, int64_t* numel, int32_t* trainable);
+/* One minibatch: structures [0, n_react) are the reactants of reaction graphs 0..n_react-1, structures [n_react, 2 n_react)
+ * their products (n_struct = 2 n_react, equal atom counts pairwise; graph from rlvd_radius_graph_*).  loss_mode 0 (dqn):
+ * loss = mean((d_target0 - rl_q)^2); loss_mode 1 (context bandit): loss = mean((q0 - d_target0)^2) + mean((q1 - d_target1)^2).
+ * d_dropout_uniform[n_react, 80] (may be NULL) drives the DQN heads' train-mode dropout like rlvd_q_head_train_step.
+ * Reads d_params, OVERWRITES d_grads (unclipped d loss / d parameter; zero for tensors the loss does not reach), writes
+ * d_loss[1], d_pred[n_react, 3] = (rl_q, q0, q1) and optionally d_q[n_nodes, 128] (final node scalars).  fp32 SIMT kernels,
+ * CSR-order sums, no atomics: bitwise reproducible.  The engine supplies only the species lookup and cutoff. */
+int  rlvd_train_forward_backward(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes, int64_t n_edges,
+                                 const int32_t* d_node_ptr, const int32_t* d_Z, const float* d_pos, const float* d_cell,
+                                 const int32_t* d_node_struct, const int32_t* d_row_ptr, const int32_t* d_col,
+                                 const int8_t* d_shift, int32_t n_react, const rlvd_q_params* qp, const float* d_temperature,
+                                 int32_t loss_mode, const float* d_target0, const float* d_target1,
+                                 const float* d_dropout_uniform, float dropout_p, const float* d_params, float* d_grads,
+                                 float* d_loss, float* d_pred, float* d_q);
+/* torch.nn.utils.clip_grad_norm_(max_norm) over the entries with d_trainable[i] != 0 (NULL = all; max_norm <= 0 = no clip)
+ * followed by torch.optim.Adam's update (no weight decay, no amsgrad) in place on d_params; step is 1-based; d_grad_norm[2]
+ * (may be NULL) receives the total norm and the clip coefficient. */
+int  rlvd_adam_step(rlvd_engine* e, void* stream, int64_t n, float* d_params, const float* d_grads, const uint8_t* d_trainable,
+                    float* d_exp_avg, float* d_exp_avg_sq, float lr, float beta1, float beta2, float eps, float max_norm,
+                    int32_t step, float* d_grad_norm);
+
 /* ---- Warren-Cowley pair counts (rlsim/utils/sro.py:49-83 `get_sro_from_atoms`, used per candidate by the sro_pixel
  *      filter at rlsim/drl/simulator.py:60-92) ------------------------------------------------------------------ */
 /* d_species_index[M] in [0, n_species) (index into the sorted species list); d_counts[n_struct, n_species, n_species]
@@ -209,6 +238,9 @@ int  rlvd_linear(rlvd_engine* e, void* stream, int32_t M, int32_t K, int32_t N, 
  * GEMMs over species-resolved radial sums instead of per-edge messages; batches containing any other atomic
  * number fall back to the per-edge kernels on the device, with identical results. */
 int  rlvd_set_species(rlvd_engine* e, const int32_t* atomic_numbers, int32_t n);
+/* Scalar hyper-parameters of the checkpoint that kernels need: "epsilon" (hyper_parameters.reaction_model.epsilon, the
+ * constant inside the mixing block's sqrt; default 1e-8). */
+int  rlvd_set_hyper(rlvd_engine* e, const char* name, double value);
 /* Engine options: "tensor_cores" (1 = tcgen05 GEMMs and filters, 0 = fp32 SIMT kernels; both fp32-accurate),
  * "sliced_edge" (1 = structure-resident edge stream kernel, edge_stream.cu, for structures of <= 256 atoms; 0 = general),
  * "fuse_mlp" (1 = each Linear-SiLU-Linear context net is one launch with the hidden tile kept on the SM),

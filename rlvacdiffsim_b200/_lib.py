@@ -61,6 +61,13 @@ SYMBOLS = {
     "rlvd_time_readout": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, C.POINTER(TimeHead), _P]),
     "rlvd_linear": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int32, _P]),
     "rlvd_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
+    "rlvd_set_hyper": (C.c_int, [_P, C.c_char_p, C.c_double]),
+    "rlvd_train_param_count": (C.c_int64, []),
+    "rlvd_train_layout": (C.c_int, [C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "rlvd_train_forward_backward": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32,
+                                              C.POINTER(QParams), _P, C.c_int32, _P, _P, _P, C.c_float, _P, _P, _P, _P, _P]),
+    "rlvd_adam_step": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                 C.c_int32, _P]),
     "rlvd_check_status": (C.c_int, [_P, _P, C.POINTER(C.c_int32)]),
     "rlvd_set_species": (C.c_int, [_P, _P, C.c_int32]),
     "rlvd_launch_count": (C.c_int64, [_P]),

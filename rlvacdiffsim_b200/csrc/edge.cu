@@ -138,6 +138,25 @@ __global__ void __launch_bounds__(EDGE_THREADS) edge_kernel(
 
 }  // namespace
 
+// The fp32 SIMT kernel with a caller-supplied filter table (train_full.cu: the training forward reads the flat master
+// parameters, not the engine's inference layouts).
+int launch_edge_simt(rlvd_engine* e, cudaStream_t s, const float* filt_T_layer, const float* freqs, float cutoff, const EdgeArgs& a) {
+    const int M = a.M;
+    if (M <= 0) return 0;
+    const int grid = (M + RPC - 1) / RPC;
+    Span sp(e, s, FAM_EDGE);
+    if (a.mu_in == nullptr) {
+        edge_kernel<false><<<grid, EDGE_THREADS, 0, s>>>(M, filt_T_layer, freqs, a.row_ptr, a.col, a.shift, a.pos, a.cell, a.node_struct,
+                                                         a.x, nullptr, a.q, a.mu_out, cutoff);
+    } else {
+        edge_kernel<true><<<grid, EDGE_THREADS, 0, s>>>(M, filt_T_layer, freqs, a.row_ptr, a.col, a.shift, a.pos, a.cell, a.node_struct,
+                                                        a.x, a.mu_in, a.q, a.mu_out, cutoff);
+    }
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_edge(rlvd_engine* e, cudaStream_t s, const EdgeArgs& a) {
     const int M = a.M;
     if (M <= 0) return 0;

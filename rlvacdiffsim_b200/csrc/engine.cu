@@ -209,7 +209,7 @@ void rlvd_engine_destroy(rlvd_engine* e) {
     cudaSetDevice(e->device);
     for (void* d : e->derived) cudaFree(d);
     for (DevBuf* b : {&e->x, &e->mu0, &e->mu1, &e->hid, &e->mix, &e->nrm, &e->vw, &e->ctx, &e->struct_edges,
-                      &e->struct_edge_ptr, &e->scratch, &e->tiles, &e->pipe_info, &e->tile_ctr, &e->stream_scratch, &e->l0A, &e->readout_scratch, &e->status, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
+                      &e->struct_edge_ptr, &e->scratch, &e->tiles, &e->pipe_info, &e->tile_ctr, &e->stream_scratch, &e->l0A, &e->train_ws, &e->readout_scratch, &e->status, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
                       &e->in_inv, &e->in_img, &e->in_rs, &e->in_ps, &e->in_temp, &e->in_qp, &e->g_row_ptr,
                       &e->g_node_struct, &e->g_col, &e->g_shift, &e->g_nedges, &e->g_q, &e->out_pack})
         b->release();
@@ -472,7 +472,7 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
         am.act = 0;
         const bool fused_mix = e->use_tensor_cores && e->fuse_mix;
         if (fused_mix) {                                  // nrm, vw from the GEMM epilogue; `mix` holds W only, [3M, F]
-            am.mixred = 1; am.n_nodes = M; am.nrm = nrm; am.vw = vw; am.Y = mix; am.ldy = F;
+            am.mixred = 1; am.n_nodes = M; am.nrm = nrm; am.vw = vw; am.Y = mix; am.ldy = F; am.eps = e->eps;
             if (launch_linear(e, s, am)) return 1;
         } else {
             am.Y = mix; am.ldy = 2 * F;
@@ -718,6 +718,16 @@ int rlvd_set_species(rlvd_engine* e, const int32_t* atomic_numbers, int32_t n) {
     }
     e->n_species = n;
     return 0;
+}
+
+int rlvd_set_hyper(rlvd_engine* e, const char* name, double value) {
+    RLVD_CHECK(e != nullptr && name != nullptr, "bad argument");
+    if (strcmp(name, "epsilon") == 0) {
+        RLVD_CHECK(value > 0.0 && value < 1.0, "rlvd_set_hyper: epsilon %g out of range", value);
+        e->eps = (float)value;
+        return 0;
+    }
+    RLVD_CHECK(false, "unknown hyper-parameter '%s'", name);
 }
 
 int rlvd_set_option(rlvd_engine* e, const char* name, int32_t value) {

@@ -247,7 +247,7 @@ int launch_mix_reduce(rlvd_engine* e, cudaStream_t s, int M, const float* mix, f
     if (M <= 0) return 0;
     Span sp(e, s, FAM_NODE);
     const int64_t n = (int64_t)M * (F / 4);
-    mix_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(M, mix, nrm, vw, 1e-8f);
+    mix_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(M, mix, nrm, vw, e->eps);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;

@@ -1,0 +1,1086 @@
+// B1, the `train_all = True` form: forward + backward of the WHOLE dqn_v2 / painn model for one replay
+// minibatch, and the clip + Adam step on a flat parameter vector.
+//
+// Replaces, for rlsim/drl/trainer.py:163-177 (`dqn_update`) and :87-98 (`context_bandit_update`):
+//     q_pred = policy_value_net(batch, q_params)["rl_q"]; loss = mean((batch["rl_q"] - q_pred)**2)        (dqn)
+//     loss   = mse(out["q0"], batch["q0"]) + mse(out["q1"], batch["q1"])                                 (context bandit)
+//     optimizer.zero_grad(); loss.backward(); clip_grad_norm_(parameters, max_norm); Adam.step()
+// i.e. what torch.autograd does through rgnn's PaiNN (index_select gathers, scatter_add, nn.Linear) — here as explicit
+// kernels over the same receiver-sorted CSR the forward uses:
+//
+//   * parameters live in ONE flat fp32 vector in the checkpoint's state_dict order (614,447 floats, `rlvd_train_layout`),
+//     gradients in a second one — the 2.46 MB bucket rl-train all-reduces over NCCL;
+//   * the training forward keeps every activation the backward needs (a replay minibatch is 8 reaction graphs = 16
+//     structures, ~4k nodes: 50 MB per layer);
+//   * edge-message backward WITHOUT a transposed CSR and without atomics: the radius graph is exactly symmetric
+//     (edge i<-j with shift S has the twin j<-i with shift -S, same d, dir negated — the fp32 edge arithmetic of
+//     neighbor.cu is odd in pos_j - pos_i), so the gradient flowing to SENDER j is a gather over j's own CSR row.  Per
+//     node and channel the kernel accumulates A[k] = sum_i g_k(d_ji) * upstream_i for the 21 radial terms g_k (20 Bessel x
+//     cutoff, and the cutoff itself for the filter bias); the filter-weight gradient, the gradient of x = context_net(q)
+//     and the gradient of mu all follow from A by 21-term dot products.  CSR order, fixed reduction trees: bitwise
+//     reproducible like the forward;
+//   * dense layers: one generic fp32 SGEMM (NN / NT / TN, split-K with ordered partial sums for the weight gradients).
+//     A minibatch is launch- and latency-bound (4k rows), not a tensor-pipe workload; the scoring path's tcgen05
+//     kernels are not used here.
+//
+// Layout contract of the batch (what DQNv2._score builds when reactants are not shared): structures [0, G) are the
+// reactants of reaction graphs 0..G-1, structures [G, 2G) their products, with equal atom counts pairwise — so node r of
+// the first half pairs with node M/2 + r.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace rlvd {
+
+// edge.cu: the fp32 SIMT forward edge kernel with caller-supplied filter table
+int launch_edge_simt(rlvd_engine* e, cudaStream_t s, const float* filt_T_layer, const float* freqs, float cutoff, const EdgeArgs& a);
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ flat parameter layout
+constexpr int64_t P_SC = 0, P_SH = 3, P_CUT = 6, P_FREQ = 7, P_EMB = 27, P_FW = 12827, P_FB = 35867, P_INTER = 37019,
+                  INTER_STRIDE = 66048, P_MIX = 235163, MIX_STRIDE = 115200, P_EN = 580763, P_RR = 589084, P_RO = 609724,
+                  P_QE = 611934, P_QO = 612750, NPARAM = 614447;
+// offsets inside one interaction / mixing block and the heads
+constexpr int64_t I_W0 = 0, I_B0 = 16384, I_W3 = 16512, I_B3 = 65664;
+constexpr int64_t X_W0 = 0, X_B0 = 32768, X_W3 = 32896, X_B3 = 82048, X_WM = 82432;
+constexpr int64_t EN_W0 = 0, EN_B0 = 8192, EN_W3 = 8256, EN_B3 = 8320;
+constexpr int64_t RR_W0 = 0, RR_B0 = 16384, RR_W3 = 16512, RR_B3 = 20608;
+constexpr int64_t RO_W0 = 0, RO_B0 = 1056, RO_W1 = 1088, RO_B1 = 2112, RO_W2 = 2144, RO_B2 = 2208;
+constexpr int64_t QE_W0 = 0, QE_B0 = 528, QE_W1 = 544, QE_B1 = 800;
+constexpr int64_t QO_W0 = 0, QO_B0 = 576, QO_W1 = 608, QO_B1 = 1632, QO_W2 = 1664, QO_B2 = 1696;
+
+struct LayoutEnt {
+    std::string name;
+    int64_t offset, numel;
+    int trainable;
+};
+
+const std::vector<LayoutEnt>& layout() {
+    static std::vector<LayoutEnt> tab;
+    if (!tab.empty()) return tab;
+    int64_t off = 0;
+    auto add = [&](const std::string& n, int64_t numel, int tr) {
+        tab.push_back({n, off, numel, tr});
+        off += numel;
+    };
+    const std::string rm = "reaction_model.", rep = rm + "representation.";
+    add(rm + "species_energy_scale.scales", 3, 1);
+    add(rm + "species_energy_scale.shifts", 3, 1);
+    add(rep + "cutoff_fn.cutoff", 1, 0);             // buffer
+    add(rep + "radial_basis.freqs", NRBF, 0);        // buffer (trainable_rbf = False)
+    add(rep + "embedding.weight", 100 * F, 1);
+    add(rep + "filter_net.weight", (int64_t)NLAYER * 3 * F * NRBF, 1);
+    add(rep + "filter_net.bias", NLAYER * 3 * F, 1);
+    for (int l = 0; l < NLAYER; ++l) {
+        const std::string p = rep + "interactions." + std::to_string(l) + ".interatomic_context_net.layers.";
+        add(p + "0.weight", F * F, 1);
+        add(p + "0.bias", F, 1);
+        add(p + "3.weight", 3 * F * F, 1);
+        add(p + "3.bias", 3 * F, 1);
+    }
+    for (int l = 0; l < NLAYER; ++l) {
+        const std::string p = rep + "mixing." + std::to_string(l) + ".";
+        add(p + "intraatomic_context_net.layers.0.weight", F * 2 * F, 1);
+        add(p + "intraatomic_context_net.layers.0.bias", F, 1);
+        add(p + "intraatomic_context_net.layers.3.weight", 3 * F * F, 1);
+        add(p + "intraatomic_context_net.layers.3.bias", 3 * F, 1);
+        add(p + "mu_channel_mix.weight", 2 * F * F, 1);
+    }
+    add(rm + "energy_output.layers.0.weight", 64 * F, 1);
+    add(rm + "energy_output.layers.0.bias", 64, 1);
+    add(rm + "energy_output.layers.3.weight", 64, 1);
+    add(rm + "energy_output.layers.3.bias", 1, 1);
+    add(rm + "reaction_representation.layers.0.weight", F * F, 1);
+    add(rm + "reaction_representation.layers.0.bias", F, 1);
+    add(rm + "reaction_representation.layers.3.weight", 32 * F, 1);
+    add(rm + "reaction_representation.layers.3.bias", 32, 1);
+    add(rm + "reaction_output.layers.0.weight", 32 * 33, 1);
+    add(rm + "reaction_output.layers.0.bias", 32, 1);
+    add(rm + "reaction_output.layers.3.weight", 32 * 32, 1);
+    add(rm + "reaction_output.layers.3.bias", 32, 1);
+    add(rm + "reaction_output.layers.6.weight", 2 * 32, 1);
+    add(rm + "reaction_output.layers.6.bias", 2, 1);
+    add("Q_emb.layers.0.weight", 16 * 33, 1);
+    add("Q_emb.layers.0.bias", 16, 1);
+    add("Q_emb.layers.3.weight", 16 * 16, 1);
+    add("Q_emb.layers.3.bias", 16, 1);
+    add("Q_output.layers.0.weight", 32 * 18, 1);
+    add("Q_output.layers.0.bias", 32, 1);
+    add("Q_output.layers.3.weight", 32 * 32, 1);
+    add("Q_output.layers.3.bias", 32, 1);
+    add("Q_output.layers.6.weight", 32, 1);
+    add("Q_output.layers.6.bias", 1, 1);
+    return tab;
+}
+
+// ------------------------------------------------------------------------------------------------ activations
+__device__ __forceinline__ float actf(float v, int code) {
+    switch (code) {
+        case RLVD_ACT_RELU: return v > 0.f ? v : 0.f;
+        case RLVD_ACT_TANH: return tanhf(v);
+        case RLVD_ACT_LEAKY_RELU: return v > 0.f ? v : 0.01f * v;
+        default: return v / (1.0f + expf(-v));
+    }
+}
+__device__ __forceinline__ float actd(float v, int code) {
+    switch (code) {
+        case RLVD_ACT_RELU: return v > 0.f ? 1.f : 0.f;
+        case RLVD_ACT_TANH: { const float t = tanhf(v); return 1.f - t * t; }
+        case RLVD_ACT_LEAKY_RELU: return v > 0.f ? 1.f : 0.01f;
+        default: { const float s = 1.0f / (1.0f + expf(-v)); return s * (1.0f + v * (1.0f - s)); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ generic fp32 SGEMM
+// C[m,n] (ldc) = (accumulate ? C : 0) + sum_k A(m,k) B(k,n) (+ bias[n]);  A(m,k) = TA ? A[k*lda+m] : A[m*lda+k];
+// B(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n].  64x64x16 tiles, 256 threads, 4x4 per thread, ascending-k accumulation.
+// gridDim.z > 1 = split-K: slice z covers k in [z*kchunk, (z+1)*kchunk) and writes its partial to C + z*zstride.
+constexpr int GT = 64, GK = 16;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                    const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                                    const float* __restrict__ bias, int accumulate, int kchunk, int64_t zstride) {
+    __shared__ float As[GK][GT + 1];
+    __shared__ float Bs[GK][GT + 1];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
+    const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+    C += (int64_t)blockIdx.z * zstride;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += GK) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int f = tid + 256 * r;            // 1024 elements of each 16 x 64 tile
+            int kk, mm;
+            if (TA) { mm = f & 63; kk = f >> 6; } else { kk = f & 15; mm = f >> 4; }
+            const int m = m0 + mm, k = k0 + kk;
+            As[kk][mm] = (m < M && k < kend) ? __ldg(TA ? A + (int64_t)k * lda + m : A + (int64_t)m * lda + k) : 0.f;
+            int kb, nn;
+            if (TB) { kb = f & 15; nn = f >> 4; } else { nn = f & 63; kb = f >> 6; }
+            const int n = n0 + nn, k2 = k0 + kb;
+            Bs[kb][nn] = (n < N && k2 < kend) ? __ldg(TB ? B + (int64_t)n * ldb + k2 : B + (int64_t)k2 * ldb + n) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            float av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (bias != nullptr) v += __ldg(bias + n);
+            float* dst = C + (int64_t)m * ldc + n;
+            *dst = accumulate ? *dst + v : v;
+        }
+    }
+}
+
+// dst[i] (+)= sum_{z < S} part[z*n + i], ascending z
+__global__ void reduce_partials_kernel(int64_t n, int S, const float* __restrict__ part, float* __restrict__ dst, int accumulate) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = 0.f;
+    for (int z = 0; z < S; ++z) v += part[(int64_t)z * n + i];
+    dst[i] = accumulate ? dst[i] + v : v;
+}
+
+// out[c] (+)= sum_r X[r*ld + c]: block = 32 columns x 8 row lanes, fixed-order combine
+__global__ void __launch_bounds__(256) colsum_kernel(int rows, int cols, const float* __restrict__ X, int ld, float* __restrict__ out,
+                                                     int accumulate) {
+    __shared__ float part[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    float v = 0.f;
+    if (c < cols)
+        for (int r = ry; r < rows; r += 8) v += X[(int64_t)r * ld + c];
+    part[ry][cx] = v;
+    __syncthreads();
+    if (ry == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += part[k][cx];
+        out[c] = accumulate ? out[c] + t : t;
+    }
+}
+
+__global__ void act_fwd_kernel(int64_t n, const float* __restrict__ pre, float* __restrict__ out, int code) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = actf(pre[i], code);
+}
+// g *= act'(pre)
+__global__ void act_bwd_kernel(int64_t n, const float* __restrict__ pre, float* __restrict__ g, int code) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) g[i] *= actd(pre[i], code);
+}
+// y[r*ldy + c] += x[r*ldx + c]
+__global__ void add_strided_kernel(int rows, int cols, const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * cols) return;
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    y[(int64_t)r * ldy + c] += x[(int64_t)r * ldx + c];
+}
+
+// ------------------------------------------------------------------------------------------------ representation pieces
+__global__ void embed_train_kernel(int M, const int* __restrict__ Z, const float* __restrict__ emb, float* __restrict__ q) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)M * F) return;
+    int z = Z[i / F];
+    z = z < 0 ? 0 : (z > 99 ? 99 : z);
+    q[i] = emb[z * F + (i % F)];
+}
+// gemb[z][c] = sum_{i : Z_i = z} gq[i][c], nodes ascending.  grid = 100, block = F
+__global__ void embed_bwd_kernel(int M, const int* __restrict__ Z, const float* __restrict__ gq, float* __restrict__ gemb) {
+    const int z = blockIdx.x, c = threadIdx.x;
+    float v = 0.f;
+    for (int i = 0; i < M; ++i) {
+        int zi = Z[i];
+        zi = zi < 0 ? 0 : (zi > 99 ? 99 : zi);
+        if (zi == z) v += gq[(int64_t)i * F + c];
+    }
+    gemb[z * F + c] = v;
+}
+// filter_net.weight [L*3F][20], bias [L*3F]  ->  filt_T [L][21][3F] (the table edge.cu's kernel reads)
+__global__ void build_filt_kernel(const float* __restrict__ fw, const float* __restrict__ fb, float* __restrict__ filt_T) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NLAYER * (NRBF + 1) * 3 * F) return;
+    const int o = i % (3 * F), k = (i / (3 * F)) % (NRBF + 1), l = i / ((NRBF + 1) * 3 * F);
+    const int row = l * 3 * F + o;
+    filt_T[i] = k < NRBF ? fw[(int64_t)row * NRBF + k] : fb[row];
+}
+// mix [3M][2F] (V | W per (node, component) row) -> nrm, vw [M][F]
+__global__ void mix_reduce_train_kernel(int M, const float* __restrict__ mix, float* __restrict__ nrm, float* __restrict__ vw, float eps) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * F) return;
+    const int i = (int)(idx / F), c = (int)(idx % F);
+    float n2 = 0.f, dot = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float v = mix[((int64_t)i * 3 + a) * 2 * F + c], w = mix[((int64_t)i * 3 + a) * 2 * F + F + c];
+        n2 = fmaf(v, v, n2);
+        dot = fmaf(v, w, dot);
+    }
+    nrm[idx] = sqrtf(n2 + eps);
+    vw[idx] = dot;
+}
+// q_out = q_mid + a + c*vw;  mu_out[a] = mu_mid[a] + b*W[a]
+__global__ void mix_update_train_kernel(int M, const float* __restrict__ ctx, const float* __restrict__ mix, const float* __restrict__ vw,
+                                        const float* __restrict__ q_mid, const float* __restrict__ mu_mid, float* __restrict__ q_out,
+                                        float* __restrict__ mu_out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * F) return;
+    const int i = (int)(idx / F), c = (int)(idx % F);
+    const float a = ctx[(int64_t)i * 3 * F + c], b = ctx[(int64_t)i * 3 * F + F + c], cc = ctx[(int64_t)i * 3 * F + 2 * F + c];
+    q_out[idx] = q_mid[idx] + a + cc * vw[idx];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int64_t mi = ((int64_t)i * 3 + k) * F + c;
+        mu_out[mi] = fmaf(b, mix[((int64_t)i * 3 + k) * 2 * F + F + c], mu_mid[mi]);
+    }
+}
+// mixing backward, stage 1: gctx = [gq_out | sum_a gmu_out[a]*W[a] | gq_out*vw]
+__global__ void mix_bwd1_kernel(int M, const float* __restrict__ gq, const float* __restrict__ gmu, const float* __restrict__ mix,
+                                const float* __restrict__ vw, float* __restrict__ gctx) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * F) return;
+    const int i = (int)(idx / F), c = (int)(idx % F);
+    const float g = gq[idx];
+    float gb = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) gb = fmaf(gmu[((int64_t)i * 3 + a) * F + c], mix[((int64_t)i * 3 + a) * 2 * F + F + c], gb);
+    gctx[(int64_t)i * 3 * F + c] = g;
+    gctx[(int64_t)i * 3 * F + F + c] = gb;
+    gctx[(int64_t)i * 3 * F + 2 * F + c] = g * vw[idx];
+}
+// mixing backward, stage 2: gmix[(i,a)] = [gV | gW],  gV = g_vw*W + gnrm*V/nrm,  gW = gmu_out*b + g_vw*V,  g_vw = gq_out*c
+__global__ void mix_bwd2_kernel(int M, const float* __restrict__ gq, const float* __restrict__ gmu, const float* __restrict__ mix,
+                                const float* __restrict__ nrm, const float* __restrict__ ctx, const float* __restrict__ gcat /* [M][2F] */,
+                                float* __restrict__ gmix) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * F) return;
+    const int i = (int)(idx / F), c = (int)(idx % F);
+    const float b = ctx[(int64_t)i * 3 * F + F + c], cc = ctx[(int64_t)i * 3 * F + 2 * F + c];
+    const float gvw = gq[idx] * cc;
+    const float gn = gcat[(int64_t)i * 2 * F + F + c] / nrm[idx];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int64_t row = (int64_t)i * 3 + a;
+        const float v = mix[row * 2 * F + c], w = mix[row * 2 * F + F + c];
+        gmix[row * 2 * F + c] = fmaf(gvw, w, gn * v);
+        gmix[row * 2 * F + F + c] = fmaf(gmu[row * F + c], b, gvw * v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ edge-message backward
+constexpr int EB_THREADS = F, EB_EC = 64;
+constexpr float PI_F = 3.14159265358979323846f;
+
+template <bool HAS_MU>
+__global__ void __launch_bounds__(EB_THREADS) edge_bwd_kernel(
+    int M, int rpc, const float* __restrict__ filt_T /* [21][3F], this layer */, const float* __restrict__ freqs,
+    const int* __restrict__ row_ptr, const int* __restrict__ col, const int8_t* __restrict__ shift, const float* __restrict__ pos,
+    const float* __restrict__ cell, const int* __restrict__ node_struct, const float* __restrict__ x, const float* __restrict__ mu_in,
+    const float* __restrict__ gq, const float* __restrict__ gmu, float* __restrict__ gx, float* __restrict__ gmu_in,
+    float* __restrict__ wpart /* [gridDim.x][63][F] */, float cutoff) {
+    __shared__ __align__(16) float g[EB_EC][GEOM];
+    __shared__ int sj[EB_EC];
+    __shared__ float sd[EB_EC], sscale[EB_EC];
+    __shared__ float sfreq[NRBF];
+    const int c = threadIdx.x;
+    if (c < NRBF) sfreq[c] = __ldg(freqs + c);
+    const float pi_over_rc = PI_F / cutoff;
+    float GW[3 * (NRBF + 1)];
+#pragma unroll
+    for (int t = 0; t < 3 * (NRBF + 1); ++t) GW[t] = 0.f;
+    const int j_begin = blockIdx.x * rpc, j_end = min(M, j_begin + rpc);
+    for (int j = j_begin; j < j_end; ++j) {
+        const int e0 = __ldg(row_ptr + j), e1 = __ldg(row_ptr + j + 1);
+        const int gs = __ldg(node_struct + j);
+        const float xj = __ldg(pos + 3 * (int64_t)j), yj = __ldg(pos + 3 * (int64_t)j + 1), zj = __ldg(pos + 3 * (int64_t)j + 2);
+        float Aq[NRBF + 1], AR[NRBF + 1], A0[NRBF + 1], A1[NRBF + 1], A2[NRBF + 1];
+#pragma unroll
+        for (int k = 0; k <= NRBF; ++k) { Aq[k] = 0.f; AR[k] = 0.f; A0[k] = 0.f; A1[k] = 0.f; A2[k] = 0.f; }
+        for (int eb = e0; eb < e1; eb += EB_EC) {
+            const int ne = min(EB_EC, e1 - eb);
+            __syncthreads();
+            if (c < ne) {                       // geometry of the row entry (j <- i), as edge.cu computes it
+                const int e = eb + c;
+                const int i = __ldg(col + e);
+                const float S0 = (float)shift[3 * (int64_t)e], S1 = (float)shift[3 * (int64_t)e + 1], S2 = (float)shift[3 * (int64_t)e + 2];
+                const float* C = cell + 9 * gs;
+                float rx = __ldg(pos + 3 * (int64_t)i) - xj, ry = __ldg(pos + 3 * (int64_t)i + 1) - yj, rz = __ldg(pos + 3 * (int64_t)i + 2) - zj;
+                rx += S0 * __ldg(C + 0) + S1 * __ldg(C + 3) + S2 * __ldg(C + 6);
+                ry += S0 * __ldg(C + 1) + S1 * __ldg(C + 4) + S2 * __ldg(C + 7);
+                rz += S0 * __ldg(C + 2) + S1 * __ldg(C + 5) + S2 * __ldg(C + 8);
+                const float d = sqrtf(rx * rx + ry * ry + rz * rz);
+                const float inv_d = 1.0f / d;
+                const float fc = d < cutoff ? 0.5f * (cosf(d * pi_over_rc) + 1.0f) : 0.f;
+                sj[c] = i;
+                sd[c] = d;
+                sscale[c] = inv_d * fc;
+                g[c][NRBF] = fc;
+                // direction of the FORWARD edge (receiver i <- sender j) = minus the direction of this row entry
+                g[c][NRBF + 1] = -rx * inv_d;
+                g[c][NRBF + 2] = -ry * inv_d;
+                g[c][NRBF + 3] = -rz * inv_d;
+            }
+            __syncthreads();
+            for (int item = c; item < ne * NRBF; item += EB_THREADS) {
+                const int ee = item / NRBF, k = item - ee * NRBF;
+                const float f = sfreq[k], d = sd[ee];
+                const float p = f * d;
+                const float perr = fmaf(f, d, -p);
+                float sn, cs;
+                sincosf(p, &sn, &cs);
+                g[ee][k] = fmaf(perr, cs, sn) * sscale[ee];
+            }
+            __syncthreads();
+            for (int ee = 0; ee < ne; ++ee) {
+                const int i = sj[ee];
+                const float gqi = __ldg(gq + (int64_t)i * F + c);
+                const float g0 = __ldg(gmu + (int64_t)i * 3 * F + c), g1 = __ldg(gmu + (int64_t)i * 3 * F + F + c),
+                            g2 = __ldg(gmu + (int64_t)i * 3 * F + 2 * F + c);
+                const float sR = g[ee][NRBF + 1] * g0 + g[ee][NRBF + 2] * g1 + g[ee][NRBF + 3] * g2;
+#pragma unroll
+                for (int k = 0; k <= NRBF; ++k) {
+                    const float gk = g[ee][k];
+                    Aq[k] = fmaf(gk, gqi, Aq[k]);
+                    AR[k] = fmaf(gk, sR, AR[k]);
+                    if (HAS_MU) {
+                        A0[k] = fmaf(gk, g0, A0[k]);
+                        A1[k] = fmaf(gk, g1, A1[k]);
+                        A2[k] = fmaf(gk, g2, A2[k]);
+                    }
+                }
+            }
+        }
+        const float xq = __ldg(x + (int64_t)j * 3 * F + c), xR = __ldg(x + (int64_t)j * 3 * F + F + c),
+                    xm = __ldg(x + (int64_t)j * 3 * F + 2 * F + c);
+        float gxq = 0.f, gxR = 0.f, U0 = 0.f, U1 = 0.f, U2 = 0.f;
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+        if (HAS_MU) {
+            m0 = __ldg(mu_in + (int64_t)j * 3 * F + c);
+            m1 = __ldg(mu_in + (int64_t)j * 3 * F + F + c);
+            m2 = __ldg(mu_in + (int64_t)j * 3 * F + 2 * F + c);
+        }
+#pragma unroll
+        for (int k = 0; k <= NRBF; ++k) {
+            const float wq = __ldg(filt_T + k * 3 * F + c), wr = __ldg(filt_T + k * 3 * F + F + c);
+            gxq = fmaf(wq, Aq[k], gxq);
+            gxR = fmaf(wr, AR[k], gxR);
+            GW[k] = fmaf(xq, Aq[k], GW[k]);
+            GW[NRBF + 1 + k] = fmaf(xR, AR[k], GW[NRBF + 1 + k]);
+            if (HAS_MU) {
+                const float wm = __ldg(filt_T + k * 3 * F + 2 * F + c);
+                U0 = fmaf(wm, A0[k], U0);
+                U1 = fmaf(wm, A1[k], U1);
+                U2 = fmaf(wm, A2[k], U2);
+                GW[2 * (NRBF + 1) + k] = fmaf(xm, m0 * A0[k] + m1 * A1[k] + m2 * A2[k], GW[2 * (NRBF + 1) + k]);
+            }
+        }
+        gx[(int64_t)j * 3 * F + c] = gxq;
+        gx[(int64_t)j * 3 * F + F + c] = gxR;
+        gx[(int64_t)j * 3 * F + 2 * F + c] = HAS_MU ? m0 * U0 + m1 * U1 + m2 * U2 : 0.f;
+        if (HAS_MU) {
+            gmu_in[(int64_t)j * 3 * F + c] = fmaf(xm, U0, __ldg(gmu + (int64_t)j * 3 * F + c));
+            gmu_in[(int64_t)j * 3 * F + F + c] = fmaf(xm, U1, __ldg(gmu + (int64_t)j * 3 * F + F + c));
+            gmu_in[(int64_t)j * 3 * F + 2 * F + c] = fmaf(xm, U2, __ldg(gmu + (int64_t)j * 3 * F + 2 * F + c));
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 3 * (NRBF + 1); ++t) wpart[((int64_t)blockIdx.x * 3 * (NRBF + 1) + t) * F + c] = GW[t];
+}
+
+// filter_net gradient of one layer from the per-CTA partials: thread = (part, k, c); CTAs ascending
+__global__ void edge_wgrad_reduce_kernel(int n_cta, int layer, const float* __restrict__ wpart, float* __restrict__ gfw,
+                                         float* __restrict__ gfb) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 3 * (NRBF + 1) * F) return;
+    const int c = idx % F, t = idx / F, part = t / (NRBF + 1), k = t % (NRBF + 1);
+    float v = 0.f;
+    for (int b = 0; b < n_cta; ++b) v += wpart[((int64_t)b * 3 * (NRBF + 1) + t) * F + c];
+    const int row = layer * 3 * F + part * F + c;
+    if (k < NRBF) gfw[(int64_t)row * NRBF + k] = v; else gfb[row] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ heads, node level
+// e_atom = e_raw*scale[s] + shift[s]
+__global__ void energy_scale_kernel(int M, const int* __restrict__ Z, const int* __restrict__ lookup, const float* __restrict__ sc,
+                                    const float* __restrict__ sh, const float* __restrict__ e_raw, float* __restrict__ e_atom) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    int z = Z[i];
+    z = z < 0 ? 0 : (z > 99 ? 99 : z);
+    const int s = lookup[z];
+    e_atom[i] = fmaf(e_raw[i], sc[s], sh[s]);
+}
+// per reaction graph: E_R, E_P, delta_e = sum (e_P - e_R) in atom order (oracle: per-atom difference, then pooled).  grid = G, 1 warp
+__global__ void energy_pool_kernel(int G, int Mr, const int* __restrict__ node_ptr, const float* __restrict__ e_atom, float* __restrict__ ER,
+                                   float* __restrict__ EP, float* __restrict__ dE) {
+    const int g = blockIdx.x;
+    if (threadIdx.x != 0 || g >= G) return;
+    const int n0 = node_ptr[g], n1 = node_ptr[g + 1];
+    float er = 0.f, ep = 0.f, de = 0.f;
+    for (int r = n0; r < n1; ++r) {
+        const float a = e_atom[r], b = e_atom[Mr + r];
+        er += a;
+        ep += b;
+        de += b - a;
+    }
+    ER[g] = er; EP[g] = ep; dE[g] = de;
+}
+// d = q_P - q_R on the reaction nodes
+__global__ void node_diff_kernel(int64_t n, const float* __restrict__ q, int64_t half, float* __restrict__ d) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = q[half + i] - q[i];
+}
+// h[g][o] = sum_{r in g} hatom[r][o], atom order.  grid = G, block = 32
+__global__ void feat_pool_kernel(int G, const int* __restrict__ node_ptr, const float* __restrict__ hatom, float* __restrict__ h) {
+    const int g = blockIdx.x, o = threadIdx.x;
+    float v = 0.f;
+    for (int r = node_ptr[g]; r < node_ptr[g + 1]; ++r) v += hatom[(int64_t)r * 32 + o];
+    h[g * 32 + o] = v;
+}
+// broadcast of the pooled-feature gradient to the reaction nodes: ghatom[r][o] = gh[g(r)][o]
+__global__ void feat_unpool_kernel(int Mr, const int* __restrict__ node_struct, const float* __restrict__ gh, float* __restrict__ ghatom) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)Mr * 32) return;
+    const int r = (int)(i / 32), o = (int)(i % 32);
+    ghatom[i] = gh[node_struct[r] * 32 + o];
+}
+// energy path: g_eraw[i] = gde[g(i)] * (+1 product / -1 reactant) * scale[s_i]; species scale / shift gradients
+__global__ void __launch_bounds__(256) energy_bwd_kernel(int M, int Mr, int G, const int* __restrict__ Z, const int* __restrict__ lookup,
+                                                         const int* __restrict__ node_struct, const float* __restrict__ sc,
+                                                         const float* __restrict__ e_raw, const float* __restrict__ gde,
+                                                         float* __restrict__ g_eraw, float* __restrict__ gsc, float* __restrict__ gsh) {
+    __shared__ float red[256][6];
+    float loc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = threadIdx.x; i < M; i += 256) {
+        int z = Z[i];
+        z = z < 0 ? 0 : (z > 99 ? 99 : z);
+        const int s = lookup[z];
+        const int st = node_struct[i];
+        const float ge = i < Mr ? -gde[st] : gde[st - G];
+        g_eraw[i] = ge * sc[s];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            loc[t] += (t == s) ? ge * e_raw[i] : 0.f;
+            loc[3 + t] += (t == s) ? ge : 0.f;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 6; ++t) red[threadIdx.x][t] = loc[t];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = 0.f;
+        for (int k = 0; k < 256; ++k) v += red[k][threadIdx.x];
+        if (threadIdx.x < 3) gsc[threadIdx.x] = v; else gsh[threadIdx.x - 3] = v;
+    }
+}
+// gq[Mr + r] += gd[r];  gq[r] -= gd[r]
+__global__ void diff_bwd_kernel(int64_t n, const float* __restrict__ gd, int64_t half, float* __restrict__ gq) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    gq[half + i] += gd[i];
+    gq[i] -= gd[i];
+}
+
+// ------------------------------------------------------------------------------------------------ heads, graph level
+// reaction_output (33-32-32-2), Q_emb (33-16-16), Q_output (18-32-32-1), the q_params mix, the loss and their backward in
+// ONE CTA; per-graph scratch in global memory; parameter gradients with graphs ascending (bitwise reproducible).
+constexpr int GS_Z = 0, GS_R1P = 33, GS_R1 = 65, GS_R2P = 97, GS_R2 = 129, GS_BF = 161, GS_E1P = 163, GS_E1 = 179, GS_T = 195,
+              GS_O1P = 213, GS_O1 = 245, GS_O2P = 277, GS_O2 = 309, GS_ME1 = 341, GS_MO1 = 357, GS_MO2 = 389, GS_DBF = 421,
+              GS_DR2 = 423, GS_DR1 = 455, GS_DO2 = 487, GS_DO1 = 519, GS_DE2 = 551, GS_DE1 = 567, GS_DQC = 583, GS_RES = 584,
+              GS_PER = 592;
+
+struct GraphHeadArgs {
+    int G, mode, dqn, act_p, act_d, std_de, qx0, qx1;
+    float alpha, beta, temperature, p_drop;
+    float mean_b, std_b, mean_f, std_f, mean_de, std_de_v;
+    const float* P;            // flat parameters
+    float* Gr;                 // flat gradients
+    const float* hpool;        // [G][32]
+    const float* dE;           // [G]
+    const float* d_temp;       // [G] or null
+    const float* target0;      // dqn: rl_q labels; bandit: q0 labels
+    const float* target1;      // bandit: q1 labels
+    const float* drop_u;       // [G][80] or null
+    float* S;                  // [G][GS_PER]
+    float* gh;                 // [G][32]   d loss / d pooled features
+    float* gde;                // [G]       d loss / d delta_e
+    float* pred;               // [G][3]    rl_q, q0, q1
+    float* loss;               // [1]
+};
+
+__device__ __forceinline__ float dotw(const float* W, int n_in, const float* in, int row) {
+    float acc = 0.f;
+    for (int k = 0; k < n_in; ++k) acc = fmaf(W[row * n_in + k], in[k], acc);
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) graph_heads_kernel(GraphHeadArgs a) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* P = a.P;
+    const float* RO = P + P_RO;
+    const float* QE = P + P_QE;
+    const float* QO = P + P_QO;
+    const float keep = 1.0f / (1.0f - a.p_drop);
+    __shared__ float s_loss;
+    for (int i = tid; i < a.G * 80; i += 256) {
+        const int g = i / 80, c = i % 80;
+        a.S[(int64_t)g * GS_PER + GS_ME1 + c] = a.drop_u != nullptr && a.p_drop > 0.f ? (a.drop_u[i] >= a.p_drop ? keep : 0.f) : 1.f;
+    }
+    __syncthreads();
+    for (int g = warp; g < a.G; g += 8) {
+        float* s = a.S + (int64_t)g * GS_PER;
+        const float dE = a.dE[g];
+        s[GS_Z + lane] = a.hpool[g * 32 + lane];
+        if (lane == 0) s[GS_Z + 32] = a.std_de ? (dE - a.mean_de) / a.std_de_v : dE;
+        __syncwarp();
+        float v = dotw(RO + RO_W0, 33, s + GS_Z, lane) + RO[RO_B0 + lane];
+        s[GS_R1P + lane] = v;
+        s[GS_R1 + lane] = actf(v, a.act_p);
+        __syncwarp();
+        v = dotw(RO + RO_W1, 32, s + GS_R1, lane) + RO[RO_B1 + lane];
+        s[GS_R2P + lane] = v;
+        s[GS_R2 + lane] = actf(v, a.act_p);
+        __syncwarp();
+        if (lane < 2) s[GS_BF + lane] = dotw(RO + RO_W2, 32, s + GS_R2, lane) + RO[RO_B2 + lane];
+        __syncwarp();
+        const float q0 = -fmaf(s[GS_BF], a.std_b, a.mean_b), q1 = fmaf(s[GS_BF + 1], a.std_f, a.mean_f);
+        const float T = a.d_temp != nullptr ? a.d_temp[g] : a.temperature;
+        const float kT = T * 8.617e-5f;
+        float rl = a.alpha * (q0 + kT * q1) + a.beta * (-dE);
+        if (a.dqn) {
+            if (lane < 16) {
+                v = dotw(QE + QE_W0, 33, s + GS_Z, lane) + QE[QE_B0 + lane];
+                s[GS_E1P + lane] = v;
+                s[GS_E1 + lane] = actf(v, a.act_d) * s[GS_ME1 + lane];
+            }
+            __syncwarp();
+            if (lane < 16) s[GS_T + lane] = dotw(QE + QE_W1, 16, s + GS_E1, lane) + QE[QE_B1 + lane];
+            if (lane == 0) {
+                s[GS_T + 16] = a.qx0 == RLVD_QX_KT_X10 ? kT * 10.0f : dE;
+                s[GS_T + 17] = a.qx1 == RLVD_QX_KT_X10 ? kT * 10.0f : dE;
+            }
+            __syncwarp();
+            v = dotw(QO + QO_W0, 18, s + GS_T, lane) + QO[QO_B0 + lane];
+            s[GS_O1P + lane] = v;
+            s[GS_O1 + lane] = actf(v, a.act_d) * s[GS_MO1 + lane];
+            __syncwarp();
+            v = dotw(QO + QO_W1, 32, s + GS_O1, lane) + QO[QO_B1 + lane];
+            s[GS_O2P + lane] = v;
+            s[GS_O2 + lane] = actf(v, a.act_d) * s[GS_MO2 + lane];
+            __syncwarp();
+            rl += dotw(QO + QO_W2, 32, s + GS_O2, 0) + QO[QO_B2];
+        }
+        if (lane == 0) {
+            a.pred[g * 3] = rl; a.pred[g * 3 + 1] = q0; a.pred[g * 3 + 2] = q1;
+            if (a.mode == 0) { s[GS_RES] = rl - a.target0[g]; s[GS_RES + 1] = 0.f; }
+            else { s[GS_RES] = q0 - a.target0[g]; s[GS_RES + 1] = q1 - a.target1[g]; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float l = 0.f;
+        for (int g = 0; g < a.G; ++g) {
+            const float* s = a.S + (int64_t)g * GS_PER;
+            l += s[GS_RES] * s[GS_RES] + s[GS_RES + 1] * s[GS_RES + 1];
+        }
+        s_loss = l / (float)a.G;
+        *a.loss = s_loss;
+    }
+    __syncthreads();
+    // ---- backward per graph
+    for (int g = warp; g < a.G; g += 8) {
+        float* s = a.S + (int64_t)g * GS_PER;
+        const float T = a.d_temp != nullptr ? a.d_temp[g] : a.temperature;
+        const float kT = T * 8.617e-5f;
+        float d_rl, d_q0, d_q1;
+        if (a.mode == 0) {
+            d_rl = 2.0f * s[GS_RES] / (float)a.G;
+            d_q0 = a.alpha * d_rl;
+            d_q1 = a.alpha * kT * d_rl;
+        } else {
+            d_rl = 0.f;
+            d_q0 = 2.0f * s[GS_RES] / (float)a.G;
+            d_q1 = 2.0f * s[GS_RES + 1] / (float)a.G;
+        }
+        float gde = -a.beta * d_rl;
+        __syncwarp();
+        if (lane == 0) { s[GS_DBF] = -a.std_b * d_q0; s[GS_DBF + 1] = a.std_f * d_q1; s[GS_DQC] = a.dqn ? d_rl : 0.f; }
+        __syncwarp();
+        s[GS_DR2 + lane] = (s[GS_DBF] * RO[RO_W2 + lane] + s[GS_DBF + 1] * RO[RO_W2 + 32 + lane]) * actd(s[GS_R2P + lane], a.act_p);
+        __syncwarp();
+        {
+            float acc = 0.f;
+            for (int r = 0; r < 32; ++r) acc = fmaf(s[GS_DR2 + r], RO[RO_W1 + r * 32 + lane], acc);
+            s[GS_DR1 + lane] = acc * actd(s[GS_R1P + lane], a.act_p);
+        }
+        __syncwarp();
+        float dz = 0.f, dz32 = 0.f;
+        for (int r = 0; r < 32; ++r) dz = fmaf(s[GS_DR1 + r], RO[RO_W0 + r * 33 + lane], dz);
+        if (lane == 0) for (int r = 0; r < 32; ++r) dz32 = fmaf(s[GS_DR1 + r], RO[RO_W0 + r * 33 + 32], dz32);
+        if (a.dqn) {
+            const float dqc = s[GS_DQC];
+            s[GS_DO2 + lane] = dqc * QO[QO_W2 + lane] * s[GS_MO2 + lane] * actd(s[GS_O2P + lane], a.act_d);
+            __syncwarp();
+            {
+                float acc = 0.f;
+                for (int r = 0; r < 32; ++r) acc = fmaf(s[GS_DO2 + r], QO[QO_W1 + r * 32 + lane], acc);
+                s[GS_DO1 + lane] = acc * s[GS_MO1 + lane] * actd(s[GS_O1P + lane], a.act_d);
+            }
+            __syncwarp();
+            if (lane < 18) {
+                float acc = 0.f;
+                for (int r = 0; r < 32; ++r) acc = fmaf(s[GS_DO1 + r], QO[QO_W0 + r * 18 + lane], acc);
+                if (lane < 16) s[GS_DE2 + lane] = acc;
+                else if ((lane == 16 ? a.qx0 : a.qx1) == RLVD_QX_DELTA_E) s[GS_RES + 2 + (lane - 16)] = acc; else s[GS_RES + 2 + (lane - 16)] = 0.f;
+            }
+            __syncwarp();
+            if (lane < 16) {
+                float acc = 0.f;
+                for (int r = 0; r < 16; ++r) acc = fmaf(s[GS_DE2 + r], QE[QE_W1 + r * 16 + lane], acc);
+                s[GS_DE1 + lane] = acc * s[GS_ME1 + lane] * actd(s[GS_E1P + lane], a.act_d);
+            }
+            __syncwarp();
+            for (int r = 0; r < 16; ++r) dz = fmaf(s[GS_DE1 + r], QE[QE_W0 + r * 33 + lane], dz);
+            if (lane == 0) {
+                for (int r = 0; r < 16; ++r) dz32 = fmaf(s[GS_DE1 + r], QE[QE_W0 + r * 33 + 32], dz32);
+                gde += s[GS_RES + 2] + s[GS_RES + 3];
+            }
+        }
+        a.gh[g * 32 + lane] = dz;
+        if (lane == 0) a.gde[g] = gde + dz32 * (a.std_de ? 1.0f / a.std_de_v : 1.0f);
+    }
+    __syncthreads();
+    // ---- parameter gradients of the three graph-level heads
+    constexpr int NRO = 2210, NQE = 816, NQO = 1697;
+    for (int p = tid; p < NRO + NQE + NQO; p += 256) {
+        int d_off, in_off, n_in, i;
+        int64_t dst;
+        if (p < NRO) {
+            dst = P_RO + p;
+            if (p < RO_B0) { d_off = GS_DR1; in_off = GS_Z; n_in = 33; i = p - RO_W0; }
+            else if (p < RO_W1) { d_off = GS_DR1; in_off = 0; n_in = 0; i = p - RO_B0; }
+            else if (p < RO_B1) { d_off = GS_DR2; in_off = GS_R1; n_in = 32; i = p - RO_W1; }
+            else if (p < RO_W2) { d_off = GS_DR2; in_off = 0; n_in = 0; i = p - RO_B1; }
+            else if (p < RO_B2) { d_off = GS_DBF; in_off = GS_R2; n_in = 32; i = p - RO_W2; }
+            else { d_off = GS_DBF; in_off = 0; n_in = 0; i = p - RO_B2; }
+        } else if (p < NRO + NQE) {
+            const int q = p - NRO;
+            dst = P_QE + q;
+            if (q < QE_B0) { d_off = GS_DE1; in_off = GS_Z; n_in = 33; i = q - QE_W0; }
+            else if (q < QE_W1) { d_off = GS_DE1; in_off = 0; n_in = 0; i = q - QE_B0; }
+            else if (q < QE_B1) { d_off = GS_DE2; in_off = GS_E1; n_in = 16; i = q - QE_W1; }
+            else { d_off = GS_DE2; in_off = 0; n_in = 0; i = q - QE_B1; }
+        } else {
+            const int q = p - NRO - NQE;
+            dst = P_QO + q;
+            if (q < QO_B0) { d_off = GS_DO1; in_off = GS_T; n_in = 18; i = q - QO_W0; }
+            else if (q < QO_W1) { d_off = GS_DO1; in_off = 0; n_in = 0; i = q - QO_B0; }
+            else if (q < QO_B1) { d_off = GS_DO2; in_off = GS_O1; n_in = 32; i = q - QO_W1; }
+            else if (q < QO_W2) { d_off = GS_DO2; in_off = 0; n_in = 0; i = q - QO_B1; }
+            else if (q < QO_B2) { d_off = GS_DQC; in_off = GS_O2; n_in = 32; i = q - QO_W2; }
+            else { d_off = GS_DQC; in_off = 0; n_in = 0; i = q - QO_B2; }
+        }
+        float gsum = 0.f;
+        if (p < NRO || a.dqn) {
+            const int r = n_in > 0 ? i / n_in : i, cidx = n_in > 0 ? i % n_in : 0;
+            for (int g = 0; g < a.G; ++g) {
+                const float* s = a.S + (int64_t)g * GS_PER;
+                gsum = n_in > 0 ? fmaf(s[d_off + r], s[in_off + cidx], gsum) : gsum + s[d_off + r];
+            }
+        }
+        a.Gr[dst] = gsum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ clip + Adam
+// total = sqrt(sum over trainable g^2): two-stage fixed-tree reduction.  stage 1: grid = nb blocks of 256
+__global__ void __launch_bounds__(256) sqsum_kernel(int64_t n, const float* __restrict__ g, const uint8_t* __restrict__ mask,
+                                                    float* __restrict__ part) {
+    __shared__ float red[256];
+    float v = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const float x = (mask == nullptr || mask[i]) ? g[i] : 0.f;
+        v = fmaf(x, x, v);
+    }
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void norm_finish_kernel(int nb, const float* __restrict__ part, float max_norm, float* __restrict__ out /* norm, coef */) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float v = 0.f;
+    for (int b = 0; b < nb; ++b) v += part[b];
+    const float norm = sqrtf(v);
+    const float coef = max_norm / (norm + 1e-6f);        // torch.nn.utils.clip_grad_norm_
+    out[0] = norm;
+    out[1] = max_norm > 0.f && coef < 1.0f ? coef : 1.0f;
+}
+__global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, const uint8_t* __restrict__ mask,
+                            float* __restrict__ m, float* __restrict__ v, const float* __restrict__ clip, float lr, float b1, float b2,
+                            float eps, float bc1, float bc2_sqrt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (mask != nullptr && !mask[i])) return;
+    const float gr = g[i] * clip[1];
+    const float mi = b1 * m[i] + (1.0f - b1) * gr;
+    const float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+}
+
+// ------------------------------------------------------------------------------------------------ host-side helpers
+struct Bump {
+    char* base;
+    size_t off = 0, cap;
+    float* f(size_t n) {
+        float* p = reinterpret_cast<float*>(base + off);
+        off += ((n * sizeof(float) + 255) / 256) * 256;
+        return p;
+    }
+};
+
+struct Ctx {
+    rlvd_engine* e;
+    cudaStream_t s;
+    int launches = 0;
+};
+
+inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+// C = A B (+bias); op flags as in sgemm_kernel
+void gemm(Ctx& c, bool TA, bool TB, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+          const float* bias, bool acc) {
+    if (M <= 0 || N <= 0) return;
+    dim3 grid((M + GT - 1) / GT, (N + GT - 1) / GT, 1);
+    if (TA && TB) sgemm_kernel<true, true><<<grid, 256, 0, c.s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, K, 0);
+    else if (TA) sgemm_kernel<true, false><<<grid, 256, 0, c.s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, K, 0);
+    else if (TB) sgemm_kernel<false, true><<<grid, 256, 0, c.s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, K, 0);
+    else sgemm_kernel<false, false><<<grid, 256, 0, c.s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, K, 0);
+    ++c.launches;
+}
+// weight gradient: dst[N][K] (ld = ldd) = Gm^T A with Gm [rows][N], A [rows][K]; split over rows, ordered partial sums
+void wgrad(Ctx& c, int rows, int N, int K, const float* Gm, int ldg, const float* A, int lda, float* dst, int ldd, float* part) {
+    const int S = std::max(1, std::min(64, (rows + 511) / 512));
+    const int kchunk = ((rows + S - 1) / S + GK - 1) / GK * GK;
+    dim3 grid((N + GT - 1) / GT, (K + GT - 1) / GT, S);
+    sgemm_kernel<true, false><<<grid, 256, 0, c.s>>>(N, K, rows, Gm, ldg, A, lda, part, K, nullptr, 0, kchunk, (int64_t)N * K);
+    if (ldd == K) {
+        reduce_partials_kernel<<<nblk((int64_t)N * K), 256, 0, c.s>>>((int64_t)N * K, S, part, dst, 0);
+    } else {      // a column block of a wider weight (intra-atomic layer 0: [F][2F])
+        float* tmp = part + (int64_t)S * N * K;
+        reduce_partials_kernel<<<nblk((int64_t)N * K), 256, 0, c.s>>>((int64_t)N * K, S, part, tmp, 0);
+        cudaMemcpy2DAsync(dst, (size_t)ldd * 4, tmp, (size_t)K * 4, (size_t)K * 4, N, cudaMemcpyDeviceToDevice, c.s);
+    }
+    c.launches += 2;
+}
+void colsum(Ctx& c, int rows, int cols, const float* X, int ld, float* out) {
+    colsum_kernel<<<nblk(cols, 32), 256, 0, c.s>>>(rows, cols, X, ld, out, 0);
+    ++c.launches;
+}
+
+}  // namespace
+
+// ================================================================================================== the training step
+int train_forward_backward(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_t E, const int* node_ptr, const int* Z,
+                           const float* pos, const float* cell, const int* node_struct, const int* row_ptr, const int* col,
+                           const int8_t* shift, int G, const rlvd_q_params& qp, const float* d_temp, int mode, const float* target0,
+                           const float* target1, const float* drop_u, float p_drop, const float* P, float* Gr, float* d_loss,
+                           float* d_pred, float* d_q_out) {
+    (void)E;
+    RLVD_CHECK(n_struct == 2 * G && M % 2 == 0, "train: the batch must hold G reactant structures followed by their G products");
+    const int Mr = M / 2;
+    const size_t MF = (size_t)M * F;
+    // ---- workspace
+    size_t need = 0;
+    auto rnd = [](size_t n) { return ((n * 4 + 255) / 256) * 256; };
+    need += 4 * rnd(MF) + 4 * rnd(3 * MF);                                       // Q[0..3], MU[0..3]
+    need += NLAYER * (rnd(MF) * 7 + rnd(3 * MF) * 3 + rnd(6 * MF));              // per layer saves
+    need += rnd((size_t)NLAYER * (NRBF + 1) * 3 * F);                            // filt_T
+    need += 2 * rnd((size_t)M * 64) + 2 * rnd(M) + 3 * rnd(G) + 3 * rnd((size_t)Mr * F) + rnd((size_t)Mr * 32) + rnd((size_t)G * 32);
+    need += rnd((size_t)G * GS_PER) + rnd((size_t)G * 32) + rnd(G);              // graph heads
+    need += rnd(MF) + 2 * rnd(3 * MF) + rnd(3 * MF) + rnd(MF) + rnd(2 * MF) + rnd(6 * MF) + rnd(3 * MF);   // backward buffers
+    need += rnd((size_t)M * 64) + rnd(M) + rnd((size_t)Mr * 32) + 2 * rnd((size_t)Mr * F);
+    const int rpc = std::max(8, (M + 1183) / 1184);
+    const int n_cta = (M + rpc - 1) / rpc;
+    need += rnd((size_t)n_cta * 3 * (NRBF + 1) * F);
+    need += rnd((size_t)65 * 3 * F * F);                                         // split-K partials + repack tile
+    need += 4096;
+    if (e->train_ws.ensure(need)) return 1;
+    Bump ws{reinterpret_cast<char*>(e->train_ws.p), 0, e->train_ws.cap};
+    Ctx c{e, s};
+    float *Q[4], *MU[4];
+    for (int l = 0; l < 4; ++l) Q[l] = ws.f(MF);
+    for (int l = 0; l < 4; ++l) MU[l] = ws.f(3 * MF);
+    float *h1pre[NLAYER], *h1[NLAYER], *xs[NLAYER], *qmid[NLAYER], *mumid[NLAYER], *mix[NLAYER], *nrm[NLAYER], *vw[NLAYER],
+        *h2pre[NLAYER], *h2[NLAYER], *ctx[NLAYER];
+    for (int l = 0; l < NLAYER; ++l) {
+        h1pre[l] = ws.f(MF); h1[l] = ws.f(MF); xs[l] = ws.f(3 * MF); qmid[l] = ws.f(MF); mumid[l] = ws.f(3 * MF);
+        mix[l] = ws.f(6 * MF); nrm[l] = ws.f(MF); vw[l] = ws.f(MF); h2pre[l] = ws.f(MF); h2[l] = ws.f(MF); ctx[l] = ws.f(3 * MF);
+    }
+    float* filt_T = ws.f((size_t)NLAYER * (NRBF + 1) * 3 * F);
+    float* en_pre = ws.f((size_t)M * 64); float* en_h = ws.f((size_t)M * 64); float* e_raw = ws.f(M); float* e_atom = ws.f(M);
+    float* ER = ws.f(G); float* EP = ws.f(G); float* dE = ws.f(G);
+    float* dnode = ws.f((size_t)Mr * F); float* rr_pre = ws.f((size_t)Mr * F); float* rr_h = ws.f((size_t)Mr * F);
+    float* hatom = ws.f((size_t)Mr * 32); float* hpool = ws.f((size_t)G * 32);
+    float* gS = ws.f((size_t)G * GS_PER); float* gh = ws.f((size_t)G * 32); float* gde = ws.f(G);
+    float* gq = ws.f(MF); float* gmuA = ws.f(3 * MF); float* gmuB = ws.f(3 * MF); float* gctx = ws.f(3 * MF); float* ghid = ws.f(MF);
+    float* gcat = ws.f(2 * MF); float* gmix = ws.f(6 * MF); float* gx = ws.f(3 * MF);
+    float* g_enh = ws.f((size_t)M * 64); float* g_eraw = ws.f(M); float* ghatom = ws.f((size_t)Mr * 32);
+    float* g_rrh = ws.f((size_t)Mr * F); float* gd = ws.f((size_t)Mr * F);
+    float* wpart = ws.f((size_t)n_cta * 3 * (NRBF + 1) * F);
+    float* part = ws.f((size_t)65 * 3 * F * F);
+    RLVD_CHECK(ws.off <= ws.cap, "train: workspace accounting error");
+    const int act_p = qp.painn_head_act;
+
+    RLVD_CUDA(cudaMemsetAsync(Gr, 0, (size_t)NPARAM * 4, s));
+    // ================= forward =================
+    build_filt_kernel<<<nblk(NLAYER * (NRBF + 1) * 3 * F), 256, 0, s>>>(P + P_FW, P + P_FB, filt_T);
+    embed_train_kernel<<<nblk(MF), 256, 0, s>>>(M, Z, P + P_EMB, Q[0]);
+    RLVD_CUDA(cudaMemsetAsync(MU[0], 0, 3 * MF * 4, s));
+    c.launches += 2;
+    for (int l = 0; l < NLAYER; ++l) {
+        const float* PI = P + P_INTER + l * INTER_STRIDE;
+        const float* PM = P + P_MIX + l * MIX_STRIDE;
+        gemm(c, false, true, M, F, F, Q[l], F, PI + I_W0, F, h1pre[l], F, PI + I_B0, false);
+        act_fwd_kernel<<<nblk(MF), 256, 0, s>>>(MF, h1pre[l], h1[l], RLVD_ACT_SILU);
+        gemm(c, false, true, M, 3 * F, F, h1[l], F, PI + I_W3, F, xs[l], 3 * F, PI + I_B3, false);
+        RLVD_CUDA(cudaMemcpyAsync(qmid[l], Q[l], MF * 4, cudaMemcpyDeviceToDevice, s));
+        EdgeArgs ea;
+        ea.layer = l; ea.M = M; ea.n_struct = n_struct; ea.node_ptr = node_ptr; ea.row_ptr = row_ptr; ea.col = col; ea.shift = shift;
+        ea.pos = pos; ea.cell = cell; ea.node_struct = node_struct; ea.x = xs[l]; ea.mu_in = l == 0 ? nullptr : MU[l];
+        ea.q = qmid[l]; ea.mu_out = mumid[l];
+        if (launch_edge_simt(e, s, filt_T + (size_t)l * (NRBF + 1) * 3 * F, P + P_FREQ, e->w.cutoff, ea)) return 1;
+        gemm(c, false, true, 3 * M, 2 * F, F, mumid[l], F, PM + X_WM, F, mix[l], 2 * F, nullptr, false);
+        mix_reduce_train_kernel<<<nblk(MF), 256, 0, s>>>(M, mix[l], nrm[l], vw[l], e->eps);
+        gemm(c, false, true, M, F, F, qmid[l], F, PM + X_W0, 2 * F, h2pre[l], F, PM + X_B0, false);
+        gemm(c, false, true, M, F, F, nrm[l], F, PM + X_W0 + F, 2 * F, h2pre[l], F, nullptr, true);
+        act_fwd_kernel<<<nblk(MF), 256, 0, s>>>(MF, h2pre[l], h2[l], RLVD_ACT_SILU);
+        gemm(c, false, true, M, 3 * F, F, h2[l], F, PM + X_W3, F, ctx[l], 3 * F, PM + X_B3, false);
+        mix_update_train_kernel<<<nblk(MF), 256, 0, s>>>(M, ctx[l], mix[l], vw[l], qmid[l], mumid[l], Q[l + 1], MU[l + 1]);
+        c.launches += 5;
+    }
+    const float* qf = Q[NLAYER];
+    if (d_q_out != nullptr) RLVD_CUDA(cudaMemcpyAsync(d_q_out, qf, MF * 4, cudaMemcpyDeviceToDevice, s));
+    // heads, node level
+    const float* PEN = P + P_EN;
+    const float* PRR = P + P_RR;
+    gemm(c, false, true, M, 64, F, qf, F, PEN + EN_W0, F, en_pre, 64, PEN + EN_B0, false);
+    act_fwd_kernel<<<nblk((int64_t)M * 64), 256, 0, s>>>((int64_t)M * 64, en_pre, en_h, act_p);
+    gemm(c, false, true, M, 1, 64, en_h, 64, PEN + EN_W3, 64, e_raw, 1, PEN + EN_B3, false);
+    energy_scale_kernel<<<nblk(M), 256, 0, s>>>(M, Z, e->w.elem_lookup, P + P_SC, P + P_SH, e_raw, e_atom);
+    energy_pool_kernel<<<G, 32, 0, s>>>(G, Mr, node_ptr, e_atom, ER, EP, dE);
+    node_diff_kernel<<<nblk((int64_t)Mr * F), 256, 0, s>>>((int64_t)Mr * F, qf, (int64_t)Mr * F, dnode);
+    gemm(c, false, true, Mr, F, F, dnode, F, PRR + RR_W0, F, rr_pre, F, PRR + RR_B0, false);
+    act_fwd_kernel<<<nblk((int64_t)Mr * F), 256, 0, s>>>((int64_t)Mr * F, rr_pre, rr_h, act_p);
+    gemm(c, false, true, Mr, 32, F, rr_h, F, PRR + RR_W3, F, hatom, 32, PRR + RR_B3, false);
+    feat_pool_kernel<<<G, 32, 0, s>>>(G, node_ptr, hatom, hpool);
+    c.launches += 7;
+    // heads, graph level: forward + loss + backward
+    GraphHeadArgs ga;
+    ga.G = G; ga.mode = mode; ga.dqn = qp.dqn; ga.act_p = act_p; ga.act_d = qp.dqn_head_act; ga.std_de = qp.delta_e_standardised;
+    ga.qx0 = qp.q_extra[0]; ga.qx1 = qp.q_extra[1]; ga.alpha = qp.alpha; ga.beta = qp.beta; ga.temperature = qp.temperature;
+    ga.p_drop = p_drop; ga.mean_b = qp.mean_barrier; ga.std_b = qp.std_barrier; ga.mean_f = qp.mean_freq; ga.std_f = qp.std_freq;
+    ga.mean_de = qp.mean_delta_e; ga.std_de_v = qp.std_delta_e; ga.P = P; ga.Gr = Gr; ga.hpool = hpool; ga.dE = dE; ga.d_temp = d_temp;
+    ga.target0 = target0; ga.target1 = target1; ga.drop_u = drop_u; ga.S = gS; ga.gh = gh; ga.gde = gde; ga.pred = d_pred; ga.loss = d_loss;
+    graph_heads_kernel<<<1, 256, 0, s>>>(ga);
+    ++c.launches;
+    // ================= backward: heads, node level =================
+    // energy_output
+    energy_bwd_kernel<<<1, 256, 0, s>>>(M, Mr, G, Z, e->w.elem_lookup, node_struct, P + P_SC, e_raw, gde, g_eraw, Gr + P_SC, Gr + P_SH);
+    wgrad(c, M, 1, 64, g_eraw, 1, en_h, 64, Gr + P_EN + EN_W3, 64, part);
+    colsum(c, M, 1, g_eraw, 1, Gr + P_EN + EN_B3);
+    gemm(c, false, false, M, 64, 1, g_eraw, 1, PEN + EN_W3, 64, g_enh, 64, nullptr, false);
+    act_bwd_kernel<<<nblk((int64_t)M * 64), 256, 0, s>>>((int64_t)M * 64, en_pre, g_enh, act_p);
+    wgrad(c, M, 64, F, g_enh, 64, qf, F, Gr + P_EN + EN_W0, F, part);
+    colsum(c, M, 64, g_enh, 64, Gr + P_EN + EN_B0);
+    gemm(c, false, false, M, F, 64, g_enh, 64, PEN + EN_W0, F, gq, F, nullptr, false);
+    // reaction_representation
+    feat_unpool_kernel<<<nblk((int64_t)Mr * 32), 256, 0, s>>>(Mr, node_struct, gh, ghatom);
+    wgrad(c, Mr, 32, F, ghatom, 32, rr_h, F, Gr + P_RR + RR_W3, F, part);
+    colsum(c, Mr, 32, ghatom, 32, Gr + P_RR + RR_B3);
+    gemm(c, false, false, Mr, F, 32, ghatom, 32, PRR + RR_W3, F, g_rrh, F, nullptr, false);
+    act_bwd_kernel<<<nblk((int64_t)Mr * F), 256, 0, s>>>((int64_t)Mr * F, rr_pre, g_rrh, act_p);
+    wgrad(c, Mr, F, F, g_rrh, F, dnode, F, Gr + P_RR + RR_W0, F, part);
+    colsum(c, Mr, F, g_rrh, F, Gr + P_RR + RR_B0);
+    gemm(c, false, false, Mr, F, F, g_rrh, F, PRR + RR_W0, F, gd, F, nullptr, false);
+    diff_bwd_kernel<<<nblk((int64_t)Mr * F), 256, 0, s>>>((int64_t)Mr * F, gd, (int64_t)Mr * F, gq);
+    c.launches += 5;
+    // ================= backward: representation =================
+    float* gmu = gmuA;
+    float* gmu_next = gmuB;
+    RLVD_CUDA(cudaMemsetAsync(gmu, 0, 3 * MF * 4, s));          // mu after the last block feeds nothing
+    for (int l = NLAYER - 1; l >= 0; --l) {
+        const float* PI = P + P_INTER + l * INTER_STRIDE;
+        const float* PM = P + P_MIX + l * MIX_STRIDE;
+        float* GI = Gr + P_INTER + l * INTER_STRIDE;
+        float* GM = Gr + P_MIX + l * MIX_STRIDE;
+        // ---- mixing block
+        mix_bwd1_kernel<<<nblk(MF), 256, 0, s>>>(M, gq, gmu, mix[l], vw[l], gctx);
+        wgrad(c, M, 3 * F, F, gctx, 3 * F, h2[l], F, GM + X_W3, F, part);
+        colsum(c, M, 3 * F, gctx, 3 * F, GM + X_B3);
+        gemm(c, false, false, M, F, 3 * F, gctx, 3 * F, PM + X_W3, F, ghid, F, nullptr, false);
+        act_bwd_kernel<<<nblk(MF), 256, 0, s>>>(MF, h2pre[l], ghid, RLVD_ACT_SILU);
+        wgrad(c, M, F, F, ghid, F, qmid[l], F, GM + X_W0, 2 * F, part);
+        wgrad(c, M, F, F, ghid, F, nrm[l], F, GM + X_W0 + F, 2 * F, part);
+        colsum(c, M, F, ghid, F, GM + X_B0);
+        gemm(c, false, false, M, 2 * F, F, ghid, F, PM + X_W0, 2 * F, gcat, 2 * F, nullptr, false);
+        mix_bwd2_kernel<<<nblk(MF), 256, 0, s>>>(M, gq, gmu, mix[l], nrm[l], ctx[l], gcat, gmix);
+        wgrad(c, 3 * M, 2 * F, F, gmix, 2 * F, mumid[l], F, GM + X_WM, F, part);
+        gemm(c, false, false, 3 * M, F, 2 * F, gmix, 2 * F, PM + X_WM, F, gmu, F, nullptr, true);       // gmu_mid = gmu_out + gmix Wmix
+        add_strided_kernel<<<nblk(MF), 256, 0, s>>>(M, F, gcat, 2 * F, gq, F);                            // gq_mid = gq_out + gcat[:, :F]
+        c.launches += 4;
+        // ---- interaction block
+        const float* ft = filt_T + (size_t)l * (NRBF + 1) * 3 * F;
+        if (l == 0)
+            edge_bwd_kernel<false><<<n_cta, EB_THREADS, 0, s>>>(M, rpc, ft, P + P_FREQ, row_ptr, col, shift, pos, cell, node_struct, xs[l],
+                                                               nullptr, gq, gmu, gx, nullptr, wpart, e->w.cutoff);
+        else
+            edge_bwd_kernel<true><<<n_cta, EB_THREADS, 0, s>>>(M, rpc, ft, P + P_FREQ, row_ptr, col, shift, pos, cell, node_struct, xs[l],
+                                                              MU[l], gq, gmu, gx, gmu_next, wpart, e->w.cutoff);
+        edge_wgrad_reduce_kernel<<<nblk(3 * (NRBF + 1) * F), 256, 0, s>>>(n_cta, l, wpart, Gr + P_FW, Gr + P_FB);
+        wgrad(c, M, 3 * F, F, gx, 3 * F, h1[l], F, GI + I_W3, F, part);
+        colsum(c, M, 3 * F, gx, 3 * F, GI + I_B3);
+        gemm(c, false, false, M, F, 3 * F, gx, 3 * F, PI + I_W3, F, ghid, F, nullptr, false);
+        act_bwd_kernel<<<nblk(MF), 256, 0, s>>>(MF, h1pre[l], ghid, RLVD_ACT_SILU);
+        wgrad(c, M, F, F, ghid, F, Q[l], F, GI + I_W0, F, part);
+        colsum(c, M, F, ghid, F, GI + I_B0);
+        gemm(c, false, false, M, F, F, ghid, F, PI + I_W0, F, gq, F, nullptr, true);                      // gq_in = gq_mid + ghid W0
+        c.launches += 3;
+        float* t = gmu; gmu = gmu_next; gmu_next = t;
+    }
+    embed_bwd_kernel<<<100, F, 0, s>>>(M, Z, gq, Gr + P_EMB);
+    ++c.launches;
+    e->launches += c.launches;
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int adam_step(rlvd_engine* e, cudaStream_t s, int64_t n, float* params, const float* grads, const uint8_t* mask, float* m, float* v,
+              float lr, float b1, float b2, float eps, float max_norm, int step, float* d_grad_norm) {
+    if (e->train_ws.ensure(4096 + 1024 * 4)) return 1;
+    float* part = reinterpret_cast<float*>(e->train_ws.p);        // [592] partial sums, then [2] norm / clip coefficient
+    const int nb = 592;
+    float* out = d_grad_norm != nullptr ? d_grad_norm : part + 1000;
+    sqsum_kernel<<<nb, 256, 0, s>>>(n, grads, mask, part);
+    norm_finish_kernel<<<1, 32, 0, s>>>(nb, part, max_norm, out);
+    const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
+    adam_kernel<<<nblk(n), 256, 0, s>>>(n, params, grads, mask, m, v, out, lr, b1, b2, eps, bc1, sqrtf(bc2));
+    e->launches += 3;
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rlvd
+
+using namespace rlvd;
+
+extern "C" {
+
+int64_t rlvd_train_param_count(void) { return NPARAM; }
+
+int rlvd_train_layout(int32_t index, const char** name, int64_t* offset, int64_t* numel, int32_t* trainable) {
+    const auto& tab = layout();
+    if (index < 0 || index >= (int32_t)tab.size()) return 1;
+    if (name) *name = tab[index].name.c_str();
+    if (offset) *offset = tab[index].offset;
+    if (numel) *numel = tab[index].numel;
+    if (trainable) *trainable = tab[index].trainable;
+    return 0;
+}
+
+int rlvd_train_forward_backward(rlvd_engine* e, void* stream, int32_t n_struct, int32_t n_nodes, int64_t n_edges,
+                                const int32_t* d_node_ptr, const int32_t* d_Z, const float* d_pos, const float* d_cell,
+                                const int32_t* d_node_struct, const int32_t* d_row_ptr, const int32_t* d_col, const int8_t* d_shift,
+                                int32_t n_react, const rlvd_q_params* qp, const float* d_temperature, int32_t loss_mode,
+                                const float* d_target0, const float* d_target1, const float* d_dropout_uniform, float dropout_p,
+                                const float* d_params, float* d_grads, float* d_loss, float* d_pred, float* d_q) {
+    RLVD_CHECK(e != nullptr && e->finalized, "rlvd_train_forward_backward: the engine needs finalized weights (species lookup, cutoff)");
+    RLVD_CHECK(qp && d_params && d_grads && d_loss && d_pred && d_target0 && n_react > 0 && n_nodes > 0, "rlvd_train_forward_backward: bad argument");
+    RLVD_CHECK(loss_mode == 0 || (loss_mode == 1 && d_target1 != nullptr), "rlvd_train_forward_backward: loss_mode 0 (dqn) or 1 (context bandit: q0 and q1 labels)");
+    RLVD_CHECK(dropout_p >= 0.f && dropout_p < 1.f, "rlvd_train_forward_backward: dropout_p out of range");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return train_forward_backward(e, (cudaStream_t)stream, n_struct, n_nodes, n_edges, d_node_ptr, d_Z, d_pos, d_cell, d_node_struct,
+                                  d_row_ptr, d_col, d_shift, n_react, *qp, d_temperature, loss_mode, d_target0, d_target1,
+                                  d_dropout_uniform, dropout_p, d_params, d_grads, d_loss, d_pred, d_q);
+}
+
+int rlvd_adam_step(rlvd_engine* e, void* stream, int64_t n, float* d_params, const float* d_grads, const uint8_t* d_trainable,
+                   float* d_exp_avg, float* d_exp_avg_sq, float lr, float beta1, float beta2, float eps, float max_norm, int32_t step,
+                   float* d_grad_norm) {
+    RLVD_CHECK(e != nullptr && n > 0 && d_params && d_grads && d_exp_avg && d_exp_avg_sq && step >= 1, "rlvd_adam_step: bad argument");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return adam_step(e, (cudaStream_t)stream, n, d_params, d_grads, d_trainable, d_exp_avg, d_exp_avg_sq, lr, beta1, beta2, eps,
+                     max_norm, step, d_grad_norm);
+}
+
+}  // extern "C"

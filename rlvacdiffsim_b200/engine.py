@@ -100,6 +100,7 @@ class Engine:
             from .structures import SYMBOL_TO_Z
             zs = np.asarray([SYMBOL_TO_Z[s] if isinstance(s, str) else int(s) for s in species], dtype=np.int32)
             check(self.lib.rlvd_set_species(self._h, zs.ctypes.data_as(C.c_void_p), int(zs.size)))
+        check(self.lib.rlvd_set_hyper(self._h, b"epsilon", float(rm.get("epsilon", 1e-8))))
         check(self.lib.rlvd_finalize_weights(self._h))
         self.cutoff = float(rm["cutoff"])
         self.means = {k: float(v) for k, v in rm["means"].items()}
@@ -223,6 +224,66 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.lib.rlvd_get_weight(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), numel))
         return out
+
+    # ------------------------------------------------------------------ B1, train_all = True: the whole model
+    _TRAIN_LAYOUT = None
+
+    @classmethod
+    def train_layout(cls):
+        """``[(checkpoint name, offset, numel, trainable)]`` of the flat parameter / gradient vector (``rlvd_train_layout``)."""
+        if cls._TRAIN_LAYOUT is None:
+            lib = _lib.load()
+            tab, i = [], 0
+            name, off, n, tr = C.c_char_p(), C.c_int64(), C.c_int64(), C.c_int32()
+            while lib.rlvd_train_layout(i, C.byref(name), C.byref(off), C.byref(n), C.byref(tr)) == 0:
+                tab.append((name.value.decode(), int(off.value), int(n.value), bool(tr.value)))
+                i += 1
+            assert tab[-1][1] + tab[-1][2] == lib.rlvd_train_param_count()
+            cls._TRAIN_LAYOUT = tab
+        return cls._TRAIN_LAYOUT
+
+    def flatten_state(self, state_dict: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Every floating-point checkpoint tensor, in ``train_layout`` order, as one fp32 device vector."""
+        flat = torch.empty(self.lib.rlvd_train_param_count(), dtype=torch.float32)
+        for name, off, n, _ in self.train_layout():
+            t = state_dict[name].detach().to("cpu", torch.float32).reshape(-1)
+            if t.numel() != n:
+                raise ValueError(f"{name}: {t.numel()} elements, the kernels expect {n}")
+            flat[off:off + n] = t
+        return flat.to(self.device)
+
+    def train_forward_backward(self, Z, pos, cell, node_ptr, node_struct, row_ptr, col, shift, n_react: int, qp: QParams,
+                               params: torch.Tensor, grads: torch.Tensor, target0: torch.Tensor,
+                               target1: Optional[torch.Tensor] = None, mode: str = "dqn",
+                               temperature: Optional[torch.Tensor] = None, dropout_uniform: Optional[torch.Tensor] = None,
+                               dropout_p: float = 0.0, return_q: bool = False) -> Dict[str, torch.Tensor]:
+        """``rlvd_train_forward_backward``: loss, predictions and the UNCLIPPED gradient of every parameter for one replay
+        minibatch (``trainer.py:166-172`` / ``:89-92``).  ``grads`` is overwritten."""
+        M, dev = pos.shape[0], self.device
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        pred = torch.empty((n_react, 3), dtype=torch.float32, device=dev)
+        q = torch.empty((M, 128), dtype=torch.float32, device=dev) if return_q else None
+        with torch.cuda.device(dev):
+            check(self.lib.rlvd_train_forward_backward(
+                self._h, self._stream(), node_ptr.numel() - 1, M, col.shape[0], _ptr(node_ptr), _ptr(Z), _ptr(pos), _ptr(cell),
+                _ptr(node_struct), _ptr(row_ptr), _ptr(col), _ptr(shift), n_react, C.byref(qp), _ptr(temperature),
+                0 if mode == "dqn" else 1, _ptr(target0), _ptr(target1), _ptr(dropout_uniform), float(dropout_p), _ptr(params),
+                _ptr(grads), _ptr(loss), _ptr(pred), _ptr(q)))
+        out = {"loss": loss, "rl_q": pred[:, 0], "q0": pred[:, 1], "q1": pred[:, 2]}
+        if return_q:
+            out["q"] = q
+        return out
+
+    def adam_step(self, params: torch.Tensor, grads: torch.Tensor, state: Dict[str, torch.Tensor], lr: float,
+                  max_norm: float, trainable: Optional[torch.Tensor] = None, betas=(0.9, 0.999), eps: float = 1e-8) -> torch.Tensor:
+        """``clip_grad_norm_(max_norm)`` + ``torch.optim.Adam.step`` in place on ``params``; → [total norm, clip coefficient]."""
+        info = torch.empty(2, dtype=torch.float32, device=self.device)
+        state["step"] = int(state["step"]) + 1
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_adam_step(self._h, self._stream(), params.numel(), _ptr(params), _ptr(grads), _ptr(trainable),
+                                          _ptr(state["exp_avg"]), _ptr(state["exp_avg_sq"]), float(lr), float(betas[0]),
+                                          float(betas[1]), float(eps), float(max_norm), int(state["step"]), _ptr(info)))
+        return info
 
     # ------------------------------------------------------------------ A1: candidate hops on the device
     def action_space(self, pos: torch.Tensor, cells: torch.Tensor, node_ptr: torch.Tensor, lattice_parameter: float,

@@ -238,6 +238,67 @@ class DQNv2(nn.Module, _EngineMixin):
         res["frozen_rl_q"] = out["rl_q"]          # eval-mode prediction with the pre-update weights
         return res
 
+    # ---- B1, train_all = True: forward + backward of the whole model on a flat parameter vector (csrc/train_full.cu)
+    def new_train_state(self, device) -> dict:
+        """Flat fp32 parameters (checkpoint order), gradient bucket, Adam moments and the trainable mask
+        (``requires_grad`` of the module's parameters: ``Trainer(train_all=False)`` freezes ``reaction_model.*``)."""
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        eng = self._engine_for(dev)
+        params = eng.flatten_state(self.state_dict())
+        req = {n: p.requires_grad for n, p in self.named_parameters()}
+        mask = torch.zeros(params.numel(), dtype=torch.uint8)
+        for name, off, n, trainable in eng.train_layout():
+            if trainable and req.get(name, False):
+                mask[off:off + n] = 1
+        z = lambda: torch.zeros_like(params)
+        return {"params": params, "grads": z(), "exp_avg": z(), "exp_avg_sq": z(), "step": 0, "mask": mask.to(dev),
+                "device": dev}
+
+    def train_forward_backward(self, batch, q_params: Dict[str, float | bool], state: dict, target0: torch.Tensor,
+                               target1: Optional[torch.Tensor] = None, mode: str = "dqn",
+                               dropout_uniform: Optional[torch.Tensor] = None, return_q: bool = False) -> dict:
+        """``output = self(batch, q_params); loss = ...; loss.backward()`` of ``trainer.py:89-92,166-172`` with the
+        parameters of ``state`` (not the module's): fills ``state["grads"]`` (unclipped) and returns loss / predictions.
+        ``mode="dqn"``: ``mean((target0 - rl_q)**2)``; ``mode="bandit"``: ``mse(q0, target0) + mse(q1, target1)``."""
+        dev = state["device"]
+        eng = self._engine_for(dev)
+        G = batch.num_graphs
+        pos = batch["pos"].to(dev, torch.float32)
+        n_atoms = np.diff(batch["ptr"].cpu().numpy())
+        cells64 = np.asarray(batch["cell64"], dtype=np.float64)
+        pos_all = torch.cat([pos, batch["pos_product"].to(dev, torch.float32)], dim=0).contiguous()
+        Z_all = torch.cat([batch["elems"], batch["elems"]]).to(dev, torch.int32).contiguous()
+        cell_all = torch.cat([batch["cell"], batch["cell"]], dim=0).to(dev, torch.float32).contiguous()
+        counts = np.concatenate([n_atoms, n_atoms])
+        node_ptr_host = np.zeros(len(counts) + 1, dtype=np.int32)
+        np.cumsum(counts, out=node_ptr_host[1:])
+        inv, img = cell_geometry(np.concatenate([cells64, cells64]), eng.cutoff)
+        node_ptr = torch.from_numpy(node_ptr_host).to(dev)
+        row_ptr, col, shift, node_struct = eng.radius_graph(pos_all, cell_all, torch.from_numpy(inv).to(dev),
+                                                            torch.from_numpy(img).to(dev), node_ptr)
+        qp = eng.q_params(q_params, self.head_spec)
+        p_drop = float(self.hyper.get("dropout_rate", 0.0)) if dropout_uniform is not None else 0.0
+        t0 = target0.to(dev, torch.float32).reshape(-1).contiguous()
+        t1 = None if target1 is None else target1.to(dev, torch.float32).reshape(-1).contiguous()
+        return eng.train_forward_backward(Z_all, pos_all, cell_all, node_ptr, node_struct, row_ptr, col, shift, G, qp,
+                                          state["params"], state["grads"], t0, t1, mode=mode, dropout_uniform=dropout_uniform,
+                                          dropout_p=p_drop, return_q=return_q)
+
+    def optimizer_step(self, state: dict, lr: float, max_norm: float) -> torch.Tensor:
+        """``clip_grad_norm_(parameters, max_norm); optimizer.step()`` (``trainer.py:93-96,173-176``) on ``state``."""
+        return self._engine_for(state["device"]).adam_step(state["params"], state["grads"], state, lr, max_norm, state["mask"])
+
+    def load_train_state(self, state: dict) -> None:
+        """Copy the flat parameters back into the module (``state_dict()`` / ``save`` / the next scoring call see them)."""
+        flat = state["params"].detach().cpu()
+        own = dict(self.named_parameters())
+        with torch.no_grad():
+            for name, off, n, trainable in self._engine_for(state["device"]).train_layout():
+                if trainable and name in own:
+                    own[name].copy_(flat[off:off + n].reshape(own[name].shape))
+
     def _pull_q_heads(self, eng: Engine) -> None:
         """Copy the updated Q_emb / Q_output tensors from the engine into this module's parameters (state_dict, save)."""
         sd = dict(self.named_parameters())

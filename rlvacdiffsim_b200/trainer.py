@@ -7,9 +7,11 @@ whose name contains ``reaction_model`` is frozen, only ``Q_emb`` / ``Q_output`` 
 ``dqn_update`` (``trainer.py:163-177``): forward, MSE against ``next_Q * gamma + reward``, backward, ``clip_grad_norm_``
 at 0.8 and the Adam step, in one kernel launch behind ``DQNv2.q_head_update`` (``csrc/train.cu``).
 
-NOT built: ``train_all=True`` (the reference configs' default) needs the backward of the PaiNN representation;
-``context_bandit_update`` (``trainer.py:55-100``) trains ``q0`` / ``q1``, which live entirely inside the frozen reaction
-model.  Both raise ``NotImplementedError`` instead of silently training something else.
+``train_all=True`` (the value in both reference configs, ``configs/train_dqn.toml:27``) and ``context_bandit_update``
+(``trainer.py:54-100``, fits ``q0`` / ``q1``) back-propagate through the whole PaiNN model: ``csrc/train_full.cu`` —
+training forward with saved activations, edge-message / mixing / head backward, the flat 614,447-float gradient bucket,
+``clip_grad_norm_`` + Adam on the device.  With ``torch.distributed`` initialised (rl-train on 2/4/8 GPUs)
+every rank runs its own minibatches and the bucket is averaged with ONE ``all_reduce`` per optimizer step.
 """
 from __future__ import annotations
 
@@ -120,6 +122,9 @@ class Trainer:
         self.lr = float(lr)
         self.q_params = q_params
         self._adam: Dict[tuple, dict] = {}          # Adam state of the DQN heads, per device (optim.Adam, trainer.py:43)
+        self._full: Dict[tuple, dict] = {}          # flat parameters / gradient bucket / Adam moments of the whole model
+        self.heads_only_kernel = True               # train_all=False: use the fused one-launch head update (csrc/train.cu)
+        self.allreduce_ms = 0.0                     # accumulated device time of the gradient all-reduce (bench.py --config 5)
         # trainer.py:123 calls policy_value_net.train(): the DQN heads' Dropout(p = hyper['dropout_rate'], 0.15 in the
         # bundled checkpoint) is ON during the update.  Same here by default (uniforms from the global numpy RNG — a
         # different stream from torch's Philox, so masks differ from a torch run draw by draw, not in distribution);
@@ -131,10 +136,80 @@ class Trainer:
             return self.dqn_update(memory_l, **kwargs)
         return self.context_bandit_update(memory_l, **kwargs)
 
-    def context_bandit_update(self, memory_l, episode_size, num_epoch, batch_size=8, device="cuda"):
-        raise NotImplementedError(
-            "context_bandit_update fits q0/q1 (rlsim/drl/trainer.py:55-100), i.e. the reaction model; its backward "
-            "(PaiNN representation + reaction heads) has no sm_100a kernels in this build")
+    # ---- whole-model updates (train_all = True, context bandit): csrc/train_full.cu
+    @staticmethod
+    def _device(device) -> torch.device:
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        if dev.type == "cuda" and dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        return dev
+
+    def _full_state(self, dev: torch.device) -> dict:
+        key = (dev.type, dev.index)
+        st = self._full.get(key)
+        if st is None:
+            st = self.policy_value_net.new_train_state(dev)
+            self._full[key] = st
+        else:      # the module may have been modified outside (load_state_dict): refresh the flat copy, keep the moments
+            st["params"].copy_(self.policy_value_net._engine_for(dev).flatten_state(self.policy_value_net.state_dict()))
+        return st
+
+    def _sync_gradients(self, state: dict) -> None:
+        """rl-train on several GPUs: average the flat gradient bucket over the ranks (2.46 MB, one NCCL all-reduce)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        dist.all_reduce(state["grads"], op=dist.ReduceOp.SUM)
+        state["grads"].mul_(1.0 / dist.get_world_size())
+        b.record()
+        self._ar_events = getattr(self, "_ar_events", []) + [(a, b)]
+
+    def _run_minibatches(self, q_dataloader, num_epoch, dev, mode, max_norm) -> float:
+        st = self._full_state(dev)
+        losses = AverageMeter()
+        pending = []
+        for _ in range(num_epoch):
+            for batch in q_dataloader:
+                batch = batch_to(batch, dev)
+                G = batch.num_graphs
+                u = torch.from_numpy(np.random.random_sample((G, 80)).astype(np.float32)).to(dev) if self.dropout else None
+                if mode == "dqn":
+                    res = self.policy_value_net.train_forward_backward(batch, self.q_params, st, batch["rl_q"].reshape(-1),
+                                                                       mode="dqn", dropout_uniform=u)
+                else:
+                    res = self.policy_value_net.train_forward_backward(batch, self.q_params, st, batch["q0"].reshape(-1),
+                                                                       batch["q1"].reshape(-1), mode="bandit", dropout_uniform=u)
+                self._sync_gradients(st)
+                self.policy_value_net.optimizer_step(st, self.lr, max_norm)
+                pending.append(res["loss"])
+        for l in pending:                                   # one host sync at the end instead of loss.item() per batch
+            losses.update(float(l.item()))
+        for a, b in getattr(self, "_ar_events", []):
+            self.allreduce_ms += a.elapsed_time(b)
+        self._ar_events = []
+        self.policy_value_net.load_train_state(st)
+        return losses.avg
+
+    def context_bandit_update(self, memory_l, episode_size, num_epoch, batch_size=8, device="cuda") -> float:
+        """``trainer.py:54-100``: fit (q0, q1) = (-barrier, freq) of the taken actions; clip at 1.0."""
+        dev = self._device(device)
+        self.policy_value_net.to(dev)
+        self.policy_value_net.train()
+        age_w = np.asarray([0.99 ** (len(memory_l) - i) for i in range(len(memory_l))])
+        episode_size = min(episode_size, len(memory_l))
+        picks = np.random.choice(range(len(memory_l)), size=episode_size, p=age_w / np.sum(age_w), replace=False)
+        graphs = []
+        for u in picks:
+            mem = memory_l[u]
+            for i, state in enumerate(mem.states):
+                for data in convert(state, [mem.act_space[i][mem.actions[i]]]):
+                    data.q1 = torch.tensor([float(mem.freq[i])], dtype=torch.float)
+                    data.q0 = torch.tensor([-1.0 * float(mem.barrier[i])], dtype=torch.float)
+                    graphs.append(data)
+        q_dataloader = DataLoader(ReactionDataset(graphs), batch_size=batch_size)
+        return self._run_minibatches(q_dataloader, num_epoch, dev, "bandit", 1.0)
 
     def get_max_Q(self, model, state, action_space, device="cuda") -> torch.Tensor:
         dataloader = DataLoader(ReactionDataset(convert(state, action_space)), batch_size=16, shuffle=False)
@@ -182,11 +257,6 @@ class Trainer:
         return [next_q[i] * gamma + rewards[i] for i in range(len(transitions))]
 
     def dqn_update(self, memory_l, gamma, episode_size, num_epoch, batch_size=8, device="cuda") -> float:
-        if self.train_all:
-            raise NotImplementedError(
-                "dqn_update with train_all=True back-propagates through the PaiNN representation (rlsim/drl/trainer.py:"
-                "163-177), which has no sm_100a kernels in this build; construct Trainer(..., train_all=False) to train "
-                "the DQN heads on the device")
         self._sync_target(device)
         transitions = self._sample_transitions(memory_l, episode_size)
         targets = self._td_targets(transitions, gamma, device)
@@ -196,10 +266,11 @@ class Trainer:
                 data.rl_q = y
                 graphs.append(data)
         q_dataloader = DataLoader(ReactionDataset(graphs), batch_size=batch_size, shuffle=False)
+        dev = self._device(device)
+        if self.train_all or not self.heads_only_kernel:
+            return self._run_minibatches(q_dataloader, num_epoch, dev, "dqn", 0.8)
+        # train_all = False: only Q_emb / Q_output learn -> the frozen forward + the one-launch head update (csrc/train.cu)
         losses = AverageMeter()
-        dev = torch.device(device) if not isinstance(device, torch.device) else device
-        if dev.type == "cuda" and dev.index is None:
-            dev = torch.device("cuda", torch.cuda.current_device())
         key = (dev.type, dev.index)
         for _ in range(num_epoch):
             for batch in q_dataloader:

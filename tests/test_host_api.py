@@ -199,7 +199,7 @@ def test_trajectory_writer_matches_per_step_appends(tmp_path):
 
 def test_trainer_surface_and_memory_roundtrip(tmp_path, checkpoint_path):
     """rlsim/drl/trainer.py / rlsim/memory.py mirror: constructor semantics (train_all freezes reaction_model), the JSON
-    layout of Memory.save / load, and loud failures for the forms that are not built."""
+    layout of Memory.save / load, and a loud failure without a GPU."""
     from rlvacdiffsim_b200.structures import apply_action
     from rlvacdiffsim_b200.trainer import Memory, Trainer
     model = rb.registry.get_model_class("dqn_v2").load(checkpoint_path)
@@ -218,7 +218,23 @@ def test_trainer_surface_and_memory_roundtrip(tmp_path, checkpoint_path):
     back.load(str(tmp_path / "traj0.json"))
     assert back.actions == [1] and back.rewards == mem.rewards and len(back.act_space[0]) == len(space)
     np.testing.assert_array_equal(back.states[0].get_positions(), s.get_positions())
-    with pytest.raises(NotImplementedError):
-        Trainer(model, {"dqn": True}, train_all=True).dqn_update([mem], gamma=0.8, episode_size=1, num_epoch=1)
-    with pytest.raises(NotImplementedError):
-        tr.context_bandit_update([mem], episode_size=1, num_epoch=1)
+    with pytest.raises(RuntimeError):                  # no CUDA device here: the whole-model update fails loudly, no CPU path
+        Trainer(model, {"alpha": 0.0, "beta": 1.0, "dqn": True}, train_all=True).dqn_update([mem, mem], gamma=0.8, episode_size=1,
+                                                                                      num_epoch=1, device="cuda")
+
+
+def test_train_layout_is_the_checkpoint_order(checkpoint_path):
+    """rlvd_train_layout (no GPU needed): the flat parameter vector is every floating-point tensor of the checkpoint in
+    state_dict order, 614,447 floats, buffers marked non-trainable."""
+    import torch
+    from rlvacdiffsim_b200.engine import Engine
+    ck = torch.load(checkpoint_path, weights_only=True, map_location="cpu")["state_dict"]
+    want = [(k, v.numel()) for k, v in ck.items() if v.is_floating_point()]
+    tab = Engine.train_layout()
+    assert [(n, c) for n, _, c, _ in tab] == want
+    off = 0
+    for name, o, c, tr in tab:
+        assert o == off
+        off += c
+        assert tr == (not name.endswith(("cutoff_fn.cutoff", "radial_basis.freqs")))
+    assert off == 614447
