@@ -514,22 +514,33 @@ __global__ void feat_unpool_kernel(int Mr, const int* __restrict__ node_struct, 
 __global__ void __launch_bounds__(256) energy_bwd_kernel(int M, int Mr, int G, const int* __restrict__ Z, const int* __restrict__ lookup,
                                                          const int* __restrict__ node_struct, const float* __restrict__ sc,
                                                          const float* __restrict__ e_raw, const float* __restrict__ gde,
-                                                         float* __restrict__ g_eraw, float* __restrict__ gsc, float* __restrict__ gsh) {
+                                                         float* __restrict__ g_eraw, float* __restrict__ gsc, float* __restrict__ gsh,
+                                                         float* __restrict__ gb3) {
     __shared__ float red[256][6];
+    __shared__ float bred[256];
     float loc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int i = threadIdx.x; i < M; i += 256) {
-        int z = Z[i];
+    float bsum = 0.f;
+    (void)M;
+    // reactant node r and product node Mr + r are the same atom: d delta_e / d e is -1 / +1, so the pair's shift gradients
+    // cancel exactly and its scale gradient is gde * (e_raw_P - e_raw_R)
+    for (int r = threadIdx.x; r < Mr; r += 256) {
+        int z = Z[r];
         z = z < 0 ? 0 : (z > 99 ? 99 : z);
         const int s = lookup[z];
-        const int st = node_struct[i];
-        const float ge = i < Mr ? -gde[st] : gde[st - G];
-        g_eraw[i] = ge * sc[s];
+        const float ge = gde[node_struct[r]];
+        (void)G;
+        g_eraw[r] = -ge * sc[s];
+        g_eraw[Mr + r] = ge * sc[s];
+        const float dsc = ge * (e_raw[Mr + r] - e_raw[r]);
+        const float dsh = ge - ge, db = g_eraw[Mr + r] + g_eraw[r];   // exactly zero for finite ge; NaN / inf propagate
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-            loc[t] += (t == s) ? ge * e_raw[i] : 0.f;
-            loc[3 + t] += (t == s) ? ge : 0.f;
+            loc[t] += (t == s) ? dsc : 0.f;
+            loc[3 + t] += (t == s) ? dsh : 0.f;
         }
+        bsum += db;
     }
+    bred[threadIdx.x] = bsum;
 #pragma unroll
     for (int t = 0; t < 6; ++t) red[threadIdx.x][t] = loc[t];
     __syncthreads();
@@ -537,6 +548,11 @@ __global__ void __launch_bounds__(256) energy_bwd_kernel(int M, int Mr, int G, c
         float v = 0.f;
         for (int k = 0; k < 256; ++k) v += red[k][threadIdx.x];
         if (threadIdx.x < 3) gsc[threadIdx.x] = v; else gsh[threadIdx.x - 3] = v;
+    }
+    if (threadIdx.x == 6) {                       // energy_output's last bias: sum of g_eraw over the (R, P) pairs
+        float v = 0.f;
+        for (int k = 0; k < 256; ++k) v += bred[k];
+        *gb3 = v;
     }
 }
 // gq[Mr + r] += gd[r];  gq[r] -= gd[r]
@@ -956,9 +972,9 @@ int train_forward_backward(rlvd_engine* e, cudaStream_t s, int n_struct, int M, 
     ++c.launches;
     // ================= backward: heads, node level =================
     // energy_output
-    energy_bwd_kernel<<<1, 256, 0, s>>>(M, Mr, G, Z, e->w.elem_lookup, node_struct, P + P_SC, e_raw, gde, g_eraw, Gr + P_SC, Gr + P_SH);
+    energy_bwd_kernel<<<1, 256, 0, s>>>(M, Mr, G, Z, e->w.elem_lookup, node_struct, P + P_SC, e_raw, gde, g_eraw, Gr + P_SC, Gr + P_SH,
+                                        Gr + P_EN + EN_B3);
     wgrad(c, M, 1, 64, g_eraw, 1, en_h, 64, Gr + P_EN + EN_W3, 64, part);
-    colsum(c, M, 1, g_eraw, 1, Gr + P_EN + EN_B3);
     gemm(c, false, false, M, 64, 1, g_eraw, 1, PEN + EN_W3, 64, g_enh, 64, nullptr, false);
     act_bwd_kernel<<<nblk((int64_t)M * 64), 256, 0, s>>>((int64_t)M * 64, en_pre, g_enh, act_p);
     wgrad(c, M, 64, F, g_enh, 64, qf, F, Gr + P_EN + EN_W0, F, part);
