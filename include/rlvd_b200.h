@@ -135,6 +135,34 @@ int  rlvd_select_apply(rlvd_engine* e, void* stream, int32_t n_rep, const int32_
                        int32_t max_actions, int32_t apply, double* d_pos, int32_t* d_chosen, int32_t* d_argmax, float* d_probs,
                        float* d_gamma);
 
+/* The same with a counter-based generator instead of caller uniforms: replica r of this call draws
+ * u = Philox4x32-10(key = seed, counter = (replica0 + r, step)) — a 10k-step trajectory needs no host RNG traffic and
+ * replays exactly whatever the sharding.  rlvd_select_apply with np.random's uniforms stays the reference-compatible mode. */
+int  rlvd_select_apply_philox(rlvd_engine* e, void* stream, int32_t n_rep, const int32_t* d_rep_ptr, const int32_t* d_first,
+                              const float* d_rl_q, const float* d_temperature, uint64_t seed, uint64_t step, uint32_t replica0,
+                              const double* d_actions, int32_t max_actions, int32_t apply, double* d_pos, int32_t* d_chosen,
+                              int32_t* d_argmax, float* d_probs, float* d_gamma);
+/* rlvd_action_space for ANY periodic cell (the reference's demo/poscars/POSCAR_0 is rhombohedral): minimum image over the
+ * 27 neighbouring images like ase.geometry.find_mic.  The perfect-lattice sites depend only on the cell: d_sites[d_site_ptr[g]
+ * .. d_site_ptr[g+1]) (fp64 [n,3], reference site order) and d_inv_cell[g] (fp64 inverse) are computed once by the caller.
+ * Status codes as rlvd_action_space (1: no sites / more than 8192). */
+int  rlvd_action_space_general(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const double* d_pos,
+                               const double* d_cell, const double* d_inv_cell, const int32_t* d_site_ptr, const double* d_sites,
+                               double lattice_parameter, int32_t max_vacancies, int32_t max_actions, int32_t* d_count,
+                               double* d_actions, int32_t* d_status);
+/* rlvd_expand_candidates for general cells: d_inv_in[n_rep,3,3] (fp32 image of the fp64 inverse) and d_img_in[n_rep,3]
+ * (periodic image ranges) of the replicas are copied to their candidates' structures; NULL = orthorhombic, heights >= 2 rc. */
+int  rlvd_expand_candidates_ex(rlvd_engine* e, void* stream, int32_t n_rep, int32_t n_cand, int32_t n_atoms_per,
+                               const int32_t* d_rep_ptr, const int32_t* d_first, const int32_t* d_Z, const double* d_pos,
+                               const double* d_cell, const double* d_actions, int32_t max_actions, const float* d_inv_in,
+                               const int32_t* d_img_in, int32_t* d_node_ptr, int32_t* d_Z_out, float* d_pos_out, float* d_cell_out,
+                               float* d_inv_out, int32_t* d_img_out, int32_t* d_react_struct, int32_t* d_prod_struct, int32_t* d_owner);
+/* One fixed-width fp32 record per replica for the per-step gather of SURVEY.md §8e (rank-0 logger / trajectory writer):
+ * d_records[n_rep, 4 + max_actions] = {replica id (replica_id0 + r * stride), n_actions, chosen, E_R, Q[...] NaN-padded}. */
+int  rlvd_pack_step_records(rlvd_engine* e, void* stream, int32_t n_rep, const int32_t* d_first, const float* d_rl_q,
+                            const int32_t* d_chosen, const float* d_E_R, int32_t replica_id0, int32_t replica_id_stride,
+                            int32_t max_actions, float* d_records);
+
 /* ---- replay-minibatch update of the DQN heads (rlsim/drl/trainer.py:163-177 with train_all = False, trainer.py:36-39) ---
  * rlvd_reaction_readout_ex = rlvd_reaction_readout that also writes d_head_in[n_react, 36]: what the trainable heads see
  * per reaction graph (33 Q_emb inputs, the 2 extra Q_output inputs, the alpha/beta part of rl_q).  Needs q_params.dqn. */
@@ -251,7 +279,9 @@ int  rlvd_set_option(rlvd_engine* e, const char* name, int32_t value);
 /* Device status word since the last call (synchronises `stream`, then clears it).  bit 0: an operand of a tensor-core GEMM
  * left the range of the fp16 hi/lo split (|x| >= 65504, inf or NaN) — the results of that call are not valid; set option
  * "tensor_cores" to 0 and repeat it (rlvd_score_reactions_host and the Python wrappers do this by themselves).  Physical
- * structures stay orders of magnitude below the limit; unphysically dense ones make the network diverge in any precision. */
+ * structures stay orders of magnitude below the limit; unphysically dense ones make the network diverge in any precision.
+ * bit 1: the edge-tile pool of the stream kernel overflowed its capacity bound — results invalid (an internal sizing error;
+ * rlvd_score_reactions_host returns non-zero, the Python wrappers raise). */
 int  rlvd_check_status(rlvd_engine* e, void* stream, int32_t* flags);
 
 /* ---- introspection ------------------------------------------------------------------------------ */

@@ -53,6 +53,12 @@ SYMBOLS = {
     "rlvd_expand_candidates": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32,
                                          _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rlvd_select_apply": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+    "rlvd_select_apply_philox": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint32, _P, C.c_int32,
+                                           C.c_int32, _P, _P, _P, _P, _P]),
+    "rlvd_action_space_general": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_double, C.c_int32, C.c_int32, _P, _P, _P]),
+    "rlvd_expand_candidates_ex": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P,
+                                            _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rlvd_pack_step_records": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "rlvd_sro_counts": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, _P]),
     "rlvd_reaction_readout_ex": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.POINTER(QParams), _P, _P, _P, _P, _P, _P, _P, _P]),
     "rlvd_q_head_train_step": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float,

@@ -135,8 +135,9 @@ def get_action_space_legacy(config, lattice_parameter: float = 3.528) -> List[Li
 def get_action_space_device(engine, replicas, lattice_parameter: float = 3.615, max_vacancies: int = 1) -> List[List[List[float]]]:
     """:func:`get_action_space` for many replicas in ONE device launch (``rlvd_action_space``).
 
-    Same rows in the same order as the host enumerator for orthorhombic cells; replicas whose cell the kernel does
-    not take (status 1) fall through to the host enumerator, and the reference's vacancy-count assert
+    Same rows in the same order as the host enumerator; orthorhombic cells take ``rlvd_action_space``, every other cell
+    ``rlvd_action_space_general`` (only a cell with more than 8192 lattice sites falls through to the host enumerator),
+    and the reference's vacancy-count assert
     (``action.py:35``) is raised for status 2.  ``engine`` is an :class:`rlvacdiffsim_b200.engine.Engine`."""
     import torch
 
@@ -151,6 +152,24 @@ def get_action_space_device(engine, replicas, lattice_parameter: float = 3.615, 
                                            torch.from_numpy(node_ptr).to(dev), lattice_parameter, max_vacancies,
                                            max_actions=12 * max_vacancies)
     cnt, act, status = cnt.cpu().numpy(), act.cpu().numpy(), status.cpu().numpy()
+    general = [g for g in range(len(atoms_l)) if status[g] == 1]
+    if general:
+        # non-orthorhombic cells (e.g. the reference's rhombohedral demo POSCAR): the general minimum-image kernel with the
+        # cells' perfect-lattice sites computed once on the host
+        site_list = [lattice_sites_for_cell(cells[g], lattice_parameter) for g in general]
+        sp = np.zeros(len(general) + 1, dtype=np.int32)
+        np.cumsum([len(x) for x in site_list], out=sp[1:])
+        np2 = np.zeros(len(general) + 1, dtype=np.int32)
+        np.cumsum([counts[g] for g in general], out=np2[1:])
+        pos_g = np.concatenate([pos[node_ptr[g]:node_ptr[g + 1]] for g in general])
+        c2, a2, s2 = engine.action_space_general(
+            torch.from_numpy(pos_g).to(dev), torch.from_numpy(cells[general]).to(dev),
+            torch.from_numpy(np.linalg.inv(cells[general])).to(dev), torch.from_numpy(np2).to(dev), torch.from_numpy(sp).to(dev),
+            torch.from_numpy(np.concatenate(site_list) if site_list else np.zeros((0, 3))).to(dev), lattice_parameter, max_vacancies,
+            max_actions=12 * max_vacancies)
+        c2, a2, s2 = c2.cpu().numpy(), a2.cpu().numpy(), s2.cpu().numpy()
+        for k, g in enumerate(general):
+            cnt[g], act[g], status[g] = c2[k], a2[k], s2[k]
     out: List[List[List[float]]] = []
     for g, atoms in enumerate(atoms_l):
         if status[g] == 1:

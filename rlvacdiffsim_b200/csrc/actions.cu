@@ -140,7 +140,142 @@ __global__ void __launch_bounds__(AT) action_space_kernel(int n_struct, const in
     }
 }
 
+
+// ---- general (non-orthorhombic) cells: the demo POSCAR_0 of the reference is rhombohedral -----------------------------
+// Same steps as above with the host mirror's general minimum image (rlvacdiffsim_b200/actions.py `mic_vectors`, which
+// restates ase.geometry.find_mic's result): fractional rounding, then the 27 images around it, a candidate replacing the
+// incumbent only if it is shorter by more than 1e-12.  The perfect-lattice sites of a cell are a property of the CELL, not
+// of the state: the caller computes them once on the host (`lattice_sites_for_cell`: conventional FCC sites clipped to the
+// cell, reference order) and passes them in.  The final displacement is the reference's formula (action.py:53-57:
+// frac = solve(cell.T, diff); frac -= round(frac); cell.T @ frac) evaluated with the fp64 inverse cell.
+__device__ __forceinline__ double mic_general(const double* C, const double* Ci, double dx, double dy, double dz) {
+    double f0 = dx * Ci[0] + dy * Ci[3] + dz * Ci[6], f1 = dx * Ci[1] + dy * Ci[4] + dz * Ci[7], f2 = dx * Ci[2] + dy * Ci[5] + dz * Ci[8];
+    f0 -= rint(f0); f1 -= rint(f1); f2 -= rint(f2);
+    const double bx = f0 * C[0] + f1 * C[3] + f2 * C[6], by = f0 * C[1] + f1 * C[4] + f2 * C[7], bz = f0 * C[2] + f1 * C[5] + f2 * C[8];
+    double best = bx * bx + by * by + bz * bz;
+    for (int s0 = -1; s0 <= 1; ++s0)
+        for (int s1 = -1; s1 <= 1; ++s1)
+            for (int s2 = -1; s2 <= 1; ++s2) {
+                if ((s0 | s1 | s2) == 0) continue;
+                const double cx = bx + s0 * C[0] + s1 * C[3] + s2 * C[6], cy = by + s0 * C[1] + s1 * C[4] + s2 * C[7],
+                             cz = bz + s0 * C[2] + s1 * C[5] + s2 * C[8];
+                const double n2 = cx * cx + cy * cy + cz * cz;
+                if (n2 < best - 1e-12) best = n2;
+            }
+    return sqrt(best);
+}
+
+__global__ void __launch_bounds__(AT) action_space_general_kernel(int n_struct, const int* __restrict__ node_ptr, const double* __restrict__ pos,
+                                                                  const double* __restrict__ cell, const double* __restrict__ inv_cell,
+                                                                  const int* __restrict__ site_ptr, const double* __restrict__ sites,
+                                                                  double a, int max_vac, int max_actions, int* __restrict__ count,
+                                                                  double* __restrict__ actions, int* __restrict__ status) {
+    __shared__ int site_atom[MAX_SITES];
+    __shared__ int vac[64];
+    __shared__ int n_vac_s, n_act_s;
+    __shared__ int part[AT + 1];
+    __shared__ double Cs[9], Cis[9];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    if (g >= n_struct) return;
+    const int n0 = node_ptr[g], n = node_ptr[g + 1] - n0;
+    const int s0 = site_ptr[g], ns = site_ptr[g + 1] - s0;
+    if (tid < 9) { Cs[tid] = cell[9 * (int64_t)g + tid]; Cis[tid] = inv_cell[9 * (int64_t)g + tid]; }
+    if (tid == 0) { count[g] = 0; n_vac_s = 0; n_act_s = 0; }
+    if (ns <= 0 || ns > MAX_SITES) {
+        if (tid == 0) status[g] = 1;
+        return;
+    }
+    for (int s = tid; s < ns; s += AT) site_atom[s] = -1;
+    __syncthreads();
+    const double* S = sites + 3 * (int64_t)s0;
+    for (int i = tid; i < n; i += AT) {
+        const double px = pos[3 * (int64_t)(n0 + i)], py = pos[3 * (int64_t)(n0 + i) + 1], pz = pos[3 * (int64_t)(n0 + i) + 2];
+        double best = 1e300;
+        int bs = 0;
+        for (int s = 0; s < ns; ++s) {
+            const double d = mic_general(Cs, Cis, S[3 * s] - px, S[3 * s + 1] - py, S[3 * s + 2] - pz);
+            if (d < best) { best = d; bs = s; }
+        }
+        atomicMax(&site_atom[bs], i);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nv = 0;
+        for (int s = 0; s < ns; ++s)
+            if (site_atom[s] < 0) {
+                if (nv < 64) vac[nv] = s;
+                ++nv;
+            }
+        n_vac_s = nv;
+    }
+    __syncthreads();
+    const int nv = n_vac_s;
+    if (nv < 1 || nv > max_vac || nv > 64) {
+        if (tid == 0) status[g] = 2;
+        return;
+    }
+    const double nn_hi = __dmul_rn(__ddiv_rn(a, sqrt(2.0)), 1.1);
+    const int chunk = (ns + AT - 1) / AT;
+    for (int v = 0; v < nv; ++v) {
+        const double vx = S[3 * vac[v]], vy = S[3 * vac[v] + 1], vz = S[3 * vac[v] + 2];
+        const int s_lo = tid * chunk, s_hi = min(ns, s_lo + chunk);
+        int mine = 0;
+        for (int s = s_lo; s < s_hi; ++s) {
+            const double d = mic_general(Cs, Cis, S[3 * s] - vx, S[3 * s + 1] - vy, S[3 * s + 2] - vz);
+            if (d > 0.1 && d < nn_hi && site_atom[s] >= 0) ++mine;
+        }
+        part[tid] = mine;
+        __syncthreads();
+        if (tid == 0) {
+            int run = n_act_s;
+            for (int t = 0; t < AT; ++t) { const int c = part[t]; part[t] = run; run += c; }
+            part[AT] = run;
+        }
+        __syncthreads();
+        int w = part[tid];
+        for (int s = s_lo; s < s_hi; ++s) {
+            const double d = mic_general(Cs, Cis, S[3 * s] - vx, S[3 * s + 1] - vy, S[3 * s + 2] - vz);
+            if (d > 0.1 && d < nn_hi && site_atom[s] >= 0) {
+                const int at = site_atom[s];
+                if (w < max_actions) {
+                    double* o = actions + ((int64_t)g * max_actions + w) * 4;
+                    const double dx = vx - pos[3 * (int64_t)(n0 + at)], dy = vy - pos[3 * (int64_t)(n0 + at) + 1],
+                                 dz = vz - pos[3 * (int64_t)(n0 + at) + 2];
+                    double f0 = dx * Cis[0] + dy * Cis[3] + dz * Cis[6], f1 = dx * Cis[1] + dy * Cis[4] + dz * Cis[7],
+                           f2 = dx * Cis[2] + dy * Cis[5] + dz * Cis[8];
+                    f0 -= rint(f0); f1 -= rint(f1); f2 -= rint(f2);
+                    o[0] = (double)at;
+                    o[1] = f0 * Cs[0] + f1 * Cs[3] + f2 * Cs[6];
+                    o[2] = f0 * Cs[1] + f1 * Cs[4] + f2 * Cs[7];
+                    o[3] = f0 * Cs[2] + f1 * Cs[5] + f2 * Cs[8];
+                }
+                ++w;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) n_act_s = part[AT];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        count[g] = min(n_act_s, max_actions);
+        status[g] = n_act_s > max_actions ? 3 : 0;
+    }
+}
+
 }  // namespace
+
+int launch_action_space_general(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const double* pos, const double* cell,
+                                const double* inv_cell, const int* site_ptr, const double* sites, double a, int max_vac, int max_actions,
+                                int* count, double* actions, int* status) {
+    if (n_struct <= 0) return 0;
+    RLVD_CHECK(a > 0.0 && max_vac >= 1 && max_actions >= 1, "rlvd_action_space_general: bad lattice parameter / limits");
+    Span sp(e, s, FAM_NEIGHBOR);
+    action_space_general_kernel<<<n_struct, AT, 0, s>>>(n_struct, node_ptr, pos, cell, inv_cell, site_ptr, sites, a, max_vac, max_actions,
+                                                       count, actions, status);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int launch_action_space(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const double* pos, const double* cell,
                         double a, int max_vac, int max_actions, int* count, double* actions, int* status) {
@@ -208,7 +343,9 @@ __global__ void __launch_bounds__(128) expand_candidates_kernel(int n_rep, const
                                                                 int max_actions, int n_atoms_per /* uniform replica size */,
                                                                 int* __restrict__ node_ptr, int* __restrict__ Zo, float* __restrict__ poso,
                                                                 float* __restrict__ cello, float* __restrict__ invo, int* __restrict__ imgo,
-                                                                int* __restrict__ rs, int* __restrict__ ps, int* __restrict__ owner) {
+                                                                int* __restrict__ rs, int* __restrict__ ps, int* __restrict__ owner,
+                                                                const float* __restrict__ inv_in /* [R,3,3] or null */,
+                                                                const int* __restrict__ img_in /* [R,3] or null */) {
     const int g = blockIdx.x, side = blockIdx.y, tid = threadIdx.x;
     // replica of graph g: binary search in first[]
     int lo = 0, hi = n_rep;
@@ -234,9 +371,10 @@ __global__ void __launch_bounds__(128) expand_candidates_kernel(int n_rep, const
         const double cv = cell[9 * (int64_t)r + tid];
         cello[9 * (int64_t)st + tid] = (float)cv;
         const int row = tid / 3, colm = tid % 3;
-        invo[9 * (int64_t)st + tid] = row == colm ? (float)(1.0 / cv) : 0.f;     // orthorhombic cells only (rlvd_action_space status 0)
+        // orthorhombic cells: 1 / L on the diagonal; general cells: the caller's fp32 image of the fp64 inverse
+        invo[9 * (int64_t)st + tid] = inv_in != nullptr ? inv_in[9 * (int64_t)r + tid] : (row == colm ? (float)(1.0 / cv) : 0.f);
     }
-    if (tid < 3) imgo[3 * (int64_t)st + tid] = 0;                                  // cell heights >= 2 * cutoff are the caller's contract
+    if (tid < 3) imgo[3 * (int64_t)st + tid] = img_in != nullptr ? img_in[3 * (int64_t)r + tid] : 0;   // 0: heights >= 2 * cutoff
     if (tid == 0) {
         node_ptr[st] = (int)o0;
         if (side == 0) { rs[g] = st; owner[g] = r; } else ps[g] = st;
@@ -248,9 +386,28 @@ __global__ void __launch_bounds__(128) expand_candidates_kernel(int n_rep, const
 // np.random.choice semantics for the draw (cdf = cumsum(p) in fp64, cdf /= cdf[-1], first index with cdf > u), then
 // pos[atom] += disp in fp64.  u[r] comes from the caller (np.random.random_sample() for bit-compatible replays, or any
 // counter-based generator).
+// Counter-based draws: Philox4x32-10 (Salmon et al., SC'11) keyed by the caller's 64-bit seed, counter =
+// (replica, step): every (replica, step) pair has its own uniform whatever the launch order, so a trajectory needs no host
+// RNG traffic and replays exactly.  u = (x0 * 2^32 + x1) >> 11 scaled to [0, 1) — 53 random bits like numpy's double draw.
+__device__ __forceinline__ double philox_uniform(unsigned long long seed, unsigned int replica, unsigned long long step) {
+    unsigned int c0 = replica, c1 = (unsigned int)step, c2 = (unsigned int)(step >> 32), c3 = 0u;
+    unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned int n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const unsigned long long bits = (((unsigned long long)c0 << 32) | (unsigned long long)c1) >> 11;
+    return (double)bits * (1.0 / 9007199254740992.0);
+}
+
 __global__ void __launch_bounds__(128) select_apply_kernel(int n_rep, const int* __restrict__ rep_ptr, const int* __restrict__ first,
                                                            const float* __restrict__ rl_q, const float* __restrict__ temperature,
-                                                           const double* __restrict__ u, const double* __restrict__ actions,
+                                                           const double* __restrict__ u, unsigned long long seed, unsigned long long step,
+                                                           unsigned int replica0, const double* __restrict__ actions,
                                                            int max_actions, int apply, double* __restrict__ pos,
                                                            int* __restrict__ chosen, int* __restrict__ argmax_out, float* __restrict__ probs,
                                                            float* __restrict__ gamma) {
@@ -278,11 +435,12 @@ __global__ void __launch_bounds__(128) select_apply_kernel(int n_rep, const int*
         if (probs != nullptr) probs[(int64_t)r * max_actions + c] = p;
         tot += (double)p;
     }
+    const double ur = u != nullptr ? u[r] : philox_uniform(seed, replica0 + (unsigned int)r, step);
     double run = 0.0;
     int pick = nc - 1;
     for (int c = 0; c < nc; ++c) {
         run += (double)(expf(rl_q[g0 + c] / kT - m) / s);
-        if (run / tot > u[r]) { pick = c; break; }
+        if (run / tot > ur) { pick = c; break; }
     }
     chosen[r] = pick;
     argmax_out[r] = am;
@@ -297,6 +455,34 @@ __global__ void __launch_bounds__(128) select_apply_kernel(int n_rep, const int*
 
 }  // namespace
 
+// The per-step record of a replica for the rank-0 logger / trajectory writer: one fixed-width fp32 row
+// [replica id, n_actions, chosen, E_R, Q[max_actions] (NaN-padded)], packed on the device so that the only exchange of a
+// multi-GPU step is ONE all_gather of these rows.
+__global__ void pack_records_kernel(int n_rep, const int* __restrict__ first, const float* __restrict__ rl_q, const int* __restrict__ chosen,
+                                    const float* __restrict__ E_R, int id0, int id_stride, int max_actions, float* __restrict__ rec) {
+    const int r = blockIdx.x, t = threadIdx.x, W = 4 + max_actions;
+    if (r >= n_rep) return;
+    const int g0 = first[r], nc = first[r + 1] - g0;
+    float* row = rec + (int64_t)r * W;
+    if (t == 0) {
+        row[0] = (float)(id0 + r * id_stride);
+        row[1] = (float)nc;
+        row[2] = chosen != nullptr ? (float)chosen[r] : -1.f;
+        row[3] = E_R != nullptr && nc > 0 ? E_R[g0] : nanf("");
+    }
+    for (int c = t; c < max_actions; c += blockDim.x) row[4 + c] = c < nc ? rl_q[g0 + c] : nanf("");
+}
+
+int launch_pack_records(rlvd_engine* e, cudaStream_t s, int n_rep, const int* first, const float* rl_q, const int* chosen, const float* E_R,
+                        int id0, int id_stride, int max_actions, float* rec) {
+    if (n_rep <= 0) return 0;
+    Span sp(e, s, FAM_READOUT);
+    pack_records_kernel<<<n_rep, 32, 0, s>>>(n_rep, first, rl_q, chosen, E_R, id0, id_stride, max_actions, rec);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_candidate_offsets(rlvd_engine* e, cudaStream_t s, int n_rep, const int* count, int* first, int* total) {
     Span sp(e, s, FAM_NEIGHBOR);
     candidate_offsets_kernel<<<1, 1024, 0, s>>>(n_rep, count, first, total);
@@ -307,22 +493,24 @@ int launch_candidate_offsets(rlvd_engine* e, cudaStream_t s, int n_rep, const in
 
 int launch_expand_candidates(rlvd_engine* e, cudaStream_t s, int n_rep, int n_cand, const int* rep_ptr, const int* first, const int* Z,
                              const double* pos, const double* cell, const double* actions, int max_actions, int n_atoms_per,
-                             int* node_ptr, int* Zo, float* poso, float* cello, float* invo, int* imgo, int* rs, int* ps, int* owner) {
+                             int* node_ptr, int* Zo, float* poso, float* cello, float* invo, int* imgo, int* rs, int* ps, int* owner,
+                             const float* inv_in, const int* img_in) {
     if (n_cand <= 0) return 0;
     Span sp(e, s, FAM_NEIGHBOR);
     expand_candidates_kernel<<<dim3(n_cand, 2), 128, 0, s>>>(n_rep, rep_ptr, first, Z, pos, cell, actions, max_actions, n_atoms_per,
-                                                            node_ptr, Zo, poso, cello, invo, imgo, rs, ps, owner);
+                                                            node_ptr, Zo, poso, cello, invo, imgo, rs, ps, owner, inv_in, img_in);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_select_apply(rlvd_engine* e, cudaStream_t s, int n_rep, const int* rep_ptr, const int* first, const float* rl_q,
-                        const float* temperature, const double* u, const double* actions, int max_actions, int apply, double* pos,
+                        const float* temperature, const double* u, unsigned long long seed, unsigned long long step, unsigned int replica0,
+                        const double* actions, int max_actions, int apply, double* pos,
                         int* chosen, int* argmax_out, float* probs, float* gamma) {
     if (n_rep <= 0) return 0;
     Span sp(e, s, FAM_READOUT);
-    select_apply_kernel<<<(n_rep + 127) / 128, 128, 0, s>>>(n_rep, rep_ptr, first, rl_q, temperature, u, actions, max_actions, apply,
+    select_apply_kernel<<<(n_rep + 127) / 128, 128, 0, s>>>(n_rep, rep_ptr, first, rl_q, temperature, u, seed, step, replica0, actions, max_actions, apply,
                                                            pos, chosen, argmax_out, probs, gamma);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());

@@ -251,9 +251,16 @@ int launch_action_space(rlvd_engine* e, cudaStream_t s, int n_struct, const int*
 int launch_candidate_offsets(rlvd_engine* e, cudaStream_t s, int n_rep, const int* count, int* first, int* total);
 int launch_expand_candidates(rlvd_engine* e, cudaStream_t s, int n_rep, int n_cand, const int* rep_ptr, const int* first, const int* Z,
                              const double* pos, const double* cell, const double* actions, int max_actions, int n_atoms_per,
-                             int* node_ptr, int* Zo, float* poso, float* cello, float* invo, int* imgo, int* rs, int* ps, int* owner);
+                             int* node_ptr, int* Zo, float* poso, float* cello, float* invo, int* imgo, int* rs, int* ps, int* owner,
+                             const float* inv_in = nullptr, const int* img_in = nullptr);
+int launch_action_space_general(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const double* pos, const double* cell,
+                                const double* inv_cell, const int* site_ptr, const double* sites, double a, int max_vac, int max_actions,
+                                int* count, double* actions, int* status);
+int launch_pack_records(rlvd_engine* e, cudaStream_t s, int n_rep, const int* first, const float* rl_q, const int* chosen, const float* E_R,
+                        int id0, int id_stride, int max_actions, float* rec);
 int launch_select_apply(rlvd_engine* e, cudaStream_t s, int n_rep, const int* rep_ptr, const int* first, const float* rl_q,
-                        const float* temperature, const double* u, const double* actions, int max_actions, int apply, double* pos,
+                        const float* temperature, const double* u, unsigned long long seed, unsigned long long step, unsigned int replica0,
+                        const double* actions, int max_actions, int apply, double* pos,
                         int* chosen, int* argmax_out, float* probs, float* gamma);
 
 int launch_sro_counts(rlvd_engine* e, cudaStream_t s, int n_struct, const int* node_ptr, const double* pos, const double* cell,

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
                                                         const float* __restrict__ feps, float cutoff,
                                                         int* __restrict__ tile_counter, int tile_capacity,
                                                         uint8_t* __restrict__ tiles, int4* __restrict__ pipe_info,
-                                                        int* __restrict__ err_flag, const int* __restrict__ Z,
+                                                        int* __restrict__ err_flag, int* __restrict__ status_word, const int* __restrict__ Z,
                                                         const int* __restrict__ z2s, float* __restrict__ l0A, int mode,
                                                         int n_splits) {
     // mode 0: allocate tiles and fill them (one CTA per structure).  Small batches run mode 1 (allocation only) and then
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
         }
         int base = atomicAdd(tile_counter, total);
         bool ok = base + total <= tile_capacity;
-        if (!ok) atomicExch(err_flag, 1);
+        if (!ok) { atomicExch(err_flag, 1); atomicOr(status_word, 2); }    // engine status bit 1: results of this call are invalid
         for (int p = 0; p < NPIPE; ++p) {
             tbeg[p] = base;
             pipe_info[g * NPIPE + p] = make_int4(base, ok ? tl[p] : 0, bnd[p], bnd[p + 1]);
@@ -987,7 +987,7 @@ int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_
     for (int mode = n_splits > 1 ? 1 : 0; mode <= (n_splits > 1 ? 2 : 0); ++mode)
         edge_pack_kernel<<<dim3(n_struct, mode == 2 ? n_splits : 1), 256, 0, s>>>(
             n_struct, node_ptr, row_ptr, col, shift, pos, cell, e->w.freqs, e->w.feps, e->w.cutoff, e->tile_ctr.as<int>(), (int)cap,
-            e->tiles.as<uint8_t>(), e->pipe_info.as<int4>(), e->tile_ctr.as<int>() + 1, Z, e->w.z2s, l0A, mode, n_splits);
+            e->tiles.as<uint8_t>(), e->pipe_info.as<int4>(), e->tile_ctr.as<int>() + 1, e->status.as<int>(), Z, e->w.z2s, l0A, mode, n_splits);
     sp.end(n_splits > 1 ? 2 : 1);
     RLVD_CUDA(cudaGetLastError());
     return 0;

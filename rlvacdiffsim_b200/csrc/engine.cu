@@ -594,8 +594,51 @@ int rlvd_select_apply(rlvd_engine* e, void* stream, int32_t n_rep, const int32_t
     RLVD_CHECK(e != nullptr && n_rep > 0 && d_first && d_rl_q && d_temperature && d_uniform && d_chosen && d_argmax,
                "rlvd_select_apply: bad argument");
     RLVD_CUDA(cudaSetDevice(e->device));
-    return launch_select_apply(e, (cudaStream_t)stream, n_rep, d_rep_ptr, d_first, d_rl_q, d_temperature, d_uniform, d_actions,
-                               max_actions, apply, d_pos, d_chosen, d_argmax, d_probs, d_gamma);
+    return launch_select_apply(e, (cudaStream_t)stream, n_rep, d_rep_ptr, d_first, d_rl_q, d_temperature, d_uniform, 0ull, 0ull, 0u,
+                               d_actions, max_actions, apply, d_pos, d_chosen, d_argmax, d_probs, d_gamma);
+}
+
+int rlvd_select_apply_philox(rlvd_engine* e, void* stream, int32_t n_rep, const int32_t* d_rep_ptr, const int32_t* d_first,
+                             const float* d_rl_q, const float* d_temperature, uint64_t seed, uint64_t step, uint32_t replica0,
+                             const double* d_actions, int32_t max_actions, int32_t apply, double* d_pos, int32_t* d_chosen,
+                             int32_t* d_argmax, float* d_probs, float* d_gamma) {
+    RLVD_CHECK(e != nullptr && n_rep > 0 && d_first && d_rl_q && d_temperature && d_chosen && d_argmax,
+               "rlvd_select_apply_philox: bad argument");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_select_apply(e, (cudaStream_t)stream, n_rep, d_rep_ptr, d_first, d_rl_q, d_temperature, nullptr, seed, step, replica0,
+                               d_actions, max_actions, apply, d_pos, d_chosen, d_argmax, d_probs, d_gamma);
+}
+
+int rlvd_action_space_general(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const double* d_pos,
+                              const double* d_cell, const double* d_inv_cell, const int32_t* d_site_ptr, const double* d_sites,
+                              double lattice_parameter, int32_t max_vacancies, int32_t max_actions, int32_t* d_count,
+                              double* d_actions, int32_t* d_status) {
+    RLVD_CHECK(e != nullptr && d_node_ptr && d_pos && d_cell && d_inv_cell && d_site_ptr && d_sites && d_count && d_actions && d_status,
+               "rlvd_action_space_general: bad argument");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_action_space_general(e, (cudaStream_t)stream, n_struct, d_node_ptr, d_pos, d_cell, d_inv_cell, d_site_ptr, d_sites,
+                                       lattice_parameter, max_vacancies, max_actions, d_count, d_actions, d_status);
+}
+
+int rlvd_expand_candidates_ex(rlvd_engine* e, void* stream, int32_t n_rep, int32_t n_cand, int32_t n_atoms_per,
+                              const int32_t* d_rep_ptr, const int32_t* d_first, const int32_t* d_Z, const double* d_pos,
+                              const double* d_cell, const double* d_actions, int32_t max_actions, const float* d_inv_in,
+                              const int32_t* d_img_in, int32_t* d_node_ptr, int32_t* d_Z_out, float* d_pos_out, float* d_cell_out,
+                              float* d_inv_out, int32_t* d_img_out, int32_t* d_react_struct, int32_t* d_prod_struct, int32_t* d_owner) {
+    RLVD_CHECK(e != nullptr && n_rep > 0 && n_cand >= 0 && n_atoms_per > 0, "rlvd_expand_candidates_ex: bad sizes");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_expand_candidates(e, (cudaStream_t)stream, n_rep, n_cand, d_rep_ptr, d_first, d_Z, d_pos, d_cell, d_actions,
+                                    max_actions, n_atoms_per, d_node_ptr, d_Z_out, d_pos_out, d_cell_out, d_inv_out, d_img_out,
+                                    d_react_struct, d_prod_struct, d_owner, d_inv_in, d_img_in);
+}
+
+int rlvd_pack_step_records(rlvd_engine* e, void* stream, int32_t n_rep, const int32_t* d_first, const float* d_rl_q,
+                           const int32_t* d_chosen, const float* d_E_R, int32_t replica_id0, int32_t replica_id_stride,
+                           int32_t max_actions, float* d_records) {
+    RLVD_CHECK(e != nullptr && n_rep > 0 && d_first && d_rl_q && d_records && max_actions > 0, "rlvd_pack_step_records: bad argument");
+    RLVD_CUDA(cudaSetDevice(e->device));
+    return launch_pack_records(e, (cudaStream_t)stream, n_rep, d_first, d_rl_q, d_chosen, d_E_R, replica_id0, replica_id_stride,
+                               max_actions, d_records);
 }
 
 int rlvd_sro_counts(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const double* d_pos,
@@ -693,6 +736,10 @@ int rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, in
     int status = 0;
     RLVD_CUDA(cudaMemcpyAsync(&status, e->status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     RLVD_CUDA(cudaStreamSynchronize(s));
+    if (status & 2) {
+        RLVD_CUDA(cudaMemsetAsync(e->status.p, 0, sizeof(int), s));
+        RLVD_CHECK(false, "edge stream: the tile pool overflowed its capacity bound (n_edges / 8 + n_nodes) / 4 + 6 n_struct; results discarded");
+    }
     if ((status & 1) && e->use_tensor_cores) {
         // an activation left the fp16-split range of the tensor-core GEMMs (|x| >= 65504: the network diverging on an
         // unphysical structure): redo the call on the fp32 SIMT kernels, which carry any finite fp32 value

@@ -127,8 +127,13 @@ class Engine:
 
     # ------------------------------------------------------------------ K1
     def radius_graph(self, pos: torch.Tensor, cell: torch.Tensor, inv_cell: torch.Tensor, img_range: torch.Tensor,
-                     node_ptr: torch.Tensor, cutoff: Optional[float] = None):
-        """→ (row_ptr i32[M+1], col i32[E], shift i8[E,3], node_struct i32[M]); receiver-sorted CSR."""
+                     node_ptr: torch.Tensor, cutoff: Optional[float] = None, edge_capacity: Optional[int] = None):
+        """→ (row_ptr i32[M+1], col i32[E], shift i8[E,3], node_struct i32[M]); receiver-sorted CSR.
+
+        ``edge_capacity``: size ``col`` / ``shift`` for at most this many edges WITHOUT reading the edge count back (no host
+        synchronisation: whole LSS / TKS steps queue up on the stream); the returned ``col`` then has ``edge_capacity``
+        rows, the tail unused, and ``self.overflow`` (a device flag, read it with :meth:`edge_overflow`) is raised if the
+        true count did not fit."""
         cutoff = self.cutoff if cutoff is None else cutoff
         n_struct, M = node_ptr.numel() - 1, pos.shape[0]
         dev = self.device
@@ -139,6 +144,17 @@ class Engine:
             check(self.lib.rlvd_radius_graph_count(self._h, self._stream(), n_struct, M, _ptr(node_ptr), _ptr(pos),
                                                    _ptr(cell), _ptr(inv_cell), _ptr(img_range), cutoff,
                                                    _ptr(row_ptr), _ptr(node_struct), _ptr(n_edges)))
+            if edge_capacity is not None:
+                E = int(edge_capacity)
+                if getattr(self, "overflow", None) is None:
+                    self.overflow = torch.zeros(1, dtype=torch.int64, device=dev)
+                self.overflow += (n_edges > E).to(torch.int64)
+                col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+                shift = torch.empty((max(E, 1), 3), dtype=torch.int8, device=dev)
+                check(self.lib.rlvd_radius_graph_fill(self._h, self._stream(), n_struct, M, _ptr(node_ptr), _ptr(pos),
+                                                      _ptr(cell), _ptr(inv_cell), _ptr(img_range), cutoff,
+                                                      _ptr(row_ptr), E, _ptr(col), _ptr(shift)))
+                return row_ptr, col, shift, node_struct[:M]
             E = int(n_edges.item())
             if E >= 2 ** 31 - 1:
                 raise RuntimeError(f"{E} edges overflow int32 CSR offsets; split the batch")
@@ -300,6 +316,21 @@ class Engine:
                                              _ptr(count), _ptr(actions), _ptr(status)))
         return count[:G], actions[:G], status[:G]
 
+    def action_space_general(self, pos: torch.Tensor, cells: torch.Tensor, inv_cells: torch.Tensor, node_ptr: torch.Tensor,
+                             site_ptr: torch.Tensor, sites: torch.Tensor, lattice_parameter: float, max_vacancies: int = 1,
+                             max_actions: int = 16):
+        """``rlvd_action_space_general``: any periodic cell; ``sites`` (fp64) / ``site_ptr`` = the perfect-lattice sites of
+        every structure's cell (``actions.lattice_sites_for_cell``), ``inv_cells`` the fp64 inverse cells."""
+        G = node_ptr.numel() - 1
+        count = torch.empty(max(G, 1), dtype=torch.int32, device=self.device)
+        status = torch.empty(max(G, 1), dtype=torch.int32, device=self.device)
+        actions = torch.zeros((max(G, 1), max_actions, 4), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_action_space_general(self._h, self._stream(), G, _ptr(node_ptr), _ptr(pos), _ptr(cells), _ptr(inv_cells),
+                                                     _ptr(site_ptr), _ptr(sites), float(lattice_parameter), int(max_vacancies),
+                                                     int(max_actions), _ptr(count), _ptr(actions), _ptr(status)))
+        return count[:G], actions[:G], status[:G]
+
     # ------------------------------------------------------------------ A2/A3/A5 on the device
     def candidate_offsets(self, count: torch.Tensor):
         R = count.numel()
@@ -309,8 +340,9 @@ class Engine:
             check(self.lib.rlvd_candidate_offsets(self._h, self._stream(), R, _ptr(count), _ptr(first), _ptr(total)))
         return first, total
 
-    def expand_candidates(self, rep_ptr, first, n_cand: int, n_atoms_per: int, Z, pos, cell, actions):
-        """→ dict of the scoring-batch tensors (Z, pos, cell, inv, img, ptr, rs, ps, owner) for ``score_device``."""
+    def expand_candidates(self, rep_ptr, first, n_cand: int, n_atoms_per: int, Z, pos, cell, actions, inv_in=None, img_in=None):
+        """→ dict of the scoring-batch tensors (Z, pos, cell, inv, img, ptr, rs, ps, owner) for ``score_device``.
+        ``inv_in`` f32[R,3,3] / ``img_in`` i32[R,3]: the replicas' inverse cells / image ranges (general cells)."""
         R, S = rep_ptr.numel() - 1, 2 * n_cand
         dev = self.device
         o = {"Z": torch.empty(S * n_atoms_per, dtype=torch.int32, device=dev),
@@ -323,16 +355,32 @@ class Engine:
              "ps": torch.empty(n_cand, dtype=torch.int32, device=dev),
              "owner": torch.empty(n_cand, dtype=torch.int32, device=dev)}
         with torch.cuda.device(dev):
-            check(self.lib.rlvd_expand_candidates(self._h, self._stream(), R, n_cand, n_atoms_per, _ptr(rep_ptr), _ptr(first),
-                                                  _ptr(Z), _ptr(pos), _ptr(cell), _ptr(actions), actions.shape[1], _ptr(o["ptr"]),
-                                                  _ptr(o["Z"]), _ptr(o["pos"]), _ptr(o["cell"]), _ptr(o["inv"]), _ptr(o["img"]),
-                                                  _ptr(o["rs"]), _ptr(o["ps"]), _ptr(o["owner"])))
+            check(self.lib.rlvd_expand_candidates_ex(self._h, self._stream(), R, n_cand, n_atoms_per, _ptr(rep_ptr), _ptr(first),
+                                                     _ptr(Z), _ptr(pos), _ptr(cell), _ptr(actions), actions.shape[1], _ptr(inv_in),
+                                                     _ptr(img_in), _ptr(o["ptr"]), _ptr(o["Z"]), _ptr(o["pos"]), _ptr(o["cell"]),
+                                                     _ptr(o["inv"]), _ptr(o["img"]), _ptr(o["rs"]), _ptr(o["ps"]), _ptr(o["owner"])))
         return o
 
-    def select_apply(self, rep_ptr, first, rl_q, temperature, uniform, actions, pos, apply: bool = True):
+    def select_apply(self, rep_ptr, first, rl_q, temperature, uniform, actions, pos, apply: bool = True,
+                     philox: Optional[Tuple[int, int, int]] = None):
         """→ (chosen i32[R], argmax i32[R], probs f32[R, max_actions], gamma f32[R]); ``pos`` (fp64) is updated in place
-        when ``apply``; gamma = sum(exp(Q / kT)) is the TKS total rate (simulator.py:262)."""
+        when ``apply``; gamma = sum(exp(Q / kT)) is the TKS total rate (simulator.py:262).  ``uniform``: the caller's
+        draws (``np.random``-compatible replay); ``uniform=None`` with ``philox=(seed, step, replica0)``: counter-based
+        draws on the device (``rlvd_select_apply_philox``)."""
         R = rep_ptr.numel() - 1
+        if uniform is None:
+            if philox is None:
+                raise ValueError("select_apply needs uniforms or a (seed, step, replica0) Philox counter")
+            chosen = torch.empty(R, dtype=torch.int32, device=self.device)
+            amax = torch.empty(R, dtype=torch.int32, device=self.device)
+            probs = torch.zeros((R, actions.shape[1]), dtype=torch.float32, device=self.device)
+            gamma = torch.empty(R, dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                check(self.lib.rlvd_select_apply_philox(self._h, self._stream(), R, _ptr(rep_ptr), _ptr(first), _ptr(rl_q),
+                                                        _ptr(temperature), int(philox[0]) & (2 ** 64 - 1), int(philox[1]),
+                                                        int(philox[2]), _ptr(actions), actions.shape[1], int(apply), _ptr(pos),
+                                                        _ptr(chosen), _ptr(amax), _ptr(probs), _ptr(gamma)))
+            return chosen, amax, probs, gamma
         chosen = torch.empty(R, dtype=torch.int32, device=self.device)
         amax = torch.empty(R, dtype=torch.int32, device=self.device)
         probs = torch.zeros((R, actions.shape[1]), dtype=torch.float32, device=self.device)
@@ -342,6 +390,15 @@ class Engine:
                                              _ptr(temperature), _ptr(uniform), _ptr(actions), actions.shape[1], int(apply),
                                              _ptr(pos), _ptr(chosen), _ptr(amax), _ptr(probs), _ptr(gamma)))
         return chosen, amax, probs, gamma
+
+    def pack_step_records(self, first, rl_q, chosen, E_R, replica_id0: int, replica_id_stride: int, max_actions: int) -> torch.Tensor:
+        """``rlvd_pack_step_records`` → f32[R, 4 + max_actions] rows {replica id, n_actions, chosen, E_R, Q...}."""
+        R = first.numel() - 1
+        rec = torch.empty((R, 4 + max_actions), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rlvd_pack_step_records(self._h, self._stream(), R, _ptr(first), _ptr(rl_q), _ptr(chosen), _ptr(E_R),
+                                                  int(replica_id0), int(replica_id_stride), int(max_actions), _ptr(rec)))
+        return rec
 
     # ------------------------------------------------------------------ Warren-Cowley pair counts
     def sro_counts(self, pos: torch.Tensor, cells: torch.Tensor, node_ptr: torch.Tensor, species_index: torch.Tensor,
@@ -366,10 +423,28 @@ class Engine:
         return out[:G]
 
     # ------------------------------------------------------------------ whole path, device-resident inputs
+    def edge_overflow(self) -> int:
+        """Number of capacity-bounded radius graphs whose true edge count did not fit (synchronises; clears the flag)."""
+        if getattr(self, "overflow", None) is None:
+            return 0
+        n = int(self.overflow.item())
+        self.overflow.zero_()
+        return n
+
     def score_device(self, Z, pos, cell, inv_cell, img_range, node_ptr, react_struct, prod_struct, qp: QParams,
-                     temperature=None, max_struct_nodes: int = 0, head_inputs: bool = False) -> Dict[str, torch.Tensor]:
+                     temperature=None, max_struct_nodes: int = 0, head_inputs: bool = False,
+                     edge_capacity: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """K1..K5 on device-resident inputs.  With ``edge_capacity`` the call never synchronises with the host: the graph is
+        built into a buffer of that many edges and the fp16-range status word is NOT polled (``check_status`` /
+        ``edge_overflow`` at the caller's next synchronisation point)."""
         n_struct = node_ptr.numel() - 1
-        row_ptr, col, shift, node_struct = self.radius_graph(pos, cell, inv_cell, img_range, node_ptr)
+        row_ptr, col, shift, node_struct = self.radius_graph(pos, cell, inv_cell, img_range, node_ptr, edge_capacity=edge_capacity)
+        if edge_capacity is not None:
+            q = self.representation(Z, pos, cell, node_struct, row_ptr, col, shift, n_struct, node_ptr=node_ptr,
+                                    max_struct_nodes=max_struct_nodes)
+            out = self.readout(q, Z, node_ptr, react_struct, prod_struct, qp, temperature, head_inputs=head_inputs)
+            out["n_edges"] = int(edge_capacity)
+            return out
 
         def run():
             q = self.representation(Z, pos, cell, node_struct, row_ptr, col, shift, n_struct, node_ptr=node_ptr,
@@ -377,7 +452,10 @@ class Engine:
             return self.readout(q, Z, node_ptr, react_struct, prod_struct, qp, temperature, head_inputs=head_inputs)
 
         out = run()
-        if self.check_status() & 1:
+        status = self.check_status()
+        if status & 2:
+            raise RuntimeError("rlvd_b200: the edge-tile pool overflowed its capacity bound; results discarded")
+        if status & 1:
             # an activation left the fp16-split range of the tensor-core GEMMs (the network diverging on an unphysical
             # structure, |x| >= 65504): repeat on the fp32 SIMT kernels, which carry any finite fp32 value
             self.set_option("tensor_cores", 0)

@@ -81,3 +81,27 @@ def allreduce_gradients(parameters, group=None) -> None:
     for g in grads:
         g.copy_(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
+
+
+def gather_step_device(engine, first: torch.Tensor, rl_q: torch.Tensor, chosen: torch.Tensor, E_R: torch.Tensor, rank: int,
+                       world: int, max_actions: int = 12, group=None) -> torch.Tensor:
+    """The per-step exchange of SURVEY.md §8e, device side: every rank packs one fixed-width fp32 row per replica
+    (``rlvd_pack_step_records``: replica id = rank + world * local index, n_actions, chosen, E_R, Q[max_actions]) and ONE
+    ``all_gather_into_tensor`` over NCCL returns all rows to every rank — no numpy round trip, no per-row Python.
+    → f32[world * R, 4 + max_actions] on the device (ranks must hold equally many replicas)."""
+    local = engine.pack_step_records(first, rl_q, chosen, E_R, rank, world, max_actions)
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return local
+    out = torch.empty((world * local.shape[0], local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out
+
+
+def unpack_records(records) -> Tuple[List[np.ndarray], np.ndarray, np.ndarray]:
+    """Host view of gathered rows: (Q per replica, chosen, E_R) in global replica order."""
+    arr = records.cpu().numpy() if torch.is_tensor(records) else np.asarray(records)
+    ids = arr[:, 0].astype(np.int64)
+    order = np.argsort(ids, kind="stable")
+    arr = arr[order]
+    Q = [row[4:4 + int(row[1])].copy() for row in arr]
+    return Q, arr[:, 2].astype(np.int64), arr[:, 3].copy()

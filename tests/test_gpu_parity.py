@@ -1064,3 +1064,207 @@ def test_trainer_full_model_updates(checkpoint_path):
         q_new = ReplicaScorer(model.to("cuda").eval(), 0).score([at], [rb.get_action_space(at, 3.528)], qp)[0]
         q_old = ReplicaScorer(fresh, 0).score([at], [rb.get_action_space(at, 3.528)], qp)[0]
         assert not np.array_equal(q_new, q_old)
+
+
+# ----------------------------------------------------------------------------- general cells, Philox draws, sync-free runs
+
+def _philox_uniform(seed: int, replica: int, step: int) -> float:
+    """Host mirror of actions.cu `philox_uniform` (Philox4x32-10, key = seed, counter = (replica, step lo, step hi, 0))."""
+    M32 = 0xFFFFFFFF
+    c = [replica & M32, step & M32, (step >> 32) & M32, 0]
+    k = [seed & M32, (seed >> 32) & M32]
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & M32, p1 & M32, ((p0 >> 32) ^ c[3] ^ k[1]) & M32, p0 & M32]
+        k = [(k[0] + 0x9E3779B9) & M32, (k[1] + 0xBB67AE85) & M32]
+    return float(((c[0] << 32) | c[1]) >> 11) / 9007199254740992.0
+
+
+def test_action_space_device_general_cell(engine):
+    """rlvd_action_space_general on the reference's own demo input (rhombohedral POSCAR_0, on which the reference's live
+    enumerator trips its assert) and on sheared / jittered cells: same rows as the host enumerator generalised to any cell;
+    on a cubic cell the general kernel reproduces the reference's own output (fixtures)."""
+    demo = read_poscar(os.path.join(GOLD, "POSCAR_0"))
+    jit = demo.copy()
+    jit.set_positions(demo.get_positions() + np.random.RandomState(1).normal(0, 0.04, demo.positions.shape))
+    shifted = demo.copy()
+    shifted.set_positions(demo.get_positions() + demo.cell[0] - 2 * demo.cell[2])          # atoms far outside the home cell
+    got = rb.get_action_space_device(engine, [demo, jit, shifted], 3.528)
+    for g, at in zip(got, (demo, jit, shifted)):
+        ref = rb.get_action_space(at, 3.528)
+        assert len(g) == len(ref) == 12 and [r[0] for r in g] == [r[0] for r in ref]
+        np.testing.assert_allclose(np.asarray(g), np.asarray(ref), rtol=0, atol=1e-11)
+    assert sorted(r[0] for r in got[0]) == [41, 43, 50, 51, 52, 53, 62, 117, 155, 168, 173, 200]      # SURVEY App. D
+    # mixed batch: orthorhombic replicas take the specialised kernel, the demo cell the general one
+    cub = make_crconi_supercell(4, seed=3, jitter=0.03)
+    mixed = rb.get_action_space_device(engine, [cub, demo], 3.528)
+    assert mixed[0] == rb.get_action_space_device(engine, [cub], 3.528)[0]
+    np.testing.assert_allclose(np.asarray(mixed[1]), np.asarray(got[0]), rtol=0, atol=0)
+    # the general kernel on a CUBIC cell against the reference's own enumerator output
+    ref = np.load(os.path.join(GOLD, "ref_actions_sro.npz"))
+    from rlvacdiffsim_b200.actions import lattice_sites_for_cell
+    for name in ("cubic4_s0", "cubic4_s2_jit", "cubic3_s1"):
+        at = Atoms(ref[f"{name}.numbers"], ref[f"{name}.positions"], ref[f"{name}.cell"])
+        sites = lattice_sites_for_cell(at.cell, 3.528)
+        dev = engine.device
+        cnt, act, st = engine.action_space_general(
+            torch.from_numpy(at.positions).to(dev), torch.from_numpy(at.cell[None]).to(dev),
+            torch.from_numpy(np.linalg.inv(at.cell)[None]).to(dev), torch.tensor([0, len(at)], dtype=torch.int32, device=dev),
+            torch.tensor([0, len(sites)], dtype=torch.int32, device=dev), torch.from_numpy(sites).to(dev), 3.528, 1, 12)
+        assert int(st[0]) == 0 and int(cnt[0]) == 12
+        g = act[0].cpu().numpy()
+        assert np.array_equal(g[:, 0], ref[f"{name}.live"][:, 0])
+        np.testing.assert_allclose(g[:, 1:], ref[f"{name}.live"][:, 1:], rtol=0, atol=1e-11)
+
+
+def test_device_lss_on_the_rhombohedral_demo_cell(model):
+    """DeviceLSS on general cells: three steps of two copies of the demo POSCAR against the host loop."""
+    from rlvacdiffsim_b200.simulator import DeviceLSS
+    from rlvacdiffsim_b200.structures import apply_action
+    demo = read_poscar(os.path.join(GOLD, "POSCAR_0"))
+    host = [demo.copy(), demo.copy()]
+    qp = {"alpha": 0.0, "beta": 1.0, "dqn": True}
+    lss = DeviceLSS(model, host, 0, 3.528, 1, qp)
+    assert lss.general
+    scorer = ReplicaScorer(model, 0)
+    rng = np.random.RandomState(8)
+    for step in range(3):
+        u = rng.random_sample(2)
+        res = lss.step(1200.0, uniforms=u)
+        first = res["first"].cpu().numpy()
+        spaces = [rb.get_action_space(h, 3.528) for h in host]
+        q_host = scorer.score(host, spaces, dict(qp, temperature=1200.0))
+        for r in range(2):
+            assert rlq_error(res["rl_q"].cpu().numpy()[first[r]:first[r + 1]], q_host[r]) <= 2e-6     # displacements differ by ~1e-12
+            z = torch.from_numpy(q_host[r]) / (1200.0 * 8.617e-5)
+            cdf = np.cumsum(torch.softmax(z, dim=0).numpy().astype(np.float64)); cdf /= cdf[-1]
+            pick = int(np.searchsorted(cdf, u[r], side="right"))
+            assert int(res["chosen"][r]) == pick
+            host[r] = apply_action(host[r], spaces[r][pick])
+        np.testing.assert_allclose(lss.positions(), np.stack([h.positions for h in host]), rtol=0, atol=1e-10)
+
+
+def test_philox_draws_and_sync_free_run(model, tmp_path):
+    """Counter-based device draws: the kernel's uniforms equal the host Philox4x32-10 mirror; a sync-free
+    TKS run (no host synchronisation inside a block of steps) equals the synchronous Philox run step for step, bitwise."""
+    from rlvacdiffsim_b200.simulator import DeviceLSS
+    eng = model._engine_for(torch.device("cuda", 0))
+    dev = eng.device
+    # (1) uniforms: two-candidate replicas with Q = (0, 0) -> p = (.5, .5): pick = 0 iff u < 0.5 ... probe with 4 bins
+    n, S = 4, 64
+    Q = torch.zeros(S * n, dtype=torch.float32, device=dev)
+    first = torch.arange(0, (S + 1) * n, n, dtype=torch.int32, device=dev)
+    rep_ptr = torch.arange(0, S + 1, dtype=torch.int32, device=dev)
+    actions = torch.zeros(S, n, 4, dtype=torch.float64, device=dev)
+    pos = torch.zeros(S, 3, dtype=torch.float64, device=dev)
+    for step in (0, 1, 7, 2 ** 33 + 5):
+        chosen, _, _, _ = eng.select_apply(rep_ptr, first, Q, torch.full((S,), 700.0, device=dev), None, actions, pos, False,
+                                           philox=(0x1234567887654321, step, 100))
+        want = [min(int(_philox_uniform(0x1234567887654321, 100 + r, step) * 4), 3) for r in range(S)]
+        assert chosen.cpu().numpy().tolist() == want
+    assert len({_philox_uniform(1, r, 0) for r in range(100)}) == 100
+    # (2) sync-free run == synchronous Philox run
+    qp = {"alpha": 1.0, "beta": 0.0, "dqn": False}
+    reps = [make_crconi_supercell(3, seed=40 + s, jitter=0.02) for s in range(3)]
+    a = DeviceLSS(model, reps, 0, 3.528, 1, qp, seed=77, replica_id0=5)
+    b = DeviceLSS(model, reps, 0, 3.528, 1, qp, seed=77, replica_id0=5)
+    H = 7
+    res_a = a.run(H, 900.0, mode="tks", sync_free=True, flush_every=3)
+    sync = [b.step(900.0, rng="philox") for _ in range(H)]
+    for t in range(H):
+        f = sync[t]["first"].cpu().numpy()
+        for r in range(3):
+            assert res_a["Q"][r][t] == sync[t]["rl_q"].cpu().numpy()[f[r]:f[r + 1]].tolist()
+            assert res_a["actions"][r][t] == int(sync[t]["chosen"][r])
+    assert np.array_equal(a.positions(), b.positions())
+    clock = np.cumsum([1.0 / float(sync[t]["gamma"][0]) * 1e-6 for t in range(H)])
+    np.testing.assert_allclose(res_a["time"][0][1:], clock, rtol=1e-12)
+    assert res_a["host_seconds"] < res_a["wall_seconds"]
+    # a different seed or replica id gives a different trajectory
+    c = DeviceLSS(model, reps, 0, 3.528, 1, qp, seed=78, replica_id0=5)
+    res_c = c.run(H, 900.0, mode="tks", sync_free=True)
+    assert res_c["actions"] != res_a["actions"]
+
+
+def test_gather_step_device_single_rank(model):
+    """rlvd_pack_step_records + the gather wrapper (world size 1): rows carry id, count, chosen, E_R and NaN-padded Q."""
+    from rlvacdiffsim_b200.sharding import gather_step_device, unpack_records
+    from rlvacdiffsim_b200.simulator import DeviceLSS
+    reps = [make_crconi_supercell(3, seed=60 + s) for s in range(3)]
+    lss = DeviceLSS(model, reps, 0, 3.528, 1, {"alpha": 0.0, "beta": 1.0, "dqn": True})
+    res = lss.step(700.0, uniforms=np.array([0.1, 0.5, 0.9]), apply=False)
+    rec = gather_step_device(lss.engine, res["first"], res["rl_q"], res["chosen"], res["E_R"], rank=2, world=4, max_actions=16)
+    assert tuple(rec.shape) == (3, 20)
+    Q, chosen, E_R = unpack_records(rec)
+    arr = rec.cpu().numpy()
+    assert arr[:, 0].tolist() == [2.0, 6.0, 10.0] and arr[:, 1].tolist() == [12.0] * 3 and np.isnan(arr[:, 16:]).all()
+    f = res["first"].cpu().numpy()
+    for r in range(3):
+        assert np.array_equal(Q[r], res["rl_q"].cpu().numpy()[f[r]:f[r + 1]]) and chosen[r] == int(res["chosen"][r])
+        assert E_R[r] == float(res["E_R"][f[r]])
+
+
+def _nccl_worker(rank, world, port, ckpt, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from rlvacdiffsim_b200.sharding import gather_step_device, unpack_records
+        from rlvacdiffsim_b200.simulator import DeviceLSS
+        from rlvacdiffsim_b200.structures import apply_action
+        from rlvacdiffsim_b200.trainer import Memory, Trainer
+        model = rb.registry.get_model_class("dqn_v2").load(ckpt).to(f"cuda:{rank}").eval()
+        # (1) per-step gather: rank r owns replicas r, r + W, ...
+        seeds = [200 + rank + world * k for k in range(2)]
+        reps = [make_crconi_supercell(3, seed=s) for s in seeds]
+        lss = DeviceLSS(model, reps, rank, 3.528, 1, {"alpha": 0.0, "beta": 1.0, "dqn": True}, seed=3, replica_id0=0)
+        res = lss.step(700.0, uniforms=np.array([0.3, 0.6]), apply=False)
+        rec = gather_step_device(lss.engine, res["first"], res["rl_q"], res["chosen"], res["E_R"], rank, world, 12)
+        Q, chosen, E_R = unpack_records(rec)
+        ok = len(Q) == 2 * world
+        mine = res["rl_q"].cpu().numpy()
+        ok = ok and np.array_equal(Q[rank], mine[:12]) and np.array_equal(Q[rank + world], mine[12:24])
+        # (2) rl-train: different minibatches per rank, ONE all-reduce of the flat gradient bucket per optimizer step
+        mems = []
+        rng = np.random.RandomState(11 + rank)
+        s = make_crconi_supercell(3, seed=70 + rank, jitter=0.02)
+        mem = Memory(alpha=0.0, beta=1.0, T=700.0)
+        for _ in range(3):
+            space = rb.get_action_space(s, 3.528)
+            a = int(rng.randint(len(space)))
+            nxt = apply_action(s, space[a])
+            mem.add({"state": s, "act": a, "act_space": space, "act_probs": [], "fail": False, "next": nxt, "log_freq": 0.0,
+                     "E_s": float(rng.rand()), "E_min": 0.0, "E_next": float(rng.normal(0, 0.1))})
+            s = nxt
+        mems.append(mem)
+        train_model = rb.registry.get_model_class("dqn_v2").load(ckpt)
+        tr = Trainer(train_model, {"alpha": 0.0, "beta": 1.0, "dqn": True, "temperature": 700.0}, lr=1e-5, train_all=True)
+        tr.dropout = False
+        np.random.seed(4)
+        loss = tr.dqn_update(mems, gamma=0.9, episode_size=1, num_epoch=2, batch_size=2, device=f"cuda:{rank}")
+        flat = tr._full[("cuda", rank)]["params"].clone()
+        others = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(others, flat)
+        ok = ok and all(torch.equal(o, others[0]) for o in others) and np.isfinite(loss) and tr.allreduce_ms > 0.0
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_gather_and_gradient_allreduce(checkpoint_path):
+    """World size 2 over NCCL (skipped on a single-GPU box; run with `gpurun --gpus 2`): the device-side step gather and
+    the rl-train gradient all-reduce — ranks train on different minibatches and end with bit-identical parameters."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, checkpoint_path, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    assert ret[0] and ret[1]
