@@ -598,9 +598,10 @@ def test_action_space_device_matches_host_enumerator(engine):
     np.testing.assert_allclose(np.asarray(two), np.asarray(ref2), rtol=0, atol=1e-12)
     with pytest.raises(AssertionError, match="Expected 1 vacancy"):            # action.py:35
         rb.get_action_space_device(engine, [reps[4]], 3.528)
-    # a non-orthorhombic cell (the demo POSCAR) falls through to the host enumerator
+    # a non-orthorhombic cell (the demo POSCAR) takes the general minimum-image kernel
     demo = read_poscar(os.path.join(GOLD, "POSCAR_0"))
-    assert rb.get_action_space_device(engine, [demo], 3.528)[0] == rb.get_action_space(demo, 3.528)
+    np.testing.assert_allclose(np.asarray(rb.get_action_space_device(engine, [demo], 3.528)[0]),
+                               np.asarray(rb.get_action_space(demo, 3.528)), rtol=0, atol=1e-12)
 
 
 def test_device_lss_steps_match_host_loop(model):
@@ -1180,10 +1181,10 @@ def test_philox_draws_and_sync_free_run(model, tmp_path):
     clock = np.cumsum([1.0 / float(sync[t]["gamma"][0]) * 1e-6 for t in range(H)])
     np.testing.assert_allclose(res_a["time"][0][1:], clock, rtol=1e-12)
     assert res_a["host_seconds"] < res_a["wall_seconds"]
-    # a different seed or replica id gives a different trajectory
-    c = DeviceLSS(model, reps, 0, 3.528, 1, qp, seed=78, replica_id0=5)
-    res_c = c.run(H, 900.0, mode="tks", sync_free=True)
-    assert res_c["actions"] != res_a["actions"]
+    # a different seed or replica id gives a different trajectory (at kT = 5 eV the policy is nearly uniform)
+    runs = [DeviceLSS(model, reps, 0, 3.528, 1, qp, seed=sd, replica_id0=rid).run(H, 60000.0, mode="tks", sync_free=True)["actions"]
+            for sd, rid in ((77, 5), (78, 5), (77, 6), (77, 5))]
+    assert runs[0] != runs[1] and runs[0] != runs[2] and runs[0] == runs[3]
 
 
 def test_gather_step_device_single_rank(model):
