@@ -426,6 +426,29 @@ class TNet(nn.Module, _EngineMixin):
         h.D_scale = 1.0 / float(self.hyper["D_scaler"])
         return h, keep
 
+    def time_device(self, Z, pos, cell, inv, img, node_ptr, max_struct_nodes: int, T, defect, edge_capacity=None) -> torch.Tensor:
+        """The forward on device-resident frames (fp32 ``pos[M,3]``, ``cell / inv [G,3,3]``, ``img[G,3]``, ``node_ptr``):
+        K1 → K2-K4 → ``rlvd_time_readout``.  ``edge_capacity``: build the graph without reading the edge count back (frames
+        of a sync-free TKS run, config 4)."""
+        eng = self._engine_for(pos.device)
+        G = node_ptr.numel() - 1
+        row_ptr, col, shift, node_struct = eng.radius_graph(pos, cell, inv, img, node_ptr, edge_capacity=edge_capacity)
+
+        def rep():
+            return eng.representation(Z, pos, cell, node_struct, row_ptr, col, shift, G, node_ptr=node_ptr,
+                                      max_struct_nodes=max_struct_nodes)
+        q = rep()
+        if edge_capacity is None and eng.check_status() & 1:   # operand outside the tensor-core split's range: fp32 SIMT kernels
+            eng.set_option("tensor_cores", 0)
+            try:
+                q = rep()
+            finally:
+                eng.set_option("tensor_cores", 1)
+        head, keep = self._head(pos.device)
+        time = eng.time_readout(q, node_ptr, T, defect, head)
+        del keep
+        return time
+
     def forward(self, batch, inference: bool = False, training: bool = False):
         if torch.is_grad_enabled() and (training or self.training) and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError("t_net backward has no sm_100a kernels yet; call under torch.no_grad() / .eval()")
@@ -441,22 +464,10 @@ class TNet(nn.Module, _EngineMixin):
         node_ptr = torch.from_numpy(node_ptr_host).to(dev)
         cell = batch["cell"].to(torch.float32).contiguous()
         posc = pos.to(torch.float32).contiguous()
-        row_ptr, col, shift, node_struct = eng.radius_graph(posc, cell, torch.from_numpy(inv).to(dev),
-                                                            torch.from_numpy(img).to(dev), node_ptr)
         Zc = batch["elems"].to(torch.int32).contiguous()
-        q = eng.representation(Zc, posc, cell, node_struct, row_ptr, col, shift, len(counts), node_ptr=node_ptr,
-                               max_struct_nodes=int(counts.max()))
-        if eng.check_status() & 1:        # operand outside the tensor-core split's range: fp32 SIMT kernels
-            eng.set_option("tensor_cores", 0)
-            try:
-                q = eng.representation(Zc, posc, cell, node_struct, row_ptr, col, shift, len(counts), node_ptr=node_ptr,
-                                       max_struct_nodes=int(counts.max()))
-            finally:
-                eng.set_option("tensor_cores", 1)
         G = len(counts)
         T = torch.as_tensor(batch["T"], dtype=torch.float32, device=dev).reshape(G).contiguous()
         defect = torch.as_tensor(batch["defect"], dtype=torch.float32, device=dev).reshape(G).contiguous()
-        head, keep = self._head(dev)
-        time = eng.time_readout(q, node_ptr, T, defect, head)
-        del keep
+        time = self.time_device(Zc, posc, cell, torch.from_numpy(inv).to(dev), torch.from_numpy(img).to(dev), node_ptr,
+                                int(counts.max()), T, defect)
         return {"time": time}
