@@ -254,8 +254,8 @@ def bench_config4(model, eng, dev, rank: int, n_rep: int, steps: int) -> dict:
         times.append((a, b, t))
         n_frames[0] += B
 
-    for _ in range(2):                                      # warm-up (also sizes every workspace)
-        lss.run(2, 900.0, mode="tks", sync_free=True, flush_every=2, on_frames=on_frames)
+    for _ in range(2):                                      # warm-up with the timed run's flush size (sizes every workspace)
+        lss.run(8, 900.0, mode="tks", sync_free=True, flush_every=8, on_frames=on_frames)
     times.clear(); n_frames[0] = 0
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
@@ -633,6 +633,23 @@ def main():
         step_one()["rl_q"].cpu()
     ms_one = (time.perf_counter() - t0) * 1e3 / 20
 
+    # the same call frozen into a CUDA graph (Engine.capture_score): one launch of ~30 kernel nodes instead of 30 launches
+    ms_one_graph = graph_err = None
+    try:
+        T1 = torch.full((len(one["react_struct"]),), Q_PARAMS["temperature"], dtype=torch.float32, device=dev)
+        gs = eng.capture_score(d1["Z"], d1["pos"], d1["cell"], d1["inv"], d1["img"], d1["ptr"], d1["rs"], d1["ps"], qp, T1, mx1)
+        for _ in range(5):
+            gs()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            q_g = gs(pos=d1["pos"])["rl_q"].cpu()
+        ms_one_graph = (time.perf_counter() - t0) * 1e3 / 50
+        graph_err = float((q_g - step_one()["rl_q"].cpu()).abs().max())
+        assert eng.edge_overflow() == 0
+    except Exception as exc:
+        graph_err = f"{type(exc).__name__}: {exc}"
+
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -754,7 +771,11 @@ def main():
             "dedup": dedup_obj,
             "single_replica": {"what": "one 255-atom replica, 12 candidate hops per call (24 structures), device-resident inputs, "
                                        "Q-values read back to the host every call (rank 0 wall clock)",
-                               "ms_per_call": ms_one, "value": len(one["react_struct"]) / (ms_one * 1e-3), "unit": "Q-evals/s"},
+                               "ms_per_call": ms_one, "value": len(one["react_struct"]) / (ms_one * 1e-3), "unit": "Q-evals/s",
+                               "cuda_graph": {"what": "the same call replayed as ONE CUDA graph (Engine.capture_score), positions copied "
+                                                      "in and Q read back every call", "ms_per_call": ms_one_graph,
+                                              "value": (len(one["react_struct"]) / (ms_one_graph * 1e-3)) if ms_one_graph else None,
+                                              "max_abs_diff_vs_eager_rl_q": graph_err}},
             "device_lss": {"what": "one full LSS step of every replica on the device: rlvd_action_space -> expand -> K1..K5 -> "
                                    "softmax/draw -> apply, fp64 state resident in HBM, one 8-byte D2H per step",
                            "ms_per_step": ms_lss, "value": world * n_q / (ms_lss * 1e-3), "unit": "Q-evals/s (rank 0 wall clock)",

@@ -126,6 +126,42 @@ def test_edges_fuzz_bit_exact(engine):
         assert np.array_equal(col.cpu().numpy(), o_col) and np.array_equal(shift.cpu().numpy(), o_shift), trial
 
 
+def test_edges_cell_list_bit_exact(engine):
+    """Structures above 512 atoms whose cell holds >= 3 cutoff-sized bins per axis take the cell-list sweep of neighbor.cu;
+    the CSR must equal the oracle's all-pairs edge list bit for bit — orthorhombic and sheared cells, strong jitter, atoms
+    outside the home cell, mixed with a small structure that takes the all-pairs sweep in the same launch."""
+    rng = np.random.RandomState(12)
+    a0 = 3.528
+    cases = []
+    for reps, shear in (((5, 5, 6), 0.0), ((6, 5, 5), 0.18), ((7, 5, 5), -0.1)):
+        m = np.stack(np.meshgrid(*[np.arange(r) for r in reps], indexing="ij"), -1).reshape(-1, 3)
+        basis = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0]])
+        frac = ((m[:, None, :] + basis[None]).reshape(-1, 3)) / np.array(reps)
+        cell = np.diag(np.array(reps) * a0).astype(np.float64)
+        cell[1, 0] = shear * cell[0, 0]; cell[2, 1] = -shear * cell[1, 1]
+        pos = frac @ cell + rng.normal(0, 0.12, (len(frac), 3))
+        pos[::7] += cell[0] - cell[2]                                   # some atoms far outside the home cell
+        keep = rng.permutation(len(pos))[: len(pos) - 3]
+        cases.append((pos[keep], cell))
+    small = make_crconi_supercell(4, seed=1, jitter=0.05)
+    cases.append((small.positions, small.cell))
+    pos = np.concatenate([c[0] for c in cases]).astype(np.float32)
+    cells = np.stack([c[1] for c in cases])
+    node_ptr = np.concatenate([[0], np.cumsum([len(c[0]) for c in cases])]).astype(np.int32)
+    assert (np.diff(node_ptr)[:3] > 512).all()
+    row_ptr, col, shift, _ = _device_graph(engine, pos, cells, node_ptr)
+    recv, send, S = _csr_to_triplets(row_ptr, col, shift)
+    off = 0
+    for g, (p, c) in enumerate(cases):
+        ri, sj, Sr = radius_graph_pbc(p.astype(np.float32), c, 5.0)
+        n_e = len(ri)
+        assert np.array_equal(recv[off:off + n_e], ri + node_ptr[g]), g
+        assert np.array_equal(send[off:off + n_e], sj + node_ptr[g]), g
+        assert np.array_equal(S[off:off + n_e], Sr), g
+        off += n_e
+    assert off == len(recv)
+
+
 def test_edges_config3_digest(engine):
     g = load_gold("syn2040_v8")
     pos = g["positions"].astype(np.float32)
