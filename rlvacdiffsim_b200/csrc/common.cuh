@@ -124,6 +124,7 @@ struct rlvd_engine {
     rlvd::DevBuf l0A;                                          // [M, 256] species-resolved radial sums of layer 0
     rlvd::DevBuf train_ws;                                     // saved activations + backward scratch (train_full.cu)
     float eps = 1e-8f;                                         // hyper_parameters.reaction_model.epsilon (rlvd_set_hyper)
+    int edge_cap_per_node = 64;                                // CSR capacity bound of rlvd_score_reactions_host (grows on demand)
     int n_species = 0;                                         // rlvd_set_species
     int species_z[3] = {};
     bool use_l0_sums = true;        // layer 0 as per-node GEMMs over species-resolved radial sums (needs rlvd_set_species)

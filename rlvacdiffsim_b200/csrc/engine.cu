@@ -704,12 +704,11 @@ int rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, in
                               e->in_cell.as<float>(), e->in_inv.as<float>(), e->in_img.as<int>(), cutoff,
                               e->g_row_ptr.as<int>(), e->g_node_struct.as<int>(), e->g_nedges.as<int64_t>()))
         return 1;
-    int64_t E = 0;
-    RLVD_CUDA(cudaMemcpyAsync(&E, e->g_nedges.p, 8, cudaMemcpyDeviceToHost, s));
-    RLVD_CUDA(cudaStreamSynchronize(s));
-    RLVD_CHECK(E >= 0 && E < (int64_t)0x7fffffff, "edge count %lld overflows int32 offsets; split the batch",
-               (long long)E);
-    if (h_n_edges != nullptr) *h_n_edges = E;
+    // No host round trip for the edge count: the CSR is filled into a buffer sized for edge_cap edges (64 per node — FCC at
+    // a = 3.528 has 54 inside 5.0 A; a denser batch is detected after the final synchronisation and the call repeated with
+    // a larger bound) and the true count comes back with the results.
+    const int64_t edge_cap = std::min<int64_t>((int64_t)0x7ffffff0, std::max<int64_t>(e->edge_cap_per_node, 8) * (int64_t)M);
+    int64_t E = edge_cap;
     if (e->g_col.ensure((size_t)(E + 1) * 4) || e->g_shift.ensure((size_t)(E + 1) * 3)) return 1;
     if (launch_neighbor_fill(e, s, n_struct, M, e->in_node_ptr.as<int>(), e->in_pos.as<float>(),
                              e->in_cell.as<float>(), e->in_inv.as<float>(), e->in_img.as<int>(), cutoff,
@@ -734,8 +733,20 @@ int rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, in
         if (hosts[k] != nullptr)
             RLVD_CUDA(cudaMemcpyAsync(hosts[k], op + (size_t)k * n_react, (size_t)n_react * 4, cudaMemcpyDeviceToHost, s));
     int status = 0;
+    int64_t E_true = 0;
     RLVD_CUDA(cudaMemcpyAsync(&status, e->status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    RLVD_CUDA(cudaMemcpyAsync(&E_true, e->g_nedges.p, 8, cudaMemcpyDeviceToHost, s));
     RLVD_CUDA(cudaStreamSynchronize(s));
+    RLVD_CHECK(E_true >= 0 && E_true < (int64_t)0x7fffffff, "edge count %lld overflows int32 offsets; split the batch", (long long)E_true);
+    if (h_n_edges != nullptr) *h_n_edges = E_true;
+    if (E_true > edge_cap) {
+        // denser than 64 neighbours per atom: the CSR was truncated — repeat with a bound that fits
+        RLVD_CUDA(cudaMemsetAsync(e->status.p, 0, sizeof(int), s));
+        e->edge_cap_per_node = (int)((E_true + M - 1) / M) + 8;
+        return rlvd_score_reactions_host(e, stream, n_struct, n_nodes, h_node_ptr, h_Z, h_pos, h_cell, h_inv_cell, h_img_range, cutoff,
+                                         n_react, h_react_struct, h_prod_struct, qp, h_temperature, h_rl_q, h_q0, h_q1, h_delta_e, h_E_R,
+                                         h_E_P, h_n_edges);
+    }
     if (status & 2) {
         RLVD_CUDA(cudaMemsetAsync(e->status.p, 0, sizeof(int), s));
         RLVD_CHECK(false, "edge stream: the tile pool overflowed its capacity bound (n_edges / 8 + n_nodes) / 4 + 6 n_struct; results discarded");

@@ -486,6 +486,8 @@ class Engine:
     def _pin(self, key: str, arr: np.ndarray) -> torch.Tensor:
         """Copy ``arr`` into a cached pinned staging tensor and return the (sliced) tensor."""
         t = torch.from_numpy(np.ascontiguousarray(arr))
+        if t.is_pinned():                  # the caller's array already lives in page-locked memory (pin_arrays): no staging copy
+            return t.reshape(-1)
         buf = self._pinned.get(key)
         if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
             buf = torch.empty(max(t.numel(), 16), dtype=t.dtype).pin_memory()
@@ -493,6 +495,21 @@ class Engine:
         view = buf[: t.numel()]
         view.copy_(t.reshape(-1))
         return view
+
+    @staticmethod
+    def pin_arrays(arrays: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+        """Copies of ``arrays`` that live in page-locked host memory (numpy views of pinned torch tensors): ``score_host``
+        then DMA-copies them straight to the device instead of staging them through its own pinned buffers first."""
+        out = {}
+        for k, a in arrays.items():
+            if not isinstance(a, np.ndarray):
+                out[k] = a
+                continue
+            t = torch.empty(a.shape, dtype=torch.from_numpy(np.empty(0, dtype=a.dtype)).dtype).pin_memory()
+            v = t.numpy()
+            v[...] = a
+            out[k] = v
+        return out
 
     def score_host(self, Z: np.ndarray, pos: np.ndarray, cells: np.ndarray, node_ptr: np.ndarray,
                    react_struct: np.ndarray, prod_struct: np.ndarray, qp: QParams,
