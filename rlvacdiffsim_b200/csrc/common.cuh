@@ -164,6 +164,8 @@ int launch_neighbor_fill(rlvd_engine* e, cudaStream_t s, int n_struct, int n_nod
                          const float* pos, const float* cell, const float* inv, const int* img, float cutoff,
                          const int* row_ptr, int64_t cap, int* col, int8_t* shift);
 
+int launch_clamp_graph(rlvd_engine* e, cudaStream_t s, int n_nodes, int* row_ptr, const int64_t* n_edges, int64_t cap);
+
 struct LinearArgs {
     const float* A = nullptr;     // [M, K1] rows of length lda
     int lda = 0;

@@ -710,6 +710,7 @@ int rlvd_score_reactions_host(rlvd_engine* e, void* stream, int32_t n_struct, in
     const int64_t edge_cap = std::min<int64_t>((int64_t)0x7ffffff0, std::max<int64_t>(e->edge_cap_per_node, 8) * (int64_t)M);
     int64_t E = edge_cap;
     if (e->g_col.ensure((size_t)(E + 1) * 4) || e->g_shift.ensure((size_t)(E + 1) * 3)) return 1;
+    if (launch_clamp_graph(e, s, M, e->g_row_ptr.as<int>(), e->g_nedges.as<int64_t>(), edge_cap)) return 1;
     if (launch_neighbor_fill(e, s, n_struct, M, e->in_node_ptr.as<int>(), e->in_pos.as<float>(),
                              e->in_cell.as<float>(), e->in_inv.as<float>(), e->in_img.as<int>(), cutoff,
                              e->g_row_ptr.as<int>(), E, e->g_col.as<int>(), e->g_shift.as<int8_t>()))

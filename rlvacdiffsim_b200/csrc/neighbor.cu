@@ -409,6 +409,14 @@ __global__ void row_ptr_final_kernel(int n_nodes, const int* __restrict__ node_s
     if (i == n_nodes) row_ptr[n_nodes] = struct_edge_ptr[n_struct];
 }
 
+// A CSR counted into more edges than the caller's buffer holds must not be walked: empty every row (the caller detects the
+// overflow from the edge count at its next synchronisation point and repeats the call with a larger buffer).
+__global__ void clamp_graph_kernel(int n_nodes, int* __restrict__ row_ptr, const int64_t* __restrict__ n_edges, long long cap) {
+    if (*n_edges <= cap) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_nodes) row_ptr[i] = 0;
+}
+
 int neighbor_splits(int n_struct) { return n_struct >= 296 ? 1 : std::min(8, (592 + n_struct - 1) / n_struct); }
 
 size_t neighbor_smem() {
@@ -457,6 +465,14 @@ int launch_neighbor_count(rlvd_engine* e, cudaStream_t s, int n_struct, int n_no
     row_ptr_final_kernel<<<(n_nodes + 1 + 255) / 256, 256, 0, s>>>(n_nodes, node_struct,
                                                                    e->struct_edge_ptr.as<int>(), n_struct, row_ptr);
     sp.end(n_splits == 1 ? 3 : 4);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_clamp_graph(rlvd_engine* e, cudaStream_t s, int n_nodes, int* row_ptr, const int64_t* n_edges, int64_t cap) {
+    if (n_nodes <= 0) return 0;
+    clamp_graph_kernel<<<(n_nodes + 1 + 255) / 256, 256, 0, s>>>(n_nodes, row_ptr, n_edges, (long long)cap);
+    e->launches += 1;
     RLVD_CUDA(cudaGetLastError());
     return 0;
 }

@@ -149,6 +149,7 @@ class Engine:
                 if getattr(self, "overflow", None) is None:
                     self.overflow = torch.zeros(1, dtype=torch.int64, device=dev)
                 self.overflow += (n_edges > E).to(torch.int64)
+                row_ptr.mul_((n_edges <= E).to(torch.int32))      # a truncated CSR must not be walked: empty every row
                 col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
                 shift = torch.empty((max(E, 1), 3), dtype=torch.int8, device=dev)
                 check(self.lib.rlvd_radius_graph_fill(self._h, self._stream(), n_struct, M, _ptr(node_ptr), _ptr(pos),

@@ -1218,7 +1218,8 @@ def test_philox_draws_and_sync_free_run(model, tmp_path):
     np.testing.assert_allclose(res_a["time"][0][1:], clock, rtol=1e-12)
     assert res_a["host_seconds"] < res_a["wall_seconds"]
     # a different seed or replica id gives a different trajectory (at kT = 5 eV the policy is nearly uniform)
-    runs = [DeviceLSS(model, reps, 0, 3.528, 1, qp, seed=sd, replica_id0=rid).run(H, 60000.0, mode="tks", sync_free=True)["actions"]
+    lss_qp = {"alpha": 0.0, "beta": 1.0, "dqn": True}            # Q = -delta_e + DQN correction: O(1 eV) spreads, flat at kT = 5 eV
+    runs = [DeviceLSS(model, reps, 0, 3.528, 1, lss_qp, seed=sd, replica_id0=rid).run(H, 60000.0, mode="lss", sync_free=True)["actions"]
             for sd, rid in ((77, 5), (78, 5), (77, 6), (77, 5))]
     assert runs[0] != runs[1] and runs[0] != runs[2] and runs[0] == runs[3]
 
