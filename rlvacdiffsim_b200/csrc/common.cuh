@@ -124,6 +124,7 @@ struct rlvd_engine {
     rlvd::DevBuf l0A;                                          // [M, 256] species-resolved radial sums of layer 0
     rlvd::DevBuf train_ws;                                     // saved activations + backward scratch (train_full.cu)
     float eps = 1e-8f;                                         // hyper_parameters.reaction_model.epsilon (rlvd_set_hyper)
+    int n_scale_species = 3;                                   // entries of species_energy_scale.{scales, shifts} in the checkpoint
     int edge_cap_per_node = 64;                                // CSR capacity bound of rlvd_score_reactions_host (grows on demand)
     int n_species = 0;                                         // rlvd_set_species
     int species_z[3] = {};

@@ -316,13 +316,22 @@ int rlvd_finalize_weights(rlvd_engine* e) {
     if (need(rm + "energy_output.layers.0.bias", 64, &t) || upload_raw(e, *t, &w.en_b0)) return 1;
     if (need(rm + "energy_output.layers.3.weight", 64, &t) || upload_raw(e, *t, &w.en_w3)) return 1;
     if (need(rm + "energy_output.layers.3.bias", 1, &t) || upload_raw(e, *t, &w.en_b3)) return 1;
-    if (need(rm + "species_energy_scale.scales", 3, &t) || upload_raw(e, *t, &w.sp_scales)) return 1;
-    if (need(rm + "species_energy_scale.shifts", 3, &t) || upload_raw(e, *t, &w.sp_shifts)) return 1;
+    // species_energy_scale: one (scale, shift) per model species — the count comes from the checkpoint, not from this file
+    int n_sp = 0;
+    {
+        auto it = hs.find(rm + "species_energy_scale.scales");
+        RLVD_CHECK(it != hs.end() && !it->second.f.empty() && it->second.f.size() <= 64,
+                   "missing checkpoint tensor 'reaction_model.species_energy_scale.scales' (1..64 species)");
+        n_sp = (int)it->second.f.size();
+    }
+    if (need(rm + "species_energy_scale.scales", n_sp, &t) || upload_raw(e, *t, &w.sp_scales)) return 1;
+    if (need(rm + "species_energy_scale.shifts", n_sp, &t) || upload_raw(e, *t, &w.sp_shifts)) return 1;
+    e->n_scale_species = n_sp;
     {
         auto it = hs.find(rm + "species_energy_scale.elem_lookup");
         RLVD_CHECK(it != hs.end() && it->second.i.size() == 100,
                    "missing int32 checkpoint tensor 'reaction_model.species_energy_scale.elem_lookup' [100]");
-        for (int32_t v : it->second.i) RLVD_CHECK(v >= 0 && v < 3, "elem_lookup entry %d out of range", v);
+        for (int32_t v : it->second.i) RLVD_CHECK(v >= 0 && v < n_sp, "elem_lookup entry %d out of range for %d species", v, n_sp);
         void* d = nullptr;
         if (upload(e, it->second.i.data(), 100 * sizeof(int32_t), &d)) return 1;
         w.elem_lookup = reinterpret_cast<const int32_t*>(d);

@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(NB_THREADS) neighbor_kernel(
     int* __restrict__ struct_edges,  // count only
     int* __restrict__ col, int8_t* __restrict__ shift, long long cap,
     int n_splits,                    // small batches: blockIdx.y takes every n_splits-th group of receivers
-    int mode) {                      // count: 0 = degrees + per-structure scan, 1 = degrees only, 2 = scan only
+    int mode,                        // count: 0 = degrees + per-structure scan, 1 = degrees only, 2 = scan only
+    int cl_enabled) {                // the launch carries the cell list's shared memory (batches of large structures only)
     extern __shared__ float smem_f[];
     __shared__ int warp_sums[NB_THREADS / 32 + 1];
     const int g = blockIdx.x;
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(NB_THREADS) neighbor_kernel(
 
     // ---- cell list (large single-image structures): bin, counting-sort, then sweep 27 bins per receiver
     CellList CLs;
-    cl_dims(C, sqrtf(rc2), staged ? n : 0, CLs.nb);
+    cl_dims(C, sqrtf(rc2), staged && cl_enabled ? n : 0, CLs.nb);
     {
         int* cl_base = reinterpret_cast<int*>(smem_f + 3 * MAX_SMEM_ATOMS) + MAX_SMEM_ATOMS;
         CLs.start = cl_base;                                                        // [CL_MAX_BINS + 1]
@@ -419,10 +420,14 @@ __global__ void clamp_graph_kernel(int n_nodes, int* __restrict__ row_ptr, const
 
 int neighbor_splits(int n_struct) { return n_struct >= 296 ? 1 : std::min(8, (592 + n_struct - 1) / n_struct); }
 
-size_t neighbor_smem() {
-    return (size_t)MAX_SMEM_ATOMS * 3 * sizeof(float) + (size_t)MAX_SMEM_ATOMS * sizeof(int)       // positions, degrees
-           + (size_t)(CL_MAX_BINS + 2) * sizeof(int) + (size_t)2 * MAX_SMEM_ATOMS * sizeof(unsigned short)   // cell list
-           + (size_t)(NB_THREADS / 32) * CL_MAX_HITS * sizeof(int2);                               // per-warp hit buffers
+// Batches of small structures (the 255-atom replicas) launch without the cell list's 31 KB: four CTAs per SM instead of two.
+bool neighbor_use_cl(int n_struct, int n_nodes) { return (int64_t)n_nodes > (int64_t)n_struct * (CL_MIN_ATOMS * 3 / 4); }
+size_t neighbor_smem(bool with_cl = true) {
+    size_t b = (size_t)MAX_SMEM_ATOMS * 3 * sizeof(float) + (size_t)MAX_SMEM_ATOMS * sizeof(int);   // positions, degrees
+    if (with_cl)
+        b += (size_t)(CL_MAX_BINS + 2) * sizeof(int) + (size_t)2 * MAX_SMEM_ATOMS * sizeof(unsigned short)   // cell list
+             + (size_t)(NB_THREADS / 32) * CL_MAX_HITS * sizeof(int2);                                    // per-warp hit buffers
+    return b;
 }
 
 }  // namespace
@@ -448,17 +453,19 @@ int launch_neighbor_count(rlvd_engine* e, cudaStream_t s, int n_struct, int n_no
     const float rc2 = rc * rc;  // fp32 product, as in the oracle
     Span sp(e, s, FAM_NEIGHBOR);
     const int n_splits = neighbor_splits(n_struct);
+    const int cl = neighbor_use_cl(n_struct, n_nodes) ? 1 : 0;
+    const size_t smem = neighbor_smem(cl != 0);
     if (n_splits == 1) {
-        neighbor_kernel<false><<<n_struct, NB_THREADS, neighbor_smem(), s>>>(
+        neighbor_kernel<false><<<n_struct, NB_THREADS, smem, s>>>(
             n_struct, node_ptr, pos, cell, inv, img, rc2, row_ptr, node_struct, e->struct_edges.as<int>(), nullptr,
-            nullptr, 0, 1, 0);
+            nullptr, 0, 1, 0, cl);
     } else {                           // few structures: spread each one's receivers over several CTAs, then scan
-        neighbor_kernel<false><<<dim3(n_struct, n_splits), NB_THREADS, neighbor_smem(), s>>>(
+        neighbor_kernel<false><<<dim3(n_struct, n_splits), NB_THREADS, smem, s>>>(
             n_struct, node_ptr, pos, cell, inv, img, rc2, row_ptr, node_struct, e->struct_edges.as<int>(), nullptr,
-            nullptr, 0, n_splits, 1);
-        neighbor_kernel<false><<<n_struct, NB_THREADS, neighbor_smem(), s>>>(
+            nullptr, 0, n_splits, 1, cl);
+        neighbor_kernel<false><<<n_struct, NB_THREADS, smem, s>>>(
             n_struct, node_ptr, pos, cell, inv, img, rc2, row_ptr, node_struct, e->struct_edges.as<int>(), nullptr,
-            nullptr, 0, 1, 2);
+            nullptr, 0, 1, 2, cl);
     }
     struct_scan_kernel<<<1, 1024, 0, s>>>(n_struct, e->struct_edges.as<int>(), e->struct_edge_ptr.as<int>(),
                                            n_edges);
@@ -485,9 +492,10 @@ int launch_neighbor_fill(rlvd_engine* e, cudaStream_t s, int n_struct, int n_nod
     const float rc2 = rc * rc;
     Span sp(e, s, FAM_NEIGHBOR);
     const int n_splits = neighbor_splits(n_struct);
-    neighbor_kernel<true><<<dim3(n_struct, n_splits), NB_THREADS, neighbor_smem(), s>>>(
+    const int cl = neighbor_use_cl(n_struct, n_nodes) ? 1 : 0;      // same decision as the count pass: identical degrees
+    neighbor_kernel<true><<<dim3(n_struct, n_splits), NB_THREADS, neighbor_smem(cl != 0), s>>>(
         n_struct, node_ptr, pos, cell, inv, img, rc2, const_cast<int*>(row_ptr), nullptr, nullptr, col, shift, (long long)cap,
-        n_splits, 0);
+        n_splits, 0, cl);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;

@@ -874,6 +874,7 @@ int train_forward_backward(rlvd_engine* e, cudaStream_t s, int n_struct, int M, 
                            float* d_pred, float* d_q_out) {
     (void)E;
     RLVD_CHECK(n_struct == 2 * G && M % 2 == 0, "train: the batch must hold G reactant structures followed by their G products");
+    RLVD_CHECK(e->n_scale_species == 3, "train: the flat parameter layout is the bundled 3-species checkpoint's (got %d species)", e->n_scale_species);
     const int Mr = M / 2;
     const size_t MF = (size_t)M * F;
     // ---- workspace
