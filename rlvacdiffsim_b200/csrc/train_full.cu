@@ -39,7 +39,7 @@ int launch_edge_simt(rlvd_engine* e, cudaStream_t s, const float* filt_T_layer, 
 namespace {
 
 // ------------------------------------------------------------------------------------------------ flat parameter layout
-constexpr int64_t P_SC = 0, P_SH = 3, P_CUT = 6, P_FREQ = 7, P_EMB = 27, P_FW = 12827, P_FB = 35867, P_INTER = 37019,
+constexpr int64_t P_SC = 0, P_SH = 3, P_FREQ = 7, P_EMB = 27, P_FW = 12827, P_FB = 35867, P_INTER = 37019,
                   INTER_STRIDE = 66048, P_MIX = 235163, MIX_STRIDE = 115200, P_EN = 580763, P_RR = 589084, P_RO = 609724,
                   P_QE = 611934, P_QO = 612750, NPARAM = 614447;
 // offsets inside one interaction / mixing block and the heads
@@ -142,7 +142,8 @@ constexpr int GT = 64, GK = 16;
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                     const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
-                                                    const float* __restrict__ bias, int accumulate, int kchunk, int64_t zstride) {
+                                                    const float* __restrict__ bias, int accumulate, int kchunk, int64_t zstride,
+                                                    float* __restrict__ rowsum /* [gridDim.z][M] or null: sum_k A(m,k) per slice */) {
     __shared__ float As[GK][GT + 1];
     __shared__ float Bs[GK][GT + 1];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -154,20 +155,37 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = kbeg; k0 < kend; k0 += GK) {
+    float rs = 0.f;                                    // thread tid < 64 of the n-tile 0 CTAs: row sum of A(m0 + tid, :)
+    const bool do_rs = rowsum != nullptr && blockIdx.y == 0 && tid < GT;
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {                          // global -> registers (the next tile's loads fly during this tile's FMAs)
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const int f = tid + 256 * r;            // 1024 elements of each 16 x 64 tile
+            const int f = tid + 256 * r;               // 1024 elements of each 16 x 64 tile
             int kk, mm;
             if (TA) { mm = f & 63; kk = f >> 6; } else { kk = f & 15; mm = f >> 4; }
             const int m = m0 + mm, k = k0 + kk;
-            As[kk][mm] = (m < M && k < kend) ? __ldg(TA ? A + (int64_t)k * lda + m : A + (int64_t)m * lda + k) : 0.f;
+            ra[r] = (m < M && k < kend) ? __ldg(TA ? A + (int64_t)k * lda + m : A + (int64_t)m * lda + k) : 0.f;
             int kb, nn;
             if (TB) { kb = f & 15; nn = f >> 4; } else { nn = f & 63; kb = f >> 6; }
             const int n = n0 + nn, k2 = k0 + kb;
-            Bs[kb][nn] = (n < N && k2 < kend) ? __ldg(TB ? B + (int64_t)n * ldb + k2 : B + (int64_t)k2 * ldb + n) : 0.f;
+            rb[r] = (n < N && k2 < kend) ? __ldg(TB ? B + (int64_t)n * ldb + k2 : B + (int64_t)k2 * ldb + n) : 0.f;
+        }
+    };
+    if (kbeg < kend) fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += GK) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int f = tid + 256 * r;
+            if (TA) As[f >> 6][f & 63] = ra[r]; else As[f & 15][f >> 4] = ra[r];
+            if (TB) Bs[f & 15][f >> 4] = rb[r]; else Bs[f >> 6][f & 63] = rb[r];
         }
         __syncthreads();
+        if (k0 + GK < kend) fetch(k0 + GK);
+        if (do_rs) {
+#pragma unroll
+            for (int kk = 0; kk < GK; ++kk) rs += As[kk][tid];
+        }
 #pragma unroll
         for (int kk = 0; kk < GK; ++kk) {
             float av[4], bv[4];
@@ -182,6 +200,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
         }
         __syncthreads();
     }
+    if (do_rs && m0 + tid < M) rowsum[(int64_t)blockIdx.z * M + m0 + tid] = rs;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + ty * 4 + i;
@@ -205,25 +224,6 @@ __global__ void reduce_partials_kernel(int64_t n, int S, const float* __restrict
     float v = 0.f;
     for (int z = 0; z < S; ++z) v += part[(int64_t)z * n + i];
     dst[i] = accumulate ? dst[i] + v : v;
-}
-
-// out[c] (+)= sum_r X[r*ld + c]: block = 32 columns x 8 row lanes, fixed-order combine
-__global__ void __launch_bounds__(256) colsum_kernel(int rows, int cols, const float* __restrict__ X, int ld, float* __restrict__ out,
-                                                     int accumulate) {
-    __shared__ float part[8][33];
-    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cx;
-    float v = 0.f;
-    if (c < cols)
-        for (int r = ry; r < rows; r += 8) v += X[(int64_t)r * ld + c];
-    part[ry][cx] = v;
-    __syncthreads();
-    if (ry == 0 && c < cols) {
-        float t = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) t += part[k][cx];
-        out[c] = accumulate ? out[c] + t : t;
-    }
 }
 
 __global__ void act_fwd_kernel(int64_t n, const float* __restrict__ pre, float* __restrict__ out, int code) {
@@ -251,16 +251,26 @@ __global__ void embed_train_kernel(int M, const int* __restrict__ Z, const float
     z = z < 0 ? 0 : (z > 99 ? 99 : z);
     q[i] = emb[z * F + (i % F)];
 }
-// gemb[z][c] = sum_{i : Z_i = z} gq[i][c], nodes ascending.  grid = 100, block = F
-__global__ void embed_bwd_kernel(int M, const int* __restrict__ Z, const float* __restrict__ gq, float* __restrict__ gemb) {
-    const int z = blockIdx.x, c = threadIdx.x;
+// gemb[z][c] = sum_{i : Z_i = z} gq[i][c].  grid = 100 (one CTA per embedding row), block = (F channels, 8 node lanes): lane r
+// sums the nodes i = r mod 8 in ascending order, the eight partials are combined in lane order — a fixed tree.  Rows of atomic
+// numbers absent from the batch (97 of 100 for CrCoNi) leave after one pass over Z without touching gq.
+__global__ void __launch_bounds__(1024) embed_bwd_kernel(int M, const int* __restrict__ Z, const float* __restrict__ gq, float* __restrict__ gemb) {
+    __shared__ float part[8][F];
+    const int z = blockIdx.x, c = threadIdx.x, r = threadIdx.y;
     float v = 0.f;
-    for (int i = 0; i < M; ++i) {
+    for (int i = r; i < M; i += 8) {
         int zi = Z[i];
         zi = zi < 0 ? 0 : (zi > 99 ? 99 : zi);
         if (zi == z) v += gq[(int64_t)i * F + c];
     }
-    gemb[z * F + c] = v;
+    part[r][c] = v;
+    __syncthreads();
+    if (r == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += part[k][c];
+        gemb[z * F + c] = t;
+    }
 }
 // filter_net.weight [L*3F][20], bias [L*3F]  ->  filt_T [L][21][3F] (the table edge.cu's kernel reads)
 __global__ void build_filt_kernel(const float* __restrict__ fw, const float* __restrict__ fb, float* __restrict__ filt_T) {
@@ -838,18 +848,24 @@ void gemm(Ctx& c, bool TA, bool TB, int M, int N, int K, const float* A, int lda
           const float* bias, bool acc) {
     if (M <= 0 || N <= 0) return;
     dim3 grid((M + GT - 1) / GT, (N + GT - 1) / GT, 1);
-    if (TA && TB) sgemm_kernel<true, true><<<grid, 256, 0, c.s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, K, 0);
-    else if (TA) sgemm_kernel<true, false><<<grid, 256, 0, c.s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, K, 0);
-    else if (TB) sgemm_kernel<false, true><<<grid, 256, 0, c.s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, K, 0);
-    else sgemm_kernel<false, false><<<grid, 256, 0, c.s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, K, 0);
+    if (TA && TB) sgemm_kernel<true, true><<<grid, 256, 0, c.s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, K, 0, nullptr);
+    else if (TA) sgemm_kernel<true, false><<<grid, 256, 0, c.s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, K, 0, nullptr);
+    else if (TB) sgemm_kernel<false, true><<<grid, 256, 0, c.s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, K, 0, nullptr);
+    else sgemm_kernel<false, false><<<grid, 256, 0, c.s>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, acc, K, 0, nullptr);
     ++c.launches;
 }
-// weight gradient: dst[N][K] (ld = ldd) = Gm^T A with Gm [rows][N], A [rows][K]; split over rows, ordered partial sums
-void wgrad(Ctx& c, int rows, int N, int K, const float* Gm, int ldg, const float* A, int lda, float* dst, int ldd, float* part) {
-    const int S = std::max(1, std::min(64, (rows + 511) / 512));
+// weight gradient: dst[N][K] (ld = ldd) = Gm^T A with Gm [rows][N], A [rows][K]; the rows are split into slices of <= 128 whose
+// partial products are summed in slice order (fixed tree).  bias_dst[N] (optional) = column sums of Gm, taken from the same
+// shared-memory tiles (the bias gradient of the layer) and reduced the same way.
+constexpr int WG_MAX_SPLIT = 128;
+void wgrad(Ctx& c, int rows, int N, int K, const float* Gm, int ldg, const float* A, int lda, float* dst, int ldd, float* part,
+           float* bias_dst = nullptr) {
+    const int S = std::max(1, std::min(WG_MAX_SPLIT, (rows + 127) / 128));
     const int kchunk = ((rows + S - 1) / S + GK - 1) / GK * GK;
     dim3 grid((N + GT - 1) / GT, (K + GT - 1) / GT, S);
-    sgemm_kernel<true, false><<<grid, 256, 0, c.s>>>(N, K, rows, Gm, ldg, A, lda, part, K, nullptr, 0, kchunk, (int64_t)N * K);
+    float* bpart = part + (int64_t)(WG_MAX_SPLIT + 1) * 3 * F * F;           // [S][N] column-sum partials
+    sgemm_kernel<true, false><<<grid, 256, 0, c.s>>>(N, K, rows, Gm, ldg, A, lda, part, K, nullptr, 0, kchunk, (int64_t)N * K,
+                                                     bias_dst != nullptr ? bpart : nullptr);
     if (ldd == K) {
         reduce_partials_kernel<<<nblk((int64_t)N * K), 256, 0, c.s>>>((int64_t)N * K, S, part, dst, 0);
     } else {      // a column block of a wider weight (intra-atomic layer 0: [F][2F])
@@ -858,10 +874,10 @@ void wgrad(Ctx& c, int rows, int N, int K, const float* Gm, int ldg, const float
         cudaMemcpy2DAsync(dst, (size_t)ldd * 4, tmp, (size_t)K * 4, (size_t)K * 4, N, cudaMemcpyDeviceToDevice, c.s);
     }
     c.launches += 2;
-}
-void colsum(Ctx& c, int rows, int cols, const float* X, int ld, float* out) {
-    colsum_kernel<<<nblk(cols, 32), 256, 0, c.s>>>(rows, cols, X, ld, out, 0);
-    ++c.launches;
+    if (bias_dst != nullptr) {
+        reduce_partials_kernel<<<nblk(N), 256, 0, c.s>>>(N, S, bpart, bias_dst, 0);
+        ++c.launches;
+    }
 }
 
 }  // namespace
@@ -887,10 +903,10 @@ int train_forward_backward(rlvd_engine* e, cudaStream_t s, int n_struct, int M, 
     need += rnd((size_t)G * GS_PER) + rnd((size_t)G * 32) + rnd(G);              // graph heads
     need += rnd(MF) + 2 * rnd(3 * MF) + rnd(3 * MF) + rnd(MF) + rnd(2 * MF) + rnd(6 * MF) + rnd(3 * MF);   // backward buffers
     need += rnd((size_t)M * 64) + rnd(M) + rnd((size_t)Mr * 32) + 2 * rnd((size_t)Mr * F);
-    const int rpc = std::max(8, (M + 1183) / 1184);
+    const int rpc = std::max(4, (M + 3 * e->sm_count - 1) / (3 * e->sm_count));   // one full wave of 3 CTAs per SM (168 registers)
     const int n_cta = (M + rpc - 1) / rpc;
     need += rnd((size_t)n_cta * 3 * (NRBF + 1) * F);
-    need += rnd((size_t)65 * 3 * F * F);                                         // split-K partials + repack tile
+    need += rnd((size_t)(WG_MAX_SPLIT + 1) * 3 * F * F + (size_t)WG_MAX_SPLIT * 3 * F);   // split partials + repack tile + bias partials
     need += 4096;
     if (e->train_ws.ensure(need)) return 1;
     Bump ws{reinterpret_cast<char*>(e->train_ws.p), 0, e->train_ws.cap};
@@ -915,7 +931,7 @@ int train_forward_backward(rlvd_engine* e, cudaStream_t s, int n_struct, int M, 
     float* g_enh = ws.f((size_t)M * 64); float* g_eraw = ws.f(M); float* ghatom = ws.f((size_t)Mr * 32);
     float* g_rrh = ws.f((size_t)Mr * F); float* gd = ws.f((size_t)Mr * F);
     float* wpart = ws.f((size_t)n_cta * 3 * (NRBF + 1) * F);
-    float* part = ws.f((size_t)65 * 3 * F * F);
+    float* part = ws.f((size_t)(WG_MAX_SPLIT + 1) * 3 * F * F + (size_t)WG_MAX_SPLIT * 3 * F);
     RLVD_CHECK(ws.off <= ws.cap, "train: workspace accounting error");
     const int act_p = qp.painn_head_act;
 
@@ -978,17 +994,14 @@ int train_forward_backward(rlvd_engine* e, cudaStream_t s, int n_struct, int M, 
     wgrad(c, M, 1, 64, g_eraw, 1, en_h, 64, Gr + P_EN + EN_W3, 64, part);
     gemm(c, false, false, M, 64, 1, g_eraw, 1, PEN + EN_W3, 64, g_enh, 64, nullptr, false);
     act_bwd_kernel<<<nblk((int64_t)M * 64), 256, 0, s>>>((int64_t)M * 64, en_pre, g_enh, act_p);
-    wgrad(c, M, 64, F, g_enh, 64, qf, F, Gr + P_EN + EN_W0, F, part);
-    colsum(c, M, 64, g_enh, 64, Gr + P_EN + EN_B0);
+    wgrad(c, M, 64, F, g_enh, 64, qf, F, Gr + P_EN + EN_W0, F, part, Gr + P_EN + EN_B0);
     gemm(c, false, false, M, F, 64, g_enh, 64, PEN + EN_W0, F, gq, F, nullptr, false);
     // reaction_representation
     feat_unpool_kernel<<<nblk((int64_t)Mr * 32), 256, 0, s>>>(Mr, node_struct, gh, ghatom);
-    wgrad(c, Mr, 32, F, ghatom, 32, rr_h, F, Gr + P_RR + RR_W3, F, part);
-    colsum(c, Mr, 32, ghatom, 32, Gr + P_RR + RR_B3);
+    wgrad(c, Mr, 32, F, ghatom, 32, rr_h, F, Gr + P_RR + RR_W3, F, part, Gr + P_RR + RR_B3);
     gemm(c, false, false, Mr, F, 32, ghatom, 32, PRR + RR_W3, F, g_rrh, F, nullptr, false);
     act_bwd_kernel<<<nblk((int64_t)Mr * F), 256, 0, s>>>((int64_t)Mr * F, rr_pre, g_rrh, act_p);
-    wgrad(c, Mr, F, F, g_rrh, F, dnode, F, Gr + P_RR + RR_W0, F, part);
-    colsum(c, Mr, F, g_rrh, F, Gr + P_RR + RR_B0);
+    wgrad(c, Mr, F, F, g_rrh, F, dnode, F, Gr + P_RR + RR_W0, F, part, Gr + P_RR + RR_B0);
     gemm(c, false, false, Mr, F, F, g_rrh, F, PRR + RR_W0, F, gd, F, nullptr, false);
     diff_bwd_kernel<<<nblk((int64_t)Mr * F), 256, 0, s>>>((int64_t)Mr * F, gd, (int64_t)Mr * F, gq);
     c.launches += 5;
@@ -1003,13 +1016,11 @@ int train_forward_backward(rlvd_engine* e, cudaStream_t s, int n_struct, int M, 
         float* GM = Gr + P_MIX + l * MIX_STRIDE;
         // ---- mixing block
         mix_bwd1_kernel<<<nblk(MF), 256, 0, s>>>(M, gq, gmu, mix[l], vw[l], gctx);
-        wgrad(c, M, 3 * F, F, gctx, 3 * F, h2[l], F, GM + X_W3, F, part);
-        colsum(c, M, 3 * F, gctx, 3 * F, GM + X_B3);
+        wgrad(c, M, 3 * F, F, gctx, 3 * F, h2[l], F, GM + X_W3, F, part, GM + X_B3);
         gemm(c, false, false, M, F, 3 * F, gctx, 3 * F, PM + X_W3, F, ghid, F, nullptr, false);
         act_bwd_kernel<<<nblk(MF), 256, 0, s>>>(MF, h2pre[l], ghid, RLVD_ACT_SILU);
-        wgrad(c, M, F, F, ghid, F, qmid[l], F, GM + X_W0, 2 * F, part);
+        wgrad(c, M, F, F, ghid, F, qmid[l], F, GM + X_W0, 2 * F, part, GM + X_B0);
         wgrad(c, M, F, F, ghid, F, nrm[l], F, GM + X_W0 + F, 2 * F, part);
-        colsum(c, M, F, ghid, F, GM + X_B0);
         gemm(c, false, false, M, 2 * F, F, ghid, F, PM + X_W0, 2 * F, gcat, 2 * F, nullptr, false);
         mix_bwd2_kernel<<<nblk(MF), 256, 0, s>>>(M, gq, gmu, mix[l], nrm[l], ctx[l], gcat, gmix);
         wgrad(c, 3 * M, 2 * F, F, gmix, 2 * F, mumid[l], F, GM + X_WM, F, part);
@@ -1025,17 +1036,15 @@ int train_forward_backward(rlvd_engine* e, cudaStream_t s, int n_struct, int M, 
             edge_bwd_kernel<true><<<n_cta, EB_THREADS, 0, s>>>(M, rpc, ft, P + P_FREQ, row_ptr, col, shift, pos, cell, node_struct, xs[l],
                                                               MU[l], gq, gmu, gx, gmu_next, wpart, e->w.cutoff);
         edge_wgrad_reduce_kernel<<<nblk(3 * (NRBF + 1) * F), 256, 0, s>>>(n_cta, l, wpart, Gr + P_FW, Gr + P_FB);
-        wgrad(c, M, 3 * F, F, gx, 3 * F, h1[l], F, GI + I_W3, F, part);
-        colsum(c, M, 3 * F, gx, 3 * F, GI + I_B3);
+        wgrad(c, M, 3 * F, F, gx, 3 * F, h1[l], F, GI + I_W3, F, part, GI + I_B3);
         gemm(c, false, false, M, F, 3 * F, gx, 3 * F, PI + I_W3, F, ghid, F, nullptr, false);
         act_bwd_kernel<<<nblk(MF), 256, 0, s>>>(MF, h1pre[l], ghid, RLVD_ACT_SILU);
-        wgrad(c, M, F, F, ghid, F, Q[l], F, GI + I_W0, F, part);
-        colsum(c, M, F, ghid, F, GI + I_B0);
+        wgrad(c, M, F, F, ghid, F, Q[l], F, GI + I_W0, F, part, GI + I_B0);
         gemm(c, false, false, M, F, F, ghid, F, PI + I_W0, F, gq, F, nullptr, true);                      // gq_in = gq_mid + ghid W0
         c.launches += 3;
         float* t = gmu; gmu = gmu_next; gmu_next = t;
     }
-    embed_bwd_kernel<<<100, F, 0, s>>>(M, Z, gq, Gr + P_EMB);
+    embed_bwd_kernel<<<100, dim3(F, 8), 0, s>>>(M, Z, gq, Gr + P_EMB);
     ++c.launches;
     e->launches += c.launches;
     RLVD_CUDA(cudaGetLastError());

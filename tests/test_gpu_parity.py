@@ -1306,3 +1306,37 @@ def test_nccl_gather_and_gradient_allreduce(checkpoint_path):
         p.join(600)
         assert p.exitcode == 0
     assert ret[0] and ret[1]
+
+
+def test_captured_scoring_graph_and_pinned_inputs(model, engine):
+    """Engine.capture_score: the sync-free scoring call frozen into a CUDA graph replays bitwise-equal Q-values, also after
+    new positions / species of the same shape are copied in; Engine.pin_arrays feeds score_host without a staging copy."""
+    dev = engine.device
+    qp_d = {"alpha": 0.0, "beta": 1.0, "dqn": True, "temperature": 700.0}
+    qp = engine.q_params(qp_d, model.head_spec)
+    packs = []
+    for seed in (0, 1):
+        at = make_crconi_supercell(4, seed=seed, jitter=0.02)
+        packs.append(pack_replicas([at], [rb.get_action_space(at, 3.528)]))
+
+    def dev_batch(pk):
+        inv, img = cell_geometry(pk["cells"], engine.cutoff)
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+        return {"Z": t(pk["Z"], torch.int32), "pos": t(pk["pos"], torch.float32), "cell": t(pk["cells"], torch.float32),
+                "inv": t(inv, torch.float32), "img": t(img, torch.int32), "ptr": t(pk["node_ptr"], torch.int32),
+                "rs": t(pk["react_struct"], torch.int32), "ps": t(pk["prod_struct"], torch.int32)}
+    d0, d1 = dev_batch(packs[0]), dev_batch(packs[1])
+    T = torch.full((12,), 700.0, dtype=torch.float32, device=dev)
+    eager = lambda d: engine.score_device(d["Z"], d["pos"], d["cell"], d["inv"], d["img"], d["ptr"], d["rs"], d["ps"], qp,
+                                          temperature=T, max_struct_nodes=255)["rl_q"].cpu().numpy()
+    gs = engine.capture_score(d0["Z"], d0["pos"], d0["cell"], d0["inv"], d0["img"], d0["ptr"], d0["rs"], d0["ps"], qp, T, 255)
+    assert np.array_equal(gs()["rl_q"].cpu().numpy(), eager(d0))
+    assert np.array_equal(gs(pos=d1["pos"], Z=d1["Z"])["rl_q"].cpu().numpy(), eager(d1))       # new state, same shape
+    assert np.array_equal(gs(pos=d0["pos"], Z=d0["Z"])["rl_q"].cpu().numpy(), eager(d0))
+    assert engine.edge_overflow() == 0
+    pk = packs[0]
+    plain = engine.score_host(pk["Z"], pk["pos"], pk["cells"], pk["node_ptr"], pk["react_struct"], pk["prod_struct"], qp)
+    hp = engine.pin_arrays({k: np.ascontiguousarray(pk[k]) for k in ("Z", "pos", "cells", "node_ptr", "react_struct", "prod_struct")})
+    assert torch.from_numpy(hp["pos"]).is_pinned()
+    pinned = engine.score_host(hp["Z"], hp["pos"], hp["cells"], hp["node_ptr"], hp["react_struct"], hp["prod_struct"], qp)
+    assert np.array_equal(plain["rl_q"], pinned["rl_q"]) and plain["n_edges"] == pinned["n_edges"] > 0
