@@ -323,6 +323,34 @@ def bench_config5(model_cpu, dev, rank: int, world: int, steps: int, warmup: int
     if world > 1:
         ms_ar, _ = _time_calls(sync_grads, 50, dev)
     ms_adam, _ = _time_calls(lambda: model.optimizer_step(st, 0.0, 0.8), steps, dev)
+    # the same step (fixed minibatch shape) as ONE CUDA graph: what is left when the 160 launches cost nothing on the host
+    ms_graph = None
+    try:
+        prep = model.prepare_train_batch(batch, dev)
+        cap = prep["n_nodes"] * 64
+
+        def gstep():
+            o = model.train_forward_backward_prepared(prep, qp_train, st, target, mode="dqn", edge_capacity=cap)
+            sync_grads()
+            model.optimizer_step(st, 1e-5, 0.8)
+            return o
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                gstep()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if world == 1:                                  # NCCL collectives are left out of the capture
+            step_saved = st["step"]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                gout = gstep()
+            st["step"] = step_saved + 1
+            ms_graph, _ = _time_calls(lambda: g.replay(), steps, dev)
+            assert eng.edge_overflow() == 0 and bool(torch.isfinite(gout["loss"]).item())
+    except Exception as exc:
+        ms_graph = f"{type(exc).__name__}: {exc}"
 
     def e2e_step():                                                     # batch_to (H2D of the minibatch) + step + loss.item() (D2H)
         b = rb.batch_to(host_batch, dev)
@@ -345,7 +373,7 @@ def bench_config5(model_cpu, dev, rank: int, world: int, steps: int, warmup: int
                     "all-reduce of the flat 2.46 MB bucket per step when N > 1",
             "graphs_per_step_per_rank": 8, "ms_per_step": ms_step, "value": world * 8 / (ms_step * 1e-3), "unit": "reaction graphs/s (fwd+bwd+update)",
             "e2e_ms_per_step": ms_e2e, "e2e_value": world * 8 / (ms_e2e * 1e-3), "ms_forward_backward": ms_fb, "ms_allreduce": ms_ar,
-            "ms_clip_adam": ms_adam, "allreduce_bytes": 4 * n_param, "kernel_launches_per_step": int(launches), "loss": loss,
+            "ms_clip_adam": ms_adam, "ms_per_step_cuda_graph": ms_graph, "allreduce_bytes": 4 * n_param, "kernel_launches_per_step": int(launches), "loss": loss,
             "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in (host_batch["pos"], host_batch["pos_product"], host_batch["elems"], host_batch["cell"]))),
             "world": world}
 

@@ -262,29 +262,45 @@ class DQNv2(nn.Module, _EngineMixin):
         """``output = self(batch, q_params); loss = ...; loss.backward()`` of ``trainer.py:89-92,166-172`` with the
         parameters of ``state`` (not the module's): fills ``state["grads"]`` (unclipped) and returns loss / predictions.
         ``mode="dqn"``: ``mean((target0 - rl_q)**2)``; ``mode="bandit"``: ``mse(q0, target0) + mse(q1, target1)``."""
-        dev = state["device"]
+        prep = self.prepare_train_batch(batch, state["device"])
+        return self.train_forward_backward_prepared(prep, q_params, state, target0, target1, mode, dropout_uniform, return_q)
+
+    def prepare_train_batch(self, batch, device) -> dict:
+        """Host side of a training minibatch: the structure arrays in the layout ``rlvd_train_forward_backward`` expects
+        (reactants, then products), cell geometry, pointers — everything that needs a host value.  What remains
+        (:meth:`train_forward_backward_prepared`) only queues device work, so a fixed-shape minibatch can be captured in a
+        CUDA graph."""
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
         eng = self._engine_for(dev)
         G = batch.num_graphs
         pos = batch["pos"].to(dev, torch.float32)
         n_atoms = np.diff(batch["ptr"].cpu().numpy())
         cells64 = np.asarray(batch["cell64"], dtype=np.float64)
-        pos_all = torch.cat([pos, batch["pos_product"].to(dev, torch.float32)], dim=0).contiguous()
-        Z_all = torch.cat([batch["elems"], batch["elems"]]).to(dev, torch.int32).contiguous()
-        cell_all = torch.cat([batch["cell"], batch["cell"]], dim=0).to(dev, torch.float32).contiguous()
         counts = np.concatenate([n_atoms, n_atoms])
         node_ptr_host = np.zeros(len(counts) + 1, dtype=np.int32)
         np.cumsum(counts, out=node_ptr_host[1:])
         inv, img = cell_geometry(np.concatenate([cells64, cells64]), eng.cutoff)
-        node_ptr = torch.from_numpy(node_ptr_host).to(dev)
-        row_ptr, col, shift, node_struct = eng.radius_graph(pos_all, cell_all, torch.from_numpy(inv).to(dev),
-                                                            torch.from_numpy(img).to(dev), node_ptr)
+        return {"G": G, "pos": torch.cat([pos, batch["pos_product"].to(dev, torch.float32)], dim=0).contiguous(),
+                "Z": torch.cat([batch["elems"], batch["elems"]]).to(dev, torch.int32).contiguous(),
+                "cell": torch.cat([batch["cell"], batch["cell"]], dim=0).to(dev, torch.float32).contiguous(),
+                "ptr": torch.from_numpy(node_ptr_host).to(dev), "inv": torch.from_numpy(inv).to(dev),
+                "img": torch.from_numpy(img).to(dev), "n_nodes": int(node_ptr_host[-1])}
+
+    def train_forward_backward_prepared(self, prep: dict, q_params, state: dict, target0: torch.Tensor,
+                                        target1: Optional[torch.Tensor] = None, mode: str = "dqn",
+                                        dropout_uniform: Optional[torch.Tensor] = None, return_q: bool = False,
+                                        edge_capacity: Optional[int] = None) -> dict:
+        dev = state["device"]
+        eng = self._engine_for(dev)
+        row_ptr, col, shift, node_struct = eng.radius_graph(prep["pos"], prep["cell"], prep["inv"], prep["img"], prep["ptr"],
+                                                            edge_capacity=edge_capacity)
         qp = eng.q_params(q_params, self.head_spec)
         p_drop = float(self.hyper.get("dropout_rate", 0.0)) if dropout_uniform is not None else 0.0
         t0 = target0.to(dev, torch.float32).reshape(-1).contiguous()
         t1 = None if target1 is None else target1.to(dev, torch.float32).reshape(-1).contiguous()
-        return eng.train_forward_backward(Z_all, pos_all, cell_all, node_ptr, node_struct, row_ptr, col, shift, G, qp,
-                                          state["params"], state["grads"], t0, t1, mode=mode, dropout_uniform=dropout_uniform,
-                                          dropout_p=p_drop, return_q=return_q)
+        return eng.train_forward_backward(prep["Z"], prep["pos"], prep["cell"], prep["ptr"], node_struct, row_ptr, col, shift,
+                                          prep["G"], qp, state["params"], state["grads"], t0, t1, mode=mode,
+                                          dropout_uniform=dropout_uniform, dropout_p=p_drop, return_q=return_q)
 
     def optimizer_step(self, state: dict, lr: float, max_norm: float) -> torch.Tensor:
         """``clip_grad_norm_(parameters, max_norm); optimizer.step()`` (``trainer.py:93-96,173-176``) on ``state``."""
