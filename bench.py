@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in ln.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
 
     def stop(self):
         self._halt.set()

@@ -51,7 +51,10 @@ namespace {
 
 constexpr int SL = 32;                    // channels per slice
 constexpr int NSLICE = F / SL;            // 4
-constexpr int NPIPE = 6;                  // 4-warp pipelines per CTA
+#ifndef RLVD_NPIPE
+#define RLVD_NPIPE 6
+#endif
+constexpr int NPIPE = RLVD_NPIPE;         // 4-warp pipelines per CTA (6: 768 threads at <= 85 registers; experiments: -DRLVD_NPIPE=5)
 constexpr int TE = 32;                    // slots per tile = MMA N
 constexpr int GS = 8;                     // slots per receiver-aligned group
 constexpr int KH = 64;                    // fp16 k-extent of the split operands
@@ -70,6 +73,7 @@ constexpr int NROT = 4;
 // rotation of pipeline p: with role costs q 45 / R 75 / M 75 / feeder 0 issue slots per group this spreads the six
 // pipelines' warps over the four schedulers as 315 / 270 / 315 / 270
 __device__ __forceinline__ int pipe_rot(int p) { return p < 4 ? p : (p == 4 ? 0 : 2); }
+static_assert(NPIPE >= 1 && NPIPE <= 6, "pipe_rot and the TMEM budget cover at most 6 pipelines");
 constexpr int TM_COLS = 512;
 constexpr int A_SLICE_WORDS = NROT * 128 * 32;   // u32 per (layer, slice): [rotation][row][32]
 constexpr int NB_STAGE = 2;               // operand buffers per pipeline
