@@ -462,6 +462,8 @@ def main():
                     help="BASELINE config whose numbers form the JSON line (default 2 = the headline; its line also carries "
                          "short runs of 1, 3, 4, 5 as extra objects)")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the config 1/3/4/5 objects of the default line")
+    ap.add_argument("--streams", type=int, default=1, help="experiment: score the shard as this many independent sub-batches on "
+                                                            "concurrent CUDA streams (one engine each), sync-free calls")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -569,6 +571,46 @@ def main():
         res = step_device()
     step_host()
     n_edges = int(res["n_edges"])
+
+    if args.streams > 1:
+        # ---- experiment: the shard as `streams` independent sub-batches, each on its own stream and engine, queued without
+        # host synchronisation — lets the hardware run one sub-batch's (issue / LSU-bound) edge kernel next to another's
+        # (HBM-bound) node kernels
+        from rlvacdiffsim_b200.engine import Engine
+        ns = args.streams
+        engines = [eng] + [Engine(dev) for _ in range(ns - 1)]
+        for e2 in engines[1:]:
+            sd, hp_ = model._engine_state()
+            e2.load_state_dict(sd, hp_)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(ns)]
+        per = n_rep // ns
+        subs = []
+        for k in range(ns):
+            pk_k = pack_replicas(reps[k * per:(k + 1) * per], spaces[k * per:(k + 1) * per])
+            subs.append(_device_batch(pk_k, eng, dev))
+        caps = [int(sb["pos"].shape[0]) * 64 for sb in subs]
+        qps = [e2.q_params(Q_PARAMS, model.head_spec) for e2 in engines]
+
+        def step_streams():
+            outs = []
+            cur = torch.cuda.current_stream(dev)
+            for k in range(ns):
+                streams[k].wait_stream(cur)
+                with torch.cuda.stream(streams[k]):
+                    sb = subs[k]
+                    outs.append(engines[k].score_device(sb["Z"], sb["pos"], sb["cell"], sb["inv"], sb["img"], sb["ptr"], sb["rs"],
+                                                        sb["ps"], qps[k], max_struct_nodes=sb["max_nodes"], edge_capacity=caps[k]))
+            for k in range(ns):
+                cur.wait_stream(streams[k])
+            return outs
+        for _ in range(3):
+            outs = step_streams()
+        torch.cuda.synchronize(dev)
+        ms_s, outs = timed(step_streams, args.steps)
+        q_cat = torch.cat([o["rl_q"] for o in outs]).cpu().numpy()
+        same = bool(np.array_equal(q_cat, res["rl_q"].cpu().numpy()[: len(q_cat)]))
+        print(json.dumps({"experiment": "streams", "streams": ns, "ms_per_step": ms_s / args.steps, "rl_q_equal_to_single_stream": same,
+                          "overflow": [e2.edge_overflow() for e2 in engines]}))
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
