@@ -1,4 +1,9 @@
-"""CPU ORACLE — TEST INFRASTRUCTURE ONLY.  **PARITY UNPINNED.**
+"""CPU ORACLE — TEST INFRASTRUCTURE ONLY.  **PARITY UNPINNED** for the model arithmetic restated here.
+
+(The parts of the path the reference DOES ship as source — `rlsim/actions/action.py`, `rlsim/utils/sro.py`, the softmax +
+`np.random.choice` lines of `rlsim/drl/simulator.py:94-98` — are not restated in this file: they are pinned by fixtures minted
+from the reference's own code, `scripts/make_ref_fixtures.py` -> `tests/golden/ref_*.npz`.)
+
 
 This file restates, in eager PyTorch / numpy on the CPU, the arithmetic the reference reaches at
 ``rlsim/drl/simulator.py:56`` (``model(batch, q_params)["rl_q"]``).  It is the checker for the CUDA

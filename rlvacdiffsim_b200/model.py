@@ -302,6 +302,12 @@ class DQNv2(nn.Module, _EngineMixin):
                                           prep["G"], qp, state["params"], state["grads"], t0, t1, mode=mode,
                                           dropout_uniform=dropout_uniform, dropout_p=p_drop, return_q=return_q)
 
+    def train_graph(self, prep: dict, q_params, state: dict, mode: str, dropout: bool) -> "TrainGraph":
+        """The forward + backward of a minibatch SHAPE (graph count, node count) frozen into a CUDA graph — a replay
+        minibatch is ~160 small launches, i.e. launch-bound; clip + Adam stay outside (their bias corrections change every
+        step, and a multi-GPU run all-reduces the bucket in between)."""
+        return TrainGraph(self, prep, q_params, state, mode, dropout)
+
     def optimizer_step(self, state: dict, lr: float, max_norm: float) -> torch.Tensor:
         """``clip_grad_norm_(parameters, max_norm); optimizer.step()`` (``trainer.py:93-96,173-176``) on ``state``."""
         return self._engine_for(state["device"]).adam_step(state["params"], state["grads"], state, lr, max_norm, state["mask"])
@@ -376,6 +382,43 @@ class DQNv2(nn.Module, _EngineMixin):
         out["barrier"] = -out["q0"]
         out["freq"] = out["q1"]
         return out
+
+
+class TrainGraph:
+    """See :meth:`DQNv2.train_graph`.  Inputs live in static device buffers; ``__call__`` copies a prepared minibatch of the
+    same shape in, replays, and returns the static outputs (loss, predictions; ``state["grads"]`` holds the gradient)."""
+
+    def __init__(self, model: "DQNv2", prep: dict, q_params, state: dict, mode: str, dropout: bool):
+        dev = state["device"]
+        self.G, self.n_nodes, self.mode = prep["G"], prep["n_nodes"], mode
+        self.static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in prep.items()}
+        self.t0 = torch.zeros(self.G, dtype=torch.float32, device=dev)
+        self.t1 = torch.zeros(self.G, dtype=torch.float32, device=dev) if mode != "dqn" else None
+        self.u = torch.ones((self.G, 80), dtype=torch.float32, device=dev) if dropout else None
+        cap = self.n_nodes * 64
+        run = lambda: model.train_forward_backward_prepared(self.static, q_params, state, self.t0, self.t1, mode, self.u,
+                                                            edge_capacity=cap)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                     # warm-up: sizes the engine's training workspace before the capture
+            for _ in range(2):
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = run()
+
+    def __call__(self, prep: dict, target0, target1=None, dropout_uniform=None) -> dict:
+        for k in ("pos", "Z", "cell", "ptr", "inv", "img"):
+            self.static[k].copy_(prep[k], non_blocking=True)
+        self.t0.copy_(target0.reshape(-1), non_blocking=True)
+        if self.t1 is not None:
+            self.t1.copy_(target1.reshape(-1), non_blocking=True)
+        if self.u is not None:
+            self.u.copy_(dropout_uniform, non_blocking=True)
+        self.graph.replay()
+        return {k: v.clone() for k, v in self.out.items()}
 
 
 class TNet(nn.Module, _EngineMixin):

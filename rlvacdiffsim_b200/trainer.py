@@ -123,6 +123,8 @@ class Trainer:
         self.q_params = q_params
         self._adam: Dict[tuple, dict] = {}          # Adam state of the DQN heads, per device (optim.Adam, trainer.py:43)
         self._full: Dict[tuple, dict] = {}          # flat parameters / gradient bucket / Adam moments of the whole model
+        self.cuda_graphs = True                     # whole-model minibatches: replay forward + backward as one CUDA graph per shape
+        self._graphs: Dict[tuple, object] = {}
         self.heads_only_kernel = True               # train_all=False: use the fused one-launch head update (csrc/train.cu)
         self.allreduce_ms = 0.0                     # accumulated device time of the gradient all-reduce (bench.py --config 5)
         # trainer.py:123 calls policy_value_net.train(): the DQN heads' Dropout(p = hyper['dropout_rate'], 0.15 in the
@@ -166,6 +168,24 @@ class Trainer:
         b.record()
         self._ar_events = getattr(self, "_ar_events", []) + [(a, b)]
 
+    def _forward_backward(self, batch, st, dev, mode, u):
+        """One minibatch's loss + gradient bucket: eagerly (~160 launches) or, with ``cuda_graphs``, as the replay of a CUDA
+        graph captured for this minibatch shape and these q_params (same kernels, same order: bitwise the same numbers)."""
+        net = self.policy_value_net
+        t0 = batch["rl_q"] if mode == "dqn" else batch["q0"]
+        t1 = None if mode == "dqn" else batch["q1"]
+        if not self.cuda_graphs:
+            return net.train_forward_backward(batch, self.q_params, st, t0.reshape(-1), None if t1 is None else t1.reshape(-1),
+                                              mode=mode, dropout_uniform=u)
+        prep = net.prepare_train_batch(batch, dev)
+        qkey = tuple(sorted((k, float(v)) for k, v in self.q_params.items() if isinstance(v, (int, float, bool))))
+        key = (dev.index, mode, prep["G"], prep["n_nodes"], u is not None, qkey, id(st))
+        g = self._graphs.get(key)
+        if g is None:
+            g = net.train_graph(prep, self.q_params, st, mode, u is not None)
+            self._graphs[key] = g
+        return g(prep, t0.to(dev, torch.float32), None if t1 is None else t1.to(dev, torch.float32), u)
+
     def _run_minibatches(self, q_dataloader, num_epoch, dev, mode, max_norm) -> float:
         st = self._full_state(dev)
         losses = AverageMeter()
@@ -175,17 +195,15 @@ class Trainer:
                 batch = batch_to(batch, dev)
                 G = batch.num_graphs
                 u = torch.from_numpy(np.random.random_sample((G, 80)).astype(np.float32)).to(dev) if self.dropout else None
-                if mode == "dqn":
-                    res = self.policy_value_net.train_forward_backward(batch, self.q_params, st, batch["rl_q"].reshape(-1),
-                                                                       mode="dqn", dropout_uniform=u)
-                else:
-                    res = self.policy_value_net.train_forward_backward(batch, self.q_params, st, batch["q0"].reshape(-1),
-                                                                       batch["q1"].reshape(-1), mode="bandit", dropout_uniform=u)
+                res = self._forward_backward(batch, st, dev, mode, u)
                 self._sync_gradients(st)
                 self.policy_value_net.optimizer_step(st, self.lr, max_norm)
                 pending.append(res["loss"])
         for l in pending:                                   # one host sync at the end instead of loss.item() per batch
             losses.update(float(l.item()))
+        if self.cuda_graphs and self.policy_value_net._engine_for(dev).edge_overflow():
+            raise RuntimeError("Trainer: a minibatch held more than 64 neighbours per atom, beyond the captured graphs' edge "
+                               "buffer; rerun with trainer.cuda_graphs = False")
         for a, b in getattr(self, "_ar_events", []):
             self.allreduce_ms += a.elapsed_time(b)
         self._ar_events = []

@@ -944,8 +944,8 @@ def test_select_apply_equals_reference_selection(engine):
 
 def _train_batch(seeds=(70, 71), n_rep=3, picks=(0, 5)):
     graphs, arrays = [], []
-    for s in seeds:
-        at = make_crconi_supercell(n_rep, seed=s, jitter=0.03)
+    for k, s in enumerate(seeds):
+        at = make_crconi_supercell(n_rep[k] if isinstance(n_rep, (tuple, list)) else n_rep, seed=s, jitter=0.03)
         acts = rb.get_action_space(at, 3.528)
         chosen = [acts[i] for i in picks]
         graphs += convert_to_graph_list(at, chosen)
@@ -985,7 +985,7 @@ def test_full_backward_matches_autograd(checkpoint_path, mode, qp):
     o, out, loss = _oracle_grads(checkpoint_path, arrays, qp, (t0, t1), mode)
     st = model.new_train_state("cuda")
     res = model.train_forward_backward(batch, qp, st, t0.float(), t1.float() if mode == "bandit" else None, mode=mode)
-    np.testing.assert_allclose(float(res["loss"]), float(loss), rtol=2e-5)
+    np.testing.assert_allclose(float(res["loss"]), float(loss.detach()), rtol=2e-5)
     for k in ("rl_q", "q0", "q1"):
         ref = out[k].detach().numpy()
         assert np.abs(res[k].cpu().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), k
@@ -1010,6 +1010,26 @@ def test_full_backward_matches_autograd(checkpoint_path, mode, qp):
     print("worst gradient error / max|grad| per tensor:", max(worst.values()), max(worst, key=worst.get))
     assert not bad, bad
     assert n_checked > 600000 or mode == "bandit"
+
+
+def test_full_backward_ragged_minibatch(checkpoint_path):
+    """A replay minibatch mixing structure sizes (107- and 255-atom replicas, like memories of different POSCARs): same bars."""
+    model = rb.registry.get_model_class("dqn_v2").load(checkpoint_path)
+    qp = {"alpha": 0.3, "beta": 0.7, "dqn": True, "temperature": 500.0}
+    batch, arrays = _train_batch(seeds=(80, 81, 82), n_rep=(3, 4, 3), picks=(1,))
+    G = batch.num_graphs
+    t0 = torch.from_numpy(np.random.RandomState(5).normal(0.0, 0.5, G))
+    o, out, loss = _oracle_grads(checkpoint_path, arrays, qp, (t0, None), "dqn")
+    st = model.new_train_state("cuda")
+    res = model.train_forward_backward(batch, qp, st, t0.float(), mode="dqn")
+    np.testing.assert_allclose(float(res["loss"]), float(loss.detach()), rtol=2e-5)
+    g = st["grads"].cpu().numpy().astype(np.float64)
+    gmax = max(float(v.grad.abs().max()) for v in o.w.values() if v.is_floating_point() and v.grad is not None)
+    for name, off, n, trainable in model._engine_for(torch.device("cuda", 0)).train_layout():
+        if not trainable or o.w[name].grad is None:
+            continue
+        ref = o.w[name].grad.numpy().reshape(-1)
+        assert np.abs(g[off:off + n] - ref).max() <= 2e-4 * max(np.abs(ref).max(), 1e-4 * gmax), name
 
 
 def test_adam_step_matches_torch(checkpoint_path):
@@ -1060,12 +1080,13 @@ def test_trainer_full_model_updates(checkpoint_path):
             mems.append(mem)
         return mems
 
-    def run(mode):
+    def run(mode, graphs=True):
         model = rb.registry.get_model_class("dqn_v2").load(checkpoint_path)
         qp = ({"alpha": 0.0, "beta": 1.0, "dqn": True, "temperature": 700.0} if mode == "dqn" else
               {"alpha": 1.0, "beta": 0.0, "dqn": False, "temperature": 900.0})
         tr = Trainer(model, qp, lr=1e-5, train_all=True)
         tr.dropout = False
+        tr.cuda_graphs = graphs
         np.random.seed(4)
         if mode == "dqn":
             l1 = tr.dqn_update(episodes(), gamma=0.9, episode_size=2, num_epoch=2, batch_size=4, device="cuda")
@@ -1077,7 +1098,9 @@ def test_trainer_full_model_updates(checkpoint_path):
     for mode in ("dqn", "bandit"):
         l1, sd1, model, tr = run(mode)
         l2, sd2, _, _ = run(mode)
-        assert np.isfinite(l1) and l1 == l2
+        l3, sd3, _, _ = run(mode, graphs=False)               # CUDA-graph replay vs eager launches: the same kernels
+        assert np.isfinite(l1) and l1 == l2 == l3
+        assert all(torch.equal(sd1[k], sd3[k]) for k in sd1)
         for k in sd1:
             assert torch.equal(sd1[k], sd2[k]), k
             moved = not torch.equal(sd1[k], ref_sd[k].cpu())
