@@ -10,6 +10,7 @@ from .graph import (AtomsDataset, AtomsGraph, Batch, DataLoader, ReactionDataset
                     batch_to)
 from .registry import registry  # noqa: F401
 from .structures import Atoms, make_crconi_supercell, read_poscar, write_poscar  # noqa: F401
+from .timeest import estimate_time, estimate_time_device, read_xdatcar, timer_converter  # noqa: F401
 from .trainer import Memory, Trainer  # noqa: F401
 from .trajectory import TrajectoryWriter  # noqa: F401
 

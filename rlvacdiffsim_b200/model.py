@@ -450,6 +450,27 @@ class TNet(nn.Module, _EngineMixin):
     def load_representation(cls, reaction_model: PaiNN, **cfg) -> "TNet":
         return cls(reaction_model, **cfg)
 
+    # ---- checkpoint I/O in the reference's format, {"state_dict", "hyper_parameters"} (time/train.py:221-226, estimate_time.py:88)
+    def save(self, path: str) -> None:
+        hp = dict(self.hyper)
+        hp["reaction_model"] = _plain(self._reaction_model.hyper)
+        hp["tau"] = float(self.tau)
+        torch.save({"state_dict": self.state_dict(), "hyper_parameters": hp}, path)
+
+    @classmethod
+    def load(cls, path: str) -> "TNet":
+        ck = torch.load(path, weights_only=True, map_location="cpu")
+        hp = dict(ck["hyper_parameters"])
+        hp.pop("@name", None)
+        tau = hp.pop("tau", None)
+        rm_hp = dict(hp.pop("reaction_model"))
+        rm_hp.pop("@name", None)
+        model = cls(PaiNN(**rm_hp), **hp)
+        model.load_state_dict(ck["state_dict"])
+        if tau is not None:
+            model.tau = float(tau)
+        return model
+
     # ---- engine plumbing: the engine wants the dqn_v2 checkpoint layout; the Q heads are irrelevant here (zeros)
     def _engine_tensors(self):
         return list(self._reaction_model.parameters()) + list(self._reaction_model.buffers())

@@ -238,3 +238,39 @@ def test_train_layout_is_the_checkpoint_order(checkpoint_path):
         off += c
         assert tr == (not name.endswith(("cutoff_fn.cutoff", "radial_basis.freqs")))
     assert off == 614447
+
+
+def test_time_estimator_glue(tmp_path, checkpoint_path):
+    """rlsim/cli/scripts/estimate_time.py mirror (no GPU): timer_converter's formula and error, the XDATCAR reader against the
+    writer, and the t_net checkpoint round trip in the reference's {"state_dict", "hyper_parameters"} format."""
+    import torch
+    from rlvacdiffsim_b200.structures import _species_blocks, append_xdatcar, apply_action
+    from rlvacdiffsim_b200.timeest import read_xdatcar, timer_converter
+    t = torch.tensor([0.0, 0.25, 0.9])
+    np.testing.assert_allclose(timer_converter(t, 1.0).numpy(), -np.log(1 - t.numpy()), rtol=1e-6)
+    with pytest.raises(ValueError, match="exceeds the tau"):
+        timer_converter(torch.tensor([0.5, 1.5]), 1.0)                                   # estimate_time.py:26-29
+    s = make_crconi_supercell(2, seed=3)
+    frames = [s]
+    for k in range(4):
+        frames.append(apply_action(frames[-1], rb.get_action_space(frames[-1], 3.528)[k]))
+    path = str(tmp_path / "XDATCAR0")
+    for k, f in enumerate(frames):
+        append_xdatcar(path, f, k, append=k > 0)
+    back = read_xdatcar(path)
+    assert len(back) == 5 and len(read_xdatcar(path, skip=2)) == 3
+    for f, b in zip(frames, back):
+        order = _species_blocks(f)[2]                                                   # XDATCAR groups atoms by species, first seen first
+        assert np.array_equal(b.get_atomic_numbers(), np.asarray(f.get_atomic_numbers())[order])
+        d = b.get_positions() - (f.get_positions()[order] % np.diag(f.get_cell()))
+        d -= np.round(d / np.diag(f.get_cell())) * np.diag(f.get_cell())
+        assert np.abs(d).max() < 2e-7 * 7.1                                             # 8 decimals of fractional coordinates
+    dqn = rb.registry.get_model_class("dqn_v2").load(checkpoint_path)
+    torch.manual_seed(0)
+    tnet = rb.registry.get_model_class("t_net").load_representation(dqn.reaction_model, n_feat=64, pooling="mean", tau0=1.0)
+    tnet.tau = 2.5
+    tnet.save(str(tmp_path / "checkpoint10.pth.tar"))
+    again = rb.registry.get_model_class("t_net").load(str(tmp_path / "checkpoint10.pth.tar"))
+    assert again.tau == 2.5 and again.hyper["n_feat"] == 64
+    for (k1, v1), (k2, v2) in zip(tnet.state_dict().items(), again.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
