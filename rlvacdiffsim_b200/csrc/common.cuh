@@ -87,6 +87,8 @@ struct Weights {
     const void* mix_wF[NLAYER] = {};
     const void* intra_w0F[NLAYER] = {};
     const void* intra_w3F[NLAYER] = {};
+    const void* intra_w3F_ac[NLAYER] = {};      // rows [a | c] of layers.3 only (256 x 128): the q-only final mixing block
+    const float* intra_b3_ac[NLAYER] = {};
     const float* en_w0T = nullptr;              // [128][64]
     const float* en_b0 = nullptr;
     const float* en_w3 = nullptr;               // [64]
@@ -139,6 +141,8 @@ struct rlvd_engine {
     bool fuse_mix = false;          // nrm / vw reductions inside the mu_channel_mix GEMM epilogue (tc_linear.cu mixred mode);
                                     // measured 0.3 ms/step SLOWER than GEMM + reduction kernel (the epilogue is the GEMM's bottleneck)
     bool fuse_mlp = true;           // Linear -> SiLU -> Linear pairs as one tcgen05 launch (tc_linear.cu two-layer mode)
+    bool prune_final_mu = true;     // callers that take q only (d_mu == NULL): the last mixing block skips everything that
+                                    // only feeds mu's update (W store, the b block of the intra-atomic net, mu += b W)
     bool profiling = false;
     std::vector<rlvd::ProfSpan> spans;
     std::vector<cudaEvent_t> event_pool;
@@ -240,6 +244,7 @@ int launch_tc_edge(rlvd_engine* e, cudaStream_t s, int layer, int M, const int* 
                    const float* x, const float* mu_in, float* q, float* mu_out);
 void tc_edge_format_filters(const float* W, const float* b, std::vector<uint8_t>& out);
 int launch_mix_reduce(rlvd_engine* e, cudaStream_t s, int M, const float* mix, float* nrm, float* vw);
+int launch_mix_update_q(rlvd_engine* e, cudaStream_t s, int M, const float* ctx_ac, const float* vw, float* q);
 int launch_mix_update(rlvd_engine* e, cudaStream_t s, int M, const float* ctx, const float* W, int ldw,
                       const float* vw, float* q, float* mu);
 int launch_readout(rlvd_engine* e, cudaStream_t s, int n_react, const int* node_ptr, const int* rs,

@@ -308,7 +308,19 @@ int rlvd_finalize_weights(rlvd_engine* e) {
         if (need(pm + "intraatomic_context_net.layers.3.weight", 3 * F * F, &t) ||
             upload_T(e, *t, 3 * F, F, &w.intra_w3T[l]) || upload_fmt(e, *t, 3 * F, F, &w.intra_w3F[l]))
             return 1;
+        {   // rows [a | c] of the same layer (the q-only final mixing block never evaluates b)
+            std::vector<float> ac((size_t)2 * F * F);
+            std::copy(t->begin(), t->begin() + (size_t)F * F, ac.begin());
+            std::copy(t->begin() + (size_t)2 * F * F, t->end(), ac.begin() + (size_t)F * F);
+            if (upload_fmt(e, ac, 2 * F, F, &w.intra_w3F_ac[l])) return 1;
+        }
         if (need(pm + "intraatomic_context_net.layers.3.bias", 3 * F, &t) || upload_raw(e, *t, &w.intra_b3[l])) return 1;
+        {
+            std::vector<float> ac((size_t)2 * F);
+            std::copy(t->begin(), t->begin() + F, ac.begin());
+            std::copy(t->begin() + 2 * F, t->end(), ac.begin() + F);
+            if (upload_raw(e, ac, &w.intra_b3_ac[l])) return 1;
+        }
     }
     if (e->n_species > 0 && build_layer0(e, hs, w)) return 1;
     const std::string rm = "reaction_model.";
@@ -479,6 +491,19 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
         LinearArgs am;
         am.A = mu_cur; am.lda = F; am.M = 3 * M; am.K = F; am.N = 2 * F; am.Wt = w.mix_wT[l]; am.Wfmt = w.mix_wF[l]; am.bias = nullptr;
         am.act = 0;
+        if (l == NLAYER - 1 && d_mu == nullptr && e->prune_final_mu && e->use_tensor_cores && e->fuse_mlp) {
+            // Final mixing block of a q-only call: mu's update has no consumer, so W is not stored, the b block of the
+            // intra-atomic net is not evaluated and only q += a + c * <V, W> remains.  Same q as the full block.
+            am.mixred = 1; am.n_nodes = M; am.nrm = nrm; am.vw = vw; am.Y = nullptr; am.ldy = F; am.eps = e->eps;
+            if (launch_linear(e, s, am)) return 1;
+            LinearArgs b0;
+            b0.A = d_q; b0.lda = F; b0.A2 = nrm; b0.lda2 = F; b0.K1 = F; b0.M = M; b0.K = 2 * F; b0.N = F;
+            b0.Wt = w.intra_w0T[l]; b0.Wfmt = w.intra_w0F[l]; b0.bias = w.intra_b0[l]; b0.act = 1;
+            b0.W2fmt = w.intra_w3F_ac[l]; b0.bias2 = w.intra_b3_ac[l]; b0.N2 = 2 * F; b0.act2 = 0; b0.Y = ctx; b0.ldy = 2 * F;
+            if (launch_linear(e, s, b0)) return 1;
+            if (launch_mix_update_q(e, s, M, ctx, vw, d_q)) return 1;
+            continue;
+        }
         const bool fused_mix = e->use_tensor_cores && e->fuse_mix;
         if (fused_mix) {                                  // nrm, vw from the GEMM epilogue; `mix` holds W only, [3M, F]
             am.mixred = 1; am.n_nodes = M; am.nrm = nrm; am.vw = vw; am.Y = mix; am.ldy = F; am.eps = e->eps;
@@ -818,6 +843,10 @@ int rlvd_set_option(rlvd_engine* e, const char* name, int32_t value) {
     }
     if (strcmp(name, "fuse_mlp") == 0) {
         e->fuse_mlp = value != 0;
+        return 0;
+    }
+    if (strcmp(name, "prune_final_mu") == 0) {
+        e->prune_final_mu = value != 0;
         return 0;
     }
     RLVD_CHECK(false, "unknown option '%s'", name);

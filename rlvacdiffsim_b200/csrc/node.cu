@@ -203,6 +203,19 @@ __global__ void mix_update_kernel(int M, const float* __restrict__ ctx, const fl
     }
 }
 
+// ctx_ac[M][256] = [a | c];  q += a + c*vw        (final mixing block when nobody reads mu afterwards)
+__global__ void mix_update_q_kernel(int M, const float* __restrict__ ctx_ac, const float* __restrict__ vw, float* __restrict__ q) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * (F / 4)) return;
+    const int i = (int)(idx / (F / 4)), c4 = (int)(idx % (F / 4));
+    const float4 a = __ldg(reinterpret_cast<const float4*>(ctx_ac + (int64_t)i * 2 * F) + c4);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(ctx_ac + (int64_t)i * 2 * F + F) + c4);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(vw) + idx);
+    float4 qv = reinterpret_cast<float4*>(q)[idx];
+    qv.x += a.x + c.x * d.x; qv.y += a.y + c.y * d.y; qv.z += a.z + c.z * d.z; qv.w += a.w + c.w * d.w;
+    reinterpret_cast<float4*>(q)[idx] = qv;
+}
+
 }  // namespace
 
 int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a) {
@@ -258,6 +271,16 @@ int launch_axpy(rlvd_engine* e, cudaStream_t s, int64_t n, const float* x, float
     Span sp(e, s, FAM_NODE);
     axpy_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(n / 4, reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y),
                                                                 gate, gate_value);
+    sp.end(1);
+    RLVD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_mix_update_q(rlvd_engine* e, cudaStream_t s, int M, const float* ctx_ac, const float* vw, float* q) {
+    if (M <= 0) return 0;
+    Span sp(e, s, FAM_NODE);
+    const int64_t n = (int64_t)M * (F / 4);
+    mix_update_q_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(M, ctx_ac, vw, q);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;

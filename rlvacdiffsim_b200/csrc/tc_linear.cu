@@ -30,7 +30,8 @@
 // tile is laid out as 4 warps x (10 nodes x 3 components) + 2 idle rows, so the three components of a node sit in
 // adjacent TMEM lanes of ONE warp; the epilogue reads V and W of a tile from the two accumulator buffers, forms
 // nrm = sqrt(sum_c V_c^2 + eps) and vw = sum_c V_c W_c with two warp shuffles per value and stores nrm, vw and W.
-// V never reaches HBM and the separate reduction kernel (and its 8 x [M,128] of traffic) is gone.
+// V never reaches HBM and the separate reduction kernel (and its 8 x [M,128] of traffic) is gone.  With Y == nullptr W is
+// not stored either (the last mixing block of a call whose caller wants q only: mu's update has no consumer).
 // Weights are formatted once on the host (rlvd_finalize_weights).
 #include <cuda_fp16.h>
 
@@ -243,10 +244,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                                 pv[u >> 2] = make_float4(dt[u], dt[u + 1], dt[u + 2], dt[u + 3]);
                             }
                         }
+                        if (a.Y != nullptr) {
 #pragma unroll
-                        for (int u = 0; u < 16; u += 4) {
-                            const int lc = h * 8 + hf * 4 + (u >> 2);
-                            *reinterpret_cast<float4*>(Yst + er * 256 + ((lc ^ (er & 7)) << 4)) = make_float4(wv[u], wv[u + 1], wv[u + 2], wv[u + 3]);
+                            for (int u = 0; u < 16; u += 4) {
+                                const int lc = h * 8 + hf * 4 + (u >> 2);
+                                *reinterpret_cast<float4*>(Yst + er * 256 + ((lc ^ (er & 7)) << 4)) = make_float4(wv[u], wv[u + 1], wv[u + 2], wv[u + 3]);
+                            }
                         }
                     }
                     if (sgm == 1) {                          // all TMEM reads of both accumulators are done
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                         mbar_arrive(&S->acc_empty[bV]);
                         mbar_arrive(&S->acc_empty[bW]);
                     }
+                    if (a.Y == nullptr) continue;            // final mixing block of a q-only call: W has no consumer
                     epi_barrier();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {

@@ -440,6 +440,28 @@ def test_tensor_core_and_simt_paths_agree_end_to_end(model, engine):
     assert int(np.argmax(tc["rl_q"])) == int(np.argmax(simt["rl_q"]))
 
 
+def test_pruned_final_mixing_block_gives_the_same_q(model, engine):
+    """A q-only call (scoring: the heads read q, never mu) skips, in the LAST mixing block, everything that only feeds mu's
+    update.  The pruned block evaluates the same expressions in the same order for q, so the outputs must agree bit for bit."""
+    g = load_gold("syn255_s2_jitter")
+    try:
+        engine.set_option("prune_final_mu", 0)
+        full = _score_batch(model, g, "lss700")
+        engine.set_option("prune_final_mu", 1)
+        before = engine.launch_count()
+        pruned = _score_batch(model, g, "lss700")
+        n_pruned = engine.launch_count() - before
+        engine.set_option("prune_final_mu", 0)
+        before = engine.launch_count()
+        _score_batch(model, g, "lss700")
+        n_full = engine.launch_count() - before
+    finally:
+        engine.set_option("prune_final_mu", 1)
+    assert n_pruned == n_full - 1                         # GEMM + reduce + net + update -> GEMM(+reduce) + net + update
+    for k in ("rl_q", "q0", "q1", "delta_e", "E_R", "E_P"):
+        assert np.array_equal(full[k], pruned[k]), k
+
+
 # ----------------------------------------------------------------------------- edge stream kernel: ragged / degenerate batches
 
 def _ragged_batch():
