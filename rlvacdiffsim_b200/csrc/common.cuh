@@ -85,6 +85,7 @@ struct Weights {
     const void* inter_w0F[NLAYER] = {};
     const void* inter_w3F[NLAYER] = {};
     const void* mix_wF[NLAYER] = {};
+    const void* mix_wF_red[NLAYER] = {};        // rows regrouped for the mix-reduce epilogue (tc_format_mix_weight)
     const void* intra_w0F[NLAYER] = {};
     const void* intra_w3F[NLAYER] = {};
     const void* intra_w3F_ac[NLAYER] = {};      // rows [a | c] of layers.3 only (256 x 128): the q-only final mixing block
@@ -138,8 +139,8 @@ struct rlvd_engine {
     bool attr_stream = false, attr_neighbor = false, attr_tc_edge = false, attr_tc_linear = false, attr_train = false;   // dynamic-smem opt-ins done on this device
     bool use_tensor_cores = true;
     bool use_sliced_edge = true;    // structure-resident edge kernels when every structure has <= 256 atoms
-    bool fuse_mix = false;          // nrm / vw reductions inside the mu_channel_mix GEMM epilogue (tc_linear.cu mixred mode);
-                                    // measured 0.3 ms/step SLOWER than GEMM + reduction kernel (the epilogue is the GEMM's bottleneck)
+    bool fuse_mix = true;           // nrm / vw reductions inside the mu_channel_mix GEMM epilogue (tc_linear.cu mixred mode): same
+                                    // step time as GEMM + reduction kernel within run-to-run noise, 4.8 GB less DRAM traffic per step
     bool fuse_mlp = true;           // Linear -> SiLU -> Linear pairs as one tcgen05 launch (tc_linear.cu two-layer mode)
     bool prune_final_mu = true;     // callers that take q only (d_mu == NULL): the last mixing block skips everything that
                                     // only feeds mu's update (W store, the b block of the intra-atomic net, mu += b W)
@@ -202,11 +203,13 @@ struct LinearArgs {
     const int* gate = nullptr;
     int gate_value = 0;
     int* status = nullptr;        // engine status word: bit 0 = an operand left the fp16-split range (tc_linear.cu)
+    long long* dbg = nullptr;     // RLVD_TC_TIMELINE builds: (tag, clock64) stamps of block 0 (tc_linear.cu)
 };
 int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a);
 int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt);
 bool tc_linear_supported(const LinearArgs& a);
 void tc_format_weight(const float* W, int N, int K, std::vector<uint8_t>& out);
+void tc_format_mix_weight(const float* W, std::vector<uint8_t>& out);
 
 int launch_embed(rlvd_engine* e, cudaStream_t s, int M, const int* Z, float* q);
 struct EdgeArgs {

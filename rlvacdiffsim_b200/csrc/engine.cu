@@ -301,6 +301,13 @@ int rlvd_finalize_weights(rlvd_engine* e) {
         if (need(pm + "mu_channel_mix.weight", 2 * F * F, &t) || upload_T(e, *t, 2 * F, F, &w.mix_wT[l]) ||
             upload_fmt(e, *t, 2 * F, F, &w.mix_wF[l]))
             return 1;
+        {
+            std::vector<uint8_t> f;
+            tc_format_mix_weight(t->data(), f);
+            void* d = nullptr;
+            if (upload(e, f.data(), f.size(), &d)) return 1;
+            w.mix_wF_red[l] = d;
+        }
         if (need(pm + "intraatomic_context_net.layers.0.weight", F * 2 * F, &t) ||
             upload_T(e, *t, F, 2 * F, &w.intra_w0T[l]) || upload_fmt(e, *t, F, 2 * F, &w.intra_w0F[l]))
             return 1;
@@ -494,7 +501,7 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
         if (l == NLAYER - 1 && d_mu == nullptr && e->prune_final_mu && e->use_tensor_cores && e->fuse_mlp) {
             // Final mixing block of a q-only call: mu's update has no consumer, so W is not stored, the b block of the
             // intra-atomic net is not evaluated and only q += a + c * <V, W> remains.  Same q as the full block.
-            am.mixred = 1; am.n_nodes = M; am.nrm = nrm; am.vw = vw; am.Y = nullptr; am.ldy = F; am.eps = e->eps;
+            am.mixred = 1; am.n_nodes = M; am.nrm = nrm; am.vw = vw; am.Y = nullptr; am.ldy = F; am.eps = e->eps; am.Wfmt = w.mix_wF_red[l];
             if (launch_linear(e, s, am)) return 1;
             LinearArgs b0;
             b0.A = d_q; b0.lda = F; b0.A2 = nrm; b0.lda2 = F; b0.K1 = F; b0.M = M; b0.K = 2 * F; b0.N = F;
@@ -506,7 +513,7 @@ int rlvd_painn_representation(rlvd_engine* e, void* stream, int32_t n_struct, in
         }
         const bool fused_mix = e->use_tensor_cores && e->fuse_mix;
         if (fused_mix) {                                  // nrm, vw from the GEMM epilogue; `mix` holds W only, [3M, F]
-            am.mixred = 1; am.n_nodes = M; am.nrm = nrm; am.vw = vw; am.Y = mix; am.ldy = F; am.eps = e->eps;
+            am.mixred = 1; am.n_nodes = M; am.nrm = nrm; am.vw = vw; am.Y = mix; am.ldy = F; am.eps = e->eps; am.Wfmt = w.mix_wF_red[l];
             if (launch_linear(e, s, am)) return 1;
         } else {
             am.Y = mix; am.ldy = 2 * F;

@@ -28,8 +28,10 @@
 // staged or converted a second time.
 // Mix-reduce mode (LinearArgs::mixred): mu_channel_mix maps every (node, component) row of mu to [V | W].  A 128-row
 // tile is laid out as 4 warps x (10 nodes x 3 components) + 2 idle rows, so the three components of a node sit in
-// adjacent TMEM lanes of ONE warp; the epilogue reads V and W of a tile from the two accumulator buffers, forms
-// nrm = sqrt(sum_c V_c^2 + eps) and vw = sum_c V_c W_c with two warp shuffles per value and stores nrm, vw and W.
+// adjacent TMEM lanes of ONE warp.  The weight rows are permuted on the host (tc_format_mix_weight) so that N-block nb
+// holds V and W of the SAME 64 channels (columns 0-63 | 64-127 of one accumulator): the epilogue of a block forms
+// nrm = sqrt(sum_c V_c^2 + eps) and vw = sum_c V_c W_c with two warp shuffles per value and stores nrm, vw and W, while
+// the MMAs of the other block (or of the next tile) run — the same double-buffered schedule as the plain epilogue.
 // V never reaches HBM and the separate reduction kernel (and its 8 x [M,128] of traffic) is gone.  With Y == nullptr W is
 // not stored either (the last mixing block of a call whose caller wants q only: mu's update has no consumer).
 // Weights are formatted once on the host (rlvd_finalize_weights).
@@ -121,6 +123,12 @@ __device__ __forceinline__ void stage_A_async(const LinearArgs& a, int tile, int
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+#ifdef RLVD_TC_TIMELINE
+#define TCS(role, tag) if (a.dbg != nullptr && blockIdx.x == 0 && tl_n < 500) { a.dbg[(role) * 1024 + 2 * tl_n] = (tag); a.dbg[(role) * 1024 + 2 * tl_n + 1] = clock64(); ++tl_n; }
+#else
+#define TCS(role, tag)
+#endif
+
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearArgs a, const uint8_t* __restrict__ Wfmt,
                                                                   const uint8_t* __restrict__ W2fmt) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -137,6 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
     const int NB2 = two ? a.N2 / TC_N : 0;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int tl_n = 0; (void)tl_n;
     const int n_tiles = a.mixred ? (a.n_nodes + 39) / 40 : (a.M + TC_M - 1) / TC_M;
     const int NB = a.N / TC_N, NPH = a.K / 128;       // K-phases of 128 (the A buffers hold one phase)
 
@@ -174,9 +183,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
         if (blockIdx.x < n_tiles) stage_A_async(a, blockIdx.x, 0, ast, t);
         // One A phase: fp32 staging (cp.async, issued one phase ahead) -> fp16 hi/lo operand buffers, then prefetch the next.
         auto convert_phase = [&](int tl, int phase) {
+            if (tid == 0) { TCS(0, 1) }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (tid == 0) { TCS(0, 2) }
             mbar_wait(&S->a_free, (ph_it & 1) ^ 1);          // MMAs that read the previous A contents have retired
             epi_barrier();                                   // everyone's cp.async data is visible
+            if (tid == 0) { TCS(0, 3) }
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int kc = khalf * 8 + c;
@@ -189,9 +201,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores → UMMA
             mbar_arrive(&S->a_ready);
+            if (tid == 0) { TCS(0, 4) }
             epi_barrier();                                   // staging fully consumed → prefetch the next phase
             if (phase + 1 < NPH) stage_A_async(a, tl, phase + 1, ast, t);
             else if (tl + (int)gridDim.x < n_tiles) stage_A_async(a, tl + gridDim.x, 0, ast, t);
+            if (tid == 0) { TCS(0, 5) }
             ++ph_it;
         };
         // Schedule: the first A phase of tile t+1 is converted BEFORE the last N-block epilogue of tile t, so the MMAs of
@@ -199,87 +213,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
         // producer warps keep their program order; every barrier still sees its events in the same sequence).
         bool pre = false;                                    // phase 0 of the current tile is already in the operand buffers
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            if (tid == 0) { TCS(0, 0) }
             for (int phase = pre ? 1 : 0; phase < NPH; ++phase) convert_phase(tile, phase);
             pre = false;
-            if (a.mixred) {
-                // ---- V (block 0) and W (block 1) of this tile -> nrm, vw per node; only W is stored
-                const uint32_t bV = acc_it & 1, bW = bV ^ 1;
-                mbar_wait(&S->acc_full[bV], (acc_it >> 1) & 1);
-                mbar_wait(&S->acc_full[bW], ((acc_it + 1) >> 1) & 1);
-                tc_fence_after();
-                bool live_row;
-                const int64_t m_row = tile_row(a, tile, er, live_row);
-                const bool owner = live_row && (lane % 3) == 0;          // lane of component 0 writes the node's nrm / vw
-                const int64_t node = m_row / 3;
-#pragma unroll 1
-                for (int sgm = 0; sgm < 2; ++sgm) {
-#pragma unroll 1
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const int c0 = 64 * sgm + 32 * h + 16 * hf;
-                        const uint32_t tV = tmem + ((uint32_t)(q * 32) << 16) + bV * 256 + c0;
-                        const uint32_t tW = tmem + ((uint32_t)(q * 32) << 16) + bW * 256 + c0;
-                        uint32_t v0[16], v1[16], w0[16], w1[16];
-                        tmem_ld16(tV, v0);
-                        tmem_ld16(tV + 128, v1);
-                        tmem_ld16(tW, w0);
-                        tmem_ld16(tW + 128, w1);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        float nr[16], dt[16], wv[16];
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) {
-                            const float v = fmaf(__uint_as_float(v1[u]), 1.0f / 2048.0f, __uint_as_float(v0[u]));
-                            const float w = fmaf(__uint_as_float(w1[u]), 1.0f / 2048.0f, __uint_as_float(w0[u]));
-                            const float vy = __shfl_down_sync(0xffffffffu, v, 1), vz = __shfl_down_sync(0xffffffffu, v, 2);
-                            const float wy = __shfl_down_sync(0xffffffffu, w, 1), wz = __shfl_down_sync(0xffffffffu, w, 2);
-                            nr[u] = sqrtf(fmaf(vz, vz, fmaf(vy, vy, v * v)) + a.eps);
-                            dt[u] = fmaf(vz, wz, fmaf(vy, wy, v * w));
-                            wv[u] = w;
-                        }
-                        if (owner) {
-                            float4* pn = reinterpret_cast<float4*>(a.nrm + node * TC_N + c0);
-                            float4* pv = reinterpret_cast<float4*>(a.vw + node * TC_N + c0);
-#pragma unroll
-                            for (int u = 0; u < 16; u += 4) {
-                                pn[u >> 2] = make_float4(nr[u], nr[u + 1], nr[u + 2], nr[u + 3]);
-                                pv[u >> 2] = make_float4(dt[u], dt[u + 1], dt[u + 2], dt[u + 3]);
-                            }
-                        }
-                        if (a.Y != nullptr) {
-#pragma unroll
-                            for (int u = 0; u < 16; u += 4) {
-                                const int lc = h * 8 + hf * 4 + (u >> 2);
-                                *reinterpret_cast<float4*>(Yst + er * 256 + ((lc ^ (er & 7)) << 4)) = make_float4(wv[u], wv[u + 1], wv[u + 2], wv[u + 3]);
-                            }
-                        }
-                    }
-                    if (sgm == 1) {                          // all TMEM reads of both accumulators are done
-                        tc_fence_before();
-                        mbar_arrive(&S->acc_empty[bV]);
-                        mbar_arrive(&S->acc_empty[bW]);
-                    }
-                    if (a.Y == nullptr) continue;            // final mixing block of a q-only call: W has no consumer
-                    epi_barrier();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int id = i * 256 + t, row = id >> 4, lc = id & 15;
-                        bool live;
-                        const int64_t m = tile_row(a, tile, row, live);
-                        if (live) {
-                            const float4 v = *reinterpret_cast<const float4*>(Yst + row * 256 + ((lc ^ (row & 7)) << 4));
-                            *reinterpret_cast<float4*>(a.Y + m * a.ldy + 64 * sgm + lc * 4) = v;
-                        }
-                    }
-                    epi_barrier();
-                }
-                acc_it += 2;
-                continue;
-            }
             if (two) {
                 // ---- hidden layer: TMEM -> registers -> bias/SiLU -> fp16 hi/lo -> A operand buffers (no HBM, no staging)
                 const uint32_t buf = acc_it & 1;
+                if (tid == 0) { TCS(0, 10) }
                 mbar_wait(&S->acc_full[buf], (acc_it >> 1) & 1);
                 mbar_wait(&S->a_free, (ph_it & 1) ^ 1);           // the first layer's MMAs have finished reading A
                 tc_fence_after();
+                if (tid == 0) { TCS(0, 11) }
 #pragma unroll 1
                 for (int sgm = 0; sgm < 2; ++sgm) {
                     const int c0 = 64 * sgm + 32 * h;
@@ -311,6 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&S->a_ready);
+                if (tid == 0) { TCS(0, 12) }
                 ++acc_it;
                 ++ph_it;
             }
@@ -324,8 +269,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                     pre = true;
                 }
                 const uint32_t buf = acc_it & 1;
+                if (tid == 0) { TCS(0, 20 + nb) }
                 mbar_wait(&S->acc_full[buf], (acc_it >> 1) & 1);
                 tc_fence_after();
+                if (tid == 0) { TCS(0, 30 + nb) }
+                if (a.mixred) {
+                    // ---- this N-block holds V (columns 0-63) and W (64-127) of channels [64 nb, 64 nb + 64): nrm, vw per node
+                    bool live_row;
+                    const int64_t m_row = tile_row(a, tile, er, live_row);
+                    const bool owner = live_row && (lane % 3) == 0;      // lane of component 0 writes the node's nrm / vw
+                    const int64_t node = m_row / 3;
+#pragma unroll 1
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int c0 = 32 * h + 16 * hf;
+                        const uint32_t tV = tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + c0;
+                        uint32_t v0[16], v1[16], w0[16], w1[16];
+                        tmem_ld16(tV, v0);
+                        tmem_ld16(tV + 128, v1);
+                        tmem_ld16(tV + 64, w0);
+                        tmem_ld16(tV + 64 + 128, w1);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        float nr[16], dt[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            const float v = fmaf(__uint_as_float(v1[u]), 1.0f / 2048.0f, __uint_as_float(v0[u]));
+                            const float w = fmaf(__uint_as_float(w1[u]), 1.0f / 2048.0f, __uint_as_float(w0[u]));
+                            const float vy = __shfl_down_sync(0xffffffffu, v, 1), vz = __shfl_down_sync(0xffffffffu, v, 2);
+                            const float wy = __shfl_down_sync(0xffffffffu, w, 1), wz = __shfl_down_sync(0xffffffffu, w, 2);
+                            nr[u] = sqrtf(fmaf(vz, vz, fmaf(vy, vy, v * v)) + a.eps);
+                            dt[u] = fmaf(vz, wz, fmaf(vy, wy, v * w));
+                        }
+                        if (owner) {
+                            float4* pn = reinterpret_cast<float4*>(a.nrm + node * TC_N + 64 * nb + c0);
+                            float4* pv = reinterpret_cast<float4*>(a.vw + node * TC_N + 64 * nb + c0);
+#pragma unroll
+                            for (int u = 0; u < 16; u += 4) {
+                                pn[u >> 2] = make_float4(nr[u], nr[u + 1], nr[u + 2], nr[u + 3]);
+                                pv[u >> 2] = make_float4(dt[u], dt[u + 1], dt[u + 2], dt[u + 3]);
+                            }
+                        }
+                    }
+                    if (a.Y != nullptr) {
+                        // W (columns 64-127 of the block) straight from TMEM in the m16n8 fragment shape: the four threads of
+                        // a row write 32 contiguous bytes, whole sectors, no staging and no block barrier
+                        const int u = lane & 3, rq = lane >> 2;
+#pragma unroll 1
+                        for (int hl = 0; hl < 2; ++hl) {
+                            const uint32_t t1 = tmem + ((uint32_t)(q * 32 + 16 * hl) << 16) + buf * 256 + 64 + 32 * h;
+                            uint32_t d0[16], d1[16];
+                            tmem_ld_16x256b_x4(t1, d0);
+                            tmem_ld_16x256b_x4(t1 + 128, d1);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int rh = 0; rh < 2; ++rh) {
+                                bool live;
+                                const int64_t m = tile_row(a, tile, q * 32 + 16 * hl + 8 * rh + rq, live);
+                                float* yrow = a.Y + m * a.ldy + 64 * nb + 32 * h + 2 * u;
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    const float w0v = fmaf(__uint_as_float(d1[4 * g + 2 * rh]), 1.0f / 2048.0f, __uint_as_float(d0[4 * g + 2 * rh]));
+                                    const float w1v = fmaf(__uint_as_float(d1[4 * g + 2 * rh + 1]), 1.0f / 2048.0f, __uint_as_float(d0[4 * g + 2 * rh + 1]));
+                                    if (live) *reinterpret_cast<float2*>(yrow + 8 * g) = make_float2(w0v, w1v);
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();                       // all TMEM reads of this accumulator are done
+                    mbar_arrive(&S->acc_empty[buf]);
+                    continue;
+                }
                 // four quarter-steps (column segment sgm, 16-lane half hl); the TMEM loads of step i+1 are in flight while
                 // step i is combined and stored (a load + wait costs 250-650 cycles, as much as the stores it feeds)
                 const int u = lane & 3, rq = lane >> 2;
@@ -427,8 +439,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
             };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, acc_base += NB + NB2) {
                 for (int phase = 0; phase < NPH; ++phase, ++ph_it) {
+                    TCS(1, 100)
                     mbar_wait(&S->a_ready, ph_it & 1);
                     tc_fence_after();
+                    TCS(1, 101)
                     for (int nb = 0; nb < NB; ++nb) {
                         const uint32_t acc_it = acc_base + nb, buf = acc_it & 1;
                         if (phase == 0) {
@@ -436,21 +450,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                             tc_fence_after();
                         }
                         const uint32_t d0 = tmem + buf * 256, d1 = d0 + 128;
+                        TCS(1, 110 + nb)
                         kstages(d0, d1, phase * (128 / TC_KS), phase == 0);
                         if (phase == NPH - 1) umma_commit(&S->acc_full[buf]);  // publishes (D0, D1)
+                        TCS(1, 120 + nb)
                     }
                     umma_commit(&S->a_free);                                 // A buffers may be overwritten
                 }
                 if (two) {                                                   // second layer from the hidden tile in A
+                    TCS(1, 130)
                     mbar_wait(&S->a_ready, ph_it & 1);
                     tc_fence_after();
+                    TCS(1, 131)
                     for (int nb = 0; nb < NB2; ++nb) {
                         const uint32_t acc_it = acc_base + NB + nb, buf = acc_it & 1;
                         mbar_wait(&S->acc_empty[buf], ((acc_it >> 1) & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t d0 = tmem + buf * 256, d1 = d0 + 128;
+                        TCS(1, 140 + nb)
                         kstages(d0, d1, 0, true);
                         umma_commit(&S->acc_full[buf]);
+                        TCS(1, 150 + nb)
                     }
                     umma_commit(&S->a_free);
                     ++ph_it;
@@ -492,6 +512,18 @@ void tc_format_weight(const float* W, int N, int K, std::vector<uint8_t>& out) {
         }
 }
 
+// mu_channel_mix.weight [256][128] (rows 0-127 -> V, 128-255 -> W) with its rows regrouped for the mix-reduce epilogue:
+// block nb = [V rows 64 nb .. 64 nb + 63 | W rows 64 nb .. 64 nb + 63].
+void tc_format_mix_weight(const float* W, std::vector<uint8_t>& out) {
+    std::vector<float> P((size_t)2 * TC_N * 128);
+    for (int r = 0; r < 2 * TC_N; ++r) {
+        const int nb = r / TC_N, within = r % TC_N;
+        const int src = within < 64 ? 64 * nb + within : TC_N + 64 * nb + (within - 64);
+        for (int k = 0; k < 128; ++k) P[(size_t)r * 128 + k] = W[(size_t)src * 128 + k];
+    }
+    tc_format_weight(P.data(), 2 * TC_N, 128, out);
+}
+
 bool tc_linear_supported(const LinearArgs& a) {
     const bool k_ok = a.K == 128 || (a.K == 256 && a.N <= 2 * TC_N);   // K=256 keeps every N-block's accumulator live
     if (a.mixred && (a.K != 128 || a.N != 2 * TC_N || a.bias != nullptr || a.A2 != nullptr || a.W2fmt != nullptr ||
@@ -513,11 +545,37 @@ int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a_in, con
     }
     const int n_tiles = a.mixred ? (a.n_nodes + 39) / 40 : (a.M + TC_M - 1) / TC_M;
     const int grid = n_tiles < e->sm_count ? n_tiles : e->sm_count;
+#ifdef RLVD_TC_TIMELINE   // (tag, clock64) stamps of block 0: epilogue thread 0 and the MMA issuer (RLVD_EXTRA_NVCC_FLAGS=-DRLVD_TC_TIMELINE)
+    static long long* dbg_buf = nullptr;
+    static int dbg_calls[4] = {0, 0, 0, 0};
+    if (dbg_buf == nullptr) cudaMalloc(&dbg_buf, 2048 * 8);
+    const int kind = a.mixred ? 0 : (a.W2fmt != nullptr ? (a.K == 128 ? 1 : 2) : 3);
+    const bool dump = a.M > 100000 && ++dbg_calls[kind] == 12;
+    if (dump) { cudaMemsetAsync(dbg_buf, 0, 2048 * 8, s); a.dbg = dbg_buf; }
+#endif
     Span sp(e, s, FAM_NODE);
     tc_linear_kernel<<<grid, TC_THREADS, tc_smem_bytes(a.K), s>>>(a, reinterpret_cast<const uint8_t*>(Wfmt),
                                                                   reinterpret_cast<const uint8_t*>(a.W2fmt));
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
+#ifdef RLVD_TC_TIMELINE
+    if (dump) {
+        cudaStreamSynchronize(s);
+        static long long h[2048];
+        cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("tc_linear timeline kind %d (0 mixred, 1 two-layer K128, 2 two-layer K256, 3 plain) M %d K %d N %d N2 %d\n", kind, a.M, a.K, a.N, a.N2);
+        for (int role = 0; role < 2; ++role) {
+            const long long t0 = h[1];
+            long long prev = h[role * 1024 + 1];
+            for (int i = 0; i < 500 && h[role * 1024 + 2 * i + 1] != 0; ++i) {
+                const long long tag = h[role * 1024 + 2 * i], c = h[role * 1024 + 2 * i + 1];
+                if (c - t0 > 120000) break;
+                printf("  role %d tag %3lld t %7lld (+%5lld)\n", role, tag, c - t0, c - prev);
+                prev = c;
+            }
+        }
+    }
+#endif
     return 0;
 }
 
