@@ -125,6 +125,12 @@ struct rlvd_engine {
     rlvd::DevBuf status;                                       // int[4] device status word (rlvd_check_status)
     rlvd::DevBuf readout_scratch;                              // split-readout partial pools + arrival counters
     rlvd::DevBuf l0A;                                          // [M, 256] species-resolved radial sums of layer 0
+    rlvd::DevBuf hit_words;                                    // [M, 8] hit bits of the last count pass (neighbor.cu); the key
+    const void* hit_key_pos = nullptr;                         // below names the graph they belong to (consumed by its fill pass)
+    const void* hit_key_ptr = nullptr;
+    int hit_key_nodes = 0, hit_key_struct = 0;
+    float hit_key_rc2 = 0.f;
+    bool use_hit_words = true;
     rlvd::DevBuf train_ws;                                     // saved activations + backward scratch (train_full.cu)
     float eps = 1e-8f;                                         // hyper_parameters.reaction_model.epsilon (rlvd_set_hyper)
     int n_scale_species = 3;                                   // entries of species_energy_scale.{scales, shifts} in the checkpoint

@@ -209,7 +209,7 @@ void rlvd_engine_destroy(rlvd_engine* e) {
     cudaSetDevice(e->device);
     for (void* d : e->derived) cudaFree(d);
     for (DevBuf* b : {&e->x, &e->mu0, &e->mu1, &e->hid, &e->mix, &e->nrm, &e->vw, &e->ctx, &e->struct_edges,
-                      &e->struct_edge_ptr, &e->scratch, &e->tiles, &e->pipe_info, &e->tile_ctr, &e->stream_scratch, &e->l0A, &e->train_ws, &e->readout_scratch, &e->status, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
+                      &e->struct_edge_ptr, &e->scratch, &e->tiles, &e->pipe_info, &e->tile_ctr, &e->stream_scratch, &e->l0A, &e->hit_words, &e->train_ws, &e->readout_scratch, &e->status, &e->in_node_ptr, &e->in_Z, &e->in_pos, &e->in_cell,
                       &e->in_inv, &e->in_img, &e->in_rs, &e->in_ps, &e->in_temp, &e->in_qp, &e->g_row_ptr,
                       &e->g_node_struct, &e->g_col, &e->g_shift, &e->g_nedges, &e->g_q, &e->out_pack})
         b->release();
@@ -850,6 +850,11 @@ int rlvd_set_option(rlvd_engine* e, const char* name, int32_t value) {
     }
     if (strcmp(name, "fuse_mlp") == 0) {
         e->fuse_mlp = value != 0;
+        return 0;
+    }
+    if (strcmp(name, "hit_words") == 0) {
+        e->use_hit_words = value != 0;
+        e->hit_key_pos = nullptr;
         return 0;
     }
     if (strcmp(name, "prune_final_mu") == 0) {

@@ -26,6 +26,7 @@ namespace rlvd {
 namespace {
 
 constexpr int NB_THREADS = 256;
+constexpr int HIT_WORDS = 8;          // hit bits kept per receiver between the count and the fill pass (structures <= 256 atoms)
 constexpr int MAX_SMEM_ATOMS = 3072;  // 36 KB of positions in static-free dynamic smem
 
 struct CellC {
@@ -78,7 +79,7 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
 template <bool FILL>
 __device__ __forceinline__ int sweep_receiver(const CellC& C, const float* P, int n, int i, int lane, float rc2,
                                               int node0, int row_start, int* col, int8_t* shift,
-                                              long long cap) {
+                                              long long cap, unsigned* hit_words = nullptr) {
     const float xi = P[3 * i], yi = P[3 * i + 1], zi = P[3 * i + 2];
     int off = 0;
     if ((C.R[0] | C.R[1] | C.R[2]) == 0) {
@@ -96,6 +97,7 @@ __device__ __forceinline__ int sweep_receiver(const CellC& C, const float* P, in
                 hit = !self && image_d2(C, dx, dy, dz, b0, b1, b2) < rc2;
             }
             const unsigned mask = __ballot_sync(0xffffffffu, hit);
+            if (!FILL && hit_words != nullptr && lane == 0) hit_words[jb >> 5] = mask;   // the fill pass walks these bits
             if (FILL && hit) {
                 const int w = row_start + off + __popc(mask & lt);
                 if (w < cap) {
@@ -147,6 +149,46 @@ __device__ __forceinline__ int sweep_receiver(const CellC& C, const float* P, in
         off += total;
     }
     return off;
+}
+
+// Fill pass of the single-image sweep from the hit words the count pass left behind (n <= 256: 8 words per receiver).
+// Lane k takes the k-th set bit (ascending sender), recomputes that pair's image with the same arithmetic and writes slot
+// row_start + k: the same col / shift arrays as sweep_receiver<true>, for ~54 pair evaluations per receiver instead of n.
+__device__ __forceinline__ void fill_from_words(const CellC& C, const float* P, int n, int i, int lane, int node0, int row_start,
+                                                int* col, int8_t* shift, long long cap, const unsigned* hit_words) {
+    const int nwords = (n + 31) >> 5;
+    const unsigned mine = lane < nwords ? __ldg(hit_words + lane) : 0u;
+    unsigned w[8];
+    int pre[9];
+    pre[0] = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        w[t] = __shfl_sync(0xffffffffu, mine, t);
+        pre[t + 1] = pre[t] + __popc(w[t]);
+    }
+    const int deg = pre[8];
+    const float xi = P[3 * i], yi = P[3 * i + 1], zi = P[3 * i + 2];
+    for (int k = lane; k < deg; k += 32) {
+        int t = 0;
+#pragma unroll
+        for (int u = 1; u < 8; ++u) t += k >= pre[u] ? 1 : 0;
+        unsigned word = w[0];
+        int base = pre[0];
+#pragma unroll
+        for (int u = 1; u < 8; ++u)
+            if (t == u) { word = w[u]; base = pre[u]; }
+        const int j = 32 * t + (int)__fns(word, 0, k - base + 1);
+        const float dx = __fsub_rn(P[3 * j], xi), dy = __fsub_rn(P[3 * j + 1], yi), dz = __fsub_rn(P[3 * j + 2], zi);
+        float b0, b1, b2;
+        base_image(C, dx, dy, dz, b0, b1, b2);
+        const int o = row_start + k;
+        if (o < cap) {
+            col[o] = node0 + j;
+            shift[3 * (int64_t)o + 0] = (int8_t)(int)b0;
+            shift[3 * (int64_t)o + 1] = (int8_t)(int)b1;
+            shift[3 * (int64_t)o + 2] = (int8_t)(int)b2;
+        }
+    }
 }
 
 
@@ -294,7 +336,9 @@ __global__ void __launch_bounds__(NB_THREADS) neighbor_kernel(
     int* __restrict__ col, int8_t* __restrict__ shift, long long cap,
     int n_splits,                    // small batches: blockIdx.y takes every n_splits-th group of receivers
     int mode,                        // count: 0 = degrees + per-structure scan, 1 = degrees only, 2 = scan only
-    int cl_enabled) {                // the launch carries the cell list's shared memory (batches of large structures only)
+    int cl_enabled,                  // the launch carries the cell list's shared memory (batches of large structures only)
+    unsigned* __restrict__ hit_words) {   // [n_nodes][8] or null: single-image structures of <= 256 atoms leave their hit bits
+                                          // here in the count pass and fill from them (HIT_WORDS per receiver)
     extern __shared__ float smem_f[];
     __shared__ int warp_sums[NB_THREADS / 32 + 1];
     const int g = blockIdx.x;
@@ -349,11 +393,17 @@ __global__ void __launch_bounds__(NB_THREADS) neighbor_kernel(
     }
 
     const bool to_global = !staged || mode == 1;
+    const bool words = hit_words != nullptr && staged && n <= 32 * HIT_WORDS && CLs.nb[0] == 0 && (C.R[0] | C.R[1] | C.R[2]) == 0;
     for (int i = wid + nw * (int)blockIdx.y; i < n; i += nw * n_splits) {
         const int row_start = FILL ? row_ptr[node0 + i] : 0;
+        unsigned* hw = words ? hit_words + (size_t)(node0 + i) * HIT_WORDS : nullptr;
+        if (FILL && words) {
+            fill_from_words(C, P, n, i, lane, node0, row_start, col, shift, cap, hw);
+            continue;
+        }
         int d = -1;
         if (CLs.nb[0] > 0) d = sweep_receiver_cl<FILL>(C, CLs, P, i, lane, rc2, node0, row_start, col, shift, cap, hits);
-        if (d < 0) d = sweep_receiver<FILL>(C, P, n, i, lane, rc2, node0, row_start, col, shift, cap);
+        if (d < 0) d = sweep_receiver<FILL>(C, P, n, i, lane, rc2, node0, row_start, col, shift, cap, hw);
         if (!FILL && lane == 0) {
             if (to_global) row_ptr[node0 + i] = d; else deg[i] = d;
             node_struct[node0 + i] = g;
@@ -455,17 +505,24 @@ int launch_neighbor_count(rlvd_engine* e, cudaStream_t s, int n_struct, int n_no
     const int n_splits = neighbor_splits(n_struct);
     const int cl = neighbor_use_cl(n_struct, n_nodes) ? 1 : 0;
     const size_t smem = neighbor_smem(cl != 0);
+    // hit bits for the fill pass of THIS graph (same stream, same inputs): remembered by (pos, node_ptr, sizes)
+    unsigned* hw = nullptr;
+    e->hit_key_pos = nullptr;
+    if (e->use_hit_words && !e->hit_words.ensure((size_t)n_nodes * HIT_WORDS * sizeof(unsigned))) {
+        hw = e->hit_words.as<unsigned>();
+        e->hit_key_pos = pos; e->hit_key_ptr = node_ptr; e->hit_key_nodes = n_nodes; e->hit_key_struct = n_struct; e->hit_key_rc2 = rc2;
+    }
     if (n_splits == 1) {
         neighbor_kernel<false><<<n_struct, NB_THREADS, smem, s>>>(
             n_struct, node_ptr, pos, cell, inv, img, rc2, row_ptr, node_struct, e->struct_edges.as<int>(), nullptr,
-            nullptr, 0, 1, 0, cl);
+            nullptr, 0, 1, 0, cl, hw);
     } else {                           // few structures: spread each one's receivers over several CTAs, then scan
         neighbor_kernel<false><<<dim3(n_struct, n_splits), NB_THREADS, smem, s>>>(
             n_struct, node_ptr, pos, cell, inv, img, rc2, row_ptr, node_struct, e->struct_edges.as<int>(), nullptr,
-            nullptr, 0, n_splits, 1, cl);
+            nullptr, 0, n_splits, 1, cl, hw);
         neighbor_kernel<false><<<n_struct, NB_THREADS, smem, s>>>(
             n_struct, node_ptr, pos, cell, inv, img, rc2, row_ptr, node_struct, e->struct_edges.as<int>(), nullptr,
-            nullptr, 0, 1, 2, cl);
+            nullptr, 0, 1, 2, cl, nullptr);
     }
     struct_scan_kernel<<<1, 1024, 0, s>>>(n_struct, e->struct_edges.as<int>(), e->struct_edge_ptr.as<int>(),
                                            n_edges);
@@ -493,9 +550,14 @@ int launch_neighbor_fill(rlvd_engine* e, cudaStream_t s, int n_struct, int n_nod
     Span sp(e, s, FAM_NEIGHBOR);
     const int n_splits = neighbor_splits(n_struct);
     const int cl = neighbor_use_cl(n_struct, n_nodes) ? 1 : 0;      // same decision as the count pass: identical degrees
+    // the count pass of the same graph left its hit bits behind: fill from them (one use; any other call sweeps again)
+    const bool same = e->hit_key_pos == pos && e->hit_key_ptr == node_ptr && e->hit_key_nodes == n_nodes &&
+                      e->hit_key_struct == n_struct && e->hit_key_rc2 == rc2;
+    unsigned* hw = same ? e->hit_words.as<unsigned>() : nullptr;
+    e->hit_key_pos = nullptr;
     neighbor_kernel<true><<<dim3(n_struct, n_splits), NB_THREADS, neighbor_smem(cl != 0), s>>>(
         n_struct, node_ptr, pos, cell, inv, img, rc2, const_cast<int*>(row_ptr), nullptr, nullptr, col, shift, (long long)cap,
-        n_splits, 0, cl);
+        n_splits, 0, cl, hw);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;

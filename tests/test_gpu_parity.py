@@ -124,6 +124,14 @@ def test_edges_fuzz_bit_exact(engine):
         o_ptr, o_col, o_shift = batched_radius_graph(pos, cells, ptr.astype(np.int64), 5.0)
         assert np.array_equal(row_ptr.cpu().numpy(), o_ptr), trial
         assert np.array_equal(col.cpu().numpy(), o_col) and np.array_equal(shift.cpu().numpy(), o_shift), trial
+        # the fill pass normally walks the hit bits its count pass left behind (single-image structures <= 256 atoms);
+        # with that off it sweeps every pair again: the same arrays either way
+        engine.set_option("hit_words", 0)
+        try:
+            r2, c2, s2, _ = _device_graph(engine, pos, cells.astype(np.float32), ptr)
+        finally:
+            engine.set_option("hit_words", 1)
+        assert torch.equal(r2, row_ptr) and torch.equal(c2, col) and torch.equal(s2, shift), trial
 
 
 def test_edges_cell_list_bit_exact(engine):
