@@ -394,6 +394,53 @@ __global__ void __launch_bounds__(NB_THREADS) neighbor_kernel(
 
     const bool to_global = !staged || mode == 1;
     const bool words = hit_words != nullptr && staged && n <= 32 * HIT_WORDS && CLs.nb[0] == 0 && (C.R[0] | C.R[1] | C.R[2]) == 0;
+    if (!FILL && words && n_splits == 1 && mode == 0) {
+        // Count pass over HALF of the pairs.  The pair arithmetic is odd in pos_j - pos_i (every product and sum is rounded
+        // separately and rounding is sign-symmetric), so (i <- j) is an edge iff (j <- i) is: a warp tests only the chunks at
+        // and above its receiver's own chunk, the words below come from the transposed bits of the rows that own them.
+        unsigned* Mw = reinterpret_cast<unsigned*>(deg + 32 * HIT_WORDS);      // [n][HIT_WORDS] hit bits of the structure
+        for (int i = wid; i < n; i += nw) {
+            const float xi = P[3 * i], yi = P[3 * i + 1], zi = P[3 * i + 2];
+            for (int jb = i & ~31; jb < n; jb += 32) {
+                const int j = jb + lane;
+                bool hit = false;
+                if (j < n) {
+                    const float dx = __fsub_rn(P[3 * j], xi), dy = __fsub_rn(P[3 * j + 1], yi), dz = __fsub_rn(P[3 * j + 2], zi);
+                    float b0, b1, b2;
+                    base_image(C, dx, dy, dz, b0, b1, b2);
+                    const bool self = (j == i) && b0 == 0.f && b1 == 0.f && b2 == 0.f;
+                    hit = !self && image_d2(C, dx, dy, dz, b0, b1, b2) < rc2;
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) Mw[i * HIT_WORDS + (jb >> 5)] = mask;
+            }
+        }
+        __syncthreads();
+        const int nwords = (n + 31) >> 5;
+        for (int i = wid; i < n; i += nw) {
+            const int wi = i >> 5;
+            unsigned mine = 0u;                                   // lane c ends up holding word c of row i
+            for (int c = 0; c < wi; ++c) {
+                const unsigned bit = (Mw[(32 * c + lane) * HIT_WORDS + wi] >> (i & 31)) & 1u;     // 32 c + lane < 32 wi <= i < n
+                const unsigned mask = __ballot_sync(0xffffffffu, bit != 0u);
+                if (lane == c) mine = mask;
+            }
+            if (lane >= wi && lane < nwords) mine = Mw[i * HIT_WORDS + lane];
+            if (lane < HIT_WORDS) hit_words[(size_t)(node0 + i) * HIT_WORDS + lane] = mine;
+            int d = __popc(mine);
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);    // lanes 0-7 carry the words
+            if (lane == 0) {
+                deg[i] = d;
+                node_struct[node0 + i] = g;
+            }
+        }
+        __syncthreads();
+        const int total = block_excl_scan_inplace(deg, n, warp_sums);
+        for (int t = tid; t < n; t += NB_THREADS) row_ptr[node0 + t] = deg[t];
+        if (tid == 0) struct_edges[g] = total;
+        return;
+    }
     for (int i = wid + nw * (int)blockIdx.y; i < n; i += nw * n_splits) {
         const int row_start = FILL ? row_ptr[node0 + i] : 0;
         unsigned* hw = words ? hit_words + (size_t)(node0 + i) * HIT_WORDS : nullptr;
