@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define RLVD_ABI_VERSION 1
+#define RLVD_ABI_VERSION 2
 #define RLVD_F 128          /* hidden channels of the bundled painn (hyper_parameters.hidden_channels) */
 #define RLVD_NRBF 20        /* n_rbf */
 #define RLVD_NLAYER 3       /* n_interactions */
@@ -235,6 +235,8 @@ typedef struct rlvd_time_head {
     int32_t pooling;                        /* 0 mean, 1 sum */
     int32_t act;                            /* RLVD_ACT_* */
     float tau, T_scale, D_scale;
+    int32_t output;                         /* 0: tau * sigmoid(out) ("time"); 1: the raw output (t_net_binary's "goal" logit,
+                                               binary_cross_entropy_with_logits at rlsim/time/misc.py:205) */
 } rlvd_time_head;
 /* d_q[M,128] from rlvd_painn_representation; d_T / d_defect / d_time are [n_struct]. */
 int  rlvd_time_readout(rlvd_engine* e, void* stream, int32_t n_struct, const int32_t* d_node_ptr, const float* d_q,

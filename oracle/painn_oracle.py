@@ -70,6 +70,8 @@ class TimeHeadSpec:
     D_input: str = "defect / D_scaler"
     activation: str = "silu"
     squash: str = "tau * sigmoid"         # time in (0, tau)
+    # t_net_binary (rlsim/time/train.py:128, misc.py:205: binary_cross_entropy_with_logits(prediction["goal"], goal_labels)):
+    goal_head: str = "a second MLP of the same shape on the same pooled input; 'goal' is its raw output (a logit)"
     name: str = "TIME_HEAD_SPEC_V0"
 
 
@@ -250,8 +252,9 @@ class PaiNNOracle:
 
     # -- T1: t_net head (TimeHeadSpec)
     def time_forward(self, Z, pos, cells, node_ptr, T, defect, head: Dict[str, np.ndarray], tau: float = 1.0,
-                     T_scaler_m: float = 7918.951990135471, D_scaler: float = 1 / 256, pooling: str = "mean"):
-        """→ time[G]; ``head`` = {"w0","b0","w1","b1","w2","b2"} in nn.Linear layout."""
+                     T_scaler_m: float = 7918.951990135471, D_scaler: float = 1 / 256, pooling: str = "mean", logit: bool = False):
+        """→ time[G]; ``head`` = {"w0","b0","w1","b1","w2","b2"} in nn.Linear layout.  ``logit=True`` returns the head's raw
+        output instead (t_net_binary's ``"goal"``, TimeHeadSpec.goal_head)."""
         dt = self.dtype
         q = self.representation(Z, pos, cells, node_ptr)
         out = []
@@ -263,7 +266,7 @@ class PaiNNOracle:
             h = F.silu(W["w0"] @ z + W["b0"])
             h = F.silu(W["w1"] @ h + W["b1"])
             o = W["w2"] @ h + W["b2"]
-            out.append(tau * torch.sigmoid(o))
+            out.append(o if logit else tau * torch.sigmoid(o))
         return torch.cat(out)
 
     # -- H1..H4

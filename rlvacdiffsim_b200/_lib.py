@@ -27,7 +27,8 @@ class TimeHead(C.Structure):
     """``rlvd_time_head`` (include/rlvd_b200.h)."""
     _fields_ = [("d_w0", C.c_void_p), ("d_b0", C.c_void_p), ("d_w1", C.c_void_p), ("d_b1", C.c_void_p),
                 ("d_w2", C.c_void_p), ("d_b2", C.c_void_p), ("n_feat", C.c_int32), ("pooling", C.c_int32),
-                ("act", C.c_int32), ("tau", C.c_float), ("T_scale", C.c_float), ("D_scale", C.c_float)]
+                ("act", C.c_int32), ("tau", C.c_float), ("T_scale", C.c_float), ("D_scale", C.c_float),
+                ("output", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/rlvd_b200.h declares
@@ -99,7 +100,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.rlvd_abi_version() != 1:
+    if lib.rlvd_abi_version() != 2:
         raise RuntimeError("librlvd_b200.so has an unexpected ABI version")
     _lib = lib
     return lib

@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(TT) time_readout_kernel(int n_struct, const in
     if (tid == 0) {
         float v = __ldg(h.d_b2);
         for (int k = 0; k < nf; ++k) v = fmaf(__ldg(h.d_w2 + k), h1[k], v);
-        time_out[g] = h.tau / (1.0f + expf(-v));
+        time_out[g] = h.output == 1 ? v : h.tau / (1.0f + expf(-v));
     }
 }
 

@@ -430,7 +430,8 @@ class TNet(nn.Module, _EngineMixin):
     rgnn's head is not in the repo, so its wiring is a named assumption (``oracle.painn_oracle.TimeHeadSpec``):
     mean-pooled node scalars ‖ T / T_scaler_m ‖ defect / D_scaler → MLP(130 → n_feat → n_feat → 1, SiLU) →
     ``time = tau * sigmoid(.)`` ∈ (0, tau), matching ``timer_converter``'s ``-tau * log(1 - t / tau)``
-    (``estimate_time.py:15-35``).  ``t_net_binary``'s ``"goal"`` logit is not built."""
+    (``estimate_time.py:15-35``).  :class:`TNetBinary` (``t_net_binary``) adds the ``"goal"`` logit."""
+    HAS_GOAL = False
 
     def __init__(self, reaction_model: PaiNN, n_feat: int = 64, pooling: str = "mean", dropout_rate: float = 0.1,
                  tau0: float = 1.0, D_scaler: float = 1 / 256, T_scaler_m: float = 7918.951990135471, **_ignored):
@@ -486,9 +487,9 @@ class TNet(nn.Module, _EngineMixin):
             sd[name] = torch.zeros(shape)
         return sd, {"@name": "dqn_v2", "reaction_model": self._reaction_model.hyper}
 
-    def _head(self, dev: torch.device):
+    def _head(self, dev: torch.device, which: str = "time"):
         from ._lib import ACT_CODES, TimeHead
-        L = self.time_output.layers
+        L = (self.time_output if which == "time" else self.goal_output).layers
         ws = [L[0].weight, L[0].bias, L[3].weight, L[3].bias, L[6].weight, L[6].bias]
         keep = []
         for w in ws:
@@ -504,9 +505,11 @@ class TNet(nn.Module, _EngineMixin):
         h.tau = float(self.tau)
         h.T_scale = 1.0 / float(self.hyper["T_scaler_m"])
         h.D_scale = 1.0 / float(self.hyper["D_scaler"])
+        h.output = 0 if which == "time" else 1
         return h, keep
 
-    def time_device(self, Z, pos, cell, inv, img, node_ptr, max_struct_nodes: int, T, defect, edge_capacity=None) -> torch.Tensor:
+    def time_device(self, Z, pos, cell, inv, img, node_ptr, max_struct_nodes: int, T, defect, edge_capacity=None,
+                    with_goal: bool = False):
         """The forward on device-resident frames (fp32 ``pos[M,3]``, ``cell / inv [G,3,3]``, ``img[G,3]``, ``node_ptr``):
         K1 → K2-K4 → ``rlvd_time_readout``.  ``edge_capacity``: build the graph without reading the edge count back (frames
         of a sync-free TKS run, config 4)."""
@@ -527,6 +530,11 @@ class TNet(nn.Module, _EngineMixin):
         head, keep = self._head(pos.device)
         time = eng.time_readout(q, node_ptr, T, defect, head)
         del keep
+        if with_goal:                                           # the same pooled input through the second head (raw logit)
+            head, keep = self._head(pos.device, "goal")
+            goal = eng.time_readout(q, node_ptr, T, defect, head)
+            del keep
+            return time, goal
         return time
 
     def forward(self, batch, inference: bool = False, training: bool = False):
@@ -548,6 +556,21 @@ class TNet(nn.Module, _EngineMixin):
         G = len(counts)
         T = torch.as_tensor(batch["T"], dtype=torch.float32, device=dev).reshape(G).contiguous()
         defect = torch.as_tensor(batch["defect"], dtype=torch.float32, device=dev).reshape(G).contiguous()
-        time = self.time_device(Zc, posc, cell, torch.from_numpy(inv).to(dev), torch.from_numpy(img).to(dev), node_ptr,
-                                int(counts.max()), T, defect)
-        return {"time": time}
+        out = self.time_device(Zc, posc, cell, torch.from_numpy(inv).to(dev), torch.from_numpy(img).to(dev), node_ptr,
+                               int(counts.max()), T, defect, with_goal=self.HAS_GOAL)
+        return {"time": out[0], "goal": out[1]} if self.HAS_GOAL else {"time": out}
+
+
+class TNetBinary(TNet):
+    """``registry.get_model_class("t_net_binary")`` (``rlsim/time/train.py:42-48,128,196``): ``forward`` also returns
+    ``"goal"``, the logit ``combined_loss_binary`` feeds to ``binary_cross_entropy_with_logits`` (``time/misc.py:205``).
+    rgnn's head is not in the reference; the wiring is the named assumption ``TimeHeadSpec.goal_head``: a second MLP
+    (130 -> n_feat -> n_feat -> 1, SiLU) on the same pooled input, raw output.  Same kernels: ``rlvd_time_readout`` with
+    ``head.output = 1``."""
+    HAS_GOAL = True
+
+    def __init__(self, reaction_model: PaiNN, **cfg):
+        super().__init__(reaction_model, **cfg)
+        self.hyper["@name"] = "t_net_binary"
+        self.goal_output = MLP(reaction_model.hyper["hidden_channels"] + 2, 1, (self.hyper["n_feat"],) * 2, "silu",
+                               self.hyper["dropout_rate"])

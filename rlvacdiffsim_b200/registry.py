@@ -1,11 +1,11 @@
 """``rgnn.common.registry`` look-alike (``rlsim/drl/deploy.py:18``, ``train.py:50-52``, ``time/train.py:40-48``)."""
 from __future__ import annotations
 
-from .model import DQNv2, PaiNN, TNet
+from .model import DQNv2, PaiNN, TNet, TNetBinary
 
 
 class _Registry:
-    _models = {"dqn_v2": DQNv2, "t_net": TNet}
+    _models = {"dqn_v2": DQNv2, "t_net": TNet, "t_net_binary": TNetBinary}
     _reaction_models = {"painn": PaiNN}
 
     def get_model_class(self, name: str):

@@ -643,6 +643,37 @@ def test_t_net_time_matches_fp64_oracle(model):
     assert np.all(np.isfinite(-tnet.tau * np.log(1 - got / tnet.tau)))
 
 
+def test_t_net_binary_goal_logit_matches_fp64_oracle(model):
+    """time/train.py:108,128: ``pred = t_model(batch)`` with ``pred["time"]`` and ``pred["goal"]`` (a logit) for t_net_binary."""
+    torch.manual_seed(12)
+    tnet = rb.registry.get_model_class("t_net_binary").load_representation(model.reaction_model, n_feat=48, tau0=5.0,
+                                                                            dropout_rate=0.0).to("cuda").eval()
+    frames = [make_crconi_supercell(4, seed=31, jitter=0.03), make_crconi_supercell(3, seed=32, jitter=0.02)]
+    Ts, defects = [800.0, 1100.0], [1 / 256, 1 / 108]
+    graphs = []
+    for a, T, d in zip(frames, Ts, defects):
+        g = rb.AtomsGraph.from_ase(a, tnet.cutoff, read_properties=False, neighborlist_backend="ase", add_batch=True)
+        g.T = torch.tensor(T, dtype=torch.float32)
+        g.defect = torch.tensor(d, dtype=torch.float32)
+        graphs.append(g)
+    batch = rb.batch_to(next(iter(rb.DataLoader(rb.AtomsDataset(graphs), batch_size=8))), "cuda")
+    with torch.no_grad():
+        out = tnet(batch, inference=True)
+    m64 = PaiNNOracle.load(os.path.join(GOLD, "model_trained"), dtype=torch.float64)
+    Z = np.concatenate([f.numbers for f in frames])
+    pos = np.concatenate([f.positions for f in frames]).astype(np.float32)
+    cells = np.stack([np.asarray(f.cell, dtype=np.float64) for f in frames])
+    ptr = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(np.int32)
+    for key, mlp, logit in (("time", tnet.time_output, False), ("goal", tnet.goal_output, True)):
+        L = mlp.layers
+        head = {"w0": L[0].weight, "b0": L[0].bias, "w1": L[3].weight, "b1": L[3].bias, "w2": L[6].weight, "b2": L[6].bias}
+        head = {k: v.detach().cpu().double().numpy() for k, v in head.items()}
+        with torch.no_grad():
+            ref = m64.time_forward(Z, pos, cells, ptr, Ts, defects, head, tau=5.0, logit=logit).numpy()
+        got = out[key].cpu().numpy()
+        assert got.shape == (2,) and np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) < TOL, key
+
+
 # ----------------------------------------------------------------------------- A1 on the device
 
 def test_action_space_device_matches_host_enumerator(engine):

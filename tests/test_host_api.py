@@ -124,7 +124,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()                      # raises if the .so is missing; no compute without a GPU
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.rlvd_abi_version() == 1
+    assert lib.rlvd_abi_version() == 2
 
 
 def test_t_net_surface_and_oracle_head(checkpoint_path):
@@ -273,4 +273,12 @@ def test_time_estimator_glue(tmp_path, checkpoint_path):
     again = rb.registry.get_model_class("t_net").load(str(tmp_path / "checkpoint10.pth.tar"))
     assert again.tau == 2.5 and again.hyper["n_feat"] == 64
     for (k1, v1), (k2, v2) in zip(tnet.state_dict().items(), again.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    # t_net_binary (time/train.py:42-48): same constructor, a second head for the "goal" logit, same checkpoint format
+    tb = rb.registry.get_model_class("t_net_binary").load_representation(dqn.reaction_model, n_feat=32, pooling="sum", tau0=2.0)
+    assert tb.HAS_GOAL and any(k.startswith("goal_output.") for k in tb.state_dict())
+    tb.save(str(tmp_path / "tb.pth.tar"))
+    tb2 = rb.registry.get_model_class("t_net_binary").load(str(tmp_path / "tb.pth.tar"))
+    assert tb2.hyper["@name"] == "t_net_binary" and tb2.hyper["pooling"] == "sum"
+    for (k1, v1), (k2, v2) in zip(tb.state_dict().items(), tb2.state_dict().items()):
         assert k1 == k2 and torch.equal(v1, v2)
