@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librlvd_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["engine.cu", "neighbor.cu", "node.cu", "tc_linear.cu", "tc_linear2.cu", "edge.cu", "tc_edge.cu", "edge_stream.cu", "readout.cu", "actions.cu", "train.cu", "train_full.cu"]
+SOURCES = ["engine.cu", "neighbor.cu", "node.cu", "tc_linear.cu", "edge.cu", "tc_edge.cu", "edge_stream.cu", "readout.cu", "actions.cu", "train.cu", "train_full.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("RLVD_EXTRA_NVCC_FLAGS", "").split()
 

@@ -142,13 +142,12 @@ struct rlvd_engine {
     rlvd::DevBuf in_node_ptr, in_Z, in_pos, in_cell, in_inv, in_img, in_rs, in_ps, in_temp, in_qp;
     rlvd::DevBuf g_row_ptr, g_node_struct, g_col, g_shift, g_nedges, g_q, out_pack;
     int64_t launches = 0;
-    bool attr_stream = false, attr_neighbor = false, attr_tc_edge = false, attr_tc_linear = false, attr_tc_linear2 = false, attr_train = false;   // dynamic-smem opt-ins done on this device
+    bool attr_stream = false, attr_neighbor = false, attr_tc_edge = false, attr_tc_linear = false, attr_train = false;   // dynamic-smem opt-ins done on this device
     bool use_tensor_cores = true;
     bool use_sliced_edge = true;    // structure-resident edge kernels when every structure has <= 256 atoms
     bool fuse_mix = true;           // nrm / vw reductions inside the mu_channel_mix GEMM epilogue (tc_linear.cu mixred mode): same
                                     // step time as GEMM + reduction kernel within run-to-run noise, 4.8 GB less DRAM traffic per step
     bool fuse_mlp = true;           // Linear -> SiLU -> Linear pairs as one tcgen05 launch (tc_linear.cu two-layer mode)
-    bool use_tc_linear2 = true;     // large node batches run the channel-mixing GEMMs as two small CTAs per SM (tc_linear2.cu)
     bool prune_final_mu = true;     // callers that take q only (d_mu == NULL): the last mixing block skips everything that
                                     // only feeds mu's update (W store, the b block of the intra-atomic net, mu += b W)
     bool profiling = false;
@@ -215,8 +214,6 @@ struct LinearArgs {
 int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a);
 int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt);
 bool tc_linear_supported(const LinearArgs& a);
-int launch_tc_linear2(rlvd_engine* e, cudaStream_t s, const LinearArgs& a, const void* Wfmt);   // two CTAs per SM (tc_linear2.cu)
-bool tc_linear2_supported(const LinearArgs& a);
 void tc_format_weight(const float* W, int N, int K, std::vector<uint8_t>& out);
 void tc_format_mix_weight(const float* W, std::vector<uint8_t>& out);
 

@@ -857,10 +857,6 @@ int rlvd_set_option(rlvd_engine* e, const char* name, int32_t value) {
         e->hit_key_pos = nullptr;
         return 0;
     }
-    if (strcmp(name, "tc_linear2") == 0) {
-        e->use_tc_linear2 = value != 0;
-        return 0;
-    }
     if (strcmp(name, "prune_final_mu") == 0) {
         e->prune_final_mu = value != 0;
         return 0;

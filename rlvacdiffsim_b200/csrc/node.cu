@@ -219,12 +219,7 @@ __global__ void mix_update_q_kernel(int M, const float* __restrict__ ctx_ac, con
 }  // namespace
 
 int launch_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a) {
-    if (e->use_tensor_cores && a.Wfmt != nullptr && tc_linear_supported(a)) {
-        // batches of at least two 128-row tiles per CTA slot: two small CTAs per SM overlap each other's phases
-        const int64_t tiles = a.mixred ? (a.n_nodes + 39) / 40 : ((int64_t)a.M + 127) / 128;
-        if (e->use_tc_linear2 && tc_linear2_supported(a) && tiles >= 4 * (int64_t)e->sm_count) return launch_tc_linear2(e, s, a, a.Wfmt);
-        return launch_tc_linear(e, s, a, a.Wfmt);
-    }
+    if (e->use_tensor_cores && a.Wfmt != nullptr && tc_linear_supported(a)) return launch_tc_linear(e, s, a, a.Wfmt);
     RLVD_CHECK(a.gate == nullptr, "linear: gated launches exist on the tcgen05 path only");
     RLVD_CHECK(a.mixred == 0, "linear: the mix-reduce form exists on the tcgen05 path only (M=%d n_nodes=%d)", a.M, a.n_nodes);
     RLVD_CHECK(a.W2fmt == nullptr, "linear: the fused two-layer form exists on the tcgen05 path only (shape M=%d K=%d N=%d N2=%d)",

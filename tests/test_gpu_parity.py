@@ -438,47 +438,6 @@ def test_tc_linear_matches_fp64(engine, M, K, N, K1, act):
     assert err_tc < 2e-6, (err_tc, err_simt)          # 22-bit operands, fp32 accumulate
 
 
-@pytest.mark.parametrize("M,K,N,K1,act", [(76000, 128, 128, 0, 1), (75937, 128, 384, 0, 0), (80001, 256, 128, 128, 1),
-                                          (76800, 128, 256, 0, 0)])
-def test_tc_linear2_equals_tc_linear(engine, M, K, N, K1, act):
-    """Large row counts run the GEMM as two small CTAs per SM (tc_linear2.cu); same operands, same accumulation order per
-    output element: bit-identical to tc_linear.cu, and fp32-accurate against float64."""
-    rng = np.random.default_rng(M + K + N)
-    A = torch.from_numpy(rng.normal(0, 1.0, (M, K)).astype(np.float32)).cuda()
-    W = (rng.normal(0, 0.1, (N, K))).astype(np.float32)
-    b = rng.normal(0, 0.1, N).astype(np.float32)
-    parts = (A[:, :K1].contiguous(), A[:, K1:].contiguous()) if K1 else (A, None)
-    before = engine.launch_count()
-    y2 = engine.linear(parts[0], W, b, act, parts[1])
-    engine.set_option("tc_linear2", 0)
-    try:
-        y1 = engine.linear(parts[0], W, b, act, parts[1])
-    finally:
-        engine.set_option("tc_linear2", 1)
-    assert engine.launch_count() - before == 2
-    assert torch.equal(y1, y2)
-    ref = A[:4096].double().cpu() @ torch.from_numpy(W).double().T + torch.from_numpy(b).double()
-    if act:
-        ref = ref * torch.sigmoid(ref)
-    assert (y2[:4096].double().cpu() - ref).abs().max().item() / ref.abs().max().item() < 2e-6
-
-
-def test_tc_linear2_end_to_end_bitwise(model, engine):
-    """26 replicas x 12 candidates = 624 structures (159 k nodes): every channel-mixing GEMM of the call takes the two-CTA
-    kernel, fused second layer and mix-reduce epilogue included; the Q-values equal the one-CTA kernel's bit for bit."""
-    reps = [make_crconi_supercell(4, seed=100 + s, jitter=0.02) for s in range(26)]
-    spaces = [rb.get_action_space(r, 3.528) for r in reps]
-    qp = {"alpha": 0.0, "beta": 1.0, "dqn": True, "temperature": 700.0}
-    two = ReplicaScorer(model, 0).score(reps, spaces, qp)
-    engine.set_option("tc_linear2", 0)
-    try:
-        one = ReplicaScorer(model, 0).score(reps, spaces, qp)
-    finally:
-        engine.set_option("tc_linear2", 1)
-    for r in range(26):
-        assert np.array_equal(one[r], two[r]), r
-
-
 def test_tensor_core_and_simt_paths_agree_end_to_end(model, engine):
     g = load_gold("syn255_s2_jitter")
     engine.set_option("tensor_cores", 0)
