@@ -334,15 +334,11 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
     const int l0k = min(lane, NK - 1);
     float* const wst = stg_v[warp];
     float4* const wsd = stg_d[warp];
-    const int i_first = warp + 8 * (int)blockIdx.y;
-    int nx0 = 0, nx1 = 0;                 // row_ptr pair of the NEXT receiver of this warp: loaded one receiver ahead
-    if (i_first < n) { nx0 = __ldg(row_ptr + node0 + i_first); nx1 = __ldg(row_ptr + node0 + i_first + 1); }
-    for (int i = i_first; i < n; i += 8 * n_splits) {
+    for (int i = warp + 8 * (int)blockIdx.y; i < n; i += 8 * n_splits) {
         int p = 0;
         while (i >= bnd[p + 1]) ++p;
         const int gi = node0 + i;
-        const int re0 = nx0, rdeg = nx1 - nx0;
-        if (i + 8 * n_splits < n) { nx0 = __ldg(row_ptr + gi + 8 * n_splits); nx1 = __ldg(row_ptr + gi + 8 * n_splits + 1); }
+        const int re0 = __ldg(row_ptr + gi), rdeg = __ldg(row_ptr + gi + 1) - re0;
         const int nslots = max(1, (rdeg + GS - 1) / GS) * GS;
         const int slot0 = (goff[i] - goff[bnd[p]]) * GS;
         const float xi = spos[3 * i], yi = spos[3 * i + 1], zi = spos[3 * i + 2];
@@ -353,11 +349,6 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
             const int s = s0 + lane;
             const bool live = s < rdeg;
             const int jg = live ? __ldg(col + re0 + s) : 0;
-            int sh0 = 0, sh1 = 0, sh2 = 0;              // issued with the sender index: all four loads of an edge in flight together
-            if (live) {
-                const int8_t* sp = shift + 3 * (int64_t)(re0 + s);
-                sh0 = sp[0]; sh1 = sp[1]; sh2 = sp[2];
-            }
             // layer-0 sums: slot records are staged sorted by sender species (CSR order within a species)
             int at = 0, c0 = 0, c1 = 0, c2 = 0;
             if (l0A != nullptr) {
@@ -374,7 +365,8 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
             const int r = slot & 31;
             if ((s & (GS - 1)) == 0) tile[TILE_B + META_FLAG + (r >> 3)] = (uint8_t)(s == 0 && i > bnd[p] ? 1 : 0);   // new receiver starts
             if (live) {
-                const float S0 = (float)sh0, S1 = (float)sh1, S2 = (float)sh2;
+                const int e = re0 + s;
+                const float S0 = (float)shift[3 * (int64_t)e], S1 = (float)shift[3 * (int64_t)e + 1], S2 = (float)shift[3 * (int64_t)e + 2];
                 const int jl = jg - node0;
                 float rx = spos[3 * jl] - xi, ry = spos[3 * jl + 1] - yi, rz = spos[3 * jl + 2] - zi;
                 rx += S0 * C[0] + S1 * C[3] + S2 * C[6];
