@@ -60,10 +60,10 @@ constexpr int GS = 8;                     // slots per receiver-aligned group
 constexpr int KH = 64;                    // fp16 k-extent of the split operands
 constexpr int NK = NRBF + 1;              // 21: 20 Bessel functions + the bias column (fcut)
 constexpr int TILE_B = TE * KH * 2;       // 4096
-constexpr int META = 432;                 // j[32] u8 | newrecv[4] u8 | pad[12] | dir[3][32] f32
-constexpr int META_DIR = 48;
-constexpr int META_FLAG = 32;
-constexpr int TILE_BYTES = TILE_B + META; // 4528
+constexpr int META = 464;                 // 4*j[32] u16 | newrecv[4] u8 | pad[12] | dir[3][32] f32
+constexpr int META_DIR = 80;
+constexpr int META_FLAG = 64;
+constexpr int TILE_BYTES = TILE_B + META; // 4560
 constexpr int MAXN = 256;
 constexpr int ST_THREADS = NPIPE * 128;
 constexpr int B_SCALE_LOG2 = 10;
@@ -171,6 +171,25 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 __device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
+// shared-memory gather with an explicit 32-bit address (the node table is read-only while the roles run)
+template <int OFF>
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+// Gather address in one instruction (IDP.2A issues at the IMAD rate, scripts/probes/idp_rate.cu): the tile meta carries
+// 4*j as u16 pairs; dp2a.lo adds (low half) * b.byte0, dp2a.hi adds (high half) * b.byte3 to the base.
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ float sum2(f32x2 v) {
     float lo, hi;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
@@ -212,7 +231,7 @@ __device__ __forceinline__ void write_slot(uint8_t* tile, int r, const uint4* ro
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(b + kc * 512) = row8[kc];
     uint8_t* m = tile + TILE_B;
-    m[r] = (uint8_t)j;
+    reinterpret_cast<uint16_t*>(m)[r] = (uint16_t)(j * 4);   // the gather address is ONE dp2a: 4j * (NODE_BYTES / 4) + base
     reinterpret_cast<float*>(m + META_DIR)[r] = dx;
     reinterpret_cast<float*>(m + META_DIR + 128)[r] = dy;
     reinterpret_cast<float*>(m + META_DIR + 256)[r] = dz;
@@ -498,7 +517,7 @@ struct PipeCtx {
     const uint8_t* tab;      // node table of the slice
     uint8_t* MetaP;          // NM_STAGE meta buffers
     float* Part;             // this SM's / pipeline's partial-sum scratch: [3][4][PART_ROWS][32] (global, L2-resident)
-    int n_tiles, ra, rb, node0, ch;
+    int n_tiles, ra, rb, node0, ch, pf_eighths;
     long long* dbg;          // RLVD_TIMELINE: clock64 stamps of block 0 / pipeline 0
 };
 
@@ -527,6 +546,8 @@ struct Feed {                // what the thread doing a pipeline's producer duty
     const uint8_t* src;      // first tile of the pipeline
     uint8_t* Bp;             // NB_STAGE operand buffers
     uint64_t bdesc0;
+    const uint8_t* pf;       // L2 prefetch duty of this feeder (see edge_stream_kernel): a chunk of the node rows a CTA that
+    uint32_t pf_bytes;       // starts ~one CTA lifetime from now will stage; 0 = none
 };
 
 __device__ __forceinline__ void feed_copy(const PipeCtx& c, const Feed& fd, int k) {
@@ -592,8 +613,10 @@ __device__ __forceinline__ void run_feeder(const PipeCtx& c, const Feed& fd) {
         feed_copy(c, fd, 3);
     }
 #pragma unroll 1
+    const int pf_t = (n_tiles * c.pf_eighths) >> 3;
     for (int t = 0; t + 2 < n_tiles; ++t) {
         const uint32_t bi = (uint32_t)t & 1u;
+        if (t == pf_t && fd.pf_bytes != 0) prefetch_l2(fd.pf, fd.pf_bytes);
         st_wait(&S->acc_free[pipe][bi], ((uint32_t)t >> 1) & 1u);
         feed_mma(c, fd, t + 2);
         if (t + 4 < n_tiles) {
@@ -614,6 +637,8 @@ template <bool HAS_MU, int ROLE>
 __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const float* __restrict__ mu_in,
                                          float* __restrict__ q, float* __restrict__ mu_out) {
     constexpr int NB = Tab<HAS_MU>::NODE_BYTES;
+    constexpr uint32_t NB_SEL = (uint32_t)(NB / 4) | ((uint32_t)(NB / 4) << 24);   // dp2a.lo: h0 * b0 | dp2a.hi: h1 * b3
+    static_assert(NB / 4 <= 255 && NB % 4 == 0, "gather stride as a dp2a byte");
     constexpr int NACC = ROLE == 0 ? 1 : 3;
     constexpr int T_OFF = ROLE == 0 ? 0 : ROLE == 1 ? SL * 4 : 2 * SL * 4;
     constexpr int P_ROW = ROLE == 1 ? 0 : 3;
@@ -623,7 +648,11 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
     if (n_tiles <= 0 || c.ra >= c.rb) return;     // (a non-empty receiver range always has tiles)
 
     const uint32_t dcol0 = c.tmem + ((uint32_t)(c.quarter * 32) << 16) + TM_D + (uint32_t)(pipe * 2) * TE;
-    const uint8_t* tb = c.tab + lane * 4 + T_OFF;
+    // Gather base as ONE opaque 32-bit shared-window address: a gather is then PRMT (sender byte) + IMAD (j * NB + tb) + LDS.
+    // (Left as a generic pointer, nvcc re-associated it into (j * NB + lane * 4) + table base in some builds of this kernel:
+    // one more integer instruction per gather, 14 % more instructions per tile.)
+    uint32_t tb = smem_u32(c.tab) + lane * 4 + T_OFF;
+    asm("mov.b32 %0, %0;" : "+r"(tb));
     float* qp = q + ((int64_t)c.node0 * F + c.ch);
     float* mup = mu_out + ((int64_t)c.node0 * 3 * F + c.ch);
 
@@ -681,7 +710,7 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
         for (int gg = 0; gg < NG; ++gg) {
             uint32_t f[8];
             tmem_ld8(dcol + gg * GS, f);
-            const uint2 jw = *reinterpret_cast<const uint2*>(meta + gg * GS);
+            const uint4 jw = *reinterpret_cast<const uint4*>(meta + gg * GS * 2);
             float dr[3][8];
             if (ROLE == 1) {
 #pragma unroll
@@ -695,11 +724,12 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
             float t1[8], t2[8], t3[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const uint8_t* row = tb + __byte_perm(u < 4 ? jw.x : jw.y, 0u, 0x4440u | (u & 3)) * NB;
-                t1[u] = *reinterpret_cast<const float*>(row);
+                const uint32_t jp = u < 2 ? jw.x : u < 4 ? jw.y : u < 6 ? jw.z : jw.w;     // (4 j_even, 4 j_odd) as two u16
+                const uint32_t row = (u & 1) ? dp2a_hi(jp, NB_SEL, tb) : dp2a_lo(jp, NB_SEL, tb);
+                t1[u] = lds_f32<0>(row);
                 if (ROLE == 2) {
-                    t2[u] = *reinterpret_cast<const float*>(row + SL * 4);
-                    t3[u] = *reinterpret_cast<const float*>(row + 2 * SL * 4);
+                    t2[u] = lds_f32<SL * 4>(row);
+                    t3[u] = lds_f32<2 * SL * 4>(row);
                 }
             }
             if ((flagw >> (8 * gg)) & 0xffu) {                       // this group starts the next receiver
@@ -782,12 +812,17 @@ __device__ __forceinline__ void run_role(const PipeCtx& c, const Feed& fd, const
     }
 }
 
+// Table staging loads bypass L1 (ld.global.cg): with 226 KB of the SM's 228 KB configured as shared memory the L1 has a
+// handful of lines left, and allocating loads (ld.global.nc) queue on them.
+#ifndef RLVD_STAGE_LD
+#define RLVD_STAGE_LD __ldcg
+#endif
 template <bool HAS_MU>
 __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     int n_max, const int* __restrict__ node_ptr, const uint32_t* __restrict__ Afmt /* [4 slices][4 rotations][128][32] */,
     float kappa, const int4* __restrict__ pipe_info, const uint8_t* __restrict__ tiles, float* __restrict__ scratch,
     const float* __restrict__ x, const float* __restrict__ mu_in, float* __restrict__ q, float* __restrict__ mu_out,
-    long long* dbg, const int* __restrict__ gate, int gate_value) {
+    long long* dbg, const int* __restrict__ gate, int gate_value, int n_struct, int pf_ahead, int pf_eighths) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if (gate != nullptr && *gate != gate_value) return;     // uniform over the grid: layer-0 fallback not needed
     constexpr int NB = Tab<HAS_MU>::NODE_BYTES;
@@ -801,6 +836,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x / NSLICE, slice = blockIdx.x % NSLICE;
     const int node0 = __ldg(node_ptr + g), n = __ldg(node_ptr + g + 1) - node0;
+#ifdef RLVD_TIMELINE   // CTA-level stamps of block 0 and of a mid-grid block: entry | feeders released | table staged | roles done | exit
+    long long* cst = dbg == nullptr ? nullptr : blockIdx.x == 0 ? dbg + 64 * 4 * 10 : blockIdx.x == 6001 ? dbg + 64 * 4 * 10 + 8 : nullptr;
+#define RLVD_CTA_STAMP(k, w) if (cst != nullptr && warp == (w) && lane == 0) cst[k] = clock64();
+#else
+#define RLVD_CTA_STAMP(k, w)
+#endif
+    RLVD_CTA_STAMP(0, 0)
     uint32_t smid;
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     if (smid >= MAX_SMID) {
@@ -808,77 +850,139 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
         __trap();
     }
 
-    if (tid == 0) {
-        for (int p = 0; p < NPIPE; ++p)
-            for (int k = 0; k < 2; ++k) {
-                mbar_init(&S->b_full[p][k], 1);
-                mbar_init(&S->mma_done[p][k], 1);
-                mbar_init(&S->acc_free[p][k], NROLE);
-            }
-        fence_mbar_init();
-    }
-    if (warp == 0) tmem_alloc(&S->tmem_base, TM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = S->tmem_base;
-
-    // Prologue overlap: the feeder warps only need the weight operand in TMEM, the consuming warps only need the node
-    // table.  Warps 0-3 load the operand and release the feeders through named barrier 1; the consuming warps stage the
-    // table meanwhile and meet at named barrier 2, so the first tiles' copies and MMAs run under the table staging.
+    // Prologue.  The feeder warps only need the weight operand in TMEM, the consuming warps only need the node table:
+    //   all warps      : warp 3 (pipeline 0's feeder) initialises the mbarriers and allocates TMEM, then ONE block barrier
+    //                    publishes both (~2.5 k cycles).  It comes BEFORE the staging loads: measured, a feeder's
+    //                    mbarrier.init / L2 loads issued under the 576-thread staging flood wait 2-5 k cycles in the LSU queue.
+    //   feeder warps   : the feeders of pipelines 0..3 sit in TMEM lane quarters 3, 2, 1, 0 (pipe_rot); each loads its quarter
+    //                    of the operand (the first two rotations are requested before the block barrier) and stores it;
+    //                    named barrier 1 (feeder warps only) then releases the feeders: the first tiles' copies and MMAs run
+    //                    under the table staging.
+    //   consuming warps: stage the node table (nothing else) and meet at named barrier 2.
+    // The waves of this kernel run in lockstep (equal work per CTA), so all 148 SMs stage at once and the 196 KB per CTA come
+    // at the HBM rate (10-11 k cycles; 4.5 k when a single SM stages: scripts/probes/stage_rate.cu) unless the previous wave
+    // asked L2 for them (Feed::pf below).
+    // (Round 2, first form: warps 0-3 loaded the operand before staging their share of the table: feeders released at
+    // 9-12 k cycles, table staged at 15-21 k of a ~175 k-cycle CTA; profiles/timeline_stream_r02.txt.)
     const int pipe_w = warp >> 2;
     const int role_w = ((warp & 3) + pipe_rot(pipe_w)) & 3;
     const bool feeds = role_w == 3 || (!HAS_MU && role_w == 2);
     constexpr int NCW = HAS_MU ? 3 : 2;                             // consuming warps per pipeline
     constexpr int N_FEED_WARPS = NPIPE * (4 - NCW);
-    constexpr int A_BAR_THREADS = (NCW + N_FEED_WARPS) * 32;        // warps 0..NCW-1 arrive, every feeder warp waits
+    constexpr int FEED_THREADS = N_FEED_WARPS * 32;
     constexpr int STAGE_THREADS = NPIPE * NCW * 32;
+    static_assert(NPIPE >= 4, "the feeders of pipelines 0..3 cover the four TMEM lane quarters");
 
-    // ---- weight operand -> TMEM in its four row rotations (lane = filter row; 64 fp16 = 32 columns each)
-    if (warp < 4) {
-#pragma unroll 1
-        for (int rot = 0; rot < NROT; ++rot) {
-            const uint4* wrow = reinterpret_cast<const uint4*>(Afmt + ((size_t)(slice * NROT + rot) * 128 + warp * 32 + lane) * 32);
-            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + TM_A + rot * 32;
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-                const uint4 w0 = __ldg(wrow + 2 * c8), w1 = __ldg(wrow + 2 * c8 + 1);
-                const uint32_t v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                tmem_st8(ta + c8 * 8, v);
-            }
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-    }
     if (feeds) {
-        asm volatile("bar.sync 1, %0;" ::"n"(A_BAR_THREADS) : "memory");
-        tc_fence_after();
-    } else {
-        if (warp < 4) asm volatile("bar.arrive 1, %0;" ::"n"(A_BAR_THREADS) : "memory");
-        // ---- stage this slice of the structure's node table (consuming warps only)
-        const int sid = (pipe_w * NCW + role_w) * 32 + lane;
-        for (int id = sid; id < n * 8; id += STAGE_THREADS) {
-            const int node = id >> 3, c4 = id & 7;
-            const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(node0 + node) * 3 * F + slice * SL) + c4;
-            float4 xq = __ldg(xr), xR = __ldg(xr + F / 4);
-            uint8_t* row = TabS + node * NB + c4 * 16;
-            xq.x *= kappa; xq.y *= kappa; xq.z *= kappa; xq.w *= kappa;
-            xR.x *= kappa; xR.y *= kappa; xR.z *= kappa; xR.w *= kappa;
-            *reinterpret_cast<float4*>(row) = xq;
-            *reinterpret_cast<float4*>(row + SL * 4) = xR;
-            if (HAS_MU) {
-                float4 xm = __ldg(xr + 2 * F / 4);
-                xm.x *= kappa; xm.y *= kappa; xm.z *= kappa; xm.w *= kappa;
-                const float4* mr = reinterpret_cast<const float4*>(mu_in + (size_t)(node0 + node) * 3 * F + slice * SL) + c4;
+        // the operand loads (L2) are issued first: their latency hides behind barrier initialisation and TMEM allocation
+        const bool loads_a = role_w == 3 && pipe_w < 4;
+        const int quarter = warp & 3;
+        const uint4* wrow = reinterpret_cast<const uint4*>(Afmt + ((size_t)(slice * NROT) * 128 + quarter * 32 + lane) * 32);
+        uint4 w[16];
+        if (loads_a) {
 #pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const float4 m = __ldg(mr + a * (F / 4));
-                    *reinterpret_cast<float4*>(row + (2 + a) * SL * 4) = make_float4(xm.x * m.x, xm.y * m.y, xm.z * m.z, xm.w * m.w);
+            for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) w[r2 * 8 + c8] = __ldg(wrow + (size_t)r2 * 128 * 8 + c8);
+        }
+        if (warp == 3) {
+            if (lane == 0) {
+                for (int p = 0; p < NPIPE; ++p)
+                    for (int k = 0; k < 2; ++k) {
+                        mbar_init(&S->b_full[p][k], 1);
+                        mbar_init(&S->mma_done[p][k], 1);
+                        mbar_init(&S->acc_free[p][k], NROLE);
+                    }
+                fence_mbar_init();
+            }
+            __syncwarp();
+            tmem_alloc(&S->tmem_base, TM_COLS);
+            tc_fence_before();
+        }
+        __syncthreads();          // barriers and TMEM base published to the whole CTA before the staging loads flood the LSU
+        tc_fence_after();
+        RLVD_CTA_STAMP(6, 3)
+        const uint32_t tmem_f = S->tmem_base;
+        // ---- weight operand -> TMEM in its four row rotations (lane = filter row; 64 fp16 = 32 columns each)
+        if (loads_a) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int r2 = 0; r2 < 2; ++r2) {
+                    const uint32_t ta = tmem_f + ((uint32_t)(quarter * 32) << 16) + TM_A + (half * 2 + r2) * 32;
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        const uint4 w0 = w[r2 * 8 + 2 * c8], w1 = w[r2 * 8 + 2 * c8 + 1];
+                        const uint32_t v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                        tmem_st8(ta + c8 * 8, v);
+                    }
+                }
+                if (half == 0) {
+#pragma unroll
+                    for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+                        for (int c8 = 0; c8 < 8; ++c8) w[r2 * 8 + c8] = __ldg(wrow + (size_t)(2 + r2) * 128 * 8 + c8);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"n"(FEED_THREADS) : "memory");
+        tc_fence_after();
+        RLVD_CTA_STAMP(1, 3)
+    } else {
+        __syncthreads();
+        tc_fence_after();
+        // ---- stage this slice of the structure's node table (consuming warps only); two items' loads in flight
+        const int sid = (pipe_w * NCW + role_w) * 32 + lane;
+        const int n_items = n * 8;
+#pragma unroll 1
+        for (int id0 = sid; id0 < n_items; id0 += 2 * STAGE_THREADS) {
+            float4 xq[2], xR[2], xm[2], m[2][3];
+            bool on[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int id = id0 + h * STAGE_THREADS;
+                on[h] = id < n_items;
+                if (on[h]) {
+                    const int node = id >> 3, c4 = id & 7;
+                    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(node0 + node) * 3 * F + slice * SL) + c4;
+                    xq[h] = RLVD_STAGE_LD(xr);
+                    xR[h] = RLVD_STAGE_LD(xr + F / 4);
+                    if (HAS_MU) {
+                        xm[h] = RLVD_STAGE_LD(xr + 2 * F / 4);
+                        const float4* mr = reinterpret_cast<const float4*>(mu_in + (size_t)(node0 + node) * 3 * F + slice * SL) + c4;
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) m[h][a] = RLVD_STAGE_LD(mr + a * (F / 4));
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (!on[h]) continue;
+                const int id = id0 + h * STAGE_THREADS;
+                const int node = id >> 3, c4 = id & 7;
+                uint8_t* row = TabS + node * NB + c4 * 16;
+                float4 a = xq[h], b = xR[h];
+                a.x *= kappa; a.y *= kappa; a.z *= kappa; a.w *= kappa;
+                b.x *= kappa; b.y *= kappa; b.z *= kappa; b.w *= kappa;
+                *reinterpret_cast<float4*>(row) = a;
+                *reinterpret_cast<float4*>(row + SL * 4) = b;
+                if (HAS_MU) {
+                    float4 c = xm[h];
+                    c.x *= kappa; c.y *= kappa; c.z *= kappa; c.w *= kappa;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        *reinterpret_cast<float4*>(row + (2 + k) * SL * 4) =
+                            make_float4(c.x * m[h][k].x, c.y * m[h][k].y, c.z * m[h][k].z, c.w * m[h][k].w);
                 }
             }
         }
         asm volatile("bar.sync 2, %0;" ::"n"(STAGE_THREADS) : "memory");
+        tc_fence_after();
+        RLVD_CTA_STAMP(2, 0)
     }
+    const uint32_t tmem = S->tmem_base;
 
     PipeCtx c;
     c.S = S;
@@ -895,20 +999,40 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     c.rb = pi.w;
     c.node0 = node0;
     c.ch = slice * SL + lane;
+    c.pf_eighths = pf_eighths;
     c.dbg = (blockIdx.x == 0 && c.pipe == 0 && lane == 0) ? dbg : nullptr;
     const int role = role_w;                          // the pipeline's rotation puts this role's filter rows in this warp's quarter
     Feed fd;
     fd.src = tiles + (size_t)pi.x * TILE_BYTES;
     fd.Bp = Bs + c.pipe * NB_STAGE * TILE_B;
     fd.bdesc0 = umma_desc(smem_u32(fd.Bp), 512, 128);
+    // Table-staging prefetch: the CTAs that take over the SMs when this wave retires (structure g + pf_ahead) will pull
+    // their x / mu rows from HBM with every consuming warp stalled on them (~15 k cycles of a ~175 k-cycle CTA).  Half way
+    // through its tiles each of the 16 (slice, pipeline < 4) feeders asks L2 for one sixteenth of those rows.
+    fd.pf = nullptr;
+    fd.pf_bytes = 0;
+    if (HAS_MU && pf_ahead > 0 && c.pipe < 4 && g + pf_ahead < n_struct) {
+        const int na = __ldg(node_ptr + g + pf_ahead), nb = __ldg(node_ptr + g + pf_ahead + 1);
+        const int chunk = c.pipe * NSLICE + slice;                       // 0..15: x chunks 0..7, mu chunks 8..15
+        const uint32_t total = (uint32_t)(nb - na) * 3u * F * 4u;        // bytes of the structure's rows in either array
+        const uint32_t per = ((total + 7u) / 8u + 127u) & ~127u;
+        const uint32_t off = (uint32_t)(chunk & 7) * per;
+        if (off < total) {
+            const uint8_t* base = reinterpret_cast<const uint8_t*>(chunk < 8 ? x : mu_in) + (size_t)na * 3 * F * 4;
+            fd.pf = base + off;
+            fd.pf_bytes = total - off < per ? total - off : per;
+        }
+    }
     if (role == 0) run_role<HAS_MU, 0>(c, fd, mu_in, q, mu_out);
     else if (role == 1) run_role<HAS_MU, 1>(c, fd, mu_in, q, mu_out);
     else if (role == 2) { if (HAS_MU) run_role<HAS_MU, 2>(c, fd, mu_in, q, mu_out); else run_feeder<2>(c, fd); }
     else run_feeder<HAS_MU ? 0 : 1>(c, fd);
+    RLVD_CTA_STAMP(3, 0)
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    RLVD_CTA_STAMP(4, 0)
+    if (warp == 3) {                                  // the allocating warp
         tc_fence_after();
         tmem_dealloc(tmem, TM_COLS);
     }
@@ -1013,26 +1137,33 @@ int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, 
     const float kappa = e->w.filt_kappa[layer];
     // both variants request the HAS_MU footprint: one CTA per SM (each CTA owns all 512 TMEM columns)
     const size_t smem = stream_smem_bytes<true>(max_struct_nodes) < 120 * 1024 ? 120 * 1024 : stream_smem_bytes<true>(max_struct_nodes);
+    // structures between a CTA and the one that follows it on the same SM (grids of more than one wave only)
+    const int pf_ahead = e->stream_prefetch > 0 && n_struct * NSLICE > e->sm_count ? (e->sm_count + NSLICE - 1) / NSLICE : 0;
     long long* dbg = nullptr;
 #ifdef RLVD_TIMELINE   // in-kernel timeline of block 0 / pipeline 0 (build with RLVD_EXTRA_NVCC_FLAGS=-DRLVD_TIMELINE)
     static long long* dbg_buf = nullptr;
     static int dbg_calls = 0;
-    if (dbg_buf == nullptr) { cudaMalloc(&dbg_buf, 64 * 4 * 10 * 8); cudaMemset(dbg_buf, 0, 64 * 4 * 10 * 8); }
+    if (dbg_buf == nullptr) { cudaMalloc(&dbg_buf, (64 * 4 * 10 + 16) * 8); cudaMemset(dbg_buf, 0, (64 * 4 * 10 + 16) * 8); }
     dbg = dbg_buf;
 #endif
     Span sp(e, s, gate != nullptr ? -1 : FAM_EDGE);     // a gated launch is the (normally skipped) layer-0 fallback
     if (mu_in == nullptr)
         edge_stream_kernel<false><<<n_struct * NSLICE, ST_THREADS, smem, s>>>(
-            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, nullptr, q, mu_out, nullptr, gate, gate_value);
+            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, nullptr, q, mu_out, nullptr, gate, gate_value, n_struct, 0, 0);
     else
         edge_stream_kernel<true><<<n_struct * NSLICE, ST_THREADS, smem, s>>>(
-            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, mu_in, q, mu_out, dbg, gate, gate_value);
+            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, mu_in, q, mu_out, dbg, gate, gate_value, n_struct, pf_ahead, e->stream_prefetch);
 #ifdef RLVD_TIMELINE
     if (mu_in != nullptr && ++dbg_calls == 20) {
         cudaStreamSynchronize(s);
-        static long long h[64 * 4 * 10];
+        static long long h[64 * 4 * 10 + 16];
         cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
         const long long t0 = h[0];
+        for (int b = 0; b < 2; ++b) {
+            const long long* w = h + 64 * 4 * 10 + 8 * b;
+            printf("cta %s | barriers initialised +%lld | TMEM allocated +%lld | feeders released +%lld | table staged +%lld | roles done +%lld | exit +%lld cycles\n",
+                   b == 0 ? "0" : "6001", w[5] - w[0], w[6] - w[0], w[1] - w[0], w[2] - w[0], w[3] - w[0], w[4] - w[0]);
+        }
         for (int t = 0; t < 40; ++t) {
             printf("tile %2d |", t);
             for (int r = 0; r < 4; ++r) {

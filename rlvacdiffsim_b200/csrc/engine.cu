@@ -857,6 +857,11 @@ int rlvd_set_option(rlvd_engine* e, const char* name, int32_t value) {
         e->hit_key_pos = nullptr;
         return 0;
     }
+    if (strcmp(name, "stream_prefetch") == 0) {
+        RLVD_CHECK(value >= 0 && value <= 7, "stream_prefetch: 0 (off) .. 7 eighths");
+        e->stream_prefetch = value;
+        return 0;
+    }
     if (strcmp(name, "prune_final_mu") == 0) {
         e->prune_final_mu = value != 0;
         return 0;
