@@ -850,20 +850,21 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
         __trap();
     }
 
-    // Prologue.  The feeder warps only need the weight operand in TMEM, the consuming warps only need the node table:
-    //   all warps      : warp 3 (pipeline 0's feeder) initialises the mbarriers and allocates TMEM, then ONE block barrier
-    //                    publishes both (~2.5 k cycles).  It comes BEFORE the staging loads: measured, a feeder's
-    //                    mbarrier.init / L2 loads issued under the 576-thread staging flood wait 2-5 k cycles in the LSU queue.
-    //   feeder warps   : the feeders of pipelines 0..3 sit in TMEM lane quarters 3, 2, 1, 0 (pipe_rot); each loads its quarter
-    //                    of the operand (the first two rotations are requested before the block barrier) and stores it;
-    //                    named barrier 1 (feeder warps only) then releases the feeders: the first tiles' copies and MMAs run
-    //                    under the table staging.
+    // Prologue.  The feeder warps only need the weight operand in TMEM, the consuming warps only need the node table.
+    //   feeder warps   : the feeders of pipelines 0..3 sit in TMEM lane quarters 3, 2, 1, 0 (pipe_rot) and each owns its quarter
+    //                    of the operand.  They request rotations 0-1 from L2 at once; warp 3 allocates TMEM while pipeline 1's
+    //                    feeder initialises the mbarriers; named barrier 1 hands the base address over; rotations 0-1 are
+    //                    stored and rotations 2-3 requested.  Only then does ONE block barrier let the consuming warps start:
+    //                    measured, a feeder's mbarrier.init / L2 loads issued under the 576-thread staging flood wait 2-5 k
+    //                    cycles in the LSU queue.  Second store, named barrier 1 again, and the first tiles' copies and MMAs
+    //                    run under the table staging (feeders released at ~4.8 k cycles, first accumulator waiting for the
+    //                    consumers when the table is ready).
     //   consuming warps: stage the node table (nothing else) and meet at named barrier 2.
     // The waves of this kernel run in lockstep (equal work per CTA), so all 148 SMs stage at once and the 196 KB per CTA come
-    // at the HBM rate (10-11 k cycles; 4.5 k when a single SM stages: scripts/probes/stage_rate.cu) unless the previous wave
-    // asked L2 for them (Feed::pf below).
+    // at the HBM rate (10-11 k cycles; 4.5 k when a single SM stages, 4.0 k from L2: scripts/probes/stage_rate.cu) unless the
+    // previous wave asked L2 for them (Feed::pf below: 7 k).
     // (Round 2, first form: warps 0-3 loaded the operand before staging their share of the table: feeders released at
-    // 9-12 k cycles, table staged at 15-21 k of a ~175 k-cycle CTA; profiles/timeline_stream_r02.txt.)
+    // 9-12 k cycles, table staged at 15-21 k, CTA 173 k cycles; now 4.8 k / 10 k / 164 k.  profiles/timeline_stream_r02.txt)
     const int pipe_w = warp >> 2;
     const int role_w = ((warp & 3) + pipe_rot(pipe_w)) & 3;
     const bool feeds = role_w == 3 || (!HAS_MU && role_w == 2);
@@ -885,43 +886,55 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
 #pragma unroll
                 for (int c8 = 0; c8 < 8; ++c8) w[r2 * 8 + c8] = __ldg(wrow + (size_t)r2 * 128 * 8 + c8);
         }
+        // warp 3 allocates TMEM, pipeline 1's feeder initialises the mbarriers meanwhile; named barrier 1 hands the base
+        // address to the feeders
+        if (role_w == 3 && pipe_w == 1 && lane == 0) {
+            for (int p = 0; p < NPIPE; ++p)
+                for (int k = 0; k < 2; ++k) {
+                    mbar_init(&S->b_full[p][k], 1);
+                    mbar_init(&S->mma_done[p][k], 1);
+                    mbar_init(&S->acc_free[p][k], NROLE);
+                }
+            fence_mbar_init();
+        }
         if (warp == 3) {
-            if (lane == 0) {
-                for (int p = 0; p < NPIPE; ++p)
-                    for (int k = 0; k < 2; ++k) {
-                        mbar_init(&S->b_full[p][k], 1);
-                        mbar_init(&S->mma_done[p][k], 1);
-                        mbar_init(&S->acc_free[p][k], NROLE);
-                    }
-                fence_mbar_init();
-            }
-            __syncwarp();
             tmem_alloc(&S->tmem_base, TM_COLS);
             tc_fence_before();
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(FEED_THREADS) : "memory");
+        tc_fence_after();
+        RLVD_CTA_STAMP(5, 3)
+        const uint32_t tmem_f = S->tmem_base;
+        // ---- weight operand -> TMEM in its four row rotations (lane = filter row; 64 fp16 = 32 columns each): rotations
+        // 0-1 stored, rotations 2-3 requested, all before the block barrier releases the staging loads
+        if (loads_a) {
+#pragma unroll
+            for (int r2 = 0; r2 < 2; ++r2) {
+                const uint32_t ta = tmem_f + ((uint32_t)(quarter * 32) << 16) + TM_A + r2 * 32;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    const uint4 w0 = w[r2 * 8 + 2 * c8], w1 = w[r2 * 8 + 2 * c8 + 1];
+                    const uint32_t v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    tmem_st8(ta + c8 * 8, v);
+                }
+            }
+#pragma unroll
+            for (int r2 = 0; r2 < 2; ++r2)
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) w[r2 * 8 + c8] = __ldg(wrow + (size_t)(2 + r2) * 128 * 8 + c8);
         }
         __syncthreads();          // barriers and TMEM base published to the whole CTA before the staging loads flood the LSU
         tc_fence_after();
         RLVD_CTA_STAMP(6, 3)
-        const uint32_t tmem_f = S->tmem_base;
-        // ---- weight operand -> TMEM in its four row rotations (lane = filter row; 64 fp16 = 32 columns each)
         if (loads_a) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int r2 = 0; r2 < 2; ++r2) {
+                const uint32_t ta = tmem_f + ((uint32_t)(quarter * 32) << 16) + TM_A + (2 + r2) * 32;
 #pragma unroll
-                for (int r2 = 0; r2 < 2; ++r2) {
-                    const uint32_t ta = tmem_f + ((uint32_t)(quarter * 32) << 16) + TM_A + (half * 2 + r2) * 32;
-#pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {
-                        const uint4 w0 = w[r2 * 8 + 2 * c8], w1 = w[r2 * 8 + 2 * c8 + 1];
-                        const uint32_t v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                        tmem_st8(ta + c8 * 8, v);
-                    }
-                }
-                if (half == 0) {
-#pragma unroll
-                    for (int r2 = 0; r2 < 2; ++r2)
-#pragma unroll
-                        for (int c8 = 0; c8 < 8; ++c8) w[r2 * 8 + c8] = __ldg(wrow + (size_t)(2 + r2) * 128 * 8 + c8);
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    const uint4 w0 = w[r2 * 8 + 2 * c8], w1 = w[r2 * 8 + 2 * c8 + 1];
+                    const uint32_t v[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    tmem_st8(ta + c8 * 8, v);
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -1161,7 +1174,7 @@ int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, 
         const long long t0 = h[0];
         for (int b = 0; b < 2; ++b) {
             const long long* w = h + 64 * 4 * 10 + 8 * b;
-            printf("cta %s | barriers initialised +%lld | TMEM allocated +%lld | feeders released +%lld | table staged +%lld | roles done +%lld | exit +%lld cycles\n",
+            printf("cta %s | TMEM base at the feeders +%lld | block barrier +%lld | feeders released +%lld | table staged +%lld | roles done +%lld | exit +%lld cycles\n",
                    b == 0 ? "0" : "6001", w[5] - w[0], w[6] - w[0], w[1] - w[0], w[2] - w[0], w[3] - w[0], w[4] - w[0]);
         }
         for (int t = 0; t < 40; ++t) {

@@ -18,7 +18,7 @@ __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta
 
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1) probe(const float* __restrict__ x, const float* __restrict__ mu, int n_struct, int reps,
-                                                    long long* out, float* sink) {
+                                                    long long* out, float* sink, int prefetch) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     const int tid = threadIdx.x;
@@ -33,6 +33,19 @@ __global__ void __launch_bounds__(THREADS, 1) probe(const float* __restrict__ x,
         const int b = (blockIdx.x * reps + r) * 977 % (n_struct * 4);
         const int g = b >> 2, slice = b & 3;
         const size_t node0 = (size_t)g * N;
+        if (prefetch) {          // ask L2 for the structure's rows (16 chunks, like the kernel), then idle ~30 k cycles
+            if (tid < 16 && slice == (tid & 3)) {}
+            if (tid < 16) {
+                const uint32_t total = (uint32_t)N * 3u * F * 4u;
+                const uint32_t per = ((total + 7u) / 8u + 127u) & ~127u;
+                const uint32_t off = (uint32_t)(tid & 7) * per;
+                const uint8_t* base = reinterpret_cast<const uint8_t*>(tid < 8 ? x : mu) + node0 * 3 * F * 4;
+                const uint32_t bytes = total - off < per ? total - off : per;
+                if (off < total) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(bytes) : "memory");
+            }
+            const long long w0 = clock64();
+            while (clock64() - w0 < 30000) {}
+        }
         __syncthreads();
         const long long t0 = clock64();
         if (tid < STAGE) {
@@ -156,11 +169,11 @@ __global__ void __launch_bounds__(THREADS, 1) probe(const float* __restrict__ x,
 }
 
 template <int MODE>
-void run(const float* x, const float* mu, int n_struct, int grid, long long* d_out, float* sink, const char* what) {
+void run(const float* x, const float* mu, int n_struct, int grid, long long* d_out, float* sink, const char* what, int prefetch = 0) {
     const int smem = 226 * 1024 - 64;
     cudaFuncSetAttribute(probe<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int reps = 24;
-    for (int it = 0; it < 2; ++it) probe<MODE><<<grid, THREADS, smem>>>(x, mu, n_struct, reps, d_out, sink);
+    for (int it = 0; it < 2; ++it) probe<MODE><<<grid, THREADS, smem>>>(x, mu, n_struct, reps, d_out, sink, prefetch);
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { printf("mode %d: %s\n", MODE, cudaGetErrorString(err)); return; }
     long long h[148];
@@ -188,5 +201,8 @@ int main() {
         run<4>(x, mu, n_struct, grid, d_out, sink, "2 items in flight, 8-byte loads");
         run<3>(x, mu, n_struct, grid, d_out, sink, "bulk copies (5 x 128 B per node) + x_m via registers");
     }
+    run<1>(x, mu, 48, 148, d_out, sink, "2 in flight, 48 structures (L2-resident)");
+    run<1>(x, mu, n_struct, 148, d_out, sink, "2 in flight, rows prefetched to L2 30 k cycles before", 1);
+    run<1>(x, mu, n_struct, 8, d_out, sink, "2 in flight, rows prefetched to L2 30 k cycles before", 1);
     return 0;
 }
