@@ -612,8 +612,8 @@ __device__ __forceinline__ void run_feeder(const PipeCtx& c, const Feed& fd) {
         st_wait(&S->mma_done[pipe][1], 0);
         feed_copy(c, fd, 3);
     }
-#pragma unroll 1
     const int pf_t = (n_tiles * c.pf_eighths) >> 3;
+#pragma unroll 1
     for (int t = 0; t + 2 < n_tiles; ++t) {
         const uint32_t bi = (uint32_t)t & 1u;
         if (t == pf_t && fd.pf_bytes != 0) prefetch_l2(fd.pf, fd.pf_bytes);

@@ -294,8 +294,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                         for (int u = 0; u < 16; ++u) {
                             const float v = fmaf(__uint_as_float(v1[u]), 1.0f / 2048.0f, __uint_as_float(v0[u]));
                             const float w = fmaf(__uint_as_float(w1[u]), 1.0f / 2048.0f, __uint_as_float(w0[u]));
+#ifdef RLVD_MIXRED_NOSHFL   // ceiling experiment (wrong numbers): what the four shuffles per value cost
+                            const float vy = v, vz = v, wy = w, wz = w;
+#else
                             const float vy = __shfl_down_sync(0xffffffffu, v, 1), vz = __shfl_down_sync(0xffffffffu, v, 2);
                             const float wy = __shfl_down_sync(0xffffffffu, w, 1), wz = __shfl_down_sync(0xffffffffu, w, 2);
+#endif
                             nr[u] = sqrtf(fmaf(vz, vz, fmaf(vy, vy, v * v)) + a.eps);
                             dt[u] = fmaf(vz, wz, fmaf(vy, wy, v * w));
                         }
