@@ -9,10 +9,11 @@
 // edge_pack_kernel (once per call, one CTA per structure)
 //   Splits the structure's receivers into NPIPE contiguous ranges of equal edge-group count and writes, per range,
 //   a stream of 32-slot tiles.  Slots come in receiver-aligned groups of 8 (short rows padded with zero filters).
-//   A tile is 4096 B of MMA operand + 432 B of meta:
+//   A tile is 4096 B of MMA operand + 464 B of meta:
 //     operand  [32 slots][64 fp16], K-major core-matrix layout:  b_hi[21] | b_lo[21] | b_hi[21] | 0
 //              b = 2^10 * {phi_k(d) * fcut(d) (k < 20), fcut(d)}, split b = b_hi + b_lo in fp16 (22 significant bits)
-//     meta     j[32] u8 (local sender index) | new_receiver[4] u8 (one per group) | pad | dir_x[32] | dir_y[32] | dir_z[32]
+//     meta     4*j[32] u16 (local sender index, pre-scaled for the dp2a gather address) | new_receiver[4] u8 (one per group) | pad |
+//              dir_x[32] | dir_y[32] | dir_z[32]
 //
 // edge_stream_kernel (per layer; CTA = one structure x one 32-channel slice; 1 CTA per SM)
 //   The slice of the structure's node table lives in shared memory (gathers never leave the SM):
