@@ -10,15 +10,17 @@
 // (the dropped A_lo·B_lo term is 2^-22 relative).  Scaling the low parts by 2^11 keeps them in fp16's normal
 // range.  Three kind::f16 passes cost 1.5 tf32-pass equivalents and 4 bytes of shared memory per element.
 //
-// Kernel shape (persistent, one CTA per SM, 320 threads, 224 KB of shared memory):
-//   warps 0-7  stage the next 128-row x 128-k fp32 A phase with fully coalesced cp.async (prefetched one phase
+// Kernel shape (persistent, one CTA per SM, 576 threads, 224 KB of shared memory; EW = 16 stager / epilogue warps — four per
+// TMEM lane quarter, each draining 32 of an accumulator's 128 columns; -DRLVD_TC_EPI_WARPS=8 is the round-1 shape, warps 8 / 9
+// below are then the producer and the issuer):
+//   warps 0-15 stage the next 128-row x 128-k fp32 A phase with fully coalesced cp.async (prefetched one phase
 //              ahead, overlapping the MMAs and the epilogue), split it into fp16 hi/lo and write it in the
 //              canonical no-swizzle K-major core-matrix layout; later drain TMEM (tcgen05.ld, thread = row),
 //              apply bias/SiLU, transpose through a swizzled staging tile and store Y with coalesced 16-byte
 //              stores
-//   warp  8    producer: 1-D bulk-TMA copies (cp.async.bulk → mbarrier complete_tx) of pre-formatted 32 KB
+//   warp  16   producer: 1-D bulk-TMA copies (cp.async.bulk → mbarrier complete_tx) of pre-formatted 32 KB
 //              weight stages [128 out-rows x 64 k, hi | lo] through a 2-deep ring
-//   warp  9    allocates TMEM (512 columns = 2 x (D0,D1) x 128); one elected lane issues tcgen05.mma and the
+//   warp  17   allocates TMEM (512 columns = 2 x (D0,D1) x 128); one elected lane issues tcgen05.mma and the
 //              tcgen05.commit arrivals that free weight stages / A buffers and publish accumulators
 // K = 256 (the [q | n] concatenation of the intra-atomic net) runs as two 128-k phases through the same A
 // buffers, accumulating in TMEM.  Every mbarrier wait is bounded (trap, never hang).
@@ -52,7 +54,17 @@ constexpr int TC_HALF_STAGE = TC_N * TC_KS * 2;        // 16384 B: one of hi / l
 constexpr int TC_STAGE_BYTES = 2 * TC_HALF_STAGE;      // 32768 B
 constexpr int CORE_LBO = 2048;                         // bytes between K-adjacent core matrices
 constexpr int CORE_SBO = 128;                          // bytes between 8-row groups
-constexpr int TC_THREADS = 320;                       // 8 stager/epilogue warps + producer + MMA issuer
+#ifndef RLVD_TC_EPI_WARPS
+#define RLVD_TC_EPI_WARPS 16
+#endif
+constexpr int EW = RLVD_TC_EPI_WARPS;                 // stager / epilogue warps: 8 or 16 (2 or 4 per TMEM lane quarter)
+constexpr int ET = EW * 32;                           // ... their threads
+constexpr int HQ = EW / 4;                            // column partitions of an accumulator per lane quarter
+constexpr int NSEG = 4 / HQ;                          // 32-column segments of a 128-column accumulator per warp
+constexpr int MIXC = 64 / HQ;                         // V (and W) columns of a mix-reduce block per warp
+constexpr int CPT = 16 / (ET / 128);                  // core columns (8 k each) one converter thread writes per phase
+static_assert(EW == 8 || EW == 16, "tc_linear: 8 or 16 epilogue warps");
+constexpr int TC_THREADS = ET + 64;                   // + weight producer warp + MMA issuer warp
 constexpr uint32_t IDESC_F16_M128_N128 = (1u << 4) | (16u << 17) | (8u << 24);   // fp32 accum, fp16 A/B, K-major
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -90,7 +102,7 @@ struct TcSmem {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory"); }
 
 // Global row of tile row `row`: plain tiles are 128 consecutive rows; mix-reduce tiles hold 40 nodes as
 // 4 warps x 30 rows (+2 idle rows per warp), global row = 120*tile + 30*warp + lane.
@@ -113,8 +125,8 @@ __device__ __forceinline__ void stage_A_async(const LinearArgs& a, int tile, int
     int ld = a.lda, k0 = phase * 128;
     if (a.A2 != nullptr && k0 >= a.K1) { base = a.A2; ld = a.lda2; k0 -= a.K1; }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int id = i * 256 + t, row = id >> 5, lc = id & 31;
+    for (int i = 0; i < 4096 / ET; ++i) {
+        const int id = i * ET + t, row = id >> 5, lc = id & 31;
         bool live;
         const int64_t m = tile_row(a, tile, row, live);
         const float* src = base + (live ? m * ld : 0) + k0 + lc * 4;
@@ -151,14 +163,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
 
     if (tid == 0) {
         for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&S->full[s], 1); mbar_init(&S->empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&S->acc_full[b], 1); mbar_init(&S->acc_empty[b], 256); }
-        mbar_init(&S->a_ready, 256);
+        for (int b = 0; b < 2; ++b) { mbar_init(&S->acc_full[b], 1); mbar_init(&S->acc_empty[b], ET); }
+        mbar_init(&S->a_ready, ET);
         mbar_init(&S->a_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < a.N; i += TC_THREADS) bias_s[i] = a.bias != nullptr ? __ldg(a.bias + i) : 0.f;
     for (int i = tid; i < (two ? a.N2 : 0); i += TC_THREADS) bias2_s[i] = a.bias2 != nullptr ? __ldg(a.bias2 + i) : 0.f;
-    if (warp == 9) {
+    if (warp == EW + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S->tmem_base)),
                      "r"(512u)
                      : "memory");
@@ -169,10 +181,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
     tc_fence_after();
     const uint32_t tmem = S->tmem_base;
 
-    if (warp < 8) {
-        // ================= A stager/converter + epilogue (256 threads) =================
+    if (warp < EW) {
+        // ================= A stager/converter + epilogue (ET threads) =================
         const int t = tid;
-        const int r = t & 127, khalf = t >> 7;               // converter role: row r, core columns khalf*8..+8
+        const int r = t & 127, khalf = t >> 7;               // converter role: row r, core columns khalf*CPT..+CPT
         const int q = warp & 3, h = warp >> 2;               // epilogue role: TMEM lane quarter q, column half h
         const int er = q * 32 + lane;                        // epilogue row = TMEM lane
 
@@ -190,8 +202,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
             epi_barrier();                                   // everyone's cp.async data is visible
             if (tid == 0) { TCS(0, 3) }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int kc = khalf * 8 + c;
+            for (int c = 0; c < CPT; ++c) {
+                const int kc = khalf * CPT + c;
                 const float4 v0 = *reinterpret_cast<const float4*>(Ast + r * 512 + (((2 * kc) ^ (r & 7)) << 4));
                 const float4 v1 = *reinterpret_cast<const float4*>(Ast + r * 512 + (((2 * kc + 1) ^ (r & 7)) << 4));
                 uint4 H, L;
@@ -225,14 +237,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                 tc_fence_after();
                 if (tid == 0) { TCS(0, 11) }
 #pragma unroll 1
-                for (int sgm = 0; sgm < 2; ++sgm) {
-                    const int c0 = 64 * sgm + 32 * h;
+                for (int sgm = 0; sgm < NSEG; ++sgm) {
+                    const int c0 = (sgm * HQ + h) * 32;
                     const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + c0;
                     uint32_t d0[32], d1[32];
                     tmem_ld32(t0, d0);
                     tmem_ld32(t0 + 128, d1);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (sgm == 1) {
+                    if (sgm == NSEG - 1) {
                         tc_fence_before();
                         mbar_arrive(&S->acc_empty[buf]);
                     }
@@ -280,8 +292,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                     const bool owner = live_row && (lane % 3) == 0;      // lane of component 0 writes the node's nrm / vw
                     const int64_t node = m_row / 3;
 #pragma unroll 1
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const int c0 = 32 * h + 16 * hf;
+                    for (int hf = 0; hf < MIXC / 16; ++hf) {
+                        const int c0 = MIXC * h + 16 * hf;
                         const uint32_t tV = tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + c0;
                         uint32_t v0[16], v1[16], w0[16], w1[16];
                         tmem_ld16(tV, v0);
@@ -319,18 +331,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                         const int u = lane & 3, rq = lane >> 2;
 #pragma unroll 1
                         for (int hl = 0; hl < 2; ++hl) {
-                            const uint32_t t1 = tmem + ((uint32_t)(q * 32 + 16 * hl) << 16) + buf * 256 + 64 + 32 * h;
+                            const uint32_t t1 = tmem + ((uint32_t)(q * 32 + 16 * hl) << 16) + buf * 256 + 64 + MIXC * h;
                             uint32_t d0[16], d1[16];
-                            tmem_ld_16x256b_x4(t1, d0);
-                            tmem_ld_16x256b_x4(t1 + 128, d1);
+                            if (MIXC == 32) {
+                                tmem_ld_16x256b_x4(t1, d0);
+                                tmem_ld_16x256b_x4(t1 + 128, d1);
+                            } else {
+                                tmem_ld_16x256b_x2(t1, d0);
+                                tmem_ld_16x256b_x2(t1 + 128, d1);
+                            }
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                             for (int rh = 0; rh < 2; ++rh) {
                                 bool live;
                                 const int64_t m = tile_row(a, tile, q * 32 + 16 * hl + 8 * rh + rq, live);
-                                float* yrow = a.Y + m * a.ldy + 64 * nb + 32 * h + 2 * u;
+                                float* yrow = a.Y + m * a.ldy + 64 * nb + MIXC * h + 2 * u;
 #pragma unroll
-                                for (int g = 0; g < 4; ++g) {
+                                for (int g = 0; g < MIXC / 8; ++g) {
                                     const float w0v = fmaf(__uint_as_float(d1[4 * g + 2 * rh]), 1.0f / 2048.0f, __uint_as_float(d0[4 * g + 2 * rh]));
                                     const float w1v = fmaf(__uint_as_float(d1[4 * g + 2 * rh + 1]), 1.0f / 2048.0f, __uint_as_float(d0[4 * g + 2 * rh + 1]));
                                     if (live) *reinterpret_cast<float2*>(yrow + 8 * g) = make_float2(w0v, w1v);
@@ -352,14 +369,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                     tmem_ld_16x256b_x4(t0 + 128, dd[0] + 16);
                 }
 #pragma unroll
-                for (int st = 0; st < 4; ++st) {
+                for (int st = 0; st < 2 * NSEG; ++st) {
                     const int sgm = st >> 1, hl = st & 1;
-                    const int c0 = 64 * sgm + 32 * h;        // first column (inside the N-block) of this warp's segment
+                    const int c0 = (sgm * HQ + h) * 32;      // first column (inside the N-block) of this warp's segment
                     const int col0 = nb * TC_N + c0;
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (st < 3) {
+                    if (st < 2 * NSEG - 1) {
                         const int sg2 = (st + 1) >> 1, hl2 = (st + 1) & 1;
-                        const uint32_t t1 = tmem + ((uint32_t)(q * 32 + 16 * hl2) << 16) + buf * 256 + 64 * sg2 + 32 * h;
+                        const uint32_t t1 = tmem + ((uint32_t)(q * 32 + 16 * hl2) << 16) + buf * 256 + (sg2 * HQ + h) * 32;
                         tmem_ld_16x256b_x4(t1, dd[(st + 1) & 1]);
                         tmem_ld_16x256b_x4(t1 + 128, dd[(st + 1) & 1] + 16);
                     } else {                                 // all TMEM reads of this accumulator are done
@@ -391,7 +408,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
             }
         }
         if (bad && a.status != nullptr) atomicOr(a.status, 1);
-    } else if (warp == 8) {
+    } else if (warp == EW) {
         // ================= weight-stage producer =================
         if (lane == 0) {
             uint32_t cnt = 0;
@@ -484,7 +501,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == EW + 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
