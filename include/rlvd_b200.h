@@ -275,7 +275,11 @@ int  rlvd_set_hyper(rlvd_engine* e, const char* name, double value);
  * "sliced_edge" (1 = structure-resident edge stream kernel, edge_stream.cu, for structures of <= 256 atoms; 0 = general),
  * "fuse_mlp" (1 = each Linear-SiLU-Linear context net is one launch with the hidden tile kept on the SM),
  * "fuse_mix" (1 = the |mu_V| and <mu_V, mu_W> reductions run in the mu_channel_mix GEMM epilogue),
- * "layer0_sums" (1 = layer 0 from species-resolved radial sums, see rlvd_set_species; 0 = per-edge kernels). */
+ * "layer0_sums" (1 = layer 0 from species-resolved radial sums, see rlvd_set_species; 0 = per-edge kernels),
+ * "prune_final_mu" (1 = a q-only call skips the last mixing block's mu update; same q bit for bit),
+ * "hit_words" (1 = the CSR fill pass walks the hit bits of the count pass; same CSR bit for bit),
+ * "stream_prefetch" (0 = off, 1..7 = the edge stream kernel asks L2 for the next wave's node rows after that many
+ *   eighths of a CTA's tiles; results do not depend on it). */
 int  rlvd_set_option(rlvd_engine* e, const char* name, int32_t value);
 
 /* Device status word since the last call (synchronises `stream`, then clears it).  bit 0: an operand of a tensor-core GEMM
