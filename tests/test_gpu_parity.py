@@ -385,6 +385,30 @@ def test_full_size_batch_properties(model):
             assert int(np.argmax(full[r])) == int(np.argmax(ref))
 
 
+def test_stream_prefetch_option_does_not_change_results(model):
+    """The edge stream kernel's L2 prefetch of the next wave's node rows (engine option ``stream_prefetch``, active once
+    a batch has more CTAs than SMs) only moves data into L2 earlier: Q-values are bitwise the same with it off, at its
+    default and at another setting."""
+    R = 4                                                      # 96 structures x 4 slices = 384 CTAs > 148 SMs
+    reps = [make_crconi_supercell(4, seed=2000 + s, jitter=0.02) for s in range(R)]
+    spaces = [rb.get_action_space(r, 3.528) for r in reps]
+    qp = {"alpha": 0.0, "beta": 1.0, "dqn": True, "temperature": 700.0}
+    eng = model._engine_for(torch.device("cuda", 0))
+    scorer = ReplicaScorer(model, 0)
+    out = {}
+    try:
+        for v in (0, 7, 3):
+            eng.set_option("stream_prefetch", v)
+            out[v] = scorer.score(reps, spaces, qp)
+    finally:
+        eng.set_option("stream_prefetch", 7)
+    for v in (0, 3):
+        for r in range(R):
+            assert np.array_equal(out[v][r], out[7][r])
+    with pytest.raises(RuntimeError):
+        eng.set_option("stream_prefetch", 8)
+
+
 def test_select_action_drop_in_seeded(model):
     """simulator.py:45-103 semantics: same Q as the golden, same seeded draw as the oracle's probabilities."""
     g = load_gold("demo")
