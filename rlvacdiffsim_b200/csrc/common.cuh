@@ -148,6 +148,7 @@ struct rlvd_engine {
     bool fuse_mix = true;           // nrm / vw reductions inside the mu_channel_mix GEMM epilogue (tc_linear.cu mixred mode): same
                                     // step time as GEMM + reduction kernel within run-to-run noise, 4.8 GB less DRAM traffic per step
     bool fuse_mlp = true;           // Linear -> SiLU -> Linear pairs as one tcgen05 launch (tc_linear.cu two-layer mode)
+    int stream_split = 1;           // CTAs per (structure, channel slice) of the edge stream kernel for the batch packed last (launch_edge_pack)
     int stream_prefetch = 7;        // edge_stream_kernel: L2 prefetch of the node rows the SM's next CTA will stage, issued after this many eighths of a CTA's tiles (0 = off)
     bool prune_final_mu = true;     // callers that take q only (d_mu == NULL): the last mixing block skips everything that
                                     // only feeds mu's update (W store, the b block of the intra-atomic net, mu += b W)

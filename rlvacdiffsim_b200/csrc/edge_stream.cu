@@ -15,7 +15,8 @@
 //     meta     4*j[32] u16 (local sender index, pre-scaled for the dp2a gather address) | new_receiver[4] u8 (one per group) | pad |
 //              dir_x[32] | dir_y[32] | dir_z[32]
 //
-// edge_stream_kernel (per layer; CTA = one structure x one 32-channel slice; 1 CTA per SM)
+// edge_stream_kernel (per layer; CTA = one structure x one 32-channel slice; 1 CTA per SM; batches of less than ~two waves put
+// S <= 3 CTAs on a (structure, slice), each with NPIPE of the structure's NPIPE x S receiver ranges)
 //   The slice of the structure's node table lives in shared memory (gathers never leave the SM):
 //     row(j) = kappa*x_q | kappa*x_R | kappa*x_m*mu_x | kappa*x_m*mu_y | kappa*x_m*mu_z        (5 x 32 fp32)
 //   Filters run on tcgen05 with the weight operand resident in TMEM (A rows = dq | dmuR | dmumu | dmumu filters of
@@ -67,6 +68,8 @@ constexpr int META_FLAG = 64;
 constexpr int TILE_BYTES = TILE_B + META; // 4560
 constexpr int MAXN = 256;
 constexpr int ST_THREADS = NPIPE * 128;
+constexpr int MAX_SPLIT = 3;              // small batches: a structure's receivers are spread over up to 3 CTAs per channel slice
+constexpr int MAXR = NPIPE * MAX_SPLIT;   // receiver ranges per structure (NPIPE per CTA)
 constexpr int B_SCALE_LOG2 = 10;
 constexpr int TM_D = 0;                   // TMEM columns: accumulator buffer b of pipe p at (2p+b)*32
 constexpr int TM_A = NPIPE * 2 * TE;      // 4 row rotations of the weight operand (64 fp16 = 32 columns each)
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
                                                         uint8_t* __restrict__ tiles, int4* __restrict__ pipe_info,
                                                         int* __restrict__ err_flag, int* __restrict__ status_word, const int* __restrict__ Z,
                                                         const int* __restrict__ z2s, float* __restrict__ l0A, int mode,
-                                                        int n_splits) {
+                                                        int n_splits, int NR /* receiver ranges per structure: NPIPE x stream split */) {
     // mode 0: allocate tiles and fill them (one CTA per structure).  Small batches run mode 1 (allocation only) and then
     // mode 2 with grid (n_struct, n_splits): CTA (g, y) fills the receivers of warp-stride class y; every CTA repeats the
     // (cheap, deterministic) scan and takes the tile bases mode 1 published in pipe_info.
@@ -258,12 +261,12 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
     __shared__ float spos[3 * MAXN];      // the structure's positions and species: senders are gathered from here
     __shared__ int8_t ssp[MAXN];
     __shared__ int wsum[8];
-    __shared__ int bnd[NPIPE + 1];        // receiver range boundaries of the pipelines
-    __shared__ int tbeg[NPIPE + 1];       // first tile of each pipeline (absolute)
+    __shared__ int bnd[MAXR + 1];         // receiver range boundaries of the pipelines
+    __shared__ int tbeg[MAXR + 1];        // first tile of each pipeline (absolute)
     const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int node0 = __ldg(node_ptr + g), n = __ldg(node_ptr + g + 1) - node0;
     if (n <= 0) {
-        if (tid < NPIPE && mode != 2) pipe_info[g * NPIPE + tid] = make_int4(0, 0, 0, 0);
+        if (tid < NR && mode != 2) pipe_info[g * NR + tid] = make_int4(0, 0, 0, 0);
         return;
     }
     for (int t = tid; t < 3 * n; t += 256) spos[t] = __ldg(pos + 3 * (int64_t)node0 + t);
@@ -297,12 +300,12 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
     __syncthreads();
     const int G = goff[256];   // threads >= n contributed 0, so goff[i] == G for i >= n
     // ---- receiver ranges with (nearly) equal group counts; tile allocation
-    if (tid <= NPIPE) {
+    if (tid <= NR) {
         int b;
         if (tid == 0) b = 0;
-        else if (tid == NPIPE) b = n;
+        else if (tid == NR) b = n;
         else {
-            const int target = (int)(((long long)tid * G) / NPIPE);
+            const int target = (int)(((long long)tid * G) / NR);
             int lo = 0, hi = n;                       // smallest i in [0, n] with goff[i] >= target
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
@@ -315,32 +318,29 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
     __syncthreads();
     if (tid == 0 && mode == 2) {
         int ok = 0;
-        for (int p = 0; p < NPIPE; ++p) {
-            const int4 pi = pipe_info[g * NPIPE + p];
+        for (int p = 0; p < NR; ++p) {
+            const int4 pi = pipe_info[g * NR + p];
             tbeg[p] = pi.x;
             ok |= pi.y > 0 ? 1 : 0;
         }
-        tbeg[NPIPE] = ok;
+        tbeg[MAXR] = ok;
     }
     if (tid == 0 && mode != 2) {
         int total = 0;
-        int tl[NPIPE];
-        for (int p = 0; p < NPIPE; ++p) {
-            tl[p] = (goff[bnd[p + 1]] - goff[bnd[p]] + 3) >> 2;
-            total += tl[p];
-        }
+        for (int p = 0; p < NR; ++p) total += (goff[bnd[p + 1]] - goff[bnd[p]] + 3) >> 2;
         int base = atomicAdd(tile_counter, total);
         bool ok = base + total <= tile_capacity;
         if (!ok) { atomicExch(err_flag, 1); atomicOr(status_word, 2); }    // engine status bit 1: results of this call are invalid
-        for (int p = 0; p < NPIPE; ++p) {
+        for (int p = 0; p < NR; ++p) {
+            const int tl = (goff[bnd[p + 1]] - goff[bnd[p]] + 3) >> 2;
             tbeg[p] = base;
-            pipe_info[g * NPIPE + p] = make_int4(base, ok ? tl[p] : 0, bnd[p], bnd[p + 1]);
-            base += tl[p];
+            pipe_info[g * NR + p] = make_int4(base, ok ? tl : 0, bnd[p], bnd[p + 1]);
+            base += tl;
         }
-        tbeg[NPIPE] = ok ? 1 : 0;
+        tbeg[MAXR] = ok ? 1 : 0;
     }
     __syncthreads();
-    if (tbeg[NPIPE] == 0 || mode == 1) return;
+    if (tbeg[MAXR] == 0 || mode == 1) return;
 
     float C[9];
 #pragma unroll
@@ -481,8 +481,9 @@ __global__ void __launch_bounds__(256, 3) edge_pack_kernel(int n_struct, const i
         }
     }
     // ---- padding groups that complete each pipeline's last tile (zero filters, harmless receiver)
-    if (tid < NPIPE * 24 && blockIdx.y == 0) {
-        const int p = tid / 24, k = tid - p * 24;
+    if (blockIdx.y == 0)
+    for (int pk = tid; pk < NR * 24; pk += 256) {
+        const int p = pk / 24, k = pk - p * 24;
         const int groups = goff[bnd[p + 1]] - goff[bnd[p]];
         const int ntile = (groups + 3) >> 2;
         const int slot = groups * GS + k;
@@ -823,7 +824,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     int n_max, const int* __restrict__ node_ptr, const uint32_t* __restrict__ Afmt /* [4 slices][4 rotations][128][32] */,
     float kappa, const int4* __restrict__ pipe_info, const uint8_t* __restrict__ tiles, float* __restrict__ scratch,
     const float* __restrict__ x, const float* __restrict__ mu_in, float* __restrict__ q, float* __restrict__ mu_out,
-    long long* dbg, const int* __restrict__ gate, int gate_value, int n_struct, int pf_ahead, int pf_eighths) {
+    long long* dbg, const int* __restrict__ gate, int gate_value, int n_struct, int pf_ahead, int pf_eighths, int n_split) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if (gate != nullptr && *gate != gate_value) return;     // uniform over the grid: layer-0 fallback not needed
     constexpr int NB = Tab<HAS_MU>::NODE_BYTES;
@@ -835,7 +836,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     StBars* S = reinterpret_cast<StBars*>(MetaS + NPIPE * NM_STAGE * META);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blockIdx.x / NSLICE, slice = blockIdx.x % NSLICE;
+    // grid = n_struct x n_split x NSLICE: CTA (g, split, slice) runs receiver ranges split * NPIPE .. + NPIPE of structure g
+    // (n_split > 1 only for batches of less than ~two waves: single-replica stepping)
+    const int g = blockIdx.x / (NSLICE * n_split), split = (blockIdx.x / NSLICE) % n_split, slice = blockIdx.x % NSLICE;
     const int node0 = __ldg(node_ptr + g), n = __ldg(node_ptr + g + 1) - node0;
 #ifdef RLVD_TIMELINE   // CTA-level stamps of block 0 and of a mid-grid block: entry | feeders released | table staged | roles done | exit
     long long* cst = dbg == nullptr ? nullptr : blockIdx.x == 0 ? dbg + 64 * 4 * 10 : blockIdx.x == 6001 ? dbg + 64 * 4 * 10 + 8 : nullptr;
@@ -1007,7 +1010,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) edge_stream_kernel(
     c.tab = TabS;
     c.MetaP = MetaS + c.pipe * NM_STAGE * META;
     c.Part = scratch + (size_t)smid * PART_SM + (size_t)c.pipe * PART_PIPE;
-    const int4 pi = __ldg(pipe_info + (size_t)g * NPIPE + c.pipe);
+    const int4 pi = __ldg(pipe_info + ((size_t)g * n_split + split) * NPIPE + c.pipe);
     c.n_tiles = pi.y;
     c.ra = pi.z;
     c.rb = pi.w;
@@ -1110,7 +1113,7 @@ void edge_stream_format(const float* W, const float* b, std::vector<uint8_t>& ou
 bool edge_stream_supported(int max_struct_nodes) { return max_struct_nodes > 0 && max_struct_nodes <= MAXN; }
 
 size_t edge_stream_tile_capacity(int n_struct, int n_nodes, int64_t n_edges) {
-    return (size_t)((n_edges / GS + n_nodes) / 4 + (int64_t)NPIPE * n_struct + 16);
+    return (size_t)((n_edges / GS + n_nodes) / 4 + (int64_t)MAXR * n_struct + 16);
 }
 
 int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_t n_edges, const int* node_ptr,
@@ -1119,17 +1122,28 @@ int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_
     if (n_struct <= 0 || M <= 0) return 0;
     const size_t cap = edge_stream_tile_capacity(n_struct, M, n_edges);
     RLVD_CHECK(cap < (size_t)0x7fffffff, "edge stream: %zu tiles overflow int32; split the batch", cap);
-    if (e->tiles.ensure(cap * TILE_BYTES) || e->pipe_info.ensure((size_t)n_struct * NPIPE * sizeof(int4)) ||
+    if (e->tiles.ensure(cap * TILE_BYTES) || e->pipe_info.ensure((size_t)n_struct * MAXR * sizeof(int4)) ||
         e->tile_ctr.ensure(16))
         return 1;
     RLVD_CUDA(cudaMemsetAsync(e->tile_ctr.p, 0, 16, s));   // tile counter | capacity error | species outside the model's list
     Span sp(e, s, FAM_PACK);
     // few structures (single-replica stepping): split each structure's receivers over several CTAs
     const int n_splits = n_struct >= 296 ? 1 : min(8, (592 + n_struct - 1) / n_struct);
+    // ... and over several CTAs of the stream kernel: with S CTAs per (structure, slice) a CTA costs ~10 k cycles of prologue plus
+    // ~154 k / S of tiles (profiles/timeline_stream_r02.txt) and the launch runs ceil(4 S n_struct / SMs) waves of them
+    int best = 1;
+    double best_cost = 0.0;
+    for (int S = 1; S <= MAX_SPLIT; ++S) {
+        const int waves = (NSLICE * S * n_struct + e->sm_count - 1) / e->sm_count;
+        const double cost = waves * (10.0 + 154.0 / S);
+        if (S == 1 || cost < 0.95 * best_cost) { best = S; best_cost = cost; }
+    }
+    e->stream_split = best;
+    const int NR = NPIPE * best;
     for (int mode = n_splits > 1 ? 1 : 0; mode <= (n_splits > 1 ? 2 : 0); ++mode)
         edge_pack_kernel<<<dim3(n_struct, mode == 2 ? n_splits : 1), 256, 0, s>>>(
             n_struct, node_ptr, row_ptr, col, shift, pos, cell, e->w.freqs, e->w.feps, e->w.cutoff, e->tile_ctr.as<int>(), (int)cap,
-            e->tiles.as<uint8_t>(), e->pipe_info.as<int4>(), e->tile_ctr.as<int>() + 1, e->status.as<int>(), Z, e->w.z2s, l0A, mode, n_splits);
+            e->tiles.as<uint8_t>(), e->pipe_info.as<int4>(), e->tile_ctr.as<int>() + 1, e->status.as<int>(), Z, e->w.z2s, l0A, mode, n_splits, NR);
     sp.end(n_splits > 1 ? 2 : 1);
     RLVD_CUDA(cudaGetLastError());
     return 0;
@@ -1152,7 +1166,8 @@ int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, 
     // both variants request the HAS_MU footprint: one CTA per SM (each CTA owns all 512 TMEM columns)
     const size_t smem = stream_smem_bytes<true>(max_struct_nodes) < 120 * 1024 ? 120 * 1024 : stream_smem_bytes<true>(max_struct_nodes);
     // structures between a CTA and the one that follows it on the same SM (grids of more than one wave only)
-    const int pf_ahead = e->stream_prefetch > 0 && n_struct * NSLICE > e->sm_count ? (e->sm_count + NSLICE - 1) / NSLICE : 0;
+    const int n_split = e->stream_split;              // chosen by launch_edge_pack for this batch
+    const int pf_ahead = e->stream_prefetch > 0 && n_split == 1 && n_struct * NSLICE > e->sm_count ? (e->sm_count + NSLICE - 1) / NSLICE : 0;
     long long* dbg = nullptr;
 #ifdef RLVD_TIMELINE   // in-kernel timeline of block 0 / pipeline 0 (build with RLVD_EXTRA_NVCC_FLAGS=-DRLVD_TIMELINE)
     static long long* dbg_buf = nullptr;
@@ -1162,11 +1177,11 @@ int launch_edge_stream(rlvd_engine* e, cudaStream_t s, int layer, int n_struct, 
 #endif
     Span sp(e, s, gate != nullptr ? -1 : FAM_EDGE);     // a gated launch is the (normally skipped) layer-0 fallback
     if (mu_in == nullptr)
-        edge_stream_kernel<false><<<n_struct * NSLICE, ST_THREADS, smem, s>>>(
-            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, nullptr, q, mu_out, nullptr, gate, gate_value, n_struct, 0, 0);
+        edge_stream_kernel<false><<<n_struct * NSLICE * n_split, ST_THREADS, smem, s>>>(
+            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, nullptr, q, mu_out, nullptr, gate, gate_value, n_struct, 0, 0, n_split);
     else
-        edge_stream_kernel<true><<<n_struct * NSLICE, ST_THREADS, smem, s>>>(
-            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, mu_in, q, mu_out, dbg, gate, gate_value, n_struct, pf_ahead, e->stream_prefetch);
+        edge_stream_kernel<true><<<n_struct * NSLICE * n_split, ST_THREADS, smem, s>>>(
+            max_struct_nodes, node_ptr, af, kappa, e->pipe_info.as<int4>(), e->tiles.as<uint8_t>(), scr, x, mu_in, q, mu_out, dbg, gate, gate_value, n_struct, pf_ahead, e->stream_prefetch, n_split);
 #ifdef RLVD_TIMELINE
     if (mu_in != nullptr && ++dbg_calls == 20) {
         cudaStreamSynchronize(s);
