@@ -46,7 +46,11 @@ __device__ __forceinline__ float head_layer(const float* __restrict__ W, const f
     return acc;
 }
 
-__global__ void __launch_bounds__(RT, 4) readout_kernel(int n_react, const int* __restrict__ node_ptr,
+// DEEP: the small-batch form (one CTA per SM at most: a single-replica call).  Its per-atom GEMM loops keep 8 k-steps of weight
+// loads in flight instead of 2 — with one tile per CTA and no other CTA on the SM the loops are a chain of L2 round trips —
+// and it may use the registers for that.  Same operations in the same order.
+template <bool DEEP>
+__global__ void __launch_bounds__(RT, DEEP ? 1 : 4) readout_kernel(int n_react, const int* __restrict__ node_ptr,
                                                      const int* __restrict__ rs, const int* __restrict__ ps,
                                                      const int* __restrict__ Z, const float* __restrict__ q,
                                                      const Weights w, const rlvd_q_params qp,
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(RT, 4) readout_kernel(int n_react, const int* 
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[r] = b0;
             const float* rows[4] = {sR + ag * QS, sR + (ag + 16) * QS, sP + ag * QS, sP + (ag + 16) * QS};
-#pragma unroll 2      // lets the next block's weight loads (L2 latency: the weights do not stay in L1) issue above this block's FMAs
+#pragma unroll (DEEP ? 8 : 2)      // lets the next block's weight loads (L2 latency: the weights do not stay in L1) issue above this block's FMAs
             for (int k = 0; k < F; k += 4) {
                 float4 wk[4];
 #pragma unroll
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(RT, 4) readout_kernel(int n_react, const int* 
             float4 acc[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[r] = b0;
-#pragma unroll 2
+#pragma unroll (DEEP ? 8 : 2)
             for (int k = 0; k < F; k += 4) {
                 float4 wk[4];
 #pragma unroll
@@ -196,6 +200,7 @@ __global__ void __launch_bounds__(RT, 4) readout_kernel(int n_react, const int* 
         {
             const int og = tid & 7, a = tid >> 3;
             float4 acc = __ldg(reinterpret_cast<const float4*>(w.rr_b3) + og);
+#pragma unroll (DEEP ? 8 : 1)
             for (int k = 0; k < F; k += 4) {
                 const float4 av = *reinterpret_cast<const float4*>(sR + a * QS + k);
                 const float a4[4] = {av.x, av.y, av.z, av.w};
@@ -388,8 +393,12 @@ int launch_readout(rlvd_engine* e, cudaStream_t s, int n_react, const int* node_
         arrived = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(e->readout_scratch.p) + cnt_off);
         RLVD_CUDA(cudaMemsetAsync(arrived, 0, 296 * sizeof(unsigned int), s));   // the kernel also re-zeroes what it used
     }
-    readout_kernel<<<dim3(n_react, n_splits), RT, readout_smem(), s>>>(n_react, node_ptr, rs, ps, Z, q, e->w, qp, d_temp, out,
-                                                                      n_splits, part, arrived);
+    if (n_react * n_splits <= e->sm_count)
+        readout_kernel<true><<<dim3(n_react, n_splits), RT, readout_smem(), s>>>(n_react, node_ptr, rs, ps, Z, q, e->w, qp, d_temp, out,
+                                                                                n_splits, part, arrived);
+    else
+        readout_kernel<false><<<dim3(n_react, n_splits), RT, readout_smem(), s>>>(n_react, node_ptr, rs, ps, Z, q, e->w, qp, d_temp, out,
+                                                                                 n_splits, part, arrived);
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
     return 0;

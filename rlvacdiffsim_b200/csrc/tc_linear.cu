@@ -155,6 +155,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
     const bool two = W2fmt != nullptr;
     float* bias2_s = bias_s + 128;                                     // [N2 <= 384] second-layer bias (two-layer mode: N == 128)
     const int NB2 = two ? a.N2 / TC_N : 0;
+    // small M (fewer tiles than SMs): gridDim.y CTAs share a tile's second-layer N-blocks, each recomputing the hidden tile
+    const int nb2_lo = two ? (int)blockIdx.y * NB2 / (int)gridDim.y : 0, nb2_hi = two ? ((int)blockIdx.y + 1) * NB2 / (int)gridDim.y : 0;
+    const int NB2c = nb2_hi - nb2_lo;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int tl_n = 0; (void)tl_n;
@@ -272,11 +275,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                 ++ph_it;
             }
             // ---- epilogue: TMEM → registers → bias/SiLU → swizzled staging → coalesced global stores
-            const int NBo = two ? NB2 : NB;
+            const int nb_first = two ? nb2_lo : 0, nb_end = two ? nb2_hi : NB;
             const float* bias_o = two ? bias2_s : bias_s;
             const int act_o = two ? a.act2 : a.act;
-            for (int nb = 0; nb < NBo; ++nb, ++acc_it) {
-                if (nb == NBo - 1 && tile + (int)gridDim.x < n_tiles) {
+            for (int nb = nb_first; nb < nb_end; ++nb, ++acc_it) {
+                if (nb == nb_end - 1 && tile + (int)gridDim.x < n_tiles) {
                     convert_phase(tile + gridDim.x, 0);
                     pre = true;
                 }
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                             bulk_g2s(Bst + s * TC_STAGE_BYTES, Wfmt + (size_t)(nb * KSN + ks) * TC_STAGE_BYTES,
                                      TC_STAGE_BYTES, &S->full[s]);
                         }
-                for (int nb = 0; nb < NB2; ++nb)                               // second layer: K = 128 hidden units
+                for (int nb = nb2_lo; nb < nb2_hi; ++nb)                       // second layer: K = 128 hidden units
                     for (int ksl = 0; ksl < 128 / TC_KS; ++ksl, ++cnt) {
                         const uint32_t s = cnt % TC_NSTAGE, ph = (cnt / TC_NSTAGE) & 1;
                         mbar_wait(&S->empty[s], ph ^ 1);
@@ -458,7 +461,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                 }
                 (void)k_first_stage;
             };
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, acc_base += NB + NB2) {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, acc_base += NB + NB2c) {
                 for (int phase = 0; phase < NPH; ++phase, ++ph_it) {
                     TCS(1, 100)
                     mbar_wait(&S->a_ready, ph_it & 1);
@@ -483,8 +486,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_linear_kernel(const LinearAr
                     mbar_wait(&S->a_ready, ph_it & 1);
                     tc_fence_after();
                     TCS(1, 131)
-                    for (int nb = 0; nb < NB2; ++nb) {
-                        const uint32_t acc_it = acc_base + NB + nb, buf = acc_it & 1;
+                    for (int nb = nb2_lo; nb < nb2_hi; ++nb) {
+                        const uint32_t acc_it = acc_base + NB + (nb - nb2_lo), buf = acc_it & 1;
                         mbar_wait(&S->acc_empty[buf], ((acc_it >> 1) & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t d0 = tmem + buf * 256, d1 = d0 + 128;
@@ -575,7 +578,9 @@ int launch_tc_linear(rlvd_engine* e, cudaStream_t s, const LinearArgs& a_in, con
     if (dump) { cudaMemsetAsync(dbg_buf, 0, 2048 * 8, s); a.dbg = dbg_buf; }
 #endif
     Span sp(e, s, FAM_NODE);
-    tc_linear_kernel<<<grid, TC_THREADS, tc_smem_bytes(a.K), s>>>(a, reinterpret_cast<const uint8_t*>(Wfmt),
+    // two-layer launches with fewer tiles than half the SMs (single-replica stepping): split the second layer's N-blocks over CTAs
+    const int gy = a.W2fmt != nullptr ? std::max(1, std::min(a.N2 / TC_N, e->sm_count / grid)) : 1;
+    tc_linear_kernel<<<dim3(grid, gy), TC_THREADS, tc_smem_bytes(a.K), s>>>(a, reinterpret_cast<const uint8_t*>(Wfmt),
                                                                   reinterpret_cast<const uint8_t*>(a.W2fmt));
     sp.end(1);
     RLVD_CUDA(cudaGetLastError());
