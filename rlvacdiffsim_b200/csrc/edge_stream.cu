@@ -1128,7 +1128,7 @@ int launch_edge_pack(rlvd_engine* e, cudaStream_t s, int n_struct, int M, int64_
     RLVD_CUDA(cudaMemsetAsync(e->tile_ctr.p, 0, 16, s));   // tile counter | capacity error | species outside the model's list
     Span sp(e, s, FAM_PACK);
     // few structures (single-replica stepping): split each structure's receivers over several CTAs
-    const int n_splits = n_struct >= 296 ? 1 : min(8, (592 + n_struct - 1) / n_struct);
+    const int n_splits = n_struct >= 296 ? 1 : min(16, (592 + n_struct - 1) / n_struct);
     // ... and over several CTAs of the stream kernel: with S CTAs per (structure, slice) a CTA costs ~10 k cycles of prologue plus
     // ~154 k / S of tiles (profiles/timeline_stream_r02.txt) and the launch runs ceil(4 S n_struct / SMs) waves of them
     int best = 1;
