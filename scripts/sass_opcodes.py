@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "rlvacdiffsim_b200", "librlvd_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-WATCH = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UBLKPF", "SYNCS", "FFMA2", "FMUL2", "HMMA", "LDGSTS", "BAR.SYNC", "NANOSLEEP")
+WATCH = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UBLKPF", "SYNCS", "FFMA2", "FMUL2", "IDP", "HMMA", "LDGSTS", "BAR.SYNC", "NANOSLEEP")
 kern, hist = None, collections.OrderedDict()
 for ln in out.splitlines():
     m = re.search(r"Function : (\S+)", ln)
