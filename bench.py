@@ -447,6 +447,14 @@ def run_other_config(args, model, eng, dev, rank, world, local):
     return 0
 
 
+def _edge_ncu_note():
+    """What one committed `ncu --set full` capture of the dominant kernel says about its shared-memory pipe (profiles/ncu_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("edge_stream_ncu")
+    except (OSError, ValueError):
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -842,7 +850,8 @@ def main():
                                   "achieved": smem_achieved, "peak": smem_peak, "unit": "GB/s",
                                   "frac": smem_achieved / smem_peak if smem_peak else None,
                                   "gather_bytes_per_launch": smem_bytes,
-                                  "peak_source": "128 B/clk/SM x SMs x sampled SM clock"}},
+                                  "peak_source": "128 B/clk/SM x SMs x sampled SM clock",
+                                  "ncu": _edge_ncu_note()}},
             "dram_by_family": dram_by_family,
             "dedup": dedup_obj,
             "single_replica": {"what": "one 255-atom replica, 12 candidate hops per call (24 structures), device-resident inputs, "
